@@ -1,0 +1,190 @@
+"""Deterministic synthetic stereo tracks in the shapes BASELINE.json names.
+
+Intrinsics are the ones the reference's camera_test.cpp:11-15 uses; the base seed 42 is the seed
+the reference hard-codes for RANSAC (point_cloud_aligner.cpp:72).  Poses are stored the way the
+reference stores them: 12 doubles [t | R row-major] of T_c_g (se3group.hpp:115-118), so that
+p_c = R p_g + t.  Observations come out grouped by pose index like the reference's CSV rows
+(dataset_problem.cpp:71-98).
+"""
+import numpy as np
+
+KITTI = dict(fu=707.0912, fv=707.0912, cu=601.8873, cv=183.1104, b=0.535105804)
+IMG_W, IMG_H = 1242.0, 375.0
+
+
+def so3_exp(phi):
+    """Rodrigues, vectorised over rows of phi (n,3) -> (n,3,3)."""
+    phi = np.atleast_2d(phi)
+    ang = np.linalg.norm(phi, axis=1)
+    small = ang < 1e-12
+    axis = phi / np.where(small, 1.0, ang)[:, None]
+    K = np.zeros((phi.shape[0], 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -axis[:, 2], axis[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = axis[:, 2], -axis[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -axis[:, 1], axis[:, 0]
+    c, s = np.cos(ang)[:, None, None], np.sin(ang)[:, None, None]
+    R = c * np.eye(3) + (1 - c) * axis[:, :, None] * axis[:, None, :] + s * K
+    R[small] = np.eye(3)
+    return R
+
+
+def pose_pack(R, t):
+    return np.concatenate([t, R.reshape(-1, 9)], axis=1)
+
+
+def pose_R(p):
+    return p[:, 3:].reshape(-1, 3, 3)
+
+
+def pose_t(p):
+    return p[:, :3]
+
+
+def perturb_poses(poses, eps):
+    """Left-multiplicative decoupled update T <- exp(eps) T (perturbations.hpp:62)."""
+    E = so3_exp(eps[:, 3:])
+    R = E @ pose_R(poses)
+    t = np.einsum("nij,nj->ni", E, pose_t(poses)) + eps[:, :3]
+    return pose_pack(R, t)
+
+
+def loop_poses(n_poses, spacing=0.3, min_radius=10.0):
+    """Closed planar loop, camera looking along the tangent (z forward, x outward, y down)."""
+    radius = max(min_radius, n_poses * spacing / (2 * np.pi))
+    th = 2 * np.pi * np.arange(n_poses) / n_poses
+    c = np.stack([radius * np.cos(th), radius * np.sin(th), np.zeros_like(th)], axis=1)
+    x = np.stack([np.cos(th), np.sin(th), np.zeros_like(th)], axis=1)
+    y = np.tile(np.array([0.0, 0.0, -1.0]), (n_poses, 1))
+    z = np.stack([-np.sin(th), np.cos(th), np.zeros_like(th)], axis=1)
+    R = np.stack([x, y, z], axis=1)
+    t = -np.einsum("nij,nj->ni", R, c)
+    return pose_pack(R, t)
+
+
+def project(cam, pc):
+    iz = 1.0 / pc[:, 2]
+    return np.stack([cam["fu"] * pc[:, 0] * iz + cam["cu"], cam["fv"] * pc[:, 1] * iz + cam["cv"],
+                     cam["fu"] * cam["b"] * iz], axis=1)
+
+
+def make_track(n_poses, new_per_frame, track_len, seed=42, pix_sigma=1.0, pose_sigma=(0.02, 0.01),
+               point_sigma=0.05, spacing=0.3, per_obs_W=False, cam=None):
+    """A sims-style stereo track.
+
+    Every frame sees `new_per_frame` new landmarks, each tracked over `track_len` consecutive
+    poses, i.e. about new_per_frame * track_len observations per frame in steady state
+    (C1/C2: 15 x 10; C5: 100 x 10 -> 20 k poses, 2 M landmarks, 20 M observations).
+    """
+    cam = dict(cam or KITTI)
+    rng = np.random.default_rng(seed)
+    poses_gt = loop_poses(n_poses, spacing)
+    n_starts = n_poses - track_len + 1
+    n_pts = n_starts * new_per_frame
+    first = np.repeat(np.arange(n_starts, dtype=np.int64), new_per_frame)
+    # place each landmark in the frustum of the middle pose of its track
+    mid = first + track_len // 2
+    u = rng.uniform(150.0, IMG_W - 150.0, n_pts)
+    v = rng.uniform(60.0, IMG_H - 60.0, n_pts)
+    z = rng.uniform(4.0, 30.0, n_pts)
+    pc = np.stack([(u - cam["cu"]) * z / cam["fu"], (v - cam["cv"]) * z / cam["fv"], z], axis=1)
+    Rm, tm = pose_R(poses_gt)[mid], pose_t(poses_gt)[mid]
+    points_gt = np.einsum("nji,nj->ni", Rm, pc - tm)  # R^T (p_c - t)
+    # observations, pose-major
+    k = (first[:, None] + np.arange(track_len)[None, :]).reshape(-1)
+    j = np.repeat(np.arange(n_pts, dtype=np.int64), track_len)
+    order = np.argsort(k, kind="stable")
+    k, j = k[order], j[order]
+    pck = np.einsum("nij,nj->ni", pose_R(poses_gt)[k], points_gt[j]) + pose_t(poses_gt)[k]
+    uvd = project(cam, pck)
+    ok = (pck[:, 2] > 0.5) & (uvd[:, 0] > 0) & (uvd[:, 0] < IMG_W) & (uvd[:, 1] > 0) & \
+         (uvd[:, 1] < IMG_H) & (uvd[:, 2] > 1.0)
+    k, j, uvd = k[ok], j[ok], uvd[ok]
+    uvd = uvd + rng.normal(0.0, pix_sigma, uvd.shape)
+    # initial guess: ground truth perturbed, first pose held at ground truth (gauge)
+    eps = np.concatenate([rng.normal(0, pose_sigma[0], (n_poses, 3)),
+                          rng.normal(0, pose_sigma[1], (n_poses, 3))], axis=1)
+    eps[0] = 0.0
+    poses_init = perturb_poses(poses_gt, eps)
+    points_init = points_gt + rng.normal(0, point_sigma, points_gt.shape)
+    if per_obs_W:
+        # SPD covariance near diag(sigma^2) per observation -> symmetric inverse square root
+        A = rng.normal(0, 0.15, (uvd.shape[0], 3, 3))
+        cov = pix_sigma ** 2 * np.eye(3) + 0.5 * (A + A.transpose(0, 2, 1)) * pix_sigma ** 2 * 0.3
+        w, V = np.linalg.eigh(cov)
+        W = np.einsum("nij,nj,nkj->nik", V, 1.0 / np.sqrt(w), V).reshape(-1, 9)
+    else:
+        W = (np.eye(3) / pix_sigma).reshape(9)
+    constant = np.zeros(n_poses, dtype=np.uint8)
+    constant[0] = 1
+    return dict(cam=cam, poses_gt=poses_gt, poses=poses_init, points_gt=points_gt,
+                points=points_init, obs_cam=k.astype(np.uint32), obs_pt=j.astype(np.uint32),
+                uvd=np.ascontiguousarray(uvd), W=np.ascontiguousarray(W), constant=constant,
+                n_poses=n_poses, n_points=n_pts)
+
+
+def add_sun(track, seed=43, sigma_deg=2.0):
+    """Ephemeris direction fixed in the global frame, observed direction = R e_g + noise
+    (dataset_problem_sun.cpp:139-175 file shapes)."""
+    rng = np.random.default_rng(seed)
+    n = track["n_poses"]
+    e_g = np.array([0.3, -0.5, 0.81])
+    e_g = e_g / np.linalg.norm(e_g)
+    R = pose_R(track["poses_gt"])
+    obs = np.einsum("nij,j->ni", R, e_g)
+    noise = so3_exp(rng.normal(0, np.deg2rad(sigma_deg), (n, 3)))
+    obs = np.einsum("nij,nj->ni", noise, obs)
+    W2 = np.tile((np.eye(2) / np.deg2rad(sigma_deg)).reshape(4), (n, 1))
+    track["sun_cam"] = np.arange(n, dtype=np.uint32)
+    track["sun_obs_c"] = np.ascontiguousarray(obs)
+    track["sun_ref_g"] = np.tile(e_g, (n, 1))
+    track["sun_W"] = W2
+    return track
+
+
+def window_of(track, k1, k2):
+    """The sub-problem `solveWindow(dataset, k1, k2)` builds (dataset_vo.cpp:40-62): observations
+    of poses k1..k2-1, restricted to points seen by at least two poses of the window (the
+    reference only optimises points its two-frame RANSAC initialised), re-indexed compactly."""
+    sel = (track["obs_cam"] >= k1) & (track["obs_cam"] < k2)
+    cam = track["obs_cam"][sel].astype(np.int64) - k1
+    pt = track["obs_pt"][sel].astype(np.int64)
+    uvd = track["uvd"][sel]
+    W = track["W"] if track["W"].size == 9 else track["W"][sel]
+    cnt = np.bincount(pt, minlength=track["n_points"])
+    keep = cnt[pt] >= 2
+    cam, pt, uvd = cam[keep], pt[keep], uvd[keep]
+    if W.size != 9:
+        W = W[keep]
+    ids, pt_local = np.unique(pt, return_inverse=True)
+    constant = np.zeros(k2 - k1, dtype=np.uint8)
+    constant[0] = 1
+    out = dict(cam=track["cam"], poses=track["poses"][k1:k2].copy(), poses_gt=track["poses_gt"][k1:k2],
+               points=track["points"][ids].copy(), points_gt=track["points_gt"][ids],
+               obs_cam=cam.astype(np.uint32), obs_pt=pt_local.astype(np.uint32),
+               uvd=np.ascontiguousarray(uvd), W=np.ascontiguousarray(W), constant=constant,
+               n_poses=k2 - k1, n_points=ids.size, k1=k1)
+    if "sun_cam" in track:
+        out["sun_cam"] = np.arange(k2 - k1, dtype=np.uint32)
+        out["sun_obs_c"] = track["sun_obs_c"][k1:k2].copy()
+        out["sun_ref_g"] = track["sun_ref_g"][k1:k2].copy()
+        out["sun_W"] = track["sun_W"][k1:k2].copy()
+    return out
+
+
+def build_problem(track, backend="b200", sun=False, prior=None, huber=0.0, hold_first=True, **options):
+    """Assemble the problem the way the reference drivers do (dataset_vo.cpp:40-62 /
+    dataset_vo_sun.cpp:49-129).  Returns (BAProblem, poses array, points array)."""
+    from .problem import BAProblem
+    p = BAProblem(backend, **options)
+    c = track["cam"]
+    p.set_camera(c["fu"], c["fv"], c["cu"], c["cv"], c["b"])
+    const = track["constant"] if hold_first else np.zeros(track["n_poses"], dtype=np.uint8)
+    poses = p.set_poses(track["poses"].copy(), const)
+    points = p.set_points(track["points"].copy())
+    p.add_stereo(track["obs_cam"], track["obs_pt"], track["uvd"], track["W"])
+    if sun:
+        p.add_sun(track["sun_cam"], track["sun_obs_c"], track["sun_ref_g"], track["sun_W"], huber=huber)
+    if prior is not None:
+        cam, Tref, W6 = prior
+        p.add_pose_prior(cam, Tref, W6)
+    return p, poses, points

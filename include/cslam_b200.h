@@ -1,0 +1,204 @@
+/*
+ * cslam_b200 — C ABI of the B200-native bundle-adjustment back end for ceres-slam's hot path.
+ *
+ * The reference (utiasSTARS/ceres-slam) has no FFI: its seam is the ceres::Problem built inside
+ * `solveWindow` and the `ceres::Solve` call that follows (tests/dataset_vo.cpp:22-85,
+ * tests/dataset_vo_sun.cpp:25-187, tests/dataset_ba_phong.cpp:26-255).  Every entry point below
+ * replaces one group of Ceres calls at that seam; the citation names the reference lines.
+ * Plain pointers and sizes only.  All arrays are caller-owned; parameter arrays (poses, points)
+ * are updated IN PLACE by cslam_solve, exactly like Ceres writes into `dataset.poses[k].data()`.
+ * No function throws; each returns a status and leaves a message for cslam_last_error().
+ * A handle is single-threaded; distinct handles may be used from distinct threads.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * CSLAM_ERR_CUDA.
+ */
+#ifndef CSLAM_B200_H_
+#define CSLAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cslam_problem cslam_problem;
+
+typedef enum cslam_status {
+    CSLAM_OK = 0,
+    CSLAM_ERR_INVALID = 1,   /* bad argument / index out of range / call order */
+    CSLAM_ERR_CUDA = 2,      /* CUDA runtime error or no device */
+    CSLAM_ERR_NOT_IMPL = 3,
+    CSLAM_ERR_NUMERIC = 4,   /* non-finite cost at the initial point */
+    CSLAM_ERR_COMM = 5       /* NCCL failure */
+} cslam_status;
+
+/* Mirrors the ceres::Solver::Options fields the drivers set (dataset_vo.cpp:65-74) plus the
+ * Ceres 1.x defaults the LM loop depends on. */
+typedef struct cslam_options {
+    int max_num_iterations;                 /* 1000  dataset_vo.cpp:69 */
+    int use_nonmonotonic_steps;             /* 1     dataset_vo.cpp:70 */
+    int max_consecutive_nonmonotonic_steps; /* 5 */
+    double initial_trust_region_radius;     /* 1e4 */
+    double max_trust_region_radius;         /* 1e16 */
+    double min_trust_region_radius;         /* 1e-32 */
+    double min_relative_decrease;           /* 1e-3 */
+    double min_lm_diagonal;                 /* 1e-6 */
+    double max_lm_diagonal;                 /* 1e32 */
+    int max_num_consecutive_invalid_steps;  /* 5 */
+    double function_tolerance;              /* 1e-6 */
+    double gradient_tolerance;              /* 1e-10 */
+    double parameter_tolerance;             /* 1e-8 */
+    int jacobi_scaling;                     /* 1 */
+    int linear_solver;      /* 0 = exact Schur solve (SPARSE_SCHUR-equivalent: PCG run to 1e-14 or
+                               in-kernel Cholesky), 1 = ITERATIVE_SCHUR (PCG, Ceres Q-rule, eta) */
+    int preconditioner;     /* 0 = JACOBI (block diag of B), 1 = SCHUR_JACOBI (block diag of S) */
+    double eta;                             /* 0.1 */
+    int max_linear_solver_iterations;       /* 500 */
+    int min_linear_solver_iterations;       /* 0 */
+    int num_threads;        /* ignored by the GPU back end (dataset_vo.cpp:67); used by the oracle */
+    int device;             /* CUDA device ordinal */
+    int profile_kernels;    /* 1 = bracket every kernel class with CUDA events (cslam_get_profile) */
+    int schur_path;         /* 0 = auto, 1 = force generic per-landmark kernel, 2 = force grouped */
+} cslam_options;
+
+typedef struct cslam_summary {
+    double initial_cost;
+    double final_cost;
+    int num_iterations;            /* LM iterations attempted (successful + unsuccessful) */
+    int num_successful_steps;
+    int num_unsuccessful_steps;
+    int termination_type;          /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE */
+    int termination_reason;        /* 1 gradient tol, 2 parameter tol, 3 function tol,
+                                      4 max iterations, 5 min radius, 6 invalid steps,
+                                      7 linear solver, 8 evaluation failed */
+    double final_radius;
+    int total_linear_iterations;
+    double device_ms;              /* CUDA-event time of the LM loop on the problem's stream */
+} cslam_summary;
+
+/* One row per LM iteration (row 0 = initial point), 10 doubles each:
+ * iteration, cost, cost_change, gradient_max_norm, step_norm, relative_decrease, radius,
+ * linear_iterations, step_is_valid, step_is_successful.  Same columns Ceres prints with
+ * minimizer_progress_to_stdout (dataset_vo.cpp:66). */
+#define CSLAM_LOG_COLS 10
+
+/* Accumulated CUDA-event times per kernel class since the last cslam_reset_profile(). */
+typedef struct cslam_profile {
+    double ms[16];
+    int launches[16];
+} cslam_profile;
+enum {
+    CSLAM_K_RESJAC = 0,      /* materialised residual + Jacobian (cslam_evaluate) */
+    CSLAM_K_COLNORM = 1,     /* column norms + gradient (Jacobi scaling, LM diagonal) */
+    CSLAM_K_SCHUR = 2,       /* fused residual/Jacobian + Schur elimination */
+    CSLAM_K_FINALIZE = 3,    /* LM diagonal on S, block-Jacobi inverse */
+    CSLAM_K_PCG = 4,         /* all PCG kernels */
+    CSLAM_K_BACKSUB = 5,     /* back-substitution + Plus + model/candidate cost */
+    CSLAM_K_ALLREDUCE = 6,   /* NCCL all-reduce of [S | g] */
+    CSLAM_K_WINDOW = 7,      /* batched sliding-window LM kernel */
+    CSLAM_K_OTHER = 8
+};
+
+void cslam_options_init(cslam_options* opt);
+
+/* ceres::Problem problem;  (dataset_vo.cpp:26) */
+cslam_status cslam_problem_create(cslam_problem** out, const cslam_options* opt);
+void cslam_problem_destroy(cslam_problem* p);
+const char* cslam_last_error(const cslam_problem* p);
+cslam_status cslam_set_options(cslam_problem* p, const cslam_options* opt);
+
+/* StereoCamera(fu, fv, cu, cv, b)  (stereo_camera.hpp:159-163, dataset_problem.cpp:42-48) */
+cslam_status cslam_set_camera(cslam_problem* p, double fu, double fv, double cu, double cv, double b);
+
+/* Pose parameter blocks: n x 12 doubles [t | R row-major] (se3group.hpp:115-118), all with
+ * SE3Perturbation (dataset_vo.cpp:58); constant[k] != 0 == SetParameterBlockConstant
+ * (dataset_vo.cpp:62).  In-out. `constant` may be NULL. */
+cslam_status cslam_set_poses(cslam_problem* p, uint32_t n, double* poses12, const uint8_t* constant);
+
+/* Map point parameter blocks: n x 3 doubles (dataset_vo.cpp:52-53).  In-out. */
+cslam_status cslam_set_points(cslam_problem* p, uint32_t n, double* xyz);
+
+/* n StereoReprojectionErrorAutomatic blocks (dataset_vo.cpp:46-53): cam[i], pt[i], uvd[3i..],
+ * stiffness W row-major 3x3: 9 doubles shared (dataset_vo.cpp:29-32) or 9 per observation when
+ * W_per_obs != 0 (dataset_vo_sun.cpp:57-59).  Replaces earlier stereo blocks. */
+cslam_status cslam_add_stereo(cslam_problem* p, uint64_t n, const uint32_t* cam, const uint32_t* pt,
+                              const double* uvd, const double* W, int W_per_obs);
+
+/* n SunSensorErrorAutomatic blocks (dataset_vo_sun.cpp:75-101): observed direction (camera
+ * frame) and ephemeris direction (global frame), 3 doubles each, normalised by the callee like
+ * the functor's constructor (sun_sensor_error.hpp:30-31); W2x2 row-major per block; thresholds
+ * in radians; huber <= 0 means no loss (dataset_vo_sun.cpp:89-99). */
+cslam_status cslam_add_sun(cslam_problem* p, uint32_t n, const uint32_t* cam, const double* obs_c,
+                           const double* ref_g, const double* W2x2, double az_thresh,
+                           double zen_thresh, double huber);
+
+/* One PoseErrorAutomatic block (dataset_vo_sun.cpp:109-124). */
+cslam_status cslam_add_pose_prior(cslam_problem* p, uint32_t cam, const double* Tref12,
+                                  const double* W6x6);
+
+/* ceres::Problem::Evaluate at the current parameter values: cost and, per residual block, the
+ * residuals and the Jacobians in tangent coordinates (ambient Jacobian times the Plus Jacobian).
+ * Outputs are in the caller's block order; any pointer may be NULL.
+ *   r_stereo 3n, Jpose_stereo 18n (3x6 row-major), Jpoint_stereo 9n (3x3 row-major)
+ *   r_sun 2m, J_sun 12m (2x6), r_prior 6q, J_prior 36q (6x6)
+ * Loss-corrected like Ceres when apply_loss != 0. */
+cslam_status cslam_evaluate(cslam_problem* p, int apply_loss, double* cost, double* r_stereo,
+                            double* Jpose_stereo, double* Jpoint_stereo, double* r_sun,
+                            double* J_sun, double* r_prior, double* J_prior);
+
+/* ceres::Solve (dataset_vo.cpp:81): uploads the problem, runs the LM loop on the device, writes
+ * the best parameters back into the caller's pose / point arrays. */
+cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary);
+
+/* The same, split so a caller can keep the problem resident in HBM:
+ *   upload   : host arrays -> device, structure analysis (landmark-major order, tiles, S pattern)
+ *   lm_begin : evaluate at the initial point, set up the trust-region state
+ *   lm_iterate: run up to n LM iterations (stops early on convergence unless
+ *               ignore_convergence != 0); may be called repeatedly
+ *   download : best parameters -> host arrays
+ *   reset_state: restore the uploaded initial parameter values on the device */
+cslam_status cslam_upload(cslam_problem* p);
+cslam_status cslam_lm_begin(cslam_problem* p);
+cslam_status cslam_lm_iterate(cslam_problem* p, int n, int ignore_convergence, cslam_summary* summary);
+cslam_status cslam_download(cslam_problem* p);
+cslam_status cslam_reset_state(cslam_problem* p);
+
+/* Config 4 (scripts/ba_all_*.sh: many independent tracks): solve n independent small problems
+ * in one launch per GPU.  Each problem must already hold its data. */
+cslam_status cslam_solve_batch(cslam_problem** problems, int n, cslam_summary* summaries);
+
+/* Iteration log of the last solve: up to max_rows rows of CSLAM_LOG_COLS doubles; returns the
+ * number of rows available in *n_rows. */
+cslam_status cslam_get_iteration_log(const cslam_problem* p, double* rows, int max_rows, int* n_rows);
+
+/* Reduced camera system of the last Schur build (diagnostics / parity): sizes first, then data.
+ * S is returned as upper block-CSR with 6x6 row-major blocks; rhs is 6 per free camera. */
+cslam_status cslam_get_reduced_sizes(const cslam_problem* p, int* n_free_cams, int* nnz_blocks);
+cslam_status cslam_get_reduced_system(const cslam_problem* p, int* rowptr, int* col, double* values,
+                                      double* rhs, int* free_cam_ids);
+
+/* Kernel-class timings (CUDA events on the problem's stream). */
+cslam_status cslam_get_profile(const cslam_problem* p, cslam_profile* out);
+cslam_status cslam_reset_profile(cslam_problem* p);
+
+/* Run the problem's work on a caller-owned stream (cudaStream_t passed as void*). */
+cslam_status cslam_set_stream(cslam_problem* p, void* cuda_stream);
+
+/* Time the materialised residual+Jacobian kernel on device-resident data: `reps` launches,
+ * average milliseconds per launch from CUDA events. */
+cslam_status cslam_time_resjac(cslam_problem* p, int reps, double* ms_per_launch);
+/* Time `reps` launches of the fused Schur-build kernel at the current state. */
+cslam_status cslam_time_schur(cslam_problem* p, int reps, double* ms_per_launch);
+/* FP64 FMA microbenchmark (register-resident DFMA chains on every SM): TFLOP/s. */
+cslam_status cslam_measure_fp64_peak(int device, double* tflops);
+
+/* Multi-GPU (config 5): every rank holds all poses and its own shard of landmarks and
+ * observations; each Schur build is followed by one all-reduce of [S | rhs | scalars].
+ * The 128-byte id comes from rank 0 and is distributed by the launcher (torch.distributed). */
+cslam_status cslam_comm_unique_id(uint8_t id[128]);
+cslam_status cslam_attach_comm(cslam_problem* p, int n_ranks, int rank, const uint8_t id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSLAM_B200_H_ */
