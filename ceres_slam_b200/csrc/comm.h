@@ -1,0 +1,14 @@
+// NCCL plumbing for the multi-GPU reduction of the partial reduced camera systems.
+// libnccl is loaded at run time (dlopen) so a single-GPU process never needs it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace cslam {
+void comm_unique_id(uint8_t id[128]);
+void* comm_create(int n_ranks, int rank, const uint8_t id[128]);
+void comm_destroy(void* comm);
+void comm_allreduce_sum(void* comm, double* buf, size_t count, cudaStream_t s);
+void comm_allreduce_max(void* comm, double* buf, size_t count, cudaStream_t s);
+}  // namespace cslam

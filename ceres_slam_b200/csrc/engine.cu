@@ -1,0 +1,834 @@
+// Host side of the cslam_b200 back end: structure analysis, device residency, and the
+// Levenberg-Marquardt loop that drives the kernels (Ceres trust-region semantics, SURVEY.md
+// App. B; the same rules the oracle restates in oracle/problem.hpp::solve).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <thread>
+
+#include "comm.h"
+#include "kernels.cuh"
+
+namespace cslam {
+
+Engine::Engine(const cslam_options& o) : opt(o) {}
+
+Engine::~Engine() {
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (ev_c) cudaEventDestroy(ev_c);
+    if (ev_d) cudaEventDestroy(ev_d);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    if (nccl_comm) comm_destroy(nccl_comm);
+}
+
+void Engine::set_stream(cudaStream_t s) {
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    stream = s;
+    own_stream = false;
+}
+
+static void ensure_device(Engine* e, cudaStream_t* stream, bool* own, cudaEvent_t* a, cudaEvent_t* b, cudaEvent_t* c,
+                          cudaEvent_t* d, double** pinned) {
+    int count = 0;
+    cudaError_t st = cudaGetDeviceCount(&count);
+    if (st != cudaSuccess || count == 0)
+        throw CudaError("no CUDA device: the cslam_b200 back end has no CPU fallback");
+    CSLAM_CUDA(cudaSetDevice(e->opt.device));
+    if (!*stream) {
+        CSLAM_CUDA(cudaStreamCreateWithFlags(stream, cudaStreamNonBlocking));
+        *own = true;
+    }
+    if (!*a) {
+        CSLAM_CUDA(cudaEventCreate(a));
+        CSLAM_CUDA(cudaEventCreate(b));
+        CSLAM_CUDA(cudaEventCreate(c));
+        CSLAM_CUDA(cudaEventCreate(d));
+    }
+    if (!*pinned) CSLAM_CUDA(cudaMallocHost(pinned, 64 * sizeof(double)));
+}
+
+void Engine::prof_begin(int) {
+    if (opt.profile_kernels) CSLAM_CUDA(cudaEventRecord(ev_c, stream));
+}
+void Engine::prof_end(int k) {
+    if (!opt.profile_kernels) return;
+    CSLAM_CUDA(cudaEventRecord(ev_d, stream));
+    CSLAM_CUDA(cudaEventSynchronize(ev_d));
+    float ms = 0;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, ev_c, ev_d));
+    prof.ms[k] += ms;
+    prof.launches[k] += 1;
+}
+
+void Engine::read_scalars(const double* dev, double* host, int n) {
+    CSLAM_CUDA(cudaMemcpyAsync(h_pinned, dev, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(host, h_pinned, n * sizeof(double));
+}
+
+DevView Engine::view(const double* poses, const double* points) const {
+    DevView v;
+    v.cam = cam;
+    v.n_cams = int(n_poses);
+    v.n_free = n_free;
+    v.n_lm = n_lm;
+    v.n_obs = n_obs;
+    v.poses = poses;
+    v.points = points;
+    v.cam_free = d_cam_free.p;
+    v.lm_ptr = d_lm_ptr.p;
+    v.obs_cam = d_obs_cam.p;
+    v.obs_u = d_obs_u.p;
+    v.obs_v = d_obs_v.p;
+    v.obs_d = d_obs_d.p;
+    v.obs_W = d_obs_W.p;
+    v.W_per_obs = st_W_per_obs;
+    v.sc_p = d_sc_p.p;
+    v.sc_l = d_sc_l.p;
+    v.s_rowptr = d_s_rowptr.p;
+    v.s_col = d_s_col.p;
+    return v;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Structure analysis: which blocks exist (dataset_vo.cpp:40-62), landmark-major order, the
+// co-visibility pattern of the reduced camera system, and this rank's landmark shard.
+// -------------------------------------------------------------------------------------------------
+void Engine::build_structure() {
+    if (!h_poses || n_poses == 0) throw std::invalid_argument("poses not set");
+    if (n_st > 0 && (!h_points || n_points == 0)) throw std::invalid_argument("points not set");
+    if (n_st >= (1ull << 32)) throw std::invalid_argument("more than 2^32 stereo blocks");
+    std::vector<uint8_t> used(n_poses, 0);
+    std::vector<uint32_t> cnt(n_points, 0), mincam(n_points, 0xffffffffu);
+    for (uint64_t i = 0; i < n_st; ++i) {
+        const uint32_t c = st_cam[i], j = st_pt[i];
+        if (c >= n_poses || j >= n_points) throw std::invalid_argument("stereo block index out of range");
+        used[c] = 1;
+        cnt[j]++;
+        if (c < mincam[j]) mincam[j] = c;
+    }
+    for (auto& s : suns) {
+        if (s.cam >= n_poses) throw std::invalid_argument("sun block index out of range");
+        used[s.cam] = 1;
+    }
+    for (auto& p : priors) {
+        if (p.cam >= n_poses) throw std::invalid_argument("prior block index out of range");
+        used[p.cam] = 1;
+    }
+    cam_free_h.assign(n_poses, -1);
+    free_cams_h.clear();
+    for (uint32_t k = 0; k < n_poses; ++k)
+        if (used[k] && !pose_const[k]) {
+            cam_free_h[k] = int(free_cams_h.size());
+            free_cams_h.push_back(int(k));
+        }
+    n_free = int(free_cams_h.size());
+
+    // landmarks in order of the first camera that sees them (counting sort, stable in user id)
+    std::vector<uint32_t> bucket(n_poses + 1, 0);
+    uint32_t n_active = 0;
+    for (uint32_t j = 0; j < n_points; ++j)
+        if (cnt[j]) {
+            bucket[mincam[j] + 1]++;
+            n_active++;
+        }
+    for (uint32_t k = 0; k < n_poses; ++k) bucket[k + 1] += bucket[k];
+    std::vector<uint32_t> all_lm(n_active);
+    std::vector<uint32_t> inv(n_points, 0xffffffffu);
+    for (uint32_t j = 0; j < n_points; ++j)
+        if (cnt[j]) {
+            const uint32_t pos = bucket[mincam[j]]++;
+            all_lm[pos] = j;
+            inv[j] = pos;
+        }
+    std::vector<uint32_t> all_ptr(size_t(n_active) + 1, 0);
+    for (uint32_t a = 0; a < n_active; ++a) all_ptr[a + 1] = all_ptr[a] + cnt[all_lm[a]];
+    std::vector<uint32_t> all_obs(n_st);
+    {
+        std::vector<uint32_t> fill(all_ptr.begin(), all_ptr.end() - 1);
+        for (uint64_t i = 0; i < n_st; ++i) all_obs[fill[inv[st_pt[i]]]++] = uint32_t(i);
+    }
+
+    // ---- reduced camera system pattern (global: every rank derives the same one) ----
+    {
+        // camera -> landmarks adjacency
+        std::vector<uint32_t> cptr(size_t(n_free) + 1, 0);
+        for (uint64_t i = 0; i < n_st; ++i) {
+            const int f = cam_free_h[st_cam[i]];
+            if (f >= 0) cptr[f + 1]++;
+        }
+        for (int f = 0; f < n_free; ++f) cptr[f + 1] += cptr[f];
+        std::vector<uint32_t> clm(cptr[n_free]);
+        {
+            std::vector<uint32_t> fill(cptr.begin(), cptr.end() - 1);
+            for (uint64_t i = 0; i < n_st; ++i) {
+                const int f = cam_free_h[st_cam[i]];
+                if (f >= 0) clm[fill[f]++] = inv[st_pt[i]];
+            }
+        }
+        std::vector<std::vector<int>> rows(n_free);
+        const int nt = int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        auto work = [&](int t) {
+            std::vector<int> stamp(n_free, -1);
+            for (int a = t; a < n_free; a += nt) {
+                std::vector<int>& row = rows[a];
+                row.push_back(a);
+                stamp[a] = a;
+                for (uint32_t x = cptr[a]; x < cptr[a + 1]; ++x) {
+                    const uint32_t lmk = clm[x];
+                    for (uint32_t e = all_ptr[lmk]; e < all_ptr[lmk + 1]; ++e) {
+                        const int b = cam_free_h[st_cam[all_obs[e]]];
+                        if (b > a && stamp[b] != a) {
+                            stamp[b] = a;
+                            row.push_back(b);
+                        }
+                    }
+                }
+                std::sort(row.begin(), row.end());
+            }
+        };
+        if (n_free < 64 || nt == 1) {
+            for (int t = 0; t < nt; ++t) work(t);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+        }
+        s_rowptr_h.assign(size_t(n_free) + 1, 0);
+        for (int a = 0; a < n_free; ++a) s_rowptr_h[a + 1] = s_rowptr_h[a] + int(rows[a].size());
+        s_col_h.clear();
+        s_col_h.reserve(s_rowptr_h[n_free]);
+        for (int a = 0; a < n_free; ++a) s_col_h.insert(s_col_h.end(), rows[a].begin(), rows[a].end());
+        nnzU = int(s_col_h.size());
+    }
+
+    // ---- this rank's shard: contiguous landmark range balanced by observation count ----
+    uint32_t lo = 0, hi = n_active;
+    if (n_ranks > 1) {
+        auto cut = [&](int r) -> uint32_t {
+            const uint64_t target = n_st * uint64_t(r) / uint64_t(n_ranks);
+            return uint32_t(std::lower_bound(all_ptr.begin(), all_ptr.end(), uint32_t(target)) - all_ptr.begin());
+        };
+        lo = std::min(cut(rank), n_active);
+        hi = rank == n_ranks - 1 ? n_active : std::min(cut(rank + 1), n_active);
+    }
+    lm_lo = 0;
+    n_lm = int(hi - lo);
+    lm_hi = n_lm;
+    lm_user_h.assign(all_lm.begin() + lo, all_lm.begin() + hi);
+    lm_ptr_h.resize(size_t(n_lm) + 1);
+    const uint32_t base = all_ptr[lo];
+    for (int a = 0; a <= n_lm; ++a) lm_ptr_h[a] = all_ptr[lo + a] - base;
+    n_obs = lm_ptr_h[n_lm];
+    obs_user_h.assign(all_obs.begin() + base, all_obs.begin() + base + n_obs);
+}
+
+void Engine::upload() {
+    ensure_device(this, &stream, &own_stream, &ev_a, &ev_b, &ev_c, &ev_d, &h_pinned);
+    build_structure();
+    // gather the shard into landmark-major SoA arrays
+    std::vector<uint32_t> ocam(n_obs);
+    std::vector<double> ou(n_obs), ov(n_obs), od(n_obs), oW;
+    if (st_W_per_obs) oW.resize(9 * size_t(n_obs));
+    for (long long e = 0; e < n_obs; ++e) {
+        const uint32_t i = obs_user_h[e];
+        ocam[e] = st_cam[i];
+        ou[e] = st_uvd[3 * size_t(i)];
+        ov[e] = st_uvd[3 * size_t(i) + 1];
+        od[e] = st_uvd[3 * size_t(i) + 2];
+        if (st_W_per_obs) std::memcpy(&oW[9 * size_t(e)], st_W + 9 * size_t(i), 72);
+    }
+    std::vector<double> pts(3 * size_t(n_lm));
+    for (int a = 0; a < n_lm; ++a) std::memcpy(&pts[3 * size_t(a)], h_points + 3 * size_t(lm_user_h[a]), 24);
+
+    d_cam_free.upload(cam_free_h, stream);
+    d_lm_ptr.upload(lm_ptr_h, stream);
+    d_obs_cam.upload(ocam, stream);
+    d_obs_u.upload(ou, stream);
+    d_obs_v.upload(ov, stream);
+    d_obs_d.upload(od, stream);
+    if (st_W_per_obs)
+        d_obs_W.upload(oW, stream);
+    else if (n_st)
+        d_obs_W.upload(st_W, 9, stream);
+    else
+        d_obs_W.alloc(9);
+    d_poses_init.upload(h_poses, 12 * size_t(n_poses), stream);
+    d_points_init.upload(pts, stream);
+    d_poses.alloc(12 * size_t(n_poses));
+    d_poses_cand.alloc(12 * size_t(n_poses));
+    d_poses_best.alloc(12 * size_t(n_poses));
+    d_points.alloc(3 * size_t(n_lm));
+    d_points_cand.alloc(3 * size_t(n_lm));
+    d_points_best.alloc(3 * size_t(n_lm));
+    d_sc_p.alloc(6 * size_t(std::max(n_free, 1)));
+    d_sc_l.alloc(3 * size_t(std::max(n_lm, 1)));
+    d_cn_l.alloc(3 * size_t(std::max(n_lm, 1)));
+    d_gl.alloc(3 * size_t(std::max(n_lm, 1)));
+    d_yl.alloc(3 * size_t(std::max(n_lm, 1)));
+    d_s_rowptr.upload(s_rowptr_h, stream);
+    d_s_col.upload(s_col_h.empty() ? std::vector<int>(1, 0) : s_col_h, stream);
+    // transposed (strictly lower) lists for the symmetric SpMV
+    {
+        std::vector<int> ltp(size_t(n_free) + 1, 0), ltc, ltb;
+        for (int a = 0; a < n_free; ++a)
+            for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e)
+                if (s_col_h[e] != a) ltp[s_col_h[e] + 1]++;
+        for (int a = 0; a < n_free; ++a) ltp[a + 1] += ltp[a];
+        ltc.resize(std::max(1, ltp[n_free]));
+        ltb.resize(std::max(1, ltp[n_free]));
+        std::vector<int> fill(ltp.begin(), ltp.end() - 1);
+        for (int a = 0; a < n_free; ++a)
+            for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) {
+                const int b = s_col_h[e];
+                if (b == a) continue;
+                ltc[fill[b]] = a;
+                ltb[fill[b]] = e;
+                fill[b]++;
+            }
+        d_lt_rowptr.upload(ltp, stream);
+        d_lt_col.upload(ltc, stream);
+        d_lt_blk.upload(ltb, stream);
+    }
+    red_count = 36 * size_t(nnzU) + 36 * size_t(n_free) + 6 * size_t(n_free) + 6 * size_t(n_free) + SC_COUNT;
+    d_red.alloc(red_count);
+    d_S = d_red.p;
+    d_Bdiag = d_S + 36 * size_t(nnzU);
+    d_bp = d_Bdiag + 36 * size_t(n_free);
+    d_gp = d_bp + 6 * size_t(n_free);
+    d_scal = d_gp + 6 * size_t(n_free);
+    d_Minv.alloc(36 * size_t(std::max(n_free, 1)));
+    d_diag_p.alloc(6 * size_t(std::max(n_free, 1)));
+    const size_t nv = 6 * size_t(std::max(n_free, 1));
+    d_yp.alloc(nv);
+    d_pr.alloc(nv);
+    d_pz.alloc(nv);
+    d_pp.alloc(nv);
+    d_pq.alloc(nv);
+    d_pscal.alloc(PS_COUNT);
+    d_scal2.alloc(SC_COUNT);
+    if (!suns.empty()) d_suns.upload(suns, stream);
+    if (!priors.empty()) d_priors.upload(priors, stream);
+    CSLAM_CUDA(cudaStreamSynchronize(stream));  // host staging vectors go out of scope
+    uploaded = true;
+    begun = false;
+    user_copy_ready = false;
+    reset_state();
+}
+
+void Engine::reset_state() {
+    if (!uploaded) throw std::invalid_argument("reset_state before upload");
+    CSLAM_CUDA(cudaMemcpyAsync(d_poses.p, d_poses_init.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(d_poses_best.p, d_poses_init.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
+    if (n_lm) {
+        CSLAM_CUDA(cudaMemcpyAsync(d_points.p, d_points_init.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
+        CSLAM_CUDA(cudaMemcpyAsync(d_points_best.p, d_points_init.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
+    }
+    begun = false;
+}
+
+void Engine::download() {
+    if (!uploaded) throw std::invalid_argument("download before upload");
+    std::vector<double> pts(3 * size_t(n_lm));
+    std::vector<double> pos(12 * size_t(n_poses));
+    CSLAM_CUDA(cudaMemcpyAsync(pos.data(), d_poses_best.p, d_poses_best.bytes(), cudaMemcpyDeviceToHost, stream));
+    if (n_lm) CSLAM_CUDA(cudaMemcpyAsync(pts.data(), d_points_best.p, d_points_best.bytes(), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    for (int k : free_cams_h) std::memcpy(h_poses + 12 * size_t(k), &pos[12 * size_t(k)], 96);
+    for (int a = 0; a < n_lm; ++a) std::memcpy(h_points + 3 * size_t(lm_user_h[a]), &pts[3 * size_t(a)], 24);
+}
+
+void Engine::allreduce_system() {
+    if (n_ranks <= 1) return;
+    prof_begin(CSLAM_K_ALLREDUCE);
+    comm_allreduce_sum(nccl_comm, d_red.p, red_count, stream);
+    prof_end(CSLAM_K_ALLREDUCE);
+}
+void Engine::allreduce_small(double* dev, int n) {
+    if (n_ranks <= 1) return;
+    comm_allreduce_sum(nccl_comm, dev, size_t(n), stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// One Schur build at (x, radius): S, rhs, gradient, cost — leaves them in d_red
+// -------------------------------------------------------------------------------------------------
+void Engine::schur_pass() {
+    const LmDiag dg{1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+    DevView v = view(d_poses.p, d_points.p);
+    prof_begin(CSLAM_K_SCHUR);
+    d_red.zero(stream);
+    launch_schur_generic(stream, v, 0, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+    if (rank == 0)
+        launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
+                             d_scal);
+    prof_end(CSLAM_K_SCHUR);
+    allreduce_system();
+    prof_begin(CSLAM_K_FINALIZE);
+    launch_finalize(stream, v, dg, opt.preconditioner, d_S, d_Bdiag, d_diag_p.p, d_Minv.p, d_scal);
+    prof_end(CSLAM_K_FINALIZE);
+    lm.have_system = true;
+}
+
+void Engine::gradient_norm_pass() {
+    DevView v = view(d_poses.p, d_points.p);
+    // SC_GRADMAX / SC_XNORM2_CUR are not touched by the Schur kernels
+    launch_gradnorm(stream, v, 0, n_lm, d_gp, d_gl.p, d_scal, rank == 0);
+    double loc[SC_COUNT];
+    if (n_ranks > 1) {
+        // max over ranks == max of the per-rank maxima: all-reduce the squared-norm slot with sum
+        // and the max slot with max
+        comm_allreduce_max(nccl_comm, d_scal + SC_GRADMAX, 1, stream);
+        comm_allreduce_sum(nccl_comm, d_scal + SC_XNORM2_CUR, 1, stream);
+    }
+    read_scalars(d_scal, loc, SC_COUNT);
+    lm.gradient_max_norm = loc[SC_GRADMAX];
+    lm.x_norm = std::sqrt(loc[SC_XNORM2_CUR]);
+    lm.grad_fresh = true;
+}
+
+void Engine::run_pcg(int* iters, bool* ok) {
+    PcgBufs B;
+    B.rowptr = d_s_rowptr.p;
+    B.col = d_s_col.p;
+    B.lt_rowptr = d_lt_rowptr.p;
+    B.lt_col = d_lt_col.p;
+    B.lt_blk = d_lt_blk.p;
+    B.S = d_S;
+    B.Minv = d_Minv.p;
+    B.b = d_bp;
+    B.x = d_yp.p;
+    B.r = d_pr.p;
+    B.z = d_pz.p;
+    B.p = d_pp.p;
+    B.q = d_pq.p;
+    B.ps = d_pscal.p;
+    B.nf = n_free;
+    *iters = 0;
+    *ok = true;
+    if (n_free == 0) return;
+    double q_tol, r_tol;
+    int max_it, min_it;
+    if (opt.linear_solver == 0) {
+        // exact: run CG to the attainable residual; a 6x6 system converges in one step because
+        // the block-Jacobi preconditioner is then the exact inverse
+        q_tol = -1.0;
+        r_tol = 1e-15;
+        max_it = std::max(50, 12 * n_free + 20);
+        min_it = 0;
+    } else {
+        q_tol = opt.eta;
+        r_tol = -1.0;
+        max_it = opt.max_linear_solver_iterations;
+        min_it = opt.min_linear_solver_iterations;
+    }
+    prof_begin(CSLAM_K_PCG);
+    launch_pcg_init(stream, B);
+    double ps[PS_COUNT];
+    read_scalars(d_pscal.p, ps, PS_COUNT);
+    const double r_tol2 = r_tol < 0 ? -1.0 : r_tol * r_tol * ps[PS_NORMB2];
+    const int poll = 8;
+    int k = 1;
+    bool done = false;
+    while (!done) {
+        for (int c = 0; c < poll && k <= max_it; ++c, ++k)
+            launch_pcg_iteration(stream, B, k, q_tol, r_tol2, min_it, max_it, 10);
+        if (k > max_it) {
+            // evaluate the termination rule of the last iteration (sets DONE: max iterations)
+            launch_pcg_iteration(stream, B, max_it + 1, q_tol, r_tol2, min_it, max_it, 0);
+        }
+        read_scalars(d_pscal.p, ps, PS_COUNT);
+        done = ps[PS_DONE] != 0.0 || k > max_it;
+    }
+    prof_end(CSLAM_K_PCG);
+    *iters = int(ps[PS_ITERS]);
+    *ok = ps[PS_FAIL] != 2.0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LM loop
+// -------------------------------------------------------------------------------------------------
+void Engine::lm_begin() {
+    if (!uploaded) throw std::invalid_argument("lm_begin before upload");
+    lm = Lm();
+    log.clear();
+    // unit scaling for the initial pass
+    std::vector<double> ones(std::max<size_t>({6 * size_t(std::max(n_free, 1)), 3 * size_t(std::max(n_lm, 1))}), 1.0);
+    CSLAM_CUDA(cudaMemcpyAsync(d_sc_p.p, ones.data(), d_sc_p.bytes(), cudaMemcpyHostToDevice, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(d_sc_l.p, ones.data(), d_sc_l.bytes(), cudaMemcpyHostToDevice, stream));
+    DevView v = view(d_poses.p, d_points.p);
+    prof_begin(CSLAM_K_COLNORM);
+    d_red.zero(stream);
+    launch_colnorm(stream, v, 0, n_lm, d_Bdiag, d_cn_l.p, d_gp, d_gl.p, d_scal);
+    if (rank == 0)
+        launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
+                             d_scal);
+    prof_end(CSLAM_K_COLNORM);
+    allreduce_system();
+    gradient_norm_pass();  // sc == 1: gp, gl are the unscaled gradient
+    double loc[SC_COUNT];
+    read_scalars(d_scal, loc, SC_COUNT);
+    launch_jacobi_scale_cams(stream, d_Bdiag, d_sc_p.p, n_free, opt.jacobi_scaling);
+    launch_jacobi_scale(stream, d_cn_l.p, d_sc_l.p, 3ll * n_lm, opt.jacobi_scaling);
+    if (!std::isfinite(loc[SC_COST])) {
+        lm.finished = true;
+        lm.termination_type = 2;
+        lm.termination_reason = 8;
+        begun = true;
+        throw std::domain_error("non-finite cost at the initial point");
+    }
+    lm.x_cost = lm.initial_cost = lm.minimum_cost = loc[SC_COST];
+    lm.se_minimum = lm.se_current = lm.se_reference = lm.se_candidate = lm.x_cost;
+    lm.radius = opt.initial_trust_region_radius;
+    lm.decrease_factor = 2.0;
+    lm.have_system = false;
+    LmRow row{};
+    row.v[0] = 0;
+    row.v[1] = lm.x_cost;
+    row.v[3] = lm.gradient_max_norm;
+    row.v[6] = lm.radius;
+    log.push_back(row);
+    begun = true;
+}
+
+void Engine::fill_summary(cslam_summary* s) const {
+    if (!s) return;
+    std::memset(s, 0, sizeof(*s));
+    s->initial_cost = lm.initial_cost;
+    s->final_cost = lm.minimum_cost;
+    s->num_iterations = lm.iteration;
+    s->num_successful_steps = lm.num_successful;
+    s->num_unsuccessful_steps = lm.num_unsuccessful;
+    s->termination_type = lm.termination_type;
+    s->termination_reason = lm.termination_reason;
+    s->final_radius = lm.radius;
+    s->total_linear_iterations = lm.total_linear;
+    s->device_ms = lm.device_ms;
+}
+
+void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
+    if (!begun) throw std::invalid_argument("lm_iterate before lm_begin");
+    CSLAM_CUDA(cudaEventRecord(ev_a, stream));
+    const int max_nonmono = opt.use_nonmonotonic_steps ? opt.max_consecutive_nonmonotonic_steps : 0;
+    auto finish = [&](int type, int reason) {
+        lm.termination_type = type;
+        lm.termination_reason = reason;
+        lm.finished = !ignore_convergence || type == 2;
+    };
+    for (int it = 0; it < n && !lm.finished; ++it) {
+        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue ----
+        if (lm.iteration > 0) {
+            if (lm.step_ok_prev) {
+                ++lm.num_successful;
+                if (lm.x_cost < lm.minimum_cost) {
+                    lm.minimum_cost = lm.x_cost;
+                    CSLAM_CUDA(cudaMemcpyAsync(d_poses_best.p, d_poses.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
+                    if (n_lm)
+                        CSLAM_CUDA(cudaMemcpyAsync(d_points_best.p, d_points.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
+                }
+            } else {
+                ++lm.num_unsuccessful;
+            }
+            lm.step_ok_prev = false;
+        }
+        if (lm.iteration >= opt.max_num_iterations && !ignore_convergence) {
+            finish(1, 4);
+            break;
+        }
+        if (!lm.have_system) schur_pass();
+        if (!lm.grad_fresh) {
+            gradient_norm_pass();
+            if (!log.empty()) log.back().v[3] = lm.gradient_max_norm;
+        }
+        if (lm.gradient_max_norm <= opt.gradient_tolerance) {
+            finish(0, 1);
+            if (lm.finished) break;
+        }
+        if (lm.radius < opt.min_trust_region_radius) {
+            finish(0, 5);
+            if (lm.finished) break;
+        }
+        ++lm.iteration;
+        LmRow row{};
+        row.v[0] = lm.iteration;
+        // ---- LevenbergMarquardtStrategy::ComputeStep ----
+        double sc1[SC_COUNT];
+        read_scalars(d_scal, sc1, SC_COUNT);
+        int lin_iters = 0;
+        bool lin_ok = true;
+        bool valid = sc1[SC_INVALID] == 0.0;
+        if (valid) run_pcg(&lin_iters, &lin_ok);
+        valid = valid && lin_ok;
+        row.v[7] = lin_iters;
+        lm.total_linear += lin_iters;
+        double sc2[SC_COUNT] = {0};
+        const LmDiag dg{1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+        if (valid) {
+            DevView v = view(d_poses.p, d_points.p);
+            prof_begin(CSLAM_K_BACKSUB);
+            d_scal2.zero(stream);
+            launch_pose_plus(stream, v, d_yp.p, d_poses_cand.p, d_scal2.p, rank == 0);
+            launch_backsub(stream, v, 0, n_lm, dg, d_yp.p, d_poses_cand.p, d_points_cand.p, d_yl.p, d_scal2.p);
+            if (rank == 0)
+                launch_camonly_step(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_yp.p,
+                                    d_poses_cand.p, d_scal2.p);
+            prof_end(CSLAM_K_BACKSUB);
+            allreduce_small(d_scal2.p, SC_COUNT);
+            read_scalars(d_scal2.p, sc2, SC_COUNT);
+            if (sc2[SC_NONFINITE] != 0.0) valid = false;
+            if (!(sc2[SC_MODEL] > 0.0)) valid = false;
+        }
+        if (!valid) {
+            row.v[1] = lm.x_cost;
+            row.v[3] = lm.gradient_max_norm;
+            if (++lm.invalid_steps >= opt.max_num_consecutive_invalid_steps) {
+                row.v[6] = lm.radius;
+                log.push_back(row);
+                lm.termination_type = 2;
+                lm.termination_reason = 6;
+                lm.finished = true;
+                break;
+            }
+            lm.radius = lm.radius / lm.decrease_factor;
+            lm.decrease_factor *= 2.0;
+            lm.have_system = false;
+            row.v[6] = lm.radius;
+            log.push_back(row);
+            continue;
+        }
+        lm.invalid_steps = 0;
+        row.v[8] = 1;
+        const double model_cost_change = sc2[SC_MODEL];
+        double cand_cost = sc2[SC_CAND_COST];
+        if (!std::isfinite(cand_cost)) cand_cost = std::numeric_limits<double>::max();
+        row.v[4] = std::sqrt(sc2[SC_STEP_NORM2]);
+        row.v[2] = lm.x_cost - cand_cost;
+        if (!ignore_convergence) {
+            if (row.v[4] <= opt.parameter_tolerance * (lm.x_norm + opt.parameter_tolerance)) {
+                row.v[1] = lm.x_cost;
+                row.v[3] = lm.gradient_max_norm;
+                row.v[6] = lm.radius;
+                log.push_back(row);
+                finish(0, 2);
+                break;
+            }
+            if (std::fabs(row.v[2]) <= opt.function_tolerance * lm.x_cost) {
+                row.v[1] = lm.x_cost;
+                row.v[3] = lm.gradient_max_norm;
+                row.v[6] = lm.radius;
+                log.push_back(row);
+                finish(0, 3);
+                break;
+            }
+        }
+        const double rel = (lm.se_current - cand_cost) / model_cost_change;
+        const double hist = (lm.se_reference - cand_cost) / (lm.se_acc_ref + model_cost_change);
+        row.v[5] = std::max(rel, hist);
+        if (row.v[5] > opt.min_relative_decrease) {
+            std::swap(d_poses.p, d_poses_cand.p);
+            std::swap(d_points.p, d_points_cand.p);
+            lm.x_cost = cand_cost;
+            lm.x_norm = std::sqrt(sc2[SC_XNORM2]);
+            lm.step_ok_prev = true;
+            lm.have_system = false;
+            lm.grad_fresh = false;
+            row.v[9] = 1;
+            lm.radius = lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.v[5] - 1.0, 3));
+            lm.radius = std::min(opt.max_trust_region_radius, lm.radius);
+            lm.decrease_factor = 2.0;
+            lm.se_current = cand_cost;
+            lm.se_acc_cand += model_cost_change;
+            lm.se_acc_ref += model_cost_change;
+            if (lm.se_current < lm.se_minimum) {
+                lm.se_minimum = lm.se_current;
+                lm.se_nonmono = 0;
+                lm.se_candidate = lm.se_current;
+                lm.se_acc_cand = 0;
+            } else {
+                ++lm.se_nonmono;
+                if (lm.se_current > lm.se_candidate) {
+                    lm.se_candidate = lm.se_current;
+                    lm.se_acc_cand = 0;
+                }
+            }
+            if (lm.se_nonmono == max_nonmono) {
+                lm.se_reference = lm.se_candidate;
+                lm.se_acc_ref = lm.se_acc_cand;
+            }
+        } else {
+            lm.radius = lm.radius / lm.decrease_factor;
+            lm.decrease_factor *= 2.0;
+            lm.have_system = false;
+        }
+        row.v[1] = lm.x_cost;
+        row.v[3] = lm.gradient_max_norm;
+        row.v[6] = lm.radius;
+        log.push_back(row);
+    }
+    // bookkeeping for a step accepted in the last iteration of this call
+    if (lm.step_ok_prev && (lm.finished || true)) {
+        if (lm.x_cost < lm.minimum_cost) {
+            lm.minimum_cost = lm.x_cost;
+            CSLAM_CUDA(cudaMemcpyAsync(d_poses_best.p, d_poses.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
+            if (n_lm)
+                CSLAM_CUDA(cudaMemcpyAsync(d_points_best.p, d_points.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    CSLAM_CUDA(cudaEventRecord(ev_b, stream));
+    CSLAM_CUDA(cudaEventSynchronize(ev_b));
+    float ms = 0;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, ev_a, ev_b));
+    lm.device_ms += ms;
+    fill_summary(s);
+}
+
+// -------------------------------------------------------------------------------------------------
+// ceres::Problem::Evaluate at the caller's current parameter values (materialised r, J)
+// -------------------------------------------------------------------------------------------------
+void Engine::ensure_user_copy() {
+    ensure_device(this, &stream, &own_stream, &ev_a, &ev_b, &ev_c, &ev_d, &h_pinned);
+    if (user_copy_ready) return;
+    if (cam_free_h.size() != n_poses) build_structure();
+    const size_t n = n_st;
+    std::vector<double> u(n), v(n), d(n);
+    for (size_t i = 0; i < n; ++i) {
+        u[i] = st_uvd[3 * i];
+        v[i] = st_uvd[3 * i + 1];
+        d[i] = st_uvd[3 * i + 2];
+    }
+    const size_t tiles = (n + 127) / 128;
+    std::vector<int> tlo(std::max<size_t>(tiles, 1), 0), tn(std::max<size_t>(tiles, 1), 0);
+    for (size_t t = 0; t < tiles; ++t) {
+        uint32_t lo = 0xffffffffu, hi = 0;
+        for (size_t i = 128 * t; i < std::min(n, 128 * (t + 1)); ++i) {
+            lo = std::min(lo, st_cam[i]);
+            hi = std::max(hi, st_cam[i]);
+        }
+        tlo[t] = int(lo);
+        tn[t] = (hi - lo + 1 <= 16) ? int(hi - lo + 1) : 0;  // 0: gather poses from global memory
+    }
+    d_u_cam.upload(st_cam, n, stream);
+    d_u_pt.upload(st_pt, n, stream);
+    d_u_u.upload(u, stream);
+    d_u_v.upload(v, stream);
+    d_u_d.upload(d, stream);
+    d_u_W.upload(st_W, st_W_per_obs ? 9 * n : 9, stream);
+    d_u_tile_lo.upload(tlo, stream);
+    d_u_tile_n.upload(tn, stream);
+    d_cam_free.upload(cam_free_h, stream);
+    d_o_r.alloc(3 * n);
+    d_o_Jc.alloc(18 * n);
+    d_o_Jp.alloc(9 * n);
+    if (!d_scal2.p) d_scal2.alloc(SC_COUNT);
+    if (!suns.empty()) d_suns.upload(suns, stream);
+    if (!priors.empty()) d_priors.upload(priors, stream);
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    user_copy_ready = true;
+}
+
+void Engine::evaluate(int apply_loss, double* cost, double* r_st, double* Jc_st, double* Jp_st, double* r_sun,
+                      double* J_sun, double* r_pr, double* J_pr) {
+    ensure_user_copy();
+    // parameter values as they are in the caller's arrays right now
+    d_poses_cand.upload(h_poses, 12 * size_t(n_poses), stream);
+    d_u_points.upload(h_points, 3 * size_t(n_points), stream);
+    d_scal2.zero(stream);
+    launch_resjac(stream, cam, (long long)n_st, d_u_cam.p, d_u_pt.p, d_u_u.p, d_u_v.p, d_u_d.p, d_u_W.p, st_W_per_obs,
+                  d_poses_cand.p, d_u_points.p, d_cam_free.p, d_u_tile_lo.p, d_u_tile_n.p, d_o_r.p, d_o_Jc.p, d_o_Jp.p,
+                  d_scal2.p);
+    const int ns = int(suns.size()), np = int(priors.size());
+    DBuf<double> o_rs, o_Js, o_rp, o_Jp2;
+    if (ns + np > 0) {
+        o_rs.alloc(2 * size_t(std::max(ns, 1)));
+        o_Js.alloc(12 * size_t(std::max(ns, 1)));
+        o_rp.alloc(6 * size_t(std::max(np, 1)));
+        o_Jp2.alloc(36 * size_t(std::max(np, 1)));
+        DevView v{};
+        v.cam = cam;
+        v.n_cams = int(n_poses);
+        v.poses = d_poses_cand.p;
+        v.cam_free = d_cam_free.p;
+        launch_camonly_eval(stream, v, d_suns.p, ns, d_priors.p, np, apply_loss, o_rs.p, o_Js.p, o_rp.p, o_Jp2.p,
+                            d_scal2.p);
+    }
+    auto d2h = [&](double* dst, const double* src, size_t count) {
+        if (dst && count) CSLAM_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    };
+    d2h(r_st, d_o_r.p, 3 * size_t(n_st));
+    d2h(Jc_st, d_o_Jc.p, 18 * size_t(n_st));
+    d2h(Jp_st, d_o_Jp.p, 9 * size_t(n_st));
+    d2h(r_sun, o_rs.p, 2 * size_t(ns));
+    d2h(J_sun, o_Js.p, 12 * size_t(ns));
+    d2h(r_pr, o_rp.p, 6 * size_t(np));
+    d2h(J_pr, o_Jp2.p, 36 * size_t(np));
+    double c = 0;
+    read_scalars(d_scal2.p, &c, 1);
+    if (cost) *cost = c;
+}
+
+double Engine::time_resjac(int reps) {
+    ensure_user_copy();
+    d_poses_cand.upload(h_poses, 12 * size_t(n_poses), stream);
+    d_u_points.upload(h_points, 3 * size_t(n_points), stream);
+    d_scal2.zero(stream);
+    auto go = [&]() {
+        launch_resjac(stream, cam, (long long)n_st, d_u_cam.p, d_u_pt.p, d_u_u.p, d_u_v.p, d_u_d.p, d_u_W.p,
+                      st_W_per_obs, d_poses_cand.p, d_u_points.p, d_cam_free.p, d_u_tile_lo.p, d_u_tile_n.p, d_o_r.p,
+                      d_o_Jc.p, d_o_Jp.p, d_scal2.p);
+    };
+    for (int i = 0; i < 3; ++i) go();
+    CSLAM_CUDA(cudaEventRecord(ev_a, stream));
+    for (int i = 0; i < reps; ++i) go();
+    CSLAM_CUDA(cudaEventRecord(ev_b, stream));
+    CSLAM_CUDA(cudaEventSynchronize(ev_b));
+    float ms = 0;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, ev_a, ev_b));
+    return double(ms) / reps;
+}
+
+double Engine::time_schur(int reps) {
+    if (!begun) throw std::invalid_argument("time_schur before lm_begin");
+    const LmDiag dg{1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+    DevView v = view(d_poses.p, d_points.p);
+    auto go = [&]() {
+        d_red.zero(stream);
+        launch_schur_generic(stream, v, 0, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+    };
+    for (int i = 0; i < 2; ++i) go();
+    float total = 0;
+    for (int i = 0; i < reps; ++i) {
+        d_red.zero(stream);
+        CSLAM_CUDA(cudaEventRecord(ev_a, stream));
+        launch_schur_generic(stream, v, 0, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+        CSLAM_CUDA(cudaEventRecord(ev_b, stream));
+        CSLAM_CUDA(cudaEventSynchronize(ev_b));
+        float ms = 0;
+        CSLAM_CUDA(cudaEventElapsedTime(&ms, ev_a, ev_b));
+        total += ms;
+    }
+    lm.have_system = false;
+    return double(total) / reps;
+}
+
+void Engine::get_reduced_sizes(int* nf, int* nnz) const {
+    *nf = n_free;
+    *nnz = nnzU;
+}
+
+void Engine::get_reduced_system(int* rowptr, int* col, double* values, double* rhs, int* ids) {
+    if (!begun) throw std::invalid_argument("no reduced system yet");
+    if (!lm.have_system) schur_pass();
+    std::memcpy(rowptr, s_rowptr_h.data(), s_rowptr_h.size() * sizeof(int));
+    std::memcpy(col, s_col_h.data(), s_col_h.size() * sizeof(int));
+    std::memcpy(ids, free_cams_h.data(), free_cams_h.size() * sizeof(int));
+    CSLAM_CUDA(cudaMemcpyAsync(values, d_S, 36 * size_t(nnzU) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(rhs, d_bp, 6 * size_t(n_free) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+}
+
+bool Engine::window_eligible() const { return false; }
+
+}  // namespace cslam

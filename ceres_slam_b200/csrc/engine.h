@@ -1,0 +1,199 @@
+// Host-side state of one bundle-adjustment problem on one B200, and the kernel launch surface.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cslam_b200.h"
+#include "closed_form.h"
+#include "common.cuh"
+
+namespace cslam {
+
+// Scalar slots accumulated on the device (doubles), one 32-slot block per use.
+enum Scal {
+    SC_COST = 0,         // 1/2 sum rho(|r|^2) at x (schur / colnorm pass)
+    SC_MODEL = 1,        // model cost change  -(J s).(r + J s / 2)
+    SC_CAND_COST = 2,    // cost at the candidate point
+    SC_STEP_NORM2 = 3,   // |x - x_cand|^2 (ambient)
+    SC_XNORM2 = 4,       // |x|^2 over free blocks (ambient) at the candidate
+    SC_INVALID = 5,      // count of point blocks whose V was not positive definite
+    SC_GRADMAX = 6,      // |x - Plus(x,-g)|_inf (bit-pattern max)
+    SC_XNORM2_CUR = 7,   // |x|^2 at the current point (initial pass)
+    SC_NONFINITE = 8,    // non-finite step entries
+    SC_COUNT = 32
+};
+// PCG scalar slots
+enum PcgScal {
+    PS_RHO = 0, PS_RHO_NEXT = 1, PS_PQ = 2, PS_Q1 = 3, PS_Q0 = 4, PS_NORMB2 = 5, PS_ALPHA = 6,
+    PS_BETA = 7, PS_DONE = 8, PS_ITERS = 9, PS_FAIL = 10, PS_NORMR2 = 11, PS_COUNT = 16
+};
+
+// Raw device pointers handed to kernels by value.
+struct DevView {
+    CameraIntrinsics cam;
+    int n_cams, n_free, n_lm;
+    long long n_obs;
+    const double* poses;      // [n_cams][12] state the pass evaluates at
+    const double* points;     // [n_lm][3], internal (landmark-major) order
+    const int* cam_free;      // [n_cams] -> free index or -1
+    const uint32_t* lm_ptr;   // [n_lm + 1] CSR over observations
+    const uint32_t* obs_cam;  // [n_obs]
+    const double* obs_u;      // SoA observations, internal order
+    const double* obs_v;
+    const double* obs_d;
+    const double* obs_W;      // 9 doubles shared, or 9 per observation (AoS)
+    int W_per_obs;
+    const double* sc_p;       // [6 n_free] Jacobi column scaling (pose tangent)
+    const double* sc_l;       // [3 n_lm]
+    // reduced camera system (upper block-CSR, 6x6 row-major blocks)
+    const int* s_rowptr;
+    const int* s_col;
+};
+
+struct SunBlockData {
+    uint32_t cam;
+    double obs_c[3], ref_g[3], W[4], az_thresh, zen_thresh, huber;
+};
+struct PriorBlockData {
+    uint32_t cam;
+    double Tref[12], W[36];
+};
+
+struct LmRow {
+    double v[CSLAM_LOG_COLS];
+};
+
+class Engine {
+   public:
+    explicit Engine(const cslam_options& o);
+    ~Engine();
+
+    // ---- host description (borrowed pointers stay owned by the caller) ----
+    cslam_options opt;
+    CameraIntrinsics cam{1, 1, 0, 0, 1};
+    double* h_poses = nullptr;
+    uint32_t n_poses = 0;
+    std::vector<uint8_t> pose_const;
+    double* h_points = nullptr;
+    uint32_t n_points = 0;
+    uint64_t n_st = 0;
+    const uint32_t* st_cam = nullptr;
+    const uint32_t* st_pt = nullptr;
+    const double* st_uvd = nullptr;
+    const double* st_W = nullptr;
+    int st_W_per_obs = 0;
+    std::vector<SunBlockData> suns;
+    std::vector<PriorBlockData> priors;
+    std::string err;
+
+    // multi-GPU
+    int n_ranks = 1, rank = 0;
+    void* nccl_comm = nullptr;
+
+    // ---- entry points used by the C ABI ----
+    void upload();
+    void lm_begin();
+    void lm_iterate(int n, bool ignore_convergence, cslam_summary* s);
+    void download();
+    void reset_state();
+    void evaluate(int apply_loss, double* cost, double* r_st, double* Jc_st, double* Jp_st, double* r_sun,
+                  double* J_sun, double* r_pr, double* J_pr);
+    double time_resjac(int reps);
+    double time_schur(int reps);
+    void fill_summary(cslam_summary* s) const;
+    void get_reduced_sizes(int* nf, int* nnz) const;
+    void get_reduced_system(int* rowptr, int* col, double* values, double* rhs, int* ids);
+    void set_stream(cudaStream_t s);
+
+    std::vector<LmRow> log;
+    cslam_profile prof{};
+    bool uploaded = false, begun = false;
+
+    // small-problem description used by the batched window kernel
+    bool window_eligible() const;
+
+   private:
+    friend struct EngineAccess;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+
+    // structure (host copies kept for download / diagnostics)
+    std::vector<int> cam_free_h, free_cams_h;
+    std::vector<uint32_t> lm_user_h;      // internal landmark -> user point index
+    std::vector<uint32_t> lm_ptr_h;
+    std::vector<uint32_t> obs_user_h;     // internal obs -> user obs index
+    std::vector<int> s_rowptr_h, s_col_h;
+    int n_free = 0, n_lm = 0;
+    long long n_obs = 0;
+    int nnzU = 0;
+    // shard of landmarks this rank owns (internal order)
+    int lm_lo = 0, lm_hi = 0;
+
+    // device state
+    DBuf<double> d_poses, d_poses_cand, d_poses_best, d_poses_init;
+    DBuf<double> d_points, d_points_cand, d_points_best, d_points_init;
+    DBuf<int> d_cam_free;
+    DBuf<uint32_t> d_lm_ptr, d_obs_cam;
+    DBuf<double> d_obs_u, d_obs_v, d_obs_d, d_obs_W;
+    DBuf<double> d_sc_p, d_sc_l, d_cn_p, d_cn_l;
+    DBuf<double> d_gl;                     // scaled point gradient from the last Schur pass
+    DBuf<int> d_s_rowptr, d_s_col, d_lt_rowptr, d_lt_col, d_lt_blk;
+    // [ S values (36 nnzU) | Bdiag (36 nf) | rhs (6 nf) | gp (6 nf) | scalars (SC_COUNT) ] — one
+    // contiguous buffer so a single all-reduce sums every rank's partial reduced system
+    DBuf<double> d_red;
+    double *d_S = nullptr, *d_Bdiag = nullptr, *d_bp = nullptr, *d_gp = nullptr, *d_scal = nullptr;
+    size_t red_count = 0;
+    DBuf<double> d_Minv, d_diag_p;
+    DBuf<double> d_yp, d_pr, d_pz, d_pp, d_pq, d_yl;
+    DBuf<double> d_pscal;
+    DBuf<double> d_scal2;                  // scalars of the back-substitution pass
+    DBuf<SunBlockData> d_suns;
+    DBuf<PriorBlockData> d_priors;
+    // user-order copy for the materialised residual/Jacobian kernel
+    DBuf<uint32_t> d_u_cam, d_u_pt;
+    DBuf<double> d_u_u, d_u_v, d_u_d, d_u_W, d_u_points;
+    DBuf<int> d_u_tile_lo, d_u_tile_n;
+    DBuf<double> d_o_r, d_o_Jc, d_o_Jp;
+    bool user_copy_ready = false;
+    double* h_pinned = nullptr;            // pinned scalar read-back
+
+    // LM state (mirrors oracle/problem.hpp::solve)
+    struct Lm {
+        double x_cost = 0, x_norm = 0, gradient_max_norm = 0;
+        double radius = 0, decrease_factor = 2;
+        bool reuse_diagonal = false;
+        double minimum_cost = 0;
+        double se_minimum = 0, se_current = 0, se_reference = 0, se_candidate = 0, se_acc_ref = 0,
+               se_acc_cand = 0;
+        int se_nonmono = 0;
+        int invalid_steps = 0;
+        int iteration = 0;
+        bool step_ok_prev = false, finished = false;
+        bool have_system = false;          // S, rhs valid for current (x, radius)
+        bool grad_fresh = false;
+        int num_successful = 0, num_unsuccessful = 0, total_linear = 0;
+        int termination_type = 1, termination_reason = 0;
+        double initial_cost = 0;
+        double device_ms = 0;
+    } lm;
+
+    DevView view(const double* poses, const double* points) const;
+    void build_structure();
+    void ensure_user_copy();
+    void schur_pass();
+    void run_pcg(int* iters, bool* ok);
+    void gradient_norm_pass();
+    void prof_begin(int k);
+    void prof_end(int k);
+    void read_scalars(const double* dev, double* host, int n);
+    void allreduce_system();
+    void allreduce_small(double* dev, int n);
+};
+
+// window batch (kernels_window.cu)
+void solve_window_batch(Engine** engines, int n, cslam_summary* summaries);
+
+}  // namespace cslam

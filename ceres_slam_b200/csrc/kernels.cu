@@ -1,0 +1,1107 @@
+// sm_100a kernels of the cslam_b200 bundle-adjustment back end (generic paths).
+//
+//   resjac_kernel        K1  materialised residual + Jacobian (ceres::Problem::Evaluate)
+//   colnorm_kernel           squared column norms + gradient + cost at the initial point
+//   schur_generic_kernel K2  fused residual/Jacobian + Schur elimination, warp per landmark
+//   camonly_*                sun-sensor / pose-prior blocks
+//   finalize_kernel          LM diagonal on the camera blocks + block-Jacobi inverse
+//   pcg_*                K3a block-Jacobi PCG on the block-sparse reduced camera system
+//   pose_plus / backsub  K4  Plus, back-substitution, model cost change, candidate cost
+//
+// Everything is FP64, no fast-math.  Reference semantics: SURVEY.md App. A / App. B.
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+
+namespace cslam {
+
+namespace {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ const double* obs_W_ptr(const DevView& v, long long e) {
+    return v.W_per_obs ? v.obs_W + 9 * e : v.obs_W;
+}
+
+__device__ __forceinline__ int find_block(const int* __restrict__ rowptr, const int* __restrict__ col, int a, int b) {
+    int lo = rowptr[a], hi = rowptr[a + 1] - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (col[mid] < b)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;  // pattern is built from co-visibility, so the block exists
+}
+
+// =============================================================================================
+// K1 — materialised residual + Jacobian
+// =============================================================================================
+constexpr int RJ_TILE = 128;
+constexpr int RJ_PMAX = 16;
+constexpr int RJ_STAGE_DOUBLES = RJ_TILE * 30;
+constexpr size_t RJ_SMEM = 2 * RJ_STAGE_DOUBLES * sizeof(double) + RJ_PMAX * 12 * sizeof(double) + 16;
+
+template <bool kWPerObs>
+__global__ void __launch_bounds__(RJ_TILE)
+    resjac_kernel(CameraIntrinsics cam, long long n, const uint32_t* __restrict__ cam_idx,
+                  const uint32_t* __restrict__ pt_idx, const double* __restrict__ ou,
+                  const double* __restrict__ ov, const double* __restrict__ od, const double* __restrict__ Wg,
+                  const double* __restrict__ poses, const double* __restrict__ points,
+                  const int* __restrict__ cam_free, const int* __restrict__ tile_lo,
+                  const int* __restrict__ tile_n, double* __restrict__ out_r, double* __restrict__ out_Jc,
+                  double* __restrict__ out_Jp, double* __restrict__ cost_out) {
+    extern __shared__ __align__(128) unsigned char smem_rj[];
+    double* s_out = reinterpret_cast<double*>(smem_rj);
+    double* s_pose = s_out + 2 * RJ_STAGE_DOUBLES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_pose + RJ_PMAX * 12);
+    __shared__ double s_red[32];
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const long long n_tiles = (n + RJ_TILE - 1) / RJ_TILE;
+    uint32_t phase = 0;
+    int it = 0;
+    double cost = 0.0;
+    double Wl[9];
+    if (!kWPerObs) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Wl[k] = Wg[k];
+    }
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const long long base = t * RJ_TILE;
+        const long long i = base + tid;
+        const bool active = i < n;
+        const int lo = tile_lo[t], np = tile_n[t];
+        if (np > 0 && tid == 0) {
+            // camera poses of this tile: one bulk async copy global -> shared, completion on mbarrier
+            mbar_expect_tx(bar, np * 96);
+            tma_load_1d(s_pose, poses + 12ll * lo, np * 96, bar);
+        }
+        uint32_t c = 0;
+        double u = 0, vv = 0, d = 0, p[3] = {0, 0, 1};
+        if (active) {
+            c = cam_idx[i];
+            const uint32_t j = pt_idx[i];
+            u = ou[i];
+            vv = ov[i];
+            d = od[i];
+            p[0] = points[3ll * j];
+            p[1] = points[3ll * j + 1];
+            p[2] = points[3ll * j + 2];
+            if (kWPerObs) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Wl[k] = Wg[9 * i + k];
+            }
+        }
+        double pose[12];
+        if (np > 0) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            const double* sp = s_pose + 12 * (active ? int(c) - lo : 0);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) pose[k] = sp[k];
+        } else {
+            const double* gp = poses + 12ll * c;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) pose[k] = gp[k];
+        }
+        double r[3] = {0, 0, 0}, Jc[18], Jp[9];
+        if (active) {
+            stereo_block<true>(cam, pose, p, u, vv, d, Wl, r, Jc, Jp);
+            if (cam_free[c] < 0) {
+                // constant pose block: Ceres drops its columns (dataset_vo.cpp:62)
+#pragma unroll
+                for (int k = 0; k < 18; ++k) Jc[k] = 0.0;
+            }
+            cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        }
+        const bool full = base + RJ_TILE <= n;
+        if (full) {
+            double* st = s_out + (it & 1) * RJ_STAGE_DOUBLES;
+            // the bulk store that read this stage two tiles ago must have drained
+            if (tid == 0) tma_store_wait_read<1>();
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st[3 * tid + k] = r[k];
+#pragma unroll
+            for (int k = 0; k < 18; ++k) st[RJ_TILE * 3 + 18 * tid + k] = Jc[k];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st[RJ_TILE * 21 + 9 * tid + k] = Jp[k];
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                if (out_r) tma_store_1d(out_r + 3 * base, st, RJ_TILE * 24);
+                if (out_Jc) tma_store_1d(out_Jc + 18 * base, st + RJ_TILE * 3, RJ_TILE * 144);
+                if (out_Jp) tma_store_1d(out_Jp + 9 * base, st + RJ_TILE * 21, RJ_TILE * 72);
+                tma_store_commit();
+            }
+        } else {
+            __syncthreads();  // keep s_pose alive until every thread has read it
+            if (active) {
+                if (out_r)
+                    for (int k = 0; k < 3; ++k) out_r[3 * i + k] = r[k];
+                if (out_Jc)
+                    for (int k = 0; k < 18; ++k) out_Jc[18 * i + k] = Jc[k];
+                if (out_Jp)
+                    for (int k = 0; k < 9; ++k) out_Jp[9 * i + k] = Jp[k];
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait<0>();
+    block_atomic_sum(cost, cost_out, s_red);
+}
+
+// =============================================================================================
+// initial pass: cost, squared column norms and gradient of the unscaled Jacobian
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+    colnorm_kernel(DevView v, int lm_lo, int lm_hi, double* __restrict__ cn_p, double* __restrict__ cn_l,
+                   double* __restrict__ gp, double* __restrict__ gl, double* __restrict__ scal) {
+    __shared__ double s_red[32];
+    double cost = 0.0;
+    for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
+        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
+        double cl[3] = {0, 0, 0}, g[3] = {0, 0, 0};
+        for (uint32_t e = v.lm_ptr[j]; e < v.lm_ptr[j + 1]; ++e) {
+            const uint32_t c = v.obs_cam[e];
+            double r[3], Jc[18], Jp[9];
+            stereo_block<true>(v.cam, v.poses + 12ll * c, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e),
+                               r, Jc, Jp);
+            cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                cl[q] += Jp[q] * Jp[q] + Jp[3 + q] * Jp[3 + q] + Jp[6 + q] * Jp[6 + q];
+                g[q] += Jp[q] * r[0] + Jp[3 + q] * r[1] + Jp[6 + q] * r[2];
+            }
+            const int f = v.cam_free[c];
+            if (f >= 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    red_add(&cn_p[36ll * f + 7 * q], Jc[q] * Jc[q] + Jc[6 + q] * Jc[6 + q] + Jc[12 + q] * Jc[12 + q]);
+                    red_add(&gp[6ll * f + q], Jc[q] * r[0] + Jc[6 + q] * r[1] + Jc[12 + q] * r[2]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            cn_l[3ll * j + q] = cl[q];
+            gl[3ll * j + q] = g[q];
+        }
+    }
+    block_atomic_sum(cost, &scal[SC_COST], s_red);
+}
+
+__global__ void jacobi_scale_kernel(const double* __restrict__ cn, double* __restrict__ sc, long long n, int enabled) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) sc[i] = enabled ? 1.0 / (1.0 + sqrt(cn[i])) : 1.0;
+}
+
+// =============================================================================================
+// K2 — generic fused Schur build: one warp per landmark, lanes over its observations
+// =============================================================================================
+constexpr int SG_WARPS = 4;
+constexpr int SG_WARP_DOUBLES = 3 * 18 * 32;  // sW, sY, sW2 stored [k][lane]
+constexpr size_t SG_SMEM = SG_WARPS * (SG_WARP_DOUBLES * sizeof(double) + 2 * 32 * sizeof(int));
+
+struct ObsEval {
+    double r[3], Jc[18], Jp[9];
+    int f;
+};
+
+__device__ __forceinline__ void eval_obs_scaled(const DevView& v, long long e, const double* p, const double* sl,
+                                                ObsEval& o) {
+    const uint32_t c = v.obs_cam[e];
+    stereo_block<true>(v.cam, v.poses + 12ll * c, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e), o.r, o.Jc,
+                       o.Jp);
+    o.f = v.cam_free[c];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o.Jp[3 * k + q] *= sl[q];
+    }
+    if (o.f >= 0) {
+        const double* sp = v.sc_p + 6ll * o.f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double s = sp[q];
+            o.Jc[q] *= s;
+            o.Jc[6 + q] *= s;
+            o.Jc[12 + q] *= s;
+        }
+    }
+}
+
+// W = Jc^T Jp (6x3 row-major)
+__device__ __forceinline__ void form_W(const ObsEval& o, double* W) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            W[3 * p + q] = o.Jc[p] * o.Jp[q] + o.Jc[6 + p] * o.Jp[3 + q] + o.Jc[12 + p] * o.Jp[6 + q];
+}
+// Y = W Vi, Vi symmetric 3x3 given by its 6 unique entries
+__device__ __forceinline__ void form_Y(const double* W, const double* Vi, double* Y) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const double w0 = W[3 * p], w1 = W[3 * p + 1], w2 = W[3 * p + 2];
+        Y[3 * p + 0] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+        Y[3 * p + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+        Y[3 * p + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+    }
+}
+
+__device__ __forceinline__ void pair_to_S(const DevView& v, double* __restrict__ S, const double* sY, const double* sW,
+                                          int x, int y, int fx, int fy, bool same_obs) {
+    // P = Y_x W_y^T ; block(fx,fy) -= P (fx <= fy) else block(fy,fx) -= P^T ;
+    // two observations from one camera (fx == fy, x != y): diagonal block -= P + P^T
+    double Yx[18], Wy[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+        Yx[k] = sY[k * 32 + x];
+        Wy[k] = sW[k * 32 + y];
+    }
+    const bool swap = fx > fy;
+    const int a = swap ? fy : fx, b = swap ? fx : fy;
+    double* B = S + 36ll * find_block(v.s_rowptr, v.s_col, a, b);
+    const bool dup = (fx == fy) && !same_obs;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double val = Yx[3 * p] * Wy[3 * q] + Yx[3 * p + 1] * Wy[3 * q + 1] + Yx[3 * p + 2] * Wy[3 * q + 2];
+            if (swap) {
+                red_add(&B[6 * q + p], -val);
+            } else {
+                red_add(&B[6 * p + q], -val);
+                if (dup) red_add(&B[6 * q + p], -val);
+            }
+        }
+}
+
+__global__ void __launch_bounds__(SG_WARPS * 32)
+    schur_generic_kernel(DevView v, int lm_lo, int lm_hi, LmDiag dg, double* __restrict__ S,
+                         double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
+                         double* __restrict__ gl, double* __restrict__ scal) {
+    extern __shared__ __align__(128) unsigned char smem_sg[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* sW = reinterpret_cast<double*>(smem_sg) + wib * SG_WARP_DOUBLES;
+    double* sY = sW + 18 * 32;
+    double* sW2 = sY + 18 * 32;
+    int* sF = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_sg) + SG_WARPS * SG_WARP_DOUBLES) + wib * 64;
+    int* sF2 = sF + 32;
+    __shared__ double s_red[32];
+
+    double cost = 0.0;
+    const int warps_total = gridDim.x * SG_WARPS;
+    for (int j = lm_lo + blockIdx.x * SG_WARPS + wib; j < lm_hi; j += warps_total) {
+        const long long e0 = v.lm_ptr[j];
+        const int L = int(v.lm_ptr[j + 1] - e0);
+        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
+        const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
+        // ---- pass 1: V = sum Jp^T Jp, g = sum Jp^T r --------------------------------------
+        double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        ObsEval o;
+        o.f = -1;
+        for (int i = lane; i < L; i += 32) {
+            eval_obs_scaled(v, e0 + i, p, sl, o);
+            cost += 0.5 * (o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double a = o.Jp[3 * k], b = o.Jp[3 * k + 1], c = o.Jp[3 * k + 2];
+                V[0] += a * a;
+                V[1] += a * b;
+                V[2] += a * c;
+                V[3] += b * b;
+                V[4] += b * c;
+                V[5] += c * c;
+                g[0] += a * o.r[k];
+                g[1] += b * o.r[k];
+                g[2] += c * o.r[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[k] = warp_sum(V[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = warp_sum(g[k]);
+        // LM diagonal on the point block: clamp(diag) / radius (levenberg_marquardt_strategy)
+        V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        double Vi[6];
+        const bool pd = invert_sym3(V, Vi);
+        if (lane == 0) {
+            gl[3ll * j] = g[0];
+            gl[3ll * j + 1] = g[1];
+            gl[3ll * j + 2] = g[2];
+            if (!pd) red_add(&scal[SC_INVALID], 1.0);
+        }
+        if (!pd) continue;
+        // ---- pass 2: camera blocks, in chunks of 32 observations ----------------------------
+        for (int c0 = 0; c0 < L; c0 += 32) {
+            const int n = min(32, L - c0);
+            if (L > 32 && lane < n) eval_obs_scaled(v, e0 + c0 + lane, p, sl, o);
+            __syncwarp();
+            if (lane < n) {
+                sF[lane] = o.f;
+                if (o.f >= 0) {
+                    double W[18], Y[18];
+                    form_W(o, W);
+                    form_Y(W, Vi, Y);
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) {
+                        sW[k * 32 + lane] = W[k];
+                        sY[k * 32 + lane] = Y[k];
+                    }
+                    // U_aa (upper 21) and gradients
+                    double* Bd = Bdiag + 36ll * o.f;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                        for (int b = a; b < 6; ++b)
+                            red_add(&Bd[6 * a + b], o.Jc[a] * o.Jc[b] + o.Jc[6 + a] * o.Jc[6 + b] + o.Jc[12 + a] * o.Jc[12 + b]);
+                        const double ga = o.Jc[a] * o.r[0] + o.Jc[6 + a] * o.r[1] + o.Jc[12 + a] * o.r[2];
+                        const double yg = Y[3 * a] * g[0] + Y[3 * a + 1] * g[1] + Y[3 * a + 2] * g[2];
+                        red_add(&gp[6ll * o.f + a], ga);
+                        red_add(&bp[6ll * o.f + a], ga - yg);
+                    }
+                }
+            }
+            __syncwarp();
+            // pairs inside the chunk (x <= y)
+            const int npairs = n * (n + 1) / 2;
+            for (int pidx = lane; pidx < npairs; pidx += 32) {
+                // row x of the upper triangle holds n - x entries
+                int x = int((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * pidx)) * 0.5);
+                while (x > 0 && x * n - x * (x - 1) / 2 > pidx) --x;
+                while ((x + 1) * n - (x + 1) * x / 2 <= pidx) ++x;
+                const int y = x + (pidx - (x * n - x * (x - 1) / 2));
+                const int fx = sF[x], fy = sF[y];
+                if (fx < 0 || fy < 0) continue;
+                pair_to_S(v, S, sY, sW, x, y, fx, fy, x == y);
+            }
+            // pairs against later chunks (tracks longer than 32 observations)
+            for (int d0 = c0 + 32; d0 < L; d0 += 32) {
+                const int m = min(32, L - d0);
+                __syncwarp();
+                if (lane < m) {
+                    ObsEval o2;
+                    eval_obs_scaled(v, e0 + d0 + lane, p, sl, o2);
+                    sF2[lane] = o2.f;
+                    if (o2.f >= 0) {
+                        double W[18];
+                        form_W(o2, W);
+#pragma unroll
+                        for (int k = 0; k < 18; ++k) sW2[k * 32 + lane] = W[k];
+                    }
+                }
+                __syncwarp();
+                for (int pidx = lane; pidx < n * m; pidx += 32) {
+                    const int x = pidx / m, y = pidx - x * m;
+                    const int fx = sF[x], fy = sF2[y];
+                    if (fx < 0 || fy < 0) continue;
+                    pair_to_S(v, S, sY, sW2, x, y, fx, fy, false);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    block_atomic_sum(cost, &scal[SC_COST], s_red);
+}
+
+// =============================================================================================
+// camera-only blocks (sun sensor, pose prior)
+// =============================================================================================
+__device__ __forceinline__ void camonly_eval(const DevView& v, const SunBlockData* suns, int n_sun,
+                                             const PriorBlockData* priors, int i, const double* poses, bool want_J,
+                                             double* r, double* J, int* rows, int* cam, double* cost) {
+    if (i < n_sun) {
+        const SunBlockData& s = suns[i];
+        *cam = int(s.cam);
+        *rows = 2;
+        sun_block(poses + 12ll * s.cam, s.obs_c, s.ref_g, s.W, s.az_thresh, s.zen_thresh, r, want_J ? J : nullptr);
+        const double sq = r[0] * r[0] + r[1] * r[1];
+        double rho0 = sq, sr = 1.0;
+        if (s.huber > 0.0) huber_rho(s.huber, sq, &rho0, &sr);
+        *cost = 0.5 * rho0;
+        r[0] *= sr;
+        r[1] *= sr;
+        if (want_J)
+            for (int k = 0; k < 12; ++k) J[k] *= sr;
+    } else {
+        const PriorBlockData& p = priors[i - n_sun];
+        *cam = int(p.cam);
+        *rows = 6;
+        prior_block(poses + 12ll * p.cam, p.Tref, p.W, r, want_J ? J : nullptr);
+        double c = 0;
+        for (int k = 0; k < 6; ++k) c += 0.5 * r[k] * r[k];
+        *cost = c;
+    }
+}
+
+__global__ void camonly_build_kernel(DevView v, const SunBlockData* suns, int n_sun, const PriorBlockData* priors,
+                                     int n_prior, double* Bdiag, double* bp, double* gp, double* scal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sun + n_prior) return;
+    double r[6], J[36], cost;
+    int rows, cam;
+    camonly_eval(v, suns, n_sun, priors, i, v.poses, true, r, J, &rows, &cam, &cost);
+    red_add(&scal[SC_COST], cost);
+    const int f = v.cam_free[cam];
+    if (f < 0) return;
+    const double* sp = v.sc_p + 6ll * f;
+    for (int a = 0; a < 6; ++a) {
+        for (int b = a; b < 6; ++b) {
+            double s = 0;
+            for (int k = 0; k < rows; ++k) s += J[6 * k + a] * J[6 * k + b];
+            red_add(&Bdiag[36ll * f + 6 * a + b], s * sp[a] * sp[b]);
+        }
+        double g = 0;
+        for (int k = 0; k < rows; ++k) g += J[6 * k + a] * r[k];
+        red_add(&gp[6ll * f + a], g * sp[a]);
+        red_add(&bp[6ll * f + a], g * sp[a]);
+    }
+}
+
+// model cost change and candidate cost of the camera-only blocks
+__global__ void camonly_step_kernel(DevView v, const SunBlockData* suns, int n_sun, const PriorBlockData* priors,
+                                    int n_prior, const double* yp, const double* poses_cand, double* scal2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sun + n_prior) return;
+    double r[6], J[36], cost;
+    int rows, cam;
+    camonly_eval(v, suns, n_sun, priors, i, v.poses, true, r, J, &rows, &cam, &cost);
+    const int f = v.cam_free[cam];
+    double acc = 0;
+    for (int k = 0; k < rows; ++k) {
+        double m = 0;
+        if (f >= 0)
+            for (int a = 0; a < 6; ++a) m -= J[6 * k + a] * v.sc_p[6ll * f + a] * yp[6ll * f + a];
+        acc -= m * (r[k] + 0.5 * m);
+    }
+    red_add(&scal2[SC_MODEL], acc);
+    double rc[6], cc;
+    camonly_eval(v, suns, n_sun, priors, i, poses_cand, false, rc, nullptr, &rows, &cam, &cc);
+    red_add(&scal2[SC_CAND_COST], cc);
+}
+
+// =============================================================================================
+// finalize: S_aa += U_aa + D^2, symmetrise, block-Jacobi inverse
+// =============================================================================================
+__device__ __forceinline__ bool chol6_inverse(const double* A, double* Ainv) {
+    double L[36];
+    for (int i = 0; i < 36; ++i) L[i] = A[i];
+    for (int j = 0; j < 6; ++j) {
+        double d = L[6 * j + j];
+        for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        L[6 * j + j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = L[6 * i + j];
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k];
+            L[6 * i + j] = s / d;
+        }
+    }
+    for (int c = 0; c < 6; ++c) {
+        double e[6];
+        for (int i = 0; i < 6; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) s -= L[6 * i + k] * e[k];
+            e[i] = s / L[6 * i + i];
+        }
+        for (int i = 5; i >= 0; --i) {
+            double s = e[i];
+            for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * e[k];
+            e[i] = s / L[6 * i + i];
+        }
+        for (int r = 0; r < 6; ++r) Ainv[6 * r + c] = e[r];
+    }
+    return true;
+}
+
+__global__ void finalize_kernel(DevView v, LmDiag dg, int preconditioner, double* S, double* Bdiag, double* diag_p,
+                                double* Minv, double* scal) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= v.n_free) return;
+    double U[36];
+    double* Bd = Bdiag + 36ll * f;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) U[6 * a + b] = U[6 * b + a] = Bd[6 * a + b];
+    for (int a = 0; a < 6; ++a) {
+        const double dd = fmin(fmax(U[7 * a], dg.min_diag), dg.max_diag);
+        diag_p[6ll * f + a] = dd;
+        U[7 * a] += dd * dg.inv_radius;
+    }
+    double* Sd = S + 36ll * v.s_rowptr[f];  // diagonal block is the first block of the row
+    double A[36];
+    for (int k = 0; k < 36; ++k) {
+        A[k] = Sd[k] + U[k];
+        Sd[k] = A[k];
+        Bd[k] = U[k];
+    }
+    double Mi[36];
+    if (!chol6_inverse(preconditioner == 0 ? U : A, Mi)) {
+        red_add(&scal[SC_INVALID], 1.0);
+        for (int k = 0; k < 36; ++k) Mi[k] = (k % 7 == 0) ? 1.0 : 0.0;
+    }
+    for (int k = 0; k < 36; ++k) Minv[36ll * f + k] = Mi[k];
+}
+
+// =============================================================================================
+// K3a — PCG (Ceres conjugate_gradients_solver semantics)
+// =============================================================================================
+__device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x) || isnan(x); }
+
+__global__ void pcg_init_kernel(PcgBufs B) {
+    __shared__ double s_red[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = 6 * B.nf;
+    double nb = 0, rz = 0;
+    if (i < n) {
+        const double bi = B.b[i];
+        B.x[i] = 0.0;
+        B.r[i] = bi;
+        B.p[i] = 0.0;
+        // z = Minv r
+        const int f = i / 6, row = i - 6 * f;
+        double z = 0;
+        for (int k = 0; k < 6; ++k) z += B.Minv[36ll * f + 6 * row + k] * B.b[6 * f + k];
+        B.z[i] = z;
+        nb = bi * bi;
+        rz = bi * z;
+    }
+    block_atomic_sum(rz, &B.ps[PS_RHO_NEXT], s_red);
+    block_atomic_sum(nb, &B.ps[PS_NORMB2], s_red);
+}
+
+// K_b: evaluate the termination rule of the previous iteration, then p = z + beta p
+__global__ void pcg_dir_kernel(PcgBufs B, int k, double q_tol, double r_tol2, int min_iters, int max_iters) {
+    double* ps = B.ps;
+    if (ps[PS_DONE] != 0.0) return;
+    bool done = false, fail = false;
+    const int prev = k - 1;
+    if (ps[PS_NORMB2] == 0.0) done = true;  // b == 0 -> x = 0
+    if (prev >= 1 && !done) {
+        if (ps[PS_FAIL] != 0.0) {
+            done = true;
+        } else {
+            const double Q1 = ps[PS_Q1], Q0 = ps[PS_Q0];
+            const double zeta = prev * (Q1 - Q0) / Q1;
+            if (zeta < q_tol && prev >= min_iters) done = true;
+            if (ps[PS_NORMR2] <= r_tol2 && prev >= min_iters) done = true;
+            if (prev >= max_iters) done = true;
+        }
+    }
+    const double rho = ps[PS_RHO_NEXT], last_rho = ps[PS_RHO];
+    double beta = 0.0;
+    if (!done) {
+        if (zero_or_inf(rho)) {
+            done = fail = true;
+        } else if (k > 1) {
+            beta = rho / last_rho;
+            if (zero_or_inf(beta)) done = fail = true;
+        }
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!done && i < 6 * B.nf) B.p[i] = B.z[i] + beta * B.p[i];
+    if (i == 0) {
+        // single writer; every other thread derived the same decision from the same sums
+        if (done) {
+            ps[PS_DONE] = 1.0;
+            ps[PS_ITERS] = double(prev);
+            if (fail) ps[PS_FAIL] = 2.0;
+        } else {
+            ps[PS_BETA] = beta;
+        }
+    }
+}
+
+// K_c: q = S v (symmetric, upper storage + transposed lower lists); optional dot with v
+__global__ void pcg_spmv_kernel(PcgBufs B, const double* __restrict__ vec, double* __restrict__ out, int want_pq,
+                                int rotate) {
+    __shared__ double s_red[32];
+    double* ps = B.ps;
+    if (ps[PS_DONE] != 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double part = 0.0;
+    if (i < 6 * B.nf) {
+        const int a = i / 6, row = i - 6 * a;
+        double acc = 0.0;
+        for (int e = B.rowptr[a]; e < B.rowptr[a + 1]; ++e) {
+            const double* blk = B.S + 36ll * e + 6 * row;
+            const double* xv = vec + 6ll * B.col[e];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc += blk[j] * xv[j];
+        }
+        for (int e = B.lt_rowptr[a]; e < B.lt_rowptr[a + 1]; ++e) {
+            const double* blk = B.S + 36ll * B.lt_blk[e] + row;
+            const double* xv = vec + 6ll * B.lt_col[e];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc += blk[6 * j] * xv[j];
+        }
+        out[i] = acc;
+        part = vec[i] * acc;
+    }
+    if (want_pq) block_atomic_sum(part, &ps[PS_PQ], s_red);
+    if (rotate && i == 0) {
+        // rho bookkeeping for the next iteration: last_rho <- rho, accumulator cleared
+        ps[PS_RHO] = ps[PS_RHO_NEXT];
+        ps[PS_RHO_NEXT] = 0.0;
+    }
+}
+
+// K_da: x += alpha p ; r -= alpha q (or r = b - Sx on reset iterations, Sx already in q2) ;
+//       z = Minv r ; rho_next = r.z ; Q1 = -x.(b + r) ; |r|^2
+__global__ void pcg_update_kernel(PcgBufs B, int reset, int stage) {
+    __shared__ double s_red[32];
+    __shared__ double s_r[256];
+    double* ps = B.ps;
+    if (ps[PS_DONE] != 0.0) return;
+    const double pq = ps[PS_PQ], rho = ps[PS_RHO];
+    const bool bad_pq = (pq <= 0.0) || isinf(pq) || isnan(pq);
+    const double alpha = rho / pq;
+    const bool bad = bad_pq || isinf(alpha) || isnan(alpha);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = 6 * B.nf;
+    if (bad) {
+        if (i == 0) ps[PS_FAIL] = bad_pq ? 1.0 : 2.0;  // 1: indefinite (NO_CONVERGENCE), 2: failure
+        return;
+    }
+    if (stage == 0) {
+        // reset iterations only: x update first, the caller then computes q = S x
+        if (i < n) B.x[i] += alpha * B.p[i];
+        return;
+    }
+    double ri = 0, xi = 0, bi = 0;
+    if (i < n) {
+        bi = B.b[i];
+        if (reset) {
+            xi = B.x[i];
+            ri = bi - B.q[i];
+        } else {
+            xi = B.x[i] + alpha * B.p[i];
+            B.x[i] = xi;
+            ri = B.r[i] - alpha * B.q[i];
+        }
+        B.r[i] = ri;
+    }
+    s_r[threadIdx.x] = ri;
+    __syncthreads();
+    double z = 0;
+    if (i < n) {
+        const int f = i / 6, row = i - 6 * f;
+        const int base = threadIdx.x - row;  // blockDim.x is a multiple of 6
+        for (int k = 0; k < 6; ++k) z += B.Minv[36ll * f + 6 * row + k] * s_r[base + k];
+        B.z[i] = z;
+    }
+    block_atomic_sum(ri * z, &ps[PS_RHO_NEXT], s_red);
+    block_atomic_sum(-xi * (bi + ri), &ps[PS_Q1], s_red);
+    block_atomic_sum(ri * ri, &ps[PS_NORMR2], s_red);
+}
+
+// clears the per-iteration accumulators once their readers (pcg_dir_kernel) have run
+__global__ void pcg_clear_kernel(double* ps) {
+    if (ps[PS_DONE] != 0.0) return;
+    ps[PS_Q0] = ps[PS_Q1];
+    ps[PS_Q1] = 0.0;
+    ps[PS_NORMR2] = 0.0;
+    ps[PS_PQ] = 0.0;
+}
+
+// =============================================================================================
+// K4 — Plus, back-substitution, model cost change, candidate cost
+// =============================================================================================
+__global__ void pose_plus_kernel(DevView v, const double* __restrict__ yp, double* __restrict__ poses_cand,
+                                 double* __restrict__ scal2, int count_cams) {
+    __shared__ double s_red[32];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;  // thread per camera
+    double sn = 0, xn = 0, bad = 0;
+    if (c < v.n_cams) {
+        const int ff = v.cam_free[c];
+        const double* x = v.poses + 12ll * c;
+        double* y = poses_cand + 12ll * c;
+        if (ff >= 0) {
+            double eps[6];
+            for (int k = 0; k < 6; ++k) {
+                eps[k] = -yp[6ll * ff + k] * v.sc_p[6ll * ff + k];
+                if (isnan(eps[k]) || isinf(eps[k])) bad = 1;
+            }
+            double out[12];
+            se3_plus(x, eps, out);
+            for (int k = 0; k < 12; ++k) {
+                y[k] = out[k];
+                sn += (x[k] - out[k]) * (x[k] - out[k]);
+                xn += out[k] * out[k];
+            }
+        } else {
+            for (int k = 0; k < 12; ++k) y[k] = x[k];
+        }
+    }
+    if (!count_cams) {
+        sn = 0;
+        xn = 0;
+    }
+    block_atomic_sum(sn, &scal2[SC_STEP_NORM2], s_red);
+    block_atomic_sum(xn, &scal2[SC_XNORM2], s_red);
+    block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
+}
+
+__global__ void __launch_bounds__(128)
+    backsub_kernel(DevView v, int lm_lo, int lm_hi, LmDiag dg, const double* __restrict__ yp,
+                   const double* __restrict__ poses_cand, double* __restrict__ points_cand,
+                   double* __restrict__ yl_out, double* __restrict__ scal2) {
+    __shared__ double s_red[32];
+    double model = 0, ccost = 0, sn = 0, xn = 0, bad = 0;
+    for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
+        const long long e0 = v.lm_ptr[j], e1 = v.lm_ptr[j + 1];
+        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
+        const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
+        double V[6] = {0, 0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
+        ObsEval o;
+        for (long long e = e0; e < e1; ++e) {
+            eval_obs_scaled(v, e, p, sl, o);
+            double Jy[3] = {0, 0, 0};
+            if (o.f >= 0) {
+                const double* y = yp + 6ll * o.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) Jy[k] += o.Jc[6 * k + a] * y[a];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double a = o.Jp[3 * k], b = o.Jp[3 * k + 1], c = o.Jp[3 * k + 2];
+                V[0] += a * a;
+                V[1] += a * b;
+                V[2] += a * c;
+                V[3] += b * b;
+                V[4] += b * c;
+                V[5] += c * c;
+                // t = g_l - W^T yp = sum Jp^T (r - Jc yp)
+                const double w = o.r[k] - Jy[k];
+                t[0] += a * w;
+                t[1] += b * w;
+                t[2] += c * w;
+            }
+        }
+        V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        double Vi[6];
+        double yl[3] = {0, 0, 0};
+        if (invert_sym3(V, Vi)) {
+            yl[0] = Vi[0] * t[0] + Vi[1] * t[1] + Vi[2] * t[2];
+            yl[1] = Vi[1] * t[0] + Vi[3] * t[1] + Vi[4] * t[2];
+            yl[2] = Vi[2] * t[0] + Vi[4] * t[1] + Vi[5] * t[2];
+        }
+        double pn[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double dl = -yl[q] * sl[q];
+            if (isnan(dl) || isinf(dl)) bad = 1;
+            pn[q] = p[q] + dl;
+            points_cand[3ll * j + q] = pn[q];
+            yl_out[3ll * j + q] = yl[q];
+            sn += (p[q] - pn[q]) * (p[q] - pn[q]);
+            xn += pn[q] * pn[q];
+        }
+        // model cost change  -(J s).(r + J s / 2) with s = -y, and the cost at the candidate
+        for (long long e = e0; e < e1; ++e) {
+            eval_obs_scaled(v, e, p, sl, o);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double m = -(o.Jp[3 * k] * yl[0] + o.Jp[3 * k + 1] * yl[1] + o.Jp[3 * k + 2] * yl[2]);
+                if (o.f >= 0) {
+                    const double* y = yp + 6ll * o.f;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) m -= o.Jc[6 * k + a] * y[a];
+                }
+                model -= m * (o.r[k] + 0.5 * m);
+            }
+            double rc[3];
+            const uint32_t c = v.obs_cam[e];
+            stereo_block<false>(v.cam, poses_cand + 12ll * c, pn, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e), rc,
+                                nullptr, nullptr);
+            ccost += 0.5 * (rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2]);
+        }
+    }
+    block_atomic_sum(model, &scal2[SC_MODEL], s_red);
+    block_atomic_sum(ccost, &scal2[SC_CAND_COST], s_red);
+    block_atomic_sum(sn, &scal2[SC_STEP_NORM2], s_red);
+    block_atomic_sum(xn, &scal2[SC_XNORM2], s_red);
+    block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
+}
+
+// |x - Plus(x, -g)|_inf (trust_region_minimizer: gradient norm in ambient coordinates) and |x|^2
+__global__ void gradnorm_kernel(DevView v, int lm_lo, int lm_hi, const double* __restrict__ gp_s,
+                                const double* __restrict__ gl_s, double* __restrict__ scal, int count_cams) {
+    __shared__ double s_red[32];
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double m = 0, xn = 0;
+    if (i < v.n_cams) {
+        const int f = v.cam_free[i];
+        if (f >= 0 && count_cams) {
+            const double* x = v.poses + 12ll * i;
+            double eps[6], out[12];
+            for (int k = 0; k < 6; ++k) eps[k] = -gp_s[6ll * f + k] / v.sc_p[6ll * f + k];
+            se3_plus(x, eps, out);
+            for (int k = 0; k < 12; ++k) {
+                m = fmax(m, fabs(x[k] - out[k]));
+                xn += x[k] * x[k];
+            }
+        }
+    } else {
+        const long long j = lm_lo + (i - v.n_cams);
+        if (j < lm_hi) {
+            for (int q = 0; q < 3; ++q) {
+                const double x = v.points[3 * j + q];
+                const double g = gl_s[3 * j + q] / v.sc_l[3 * j + q];
+                m = fmax(m, fabs(x - (x - g)));
+                xn += x * x;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomic_max_nonneg(&scal[SC_GRADMAX], m);
+    block_atomic_sum(xn, &scal[SC_XNORM2_CUR], s_red);
+}
+
+// FP64 FMA microbenchmark: 8 independent chains per thread, register resident
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c);
+        a1 = fma(a1, b, c);
+        a2 = fma(a2, b, c);
+        a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c);
+        a5 = fma(a5, b, c);
+        a6 = fma(a6, b, c);
+        a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// camera scaling from the diagonal of Bdiag (squared column norms of the unscaled Jacobian)
+__global__ void jacobi_scale_cams_kernel(const double* __restrict__ Bdiag, double* __restrict__ sc, int nf, int enabled) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6 * nf) {
+        const int f = i / 6, a = i - 6 * f;
+        sc[i] = enabled ? 1.0 / (1.0 + sqrt(Bdiag[36ll * f + 7 * a])) : 1.0;
+    }
+}
+
+// materialised residuals / Jacobians of the camera-only blocks (cslam_evaluate)
+__global__ void camonly_eval_kernel(DevView v, const SunBlockData* suns, int n_sun, const PriorBlockData* priors,
+                                    int n_prior, int apply_loss, double* r_sun, double* J_sun, double* r_pr,
+                                    double* J_pr, double* cost_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sun + n_prior) return;
+    double r[6], J[36], cost;
+    int rows, cam;
+    if (i < n_sun && !apply_loss) {
+        const SunBlockData& s = suns[i];
+        cam = int(s.cam);
+        rows = 2;
+        sun_block(v.poses + 12ll * s.cam, s.obs_c, s.ref_g, s.W, s.az_thresh, s.zen_thresh, r, J);
+        cost = 0.5 * (r[0] * r[0] + r[1] * r[1]);
+    } else {
+        camonly_eval(v, suns, n_sun, priors, i, v.poses, true, r, J, &rows, &cam, &cost);
+    }
+    red_add(cost_out, cost);
+    const bool is_const = v.cam_free[cam] < 0;
+    if (i < n_sun) {
+        for (int k = 0; k < 2; ++k) r_sun[2 * i + k] = r[k];
+        for (int k = 0; k < 12; ++k) J_sun[12 * i + k] = is_const ? 0.0 : J[k];
+    } else {
+        const int q = i - n_sun;
+        for (int k = 0; k < 6; ++k) r_pr[6 * q + k] = r[k];
+        for (int k = 0; k < 36; ++k) J_pr[36 * q + k] = is_const ? 0.0 : J[k];
+    }
+}
+
+inline int grid_for(long long n, int block, int max_blocks) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return int(g);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+void launch_resjac(cudaStream_t s, const CameraIntrinsics& cam, long long n, const uint32_t* cam_idx,
+                   const uint32_t* pt_idx, const double* u, const double* v, const double* d, const double* W,
+                   int W_per_obs, const double* poses, const double* points, const int* cam_free, const int* tile_lo,
+                   const int* tile_n, double* r, double* Jc, double* Jp, double* cost) {
+    if (n <= 0) return;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CSLAM_CUDA(cudaFuncSetAttribute(resjac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RJ_SMEM)));
+        CSLAM_CUDA(cudaFuncSetAttribute(resjac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RJ_SMEM)));
+        attr_done = true;
+    }
+    const long long tiles = (n + RJ_TILE - 1) / RJ_TILE;
+    const int grid = int(tiles < 3ll * kSMs ? tiles : 3ll * kSMs);  // persistent: 3 CTAs per SM
+    if (W_per_obs)
+        resjac_kernel<true><<<grid, RJ_TILE, RJ_SMEM, s>>>(cam, n, cam_idx, pt_idx, u, v, d, W, poses, points, cam_free,
+                                                           tile_lo, tile_n, r, Jc, Jp, cost);
+    else
+        resjac_kernel<false><<<grid, RJ_TILE, RJ_SMEM, s>>>(cam, n, cam_idx, pt_idx, u, v, d, W, poses, points, cam_free,
+                                                            tile_lo, tile_n, r, Jc, Jp, cost);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_colnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, double* cn_p, double* cn_l, double* gp,
+                    double* gl, double* scal) {
+    if (lm_hi <= lm_lo) return;
+    colnorm_kernel<<<grid_for(lm_hi - lm_lo, 256, 8 * kSMs), 256, 0, s>>>(v, lm_lo, lm_hi, cn_p, cn_l, gp, gl, scal);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_jacobi_scale(cudaStream_t s, const double* cn, double* sc, long long n, int enabled) {
+    if (n <= 0) return;
+    jacobi_scale_kernel<<<int((n + 255) / 256), 256, 0, s>>>(cn, sc, n, enabled);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_jacobi_scale_cams(cudaStream_t s, const double* Bdiag, double* sc, int nf, int enabled) {
+    if (nf <= 0) return;
+    jacobi_scale_cams_kernel<<<(6 * nf + 255) / 256, 256, 0, s>>>(Bdiag, sc, nf, enabled);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_camonly_eval(cudaStream_t s, const DevView& v, const SunBlockData* suns, int n_sun,
+                         const PriorBlockData* priors, int n_prior, int apply_loss, double* r_sun, double* J_sun,
+                         double* r_pr, double* J_pr, double* cost) {
+    const int n = n_sun + n_prior;
+    if (n <= 0) return;
+    camonly_eval_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, apply_loss, r_sun, J_sun, r_pr,
+                                                    J_pr, cost);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, double* S, double* Bdiag,
+                          double* bp, double* gp, double* gl, double* scal) {
+    if (lm_hi <= lm_lo) return;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CSLAM_CUDA(cudaFuncSetAttribute(schur_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SG_SMEM)));
+        attr_done = true;
+    }
+    const int grid = grid_for(lm_hi - lm_lo, SG_WARPS, 4 * kSMs);
+    schur_generic_kernel<<<grid, SG_WARPS * 32, SG_SMEM, s>>>(v, lm_lo, lm_hi, dg, S, Bdiag, bp, gp, gl, scal);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_camonly_build(cudaStream_t s, const DevView& v, const SunBlockData* suns, int n_sun,
+                          const PriorBlockData* priors, int n_prior, double* Bdiag, double* bp, double* gp, double* scal) {
+    const int n = n_sun + n_prior;
+    if (n <= 0) return;
+    camonly_build_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, Bdiag, bp, gp, scal);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_finalize(cudaStream_t s, const DevView& v, LmDiag dg, int preconditioner, double* S, double* Bdiag,
+                     double* diag_p, double* Minv, double* scal) {
+    if (v.n_free <= 0) return;
+    finalize_kernel<<<(v.n_free + 63) / 64, 64, 0, s>>>(v, dg, preconditioner, S, Bdiag, diag_p, Minv, scal);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+constexpr int PCG_BLOCK = 192;  // multiple of 6: a 6-row block never straddles a CTA
+
+void launch_pcg_init(cudaStream_t s, const PcgBufs& B) {
+    CSLAM_CUDA(cudaMemsetAsync(B.ps, 0, PS_COUNT * sizeof(double), s));
+    const int n = 6 * B.nf;
+    pcg_init_kernel<<<(n + PCG_BLOCK - 1) / PCG_BLOCK, PCG_BLOCK, 0, s>>>(B);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_pcg_iteration(cudaStream_t s, const PcgBufs& B, int k, double q_tol, double r_tol2, int min_iters,
+                          int max_iters, int reset_period) {
+    const int n = 6 * B.nf;
+    const int grid = (n + PCG_BLOCK - 1) / PCG_BLOCK;
+    pcg_dir_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, k, q_tol, r_tol2, min_iters, max_iters);
+    pcg_clear_kernel<<<1, 1, 0, s>>>(B.ps);
+    pcg_spmv_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, B.p, B.q, 1, 1);
+    const bool reset = reset_period > 0 && (k % reset_period == 0);
+    if (reset) {
+        pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 1, 0);
+        pcg_spmv_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, B.x, B.q, 0, 0);
+        pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 1, 1);
+    } else {
+        pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 0, 1);
+    }
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_pose_plus(cudaStream_t s, const DevView& v, const double* yp, double* poses_cand, double* scal2,
+                      int count_cams) {
+    pose_plus_kernel<<<(v.n_cams + 127) / 128, 128, 0, s>>>(v, yp, poses_cand, scal2, count_cams);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_backsub(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, const double* yp,
+                    const double* poses_cand, double* points_cand, double* yl, double* scal2) {
+    if (lm_hi <= lm_lo) return;
+    backsub_kernel<<<grid_for(lm_hi - lm_lo, 128, 16 * kSMs), 128, 0, s>>>(v, lm_lo, lm_hi, dg, yp, poses_cand,
+                                                                          points_cand, yl, scal2);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_camonly_step(cudaStream_t s, const DevView& v, const SunBlockData* suns, int n_sun,
+                         const PriorBlockData* priors, int n_prior, const double* yp, const double* poses_cand,
+                         double* scal2) {
+    const int n = n_sun + n_prior;
+    if (n <= 0) return;
+    camonly_step_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, yp, poses_cand, scal2);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const double* gp_scaled,
+                     const double* gl_scaled, double* scal, int count_cams) {
+    const long long n = (long long)v.n_cams + (lm_hi - lm_lo);
+    if (n <= 0) return;
+    gradnorm_kernel<<<int((n + 255) / 256), 256, 0, s>>>(v, lm_lo, lm_hi, gp_scaled, gl_scaled, scal, count_cams);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+double measure_fp64_peak_tflops(int device) {
+    CSLAM_CUDA(cudaSetDevice(device));
+    const int blocks = kSMs * 8, threads = 256, iters = 1 << 15;
+    double* out = nullptr;
+    CSLAM_CUDA(cudaMalloc(&out, size_t(blocks) * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    CSLAM_CUDA(cudaEventCreate(&a));
+    CSLAM_CUDA(cudaEventCreate(&b));
+    fp64_peak_kernel<<<blocks, threads>>>(out, 1024);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CSLAM_CUDA(cudaEventRecord(a));
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+        CSLAM_CUDA(cudaEventRecord(b));
+        CSLAM_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        CSLAM_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 8.0 * iters * double(blocks) * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    return best;
+}
+
+}  // namespace cslam

@@ -158,6 +158,14 @@ int cslam_oracle_evaluate(cslam_oracle_problem* p, int apply_loss, double* cost,
         return CSLAM_ERR_NUMERIC;
     }
     if (cost) *cost = ev.cost;
+    // constant parameter blocks have no Jacobian columns in ceres::Problem::Evaluate
+    // (dataset_vo.cpp:62): report them as zeros
+    for (size_t i = 0; i < q.n_stereo(); ++i)
+        if (q.pose_const[q.st_cam[i]]) std::fill(&ev.Jc_st[18 * i], &ev.Jc_st[18 * i] + 18, 0.0);
+    for (size_t i = 0; i < q.suns.size(); ++i)
+        if (q.pose_const[q.suns[i].cam]) std::fill(&ev.J_sun[12 * i], &ev.J_sun[12 * i] + 12, 0.0);
+    for (size_t i = 0; i < q.priors.size(); ++i)
+        if (q.pose_const[q.priors[i].cam]) std::fill(&ev.J_pr[36 * i], &ev.J_pr[36 * i] + 36, 0.0);
     auto cp = [](double* dst, const std::vector<double>& src) {
         if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(double));
     };

@@ -1,0 +1,151 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances are BASELINE.json's: residuals/Jacobians 1e-10 relative (per block
+array, relative to its largest entry), cost/poses/landmarks after a fixed LM iteration count
+1e-6 relative."""
+import numpy as np
+import pytest
+
+from ceres_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+RJ_TOL = 1e-10
+LM_TOL = 1e-6
+FIXED = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+
+
+def rel_err(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max()) / max(float(np.abs(b).max()), 1e-300)
+
+
+def eval_pair(track, **kw):
+    pg, _, _ = syn.build_problem(track, backend="b200", **kw)
+    po, _, _ = syn.build_problem(track, backend="oracle", **kw)
+    return pg.evaluate(), po.evaluate()
+
+
+@pytest.mark.parametrize("per_obs_W", [False, True])
+@pytest.mark.parametrize("shape", [(30, 3, 4), (60, 15, 6), (100, 15, 10)])
+def test_resjac_stereo(product, per_obs_W, shape):
+    tr = syn.make_track(*shape, seed=11, per_obs_W=per_obs_W)
+    eg, eo = eval_pair(tr)
+    assert eg["r_stereo"].shape[0] == tr["obs_cam"].size > 0
+    for k in ("r_stereo", "Jpose_stereo", "Jpoint_stereo"):
+        assert rel_err(eg[k], eo[k]) < RJ_TOL, k
+    assert abs(eg["cost"] - eo["cost"]) <= 1e-12 * eo["cost"]
+    # constant first pose: its Jacobian columns are dropped
+    first = tr["obs_cam"] == 0
+    assert np.all(eg["Jpose_stereo"][first] == 0.0)
+
+
+def test_resjac_unsorted_and_ragged(product):
+    """Observation order that is not grouped by camera (tile pose staging falls back to global
+    gathers) and a size that is not a multiple of the 128-observation tile."""
+    tr = syn.make_track(60, 15, 6, seed=5)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(tr["obs_cam"].size)[:1000 + 37]
+    for k in ("obs_cam", "obs_pt", "uvd"):
+        tr[k] = np.ascontiguousarray(tr[k][perm])
+    eg, eo = eval_pair(tr)
+    for k in ("r_stereo", "Jpose_stereo", "Jpoint_stereo"):
+        assert rel_err(eg[k], eo[k]) < RJ_TOL, k
+
+
+@pytest.mark.parametrize("huber", [0.0, 0.5])
+def test_resjac_sun_and_prior(product, huber):
+    tr = syn.add_sun(syn.make_track(40, 6, 5, seed=3), sigma_deg=8.0)
+    W6 = np.diag([1e6, 1e6, 1e6, 1e3, 1e3, 1e3]).astype(float)
+    prior = (2, tr["poses_gt"][2].copy(), W6)
+    eg, eo = eval_pair(tr, sun=True, prior=prior, huber=huber)
+    for k in ("r_sun", "J_sun", "r_prior", "J_prior", "r_stereo", "Jpose_stereo"):
+        assert rel_err(eg[k], eo[k]) < RJ_TOL, k
+    assert abs(eg["cost"] - eo["cost"]) <= 1e-12 * eo["cost"]
+
+
+def solve_pair(track, iters, **kw):
+    kw = dict(FIXED, max_num_iterations=iters, **kw)
+    pg, poses_g, points_g = syn.build_problem(track, backend="b200", **kw)
+    po, poses_o, points_o = syn.build_problem(track, backend="oracle", **kw)
+    sg, so = pg.solve(), po.solve()
+    return (pg, sg, poses_g, points_g), (po, so, poses_o, points_o)
+
+
+def check_lm(g, o, tol=LM_TOL):
+    (pg, sg, poses_g, points_g), (po, so, poses_o, points_o) = g, o
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape
+    assert sg.num_iterations == so.num_iterations
+    assert sg.num_successful_steps == so.num_successful_steps
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=tol, atol=0), "cost trajectory"
+    assert np.allclose(lg[:, 6], lo[:, 6], rtol=1e-5, atol=0), "radius trajectory"
+    assert np.array_equal(lg[:, 9], lo[:, 9]), "accept/reject pattern"
+    assert abs(sg.final_cost - so.final_cost) <= tol * so.final_cost
+    assert rel_err(poses_g, poses_o) < tol
+    assert rel_err(points_g, points_o) < tol
+
+
+@pytest.mark.parametrize("shape,iters", [((30, 4, 4), 6), ((60, 15, 6), 5), ((100, 15, 10), 5)])
+def test_lm_full_batch_stereo_exact(product, shape, iters):
+    """dataset_vo --window 0 on a C1-style track: first pose constant, exact Schur solve."""
+    tr = syn.make_track(*shape, seed=21)
+    g, o = solve_pair(tr, iters)
+    check_lm(g, o)
+    assert g[1].final_cost < 0.1 * g[1].initial_cost
+
+
+def test_lm_window2(product):
+    """dataset_vo --window 2: one free pose, ~150 points."""
+    tr = syn.make_track(100, 15, 10, seed=42)
+    w = syn.window_of(tr, 10, 12)
+    g, o = solve_pair(w, 6)
+    check_lm(g, o)
+
+
+def test_lm_sun_prior_window(product):
+    """dataset_vo_sun window: no constant pose, pose prior on the first pose, sun blocks with
+    Huber loss (dataset_vo_sun.cpp:75-124)."""
+    tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42, per_obs_W=True))
+    w = syn.window_of(tr, 20, 22)
+    W6 = np.eye(6) * 1e6                       # Sigma_0 = 1e-12 I (dataset_problem_sun.cpp:80)
+    prior = (0, w["poses"][0].copy(), W6)
+    g, o = solve_pair(w, 6, sun=True, prior=prior, huber=1.0, hold_first=False)
+    check_lm(g, o)
+
+
+def test_lm_iterative_schur(product):
+    """ITERATIVE_SCHUR-equivalent: both sides run the same block-Jacobi PCG rule (eta = 0.1), so
+    the inexact-Newton iterates agree.  While the inner solves are short (<= ~20 CG iterations)
+    the agreement is at rounding level; once a solve runs ~50-90 CG iterations, finite-precision
+    CG loses conjugacy and the iterate depends on the summation order (atomics on the GPU), so
+    the 5-iteration comparison uses 1e-4 on the parameters (the cost still agrees to 1e-6)."""
+    tr = syn.make_track(80, 15, 8, seed=9)
+    for pre in (0, 1):
+        g, o = solve_pair(tr, 3, linear_solver=1, preconditioner=pre)
+        lg, lo = g[0].iteration_log(), o[0].iteration_log()
+        assert np.array_equal(lg[:, 7], lo[:, 7]), "CG iterations per LM step"
+        check_lm(g, o)
+        g, o = solve_pair(tr, 5, linear_solver=1, preconditioner=pre)
+        lg, lo = g[0].iteration_log(), o[0].iteration_log()
+        assert np.array_equal(lg[:, 7], lo[:, 7]), "CG iterations per LM step"
+        assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0)
+        assert rel_err(g[2], o[2]) < 1e-4 and rel_err(g[3], o[3]) < 1e-4
+
+
+def test_rejected_step_path(product):
+    """A tiny initial radius and large perturbation forces rejected / clamped steps; the radius
+    bookkeeping must follow the oracle."""
+    tr = syn.make_track(60, 10, 6, seed=4, pose_sigma=(0.3, 0.08), point_sigma=0.5)
+    g, o = solve_pair(tr, 8, initial_trust_region_radius=1e-2)
+    check_lm(g, o, tol=1e-5)
+
+
+def test_errors(product):
+    from ceres_slam_b200.problem import BAProblem, CslamError
+    p = BAProblem("b200")
+    p.set_camera(1, 1, 0, 0, 1)
+    p.set_poses(np.zeros((2, 12)))
+    p.set_points(np.zeros((3, 3)))
+    with pytest.raises(CslamError):
+        p.add_stereo([5], [0], np.zeros((1, 3)), np.eye(3).reshape(9))
+    with pytest.raises(CslamError):
+        p.lm_begin()
