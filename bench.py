@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the bundle-adjustment hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA back end
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (the oracle restatement of
+                                                             # the reference's Ceres path)
+
+A "step" is one Levenberg-Marquardt iteration of the hot path: fused residual/Jacobian + Schur
+elimination, block-Jacobi PCG on the reduced camera system, back-substitution + Plus + candidate
+cost.  Workload at every N: BASELINE.json config 5, the large full-batch stereo BA (20 k poses x
+2 M landmarks x 20 M observations, synthetic), landmarks sharded over the N GPUs with one NCCL
+all-reduce of [S | g] per Schur build ("strong" scaling: the total problem is fixed).
+One JSON line on stdout from rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ceres_slam_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "BA LM iterations/s (full-batch stereo BA, C5: 20k poses x 2M landmarks x 20M obs)"
+LM_OPTS = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0,
+               linear_solver=1, preconditioner=1, eta=0.1, max_linear_solver_iterations=500)
+
+
+def c5_track(scale=1.0, seed=42):
+    """Config 5 at `scale` (1.0 = 20 k poses, 100 new landmarks per frame tracked for 10 frames)."""
+    n_poses = max(40, int(round(20000 * scale)))
+    return syn.make_track(n_poses, 100, 10, seed=seed)
+
+
+def schur_algorithmic_bytes(n_obs, n_lm, n_cam, nnzU):
+    # 32 n_o + 24 n_l + 96 n_c + 288 nnzU + 48 n_c
+    return 32 * n_obs + 24 * n_lm + 96 * n_cam + 288 * nnzU + 48 * n_cam
+
+
+def schur_algorithmic_flops(n_lm, L):
+    # n_l (618 L + 108 L (L + 1) + 50)
+    return n_lm * (618 * L + 108 * L * (L + 1) + 50)
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_oracle_run(steps, warmup, threads, sample_scale):
+    """The reference's path on the host cores: the oracle restatement (Jet autodiff functors +
+    Ceres-semantics LM + Schur + the same PCG rule), on a bounded sample of config 5."""
+    tr = c5_track(sample_scale)
+    opts = dict(LM_OPTS, num_threads=threads)
+    # warm-up + timed in separate solves from the same start (the oracle has no resume entry)
+    t_w = 0.0
+    if warmup > 0:
+        p, _, _ = syn.build_problem(tr, backend="oracle", max_num_iterations=warmup, **opts)
+        t0 = time.perf_counter()
+        p.solve()
+        t_w = time.perf_counter() - t0
+    p, _, _ = syn.build_problem(tr, backend="oracle", max_num_iterations=warmup + steps, **opts)
+    t0 = time.perf_counter()
+    s = p.solve()
+    t_all = time.perf_counter() - t0
+    iters = max(1, s.num_iterations - warmup)
+    t_steps = max(1e-9, t_all - t_w)
+    n_obs = int(tr["obs_cam"].size)
+    return dict(ms_per_iter_sample=1e3 * t_steps / iters, n_obs_sample=n_obs, iters=iters,
+                final_cost=s.final_cost)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    scale = args.cpu_scale
+    full_obs = int(c5_obs_count())
+    r = cpu_oracle_run(args.steps, min(args.warmup, 1), threads, scale)
+    # LM iterations/s the CPU path would sustain on the full workload (cost is linear in n_obs)
+    ms_full = r["ms_per_iter_sample"] * full_obs / r["n_obs_sample"]
+    value = 1e3 / ms_full
+    sample = (f"config 5 at {scale:g} scale ({r['n_obs_sample']} observations), {r['iters']} LM iterations, "
+              f"{threads} threads; per-iteration time scaled by n_obs to the full 20 M-observation problem")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "LM iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "LM iter/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "LM iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "obs_per_s": value * full_obs,
+    }
+    print(json.dumps(line))
+
+
+def c5_obs_count():
+    return 19_991 * 100 * 10  # n_starts * new_per_frame * track_len before visibility filtering
+
+
+def workload_config(n_gpus):
+    return {"workload": "C5 large full-batch stereo BA: 20k poses x 2M landmarks x 20M observations "
+                        "(synthetic loop track, 100 new landmarks/frame tracked 10 frames)",
+            "lm": "Ceres-semantics LM, ITERATIVE_SCHUR-equivalent (block-Jacobi PCG, eta=0.1), first pose constant",
+            "sharding": f"landmarks over {n_gpus} GPU(s), NCCL all-reduce of [S|g]" if n_gpus > 1 else "single GPU",
+            "l2": "inputs (640 MB of observations) larger than the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="workload scale (1.0 = config 5)")
+    ap.add_argument("--cpu-scale", type=float, default=0.02, help="sample of config 5 timed on the CPU")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ceres_slam_b200 import capi
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the cslam_b200 back end has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.load_product()
+    W = max(3, args.warmup)
+    K = args.steps
+
+    t0 = time.perf_counter()
+    tr = c5_track(args.scale)
+    n_obs, n_lm, n_cam = int(tr["obs_cam"].size), int(tr["n_points"]), int(tr["n_poses"])
+    gen_s = time.perf_counter() - t0
+
+    def make_problem(**extra):
+        p, poses, points = syn.build_problem(tr, backend="b200", device=local, **dict(LM_OPTS, **extra))
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_uint8 * 128)()
+                assert lib.comm_unique_id(buf) == 0
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            p.attach_comm(world, rank, uid.cpu().numpy())
+        return p, poses, points
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value) ------------------------------------------------------
+    p, _, _ = make_problem(max_num_iterations=10 ** 6)
+    stream = torch.cuda.current_stream()
+    p.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    p.upload()
+    upload_s = time.perf_counter() - t0
+    p.lm_begin()
+    p.lm_iterate(W, ignore_convergence=True)
+    launches0 = C.c_uint64(0)
+    lib.get_launch_count(C.byref(launches0))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    s = p.lm_iterate(K, ignore_convergence=True)
+    ev1.record(stream)
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches1 = C.c_uint64(0)
+    lib.get_launch_count(C.byref(launches1))
+    log = p.iteration_log()
+    value = K / (ms * 1e-3)
+
+    # ---- per-kernel-class profile and roofline of the dominant kernel (separate short run) ----
+    p.set_options(profile_kernels=1)
+    p.reset_profile()
+    p.lm_iterate(3, ignore_convergence=True)
+    prof = p.profile()
+    p.set_options(profile_kernels=0)
+    nf, nnz = C.c_int(0), C.c_int(0)
+    lib.get_reduced_sizes(p._h, C.byref(nf), C.byref(nnz))
+    schur_ms = max_over_ranks(prof["schur"][0] / max(1, prof["schur"][1]))
+    peak, peak_src = measured_peaks()
+    alg_bytes = schur_algorithmic_bytes(n_obs // world, n_lm // world, n_cam, nnz.value)
+    achieved = alg_bytes / (schur_ms * 1e-3) / 1e9
+    L = n_obs / max(1, n_lm)
+    alg_flops = schur_algorithmic_flops(n_lm // world, L)
+    fp64 = C.c_double(0)
+    lib.measure_fp64_peak(local, C.byref(fp64))
+    roofline = {"kernel": "schur_build (fused residual/Jacobian + Schur elimination)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": schur_ms}
+    roofline_fp64 = {"kernel": "schur_build", "bound": "fp64", "achieved": alg_flops / (schur_ms * 1e-3) / 1e12,
+                     "peak": fp64.value, "unit": "TFLOP/s", "frac": alg_flops / (schur_ms * 1e-3) / 1e12 / max(fp64.value, 1e-9),
+                     "peak_source": "measured in this run (register-resident DFMA chains, all SMs)",
+                     "algorithmic_flops_per_launch": alg_flops}
+    step_profile = {k: {"ms": v[0] / max(1, v[1]), "launches": v[1]} for k, v in prof.items() if v[1]}
+
+    # ---- materialised residual + Jacobian throughput (K1) -------------------------------------
+    resjac = None
+    if rank == 0:
+        rj_ms = p.time_resjac(5)
+        resjac = {"obs_per_s": n_obs / (rj_ms * 1e-3), "ms": rj_ms, "bytes_per_obs": 272,
+                  "achieved_gbs": 272 * n_obs / (rj_ms * 1e-3) / 1e9,
+                  "frac_of_hbm": 272 * n_obs / (rj_ms * 1e-3) / 1e9 / peak}
+    p.close()
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pe, poses_e, points_e = make_problem(max_num_iterations=K)
+        barrier()
+        t0 = time.perf_counter()
+        se = pe.solve()
+        torch.cuda.synchronize()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        h2d = (n_obs // world) * (4 + 24) + 4 * (n_lm // world + 1) + 96 * n_cam + 24 * (n_lm // world)
+        d2h = 96 * n_cam + 24 * (n_lm // world)
+        e2e = {"value": se.num_iterations / wall, "unit": "LM iter/s", "h2d_bytes_per_step": h2d / max(1, K),
+               "d2h_bytes_per_step": d2h / max(1, K), "wall_s": wall, "iterations": se.num_iterations,
+               "note": "one cslam_solve call from host arrays: structure analysis + H2D + K LM iterations + D2H"}
+        pe.close()
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r = cpu_oracle_run(3, 1, threads, args.cpu_scale)
+        ms_full = r["ms_per_iter_sample"] * n_obs / r["n_obs_sample"]
+        cpu = {"value": 1e3 / ms_full, "unit": "LM iter/s", "cores": threads, "kind": "port",
+               "sample": f"config 5 at {args.cpu_scale:g} scale ({r['n_obs_sample']} observations), "
+                         f"{r['iters']} LM iterations, scaled by n_obs to the full problem",
+               "ms_per_iter_sample": r["ms_per_iter_sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "LM iter/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "obs_per_s": value * n_obs, "n_obs": n_obs, "n_landmarks": n_lm, "n_poses": n_cam,
+            "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
+            "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
+            "resjac": resjac, "step_profile_ms": step_profile,
+            "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
+                   "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},
+            "setup_s": {"generate": gen_s, "upload_and_structure": upload_s},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,7 @@ _PRODUCT_ONLY = {
     "time_resjac": (C.c_int, [_h, C.c_int, _dp]),
     "time_schur": (C.c_int, [_h, C.c_int, _dp]),
     "measure_fp64_peak": (C.c_int, [C.c_int, _dp]),
+    "get_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "comm_unique_id": (C.c_int, [_u8p]),
     "attach_comm": (C.c_int, [_h, C.c_int, C.c_int, _u8p]),
 }

@@ -267,6 +267,12 @@ cslam_status cslam_measure_fp64_peak(int device, double* tflops) {
     }
 }
 
+cslam_status cslam_get_launch_count(uint64_t* count) {
+    if (!count) return CSLAM_ERR_INVALID;
+    *count = cslam::g_kernel_launches.load();
+    return CSLAM_OK;
+}
+
 cslam_status cslam_comm_unique_id(uint8_t id[128]) {
     try {
         cslam::comm_unique_id(id);

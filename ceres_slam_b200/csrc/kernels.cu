@@ -9,15 +9,18 @@
 //   pose_plus / backsub  K4  Plus, back-substitution, model cost change, candidate cost
 //
 // Everything is FP64, no fast-math.  Reference semantics: SURVEY.md App. A / App. B.
-#include <cooperative_groups.h>
+#include <atomic>
 
 #include "kernels.cuh"
 
 namespace cslam {
 
+std::atomic<unsigned long long> g_kernel_launches{0};
+
 namespace {
 
 constexpr int kSMs = 148;
+#define CSLAM_LAUNCHED(n) g_kernel_launches.fetch_add((n), std::memory_order_relaxed)
 
 __device__ __forceinline__ const double* obs_W_ptr(const DevView& v, long long e) {
     return v.W_per_obs ? v.obs_W + 9 * e : v.obs_W;
@@ -959,6 +962,7 @@ void launch_resjac(cudaStream_t s, const CameraIntrinsics& cam, long long n, con
     else
         resjac_kernel<false><<<grid, RJ_TILE, RJ_SMEM, s>>>(cam, n, cam_idx, pt_idx, u, v, d, W, poses, points, cam_free,
                                                             tile_lo, tile_n, r, Jc, Jp, cost);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -966,18 +970,21 @@ void launch_colnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, doub
                     double* gl, double* scal) {
     if (lm_hi <= lm_lo) return;
     colnorm_kernel<<<grid_for(lm_hi - lm_lo, 256, 8 * kSMs), 256, 0, s>>>(v, lm_lo, lm_hi, cn_p, cn_l, gp, gl, scal);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
 void launch_jacobi_scale(cudaStream_t s, const double* cn, double* sc, long long n, int enabled) {
     if (n <= 0) return;
     jacobi_scale_kernel<<<int((n + 255) / 256), 256, 0, s>>>(cn, sc, n, enabled);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
 void launch_jacobi_scale_cams(cudaStream_t s, const double* Bdiag, double* sc, int nf, int enabled) {
     if (nf <= 0) return;
     jacobi_scale_cams_kernel<<<(6 * nf + 255) / 256, 256, 0, s>>>(Bdiag, sc, nf, enabled);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -988,6 +995,7 @@ void launch_camonly_eval(cudaStream_t s, const DevView& v, const SunBlockData* s
     if (n <= 0) return;
     camonly_eval_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, apply_loss, r_sun, J_sun, r_pr,
                                                     J_pr, cost);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1001,6 +1009,7 @@ void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi
     }
     const int grid = grid_for(lm_hi - lm_lo, SG_WARPS, 4 * kSMs);
     schur_generic_kernel<<<grid, SG_WARPS * 32, SG_SMEM, s>>>(v, lm_lo, lm_hi, dg, S, Bdiag, bp, gp, gl, scal);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1009,6 +1018,7 @@ void launch_camonly_build(cudaStream_t s, const DevView& v, const SunBlockData* 
     const int n = n_sun + n_prior;
     if (n <= 0) return;
     camonly_build_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, Bdiag, bp, gp, scal);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1016,6 +1026,7 @@ void launch_finalize(cudaStream_t s, const DevView& v, LmDiag dg, int preconditi
                      double* diag_p, double* Minv, double* scal) {
     if (v.n_free <= 0) return;
     finalize_kernel<<<(v.n_free + 63) / 64, 64, 0, s>>>(v, dg, preconditioner, S, Bdiag, diag_p, Minv, scal);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1025,6 +1036,7 @@ void launch_pcg_init(cudaStream_t s, const PcgBufs& B) {
     CSLAM_CUDA(cudaMemsetAsync(B.ps, 0, PS_COUNT * sizeof(double), s));
     const int n = 6 * B.nf;
     pcg_init_kernel<<<(n + PCG_BLOCK - 1) / PCG_BLOCK, PCG_BLOCK, 0, s>>>(B);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1040,15 +1052,18 @@ void launch_pcg_iteration(cudaStream_t s, const PcgBufs& B, int k, double q_tol,
         pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 1, 0);
         pcg_spmv_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, B.x, B.q, 0, 0);
         pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 1, 1);
+        CSLAM_LAUNCHED(2);
     } else {
         pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 0, 1);
     }
+    CSLAM_LAUNCHED(4);
     CSLAM_CUDA(cudaGetLastError());
 }
 
 void launch_pose_plus(cudaStream_t s, const DevView& v, const double* yp, double* poses_cand, double* scal2,
                       int count_cams) {
     pose_plus_kernel<<<(v.n_cams + 127) / 128, 128, 0, s>>>(v, yp, poses_cand, scal2, count_cams);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1057,6 +1072,7 @@ void launch_backsub(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDi
     if (lm_hi <= lm_lo) return;
     backsub_kernel<<<grid_for(lm_hi - lm_lo, 128, 16 * kSMs), 128, 0, s>>>(v, lm_lo, lm_hi, dg, yp, poses_cand,
                                                                           points_cand, yl, scal2);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1066,6 +1082,7 @@ void launch_camonly_step(cudaStream_t s, const DevView& v, const SunBlockData* s
     const int n = n_sun + n_prior;
     if (n <= 0) return;
     camonly_step_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, yp, poses_cand, scal2);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 
@@ -1074,6 +1091,7 @@ void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, con
     const long long n = (long long)v.n_cams + (lm_hi - lm_lo);
     if (n <= 0) return;
     gradnorm_kernel<<<int((n + 255) / 256), 256, 0, s>>>(v, lm_lo, lm_hi, gp_scaled, gl_scaled, scal, count_cams);
+    CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
 

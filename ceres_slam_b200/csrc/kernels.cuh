@@ -1,5 +1,7 @@
 // Kernel launch surface of the cslam_b200 back end.  Every launcher enqueues on `s` and returns.
 #pragma once
+#include <atomic>
+
 #include "engine.h"
 
 namespace cslam {
@@ -60,5 +62,6 @@ void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, con
                      const double* gl_scaled, double* scal, int count_cams);
 
 double measure_fp64_peak_tflops(int device);
+extern std::atomic<unsigned long long> g_kernel_launches;  // every kernel this library launches
 
 }  // namespace cslam

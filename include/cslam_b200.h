@@ -192,6 +192,9 @@ cslam_status cslam_time_schur(cslam_problem* p, int reps, double* ms_per_launch)
 /* FP64 FMA microbenchmark (register-resident DFMA chains on every SM): TFLOP/s. */
 cslam_status cslam_measure_fp64_peak(int device, double* tflops);
 
+/* Number of kernels this library has launched in this process (all handles). */
+cslam_status cslam_get_launch_count(uint64_t* count);
+
 /* Multi-GPU (config 5): every rank holds all poses and its own shard of landmarks and
  * observations; each Schur build is followed by one all-reduce of [S | rhs | scalars].
  * The 128-byte id comes from rank 0 and is distributed by the launcher (torch.distributed). */
