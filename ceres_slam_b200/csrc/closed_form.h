@@ -72,6 +72,36 @@ CSLAM_HD void stereo_block(const CameraIntrinsics& c, const double* pose, const 
     }
 }
 
+// Same block, residual and point Jacobian only (first pass of the Schur elimination, where only
+// V = sum Jp^T Jp and g = sum Jp^T r are needed).
+CSLAM_HD void stereo_block_point(const CameraIntrinsics& c, const double* pose, const double* p,
+                                 double u, double v, double d, const double* W, double* r,
+                                 double* Jp) {
+    double pc[3];
+    transform_point(pose, p, pc);
+    const double iz = 1.0 / pc[2];
+    const double e0 = c.fu * pc[0] * iz + c.cu - u;
+    const double e1 = c.fv * pc[1] * iz + c.cv - v;
+    const double e2 = c.fu * c.b * iz - d;
+    r[0] = W[0] * e0 + W[1] * e1 + W[2] * e2;
+    r[1] = W[3] * e0 + W[4] * e1 + W[5] * e2;
+    r[2] = W[6] * e0 + W[7] * e1 + W[8] * e2;
+    const double iz2 = iz * iz;
+    const double p00 = c.fu * iz, p02 = -c.fu * pc[0] * iz2;
+    const double p11 = c.fv * iz, p12 = -c.fv * pc[1] * iz2;
+    const double p22 = -c.fu * c.b * iz2;
+    const double* R = pose + 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double a0 = W[3 * i] * p00;
+        const double a1 = W[3 * i + 1] * p11;
+        const double a2 = W[3 * i] * p02 + W[3 * i + 1] * p12 + W[3 * i + 2] * p22;
+        Jp[3 * i + 0] = a0 * R[0] + a1 * R[3] + a2 * R[6];
+        Jp[3 * i + 1] = a0 * R[1] + a1 * R[4] + a2 * R[7];
+        Jp[3 * i + 2] = a0 * R[2] + a1 * R[5] + a2 * R[8];
+    }
+}
+
 // utils.hpp:28-31
 CSLAM_HD double t_fabs(double a) { return (a >= 0.0) ? a : -a; }
 

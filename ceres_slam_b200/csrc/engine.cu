@@ -80,7 +80,9 @@ DevView Engine::view(const double* poses, const double* points) const {
     v.poses = poses;
     v.points = points;
     v.cam_free = d_cam_free.p;
-    v.lm_ptr = d_lm_ptr.p;
+    v.lm_base = d_lm_base.p;
+    v.lm_stride = d_lm_stride.p;
+    v.lm_cnt = d_lm_cnt.p;
     v.obs_cam = d_obs_cam.p;
     v.obs_u = d_obs_u.p;
     v.obs_v = d_obs_v.p;
@@ -206,6 +208,21 @@ void Engine::build_structure() {
         nnzU = int(s_col_h.size());
     }
 
+    // every landmark's observations in ascending camera order (canonical camera list)
+    for (uint32_t a = 0; a < n_active; ++a) {
+        uint32_t* first = all_obs.data() + all_ptr[a];
+        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
+        for (uint32_t x = 1; x < len; ++x) {
+            const uint32_t key = first[x];
+            uint32_t y = x;
+            while (y > 0 && st_cam[first[y - 1]] > st_cam[key]) {
+                first[y] = first[y - 1];
+                --y;
+            }
+            first[y] = key;
+        }
+    }
+
     // ---- this rank's shard: contiguous landmark range balanced by observation count ----
     uint32_t lo = 0, hi = n_active;
     if (n_ranks > 1) {
@@ -216,15 +233,144 @@ void Engine::build_structure() {
         lo = std::min(cut(rank), n_active);
         hi = rank == n_ranks - 1 ? n_active : std::min(cut(rank + 1), n_active);
     }
-    lm_lo = 0;
     n_lm = int(hi - lo);
+    lm_lo = 0;
     lm_hi = n_lm;
-    lm_user_h.assign(all_lm.begin() + lo, all_lm.begin() + hi);
-    lm_ptr_h.resize(size_t(n_lm) + 1);
-    const uint32_t base = all_ptr[lo];
-    for (int a = 0; a <= n_lm; ++a) lm_ptr_h[a] = all_ptr[lo + a] - base;
-    n_obs = lm_ptr_h[n_lm];
-    obs_user_h.assign(all_obs.begin() + base, all_obs.begin() + base + n_obs);
+    n_obs = (long long)all_ptr[hi] - (long long)all_ptr[lo];
+
+    // ---- group landmarks with identical camera lists (grouped Schur kernel) ----
+    struct Key {
+        uint64_t k1, hash;
+        uint32_t lm;
+    };
+    std::vector<Key> keys;
+    std::vector<uint32_t> rest;
+    keys.reserve(n_lm);
+    for (uint32_t a = lo; a < hi; ++a) {
+        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
+        bool ok = opt.schur_path != 1 && len <= uint32_t(kGroupLmax);
+        uint64_t h = 1469598103934665603ull;
+        uint32_t prev = 0xffffffffu;
+        for (uint32_t e = all_ptr[a]; e < all_ptr[a + 1]; ++e) {
+            const uint32_t c = st_cam[all_obs[e]];
+            if (c == prev) ok = false;  // the same camera twice: generic kernel only
+            prev = c;
+            h = (h ^ c) * 1099511628211ull;
+        }
+        if (ok)
+            keys.push_back(Key{(uint64_t(st_cam[all_obs[all_ptr[a]]]) << 8) | len, h, a});
+        else
+            rest.push_back(a);
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
+        if (x.k1 != y.k1) return x.k1 < y.k1;
+        if (x.hash != y.hash) return x.hash < y.hash;
+        return x.lm < y.lm;
+    });
+    auto same_cams = [&](uint32_t a, uint32_t b) {
+        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
+        for (uint32_t k = 0; k < len; ++k)
+            if (st_cam[all_obs[all_ptr[a] + k]] != st_cam[all_obs[all_ptr[b] + k]]) return false;
+        return true;
+    };
+    const size_t min_group = opt.schur_path == 2 ? 1 : 4;
+    g_L_h.clear(); g_G_h.clear(); g_lm0_h.clear(); g_obs0_h.clear(); g_off_h.clear(); g_cams_h.clear();
+    g_blk_off_h.clear(); g_blk_h.clear(); item_group_h.clear(); item_j0_h.clear(); item_n_h.clear();
+    lm_user_h.clear(); lm_base_h.clear(); lm_stride_h.clear(); lm_cnt_h.clear();
+    lm_user_h.reserve(n_lm); lm_base_h.reserve(n_lm); lm_stride_h.reserve(n_lm); lm_cnt_h.reserve(n_lm);
+    obs_user_h.assign(size_t(n_obs), 0);
+    uint32_t obs_cursor = 0;
+    std::vector<std::pair<int, int>> items_small, items_large;  // (group, j0)
+    for (size_t x = 0; x < keys.size();) {
+        size_t y = x + 1;
+        while (y < keys.size() && keys[y].k1 == keys[x].k1 && keys[y].hash == keys[x].hash && same_cams(keys[x].lm, keys[y].lm)) ++y;
+        const size_t G = y - x;
+        if (G < min_group) {
+            for (size_t z = x; z < y; ++z) rest.push_back(keys[z].lm);
+            x = y;
+            continue;
+        }
+        const uint32_t a0 = keys[x].lm;
+        const int L = int(all_ptr[a0 + 1] - all_ptr[a0]);
+        const int gid = int(g_L_h.size());
+        g_L_h.push_back(L);
+        g_G_h.push_back(int(G));
+        g_lm0_h.push_back(int(lm_user_h.size()));
+        g_obs0_h.push_back(obs_cursor);
+        g_off_h.push_back(int(g_cams_h.size()));
+        g_blk_off_h.push_back(int(g_blk_h.size()));
+        int fr[kGroupLmax];
+        for (int i = 0; i < L; ++i) {
+            const int c = int(st_cam[all_obs[all_ptr[a0] + i]]);
+            g_cams_h.push_back(c);
+            fr[i] = cam_free_h[c];
+        }
+        for (int i = 0; i < L; ++i)
+            for (int k = i; k < L; ++k) {
+                int e = -1;
+                if (fr[i] >= 0 && fr[k] >= 0) {
+                    auto b0 = s_col_h.begin() + s_rowptr_h[fr[i]], b1 = s_col_h.begin() + s_rowptr_h[fr[i] + 1];
+                    e = int(std::lower_bound(b0, b1, fr[k]) - s_col_h.begin());
+                }
+                g_blk_h.push_back(e);
+            }
+        for (size_t z = x; z < y; ++z) {
+            const uint32_t a = keys[z].lm;
+            const uint32_t jl = uint32_t(z - x);
+            lm_user_h.push_back(all_lm[a]);
+            lm_base_h.push_back(obs_cursor + jl);
+            lm_stride_h.push_back(uint32_t(G));
+            lm_cnt_h.push_back(uint32_t(L));
+            for (int i = 0; i < L; ++i) obs_user_h[size_t(obs_cursor) + size_t(i) * G + jl] = all_obs[all_ptr[a] + i];
+        }
+        obs_cursor += uint32_t(G) * uint32_t(L);
+        for (size_t j0 = 0; j0 < G; j0 += kItemMax) (L <= 10 ? items_small : items_large).push_back({gid, int(j0)});
+        max_group_L = std::max(max_group_L, L);
+        x = y;
+    }
+    n_lm_grouped = int(lm_user_h.size());
+    n_items_small = int(items_small.size());
+    for (auto* lst : {&items_small, &items_large})
+        for (auto& it : *lst) {
+            item_group_h.push_back(it.first);
+            item_j0_h.push_back(it.second);
+            item_n_h.push_back(std::min(kItemMax, g_G_h[it.first] - it.second));
+        }
+    // the remaining landmarks, landmark-major, in first-camera order
+    std::sort(rest.begin(), rest.end());
+    for (uint32_t a : rest) {
+        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
+        lm_user_h.push_back(all_lm[a]);
+        lm_base_h.push_back(obs_cursor);
+        lm_stride_h.push_back(1);
+        lm_cnt_h.push_back(len);
+        for (uint32_t k = 0; k < len; ++k) obs_user_h[size_t(obs_cursor) + k] = all_obs[all_ptr[a] + k];
+        obs_cursor += len;
+    }
+}
+
+GroupView Engine::group_view() const {
+    GroupView g;
+    g.n_items = int(item_group_h.size());
+    g.item_group = d_item_group.p;
+    g.item_j0 = d_item_j0.p;
+    g.item_n = d_item_n.p;
+    g.g_L = d_g_L.p;
+    g.g_G = d_g_G.p;
+    g.g_lm0 = d_g_lm0.p;
+    g.g_obs0 = d_g_obs0.p;
+    g.g_off = d_g_off.p;
+    g.g_cams = d_g_cams.p;
+    g.g_blk_off = d_g_blk_off.p;
+    g.g_blk = d_g_blk.p;
+    return g;
+}
+
+void Engine::launch_schur(const DevView& v, const LmDiag& dg) {
+    if (!item_group_h.empty())
+        launch_schur_grouped(stream, v, group_view(), n_items_small, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+    if (n_lm > n_lm_grouped)
+        launch_schur_generic(stream, v, n_lm_grouped, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
 }
 
 void Engine::upload() {
@@ -246,7 +392,24 @@ void Engine::upload() {
     for (int a = 0; a < n_lm; ++a) std::memcpy(&pts[3 * size_t(a)], h_points + 3 * size_t(lm_user_h[a]), 24);
 
     d_cam_free.upload(cam_free_h, stream);
-    d_lm_ptr.upload(lm_ptr_h, stream);
+    auto up_i = [&](DBuf<int>& d, const std::vector<int>& h) { d.upload(h.empty() ? std::vector<int>(1, 0) : h, stream); };
+    auto up_u = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) {
+        d.upload(h.empty() ? std::vector<uint32_t>(1, 0) : h, stream);
+    };
+    up_u(d_lm_base, lm_base_h);
+    up_u(d_lm_stride, lm_stride_h);
+    up_u(d_lm_cnt, lm_cnt_h);
+    up_i(d_item_group, item_group_h);
+    up_i(d_item_j0, item_j0_h);
+    up_i(d_item_n, item_n_h);
+    up_i(d_g_L, g_L_h);
+    up_i(d_g_G, g_G_h);
+    up_i(d_g_lm0, g_lm0_h);
+    up_u(d_g_obs0, g_obs0_h);
+    up_i(d_g_off, g_off_h);
+    up_i(d_g_cams, g_cams_h);
+    up_i(d_g_blk_off, g_blk_off_h);
+    up_i(d_g_blk, g_blk_h);
     d_obs_cam.upload(ocam, stream);
     d_obs_u.upload(ou, stream);
     d_obs_v.upload(ov, stream);
@@ -272,27 +435,25 @@ void Engine::upload() {
     d_yl.alloc(3 * size_t(std::max(n_lm, 1)));
     d_s_rowptr.upload(s_rowptr_h, stream);
     d_s_col.upload(s_col_h.empty() ? std::vector<int>(1, 0) : s_col_h, stream);
-    // transposed (strictly lower) lists for the symmetric SpMV
+    // mirrored lists for the symmetric SpMV: row b lists (a, block) for every stored upper block
+    // (a, b) with a < b, i.e. the blocks that act on it transposed
     {
-        std::vector<int> ltp(size_t(n_free) + 1, 0), ltc, ltb;
+        std::vector<int> ep(size_t(n_free) + 1, 0);
         for (int a = 0; a < n_free; ++a)
             for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e)
-                if (s_col_h[e] != a) ltp[s_col_h[e] + 1]++;
-        for (int a = 0; a < n_free; ++a) ltp[a + 1] += ltp[a];
-        ltc.resize(std::max(1, ltp[n_free]));
-        ltb.resize(std::max(1, ltp[n_free]));
-        std::vector<int> fill(ltp.begin(), ltp.end() - 1);
+                if (s_col_h[e] != a) ep[s_col_h[e] + 1]++;
+        for (int a = 0; a < n_free; ++a) ep[a + 1] += ep[a];
+        std::vector<int> ecb(2 * size_t(std::max(1, ep[n_free])));
+        std::vector<int> fill(ep.begin(), ep.end() - 1);
         for (int a = 0; a < n_free; ++a)
             for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) {
                 const int b = s_col_h[e];
                 if (b == a) continue;
-                ltc[fill[b]] = a;
-                ltb[fill[b]] = e;
-                fill[b]++;
+                ecb[2 * size_t(fill[b])] = a;
+                ecb[2 * size_t(fill[b]++) + 1] = e;
             }
-        d_lt_rowptr.upload(ltp, stream);
-        d_lt_col.upload(ltc, stream);
-        d_lt_blk.upload(ltb, stream);
+        d_lt_rowptr.upload(ep, stream);
+        d_lt_col.upload(ecb, stream);
     }
     red_count = 36 * size_t(nnzU) + 36 * size_t(n_free) + 6 * size_t(n_free) + 6 * size_t(n_free) + SC_COUNT;
     d_red.alloc(red_count);
@@ -309,6 +470,8 @@ void Engine::upload() {
     d_pz.alloc(nv);
     d_pp.alloc(nv);
     d_pq.alloc(nv);
+    d_pp2.alloc(nv);
+    d_prec.alloc(16);
     d_pscal.alloc(PS_COUNT);
     d_scal2.alloc(SC_COUNT);
     if (!suns.empty()) d_suns.upload(suns, stream);
@@ -361,7 +524,7 @@ void Engine::schur_pass() {
     DevView v = view(d_poses.p, d_points.p);
     prof_begin(CSLAM_K_SCHUR);
     d_red.zero(stream);
-    launch_schur_generic(stream, v, 0, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+    launch_schur(v, dg);
     if (rank == 0)
         launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
                              d_scal);
@@ -394,9 +557,8 @@ void Engine::run_pcg(int* iters, bool* ok) {
     PcgBufs B;
     B.rowptr = d_s_rowptr.p;
     B.col = d_s_col.p;
-    B.lt_rowptr = d_lt_rowptr.p;
-    B.lt_col = d_lt_col.p;
-    B.lt_blk = d_lt_blk.p;
+    B.ent_ptr = d_lt_rowptr.p;
+    B.ent_cb = d_lt_col.p;
     B.S = d_S;
     B.Minv = d_Minv.p;
     B.b = d_bp;
@@ -426,23 +588,9 @@ void Engine::run_pcg(int* iters, bool* ok) {
         min_it = opt.min_linear_solver_iterations;
     }
     prof_begin(CSLAM_K_PCG);
-    launch_pcg_init(stream, B);
+    launch_pcg_persistent(stream, B, d_pp2.p, d_prec.p, q_tol, r_tol, min_it, max_it, 10);
     double ps[PS_COUNT];
     read_scalars(d_pscal.p, ps, PS_COUNT);
-    const double r_tol2 = r_tol < 0 ? -1.0 : r_tol * r_tol * ps[PS_NORMB2];
-    const int poll = 8;
-    int k = 1;
-    bool done = false;
-    while (!done) {
-        for (int c = 0; c < poll && k <= max_it; ++c, ++k)
-            launch_pcg_iteration(stream, B, k, q_tol, r_tol2, min_it, max_it, 10);
-        if (k > max_it) {
-            // evaluate the termination rule of the last iteration (sets DONE: max iterations)
-            launch_pcg_iteration(stream, B, max_it + 1, q_tol, r_tol2, min_it, max_it, 0);
-        }
-        read_scalars(d_pscal.p, ps, PS_COUNT);
-        done = ps[PS_DONE] != 0.0 || k > max_it;
-    }
     prof_end(CSLAM_K_PCG);
     *iters = int(ps[PS_ITERS]);
     *ok = ps[PS_FAIL] != 2.0;
@@ -795,14 +943,14 @@ double Engine::time_schur(int reps) {
     DevView v = view(d_poses.p, d_points.p);
     auto go = [&]() {
         d_red.zero(stream);
-        launch_schur_generic(stream, v, 0, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+        launch_schur(v, dg);
     };
     for (int i = 0; i < 2; ++i) go();
     float total = 0;
     for (int i = 0; i < reps; ++i) {
         d_red.zero(stream);
         CSLAM_CUDA(cudaEventRecord(ev_a, stream));
-        launch_schur_generic(stream, v, 0, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+        launch_schur(v, dg);
         CSLAM_CUDA(cudaEventRecord(ev_b, stream));
         CSLAM_CUDA(cudaEventSynchronize(ev_b));
         float ms = 0;

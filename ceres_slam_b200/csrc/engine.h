@@ -38,7 +38,12 @@ struct DevView {
     const double* poses;      // [n_cams][12] state the pass evaluates at
     const double* points;     // [n_lm][3], internal (landmark-major) order
     const int* cam_free;      // [n_cams] -> free index or -1
-    const uint32_t* lm_ptr;   // [n_lm + 1] CSR over observations
+    // observation k of landmark j sits at lm_base[j] + k * lm_stride[j]: stride 1 for
+    // landmark-major storage, stride G inside a group of G landmarks with identical camera
+    // lists (slot-major storage: consecutive landmarks are consecutive in memory)
+    const uint32_t* lm_base;
+    const uint32_t* lm_stride;
+    const uint32_t* lm_cnt;
     const uint32_t* obs_cam;  // [n_obs]
     const double* obs_u;      // SoA observations, internal order
     const double* obs_v;
@@ -52,6 +57,25 @@ struct DevView {
     const int* s_col;
 };
 
+// Landmarks that share one camera list, processed together by the grouped Schur kernel.
+// A work item is a slice of at most kItemMax landmarks of one group.
+constexpr int kGroupLmax = 16;   // longest camera list the grouped kernel takes
+constexpr int kItemMax = 128;    // landmarks per work item
+struct GroupView {
+    int n_items;
+    const int* item_group;       // [n_items]
+    const int* item_j0;          // first landmark of the slice, local to the group
+    const int* item_n;           // landmarks in the slice
+    const int* g_L;              // cameras per landmark
+    const int* g_G;              // landmarks in the group
+    const int* g_lm0;            // first internal landmark index
+    const uint32_t* g_obs0;      // first observation index
+    const int* g_off;            // offset of the group's camera list in g_cams
+    const int* g_cams;           // camera ids, ascending
+    const int* g_blk_off;        // offset of the group's pair table in g_blk
+    const int* g_blk;            // S block index for slot pair (a <= b), -1 if a camera is constant
+};
+
 struct SunBlockData {
     uint32_t cam;
     double obs_c[3], ref_g[3], W[4], az_thresh, zen_thresh, huber;
@@ -59,6 +83,11 @@ struct SunBlockData {
 struct PriorBlockData {
     uint32_t cam;
     double Tref[12], W[36];
+};
+
+// LM diagonal parameters: D^2 = clamp(diag, min, max) * inv_radius (levenberg_marquardt_strategy)
+struct LmDiag {
+    double inv_radius, min_diag, max_diag;
 };
 
 struct LmRow {
@@ -123,7 +152,8 @@ class Engine {
     // structure (host copies kept for download / diagnostics)
     std::vector<int> cam_free_h, free_cams_h;
     std::vector<uint32_t> lm_user_h;      // internal landmark -> user point index
-    std::vector<uint32_t> lm_ptr_h;
+    std::vector<uint32_t> lm_base_h, lm_stride_h, lm_cnt_h;
+    int n_lm_grouped = 0;                 // internal landmarks [0, n_lm_grouped) belong to groups
     std::vector<uint32_t> obs_user_h;     // internal obs -> user obs index
     std::vector<int> s_rowptr_h, s_col_h;
     int n_free = 0, n_lm = 0;
@@ -136,7 +166,15 @@ class Engine {
     DBuf<double> d_poses, d_poses_cand, d_poses_best, d_poses_init;
     DBuf<double> d_points, d_points_cand, d_points_best, d_points_init;
     DBuf<int> d_cam_free;
-    DBuf<uint32_t> d_lm_ptr, d_obs_cam;
+    DBuf<uint32_t> d_lm_base, d_lm_stride, d_lm_cnt, d_obs_cam;
+    // grouped Schur path
+    std::vector<int> item_group_h, item_j0_h, item_n_h, g_L_h, g_G_h, g_lm0_h, g_off_h, g_cams_h, g_blk_off_h, g_blk_h;
+    std::vector<uint32_t> g_obs0_h;
+    DBuf<int> d_item_group, d_item_j0, d_item_n, d_g_L, d_g_G, d_g_lm0, d_g_off, d_g_cams, d_g_blk_off, d_g_blk;
+    DBuf<uint32_t> d_g_obs0;
+    int max_group_L = 0, n_items_small = 0;
+    GroupView group_view() const;
+    void launch_schur(const DevView& v, const LmDiag& dg);
     DBuf<double> d_obs_u, d_obs_v, d_obs_d, d_obs_W;
     DBuf<double> d_sc_p, d_sc_l, d_cn_p, d_cn_l;
     DBuf<double> d_gl;                     // scaled point gradient from the last Schur pass
@@ -147,7 +185,7 @@ class Engine {
     double *d_S = nullptr, *d_Bdiag = nullptr, *d_bp = nullptr, *d_gp = nullptr, *d_scal = nullptr;
     size_t red_count = 0;
     DBuf<double> d_Minv, d_diag_p;
-    DBuf<double> d_yp, d_pr, d_pz, d_pp, d_pq, d_yl;
+    DBuf<double> d_yp, d_pr, d_pz, d_pp, d_pq, d_yl, d_pp2, d_prec;
     DBuf<double> d_pscal;
     DBuf<double> d_scal2;                  // scalars of the back-substitution pass
     DBuf<SunBlockData> d_suns;

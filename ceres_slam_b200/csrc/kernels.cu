@@ -5,7 +5,7 @@
 //   schur_generic_kernel K2  fused residual/Jacobian + Schur elimination, warp per landmark
 //   camonly_*                sun-sensor / pose-prior blocks
 //   finalize_kernel          LM diagonal on the camera blocks + block-Jacobi inverse
-//   pcg_*                K3a block-Jacobi PCG on the block-sparse reduced camera system
+//   (K3a, the persistent PCG kernel, lives in kernels_pcg.cu; the grouped K2 in kernels_grouped.cu)
 //   pose_plus / backsub  K4  Plus, back-substitution, model cost change, candidate cost
 //
 // Everything is FP64, no fast-math.  Reference semantics: SURVEY.md App. A / App. B.
@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(256)
     for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
         const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
         double cl[3] = {0, 0, 0}, g[3] = {0, 0, 0};
-        for (uint32_t e = v.lm_ptr[j]; e < v.lm_ptr[j + 1]; ++e) {
+        const uint32_t cnt = v.lm_cnt[j], stride = v.lm_stride[j];
+        uint32_t e = v.lm_base[j];
+        for (uint32_t k = 0; k < cnt; ++k, e += stride) {
             const uint32_t c = v.obs_cam[e];
             double r[3], Jc[18], Jp[9];
             stereo_block<true>(v.cam, v.poses + 12ll * c, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e),
@@ -272,18 +274,25 @@ __device__ __forceinline__ void pair_to_S(const DevView& v, double* __restrict__
     const bool swap = fx > fy;
     const int a = swap ? fy : fx, b = swap ? fx : fy;
     double* B = S + 36ll * find_block(v.s_rowptr, v.s_col, a, b);
-    const bool dup = (fx == fy) && !same_obs;
+    if (fx == fy) {
+        // diagonal block: only its upper triangle is accumulated (finalize mirrors it)
+        const bool dup = !same_obs;
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = p; q < 6; ++q) {
+                double val = Yx[3 * p] * Wy[3 * q] + Yx[3 * p + 1] * Wy[3 * q + 1] + Yx[3 * p + 2] * Wy[3 * q + 2];
+                if (dup) val += Yx[3 * q] * Wy[3 * p] + Yx[3 * q + 1] * Wy[3 * p + 1] + Yx[3 * q + 2] * Wy[3 * p + 2];
+                red_add(&B[6 * p + q], -val);
+            }
+        return;
+    }
 #pragma unroll
     for (int p = 0; p < 6; ++p)
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
             const double val = Yx[3 * p] * Wy[3 * q] + Yx[3 * p + 1] * Wy[3 * q + 1] + Yx[3 * p + 2] * Wy[3 * q + 2];
-            if (swap) {
-                red_add(&B[6 * q + p], -val);
-            } else {
-                red_add(&B[6 * p + q], -val);
-                if (dup) red_add(&B[6 * q + p], -val);
-            }
+            red_add(swap ? &B[6 * q + p] : &B[6 * p + q], -val);
         }
 }
 
@@ -303,8 +312,9 @@ __global__ void __launch_bounds__(SG_WARPS * 32)
     double cost = 0.0;
     const int warps_total = gridDim.x * SG_WARPS;
     for (int j = lm_lo + blockIdx.x * SG_WARPS + wib; j < lm_hi; j += warps_total) {
-        const long long e0 = v.lm_ptr[j];
-        const int L = int(v.lm_ptr[j + 1] - e0);
+        const long long e0 = v.lm_base[j];
+        const long long es = v.lm_stride[j];
+        const int L = int(v.lm_cnt[j]);
         const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
         const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
         // ---- pass 1: V = sum Jp^T Jp, g = sum Jp^T r --------------------------------------
@@ -312,7 +322,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32)
         ObsEval o;
         o.f = -1;
         for (int i = lane; i < L; i += 32) {
-            eval_obs_scaled(v, e0 + i, p, sl, o);
+            eval_obs_scaled(v, e0 + i * es, p, sl, o);
             cost += 0.5 * (o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2]);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32)
         // ---- pass 2: camera blocks, in chunks of 32 observations ----------------------------
         for (int c0 = 0; c0 < L; c0 += 32) {
             const int n = min(32, L - c0);
-            if (L > 32 && lane < n) eval_obs_scaled(v, e0 + c0 + lane, p, sl, o);
+            if (L > 32 && lane < n) eval_obs_scaled(v, e0 + (c0 + lane) * es, p, sl, o);
             __syncwarp();
             if (lane < n) {
                 sF[lane] = o.f;
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32)
                 __syncwarp();
                 if (lane < m) {
                     ObsEval o2;
-                    eval_obs_scaled(v, e0 + d0 + lane, p, sl, o2);
+                    eval_obs_scaled(v, e0 + (d0 + lane) * es, p, sl, o2);
                     sF2[lane] = o2.f;
                     if (o2.f >= 0) {
                         double W[18];
@@ -543,8 +553,12 @@ __global__ void finalize_kernel(DevView v, LmDiag dg, int preconditioner, double
     }
     double* Sd = S + 36ll * v.s_rowptr[f];  // diagonal block is the first block of the row
     double A[36];
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) {
+            const double sv = Sd[6 * a + b] + U[6 * a + b];  // Schur part arrives as an upper triangle
+            A[6 * a + b] = A[6 * b + a] = sv;
+        }
     for (int k = 0; k < 36; ++k) {
-        A[k] = Sd[k] + U[k];
         Sd[k] = A[k];
         Bd[k] = U[k];
     }
@@ -554,167 +568,6 @@ __global__ void finalize_kernel(DevView v, LmDiag dg, int preconditioner, double
         for (int k = 0; k < 36; ++k) Mi[k] = (k % 7 == 0) ? 1.0 : 0.0;
     }
     for (int k = 0; k < 36; ++k) Minv[36ll * f + k] = Mi[k];
-}
-
-// =============================================================================================
-// K3a — PCG (Ceres conjugate_gradients_solver semantics)
-// =============================================================================================
-__device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x) || isnan(x); }
-
-__global__ void pcg_init_kernel(PcgBufs B) {
-    __shared__ double s_red[32];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = 6 * B.nf;
-    double nb = 0, rz = 0;
-    if (i < n) {
-        const double bi = B.b[i];
-        B.x[i] = 0.0;
-        B.r[i] = bi;
-        B.p[i] = 0.0;
-        // z = Minv r
-        const int f = i / 6, row = i - 6 * f;
-        double z = 0;
-        for (int k = 0; k < 6; ++k) z += B.Minv[36ll * f + 6 * row + k] * B.b[6 * f + k];
-        B.z[i] = z;
-        nb = bi * bi;
-        rz = bi * z;
-    }
-    block_atomic_sum(rz, &B.ps[PS_RHO_NEXT], s_red);
-    block_atomic_sum(nb, &B.ps[PS_NORMB2], s_red);
-}
-
-// K_b: evaluate the termination rule of the previous iteration, then p = z + beta p
-__global__ void pcg_dir_kernel(PcgBufs B, int k, double q_tol, double r_tol2, int min_iters, int max_iters) {
-    double* ps = B.ps;
-    if (ps[PS_DONE] != 0.0) return;
-    bool done = false, fail = false;
-    const int prev = k - 1;
-    if (ps[PS_NORMB2] == 0.0) done = true;  // b == 0 -> x = 0
-    if (prev >= 1 && !done) {
-        if (ps[PS_FAIL] != 0.0) {
-            done = true;
-        } else {
-            const double Q1 = ps[PS_Q1], Q0 = ps[PS_Q0];
-            const double zeta = prev * (Q1 - Q0) / Q1;
-            if (zeta < q_tol && prev >= min_iters) done = true;
-            if (ps[PS_NORMR2] <= r_tol2 && prev >= min_iters) done = true;
-            if (prev >= max_iters) done = true;
-        }
-    }
-    const double rho = ps[PS_RHO_NEXT], last_rho = ps[PS_RHO];
-    double beta = 0.0;
-    if (!done) {
-        if (zero_or_inf(rho)) {
-            done = fail = true;
-        } else if (k > 1) {
-            beta = rho / last_rho;
-            if (zero_or_inf(beta)) done = fail = true;
-        }
-    }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!done && i < 6 * B.nf) B.p[i] = B.z[i] + beta * B.p[i];
-    if (i == 0) {
-        // single writer; every other thread derived the same decision from the same sums
-        if (done) {
-            ps[PS_DONE] = 1.0;
-            ps[PS_ITERS] = double(prev);
-            if (fail) ps[PS_FAIL] = 2.0;
-        } else {
-            ps[PS_BETA] = beta;
-        }
-    }
-}
-
-// K_c: q = S v (symmetric, upper storage + transposed lower lists); optional dot with v
-__global__ void pcg_spmv_kernel(PcgBufs B, const double* __restrict__ vec, double* __restrict__ out, int want_pq,
-                                int rotate) {
-    __shared__ double s_red[32];
-    double* ps = B.ps;
-    if (ps[PS_DONE] != 0.0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double part = 0.0;
-    if (i < 6 * B.nf) {
-        const int a = i / 6, row = i - 6 * a;
-        double acc = 0.0;
-        for (int e = B.rowptr[a]; e < B.rowptr[a + 1]; ++e) {
-            const double* blk = B.S + 36ll * e + 6 * row;
-            const double* xv = vec + 6ll * B.col[e];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) acc += blk[j] * xv[j];
-        }
-        for (int e = B.lt_rowptr[a]; e < B.lt_rowptr[a + 1]; ++e) {
-            const double* blk = B.S + 36ll * B.lt_blk[e] + row;
-            const double* xv = vec + 6ll * B.lt_col[e];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) acc += blk[6 * j] * xv[j];
-        }
-        out[i] = acc;
-        part = vec[i] * acc;
-    }
-    if (want_pq) block_atomic_sum(part, &ps[PS_PQ], s_red);
-    if (rotate && i == 0) {
-        // rho bookkeeping for the next iteration: last_rho <- rho, accumulator cleared
-        ps[PS_RHO] = ps[PS_RHO_NEXT];
-        ps[PS_RHO_NEXT] = 0.0;
-    }
-}
-
-// K_da: x += alpha p ; r -= alpha q (or r = b - Sx on reset iterations, Sx already in q2) ;
-//       z = Minv r ; rho_next = r.z ; Q1 = -x.(b + r) ; |r|^2
-__global__ void pcg_update_kernel(PcgBufs B, int reset, int stage) {
-    __shared__ double s_red[32];
-    __shared__ double s_r[256];
-    double* ps = B.ps;
-    if (ps[PS_DONE] != 0.0) return;
-    const double pq = ps[PS_PQ], rho = ps[PS_RHO];
-    const bool bad_pq = (pq <= 0.0) || isinf(pq) || isnan(pq);
-    const double alpha = rho / pq;
-    const bool bad = bad_pq || isinf(alpha) || isnan(alpha);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = 6 * B.nf;
-    if (bad) {
-        if (i == 0) ps[PS_FAIL] = bad_pq ? 1.0 : 2.0;  // 1: indefinite (NO_CONVERGENCE), 2: failure
-        return;
-    }
-    if (stage == 0) {
-        // reset iterations only: x update first, the caller then computes q = S x
-        if (i < n) B.x[i] += alpha * B.p[i];
-        return;
-    }
-    double ri = 0, xi = 0, bi = 0;
-    if (i < n) {
-        bi = B.b[i];
-        if (reset) {
-            xi = B.x[i];
-            ri = bi - B.q[i];
-        } else {
-            xi = B.x[i] + alpha * B.p[i];
-            B.x[i] = xi;
-            ri = B.r[i] - alpha * B.q[i];
-        }
-        B.r[i] = ri;
-    }
-    s_r[threadIdx.x] = ri;
-    __syncthreads();
-    double z = 0;
-    if (i < n) {
-        const int f = i / 6, row = i - 6 * f;
-        const int base = threadIdx.x - row;  // blockDim.x is a multiple of 6
-        for (int k = 0; k < 6; ++k) z += B.Minv[36ll * f + 6 * row + k] * s_r[base + k];
-        B.z[i] = z;
-    }
-    block_atomic_sum(ri * z, &ps[PS_RHO_NEXT], s_red);
-    block_atomic_sum(-xi * (bi + ri), &ps[PS_Q1], s_red);
-    block_atomic_sum(ri * ri, &ps[PS_NORMR2], s_red);
-}
-
-// clears the per-iteration accumulators once their readers (pcg_dir_kernel) have run
-__global__ void pcg_clear_kernel(double* ps) {
-    if (ps[PS_DONE] != 0.0) return;
-    ps[PS_Q0] = ps[PS_Q1];
-    ps[PS_Q1] = 0.0;
-    ps[PS_NORMR2] = 0.0;
-    ps[PS_PQ] = 0.0;
 }
 
 // =============================================================================================
@@ -762,12 +615,13 @@ __global__ void __launch_bounds__(128)
     __shared__ double s_red[32];
     double model = 0, ccost = 0, sn = 0, xn = 0, bad = 0;
     for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
-        const long long e0 = v.lm_ptr[j], e1 = v.lm_ptr[j + 1];
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const long long e1 = e0 + es * v.lm_cnt[j];
         const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
         const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
         double V[6] = {0, 0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
         ObsEval o;
-        for (long long e = e0; e < e1; ++e) {
+        for (long long e = e0; e < e1; e += es) {
             eval_obs_scaled(v, e, p, sl, o);
             double Jy[3] = {0, 0, 0};
             if (o.f >= 0) {
@@ -815,7 +669,7 @@ __global__ void __launch_bounds__(128)
             xn += pn[q] * pn[q];
         }
         // model cost change  -(J s).(r + J s / 2) with s = -y, and the cost at the candidate
-        for (long long e = e0; e < e1; ++e) {
+        for (long long e = e0; e < e1; e += es) {
             eval_obs_scaled(v, e, p, sl, o);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -1027,36 +881,6 @@ void launch_finalize(cudaStream_t s, const DevView& v, LmDiag dg, int preconditi
     if (v.n_free <= 0) return;
     finalize_kernel<<<(v.n_free + 63) / 64, 64, 0, s>>>(v, dg, preconditioner, S, Bdiag, diag_p, Minv, scal);
     CSLAM_LAUNCHED(1);
-    CSLAM_CUDA(cudaGetLastError());
-}
-
-constexpr int PCG_BLOCK = 192;  // multiple of 6: a 6-row block never straddles a CTA
-
-void launch_pcg_init(cudaStream_t s, const PcgBufs& B) {
-    CSLAM_CUDA(cudaMemsetAsync(B.ps, 0, PS_COUNT * sizeof(double), s));
-    const int n = 6 * B.nf;
-    pcg_init_kernel<<<(n + PCG_BLOCK - 1) / PCG_BLOCK, PCG_BLOCK, 0, s>>>(B);
-    CSLAM_LAUNCHED(1);
-    CSLAM_CUDA(cudaGetLastError());
-}
-
-void launch_pcg_iteration(cudaStream_t s, const PcgBufs& B, int k, double q_tol, double r_tol2, int min_iters,
-                          int max_iters, int reset_period) {
-    const int n = 6 * B.nf;
-    const int grid = (n + PCG_BLOCK - 1) / PCG_BLOCK;
-    pcg_dir_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, k, q_tol, r_tol2, min_iters, max_iters);
-    pcg_clear_kernel<<<1, 1, 0, s>>>(B.ps);
-    pcg_spmv_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, B.p, B.q, 1, 1);
-    const bool reset = reset_period > 0 && (k % reset_period == 0);
-    if (reset) {
-        pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 1, 0);
-        pcg_spmv_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, B.x, B.q, 0, 0);
-        pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 1, 1);
-        CSLAM_LAUNCHED(2);
-    } else {
-        pcg_update_kernel<<<grid, PCG_BLOCK, 0, s>>>(B, 0, 1);
-    }
-    CSLAM_LAUNCHED(4);
     CSLAM_CUDA(cudaGetLastError());
 }
 

@@ -6,10 +6,6 @@
 
 namespace cslam {
 
-struct LmDiag {
-    double inv_radius, min_diag, max_diag;
-};
-
 // K1 — materialised residual + Jacobian, caller's block order, TMA-staged poses / TMA bulk stores
 void launch_resjac(cudaStream_t s, const CameraIntrinsics& cam, long long n, const uint32_t* cam_idx,
                    const uint32_t* pt_idx, const double* u, const double* v, const double* d,
@@ -30,6 +26,11 @@ void launch_camonly_eval(cudaStream_t s, const DevView& v, const SunBlockData* s
 // K2 — fused residual/Jacobian + Schur elimination, one warp per landmark (any track length)
 void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, double* S,
                           double* Bdiag, double* bp, double* gp, double* gl, double* scal);
+// K2 (fast path) — landmarks grouped by identical camera list: one CTA per slice of a group,
+// a producer warp forms Z = W chol(V)^-T per observation, consumer warps keep the 6x6 pair
+// blocks of the slice in registers and flush them once (SYRK-shaped, output stationary)
+void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
+                          double* Bdiag, double* bp, double* gp, double* gl, double* scal);
 // sun-sensor and pose-prior blocks (camera-only): adds to Bdiag, bp, gp and the cost
 void launch_camonly_build(cudaStream_t s, const DevView& v, const SunBlockData* suns, int n_sun,
                           const PriorBlockData* priors, int n_prior, double* Bdiag, double* bp, double* gp,
@@ -40,14 +41,17 @@ void launch_finalize(cudaStream_t s, const DevView& v, LmDiag dg, int preconditi
 
 // K3a — block-Jacobi PCG on the block-sparse reduced system
 struct PcgBufs {
-    const int *rowptr, *col, *lt_rowptr, *lt_col, *lt_blk;
+    const int *rowptr, *col;              // upper block-CSR of S
+    const int* ent_ptr;                   // mirrored lists: row b -> packed (a, block) pairs of the
+    const int* ent_cb;                    //   stored upper blocks (a, b), a < b
     const double *S, *Minv, *b;
     double *x, *r, *z, *p, *q, *ps;
     int nf;
 };
-void launch_pcg_init(cudaStream_t s, const PcgBufs& B);
-void launch_pcg_iteration(cudaStream_t s, const PcgBufs& B, int iteration, double q_tol, double r_tol2,
-                          int min_iters, int max_iters, int reset_period);
+// One cooperative launch runs the whole solve; results: x, and ps[PS_ITERS], ps[PS_FAIL]
+// (1 = indefinite / NO_CONVERGENCE, 2 = FAILURE).  r_tol < 0 disables the residual rule.
+void launch_pcg_persistent(cudaStream_t s, const PcgBufs& B, double* pbuf2, double* rec3, double q_tol, double r_tol,
+                           int min_iters, int max_iters, int reset_period);
 
 // K4 — Plus on the poses, back-substitution, model cost change, candidate cost
 void launch_pose_plus(cudaStream_t s, const DevView& v, const double* yp, double* poses_cand, double* scal2,

@@ -1,0 +1,343 @@
+// K2 fast path — fused residual/Jacobian + Schur elimination for landmarks grouped by identical
+// camera list (sm_100a, FP64).
+//
+// For a group of G landmarks that are all seen by the same L cameras, the landmark elimination
+//      S_ab -= sum_j W_aj V_j^-1 W_bj^T ,      b_a = g_a - sum_j W_aj V_j^-1 g_lj
+// is a rank-3G symmetric update of one (6L x 6L) tile:  with V_j = C_j C_j^T (Cholesky) and
+// Z_aj = W_aj C_j^-T it reads  S_tile -= Z Z^T  (SYRK-shaped).  One CTA owns a slice of a group:
+//   * warp 0 (producer): lane = (landmark-in-round q, camera slot i); the slot's pose and Jacobi
+//     scaling stay in registers; per observation it evaluates r, Jc, Jp in closed form, forms
+//     W = Jc^T Jp and Z = W C^-T, writes Z to a double-buffered shared tile, and accumulates the
+//     slot's U_aa = sum Jc^T Jc, gradient and reduced right-hand side in registers;
+//   * warps 1.. (consumers): thread = camera-slot pair (a <= b); its 6x6 block of the tile lives
+//     in 36 registers (output stationary) and receives  Z_a Z_b^T  for every landmark of the
+//     slice; it is flushed to the global block-sparse S with one RED per entry per slice.
+// Camera poses of the slice are staged in shared memory with one TMA bulk copy (contiguous camera
+// lists) or L bulk copies, completion on an mbarrier.  Observations are stored slot-major inside
+// a group, so every global load of u, v, d is coalesced.
+#include "kernels.cuh"
+
+namespace cslam {
+
+namespace {
+
+constexpr int kSMs = 148;
+constexpr int GZ_DOUBLES = 32 * 18;  // one Z tile: up to 32 (landmark, slot) lanes x 18
+
+__device__ __forceinline__ const double* gW_ptr(const DevView& v, long long e) {
+    return v.W_per_obs ? v.obs_W + 9 * e : v.obs_W;
+}
+
+template <int CW>
+__global__ void __launch_bounds__(32 * (1 + CW))
+    schur_grouped_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
+                         double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
+                         double* __restrict__ gl, double* __restrict__ scal) {
+    __shared__ __align__(128) double s_pose[kGroupLmax * 12];
+    __shared__ double s_sp[kGroupLmax * 6];
+    __shared__ double s_A[kItemMax * 9];
+    __shared__ __align__(16) double s_Z[2 * GZ_DOUBLES];
+    __shared__ double s_redsum[32];
+    __shared__ int s_free[kGroupLmax];
+    __shared__ int s_blk[kGroupLmax * (kGroupLmax + 1) / 2];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_producer = warp == 0;
+    const int cid = tid - 32;  // consumer index
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    double cost = 0.0;
+    double Wsh[9];
+    if (!v.W_per_obs) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Wsh[k] = v.obs_W[k];
+    }
+
+    for (int w = item_lo + blockIdx.x; w < item_hi; w += gridDim.x) {
+        const int g = gv.item_group[w];
+        const int L = gv.g_L[g], G = gv.g_G[g];
+        const int j0 = gv.item_j0[w], nj = gv.item_n[w];
+        const int lm0 = gv.g_lm0[g] + j0;
+        const long long obs0 = (long long)gv.g_obs0[g] + j0;
+        const int* __restrict__ cams = gv.g_cams + gv.g_off[g];
+        const int* __restrict__ blk = gv.g_blk + gv.g_blk_off[g];
+        const int P = L * (L + 1) / 2;
+
+        // ---- stage the slice's cameras: free index, scaling, pair->block table, poses (TMA) ----
+        if (tid < L) {
+            const int f = v.cam_free[cams[tid]];
+            s_free[tid] = f;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s_sp[6 * tid + k] = f >= 0 ? v.sc_p[6ll * f + k] : 0.0;
+        }
+        for (int k = tid; k < P; k += blockDim.x) s_blk[k] = blk[k];
+        if (tid == 0) {
+            const int c0 = cams[0];
+            mbar_expect_tx(&s_bar, L * 96);
+            if (cams[L - 1] - c0 == L - 1) {
+                tma_load_1d(s_pose, v.poses + 12ll * c0, L * 96, &s_bar);
+            } else {
+                for (int i = 0; i < L; ++i) tma_load_1d(s_pose + 12 * i, v.poses + 12ll * cams[i], 96, &s_bar);
+            }
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        __syncthreads();
+
+        // ---- pass 1: V_j = sum Jp^T Jp + D^2, Cholesky, A = C^-1, t = A g_l ----
+        for (int jl = tid; jl < nj; jl += blockDim.x) {
+            const long long j = lm0 + jl;
+            const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
+            const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
+            double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
+            for (int i = 0; i < L; ++i) {
+                const long long e = obs0 + (long long)i * G + jl;
+                double r[3], Jp[9];
+                stereo_block_point(v.cam, s_pose + 12 * i, p, v.obs_u[e], v.obs_v[e], v.obs_d[e],
+                                   v.W_per_obs ? v.obs_W + 9 * e : Wsh, r, Jp);
+                cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double a = Jp[3 * k] * sl[0], b = Jp[3 * k + 1] * sl[1], c = Jp[3 * k + 2] * sl[2];
+                    V[0] += a * a;
+                    V[1] += a * b;
+                    V[2] += a * c;
+                    V[3] += b * b;
+                    V[4] += b * c;
+                    V[5] += c * c;
+                    gq[0] += a * r[k];
+                    gq[1] += b * r[k];
+                    gq[2] += c * r[k];
+                }
+            }
+            V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            // V = C C^T, C lower triangular
+            double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            bool pd = V[0] > 0.0;
+            if (pd) {
+                const double c00 = sqrt(V[0]);
+                const double c10 = V[1] / c00, c20 = V[2] / c00;
+                const double d1 = V[3] - c10 * c10;
+                pd = d1 > 0.0;
+                if (pd) {
+                    const double c11 = sqrt(d1);
+                    const double c21 = (V[4] - c20 * c10) / c11;
+                    const double d2 = V[5] - c20 * c20 - c21 * c21;
+                    pd = d2 > 0.0 && d2 < 1.7976931348623157e308;
+                    if (pd) {
+                        const double c22 = sqrt(d2);
+                        const double a00 = 1.0 / c00, a11 = 1.0 / c11, a22 = 1.0 / c22;
+                        const double a10 = -c10 * a00 * a11;
+                        const double a21 = -c21 * a11 * a22;
+                        const double a20 = -(c20 * a00 + c21 * a10) * a22;
+                        A[0] = a00;
+                        A[1] = a10;
+                        A[2] = a11;
+                        A[3] = a20;
+                        A[4] = a21;
+                        A[5] = a22;
+                        A[6] = a00 * gq[0];
+                        A[7] = a10 * gq[0] + a11 * gq[1];
+                        A[8] = a20 * gq[0] + a21 * gq[1] + a22 * gq[2];
+                    }
+                }
+            }
+            if (!pd) red_add(&scal[SC_INVALID], 1.0);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s_A[9 * jl + k] = A[k];
+            gl[3 * j] = gq[0];
+            gl[3 * j + 1] = gq[1];
+            gl[3 * j + 2] = gq[2];
+        }
+        __syncthreads();
+
+        // ---- main loop: producer forms Z, consumers accumulate Z_a Z_b^T ----
+        const int R = 32 / L;  // landmarks per round
+        const int rounds = (nj + R - 1) / R;
+        // producer lane state
+        const int pi = lane / R, pq = lane - pi * R;
+        const bool p_active = is_producer && lane < R * L;
+        int pf = -1;
+        double pose[12], sp[6];
+        double U[21], gpa[6], bpa[6];
+        if (p_active) {
+            pf = s_free[pi];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) pose[k] = s_pose[12 * pi + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sp[k] = s_sp[6 * pi + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 21; ++k) U[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gpa[k] = bpa[k] = 0.0;
+        // consumer thread state: pair (a <= b), row-major enumeration of the upper triangle
+        int ca = 0, cb = 0;
+        const bool c_active = !is_producer && cid < P;
+        if (c_active) {
+            int rem = cid;
+            while (rem >= L - ca) {
+                rem -= L - ca;
+                ++ca;
+            }
+            cb = ca + rem;
+        }
+        double M[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) M[k] = 0.0;
+
+        for (int rd = 0; rd <= rounds; ++rd) {
+            if (is_producer) {
+                if (rd < rounds && p_active) {
+                    double* zt = s_Z + (rd & 1) * GZ_DOUBLES + (pq * L + pi) * 18;
+                    const int jl = rd * R + pq;
+                    double Z[18];
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) Z[k] = 0.0;
+                    if (jl < nj && pf >= 0) {
+                        const long long j = lm0 + jl;
+                        const long long e = obs0 + (long long)pi * G + jl;
+                        const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
+                        const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
+                        double r[3], Jc[18], Jp[9];
+                        stereo_block<true>(v.cam, pose, p, v.obs_u[e], v.obs_v[e], v.obs_d[e],
+                                           v.W_per_obs ? v.obs_W + 9 * e : Wsh, r, Jc, Jp);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) Jp[3 * k + q] *= sl[q];
+#pragma unroll
+                            for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= sp[q];
+                        }
+                        const double* A = s_A + 9 * jl;
+                        const double a00 = A[0], a10 = A[1], a11 = A[2], a20 = A[3], a21 = A[4], a22 = A[5];
+                        const double t0 = A[6], t1 = A[7], t2 = A[8];
+                        int u = 0;
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3] + Jc[12 + a] * Jp[6];
+                            const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4] + Jc[12 + a] * Jp[7];
+                            const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5] + Jc[12 + a] * Jp[8];
+                            // Z = W A^T (A lower triangular)
+                            const double z0 = w0 * a00;
+                            const double z1 = w0 * a10 + w1 * a11;
+                            const double z2 = w0 * a20 + w1 * a21 + w2 * a22;
+                            Z[3 * a] = z0;
+                            Z[3 * a + 1] = z1;
+                            Z[3 * a + 2] = z2;
+                            const double ga = Jc[a] * r[0] + Jc[6 + a] * r[1] + Jc[12 + a] * r[2];
+                            gpa[a] += ga;
+                            bpa[a] += ga - (z0 * t0 + z1 * t1 + z2 * t2);
+#pragma unroll
+                            for (int b = a; b < 6; ++b, ++u)
+                                U[u] += Jc[a] * Jc[b] + Jc[6 + a] * Jc[6 + b] + Jc[12 + a] * Jc[12 + b];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(Z[k], Z[k + 1]);
+                }
+            } else if (rd > 0 && c_active) {
+                const double* zt = s_Z + ((rd - 1) & 1) * GZ_DOUBLES;
+                const int nval = min(R, nj - (rd - 1) * R);
+                for (int jj = 0; jj < nval; ++jj) {
+                    const double* za = zt + (jj * L + ca) * 18;
+                    const double* zb = zt + (jj * L + cb) * 18;
+                    double B[18];
+#pragma unroll
+                    for (int k = 0; k < 18; k += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(zb + k);
+                        B[k] = t.x;
+                        B[k + 1] = t.y;
+                    }
+#pragma unroll
+                    for (int p = 0; p < 6; ++p) {
+                        const double x0 = za[3 * p], x1 = za[3 * p + 1], x2 = za[3 * p + 2];
+#pragma unroll
+                        for (int q = 0; q < 6; ++q)
+                            M[6 * p + q] += x0 * B[3 * q] + x1 * B[3 * q + 1] + x2 * B[3 * q + 2];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- flush: pair blocks (consumers), camera diagonal / gradients (producer) ----
+        if (c_active) {
+            const int e = s_blk[cid];
+            if (e >= 0) {
+                double* Bk = S + 36ll * e;
+                if (ca == cb) {
+                    // diagonal block: upper triangle only, finalize mirrors it
+#pragma unroll
+                    for (int p = 0; p < 6; ++p)
+#pragma unroll
+                        for (int q = p; q < 6; ++q) red_add(&Bk[6 * p + q], -M[6 * p + q]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 36; ++k) red_add(&Bk[k], -M[k]);
+                }
+            }
+        }
+        if (is_producer) {
+            // reduce over the R lanes that share a slot (consecutive lanes), then one RED each
+            double* red = s_Z;  // all consumer reads of s_Z are behind the last barrier
+            if (p_active) {
+#pragma unroll
+                for (int k = 0; k < 21; ++k) red[lane * 33 + k] = U[k];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    red[lane * 33 + 21 + k] = gpa[k];
+                    red[lane * 33 + 27 + k] = bpa[k];
+                }
+            }
+            __syncwarp();
+            if (p_active && pq == 0 && pf >= 0) {
+                double acc[33];
+#pragma unroll
+                for (int k = 0; k < 33; ++k) acc[k] = red[lane * 33 + k];
+                for (int q = 1; q < R; ++q)
+#pragma unroll
+                    for (int k = 0; k < 33; ++k) acc[k] += red[(lane + q) * 33 + k];
+                double* Bd = Bdiag + 36ll * pf;
+                int u = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                    for (int b = a; b < 6; ++b, ++u) red_add(&Bd[6 * a + b], acc[u]);
+                    red_add(&gp[6ll * pf + a], acc[21 + a]);
+                    red_add(&bp[6ll * pf + a], acc[27 + a]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    block_atomic_sum(cost, &scal[SC_COST], s_redsum);
+}
+
+}  // namespace
+
+void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
+                          double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
+    // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
+    if (n_items_small > 0) {
+        const int grid = n_items_small < 4 * kSMs ? n_items_small : 4 * kSMs;
+        schur_grouped_kernel<2><<<grid, 96, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (g.n_items > n_items_small) {
+        const int n = g.n_items - n_items_small;
+        const int grid = n < 2 * kSMs ? n : 2 * kSMs;
+        schur_grouped_kernel<5><<<grid, 192, 0, s>>>(v, g, n_items_small, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+}  // namespace cslam

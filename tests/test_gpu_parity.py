@@ -149,3 +149,32 @@ def test_errors(product):
         p.add_stereo([5], [0], np.zeros((1, 3)), np.eye(3).reshape(9))
     with pytest.raises(CslamError):
         p.lm_begin()
+
+
+def _reduced(track, path, **kw):
+    p, _, _ = syn.build_problem(track, backend="b200", schur_path=path, **kw)
+    p.upload()
+    p.lm_begin()
+    return p.reduced_system()
+
+
+@pytest.mark.parametrize("shape", [(60, 15, 6), (100, 15, 10), (80, 3, 14)])
+def test_schur_paths_agree(product, shape):
+    """The grouped (SYRK-shaped) Schur kernel and the generic warp-per-landmark kernel build the
+    same reduced camera system; both orders of summation agree to rounding."""
+    tr = syn.make_track(*shape, seed=17, per_obs_W=(shape[2] == 6))
+    rp1, col1, S1, b1, ids1 = _reduced(tr, 1)
+    rp2, col2, S2, b2, ids2 = _reduced(tr, 2)
+    assert np.array_equal(rp1, rp2) and np.array_equal(col1, col2) and np.array_equal(ids1, ids2)
+    assert rel_err(S2, S1) < 1e-12
+    assert rel_err(b2, b1) < 1e-11
+    # diagonal blocks come out symmetric, off-diagonal pattern is upper block-triangular
+    diag = S2[rp2[:-1]]
+    assert np.allclose(diag, diag.transpose(0, 2, 1), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_lm_both_schur_paths(product, path):
+    tr = syn.make_track(100, 15, 10, seed=23)
+    g, o = solve_pair(tr, 5, schur_path=path)
+    check_lm(g, o)
