@@ -17,6 +17,7 @@ typedef int (*GetUniqueIdFn)(NcclId*);
 typedef int (*CommInitRankFn)(void**, int, NcclId, int);
 typedef int (*CommDestroyFn)(void*);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*BroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*GetErrorStringFn)(int);
 
 struct Api {
@@ -25,6 +26,7 @@ struct Api {
     CommInitRankFn comm_init_rank = nullptr;
     CommDestroyFn comm_destroy = nullptr;
     AllReduceFn all_reduce = nullptr;
+    BroadcastFn broadcast = nullptr;
     GetErrorStringFn error_string = nullptr;
 };
 
@@ -41,8 +43,9 @@ Api& api() {
     a.comm_init_rank = (CommInitRankFn)dlsym(a.handle, "ncclCommInitRank");
     a.comm_destroy = (CommDestroyFn)dlsym(a.handle, "ncclCommDestroy");
     a.all_reduce = (AllReduceFn)dlsym(a.handle, "ncclAllReduce");
+    a.broadcast = (BroadcastFn)dlsym(a.handle, "ncclBroadcast");
     a.error_string = (GetErrorStringFn)dlsym(a.handle, "ncclGetErrorString");
-    if (!a.get_unique_id || !a.comm_init_rank || !a.comm_destroy || !a.all_reduce)
+    if (!a.get_unique_id || !a.comm_init_rank || !a.comm_destroy || !a.all_reduce || !a.broadcast)
         throw std::runtime_error("libnccl is missing required symbols");
     return a;
 }
@@ -74,5 +77,8 @@ void comm_allreduce_sum(void* comm, double* buf, size_t count, cudaStream_t s) {
 }
 void comm_allreduce_max(void* comm, double* buf, size_t count, cudaStream_t s) {
     check(api().all_reduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclMax*/ 2, comm, s), "ncclAllReduce(max)");
+}
+void comm_broadcast(void* comm, double* buf, size_t count, int root, cudaStream_t s) {
+    check(api().broadcast(buf, buf, count, /*ncclFloat64*/ 8, root, comm, s), "ncclBroadcast");
 }
 }  // namespace cslam

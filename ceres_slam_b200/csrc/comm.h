@@ -11,4 +11,5 @@ void* comm_create(int n_ranks, int rank, const uint8_t id[128]);
 void comm_destroy(void* comm);
 void comm_allreduce_sum(void* comm, double* buf, size_t count, cudaStream_t s);
 void comm_allreduce_max(void* comm, double* buf, size_t count, cudaStream_t s);
+void comm_broadcast(void* comm, double* buf, size_t count, int root, cudaStream_t s);
 }  // namespace cslam

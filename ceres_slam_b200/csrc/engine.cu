@@ -579,7 +579,7 @@ void Engine::run_pcg(int* iters, bool* ok) {
         // the block-Jacobi preconditioner is then the exact inverse
         q_tol = -1.0;
         r_tol = 1e-15;
-        max_it = std::max(50, 12 * n_free + 20);
+        max_it = std::max(64, 12 * n_free + 32);
         min_it = 0;
     } else {
         q_tol = opt.eta;
@@ -589,6 +589,12 @@ void Engine::run_pcg(int* iters, bool* ok) {
     }
     prof_begin(CSLAM_K_PCG);
     launch_pcg_persistent(stream, B, d_pp2.p, d_prec.p, q_tol, r_tol, min_it, max_it, 10);
+    if (n_ranks > 1) {
+        // every rank solved the same system; rank 0's iterate is adopted everywhere so that all
+        // ranks keep bit-identical poses (and therefore take identical accept/reject decisions)
+        comm_broadcast(nccl_comm, d_yp.p, 6 * size_t(n_free), 0, stream);
+        comm_broadcast(nccl_comm, d_pscal.p, PS_COUNT, 0, stream);
+    }
     double ps[PS_COUNT];
     read_scalars(d_pscal.p, ps, PS_COUNT);
     prof_end(CSLAM_K_PCG);
