@@ -57,6 +57,18 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_host_driver():
+    """C++ host mirror + restated dataset_vo driver (links the C ABI library)."""
+    host = os.path.join(HERE, "host")
+    out = os.path.join(host, "dataset_vo_b200")
+    src = os.path.join(host, "dataset_vo_b200.cpp")
+    deps = [src, os.path.join(host, "cslam_problem.hpp"), OUT]
+    if _stale(out, deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + CSRC, "-lcslam_b200",
+                               "-Wl,-rpath," + CSRC, "-Wl,-rpath,$ORIGIN/../csrc"])
+    return out
+
+
 def build_oracle():
     subprocess.check_call(["make", "-C", os.path.join(os.path.dirname(HERE), "oracle")])
 

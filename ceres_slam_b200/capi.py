@@ -70,6 +70,15 @@ class Summary(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class StructureInfo(C.Structure):
+    _fields_ = [("n_free_cams", C.c_int), ("n_landmarks", C.c_int), ("n_observations", C.c_longlong),
+                ("nnz_blocks", C.c_int), ("pattern_hash", C.c_ulonglong), ("n_groups", C.c_int),
+                ("n_grouped_landmarks", C.c_int), ("n_work_items", C.c_int), ("landmark_id_sum", C.c_ulonglong)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_int * 16)]
 
@@ -112,6 +121,7 @@ _PRODUCT_ONLY = {
     "time_resjac": (C.c_int, [_h, C.c_int, _dp]),
     "time_schur": (C.c_int, [_h, C.c_int, _dp]),
     "measure_fp64_peak": (C.c_int, [C.c_int, _dp]),
+    "analyze": (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(StructureInfo)]),
     "get_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "comm_unique_id": (C.c_int, [_u8p]),
     "attach_comm": (C.c_int, [_h, C.c_int, C.c_int, _u8p]),

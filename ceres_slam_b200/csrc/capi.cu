@@ -267,6 +267,13 @@ cslam_status cslam_measure_fp64_peak(int device, double* tflops) {
     }
 }
 
+cslam_status cslam_analyze(cslam_problem* p, int n_ranks, int rank, cslam_structure_info* out) {
+    return guarded(p, [&](Engine& e) {
+        if (!out || n_ranks < 1 || rank < 0 || rank >= n_ranks) throw std::invalid_argument("bad arguments");
+        e.analyze(n_ranks, rank, out);
+    });
+}
+
 cslam_status cslam_get_launch_count(uint64_t* count) {
     if (!count) return CSLAM_ERR_INVALID;
     *count = cslam::g_kernel_launches.load();

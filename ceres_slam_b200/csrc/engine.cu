@@ -983,6 +983,36 @@ void Engine::get_reduced_system(int* rowptr, int* col, double* values, double* r
     CSLAM_CUDA(cudaStreamSynchronize(stream));
 }
 
+void Engine::analyze(int n_ranks_, int rank_, cslam_structure_info* out) {
+    const int keep_n = n_ranks, keep_r = rank;
+    n_ranks = n_ranks_;
+    rank = rank_;
+    try {
+        build_structure();
+    } catch (...) {
+        n_ranks = keep_n;
+        rank = keep_r;
+        throw;
+    }
+    n_ranks = keep_n;
+    rank = keep_r;
+    uploaded = begun = false;
+    out->n_free_cams = n_free;
+    out->n_landmarks = n_lm;
+    out->n_observations = n_obs;
+    out->nnz_blocks = nnzU;
+    unsigned long long h = 1469598103934665603ull;
+    for (int v : s_rowptr_h) h = (h ^ (unsigned long long)(unsigned)v) * 1099511628211ull;
+    for (int v : s_col_h) h = (h ^ (unsigned long long)(unsigned)v) * 1099511628211ull;
+    out->pattern_hash = h;
+    out->n_groups = int(g_L_h.size());
+    out->n_grouped_landmarks = n_lm_grouped;
+    out->n_work_items = int(item_group_h.size());
+    unsigned long long s = 0;
+    for (uint32_t id : lm_user_h) s += id;
+    out->landmark_id_sum = s;
+}
+
 bool Engine::window_eligible() const { return false; }
 
 }  // namespace cslam

@@ -135,6 +135,7 @@ class Engine {
     void get_reduced_sizes(int* nf, int* nnz) const;
     void get_reduced_system(int* rowptr, int* col, double* values, double* rhs, int* ids);
     void set_stream(cudaStream_t s);
+    void analyze(int n_ranks_, int rank_, cslam_structure_info* out);  // host only
 
     std::vector<LmRow> log;
     cslam_profile prof{};

@@ -193,6 +193,12 @@ class BAProblem:
         self._check(self.lib.time_schur(self._h, reps, C.byref(ms)))
         return ms.value
 
+    def analyze(self, n_ranks=1, rank=0):
+        """Host-only structure analysis (works without a GPU)."""
+        info = capi.StructureInfo()
+        self._check(self.lib.analyze(self._h, n_ranks, rank, C.byref(info)))
+        return info.as_dict()
+
     def attach_comm(self, n_ranks, rank, uid):
         uid = np.ascontiguousarray(uid, dtype=np.uint8)
         assert uid.size == 128

@@ -188,3 +188,21 @@ def build_problem(track, backend="b200", sun=False, prior=None, huber=0.0, hold_
         cam, Tref, W6 = prior
         p.add_pose_prior(cam, Tref, W6)
     return p, poses, points
+
+
+def write_track_csv(track, path):
+    """The reference's plain track CSV (src/ceres_slam/dataset_problem.cpp:27-83): counts,
+    intrinsics, variances, first pose as a 4x4 row-major matrix, then rows k,j,u,v,d grouped by k."""
+    c = track["cam"]
+    W = np.asarray(track["W"]).reshape(-1)[:9].reshape(3, 3)
+    var = 1.0 / np.diag(W) ** 2
+    T0 = np.eye(4)
+    T0[:3, :3] = track["poses_gt"][0, 3:].reshape(3, 3)
+    T0[:3, 3] = track["poses_gt"][0, :3]
+    with open(path, "w") as f:
+        f.write(f"{track['n_poses']},{track['n_points']}\n")
+        f.write(",".join(repr(float(c[k])) for k in ("fu", "fv", "cu", "cv", "b")) + "\n")
+        f.write(",".join(repr(float(v)) for v in var) + "\n")
+        f.write(",".join(repr(float(v)) for v in T0.reshape(-1)) + "\n")
+        for k, j, z in zip(track["obs_cam"], track["obs_pt"], track["uvd"]):
+            f.write(f"{int(k)},{int(j)},{z[0]!r},{z[1]!r},{z[2]!r}\n".replace("np.float64(", "").replace(")", ""))

@@ -192,6 +192,22 @@ cslam_status cslam_time_schur(cslam_problem* p, int reps, double* ms_per_launch)
 /* FP64 FMA microbenchmark (register-resident DFMA chains on every SM): TFLOP/s. */
 cslam_status cslam_measure_fp64_peak(int device, double* tflops);
 
+/* Host-only structure analysis (no CUDA needed): which blocks are free, this rank's landmark
+ * shard, the grouping used by the fused Schur kernel and the pattern of the reduced camera
+ * system.  Lets the sharding logic be tested without a GPU. */
+typedef struct cslam_structure_info {
+    int n_free_cams;
+    int n_landmarks;          /* landmarks in this rank's shard */
+    long long n_observations; /* observations in this rank's shard */
+    int nnz_blocks;           /* upper 6x6 blocks of S (global pattern, identical on all ranks) */
+    unsigned long long pattern_hash; /* FNV-1a over (rowptr, col) of that pattern */
+    int n_groups;             /* camera-list groups in the shard */
+    int n_grouped_landmarks;
+    int n_work_items;
+    unsigned long long landmark_id_sum; /* sum of the caller's point indices in the shard */
+} cslam_structure_info;
+cslam_status cslam_analyze(cslam_problem* p, int n_ranks, int rank, cslam_structure_info* out);
+
 /* Number of kernels this library has launched in this process (all handles). */
 cslam_status cslam_get_launch_count(uint64_t* count);
 

@@ -178,3 +178,25 @@ def test_lm_both_schur_paths(product, path):
     tr = syn.make_track(100, 15, 10, seed=23)
     g, o = solve_pair(tr, 5, schur_path=path)
     check_lm(g, o)
+
+
+def test_cpp_driver_dataset_vo(product, tmp_path):
+    """The C++ host mirror (host/cslam_problem.hpp) and the restated dataset_vo driver run the
+    reference's CSV format through the C ABI: full batch from a constant-pose initial guess must
+    land on the ground-truth track (noise-limited)."""
+    import os
+    import subprocess
+    from ceres_slam_b200 import build as b
+    exe = b.build_host_driver()
+    tr = syn.make_track(40, 12, 6, seed=31, spacing=0.1)
+    csv = os.path.join(tmp_path, "track.csv")
+    syn.write_track_csv(tr, csv)
+    out = subprocess.run([exe, csv, "--window", "0", "--max-iters", "50"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "Termination: CONVERGENCE" in out.stdout, out.stdout
+    poses = np.loadtxt(os.path.join(tmp_path, "track_poses.csv"), delimiter=",", skiprows=1)
+    assert poses.shape == (40, 16)
+    T = poses.reshape(-1, 4, 4)
+    gt_t, gt_R = tr["poses_gt"][:, :3], tr["poses_gt"][:, 3:].reshape(-1, 3, 3)
+    assert np.abs(T[:, :3, 3] - gt_t).max() < 0.05
+    assert np.abs(T[:, :3, :3] - gt_R).max() < 0.01
