@@ -271,6 +271,169 @@ CSLAM_HD void se3_plus(const double* pose, const double* eps, double* out) {
     for (int i = 0; i < 12; ++i) out[i] = o[i];
 }
 
+// UnitVectorPerturbation on plain doubles (perturbations.hpp:97-104):
+//   x' = normalize(x + delta - (delta . x / |x|^2) x)
+CSLAM_HD void unit_plus(const double* x, const double* dl, double* out) {
+    const double s = (dl[0] * x[0] + dl[1] * x[1] + dl[2] * x[2]) / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const double y0 = x[0] + dl[0] - s * x[0], y1 = x[1] + dl[1] - s * x[1], y2 = x[2] + dl[2] - s * x[2];
+    const double n = sqrt(y0 * y0 + y1 * y1 + y2 * y2);
+    out[0] = y0 / n;
+    out[1] = y1 / n;
+    out[2] = y2 / n;
+}
+// Its Jacobian at delta = 0 (what AutoDiffLocalParameterization yields, perturbations.hpp:110-111,
+// declared 3 -> 3, rank 2):  (I - x x^T / |x|^2) / |x|.   Row-vector product g^T J:
+CSLAM_HD void unit_plus_pullback(const double* x, const double* g, double* out) {
+    const double n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    const double in = 1.0 / sqrt(n2);
+    const double gx = (g[0] * x[0] + g[1] * x[1] + g[2] * x[2]) / n2;
+    out[0] = (g[0] - gx * x[0]) * in;
+    out[1] = (g[1] - gx * x[1]) * in;
+    out[2] = (g[2] - gx * x[2]) * in;
+}
+
+// Normal block (normal_error.hpp:20-41): r = W (R n - n_obs).
+//   Jc = W [ 0 | -[n_c]x ]   3x6,   Jn = W R (I - n n^T/|n|^2)/|n|   3x3 (through UnitVectorPerturbation)
+CSLAM_HD void normal_block(const double* pose, const double* n, const double* obs, const double* W,
+                           double* r, double* Jc, double* Jn) {
+    const double* R = pose + 3;
+    double nc[3];
+    for (int i = 0; i < 3; ++i) nc[i] = R[3 * i] * n[0] + R[3 * i + 1] * n[1] + R[3 * i + 2] * n[2];
+    const double e0 = nc[0] - obs[0], e1 = nc[1] - obs[1], e2 = nc[2] - obs[2];
+    for (int i = 0; i < 3; ++i) r[i] = W[3 * i] * e0 + W[3 * i + 1] * e1 + W[3 * i + 2] * e2;
+    if (!Jc) return;
+    for (int i = 0; i < 3; ++i) {
+        const double a0 = W[3 * i], a1 = W[3 * i + 1], a2 = W[3 * i + 2];
+        Jc[6 * i + 0] = Jc[6 * i + 1] = Jc[6 * i + 2] = 0.0;
+        Jc[6 * i + 3] = a2 * nc[1] - a1 * nc[2];
+        Jc[6 * i + 4] = a0 * nc[2] - a2 * nc[0];
+        Jc[6 * i + 5] = a1 * nc[0] - a0 * nc[1];
+        const double g[3] = {a0 * R[0] + a1 * R[3] + a2 * R[6], a0 * R[1] + a1 * R[4] + a2 * R[7],
+                             a0 * R[2] + a1 * R[5] + a2 * R[8]};
+        unit_plus_pullback(n, g, Jn + 3 * i);
+    }
+}
+
+// Intensity block (intensity_error_point_light.hpp:24-90 / intensity_error_directional_light.hpp:24-90
+// -> point_light.hpp:76-90 / directional_light.hpp:82-91 -> phong.hpp:25-139):
+//   I = clamp(kd max(0, l.n_c) + ks (m.c)^alpha, 0, 1),  r = w (I - I_obs)
+// with p_c = R p + t, n_c = R n, light vector lv = R (l - p) (point light; t cancels) or R d
+// (directional, normalised by the DirectionalLight constructor), l = lv/|lv|, camera direction
+// c = -p_c/|p_c| (camera at the origin, intensity_error_point_light.hpp:83), m = 2 (n_c.l) n_c - l
+// normalised.  Ambient is disabled (phong.hpp:31-33).  Branches as in the reference: diffuse 0 when
+// l is not finite or l.n_c <= 0; specular 0 when |m|^2 <= 0 or m.c <= 0; clamp with the constant as
+// first argument of fmax/fmin (utils.hpp:16-25) so ties take the constant (zero derivative).
+// Jacobians (one row): pose tangent 6, point 3, normal 3 (through UnitVectorPerturbation),
+// phong [ka, ks, alpha] 3, texture kd 1, light 3 (through UnitVectorPerturbation when directional).
+CSLAM_HD void intensity_block(const double* pose, const double* p, const double* n, const double* phong,
+                              double kd, const double* light, double colour, double w, bool directional,
+                              double* r, double* Jc, double* Jp, double* Jn, double* Jk, double* Jt,
+                              double* Jl) {
+    const double* R = pose + 3;
+    double pc[3], nc[3], lv[3];
+    transform_point(pose, p, pc);
+    for (int i = 0; i < 3; ++i) nc[i] = R[3 * i] * n[0] + R[3 * i + 1] * n[1] + R[3 * i + 2] * n[2];
+    if (directional) {
+        for (int i = 0; i < 3; ++i) lv[i] = R[3 * i] * light[0] + R[3 * i + 1] * light[1] + R[3 * i + 2] * light[2];
+    } else {
+        double lc[3];
+        transform_point(pose, light, lc);
+        for (int i = 0; i < 3; ++i) lv[i] = lc[i] - pc[i];
+    }
+    const double L = sqrt(lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2]);
+    const double l[3] = {lv[0] / L, lv[1] / L, lv[2] / L};
+    const double cn = sqrt(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]);
+    const double c[3] = {-pc[0] / cn, -pc[1] / cn, -pc[2] / cn};
+    const double ks = phong[1], alpha = phong[2];
+    // gradients of the colour w.r.t. camera-frame quantities
+    double g_nc[3] = {0, 0, 0}, g_l[3] = {0, 0, 0}, g_c[3] = {0, 0, 0};
+    double d_kd = 0.0, d_ks = 0.0, d_alpha = 0.0;
+    const double a = l[0] * nc[0] + l[1] * nc[1] + l[2] * nc[2];
+    const bool finite_l = (l[0] - l[0] == 0.0) && (l[1] - l[1] == 0.0) && (l[2] - l[2] == 0.0);
+    double col = 0.0;
+    if (finite_l && !(a <= 0.0)) {
+        col = kd * a;
+        d_kd = a;
+        for (int i = 0; i < 3; ++i) {
+            g_nc[i] = kd * l[i];
+            g_l[i] = kd * nc[i];
+        }
+    }
+    double m[3] = {2.0 * a * nc[0] - l[0], 2.0 * a * nc[1] - l[1], 2.0 * a * nc[2] - l[2]};
+    const double m2 = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+    if (!(m2 <= 0.0)) {
+        const double mn = sqrt(m2);
+        m[0] /= mn; m[1] /= mn; m[2] /= mn;
+        const double s = m[0] * c[0] + m[1] * c[1] + m[2] * c[2];
+        if (!(s <= 0.0)) {
+            const double sa = pow(s, alpha);
+            col += ks * sa;
+            d_ks = sa;
+            d_alpha = ks * sa * log(s);
+            const double dS = ks * alpha * pow(s, alpha - 1.0);  // d spec / d s
+            double u[3];                                          // d spec / d m (unnormalised m)
+            for (int i = 0; i < 3; ++i) u[i] = dS * (c[i] - s * m[i]) / mn;
+            const double un = u[0] * nc[0] + u[1] * nc[1] + u[2] * nc[2];
+            for (int i = 0; i < 3; ++i) {
+                g_nc[i] += 2.0 * a * u[i] + 2.0 * un * l[i];
+                g_l[i] += 2.0 * un * nc[i] - u[i];
+                g_c[i] = dS * m[i];
+            }
+        }
+    }
+    bool flat = false;  // clamp (phong.hpp:136-139)
+    if (0.0 >= col) { col = 0.0; flat = true; }
+    if (1.0 <= col) { col = 1.0; flat = true; }
+    r[0] = w * (col - colour);
+    if (!Jc) return;
+    if (flat) {
+        for (int i = 0; i < 6; ++i) Jc[i] = 0.0;
+        for (int i = 0; i < 3; ++i) Jp[i] = Jn[i] = Jk[i] = Jl[i] = 0.0;
+        Jt[0] = 0.0;
+        return;
+    }
+    // through the normalisations: l = lv/|lv|, c = -p_c/|p_c|
+    const double gl_l = g_l[0] * l[0] + g_l[1] * l[1] + g_l[2] * l[2];
+    const double gc_c = g_c[0] * c[0] + g_c[1] * c[1] + g_c[2] * c[2];
+    double g_lv[3], g_pc[3];
+    for (int i = 0; i < 3; ++i) {
+        g_lv[i] = (g_l[i] - gl_l * l[i]) / L;
+        g_pc[i] = -(g_c[i] - gc_c * c[i]) / cn;
+    }
+    // pose tangent: translation g_pc; rotation p_c x g_pc + n_c x g_nc + lv x g_lv
+    Jc[0] = w * g_pc[0];
+    Jc[1] = w * g_pc[1];
+    Jc[2] = w * g_pc[2];
+    Jc[3] = w * ((pc[1] * g_pc[2] - pc[2] * g_pc[1]) + (nc[1] * g_nc[2] - nc[2] * g_nc[1]) + (lv[1] * g_lv[2] - lv[2] * g_lv[1]));
+    Jc[4] = w * ((pc[2] * g_pc[0] - pc[0] * g_pc[2]) + (nc[2] * g_nc[0] - nc[0] * g_nc[2]) + (lv[2] * g_lv[0] - lv[0] * g_lv[2]));
+    Jc[5] = w * ((pc[0] * g_pc[1] - pc[1] * g_pc[0]) + (nc[0] * g_nc[1] - nc[1] * g_nc[0]) + (lv[0] * g_lv[1] - lv[1] * g_lv[0]));
+    double gp[3], gn[3], gl[3];
+    for (int j = 0; j < 3; ++j) {
+        const double dp0 = directional ? g_pc[0] : g_pc[0] - g_lv[0];
+        const double dp1 = directional ? g_pc[1] : g_pc[1] - g_lv[1];
+        const double dp2 = directional ? g_pc[2] : g_pc[2] - g_lv[2];
+        gp[j] = dp0 * R[j] + dp1 * R[3 + j] + dp2 * R[6 + j];
+        gn[j] = g_nc[0] * R[j] + g_nc[1] * R[3 + j] + g_nc[2] * R[6 + j];
+        gl[j] = g_lv[0] * R[j] + g_lv[1] * R[3 + j] + g_lv[2] * R[6 + j];
+    }
+    double t3[3];
+    unit_plus_pullback(n, gn, t3);
+    for (int j = 0; j < 3; ++j) {
+        Jp[j] = w * gp[j];
+        Jn[j] = w * t3[j];
+    }
+    if (directional) {
+        unit_plus_pullback(light, gl, t3);
+        for (int j = 0; j < 3; ++j) Jl[j] = w * t3[j];
+    } else {
+        for (int j = 0; j < 3; ++j) Jl[j] = w * gl[j];
+    }
+    Jk[0] = 0.0;
+    Jk[1] = w * d_ks;
+    Jk[2] = w * d_alpha;
+    Jt[0] = w * d_kd;
+}
+
 // ceres::HuberLoss + Corrector (rho'' <= 0 branch): residual and Jacobian scale sqrt(rho')
 CSLAM_HD void huber_rho(double a, double s, double* rho0, double* sqrt_rho1) {
     const double b = a * a;

@@ -17,4 +17,14 @@ void cf_prior_block(const double* pose, const double* Tref, const double* W6, do
 }
 void cf_se3_plus(const double* pose, const double* eps, double* out) { se3_plus(pose, eps, out); }
 void cf_so3_log(const double* C, double* phi) { so3_log(C, phi); }
+void cf_unit_plus(const double* x, const double* dl, double* out) { unit_plus(x, dl, out); }
+void cf_normal_block(const double* pose, const double* n, const double* obs, const double* W, double* r,
+                     double* Jc, double* Jn) {
+    normal_block(pose, n, obs, W, r, Jc, Jn);
+}
+void cf_intensity_block(const double* pose, const double* p, const double* n, const double* phong,
+                        const double* tex, const double* light, double colour, double w, int directional,
+                        double* r, double* Jc, double* Jp, double* Jn, double* Jk, double* Jt, double* Jl) {
+    intensity_block(pose, p, n, phong, tex[0], light, colour, w, directional != 0, r, Jc, Jp, Jn, Jk, Jt, Jl);
+}
 }
