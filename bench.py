@@ -49,46 +49,52 @@ def schur_algorithmic_flops(n_lm, L):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~4 ms from
+    a thread (an `nvidia-smi -lms` child needs longer to start than a 10-step region lasts)."""
+
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
-            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
-            "clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].strip().isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                    "hw_thermal_slowdown": 0x40}
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        try:
+                            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for name, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+        except Exception:
+            self._thr = None
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_peaks():
@@ -160,6 +166,38 @@ def workload_config(n_gpus):
             "l2": "inputs (640 MB of observations) larger than the 126 MB L2"}
 
 
+def bench_c4_windows(lib, n_windows=256, iters=6, reps=5):
+    """BASELINE.json config 4: 256 independent sliding windows (dataset_vo --window 2 shape: 2 poses,
+    ~150 landmarks, ~300 observations each) packed into ONE launch; latency-bound, so the figures
+    are windows/s and window-LM-iterations/s, not a roofline fraction."""
+    import ctypes as C
+    from ceres_slam_b200.problem import solve_batch
+    tracks = [syn.make_track(100, 15, 10, seed=42 + t) for t in range((n_windows + 89) // 90)]
+    wins = []
+    for tr in tracks:
+        for k1 in range(5, 95):
+            if len(wins) < n_windows:
+                wins.append(syn.window_of(tr, k1, k1 + 2))
+    kw = dict(max_num_iterations=iters, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    best_wall, dev_ms, n_it, n_obs = None, None, 0, sum(int(w["obs_cam"].size) for w in wins)
+    for rep in range(reps + 1):
+        probs = [syn.build_problem(w, backend="b200", **kw)[0] for w in wins]
+        t0 = time.perf_counter()
+        sums = solve_batch(probs)
+        wall = time.perf_counter() - t0
+        if rep > 0 and (best_wall is None or wall < best_wall):
+            best_wall, dev_ms = wall, sums[0].device_ms
+            n_it = sum(s.num_iterations for s in sums)
+        for p in probs:
+            p.close()
+    return {"windows": n_windows, "lm_iterations_per_window": iters, "observations": n_obs,
+            "kernel_ms": dev_ms, "windows_per_s_kernel": n_windows / (dev_ms * 1e-3),
+            "window_lm_iters_per_s_kernel": n_it / (dev_ms * 1e-3),
+            "e2e_wall_ms": best_wall * 1e3, "windows_per_s_e2e": n_windows / best_wall,
+            "note": "one CTA per window, LM loop on the device, one launch per batch; e2e = host packing + "
+                    "H2D + kernel + D2H through cslam_solve_batch"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +208,7 @@ def main():
     ap.add_argument("--cpu-scale", type=float, default=0.02, help="sample of config 5 timed on the CPU")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c4", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -284,6 +323,7 @@ def main():
                   "achieved_gbs": 272 * n_obs / (rj_ms * 1e-3) / 1e9,
                   "frac_of_hbm": 272 * n_obs / (rj_ms * 1e-3) / 1e9 / peak}
     p.close()
+    c4 = bench_c4_windows(lib) if (rank == 0 and not args.no_c4) else None
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     e2e = None
@@ -320,7 +360,7 @@ def main():
             "obs_per_s": value * n_obs, "n_obs": n_obs, "n_landmarks": n_lm, "n_poses": n_cam,
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
-            "resjac": resjac, "step_profile_ms": step_profile,
+            "resjac": resjac, "step_profile_ms": step_profile, "c4_windows": c4,
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},
             "setup_s": {"generate": gen_s, "upload_and_structure": upload_s},

@@ -62,7 +62,7 @@ def build_host_driver():
     host = os.path.join(HERE, "host")
     out = os.path.join(host, "dataset_vo_b200")
     src = os.path.join(host, "dataset_vo_b200.cpp")
-    deps = [src, os.path.join(host, "cslam_problem.hpp"), OUT]
+    deps = [src, os.path.join(host, "cslam_problem.hpp"), OUT, os.path.join(os.path.dirname(HERE), "include", "cslam_b200.h")]
     if _stale(out, deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + CSRC, "-lcslam_b200",
                                "-Wl,-rpath," + CSRC, "-Wl,-rpath,$ORIGIN/../csrc"])

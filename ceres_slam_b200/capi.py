@@ -49,6 +49,7 @@ class Options(C.Structure):
         ("device", C.c_int),
         ("profile_kernels", C.c_int),
         ("schur_path", C.c_int),
+        ("window_path", C.c_int),
     ]
 
 

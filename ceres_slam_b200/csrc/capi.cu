@@ -63,6 +63,7 @@ void cslam_options_init(cslam_options* o) {
     o->device = 0;
     o->profile_kernels = 0;
     o->schur_path = 0;
+    o->window_path = 0;
 }
 
 cslam_status cslam_problem_create(cslam_problem** out, const cslam_options* opt) {
@@ -202,6 +203,12 @@ cslam_status cslam_reset_state(cslam_problem* p) {
 
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary) {
     return guarded(p, [&](Engine& e) {
+        if (e.window_eligible() || e.opt.window_path == 2) {
+            // configs 1/2: a sliding window is one CTA with the LM loop on the device
+            Engine* one = &e;
+            cslam::solve_window_batch(&one, 1, summary);
+            return;
+        }
         e.upload();
         e.lm_begin();
         e.lm_iterate(e.opt.max_num_iterations + 1, false, summary);

@@ -869,7 +869,10 @@ void Engine::ensure_user_copy() {
     d_u_u.upload(u, stream);
     d_u_v.upload(v, stream);
     d_u_d.upload(d, stream);
-    d_u_W.upload(st_W, st_W_per_obs ? 9 * n : 9, stream);
+    if (st_W && n)
+        d_u_W.upload(st_W, st_W_per_obs ? 9 * n : 9, stream);
+    else
+        d_u_W.alloc(9);
     d_u_tile_lo.upload(tlo, stream);
     d_u_tile_n.upload(tn, stream);
     d_cam_free.upload(cam_free_h, stream);
@@ -1013,6 +1016,20 @@ void Engine::analyze(int n_ranks_, int rank_, cslam_structure_info* out) {
     out->landmark_id_sum = s;
 }
 
-bool Engine::window_eligible() const { return false; }
+void Engine::set_window_summary(const cslam_summary& s) {
+    lm = Lm();
+    lm.initial_cost = s.initial_cost;
+    lm.minimum_cost = s.final_cost;
+    lm.iteration = s.num_iterations;
+    lm.num_successful = s.num_successful_steps;
+    lm.num_unsuccessful = s.num_unsuccessful_steps;
+    lm.termination_type = s.termination_type;
+    lm.termination_reason = s.termination_reason;
+    lm.radius = s.final_radius;
+    lm.total_linear = s.total_linear_iterations;
+    lm.device_ms = s.device_ms;
+    lm.finished = true;
+    uploaded = begun = false;
+}
 
 }  // namespace cslam

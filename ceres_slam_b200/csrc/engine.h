@@ -143,6 +143,7 @@ class Engine {
 
     // small-problem description used by the batched window kernel
     bool window_eligible() const;
+    void set_window_summary(const cslam_summary& s);
 
    private:
     friend struct EngineAccess;

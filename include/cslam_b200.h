@@ -59,6 +59,8 @@ typedef struct cslam_options {
     int device;             /* CUDA device ordinal */
     int profile_kernels;    /* 1 = bracket every kernel class with CUDA events (cslam_get_profile) */
     int schur_path;         /* 0 = auto, 1 = force generic per-landmark kernel, 2 = force grouped */
+    int window_path;        /* small problems (<= 8 poses, exact solve): 0 = auto (one-CTA-per-window kernel
+                               with the LM loop on the device), 1 = never, 2 = require it */
 } cslam_options;
 
 typedef struct cslam_summary {
