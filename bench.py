@@ -28,8 +28,10 @@ sys.path.insert(0, ROOT)
 from ceres_slam_b200 import synthetic as syn  # noqa: E402
 
 METRIC = "BA LM iterations/s (full-batch stereo BA, C5: 20k poses x 2M landmarks x 20M obs)"
-LM_OPTS = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0,
-               linear_solver=1, preconditioner=1, eta=0.1, max_linear_solver_iterations=500)
+LM_EXACT = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0, linear_solver=0)
+LM_ITERATIVE = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0,
+                    linear_solver=1, preconditioner=1, eta=0.1, max_linear_solver_iterations=500)
+LM_OPTS = dict(LM_EXACT)  # main() switches to LM_ITERATIVE with --linear iterative
 
 
 def c5_track(scale=1.0, seed=42):
@@ -161,7 +163,9 @@ def c5_obs_count():
 def workload_config(n_gpus):
     return {"workload": "C5 large full-batch stereo BA: 20k poses x 2M landmarks x 20M observations "
                         "(synthetic loop track, 100 new landmarks/frame tracked 10 frames)",
-            "lm": "Ceres-semantics LM, ITERATIVE_SCHUR-equivalent (block-Jacobi PCG, eta=0.1), first pose constant",
+            "lm": ("Ceres-semantics LM, SPARSE_SCHUR-equivalent exact reduced solve (banded block Cholesky), "
+                   "first pose constant") if LM_OPTS["linear_solver"] == 0 else
+                  "Ceres-semantics LM, ITERATIVE_SCHUR-equivalent (block-Jacobi PCG, eta=0.1), first pose constant",
             "sharding": f"landmarks over {n_gpus} GPU(s), NCCL all-reduce of [S|g]" if n_gpus > 1 else "single GPU",
             "l2": "inputs (640 MB of observations) larger than the 126 MB L2"}
 
@@ -209,7 +213,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--linear", default="exact", choices=["exact", "iterative"],
+                    help="reduced-system solve: exact = SPARSE_SCHUR-equivalent (banded direct solver), "
+                         "iterative = ITERATIVE_SCHUR-equivalent (block-Jacobi PCG, eta = 0.1)")
     args = ap.parse_args()
+    LM_OPTS.clear()
+    LM_OPTS.update(LM_EXACT if args.linear == "exact" else LM_ITERATIVE)
     if args.impl == "reference":
         run_reference(args)
         return

@@ -20,7 +20,7 @@ LOG_NAMES = ("iteration", "cost", "cost_change", "gradient_max_norm", "step_norm
              "step_is_successful")
 
 K_RESJAC, K_COLNORM, K_SCHUR, K_FINALIZE, K_PCG, K_BACKSUB, K_ALLREDUCE, K_WINDOW, K_OTHER = range(9)
-KERNEL_CLASSES = ("resjac", "colnorm", "schur", "finalize", "pcg", "backsub", "allreduce",
+KERNEL_CLASSES = ("resjac", "colnorm", "schur", "finalize", "linear_solve", "backsub", "allreduce",
                   "window", "other")
 
 
@@ -49,6 +49,7 @@ class Options(C.Structure):
         ("device", C.c_int),
         ("profile_kernels", C.c_int),
         ("schur_path", C.c_int),
+        ("band_leaves", C.c_int),
         ("window_path", C.c_int),
     ]
 

@@ -63,6 +63,7 @@ void cslam_options_init(cslam_options* o) {
     o->device = 0;
     o->profile_kernels = 0;
     o->schur_path = 0;
+    o->band_leaves = 0;
     o->window_path = 0;
 }
 

@@ -473,6 +473,7 @@ void Engine::upload() {
     d_pp2.alloc(nv);
     d_prec.alloc(16);
     d_pscal.alloc(PS_COUNT);
+    plan_band_solver();
     d_scal2.alloc(SC_COUNT);
     if (!suns.empty()) d_suns.upload(suns, stream);
     if (!priors.empty()) d_priors.upload(priors, stream);
@@ -481,6 +482,51 @@ void Engine::upload() {
     begun = false;
     user_copy_ready = false;
     reset_state();
+}
+
+// Decide whether the exact solve can use the banded direct solver, and lay out its buffers.
+void Engine::plan_band_solver() {
+    band_active = false;
+    if (opt.linear_solver != 0 || n_free <= 0) return;
+    int w = 0;
+    for (int a = 0; a < n_free; ++a)
+        if (s_rowptr_h[a + 1] > s_rowptr_h[a]) w = std::max(w, s_col_h[s_rowptr_h[a + 1] - 1] - a);
+    if (w > kBandWmax) return;
+    if (w == 0) w = 1;  // a single camera: treat as bandwidth 1 (absent blocks read as zero)
+    const int n = n_free;
+    const int W = band_storage_width(w);  // separators and the shared-memory window use this width
+    // leaves cost ~1.2 us per block row, the separator chain ~1.5 us per separator row
+    int P = opt.band_leaves > 0 ? opt.band_leaves : int(std::lround(std::sqrt(0.8 * double(n) / W)));
+    P = std::min(P, 148);
+    P = std::min(P, n / (4 * W));
+    P = std::max(P, (n + 3499) / 3500);
+    P = std::max(P, 1);
+    int m = (n + P - 1) / P;
+    P = (n + m - 1) / m;
+    if (P > 1 && (m < 2 * W || n - (P - 1) * m < 1)) return;
+    band_w = w;
+    band_P = P;
+    band_m = m;
+    std::vector<int> idx(size_t(n) * (w + 1), -1);
+    for (int a = 0; a < n; ++a)
+        for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) idx[size_t(a) * (w + 1) + (s_col_h[e] - a)] = e;
+    d_band_idx.upload(idx, stream);
+    d_band_fail.alloc(1);
+    const size_t b = 6 * size_t(W), GC = P > 1 ? 1 + b : 1;
+    d_Lbuf.alloc(size_t(n) * (W + 1) * 36);
+    d_Xbuf.alloc(size_t(n) * 6 * GC);
+    d_Ta.alloc(size_t(P) * b * b);
+    d_Ca.alloc(size_t(P) * b * b);
+    d_Tb.alloc(size_t(P) * b * b);
+    d_fa.alloc(size_t(P) * b);
+    d_fb.alloc(size_t(P) * b);
+    const size_t n2 = size_t(std::max(P - 1, 1)) * W, W2 = 2 * size_t(W) - 1;
+    d_T2.alloc(n2 * (W2 + 1) * 36);
+    d_L2.alloc(n2 * (W2 + 1) * 36);
+    d_rhs2.alloc(6 * n2);
+    d_X2.alloc(6 * n2);
+    d_y2.alloc(6 * n2);
+    band_active = true;
 }
 
 void Engine::reset_state() {
@@ -588,7 +634,29 @@ void Engine::run_pcg(int* iters, bool* ok) {
         min_it = opt.min_linear_solver_iterations;
     }
     prof_begin(CSLAM_K_PCG);
-    launch_pcg_persistent(stream, B, d_pp2.p, d_prec.p, q_tol, r_tol, min_it, max_it, 10);
+    if (band_active) {
+        BandView V;
+        V.n = n_free;
+        V.w = band_w;
+        V.P = band_P;
+        V.m = band_m;
+        V.band_idx = d_band_idx.p;
+        V.S = d_S;
+        V.rhs = d_bp;
+        V.Lbuf = d_Lbuf.p;
+        V.Xbuf = d_Xbuf.p;
+        V.Ta = d_Ta.p;
+        V.Ca = d_Ca.p;
+        V.fa = d_fa.p;
+        V.Tb = d_Tb.p;
+        V.fb = d_fb.p;
+        V.y = d_yp.p;
+        V.fail = d_band_fail.p;
+        const BandScratch K{d_T2.p, d_rhs2.p, d_L2.p, d_X2.p, d_y2.p};
+        launch_band_solve(stream, V, K, d_pscal.p);
+    } else {
+        launch_pcg_persistent(stream, B, d_pp2.p, d_prec.p, q_tol, r_tol, min_it, max_it, 10);
+    }
     if (n_ranks > 1) {
         // every rank solved the same system; rank 0's iterate is adopted everywhere so that all
         // ranks keep bit-identical poses (and therefore take identical accept/reject decisions)

@@ -76,6 +76,26 @@ struct GroupView {
     const int* g_blk;            // S block index for slot pair (a <= b), -1 if a camera is constant
 };
 
+// Direct solve of a block-banded reduced camera system (kernels_band.cu).
+constexpr int kBandWmax = 12;    // widest half-bandwidth (in 6x6 blocks) the direct solver takes
+struct BandView {
+    int n, w, P, m;              // block rows, half-bandwidth, leaves, rows per leaf
+    const int* band_idx;         // [n][w+1] index of block (a, a+d) in the upper block-CSR, or -1
+    const double* S;             // block values (diagonal blocks full symmetric)
+    const double* rhs;           // [6 n]
+    double* Lbuf;                // [n][w+1][36] Cholesky factor, column k: Lkk, L_{k+1,k}, ...
+    double* Xbuf;                // [n][6][1+6w] Lkk^-1 [r | B_left] rows
+    double *Ta, *Ca, *fa;        // per leaf: separator block, coupling to the previous separator, rhs
+    double *Tb, *fb;             // per leaf: X^T X contribution to the separator before it
+    double* y;                   // [6 n] solution
+    int* fail;
+};
+// Level-2 (separator) system of the banded solver, dense band storage of width 2W-1.
+struct BandScratch {
+    double *T2, *rhs2, *L2, *X2, *y2;
+};
+int band_storage_width(int w);   // 3, 6, 9 or 12: the compiled window widths
+
 struct SunBlockData {
     uint32_t cam;
     double obs_c[3], ref_g[3], W[4], az_thresh, zen_thresh, huber;
@@ -189,6 +209,12 @@ class Engine {
     DBuf<double> d_Minv, d_diag_p;
     DBuf<double> d_yp, d_pr, d_pz, d_pp, d_pq, d_yl, d_pp2, d_prec;
     DBuf<double> d_pscal;
+    // banded direct solver (linear_solver == 0 and S block-banded)
+    int band_w = 0, band_P = 0, band_m = 0;
+    bool band_active = false;
+    DBuf<int> d_band_idx, d_band_fail;
+    DBuf<double> d_Lbuf, d_Xbuf, d_Ta, d_Ca, d_fa, d_Tb, d_fb, d_T2, d_rhs2, d_L2, d_X2, d_y2;
+    void plan_band_solver();
     DBuf<double> d_scal2;                  // scalars of the back-substitution pass
     DBuf<SunBlockData> d_suns;
     DBuf<PriorBlockData> d_priors;

@@ -53,6 +53,10 @@ struct PcgBufs {
 void launch_pcg_persistent(cudaStream_t s, const PcgBufs& B, double* pbuf2, double* rec3, double q_tol, double r_tol,
                            int min_iters, int max_iters, int reset_period);
 
+// K3b — direct solve of a block-banded reduced system (leaves + separators, kernels_band.cu);
+// writes ps[PS_ITERS] = 1 and ps[PS_FAIL] = 2 when a pivot is not positive
+void launch_band_solve(cudaStream_t s, const BandView& B, const BandScratch& K, double* ps);
+
 // K4 — Plus on the poses, back-substitution, model cost change, candidate cost
 void launch_pose_plus(cudaStream_t s, const DevView& v, const double* yp, double* poses_cand, double* scal2,
                       int count_cams);

@@ -49,8 +49,10 @@ typedef struct cslam_options {
     double gradient_tolerance;              /* 1e-10 */
     double parameter_tolerance;             /* 1e-8 */
     int jacobi_scaling;                     /* 1 */
-    int linear_solver;      /* 0 = exact Schur solve (SPARSE_SCHUR-equivalent: PCG run to 1e-14 or
-                               in-kernel Cholesky), 1 = ITERATIVE_SCHUR (PCG, Ceres Q-rule, eta) */
+    int linear_solver;      /* 0 = exact Schur solve (SPARSE_SCHUR-equivalent): block-banded Cholesky cut
+                               into leaves + separators when the reduced system is banded (half-bandwidth
+                               <= 12 blocks), in-kernel dense Cholesky for windows, else PCG run to 1e-15;
+                               1 = ITERATIVE_SCHUR (PCG, Ceres Q-rule, eta) */
     int preconditioner;     /* 0 = JACOBI (block diag of B), 1 = SCHUR_JACOBI (block diag of S) */
     double eta;                             /* 0.1 */
     int max_linear_solver_iterations;       /* 500 */
@@ -59,6 +61,8 @@ typedef struct cslam_options {
     int device;             /* CUDA device ordinal */
     int profile_kernels;    /* 1 = bracket every kernel class with CUDA events (cslam_get_profile) */
     int schur_path;         /* 0 = auto, 1 = force generic per-landmark kernel, 2 = force grouped */
+    int band_leaves;        /* exact solve of a banded reduced system: number of leaves the band is cut
+                               into (0 = auto) */
     int window_path;        /* small problems (<= 8 poses, exact solve): 0 = auto (one-CTA-per-window kernel
                                with the LM loop on the device), 1 = never, 2 = require it */
 } cslam_options;
