@@ -75,7 +75,8 @@ class Summary(C.Structure):
 class StructureInfo(C.Structure):
     _fields_ = [("n_free_cams", C.c_int), ("n_landmarks", C.c_int), ("n_observations", C.c_longlong),
                 ("nnz_blocks", C.c_int), ("pattern_hash", C.c_ulonglong), ("n_groups", C.c_int),
-                ("n_grouped_landmarks", C.c_int), ("n_work_items", C.c_int), ("landmark_id_sum", C.c_ulonglong)]
+                ("n_grouped_landmarks", C.c_int), ("n_work_items", C.c_int), ("landmark_id_sum", C.c_ulonglong),
+                ("layout_hash", C.c_ulonglong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

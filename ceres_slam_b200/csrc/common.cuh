@@ -32,18 +32,32 @@ struct DBuf {
     DBuf& operator=(const DBuf&) = delete;
     ~DBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFree(p);  // also valid for stream-ordered allocations (synchronises)
         p = nullptr;
         n = 0;
     }
-    void alloc(size_t count) {
+    // stream-ordered release: no device synchronisation, memory returns to the pool
+    void release_async(cudaStream_t s) {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    // With a stream the memory comes from the device's stream-ordered pool (cudaMallocAsync): no
+    // implicit synchronisation with in-flight copies / kernels and reuse across solves.
+    void alloc(size_t count, cudaStream_t s = nullptr) {
         if (count == n && p) return;
+        if (s) {
+            release_async(s);
+            n = count;
+            if (count) CSLAM_CUDA(cudaMallocAsync(&p, count * sizeof(T), s));
+            return;
+        }
         release();
         n = count;
         if (count) CSLAM_CUDA(cudaMalloc(&p, count * sizeof(T)));
     }
     void upload(const T* src, size_t count, cudaStream_t s) {
-        alloc(count);
+        alloc(count, s);
         if (count) CSLAM_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
     void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }

@@ -2,9 +2,13 @@
 // Levenberg-Marquardt loop that drives the kernels (Ceres trust-region semantics, SURVEY.md
 // App. B; the same rules the oracle restates in oracle/problem.hpp::solve).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <limits>
+#include <mutex>
 #include <numeric>
 #include <thread>
 
@@ -12,6 +16,21 @@
 #include "kernels.cuh"
 
 namespace cslam {
+
+namespace {
+// CSLAM_TIMING=1 prints host-side phase times of upload() to stderr
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(std::getenv("CSLAM_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[cslam timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
 
 Engine::Engine(const cslam_options& o) : opt(o) {}
 
@@ -38,6 +57,14 @@ static void ensure_device(Engine* e, cudaStream_t* stream, bool* own, cudaEvent_
     if (st != cudaSuccess || count == 0)
         throw CudaError("no CUDA device: the cslam_b200 back end has no CPU fallback");
     CSLAM_CUDA(cudaSetDevice(e->opt.device));
+    {
+        // keep freed blocks in the stream-ordered pool: repeated solves reuse them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, e->opt.device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (!*stream) {
         CSLAM_CUDA(cudaStreamCreateWithFlags(stream, cudaStreamNonBlocking));
         *own = true;
@@ -100,19 +127,59 @@ DevView Engine::view(const double* poses, const double* points) const {
 // Structure analysis: which blocks exist (dataset_vo.cpp:40-62), landmark-major order, the
 // co-visibility pattern of the reduced camera system, and this rank's landmark shard.
 // -------------------------------------------------------------------------------------------------
+// Run fn(t, lo, hi) over [0, n) split into contiguous chunks, one per host thread.
+template <class F>
+static void parallel_chunks(size_t n, size_t min_chunk, F&& fn) {
+    static const size_t hw = [] {
+        const char* e = std::getenv("CSLAM_THREADS");
+        const unsigned v = e ? unsigned(std::atoi(e)) : std::thread::hardware_concurrency();
+        return size_t(std::max(1u, std::min(32u, v)));
+    }();
+    const size_t nt = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
+    if (nt <= 1) {
+        fn(0, size_t(0), n);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::exception_ptr err;
+    std::mutex mu;
+    for (size_t t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+            try {
+                fn(int(t), n * t / nt, n * (t + 1) / nt);
+            } catch (...) {
+                std::lock_guard<std::mutex> g(mu);
+                err = std::current_exception();
+            }
+        });
+    for (auto& x : th) x.join();
+    if (err) std::rethrow_exception(err);
+}
+
 void Engine::build_structure() {
     if (!h_poses || n_poses == 0) throw std::invalid_argument("poses not set");
     if (n_st > 0 && (!h_points || n_points == 0)) throw std::invalid_argument("points not set");
     if (n_st >= (1ull << 32)) throw std::invalid_argument("more than 2^32 stereo blocks");
+    PhaseTimer bt;
+    const size_t kChunk = 1 << 16;
+    const int max_threads = 32;
+
+    // ---- which blocks exist; observations per point (dataset_vo.cpp:40-62) ----------------------
+    std::vector<uint32_t> cnt(n_points, 0);
+    std::vector<std::vector<uint8_t>> used_t(max_threads);
+    parallel_chunks(n_st, kChunk, [&](int t, size_t lo, size_t hi) {
+        std::vector<uint8_t>& used = used_t[t];
+        used.assign(n_poses, 0);
+        for (size_t i = lo; i < hi; ++i) {
+            const uint32_t c = st_cam[i], j = st_pt[i];
+            if (c >= n_poses || j >= n_points) throw std::invalid_argument("stereo block index out of range");
+            used[c] = 1;
+            __atomic_fetch_add(&cnt[j], 1u, __ATOMIC_RELAXED);
+        }
+    });
     std::vector<uint8_t> used(n_poses, 0);
-    std::vector<uint32_t> cnt(n_points, 0), mincam(n_points, 0xffffffffu);
-    for (uint64_t i = 0; i < n_st; ++i) {
-        const uint32_t c = st_cam[i], j = st_pt[i];
-        if (c >= n_poses || j >= n_points) throw std::invalid_argument("stereo block index out of range");
-        used[c] = 1;
-        cnt[j]++;
-        if (c < mincam[j]) mincam[j] = c;
-    }
+    for (auto& u : used_t)
+        for (size_t k = 0; k < u.size(); ++k) used[k] |= u[k];
     for (auto& s : suns) {
         if (s.cam >= n_poses) throw std::invalid_argument("sun block index out of range");
         used[s.cam] = 1;
@@ -129,9 +196,44 @@ void Engine::build_structure() {
             free_cams_h.push_back(int(k));
         }
     n_free = int(free_cams_h.size());
+    bt.lap("  count / free cams");
 
+    // ---- observation lists per point, each sorted by (camera, block index) ---------------------
+    std::vector<uint32_t> ptr_u(size_t(n_points) + 1, 0);
+    for (uint32_t j = 0; j < n_points; ++j) ptr_u[j + 1] = ptr_u[j] + cnt[j];
+    std::unique_ptr<uint32_t[]> obs_u_store(new uint32_t[std::max<size_t>(n_st, 1)]);  // filled in parallel below
+    uint32_t* const obs_u = obs_u_store.get();
+    {
+        std::vector<uint32_t> fill(ptr_u.begin(), ptr_u.end() - 1);
+        parallel_chunks(n_st, kChunk, [&](int, size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) obs_u[__atomic_fetch_add(&fill[st_pt[i]], 1u, __ATOMIC_RELAXED)] = uint32_t(i);
+        });
+    }
+    std::vector<uint32_t> mincam(n_points, 0xffffffffu);
+    parallel_chunks(n_points, 1 << 12, [&](int, size_t lo, size_t hi) {
+        for (size_t j = lo; j < hi; ++j) {
+            uint32_t* first = obs_u + ptr_u[j];
+            const uint32_t len = cnt[j];
+            if (!len) continue;
+            auto less = [&](uint32_t a, uint32_t b) { return st_cam[a] != st_cam[b] ? st_cam[a] < st_cam[b] : a < b; };
+            if (len <= 32) {
+                for (uint32_t x = 1; x < len; ++x) {
+                    const uint32_t key = first[x];
+                    uint32_t y = x;
+                    while (y > 0 && less(key, first[y - 1])) {
+                        first[y] = first[y - 1];
+                        --y;
+                    }
+                    first[y] = key;
+                }
+            } else {
+                std::sort(first, first + len, less);
+            }
+            mincam[j] = st_cam[first[0]];
+        }
+    });
     // landmarks in order of the first camera that sees them (counting sort, stable in user id)
-    std::vector<uint32_t> bucket(n_poses + 1, 0);
+    std::vector<uint32_t> bucket(size_t(n_poses) + 1, 0);
     uint32_t n_active = 0;
     for (uint32_t j = 0; j < n_points; ++j)
         if (cnt[j]) {
@@ -139,89 +241,64 @@ void Engine::build_structure() {
             n_active++;
         }
     for (uint32_t k = 0; k < n_poses; ++k) bucket[k + 1] += bucket[k];
+    const std::vector<uint32_t> bstart(bucket);  // landmarks [bstart[c], bstart[c+1]) start at camera c
     std::vector<uint32_t> all_lm(n_active);
-    std::vector<uint32_t> inv(n_points, 0xffffffffu);
     for (uint32_t j = 0; j < n_points; ++j)
-        if (cnt[j]) {
-            const uint32_t pos = bucket[mincam[j]]++;
-            all_lm[pos] = j;
-            inv[j] = pos;
-        }
+        if (cnt[j]) all_lm[bucket[mincam[j]]++] = j;
     std::vector<uint32_t> all_ptr(size_t(n_active) + 1, 0);
     for (uint32_t a = 0; a < n_active; ++a) all_ptr[a + 1] = all_ptr[a] + cnt[all_lm[a]];
-    std::vector<uint32_t> all_obs(n_st);
-    {
-        std::vector<uint32_t> fill(all_ptr.begin(), all_ptr.end() - 1);
-        for (uint64_t i = 0; i < n_st; ++i) all_obs[fill[inv[st_pt[i]]]++] = uint32_t(i);
-    }
+    auto lm_obs = [&](uint32_t a) { return obs_u + ptr_u[all_lm[a]]; };  // cnt[all_lm[a]] entries
+    auto lm_len = [&](uint32_t a) { return cnt[all_lm[a]]; };
+    bt.lap("  landmark-major order");
 
-    // ---- reduced camera system pattern (global: every rank derives the same one) ----
+    // ---- reduced camera system pattern (global: every rank derives the same one) ---------------
     {
-        // camera -> landmarks adjacency
-        std::vector<uint32_t> cptr(size_t(n_free) + 1, 0);
-        for (uint64_t i = 0; i < n_st; ++i) {
-            const int f = cam_free_h[st_cam[i]];
-            if (f >= 0) cptr[f + 1]++;
-        }
-        for (int f = 0; f < n_free; ++f) cptr[f + 1] += cptr[f];
-        std::vector<uint32_t> clm(cptr[n_free]);
-        {
-            std::vector<uint32_t> fill(cptr.begin(), cptr.end() - 1);
-            for (uint64_t i = 0; i < n_st; ++i) {
-                const int f = cam_free_h[st_cam[i]];
-                if (f >= 0) clm[fill[f]++] = inv[st_pt[i]];
-            }
-        }
-        std::vector<std::vector<int>> rows(n_free);
-        const int nt = int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
-        auto work = [&](int t) {
-            std::vector<int> stamp(n_free, -1);
-            for (int a = t; a < n_free; a += nt) {
-                std::vector<int>& row = rows[a];
-                row.push_back(a);
-                stamp[a] = a;
-                for (uint32_t x = cptr[a]; x < cptr[a + 1]; ++x) {
-                    const uint32_t lmk = clm[x];
-                    for (uint32_t e = all_ptr[lmk]; e < all_ptr[lmk + 1]; ++e) {
-                        const int b = cam_free_h[st_cam[all_obs[e]]];
-                        if (b > a && stamp[b] != a) {
-                            stamp[b] = a;
-                            row.push_back(b);
-                        }
-                    }
+        // pair (a, b), a <= b, of free cameras that share a landmark: bit (b - a) of row a's mask
+        // for offsets below 64, an explicit list beyond
+        std::vector<std::vector<uint64_t>> mask_t(max_threads);
+        std::vector<std::vector<std::pair<int, int>>> far_t(max_threads);
+        parallel_chunks(n_active, 1 << 12, [&](int t, size_t lo, size_t hi) {
+            std::vector<uint64_t>& mask = mask_t[t];
+            mask.assign(size_t(std::max(n_free, 1)), 0);
+            std::vector<int> fr;
+            for (size_t a = lo; a < hi; ++a) {
+                const uint32_t* ob = lm_obs(uint32_t(a));
+                const uint32_t len = lm_len(uint32_t(a));
+                fr.clear();
+                for (uint32_t k = 0; k < len; ++k) {
+                    const int f = cam_free_h[st_cam[ob[k]]];
+                    if (f >= 0 && (fr.empty() || fr.back() != f)) fr.push_back(f);
                 }
-                std::sort(row.begin(), row.end());
+                for (size_t x = 0; x < fr.size(); ++x)
+                    for (size_t y = x + 1; y < fr.size(); ++y) {
+                        const int d = fr[y] - fr[x];
+                        if (d < 64)
+                            mask[fr[x]] |= 1ull << d;
+                        else
+                            far_t[t].push_back({fr[x], fr[y]});
+                    }
             }
-        };
-        if (n_free < 64 || nt == 1) {
-            for (int t = 0; t < nt; ++t) work(t);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-            for (auto& x : th) x.join();
-        }
+        });
+        std::vector<uint64_t> mask(size_t(std::max(n_free, 1)), 0);
+        for (auto& m : mask_t)
+            for (size_t k = 0; k < m.size(); ++k) mask[k] |= m[k];
+        std::vector<std::pair<int, int>> far;
+        for (auto& f : far_t) far.insert(far.end(), f.begin(), f.end());
+        std::sort(far.begin(), far.end());
+        far.erase(std::unique(far.begin(), far.end()), far.end());
         s_rowptr_h.assign(size_t(n_free) + 1, 0);
-        for (int a = 0; a < n_free; ++a) s_rowptr_h[a + 1] = s_rowptr_h[a] + int(rows[a].size());
         s_col_h.clear();
-        s_col_h.reserve(s_rowptr_h[n_free]);
-        for (int a = 0; a < n_free; ++a) s_col_h.insert(s_col_h.end(), rows[a].begin(), rows[a].end());
+        size_t fx = 0;
+        for (int a = 0; a < n_free; ++a) {
+            s_col_h.push_back(a);
+            for (int d = 1; d < 64; ++d)
+                if (mask[a] >> d & 1) s_col_h.push_back(a + d);
+            for (; fx < far.size() && far[fx].first == a; ++fx) s_col_h.push_back(far[fx].second);
+            s_rowptr_h[a + 1] = int(s_col_h.size());
+        }
         nnzU = int(s_col_h.size());
     }
-
-    // every landmark's observations in ascending camera order (canonical camera list)
-    for (uint32_t a = 0; a < n_active; ++a) {
-        uint32_t* first = all_obs.data() + all_ptr[a];
-        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
-        for (uint32_t x = 1; x < len; ++x) {
-            const uint32_t key = first[x];
-            uint32_t y = x;
-            while (y > 0 && st_cam[first[y - 1]] > st_cam[key]) {
-                first[y] = first[y - 1];
-                --y;
-            }
-            first[y] = key;
-        }
-    }
+    bt.lap("  S pattern");
 
     // ---- this rank's shard: contiguous landmark range balanced by observation count ----
     uint32_t lo = 0, hi = n_active;
@@ -239,96 +316,103 @@ void Engine::build_structure() {
     n_obs = (long long)all_ptr[hi] - (long long)all_ptr[lo];
 
     // ---- group landmarks with identical camera lists (grouped Schur kernel) ----
-    struct Key {
-        uint64_t k1, hash;
-        uint32_t lm;
-    };
-    std::vector<Key> keys;
-    std::vector<uint32_t> rest;
-    keys.reserve(n_lm);
-    for (uint32_t a = lo; a < hi; ++a) {
-        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
-        bool ok = opt.schur_path != 1 && len <= uint32_t(kGroupLmax);
-        uint64_t h = 1469598103934665603ull;
-        uint32_t prev = 0xffffffffu;
-        for (uint32_t e = all_ptr[a]; e < all_ptr[a + 1]; ++e) {
-            const uint32_t c = st_cam[all_obs[e]];
-            if (c == prev) ok = false;  // the same camera twice: generic kernel only
-            prev = c;
-            h = (h ^ c) * 1099511628211ull;
+    // A landmark's sort key is (first camera, track length, hash of the camera list, index); the
+    // landmark order is already first-camera major, so each camera's bucket is sorted on its own.
+    const uint32_t nl = hi - lo;
+    std::vector<uint64_t> khash(nl);
+    std::vector<uint8_t> kok(nl);
+    parallel_chunks(nl, 1 << 12, [&](int, size_t x0, size_t x1) {
+        for (size_t x = x0; x < x1; ++x) {
+            const uint32_t a = lo + uint32_t(x);
+            const uint32_t* ob = lm_obs(a);
+            const uint32_t len = lm_len(a);
+            bool ok = opt.schur_path != 1 && len <= uint32_t(kGroupLmax);
+            uint64_t h = 1469598103934665603ull;
+            uint32_t prev = 0xffffffffu;
+            for (uint32_t k = 0; k < len; ++k) {
+                const uint32_t c = st_cam[ob[k]];
+                if (c == prev) ok = false;  // the same camera twice: generic kernel only
+                prev = c;
+                h = (h ^ c) * 1099511628211ull;
+            }
+            khash[x] = h;
+            kok[x] = ok ? 1 : 0;
         }
-        if (ok)
-            keys.push_back(Key{(uint64_t(st_cam[all_obs[all_ptr[a]]]) << 8) | len, h, a});
-        else
-            rest.push_back(a);
-    }
-    std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
-        if (x.k1 != y.k1) return x.k1 < y.k1;
-        if (x.hash != y.hash) return x.hash < y.hash;
-        return x.lm < y.lm;
     });
     auto same_cams = [&](uint32_t a, uint32_t b) {
-        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
+        const uint32_t len = lm_len(a);
+        const uint32_t *oa = lm_obs(a), *ob = lm_obs(b);
         for (uint32_t k = 0; k < len; ++k)
-            if (st_cam[all_obs[all_ptr[a] + k]] != st_cam[all_obs[all_ptr[b] + k]]) return false;
+            if (st_cam[oa[k]] != st_cam[ob[k]]) return false;
         return true;
     };
+    // per camera bucket: sorted eligible landmarks and the runs of identical camera lists
+    std::vector<uint32_t> sorted_a(nl);           // eligible landmarks, bucket by bucket
+    std::vector<uint32_t> sorted_off(size_t(n_poses) + 1, 0);
+    for (uint32_t c = 0; c < n_poses; ++c) {
+        const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
+        uint32_t k = 0;
+        for (uint32_t a = b0; a < b1; ++a) k += kok[a - lo];
+        sorted_off[c + 1] = sorted_off[c] + k;
+    }
+    std::vector<uint8_t> run_start(nl, 0);
+    parallel_chunks(n_poses, 16, [&](int, size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; ++c) {
+            const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
+            uint32_t* out = sorted_a.data() + sorted_off[c];
+            uint32_t k = 0;
+            for (uint32_t a = b0; a < b1; ++a)
+                if (kok[a - lo]) out[k++] = a;
+            std::sort(out, out + k, [&](uint32_t x, uint32_t y) {
+                const uint32_t lx = lm_len(x), ly = lm_len(y);
+                if (lx != ly) return lx < ly;
+                if (khash[x - lo] != khash[y - lo]) return khash[x - lo] < khash[y - lo];
+                return x < y;
+            });
+            for (uint32_t x = 0; x < k;) {
+                run_start[sorted_off[c] + x] = 1;
+                uint32_t y = x + 1;
+                while (y < k && lm_len(out[y]) == lm_len(out[x]) && khash[out[y] - lo] == khash[out[x] - lo] &&
+                       same_cams(out[x], out[y]))
+                    ++y;
+                x = y;
+            }
+        }
+    });
+    const uint32_t n_ok = sorted_off[n_poses];
     const size_t min_group = opt.schur_path == 2 ? 1 : 4;
     g_L_h.clear(); g_G_h.clear(); g_lm0_h.clear(); g_obs0_h.clear(); g_off_h.clear(); g_cams_h.clear();
     g_blk_off_h.clear(); g_blk_h.clear(); item_group_h.clear(); item_j0_h.clear(); item_n_h.clear();
-    lm_user_h.clear(); lm_base_h.clear(); lm_stride_h.clear(); lm_cnt_h.clear();
-    lm_user_h.reserve(n_lm); lm_base_h.reserve(n_lm); lm_stride_h.reserve(n_lm); lm_cnt_h.reserve(n_lm);
-    obs_user_h.assign(size_t(n_obs), 0);
-    uint32_t obs_cursor = 0;
+    std::vector<uint32_t> g_first;  // position of each group's first landmark in sorted_a
+    std::vector<uint8_t> grouped(nl, 0);
+    uint32_t obs_cursor = 0, lm_cursor = 0;
+    int cams_cursor = 0, blk_cursor = 0;
     std::vector<std::pair<int, int>> items_small, items_large;  // (group, j0)
-    for (size_t x = 0; x < keys.size();) {
-        size_t y = x + 1;
-        while (y < keys.size() && keys[y].k1 == keys[x].k1 && keys[y].hash == keys[x].hash && same_cams(keys[x].lm, keys[y].lm)) ++y;
-        const size_t G = y - x;
-        if (G < min_group) {
-            for (size_t z = x; z < y; ++z) rest.push_back(keys[z].lm);
-            x = y;
-            continue;
+    for (uint32_t x = 0; x < n_ok;) {
+        uint32_t y = x + 1;
+        while (y < n_ok && !run_start[y]) ++y;
+        const uint32_t G = y - x;
+        if (G >= min_group) {
+            const int L = int(lm_len(sorted_a[x]));
+            const int gid = int(g_L_h.size());
+            g_L_h.push_back(L);
+            g_G_h.push_back(int(G));
+            g_lm0_h.push_back(int(lm_cursor));
+            g_obs0_h.push_back(obs_cursor);
+            g_off_h.push_back(cams_cursor);
+            g_blk_off_h.push_back(blk_cursor);
+            g_first.push_back(x);
+            cams_cursor += L;
+            blk_cursor += L * (L + 1) / 2;
+            lm_cursor += G;
+            obs_cursor += G * uint32_t(L);
+            for (uint32_t j0 = 0; j0 < G; j0 += kItemMax) (L <= 10 ? items_small : items_large).push_back({gid, int(j0)});
+            max_group_L = std::max(max_group_L, L);
         }
-        const uint32_t a0 = keys[x].lm;
-        const int L = int(all_ptr[a0 + 1] - all_ptr[a0]);
-        const int gid = int(g_L_h.size());
-        g_L_h.push_back(L);
-        g_G_h.push_back(int(G));
-        g_lm0_h.push_back(int(lm_user_h.size()));
-        g_obs0_h.push_back(obs_cursor);
-        g_off_h.push_back(int(g_cams_h.size()));
-        g_blk_off_h.push_back(int(g_blk_h.size()));
-        int fr[kGroupLmax];
-        for (int i = 0; i < L; ++i) {
-            const int c = int(st_cam[all_obs[all_ptr[a0] + i]]);
-            g_cams_h.push_back(c);
-            fr[i] = cam_free_h[c];
-        }
-        for (int i = 0; i < L; ++i)
-            for (int k = i; k < L; ++k) {
-                int e = -1;
-                if (fr[i] >= 0 && fr[k] >= 0) {
-                    auto b0 = s_col_h.begin() + s_rowptr_h[fr[i]], b1 = s_col_h.begin() + s_rowptr_h[fr[i] + 1];
-                    e = int(std::lower_bound(b0, b1, fr[k]) - s_col_h.begin());
-                }
-                g_blk_h.push_back(e);
-            }
-        for (size_t z = x; z < y; ++z) {
-            const uint32_t a = keys[z].lm;
-            const uint32_t jl = uint32_t(z - x);
-            lm_user_h.push_back(all_lm[a]);
-            lm_base_h.push_back(obs_cursor + jl);
-            lm_stride_h.push_back(uint32_t(G));
-            lm_cnt_h.push_back(uint32_t(L));
-            for (int i = 0; i < L; ++i) obs_user_h[size_t(obs_cursor) + size_t(i) * G + jl] = all_obs[all_ptr[a] + i];
-        }
-        obs_cursor += uint32_t(G) * uint32_t(L);
-        for (size_t j0 = 0; j0 < G; j0 += kItemMax) (L <= 10 ? items_small : items_large).push_back({gid, int(j0)});
-        max_group_L = std::max(max_group_L, L);
         x = y;
     }
-    n_lm_grouped = int(lm_user_h.size());
+    const size_t n_groups = g_L_h.size();
+    n_lm_grouped = int(lm_cursor);
     n_items_small = int(items_small.size());
     for (auto* lst : {&items_small, &items_large})
         for (auto& it : *lst) {
@@ -336,17 +420,72 @@ void Engine::build_structure() {
             item_j0_h.push_back(it.second);
             item_n_h.push_back(std::min(kItemMax, g_G_h[it.first] - it.second));
         }
+    g_cams_h.assign(size_t(cams_cursor), 0);
+    g_blk_h.assign(size_t(blk_cursor), -1);
+    lm_user_h.assign(nl, 0);
+    lm_base_h.assign(nl, 0);
+    lm_stride_h.assign(nl, 0);
+    lm_cnt_h.assign(nl, 0);
+    obs_user_n = size_t(n_obs);
+    obs_user_h.reset(new uint32_t[std::max<size_t>(obs_user_n, 1)]);
+    parallel_chunks(n_groups, 8, [&](int, size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; ++g) {
+            const uint32_t x = g_first[g], G = uint32_t(g_G_h[g]);
+            const int L = g_L_h[g];
+            const uint32_t a0 = sorted_a[x];
+            const uint32_t* ob0 = lm_obs(a0);
+            int fr[kGroupLmax];
+            for (int i = 0; i < L; ++i) {
+                const int c = int(st_cam[ob0[i]]);
+                g_cams_h[size_t(g_off_h[g]) + i] = c;
+                fr[i] = cam_free_h[c];
+            }
+            int t = g_blk_off_h[g];
+            for (int i = 0; i < L; ++i)
+                for (int k = i; k < L; ++k) {
+                    int e = -1;
+                    if (fr[i] >= 0 && fr[k] >= 0) {
+                        auto b0 = s_col_h.begin() + s_rowptr_h[fr[i]], b1 = s_col_h.begin() + s_rowptr_h[fr[i] + 1];
+                        e = int(std::lower_bound(b0, b1, fr[k]) - s_col_h.begin());
+                    }
+                    g_blk_h[size_t(t++)] = e;
+                }
+            const uint32_t base = g_obs0_h[g];
+            for (uint32_t jl = 0; jl < G; ++jl) {
+                const uint32_t a = sorted_a[x + jl];
+                const size_t li = size_t(g_lm0_h[g]) + jl;
+                grouped[a - lo] = 1;
+                lm_user_h[li] = all_lm[a];
+                lm_base_h[li] = base + jl;
+                lm_stride_h[li] = G;
+                lm_cnt_h[li] = uint32_t(L);
+                const uint32_t* ob = lm_obs(a);
+                for (int i = 0; i < L; ++i) obs_user_h[size_t(base) + size_t(i) * G + jl] = ob[i];
+            }
+        }
+    });
+    bt.lap("  grouping");
     // the remaining landmarks, landmark-major, in first-camera order
-    std::sort(rest.begin(), rest.end());
-    for (uint32_t a : rest) {
-        const uint32_t len = all_ptr[a + 1] - all_ptr[a];
-        lm_user_h.push_back(all_lm[a]);
-        lm_base_h.push_back(obs_cursor);
-        lm_stride_h.push_back(1);
-        lm_cnt_h.push_back(len);
-        for (uint32_t k = 0; k < len; ++k) obs_user_h[size_t(obs_cursor) + k] = all_obs[all_ptr[a] + k];
-        obs_cursor += len;
+    {
+        std::vector<uint32_t> rest;
+        for (uint32_t x = 0; x < nl; ++x)
+            if (!grouped[x]) rest.push_back(lo + x);
+        std::vector<uint32_t> roff(rest.size() + 1, obs_cursor);
+        for (size_t r = 0; r < rest.size(); ++r) roff[r + 1] = roff[r] + lm_len(rest[r]);
+        parallel_chunks(rest.size(), 1 << 12, [&](int, size_t r0, size_t r1) {
+            for (size_t r = r0; r < r1; ++r) {
+                const uint32_t a = rest[r], len = lm_len(a);
+                const size_t li = size_t(n_lm_grouped) + r;
+                lm_user_h[li] = all_lm[a];
+                lm_base_h[li] = roff[r];
+                lm_stride_h[li] = 1;
+                lm_cnt_h[li] = len;
+                const uint32_t* ob = lm_obs(a);
+                for (uint32_t k = 0; k < len; ++k) obs_user_h[size_t(roff[r]) + k] = ob[k];
+            }
+        });
     }
+    bt.lap("  remaining landmarks");
 }
 
 GroupView Engine::group_view() const {
@@ -374,23 +513,47 @@ void Engine::launch_schur(const DevView& v, const LmDiag& dg) {
 }
 
 void Engine::upload() {
+    PhaseTimer pt;
     ensure_device(this, &stream, &own_stream, &ev_a, &ev_b, &ev_c, &ev_d, &h_pinned);
-    build_structure();
-    // gather the shard into landmark-major SoA arrays
-    std::vector<uint32_t> ocam(n_obs);
-    std::vector<double> ou(n_obs), ov(n_obs), od(n_obs), oW;
-    if (st_W_per_obs) oW.resize(9 * size_t(n_obs));
-    for (long long e = 0; e < n_obs; ++e) {
-        const uint32_t i = obs_user_h[e];
-        ocam[e] = st_cam[i];
-        ou[e] = st_uvd[3 * size_t(i)];
-        ov[e] = st_uvd[3 * size_t(i) + 1];
-        od[e] = st_uvd[3 * size_t(i) + 2];
-        if (st_W_per_obs) std::memcpy(&oW[9 * size_t(e)], st_W + 9 * size_t(i), 72);
+    pt.lap("ensure_device");
+    // The caller's arrays go to the device as they are, from a second host thread, while this
+    // thread analyses the structure; the landmark-major SoA layout is then gathered on the GPU.
+    cudaStream_t copy_stream = nullptr;
+    CSLAM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    d_raw_cam.alloc(std::max<size_t>(n_st, 1), stream);
+    d_raw_uvd.alloc(3 * std::max<size_t>(n_st, 1), stream);
+    d_raw_W.alloc(st_W_per_obs ? 9 * std::max<size_t>(n_st, 1) : 9, stream);
+    d_raw_pts.alloc(3 * std::max<size_t>(n_points, 1), stream);
+    CSLAM_CUDA(cudaStreamSynchronize(stream));  // the copy stream may touch them from here on
+    std::string copy_err;
+    const int dev = opt.device;
+    std::thread copier([&, dev]() {
+        auto chk = [&](cudaError_t e) {
+            if (e != cudaSuccess && copy_err.empty()) copy_err = cudaGetErrorString(e);
+        };
+        chk(cudaSetDevice(dev));
+        if (n_st) {
+            chk(cudaMemcpyAsync(d_raw_cam.p, st_cam, n_st * sizeof(uint32_t), cudaMemcpyHostToDevice, copy_stream));
+            chk(cudaMemcpyAsync(d_raw_uvd.p, st_uvd, 3 * n_st * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+            chk(cudaMemcpyAsync(d_raw_W.p, st_W, (st_W_per_obs ? 9 * n_st : 9) * sizeof(double), cudaMemcpyHostToDevice,
+                                copy_stream));
+        }
+        if (n_points)
+            chk(cudaMemcpyAsync(d_raw_pts.p, h_points, 3 * size_t(n_points) * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+        chk(cudaStreamSynchronize(copy_stream));
+    });
+    try {
+        build_structure();
+    } catch (...) {
+        copier.join();
+        cudaStreamDestroy(copy_stream);
+        throw;
     }
-    std::vector<double> pts(3 * size_t(n_lm));
-    for (int a = 0; a < n_lm; ++a) std::memcpy(&pts[3 * size_t(a)], h_points + 3 * size_t(lm_user_h[a]), 24);
-
+    pt.lap("build_structure");
+    copier.join();
+    cudaStreamDestroy(copy_stream);
+    if (!copy_err.empty()) throw CudaError("raw H2D copy failed: " + copy_err);
+    pt.lap("wait for raw H2D");
     d_cam_free.upload(cam_free_h, stream);
     auto up_i = [&](DBuf<int>& d, const std::vector<int>& h) { d.upload(h.empty() ? std::vector<int>(1, 0) : h, stream); };
     auto up_u = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) {
@@ -410,31 +573,52 @@ void Engine::upload() {
     up_i(d_g_cams, g_cams_h);
     up_i(d_g_blk_off, g_blk_off_h);
     up_i(d_g_blk, g_blk_h);
-    d_obs_cam.upload(ocam, stream);
-    d_obs_u.upload(ou, stream);
-    d_obs_v.upload(ov, stream);
-    d_obs_d.upload(od, stream);
-    if (st_W_per_obs)
-        d_obs_W.upload(oW, stream);
-    else if (n_st)
-        d_obs_W.upload(st_W, 9, stream);
-    else
-        d_obs_W.alloc(9);
+    // internal order <- caller's order, on the device
+    const size_t no = size_t(std::max<long long>(n_obs, 1));
+    d_obs_user.alloc(std::max<size_t>(obs_user_n, 1), stream);
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    {
+        // pageable H2D is bound by the host-side staging copy: split it over a few threads / streams
+        std::string perr;
+        const int dev = opt.device;
+        parallel_chunks(obs_user_n, size_t(1) << 21, [&](int, size_t c0, size_t c1) {
+            cudaStream_t cs = nullptr;
+            cudaError_t e = cudaSetDevice(dev);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d_obs_user.p + c0, obs_user_h.get() + c0, (c1 - c0) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+            if (cs) cudaStreamDestroy(cs);
+            if (e != cudaSuccess) perr = cudaGetErrorString(e);
+        });
+        if (!perr.empty()) throw CudaError("layout H2D failed: " + perr);
+    }
+    d_lm_user.upload(lm_user_h.empty() ? std::vector<uint32_t>(1, 0) : lm_user_h, stream);
+    pt.lap("  small arrays + perm H2D (enqueue)");
+    d_obs_cam.alloc(no, stream);
+    d_obs_u.alloc(no, stream);
+    d_obs_v.alloc(no, stream);
+    d_obs_d.alloc(no, stream);
+    d_obs_W.alloc(st_W_per_obs ? 9 * no : 9, stream);
+    d_points_init.alloc(3 * size_t(std::max(n_lm, 1)), stream);
+    launch_gather_layout(stream, n_obs, d_obs_user.p, d_raw_cam.p, d_raw_uvd.p, d_raw_W.p, st_W_per_obs, d_obs_cam.p,
+                         d_obs_u.p, d_obs_v.p, d_obs_d.p, d_obs_W.p, n_lm, d_lm_user.p, d_raw_pts.p, d_points_init.p);
+    pt.lap("  obs alloc + gather launch");
     d_poses_init.upload(h_poses, 12 * size_t(n_poses), stream);
-    d_points_init.upload(pts, stream);
-    d_poses.alloc(12 * size_t(n_poses));
-    d_poses_cand.alloc(12 * size_t(n_poses));
-    d_poses_best.alloc(12 * size_t(n_poses));
-    d_points.alloc(3 * size_t(n_lm));
-    d_points_cand.alloc(3 * size_t(n_lm));
-    d_points_best.alloc(3 * size_t(n_lm));
-    d_sc_p.alloc(6 * size_t(std::max(n_free, 1)));
-    d_sc_l.alloc(3 * size_t(std::max(n_lm, 1)));
-    d_cn_l.alloc(3 * size_t(std::max(n_lm, 1)));
-    d_gl.alloc(3 * size_t(std::max(n_lm, 1)));
-    d_yl.alloc(3 * size_t(std::max(n_lm, 1)));
+    d_poses.alloc(12 * size_t(n_poses), stream);
+    d_poses_cand.alloc(12 * size_t(n_poses), stream);
+    d_poses_best.alloc(12 * size_t(n_poses), stream);
+    d_points.alloc(3 * size_t(n_lm), stream);
+    d_points_cand.alloc(3 * size_t(n_lm), stream);
+    d_points_best.alloc(3 * size_t(n_lm), stream);
+    d_sc_p.alloc(6 * size_t(std::max(n_free, 1)), stream);
+    d_sc_l.alloc(3 * size_t(std::max(n_lm, 1)), stream);
+    d_cn_l.alloc(3 * size_t(std::max(n_lm, 1)), stream);
+    d_gl.alloc(3 * size_t(std::max(n_lm, 1)), stream);
+    d_yl.alloc(3 * size_t(std::max(n_lm, 1)), stream);
     d_s_rowptr.upload(s_rowptr_h, stream);
     d_s_col.upload(s_col_h.empty() ? std::vector<int>(1, 0) : s_col_h, stream);
+    pt.lap("  state allocs");
     // mirrored lists for the symmetric SpMV: row b lists (a, block) for every stored upper block
     // (a, b) with a < b, i.e. the blocks that act on it transposed
     {
@@ -455,29 +639,38 @@ void Engine::upload() {
         d_lt_rowptr.upload(ep, stream);
         d_lt_col.upload(ecb, stream);
     }
+    pt.lap("  mirrored lists");
     red_count = 36 * size_t(nnzU) + 36 * size_t(n_free) + 6 * size_t(n_free) + 6 * size_t(n_free) + SC_COUNT;
-    d_red.alloc(red_count);
+    d_red.alloc(red_count, stream);
     d_S = d_red.p;
     d_Bdiag = d_S + 36 * size_t(nnzU);
     d_bp = d_Bdiag + 36 * size_t(n_free);
     d_gp = d_bp + 6 * size_t(n_free);
     d_scal = d_gp + 6 * size_t(n_free);
-    d_Minv.alloc(36 * size_t(std::max(n_free, 1)));
-    d_diag_p.alloc(6 * size_t(std::max(n_free, 1)));
+    d_Minv.alloc(36 * size_t(std::max(n_free, 1)), stream);
+    d_diag_p.alloc(6 * size_t(std::max(n_free, 1)), stream);
     const size_t nv = 6 * size_t(std::max(n_free, 1));
-    d_yp.alloc(nv);
-    d_pr.alloc(nv);
-    d_pz.alloc(nv);
-    d_pp.alloc(nv);
-    d_pq.alloc(nv);
-    d_pp2.alloc(nv);
-    d_prec.alloc(16);
-    d_pscal.alloc(PS_COUNT);
+    d_yp.alloc(nv, stream);
+    d_pr.alloc(nv, stream);
+    d_pz.alloc(nv, stream);
+    d_pp.alloc(nv, stream);
+    d_pq.alloc(nv, stream);
+    d_pp2.alloc(nv, stream);
+    d_prec.alloc(16, stream);
+    d_pscal.alloc(PS_COUNT, stream);
+    pt.lap("  reduced system allocs");
     plan_band_solver();
-    d_scal2.alloc(SC_COUNT);
+    pt.lap("  plan_band_solver");
+    d_scal2.alloc(SC_COUNT, stream);
     if (!suns.empty()) d_suns.upload(suns, stream);
     if (!priors.empty()) d_priors.upload(priors, stream);
-    CSLAM_CUDA(cudaStreamSynchronize(stream));  // host staging vectors go out of scope
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    pt.lap("  stream sync");
+    d_raw_cam.release_async(stream);  // d_raw_pts stays: download() scatters the result into it
+    d_raw_uvd.release_async(stream);
+    d_raw_W.release_async(stream);
+    d_obs_user.release_async(stream);
+    pt.lap("alloc + layout H2D + gather");
     uploaded = true;
     begun = false;
     user_copy_ready = false;
@@ -511,21 +704,21 @@ void Engine::plan_band_solver() {
     for (int a = 0; a < n; ++a)
         for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) idx[size_t(a) * (w + 1) + (s_col_h[e] - a)] = e;
     d_band_idx.upload(idx, stream);
-    d_band_fail.alloc(1);
+    d_band_fail.alloc(1, stream);
     const size_t b = 6 * size_t(W), GC = P > 1 ? 1 + b : 1;
-    d_Lbuf.alloc(size_t(n) * (W + 1) * 36);
-    d_Xbuf.alloc(size_t(n) * 6 * GC);
-    d_Ta.alloc(size_t(P) * b * b);
-    d_Ca.alloc(size_t(P) * b * b);
-    d_Tb.alloc(size_t(P) * b * b);
-    d_fa.alloc(size_t(P) * b);
-    d_fb.alloc(size_t(P) * b);
+    d_Lbuf.alloc(size_t(n) * (W + 1) * 36, stream);
+    d_Xbuf.alloc(size_t(n) * 6 * GC, stream);
+    d_Ta.alloc(size_t(P) * b * b, stream);
+    d_Ca.alloc(size_t(P) * b * b, stream);
+    d_Tb.alloc(size_t(P) * b * b, stream);
+    d_fa.alloc(size_t(P) * b, stream);
+    d_fb.alloc(size_t(P) * b, stream);
     const size_t n2 = size_t(std::max(P - 1, 1)) * W, W2 = 2 * size_t(W) - 1;
-    d_T2.alloc(n2 * (W2 + 1) * 36);
-    d_L2.alloc(n2 * (W2 + 1) * 36);
-    d_rhs2.alloc(6 * n2);
-    d_X2.alloc(6 * n2);
-    d_y2.alloc(6 * n2);
+    d_T2.alloc(n2 * (W2 + 1) * 36, stream);
+    d_L2.alloc(n2 * (W2 + 1) * 36, stream);
+    d_rhs2.alloc(6 * n2, stream);
+    d_X2.alloc(6 * n2, stream);
+    d_y2.alloc(6 * n2, stream);
     band_active = true;
 }
 
@@ -542,13 +735,16 @@ void Engine::reset_state() {
 
 void Engine::download() {
     if (!uploaded) throw std::invalid_argument("download before upload");
-    std::vector<double> pts(3 * size_t(n_lm));
     std::vector<double> pos(12 * size_t(n_poses));
     CSLAM_CUDA(cudaMemcpyAsync(pos.data(), d_poses_best.p, d_poses_best.bytes(), cudaMemcpyDeviceToHost, stream));
-    if (n_lm) CSLAM_CUDA(cudaMemcpyAsync(pts.data(), d_points_best.p, d_points_best.bytes(), cudaMemcpyDeviceToHost, stream));
+    if (n_lm) {
+        // best landmarks back into the caller's point order on the device, then one copy straight
+        // into the caller's array (points this rank does not own keep the values it uploaded)
+        launch_scatter_points(stream, n_lm, d_lm_user.p, d_points_best.p, d_raw_pts.p);
+        CSLAM_CUDA(cudaMemcpyAsync(h_points, d_raw_pts.p, 3 * size_t(n_points) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     for (int k : free_cams_h) std::memcpy(h_poses + 12 * size_t(k), &pos[12 * size_t(k)], 96);
-    for (int a = 0; a < n_lm; ++a) std::memcpy(h_points + 3 * size_t(lm_user_h[a]), &pts[3 * size_t(a)], 24);
 }
 
 void Engine::allreduce_system() {
@@ -678,9 +874,8 @@ void Engine::lm_begin() {
     lm = Lm();
     log.clear();
     // unit scaling for the initial pass
-    std::vector<double> ones(std::max<size_t>({6 * size_t(std::max(n_free, 1)), 3 * size_t(std::max(n_lm, 1))}), 1.0);
-    CSLAM_CUDA(cudaMemcpyAsync(d_sc_p.p, ones.data(), d_sc_p.bytes(), cudaMemcpyHostToDevice, stream));
-    CSLAM_CUDA(cudaMemcpyAsync(d_sc_l.p, ones.data(), d_sc_l.bytes(), cudaMemcpyHostToDevice, stream));
+    launch_fill(stream, d_sc_p.p, d_sc_p.n, 1.0);
+    launch_fill(stream, d_sc_l.p, d_sc_l.n, 1.0);
     DevView v = view(d_poses.p, d_points.p);
     prof_begin(CSLAM_K_COLNORM);
     d_red.zero(stream);
@@ -1082,6 +1277,20 @@ void Engine::analyze(int n_ranks_, int rank_, cslam_structure_info* out) {
     unsigned long long s = 0;
     for (uint32_t id : lm_user_h) s += id;
     out->landmark_id_sum = s;
+    unsigned long long lh = 1469598103934665603ull;
+    auto mix = [&](const auto& vec) {
+        for (auto v : vec) lh = (lh ^ (unsigned long long)(unsigned)v) * 1099511628211ull;
+        lh = (lh ^ 0xffull) * 1099511628211ull;
+    };
+    mix(cam_free_h); mix(free_cams_h); mix(lm_user_h); mix(lm_base_h); mix(lm_stride_h); mix(lm_cnt_h);
+    for (size_t i = 0; i < obs_user_n; ++i) lh = (lh ^ (unsigned long long)obs_user_h[i]) * 1099511628211ull;
+    lh = (lh ^ 0xffull) * 1099511628211ull;
+    mix(item_group_h); mix(item_j0_h); mix(item_n_h); mix(g_L_h); mix(g_G_h); mix(g_lm0_h);
+    mix(g_obs0_h); mix(g_off_h); mix(g_cams_h); mix(g_blk_off_h); mix(g_blk_h);
+    lh = (lh ^ (unsigned long long)n_lm_grouped) * 1099511628211ull;
+    lh = (lh ^ (unsigned long long)n_items_small) * 1099511628211ull;
+    lh = (lh ^ (unsigned long long)max_group_L) * 1099511628211ull;
+    out->layout_hash = lh;
 }
 
 void Engine::set_window_summary(const cslam_summary& s) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -176,7 +177,10 @@ class Engine {
     std::vector<uint32_t> lm_user_h;      // internal landmark -> user point index
     std::vector<uint32_t> lm_base_h, lm_stride_h, lm_cnt_h;
     int n_lm_grouped = 0;                 // internal landmarks [0, n_lm_grouped) belong to groups
-    std::vector<uint32_t> obs_user_h;     // internal obs -> user obs index
+    // internal obs -> user obs index; not value-initialised (80 MB for config 5: the pages are first
+    // touched by the parallel fill, not by one thread zeroing them)
+    std::unique_ptr<uint32_t[]> obs_user_h;
+    size_t obs_user_n = 0;
     std::vector<int> s_rowptr_h, s_col_h;
     int n_free = 0, n_lm = 0;
     long long n_obs = 0;
@@ -189,6 +193,9 @@ class Engine {
     DBuf<double> d_points, d_points_cand, d_points_best, d_points_init;
     DBuf<int> d_cam_free;
     DBuf<uint32_t> d_lm_base, d_lm_stride, d_lm_cnt, d_obs_cam;
+    // caller-order staging on the device (upload gathers from it, download scatters into d_raw_pts)
+    DBuf<uint32_t> d_raw_cam, d_obs_user, d_lm_user;
+    DBuf<double> d_raw_uvd, d_raw_W, d_raw_pts;
     // grouped Schur path
     std::vector<int> item_group_h, item_j0_h, item_n_h, g_L_h, g_G_h, g_lm0_h, g_off_h, g_cams_h, g_blk_off_h, g_blk_h;
     std::vector<uint32_t> g_obs0_h;

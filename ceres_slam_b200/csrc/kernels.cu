@@ -785,6 +785,47 @@ __global__ void camonly_eval_kernel(DevView v, const SunBlockData* suns, int n_s
     }
 }
 
+__global__ void gather_obs_kernel(long long n_obs, const uint32_t* __restrict__ obs_user, const uint32_t* __restrict__ raw_cam,
+                                  const double* __restrict__ raw_uvd, const double* __restrict__ raw_W, int W_per_obs,
+                                  uint32_t* __restrict__ obs_cam, double* __restrict__ u, double* __restrict__ v,
+                                  double* __restrict__ d, double* __restrict__ W) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_obs; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = obs_user[e];
+        obs_cam[e] = raw_cam[i];
+        u[e] = raw_uvd[3 * i];
+        v[e] = raw_uvd[3 * i + 1];
+        d[e] = raw_uvd[3 * i + 2];
+        if (W_per_obs) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) W[9 * e + k] = raw_W[9 * i + k];
+        }
+    }
+    if (!W_per_obs && blockIdx.x == 0 && threadIdx.x < 9) W[threadIdx.x] = raw_W[threadIdx.x];
+}
+__global__ void gather_points_kernel(int n_lm, const uint32_t* __restrict__ lm_user, const double* __restrict__ raw_pts,
+                                     double* __restrict__ points) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n_lm) {
+        const long long j = lm_user[a];
+        points[3ll * a] = raw_pts[3 * j];
+        points[3ll * a + 1] = raw_pts[3 * j + 1];
+        points[3ll * a + 2] = raw_pts[3 * j + 2];
+    }
+}
+__global__ void scatter_points_kernel(int n_lm, const uint32_t* __restrict__ lm_user, const double* __restrict__ points,
+                                      double* __restrict__ raw_pts) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n_lm) {
+        const long long j = lm_user[a];
+        raw_pts[3 * j] = points[3ll * a];
+        raw_pts[3 * j + 1] = points[3ll * a + 1];
+        raw_pts[3 * j + 2] = points[3ll * a + 2];
+    }
+}
+__global__ void fill_kernel(double* p, size_t n, double value) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = value;
+}
+
 inline int grid_for(long long n, int block, int max_blocks) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -915,6 +956,35 @@ void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, con
     const long long n = (long long)v.n_cams + (lm_hi - lm_lo);
     if (n <= 0) return;
     gradnorm_kernel<<<int((n + 255) / 256), 256, 0, s>>>(v, lm_lo, lm_hi, gp_scaled, gl_scaled, scal, count_cams);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_gather_layout(cudaStream_t s, long long n_obs, const uint32_t* obs_user, const uint32_t* raw_cam,
+                          const double* raw_uvd, const double* raw_W, int W_per_obs, uint32_t* obs_cam, double* u,
+                          double* v, double* d, double* W, int n_lm, const uint32_t* lm_user, const double* raw_pts,
+                          double* points) {
+    gather_obs_kernel<<<grid_for(std::max<long long>(n_obs, 1), 256, 16 * kSMs), 256, 0, s>>>(n_obs, obs_user, raw_cam, raw_uvd, raw_W,
+                                                                                   W_per_obs, obs_cam, u, v, d, W);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+    if (n_lm > 0) {
+        gather_points_kernel<<<(n_lm + 255) / 256, 256, 0, s>>>(n_lm, lm_user, raw_pts, points);
+        CSLAM_LAUNCHED(1);
+        CSLAM_CUDA(cudaGetLastError());
+    }
+}
+
+void launch_scatter_points(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* raw_pts) {
+    if (n_lm <= 0) return;
+    scatter_points_kernel<<<(n_lm + 255) / 256, 256, 0, s>>>(n_lm, lm_user, points, raw_pts);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_fill(cudaStream_t s, double* p, size_t n, double value) {
+    if (!n) return;
+    fill_kernel<<<grid_for((long long)n, 256, 8 * kSMs), 256, 0, s>>>(p, n, value);
     CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }

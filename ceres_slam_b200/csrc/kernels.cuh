@@ -69,6 +69,15 @@ void launch_camonly_step(cudaStream_t s, const DevView& v, const SunBlockData* s
 void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const double* gp_scaled,
                      const double* gl_scaled, double* scal, int count_cams);
 
+// layout: internal (landmark-major / slot-major) observation and landmark arrays gathered from the
+// caller-order arrays on the device; the reverse for the landmarks at download
+void launch_gather_layout(cudaStream_t s, long long n_obs, const uint32_t* obs_user, const uint32_t* raw_cam,
+                          const double* raw_uvd, const double* raw_W, int W_per_obs, uint32_t* obs_cam, double* u,
+                          double* v, double* d, double* W, int n_lm, const uint32_t* lm_user, const double* raw_pts,
+                          double* points);
+void launch_scatter_points(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* raw_pts);
+void launch_fill(cudaStream_t s, double* p, size_t n, double value);
+
 double measure_fp64_peak_tflops(int device);
 extern std::atomic<unsigned long long> g_kernel_launches;  // every kernel this library launches
 

@@ -1056,10 +1056,10 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         d_poses.upload(poses, stream);
         d_cam_free.upload(cam_free, stream);
         d_pts.upload(pts, stream);
-        d_pts_cand.alloc(pts.size());
-        d_pts_best.alloc(pts.size());
-        d_scl.alloc(pts.size());
-        d_gl.alloc(pts.size());
+        d_pts_cand.alloc(pts.size(), stream);
+        d_pts_best.alloc(pts.size(), stream);
+        d_scl.alloc(pts.size(), stream);
+        d_gl.alloc(pts.size(), stream);
         d_lm_ptr.upload(lm_ptr, stream);
         d_ocam.upload(ocam, stream);
         d_ou.upload(ou, stream);
@@ -1068,9 +1068,9 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         d_oW.upload(oW, stream);
         d_suns.upload(suns, stream);
         d_priors.upload(priors, stream);
-        d_sum.alloc(nw);
-        d_logs.alloc(size_t(log_total) * CSLAM_LOG_COLS);
-        d_log_rows.alloc(nw);
+        d_sum.alloc(nw, stream);
+        d_logs.alloc(size_t(log_total) * CSLAM_LOG_COLS, stream);
+        d_log_rows.alloc(nw, stream);
         WinBufs B;
         B.desc = d_desc.p;
         B.poses = d_poses.p;

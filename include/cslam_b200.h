@@ -211,6 +211,7 @@ typedef struct cslam_structure_info {
     int n_grouped_landmarks;
     int n_work_items;
     unsigned long long landmark_id_sum; /* sum of the caller's point indices in the shard */
+    unsigned long long layout_hash;     /* FNV-1a over the whole internal layout (orders, groups, work items) */
 } cslam_structure_info;
 cslam_status cslam_analyze(cslam_problem* p, int n_ranks, int rank, cslam_structure_info* out);
 
