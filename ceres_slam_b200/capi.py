@@ -110,6 +110,12 @@ _COMMON = {
     "get_iteration_log": (C.c_int, [_h, _dp, C.c_int, _ip]),
 }
 _PRODUCT_ONLY = {
+    "set_vertices": (C.c_int, [_h, C.c_uint32, _dp, _dp, _u32p]),
+    "set_materials": (C.c_int, [_h, C.c_uint32, _dp]),
+    "set_light": (C.c_int, [_h, _dp, C.c_int]),
+    "add_phong": (C.c_int, [_h, C.c_uint64, _u32p, _u32p, _dp, C.c_double, _dp, _dp]),
+    "evaluate_phong": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "time_phong": (C.c_int, [_h, C.c_int, _dp]),
     "upload": (C.c_int, [_h]),
     "lm_begin": (C.c_int, [_h]),
     "lm_iterate": (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(Summary)]),

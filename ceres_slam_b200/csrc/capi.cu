@@ -186,6 +186,59 @@ cslam_status cslam_evaluate(cslam_problem* p, int apply_loss, double* cost, doub
     });
 }
 
+cslam_status cslam_set_vertices(cslam_problem* p, uint32_t n, double* normals3, double* textures,
+                                const uint32_t* material_id) {
+    return guarded(p, [&](Engine& e) {
+        if (n && (!normals3 || !textures || !material_id)) throw std::invalid_argument("vertices: null array");
+        e.h_normals = normals3;
+        e.h_textures = textures;
+        e.h_material_id = material_id;
+        e.n_vertices = n;
+        e.phong_ready = false;
+    });
+}
+cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double* phong3) {
+    return guarded(p, [&](Engine& e) {
+        if (!phong3 || n_materials == 0) throw std::invalid_argument("materials: null or empty");
+        e.h_phong = phong3;
+        e.n_materials = n_materials;
+    });
+}
+cslam_status cslam_set_light(cslam_problem* p, double* light3, int directional) {
+    return guarded(p, [&](Engine& e) {
+        if (!light3) throw std::invalid_argument("light: null");
+        e.h_light = light3;
+        e.light_directional = directional ? 1 : 0;
+    });
+}
+cslam_status cslam_add_phong(cslam_problem* p, uint64_t n, const uint32_t* cam, const uint32_t* vertex,
+                             const double* intensity, double int_stiffness, const double* normal_obs3,
+                             const double* W_normal9) {
+    return guarded(p, [&](Engine& e) {
+        if (n && (!cam || !vertex || !intensity || !normal_obs3 || !W_normal9)) throw std::invalid_argument("phong: null array");
+        for (uint64_t i = 0; i < n; ++i)
+            if (cam[i] >= e.n_poses || vertex[i] >= e.n_points) throw std::invalid_argument("lighting block index out of range");
+        e.n_ph = n;
+        e.ph_cam = cam;
+        e.ph_vertex = vertex;
+        e.ph_intensity = intensity;
+        e.ph_normal_obs = normal_obs3;
+        e.ph_int_stiffness = int_stiffness;
+        std::memcpy(e.ph_W_normal, W_normal9, 72);
+        e.phong_ready = false;
+    });
+}
+cslam_status cslam_evaluate_phong(cslam_problem* p, double* cost, double* r_int, double* J_int, double* r_normal,
+                                  double* Jpose_normal, double* Jn_normal) {
+    return guarded(p, [&](Engine& e) { e.evaluate_phong(cost, r_int, J_int, r_normal, Jpose_normal, Jn_normal); });
+}
+cslam_status cslam_time_phong(cslam_problem* p, int reps, double* ms_per_launch) {
+    return guarded(p, [&](Engine& e) {
+        if (!ms_per_launch || reps <= 0) throw std::invalid_argument("time_phong: bad arguments");
+        *ms_per_launch = e.time_phong(reps);
+    });
+}
+
 cslam_status cslam_upload(cslam_problem* p) {
     return guarded(p, [&](Engine& e) { e.upload(); });
 }

@@ -1189,6 +1189,99 @@ void Engine::evaluate(int apply_loss, double* cost, double* r_st, double* Jc_st,
     if (cost) *cost = c;
 }
 
+// -------------------------------------------------------------------------------------------------
+// lighting blocks: ceres::Problem::Evaluate over the intensity and normal residual blocks
+// -------------------------------------------------------------------------------------------------
+void Engine::ensure_phong() {
+    ensure_device(this, &stream, &own_stream, &ev_a, &ev_b, &ev_c, &ev_d, &h_pinned);
+    if (!h_poses || !h_points) throw std::invalid_argument("poses / points not set");
+    if (!h_normals || !h_textures || !h_material_id || !h_phong || !h_light)
+        throw std::invalid_argument("vertices / materials / light not set");
+    if (n_vertices != n_points) throw std::invalid_argument("one normal / texture / material id per point expected");
+    for (uint32_t j = 0; j < n_vertices; ++j)
+        if (h_material_id[j] >= n_materials) throw std::invalid_argument("material id out of range");
+    if (!phong_ready) {
+        for (uint64_t i = 0; i < n_ph; ++i)
+            if (ph_cam[i] >= n_poses || ph_vertex[i] >= n_points) throw std::invalid_argument("lighting block index out of range");
+        std::vector<int> cf(n_poses);
+        for (uint32_t k = 0; k < n_poses; ++k) cf[k] = pose_const[k] ? -1 : int(k);
+        d_ph_cam_free.upload(cf, stream);
+        d_ph_cam.upload(ph_cam, n_ph, stream);
+        d_ph_vertex.upload(ph_vertex, n_ph, stream);
+        d_ph_int.upload(ph_intensity, n_ph, stream);
+        d_ph_nobs.upload(ph_normal_obs, 3 * n_ph, stream);
+        d_ph_mat.upload(h_material_id, n_vertices, stream);
+        d_ph_W.upload(ph_W_normal, 9, stream);
+        d_ph_rI.alloc(n_ph, stream);
+        d_ph_JI.alloc(19 * n_ph, stream);
+        d_ph_rN.alloc(3 * n_ph, stream);
+        d_ph_JNc.alloc(18 * n_ph, stream);
+        d_ph_JNn.alloc(9 * n_ph, stream);
+        if (!d_scal2.p) d_scal2.alloc(SC_COUNT, stream);
+        phong_ready = true;
+    }
+    // parameter values as they are in the caller's arrays right now
+    d_ph_poses.upload(h_poses, 12 * size_t(n_poses), stream);
+    d_ph_points.upload(h_points, 3 * size_t(n_points), stream);
+    d_ph_normals.upload(h_normals, 3 * size_t(n_vertices), stream);
+    d_ph_tex.upload(h_textures, n_vertices, stream);
+    d_ph_phong.upload(h_phong, 3 * size_t(n_materials), stream);
+    d_ph_light.upload(h_light, 3, stream);
+}
+
+PhongView Engine::phong_view() {
+    PhongView v;
+    v.n = (long long)n_ph;
+    v.cam = d_ph_cam.p;
+    v.vertex = d_ph_vertex.p;
+    v.material_id = d_ph_mat.p;
+    v.intensity = d_ph_int.p;
+    v.normal_obs = d_ph_nobs.p;
+    v.poses = d_ph_poses.p;
+    v.points = d_ph_points.p;
+    v.normals = d_ph_normals.p;
+    v.texture = d_ph_tex.p;
+    v.phong = d_ph_phong.p;
+    v.light = d_ph_light.p;
+    v.W_normal = d_ph_W.p;
+    v.cam_free = d_ph_cam_free.p;
+    v.int_stiffness = ph_int_stiffness;
+    v.directional = light_directional;
+    return v;
+}
+
+void Engine::evaluate_phong(double* cost, double* r_int, double* J_int, double* r_n, double* Jc_n, double* Jn_n) {
+    ensure_phong();
+    d_scal2.zero(stream);
+    launch_phong_eval(stream, phong_view(), d_ph_rI.p, d_ph_JI.p, d_ph_rN.p, d_ph_JNc.p, d_ph_JNn.p, d_scal2.p);
+    auto d2h = [&](double* dst, const double* src, size_t count) {
+        if (dst && count) CSLAM_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    };
+    d2h(r_int, d_ph_rI.p, n_ph);
+    d2h(J_int, d_ph_JI.p, 19 * n_ph);
+    d2h(r_n, d_ph_rN.p, 3 * n_ph);
+    d2h(Jc_n, d_ph_JNc.p, 18 * n_ph);
+    d2h(Jn_n, d_ph_JNn.p, 9 * n_ph);
+    double c = 0;
+    read_scalars(d_scal2.p, &c, 1);
+    if (cost) *cost = c;
+}
+
+double Engine::time_phong(int reps) {
+    ensure_phong();
+    d_scal2.zero(stream);
+    const PhongView v = phong_view();
+    auto go = [&]() { launch_phong_eval(stream, v, d_ph_rI.p, d_ph_JI.p, d_ph_rN.p, d_ph_JNc.p, d_ph_JNn.p, d_scal2.p); };
+    for (int i = 0; i < 3; ++i) go();
+    CSLAM_CUDA(cudaEventRecord(ev_a, stream));
+    for (int i = 0; i < reps; ++i) go();
+    CSLAM_CUDA(cudaEventRecord(ev_b, stream));
+    CSLAM_CUDA(cudaEventSynchronize(ev_b));
+    float ms = 0;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, ev_a, ev_b));
+    return double(ms) / reps;
+}
+
 double Engine::time_resjac(int reps) {
     ensure_user_copy();
     d_poses_cand.upload(h_poses, 12 * size_t(n_poses), stream);

@@ -106,6 +106,17 @@ struct PriorBlockData {
     double Tref[12], W[36];
 };
 
+// Lighting blocks (kernels_phong.cu): raw device pointers, caller's block order.
+struct PhongView {
+    long long n;
+    const uint32_t *cam, *vertex, *material_id;
+    const double *intensity, *normal_obs;
+    const double *poses, *points, *normals, *texture, *phong, *light, *W_normal;
+    const int* cam_free;
+    double int_stiffness;
+    int directional;
+};
+
 // LM diagonal parameters: D^2 = clamp(diag, min, max) * inv_radius (levenberg_marquardt_strategy)
 struct LmDiag {
     double inv_radius, min_diag, max_diag;
@@ -135,6 +146,22 @@ class Engine {
     const double* st_W = nullptr;
     int st_W_per_obs = 0;
     std::vector<SunBlockData> suns;
+    // lighting blocks (dataset_ba_phong)
+    double* h_normals = nullptr;
+    double* h_textures = nullptr;
+    const uint32_t* h_material_id = nullptr;
+    uint32_t n_vertices = 0;
+    double* h_phong = nullptr;
+    uint32_t n_materials = 0;
+    double* h_light = nullptr;
+    int light_directional = 0;
+    uint64_t n_ph = 0;
+    const uint32_t* ph_cam = nullptr;
+    const uint32_t* ph_vertex = nullptr;
+    const double* ph_intensity = nullptr;
+    const double* ph_normal_obs = nullptr;
+    double ph_int_stiffness = 1.0;
+    double ph_W_normal[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     std::vector<PriorBlockData> priors;
     std::string err;
 
@@ -151,6 +178,8 @@ class Engine {
     void evaluate(int apply_loss, double* cost, double* r_st, double* Jc_st, double* Jp_st, double* r_sun,
                   double* J_sun, double* r_pr, double* J_pr);
     double time_resjac(int reps);
+    void evaluate_phong(double* cost, double* r_int, double* J_int, double* r_n, double* Jc_n, double* Jn_n);
+    double time_phong(int reps);
     double time_schur(int reps);
     void fill_summary(cslam_summary* s) const;
     void get_reduced_sizes(int* nf, int* nnz) const;
@@ -161,6 +190,7 @@ class Engine {
     std::vector<LmRow> log;
     cslam_profile prof{};
     bool uploaded = false, begun = false;
+    bool phong_ready = false;             // block-index arrays of the lighting blocks are on the device
 
     // small-problem description used by the batched window kernel
     bool window_eligible() const;
@@ -231,6 +261,13 @@ class Engine {
     DBuf<int> d_u_tile_lo, d_u_tile_n;
     DBuf<double> d_o_r, d_o_Jc, d_o_Jp;
     bool user_copy_ready = false;
+    // lighting blocks, caller's order
+    DBuf<uint32_t> d_ph_cam, d_ph_vertex, d_ph_mat;
+    DBuf<double> d_ph_int, d_ph_nobs, d_ph_normals, d_ph_tex, d_ph_phong, d_ph_light, d_ph_W, d_ph_points, d_ph_poses;
+    DBuf<double> d_ph_rI, d_ph_JI, d_ph_rN, d_ph_JNc, d_ph_JNn;
+    DBuf<int> d_ph_cam_free;
+    PhongView phong_view();
+    void ensure_phong();
     double* h_pinned = nullptr;            // pinned scalar read-back
 
     // LM state (mirrors oracle/problem.hpp::solve)

@@ -78,6 +78,10 @@ void launch_gather_layout(cudaStream_t s, long long n_obs, const uint32_t* obs_u
 void launch_scatter_points(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* raw_pts);
 void launch_fill(cudaStream_t s, double* p, size_t n, double value);
 
+// K1-phong — materialised residuals / Jacobians of the intensity and normal blocks
+void launch_phong_eval(cudaStream_t s, const PhongView& v, double* r_int, double* J_int, double* r_normal,
+                       double* Jpose_normal, double* Jn_normal, double* cost);
+
 double measure_fp64_peak_tflops(int device);
 extern std::atomic<unsigned long long> g_kernel_launches;  // every kernel this library launches
 

@@ -30,13 +30,13 @@ namespace cslam {
 
 namespace {
 
-constexpr int BL_THREADS = 256;
+constexpr int BL_THREADS = 512;
 constexpr int BL_WORKERS = BL_THREADS - 32;  // warps 1..7 do the bulk update, warp 0 the look-ahead
 
 // 6x6 Cholesky of a symmetric block (lower triangle read from `A`, row-major) entirely in
 // registers: L (lower, zeros above) and Li = L^-1.  Returns false when a pivot is not positive.
 __device__ __forceinline__ bool potrf6_inv_reg(const double* A, double* Lout, double* Liout) {
-    double L[6][6];
+    double L[6][6], inv[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -48,9 +48,11 @@ __device__ __forceinline__ bool potrf6_inv_reg(const double* A, double* Lout, do
 #pragma unroll
         for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
         if (!(d > 0.0) || !(d < 1.7976931348623157e308)) ok = false;
-        const double sd = sqrt(d);
-        const double id = 1.0 / sd;
-        L[j][j] = sd;
+        // one reciprocal square root per pivot (FP64 sqrt and divide are long software sequences)
+        double id = rsqrt(d);
+        id = id * (1.5 - 0.5 * d * id * id);  // one Newton step: full double precision
+        inv[j] = id;
+        L[j][j] = d * id;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = L[i][j];
@@ -66,11 +68,13 @@ __device__ __forceinline__ bool potrf6_inv_reg(const double* A, double* Lout, do
         for (int i = 0; i < 6; ++i) {
             if (i < c) {
                 Li[i][c] = 0.0;
+            } else if (i == c) {
+                Li[i][c] = inv[c];
             } else {
-                double s = (i == c) ? 1.0 : 0.0;
+                double s = 0.0;
 #pragma unroll
                 for (int k = c; k < i; ++k) s -= L[i][k] * Li[k][c];
-                Li[i][c] = s / L[i][i];
+                Li[i][c] = s * inv[i];
             }
         }
     }
@@ -102,7 +106,7 @@ template <int W, bool kSpike>
 __global__ void __launch_bounds__(BL_THREADS) band_leaf_kernel(BandView B) {
     constexpr int W1 = W + 1, GC = kSpike ? 1 + 6 * W : 1, b = 6 * W;
     constexpr int NPAIR = W * (W + 1) / 2;
-    constexpr int ACC = kSpike ? (b * GC + BL_WORKERS - 1) / BL_WORKERS : 1;
+    constexpr int ACC = kSpike ? (b + (BL_WORKERS / GC) - 1) / (BL_WORKERS / GC) : 1;  // left columns per thread
     constexpr int NROW = W1 * 36 + 6 * GC;  // values of one window row (blocks + border)
     constexpr int NXT = (NROW + BL_WORKERS - 1) / BL_WORKERS;
     extern __shared__ __align__(16) double smem_bl[];
@@ -227,38 +231,51 @@ __global__ void __launch_bounds__(BL_THREADS) band_leaf_kernel(BandView B) {
                     nxt[u] = idx < NROW ? row_value(inew, idx) : 0.0;
                 }
             }
-            // trailing window: A_ij -= L_ik L_jk^T (pair (1,1) is warp 0's)
+            // trailing window: A_ij -= L_ik L_jk^T (pair (1,1) is warp 0's).  One item = one row r
+            // of one pair and three of its columns: the L_ik row stays in registers.
             const int npairs = nb * (nb + 1) / 2;
-            for (int idx = 36 + t; idx < npairs * 36; idx += BL_WORKERS) {
-                const int pr = idx / 36, rc = idx % 36, r = rc / 6, c = rc % 6;
+            for (int item = 12 + t; item < npairs * 12; item += BL_WORKERS) {
+                const int pr = item / 12, rh = item % 12, r = rh >> 1, c0 = (rh & 1) * 3;
                 const int di = pair_i[pr], dj = pair_j[pr];
-                const double* Li = Lcol + di * 36 + 6 * r;
-                const double* Lj = Lcol + dj * 36 + 6 * c;
-                double v = 0.0;
+                const double2* Li2 = reinterpret_cast<const double2*>(Lcol + di * 36 + 6 * r);
+                const double2 l0 = Li2[0], l1 = Li2[1], l2 = Li2[2];
+                int si = sk + di, sj = sk + dj;
+                si -= si >= W1 ? W1 : 0;
+                sj -= sj >= W1 ? W1 : 0;
+                double* Arow = Awin + (si * W1 + sj) * 36 + 6 * r + c0;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) v += Li[q] * Lj[q];
-                Awin[(((k + di) % W1) * W1 + ((k + dj) % W1)) * 36 + rc] -= v;
+                for (int cc = 0; cc < 3; ++cc) {
+                    const double2* Lj2 = reinterpret_cast<const double2*>(Lcol + dj * 36 + 6 * (c0 + cc));
+                    const double2 m0 = Lj2[0], m1 = Lj2[1], m2 = Lj2[2];
+                    Arow[cc] -= l0.x * m0.x + l0.y * m0.y + l1.x * m1.x + l1.y * m1.y + l2.x * m2.x + l2.y * m2.y;
+                }
             }
-            // border: G_i -= L_ik X_k
-            for (int idx = t; idx < nb * 6 * GC; idx += BL_WORKERS) {
-                const int d = idx / (6 * GC) + 1, rem = idx % (6 * GC), r = rem / GC, col = rem % GC;
-                const double* Li = Lcol + d * 36 + 6 * r;
-                double v = 0.0;
+            // border G_i -= L_ik X_k and X^T X: a thread owns one border column (its X_k column
+            // stays in registers) and every NG-th (block, row) / left column
+            constexpr int NG = BL_WORKERS / GC;
+            const int col = t % GC, grp = t / GC;
+            if (grp < NG) {
+                double x[6];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) v += Li[q] * Xk[q * GC + col];
-                Gwin[((k + d) % W1) * 6 * GC + rem] -= v;
-            }
-            // contribution to the separator before this leaf: X^T X over (left column, any column)
-            if (kSpike && has_left) {
+                for (int q = 0; q < 6; ++q) x[q] = Xk[q * GC + col];
+                for (int dr = grp; dr < nb * 6; dr += NG) {
+                    const int d = dr / 6 + 1, r = dr % 6;
+                    const double2* Li2 = reinterpret_cast<const double2*>(Lcol + d * 36 + 6 * r);
+                    const double2 l0 = Li2[0], l1 = Li2[1], l2 = Li2[2];
+                    int si = sk + d;
+                    si -= si >= W1 ? W1 : 0;
+                    Gwin[(si * 6 + r) * GC + col] -= l0.x * x[0] + l0.y * x[1] + l1.x * x[2] + l1.y * x[3] + l2.x * x[4] + l2.y * x[5];
+                }
+                if (kSpike && has_left) {
 #pragma unroll
-                for (int u = 0; u < ACC; ++u) {
-                    const int flat = t + BL_WORKERS * u;
-                    if (flat < b * GC) {
-                        const int c1 = 1 + flat / GC, c2 = flat % GC;
-                        double v = 0.0;
+                    for (int u = 0; u < ACC; ++u) {
+                        const int c1 = 1 + grp + NG * u;
+                        if (c1 < GC) {
+                            double v = 0.0;
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) v += Xk[q * GC + c1] * Xk[q * GC + c2];
-                        acc[u] += v;
+                            for (int q = 0; q < 6; ++q) v += Xk[q * GC + c1] * x[q];
+                            acc[u] += v;
+                        }
                     }
                 }
             }
@@ -293,16 +310,18 @@ __global__ void __launch_bounds__(BL_THREADS) band_leaf_kernel(BandView B) {
         for (int R = tid; R < b; R += BL_THREADS) B.fa[(long long)p * b + R] = Gwin[(((ie + R / 6) % W1) * 6 + R % 6) * GC];
     }
     if (kSpike && has_left && tid >= 32) {
-        const int t = tid - 32;
+        constexpr int NG = BL_WORKERS / GC;
+        const int t = tid - 32, c2 = t % GC, grp = t / GC;
+        if (grp < NG) {
 #pragma unroll
-        for (int u = 0; u < ACC; ++u) {
-            const int flat = t + BL_WORKERS * u;
-            if (flat < b * GC) {
-                const int c1 = flat / GC, c2 = flat % GC;
-                if (c2 == 0)
-                    B.fb[(long long)(p - 1) * b + c1] = acc[u];
-                else
-                    B.Tb[(long long)(p - 1) * b * b + c1 * b + (c2 - 1)] = acc[u];
+            for (int u = 0; u < ACC; ++u) {
+                const int c1 = 1 + grp + NG * u;  // left column (1-based border column)
+                if (c1 < GC) {
+                    if (c2 == 0)
+                        B.fb[(long long)(p - 1) * b + (c1 - 1)] = acc[u];
+                    else
+                        B.Tb[(long long)(p - 1) * b * b + (c1 - 1) * b + (c2 - 1)] = acc[u];
+                }
             }
         }
     }
@@ -344,10 +363,17 @@ __global__ void band_assemble_kernel(BandView B, double* T2, double* rhs2) {
 
 // Interior unknowns of every leaf.  `ysep` holds the separator unknowns of the level (block row
 // q W + i of the separator system = row i of separator q); nullptr when the level has one leaf.
+//
+// The recurrence y_k = Lkk^-T (z_k - sum_{d>=1} L_{k+d,k}^T y_{k+d}) is sequential in k; one warp
+// walks it.  Only the d = 1 term depends on the value finished in the previous step, so the
+// d >= 2 terms of step k-1 are formed (lane groups 1..4) while step k is completed (lane group 0),
+// and the factor columns stream through a cp.async ring several steps ahead of their use.
 template <int W, bool kSpike>
 __global__ void __launch_bounds__(128) band_backsub_kernel(BandView B, const double* ysep) {
     constexpr int W1 = W + 1, GC = kSpike ? 1 + 6 * W : 1, b = 6 * W;
-    constexpr int DG = (W + 4) / 5;  // block columns per lane group (5 groups x 6 lanes)
+    constexpr int COLD = W1 * 36;           // doubles of one factor column
+    constexpr int NST = 8, PD = 6;          // ring stages, prefetch distance
+    constexpr int DGB = (W - 1 + 3) / 4;    // d >= 2 blocks per lane group
     extern __shared__ __align__(16) double smem_bb[];
     const int tid = threadIdx.x;
     const int p = blockIdx.x;
@@ -356,9 +382,9 @@ __global__ void __launch_bounds__(128) band_backsub_kernel(BandView B, const dou
     const bool has_left = kSpike && p > 0, has_right = p < B.P - 1;
     const int ie = has_right ? e - W : e;
     const int ni = ie - s;
-    double* z = smem_bb;           // [6 (ni + W)] leaf rows: z_k - X_left,k y_left, then the solution
-    double* yl = z + 6 * (B.m + W);  // [b] separator before
-    __shared__ double s_part[5][6], s_t[6];
+    double* ring = smem_bb;                  // [NST][COLD]
+    double* z = ring + NST * COLD;           // [6 (m + W)] leaf rows: right-hand side, then the solution
+    double* yl = z + 6 * (B.m + W);          // [b] separator before
     if (*B.fail) return;
     if (has_left)
         for (int c = tid; c < b; c += 128) yl[c] = ysep[(long long)(p - 1) * b + c];
@@ -377,62 +403,64 @@ __global__ void __launch_bounds__(128) band_backsub_kernel(BandView B, const dou
         z[idx] = v;
     }
     __syncthreads();
-    if (tid < 32) {
-        const int lane = tid, c = lane % 6, g = lane / 6;  // lanes 30, 31 idle
-        double Lr[DG][6], Li[6];
-        auto fetch = [&](int k) {
-            const double* L = B.Lbuf + ((long long)k * W1) * 36;
-            const int nb = min(k + W, e - 1) - k;
-            if (g < 5) {
-#pragma unroll
-                for (int u = 0; u < DG; ++u) {
-                    const int d = 1 + g * DG + u;
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) Lr[u][r] = (d <= nb) ? L[d * 36 + 6 * r + c] : 0.0;
-                }
+    if (tid < 32 && ni > 0) {
+        const int lane = tid, g = lane / 6, c = lane % 6;
+        auto issue = [&](int kk) {
+            if (kk >= s) {
+                const double* src = B.Lbuf + (long long)kk * COLD;
+                double* dst = ring + ((kk - s) % NST) * COLD;
+                for (int idx = lane; idx < COLD / 2; idx += 32) cp_async16(dst + 2 * idx, src + 2 * idx);
             }
-            if (lane < 6) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) Li[i] = L[6 * i + c];  // column c of Lkk^-1
-            }
+            cp_async_commit();
         };
-        if (ni > 0) fetch(ie - 1);
-        for (int k = ie - 1; k >= s; --k) {
-            // partial sums with this step's factor column (already in registers)
+        for (int q = 0; q < PD; ++q) issue(ie - 1 - q);
+        double zt = 0.0;  // lanes 0..5: z_k[c] minus the d >= 2 terms of step k
+        for (int k = ie; k >= s; --k) {
+            issue(k - 1 - PD);
+            cp_async_wait<PD>();  // column k-1 has landed (k was waited for one step earlier)
+            __syncwarp();
+            const int kk = k - 1;
+            // lane groups 1..4: d >= 2 terms of step kk (every y they need is final)
             double part = 0.0;
-            if (g < 5) {
+            if (kk >= s && g >= 1 && g <= 4) {
+                const double* Lc = ring + ((kk - s) % NST) * COLD;
+                const int nbk = min(kk + W, e - 1) - kk;
 #pragma unroll
-                for (int u = 0; u < DG; ++u) {
-                    const int d = 1 + g * DG + u;
-                    if (d <= W && k + d < e) {
-                        const double* yv = z + 6 * (k + d - s);
+                for (int u = 0; u < DGB; ++u) {
+                    const int d = 2 + (g - 1) * DGB + u;
+                    if (d <= nbk) {
+                        const double* yv = z + 6 * (kk + d - s);
 #pragma unroll
-                        for (int r = 0; r < 6; ++r) part += Lr[u][r] * yv[r];
+                        for (int r = 0; r < 6; ++r) part += Lc[d * 36 + 6 * r + c] * yv[r];
                     }
                 }
-                s_part[g][c] = part;
             }
-            double Lic[6];
+            // lane group 0: finish step k
+            double t = 0.0;
+            const double* Lk = ring + (((k < ie ? k : ie - 1) - s) % NST) * COLD;
+            if (k < ie && lane < 6) {
+                t = zt;
+                if (k + 1 < e) {
+                    const double* yv = z + 6 * (k + 1 - s);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) Lic[i] = Li[i];
-            if (k > s) fetch(k - 1);  // next step's loads are in flight during the dependent part
-            __syncwarp();
-            if (lane < 6) {
-                double t = z[6 * (k - s) + lane];
-#pragma unroll
-                for (int gg = 0; gg < 5; ++gg) t -= s_part[gg][lane];
-                s_t[lane] = t;
+                    for (int r = 0; r < 6; ++r) t -= Lk[36 + 6 * r + c] * yv[r];
+                }
             }
-            __syncwarp();
-            if (lane < 6) {
-                double yv = 0.0;
+            double ycur = 0.0;
 #pragma unroll
-                for (int i = 0; i < 6; ++i)
-                    if (i >= lane) yv += Lic[i] * s_t[i];  // (Lkk^-T t)_c = sum_{i >= c} Linv[i][c] t_i
-                z[6 * (k - s) + lane] = yv;
+            for (int i = 0; i < 6; ++i) {
+                const double ti = __shfl_sync(0xffffffffu, t, i);
+                if (k < ie && lane < 6 && i >= c) ycur += Lk[6 * i + c] * ti;  // (Lkk^-T t)_c
             }
+            if (k < ie && lane < 6) z[6 * (k - s) + c] = ycur;
+            // right-hand side of the next step: z_kk minus the partial sums of groups 1..4
+            double psum = 0.0;
+#pragma unroll
+            for (int gg = 1; gg <= 4; ++gg) psum += __shfl_sync(0xffffffffu, part, (c + 6 * gg) & 31);
+            if (lane < 6 && kk >= s) zt = z[6 * (kk - s) + c] - psum;
             __syncwarp();
         }
+        cp_async_wait<0>();
     }
     __syncthreads();
     for (int idx = tid; idx < 6 * ni; idx += 128) B.y[6ll * s + idx] = z[idx];
@@ -468,7 +496,7 @@ void run_backsub(cudaStream_t s, const BandView& V, const double* ysep) {
         CSLAM_CUDA(cudaFuncSetAttribute(band_backsub_kernel<W, kSpike>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
-    const size_t smem = sizeof(double) * (6 * size_t(V.m + W) + 6 * size_t(W));
+    const size_t smem = sizeof(double) * (8 * size_t(W + 1) * 36 + 6 * size_t(V.m + W) + 6 * size_t(W));
     band_backsub_kernel<W, kSpike><<<V.P, 128, smem, s>>>(V, ysep);
     CSLAM_CUDA(cudaGetLastError());
 }

@@ -35,7 +35,7 @@ class BAProblem:
         self._h = capi._h()
         self._check(self.lib.problem_create(C.byref(self._h), C.byref(self.options)))
         self._keep = {}
-        self.n_stereo = self.n_sun = self.n_prior = 0
+        self.n_stereo = self.n_sun = self.n_prior = self.n_phong = 0
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, status):
@@ -107,6 +107,58 @@ class BAProblem:
         W6x6 = np.ascontiguousarray(W6x6, dtype=np.float64).reshape(36)
         self.n_prior += 1
         self._check(self.lib.add_pose_prior(self._h, int(cam), capi.dptr(Tref12), capi.dptr(W6x6)))
+
+    # -- lighting blocks (dataset_ba_phong) ---------------------------------------------------
+    def set_vertices(self, normals, textures, material_id):
+        normals = np.ascontiguousarray(normals, dtype=np.float64).reshape(-1, 3)
+        textures = np.ascontiguousarray(textures, dtype=np.float64).reshape(-1)
+        material_id = np.ascontiguousarray(material_id, dtype=np.uint32)
+        assert normals.shape[0] == textures.size == material_id.size
+        self._keep["vertices"] = (normals, textures, material_id)
+        self._check(self.lib.set_vertices(self._h, textures.size, capi.dptr(normals), capi.dptr(textures),
+                                          capi.u32ptr(material_id)))
+        return normals, textures
+
+    def set_materials(self, phong):
+        phong = np.ascontiguousarray(phong, dtype=np.float64).reshape(-1, 3)
+        self._keep["materials"] = phong
+        self._check(self.lib.set_materials(self._h, phong.shape[0], capi.dptr(phong)))
+        return phong
+
+    def set_light(self, light, directional=False):
+        light = np.ascontiguousarray(light, dtype=np.float64).reshape(3)
+        self._keep["light"] = light
+        self._check(self.lib.set_light(self._h, capi.dptr(light), int(directional)))
+        return light
+
+    def add_phong(self, cam, vertex, intensity, int_stiffness, normal_obs, W_normal):
+        cam = np.ascontiguousarray(cam, dtype=np.uint32)
+        vertex = np.ascontiguousarray(vertex, dtype=np.uint32)
+        intensity = np.ascontiguousarray(intensity, dtype=np.float64).reshape(-1)
+        normal_obs = np.ascontiguousarray(normal_obs, dtype=np.float64).reshape(-1, 3)
+        W_normal = np.ascontiguousarray(W_normal, dtype=np.float64).reshape(9)
+        assert cam.size == vertex.size == intensity.size == normal_obs.shape[0]
+        self._keep["phong"] = (cam, vertex, intensity, normal_obs, W_normal)
+        self.n_phong = cam.size
+        self._check(self.lib.add_phong(self._h, cam.size, capi.u32ptr(cam), capi.u32ptr(vertex),
+                                       capi.dptr(intensity), float(int_stiffness), capi.dptr(normal_obs),
+                                       capi.dptr(W_normal)))
+
+    def evaluate_phong(self):
+        """Residuals and tangent-space Jacobians of the intensity and normal blocks."""
+        n = self.n_phong
+        out = {"r_int": np.zeros(n), "J_int": np.zeros((n, 19)), "r_normal": np.zeros((n, 3)),
+               "Jpose_normal": np.zeros((n, 3, 6)), "Jn_normal": np.zeros((n, 3, 3))}
+        cost = C.c_double(0.0)
+        self._check(self.lib.evaluate_phong(self._h, C.byref(cost), *[capi.dptr(out[k]) for k in
+                                            ("r_int", "J_int", "r_normal", "Jpose_normal", "Jn_normal")]))
+        out["cost"] = cost.value
+        return out
+
+    def time_phong(self, reps):
+        ms = C.c_double(0)
+        self._check(self.lib.time_phong(self._h, reps, C.byref(ms)))
+        return ms.value
 
     # -- evaluation / solve -----------------------------------------------------------------
     def evaluate(self, apply_loss=True, jacobians=True):

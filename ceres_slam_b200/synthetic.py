@@ -141,6 +141,71 @@ def add_sun(track, seed=43, sigma_deg=2.0):
     return track
 
 
+def add_phong(track, seed=44, n_materials=8, directional=False, int_var=1e-4, normal_var=1e-4):
+    """Lighting data in the shape of dataset_ba_phong's input (dataset_problem_phong.cpp:29-117):
+    per vertex a unit normal facing the cameras that see it, a diffuse texture kd and a material
+    id; per material [ka, ks, alpha]; one point light at (-2, -2, 2) (light_test.cpp:49) or a
+    directional light; per observation the rendered Phong intensity (+ noise, variance int_var)
+    and the normal in the camera frame (+ noise, variance normal_var)."""
+    rng = np.random.default_rng(seed)
+    n_pts = track["n_points"]
+    k, j = track["obs_cam"].astype(np.int64), track["obs_pt"].astype(np.int64)
+    R, t = pose_R(track["poses_gt"]), pose_t(track["poses_gt"])
+    # normal: towards the mean camera centre of the observing poses, perturbed
+    centres = -np.einsum("nji,nj->ni", R, t)
+    acc = np.zeros((n_pts, 3))
+    np.add.at(acc, j, centres[k] - track["points_gt"][j])
+    nrm = acc + rng.normal(0, 0.3, acc.shape) * np.linalg.norm(acc, axis=1, keepdims=True).clip(1e-9)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True).clip(1e-12)
+    nrm[~np.isfinite(nrm).all(axis=1)] = np.array([0.0, 0.0, 1.0])
+    mat_id = rng.integers(0, n_materials, n_pts).astype(np.uint32)
+    phong = np.stack([rng.uniform(0.0, 0.2, n_materials), rng.uniform(0.1, 0.5, n_materials),
+                      rng.uniform(5.0, 30.0, n_materials)], axis=1)
+    tex = rng.uniform(0.3, 0.9, n_pts)
+    if directional:
+        light = np.array([0.2, -0.4, 0.9])
+        light /= np.linalg.norm(light)
+    else:
+        light = np.array([-2.0, -2.0, 2.0])
+    # render with the model (float64 numpy restatement of phong.hpp:25-104 for data generation only)
+    pc = np.einsum("nij,nj->ni", R[k], track["points_gt"][j]) + t[k]
+    nc = np.einsum("nij,nj->ni", R[k], nrm[j])
+    if directional:
+        lv = np.einsum("nij,j->ni", R[k], light)
+    else:
+        lv = np.einsum("nij,nj->ni", R[k], light[None, :] - track["points_gt"][j])
+    lhat = lv / np.linalg.norm(lv, axis=1, keepdims=True)
+    chat = -pc / np.linalg.norm(pc, axis=1, keepdims=True)
+    a = np.einsum("ni,ni->n", lhat, nc)
+    diffuse = np.where(a > 0, tex[j] * a, 0.0)
+    m = 2 * a[:, None] * nc - lhat
+    mn = np.linalg.norm(m, axis=1, keepdims=True).clip(1e-300)
+    s = np.einsum("ni,ni->n", m / mn, chat)
+    spec = np.where(s > 0, phong[mat_id[j], 1] * np.power(np.clip(s, 1e-300, None), phong[mat_id[j], 2]), 0.0)
+    inten = np.clip(diffuse + spec, 0.0, 1.0) + rng.normal(0, np.sqrt(int_var), k.size)
+    nobs = nc + rng.normal(0, np.sqrt(normal_var), nc.shape)
+    # initial guesses: perturbed normals (re-normalised), textures and material parameters
+    n0 = nrm + rng.normal(0, 0.05, nrm.shape)
+    n0 /= np.linalg.norm(n0, axis=1, keepdims=True)
+    track.update(normals_gt=nrm, normals=n0, textures_gt=tex, textures=np.clip(tex + rng.normal(0, 0.05, n_pts), 0, 1),
+                 material_id=mat_id, phong_gt=phong, phong=phong * rng.uniform(0.9, 1.1, phong.shape),
+                 light_gt=light, light=light + (0 if directional else rng.normal(0, 0.05, 3)),
+                 directional=bool(directional), intensity=inten, normal_obs=np.ascontiguousarray(nobs),
+                 int_stiffness=1.0 / np.sqrt(int_var), W_normal=(np.eye(3) / np.sqrt(normal_var)).reshape(9))
+    return track
+
+
+def build_phong_problem(track, backend="b200", **options):
+    """dataset_ba_phong's problem (stereo + intensity + normal blocks, first pose constant)."""
+    p, poses, points = build_problem(track, backend=backend, **options)
+    normals, textures = p.set_vertices(track["normals"].copy(), track["textures"].copy(), track["material_id"])
+    phong = p.set_materials(track["phong"].copy())
+    light = p.set_light(track["light"].copy(), track["directional"])
+    p.add_phong(track["obs_cam"], track["obs_pt"], track["intensity"], track["int_stiffness"],
+                track["normal_obs"], track["W_normal"])
+    return p, dict(poses=poses, points=points, normals=normals, textures=textures, phong=phong, light=light)
+
+
 def window_of(track, k1, k2):
     """The sub-problem `solveWindow(dataset, k1, k2)` builds (dataset_vo.cpp:40-62): observations
     of poses k1..k2-1, restricted to points seen by at least two poses of the window (the

@@ -152,6 +152,31 @@ cslam_status cslam_evaluate(cslam_problem* p, int apply_loss, double* cost, doub
                             double* Jpose_stereo, double* Jpoint_stereo, double* r_sun,
                             double* J_sun, double* r_prior, double* J_prior);
 
+/* ---- lighting blocks of dataset_ba_phong (tests/dataset_ba_phong.cpp:100-205) --------------------
+ * A map vertex is a point (cslam_set_points) plus a unit normal, a diffuse texture value kd and a
+ * material id (map_vertex / material / texture, dataset_problem_phong.cpp:335-376); a material is
+ * the Phong parameter block [ka, ks, alpha] (material.hpp); the light is a position or, when
+ * `directional` != 0, a direction (dataset_ba_phong.cpp:103-123).  All arrays are caller-owned.
+ * The normal (and a directional light) carry UnitVectorPerturbation (perturbations.hpp:87-113). */
+cslam_status cslam_set_vertices(cslam_problem* p, uint32_t n, double* normals3, double* textures,
+                                const uint32_t* material_id);
+cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double* phong3);
+cslam_status cslam_set_light(cslam_problem* p, double* light3, int directional);
+/* n observations, each adding one IntensityError{Point,Directional}LightAutomatic block
+ * (dataset_ba_phong.cpp:103-123: pose, position, normal, phong params, texture, light) and one
+ * NormalErrorAutomatic block (dataset_ba_phong.cpp:183-190: pose, normal).  int_stiffness =
+ * 1/sqrt(int_var) (dataset_ba_phong.cpp:43); W_normal9 row-major 3x3 (dataset_ba_phong.cpp:38-41). */
+cslam_status cslam_add_phong(cslam_problem* p, uint64_t n, const uint32_t* cam, const uint32_t* vertex,
+                             const double* intensity, double int_stiffness, const double* normal_obs3,
+                             const double* W_normal9);
+/* ceres::Problem::Evaluate restricted to the lighting blocks, caller's block order; any output
+ * may be NULL.  Per block: r_int 1; J_int 19 = [pose 6 | point 3 | normal 3 | phong 3 | texture 1 |
+ * light 3]; r_normal 3; Jpose_normal 3x6; Jn_normal 3x3.  cost = 1/2 sum of squares. */
+cslam_status cslam_evaluate_phong(cslam_problem* p, double* cost, double* r_int, double* J_int,
+                                  double* r_normal, double* Jpose_normal, double* Jn_normal);
+/* `reps` launches of the lighting-block kernel on device-resident data: ms per launch. */
+cslam_status cslam_time_phong(cslam_problem* p, int reps, double* ms_per_launch);
+
 /* ceres::Solve (dataset_vo.cpp:81): uploads the problem, runs the LM loop on the device, writes
  * the best parameters back into the caller's pose / point arrays. */
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary);

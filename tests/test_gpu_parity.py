@@ -309,3 +309,53 @@ def test_cpp_driver_dataset_vo(product, tmp_path):
     assert text.count("cslam_b200 Report") == 36 and text.count("Termination: CONVERGENCE") >= 30, text
     assert np.abs(T[:, :3, 3] - gt_t).max() < 0.5
     assert np.abs(T[:, :3, :3] - gt_R).max() < 0.03
+
+
+def _oracle_phong(tr, st, oracle):
+    """Every lighting block through the Jet oracle (one call per block)."""
+    import ctypes as C
+    from ceres_slam_b200 import capi
+    d = capi.dptr
+    n = tr["obs_cam"].size
+    out = {"r_int": np.zeros(n), "J_int": np.zeros((n, 19)), "r_normal": np.zeros((n, 3)),
+           "Jpose_normal": np.zeros((n, 3, 6)), "Jn_normal": np.zeros((n, 3, 3))}
+    W = np.ascontiguousarray(tr["W_normal"], dtype=np.float64)
+    for i in range(n):
+        k, j = int(tr["obs_cam"][i]), int(tr["obs_pt"][i])
+        pose, pt, nr = st["poses"][k].copy(), st["points"][j].copy(), st["normals"][j].copy()
+        ph, tx = st["phong"][tr["material_id"][j]].copy(), st["textures"][j:j + 1].copy()
+        r, Jc, Jp, Jn, Jk, Jt, Jl = (np.zeros(m) for m in (1, 6, 3, 3, 3, 1, 3))
+        assert oracle.intensity_block(d(pose), d(pt), d(nr), d(ph), d(tx), d(st["light"].copy()), float(tr["intensity"][i]),
+                                      float(tr["int_stiffness"]), int(tr["directional"]), d(r), d(Jc), d(Jp), d(Jn),
+                                      d(Jk), d(Jt), d(Jl)) == 0
+        out["r_int"][i] = r[0]
+        out["J_int"][i] = np.concatenate([Jc if k != 0 else np.zeros(6), Jp, Jn, Jk, Jt, Jl])
+        rn, Jcn, Jnn = np.zeros(3), np.zeros(18), np.zeros(9)
+        assert oracle.normal_block(d(pose), d(nr), d(tr["normal_obs"][i].copy()), d(W), d(rn), d(Jcn), d(Jnn)) == 0
+        out["r_normal"][i] = rn
+        out["Jpose_normal"][i] = Jcn.reshape(3, 6) if k != 0 else 0.0
+        out["Jn_normal"][i] = Jnn.reshape(3, 3)
+    return out
+
+
+@pytest.mark.parametrize("directional", [False, True])
+def test_phong_blocks(product, oracle, directional):
+    """dataset_ba_phong's lighting blocks (a8-a10): IntensityError{Point,Directional}Light and
+    NormalError residuals and tangent-space Jacobians against the Jet oracle, 1e-10 per block."""
+    tr = syn.add_phong(syn.make_track(40, 12, 6, seed=8), directional=directional)
+    n = tr["obs_cam"].size
+    assert n > 2000 and n % 128 != 0
+    p, st = syn.build_phong_problem(tr, backend="b200")
+    eg = p.evaluate_phong()
+    eo = _oracle_phong(tr, st, oracle)
+    assert rel_err(eg["r_int"], eo["r_int"]) < RJ_TOL
+    assert rel_err(eg["r_normal"], eo["r_normal"]) < RJ_TOL
+    for i in range(n):
+        assert rel_err(eg["J_int"][i], eo["J_int"][i]) < RJ_TOL or np.abs(eo["J_int"][i]).max() == 0, i
+        assert rel_err(eg["Jpose_normal"][i], eo["Jpose_normal"][i]) < RJ_TOL or tr["obs_cam"][i] == 0, i
+        assert rel_err(eg["Jn_normal"][i], eo["Jn_normal"][i]) < RJ_TOL, i
+    cost = 0.5 * (np.sum(eo["r_int"] ** 2) + np.sum(eo["r_normal"] ** 2))
+    assert abs(eg["cost"] - cost) <= 1e-12 * cost
+    # a meaningful scene: most vertices are lit and unsaturated
+    lit = np.abs(eo["J_int"][:, 15]) > 0
+    assert lit.mean() > 0.3
