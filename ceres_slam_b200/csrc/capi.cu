@@ -355,7 +355,19 @@ cslam_status cslam_attach_comm(cslam_problem* p, int n_ranks, int rank, const ui
         CSLAM_CUDA(cudaSetDevice(e.opt.device));
         e.n_ranks = n_ranks;
         e.rank = rank;
-        if (n_ranks > 1) e.nccl_comm = cslam::comm_create(n_ranks, rank, id);
+        if (n_ranks > 1) {
+            e.nccl_comm = cslam::comm_create(n_ranks, rank, id);
+            // NCCL connects its channels lazily at the first collective of each kind: do that here,
+            // not inside the first solve
+            double* tmp = nullptr;
+            CSLAM_CUDA(cudaMalloc(&tmp, 64 * sizeof(double)));
+            CSLAM_CUDA(cudaMemset(tmp, 0, 64 * sizeof(double)));
+            cslam::comm_allreduce_sum(e.nccl_comm, tmp, 64, nullptr);
+            cslam::comm_allreduce_max(e.nccl_comm, tmp, 1, nullptr);
+            cslam::comm_broadcast(e.nccl_comm, tmp, 64, 0, nullptr);
+            CSLAM_CUDA(cudaDeviceSynchronize());
+            cudaFree(tmp);
+        }
         e.uploaded = e.begun = false;
     });
 }

@@ -15,6 +15,8 @@
 // Camera poses of the slice are staged in shared memory with one TMA bulk copy (contiguous camera
 // lists) or L bulk copies, completion on an mbarrier.  Observations are stored slot-major inside
 // a group, so every global load of u, v, d is coalesced.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace cslam {
@@ -321,14 +323,309 @@ __global__ void __launch_bounds__(32 * (1 + CW))
     block_atomic_sum(cost, &scal[SC_COST], s_redsum);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Variant for track length L <= 10 (two threads per camera pair fit in one 128-thread CTA).
+// Every thread is producer AND consumer: in one step of the software pipeline a thread first
+// evaluates one observation of batch n+1 (camera slot fixed per thread: pose and scaling stay in
+// registers) and writes its Z = W C^-T to one half of a double-buffered shared tile, then
+// accumulates its half (three rows) of one pair block over the landmarks of batch n.  One CTA
+// barrier per batch; no warp is a serial bottleneck and all warps issue FP64 work throughout.
+// ---------------------------------------------------------------------------------------------
+constexpr int G2_NT = 128;
+constexpr int G2_LMAX = 10;  // longest camera list this variant takes
+constexpr int G2_ZB = G2_NT * 18;  // doubles per Z buffer: one (landmark, slot) entry per thread
+
+template <int MINB>
+__global__ void __launch_bounds__(G2_NT, MINB)
+    schur_grouped2_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
+                          double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
+                          double* __restrict__ gl, double* __restrict__ scal) {
+    __shared__ __align__(128) double s_pose[G2_LMAX * 12];
+    __shared__ double s_sp[G2_LMAX * 6];
+    __shared__ double s_A[kItemMax * 9];
+    __shared__ __align__(16) double s_Z[2 * G2_ZB];
+    __shared__ double s_redsum[32];
+    __shared__ int s_free[G2_LMAX];
+    __shared__ int s_blk[G2_LMAX * (G2_LMAX + 1) / 2];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    double cost = 0.0;
+    double Wsh[9];
+    if (!v.W_per_obs) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Wsh[k] = v.obs_W[k];
+    }
+
+    for (int w = item_lo + blockIdx.x; w < item_hi; w += gridDim.x) {
+        const int g = gv.item_group[w];
+        const int L = gv.g_L[g], G = gv.g_G[g];
+        const int j0 = gv.item_j0[w], nj = gv.item_n[w];
+        const int lm0 = gv.g_lm0[g] + j0;
+        const long long obs0 = (long long)gv.g_obs0[g] + j0;
+        const int* __restrict__ cams = gv.g_cams + gv.g_off[g];
+        const int* __restrict__ blk = gv.g_blk + gv.g_blk_off[g];
+        const int P = L * (L + 1) / 2;
+
+        // ---- stage the slice's cameras: free index, scaling, pair->block table, poses (TMA) ----
+        if (tid < L) {
+            const int f = v.cam_free[cams[tid]];
+            s_free[tid] = f;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s_sp[6 * tid + k] = f >= 0 ? v.sc_p[6ll * f + k] : 0.0;
+        }
+        for (int k = tid; k < P; k += G2_NT) s_blk[k] = blk[k];
+        if (tid == 0) {
+            const int c0 = cams[0];
+            mbar_expect_tx(&s_bar, L * 96);
+            if (cams[L - 1] - c0 == L - 1) {
+                tma_load_1d(s_pose, v.poses + 12ll * c0, L * 96, &s_bar);
+            } else {
+                for (int i = 0; i < L; ++i) tma_load_1d(s_pose + 12 * i, v.poses + 12ll * cams[i], 96, &s_bar);
+            }
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        __syncthreads();
+
+        // ---- pass 1: V_j = sum Jp^T Jp + D^2, Cholesky, A = C^-1, t = A g_l ----
+        for (int jl = tid; jl < nj; jl += G2_NT) {
+            const long long j = lm0 + jl;
+            const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
+            const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
+            double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
+            for (int i = 0; i < L; ++i) {
+                const long long e = obs0 + (long long)i * G + jl;
+                double r[3], Jp[9];
+                stereo_block_point(v.cam, s_pose + 12 * i, p, v.obs_u[e], v.obs_v[e], v.obs_d[e],
+                                   v.W_per_obs ? v.obs_W + 9 * e : Wsh, r, Jp);
+                cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double a = Jp[3 * k] * sl[0], b = Jp[3 * k + 1] * sl[1], c = Jp[3 * k + 2] * sl[2];
+                    V[0] += a * a; V[1] += a * b; V[2] += a * c; V[3] += b * b; V[4] += b * c; V[5] += c * c;
+                    gq[0] += a * r[k]; gq[1] += b * r[k]; gq[2] += c * r[k];
+                }
+            }
+            V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            bool pd = V[0] > 0.0;
+            if (pd) {
+                const double c00 = sqrt(V[0]);
+                const double c10 = V[1] / c00, c20 = V[2] / c00;
+                const double d1 = V[3] - c10 * c10;
+                pd = d1 > 0.0;
+                if (pd) {
+                    const double c11 = sqrt(d1);
+                    const double c21 = (V[4] - c20 * c10) / c11;
+                    const double d2 = V[5] - c20 * c20 - c21 * c21;
+                    pd = d2 > 0.0 && d2 < 1.7976931348623157e308;
+                    if (pd) {
+                        const double c22 = sqrt(d2);
+                        const double a00 = 1.0 / c00, a11 = 1.0 / c11, a22 = 1.0 / c22;
+                        const double a10 = -c10 * a00 * a11;
+                        const double a21 = -c21 * a11 * a22;
+                        const double a20 = -(c20 * a00 + c21 * a10) * a22;
+                        A[0] = a00; A[1] = a10; A[2] = a11; A[3] = a20; A[4] = a21; A[5] = a22;
+                        A[6] = a00 * gq[0];
+                        A[7] = a10 * gq[0] + a11 * gq[1];
+                        A[8] = a20 * gq[0] + a21 * gq[1] + a22 * gq[2];
+                    }
+                }
+            }
+            if (!pd) red_add(&scal[SC_INVALID], 1.0);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s_A[9 * jl + k] = A[k];
+            gl[3 * j] = gq[0];
+            gl[3 * j + 1] = gq[1];
+            gl[3 * j + 2] = gq[2];
+        }
+        __syncthreads();
+
+        // ---- pipeline: produce Z of batch n+1, accumulate Z_a Z_b^T of batch n ----
+        const int TL = G2_NT / L;            // landmarks per batch (one observation per thread)
+        const int nbatch = (nj + TL - 1) / TL;
+        const int pq = tid % TL, pi = tid / TL;
+        const bool p_active = pi < L;
+        int pf = -1;
+        double pose[12], sp[6];
+        double U[21], gpa[6], bpa[6];
+        if (p_active) {
+            pf = s_free[pi];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) pose[k] = s_pose[12 * pi + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sp[k] = s_sp[6 * pi + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 21; ++k) U[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gpa[k] = bpa[k] = 0.0;
+        // consumer role: pair (a <= b) in row-major order of the upper triangle, half = rows 3h..3h+2
+        const int cpair = tid >> 1, half = tid & 1;
+        const bool c_active = cpair < P;
+        int ca = 0, cb = 0;
+        if (c_active) {
+            int rem = cpair;
+            while (rem >= L - ca) {
+                rem -= L - ca;
+                ++ca;
+            }
+            cb = ca + rem;
+        }
+        double M[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) M[k] = 0.0;
+
+        for (int bt = 0; bt <= nbatch; ++bt) {
+            if (bt < nbatch && p_active && pf >= 0) {
+                const int jl = bt * TL + pq;
+                if (jl < nj) {
+                    double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
+                    const long long j = lm0 + jl;
+                    const long long e = obs0 + (long long)pi * G + jl;
+                    const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
+                    const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
+                    double r[3], Jc[18], Jp[9];
+                    stereo_block<true>(v.cam, pose, p, v.obs_u[e], v.obs_v[e], v.obs_d[e],
+                                       v.W_per_obs ? v.obs_W + 9 * e : Wsh, r, Jc, Jp);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) Jp[3 * k + q] *= sl[q];
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= sp[q];
+                    }
+                    const double* A = s_A + 9 * jl;
+                    const double a00 = A[0], a10 = A[1], a11 = A[2], a20 = A[3], a21 = A[4], a22 = A[5];
+                    const double t0 = A[6], t1 = A[7], t2 = A[8];
+                    int u = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3] + Jc[12 + a] * Jp[6];
+                        const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4] + Jc[12 + a] * Jp[7];
+                        const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5] + Jc[12 + a] * Jp[8];
+                        const double z0 = w0 * a00;
+                        const double z1 = w0 * a10 + w1 * a11;
+                        const double z2 = w0 * a20 + w1 * a21 + w2 * a22;
+                        zt[3 * a] = z0;
+                        zt[3 * a + 1] = z1;
+                        zt[3 * a + 2] = z2;
+                        const double ga = Jc[a] * r[0] + Jc[6 + a] * r[1] + Jc[12 + a] * r[2];
+                        gpa[a] += ga;
+                        bpa[a] += ga - (z0 * t0 + z1 * t1 + z2 * t2);
+#pragma unroll
+                        for (int b = a; b < 6; ++b, ++u)
+                            U[u] += Jc[a] * Jc[b] + Jc[6 + a] * Jc[6 + b] + Jc[12 + a] * Jc[12 + b];
+                    }
+                }
+            }
+            if (bt > 0 && c_active) {
+                const double* zt = s_Z + ((bt - 1) & 1) * G2_ZB;
+                const int nval = min(TL, nj - (bt - 1) * TL);
+                for (int jj = 0; jj < nval; ++jj) {
+                    const double* za = zt + (jj * L + ca) * 18 + 9 * half;
+                    const double* zb = zt + (jj * L + cb) * 18;
+                    double B[18];
+#pragma unroll
+                    for (int k = 0; k < 18; k += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(zb + k);
+                        B[k] = t.x;
+                        B[k + 1] = t.y;
+                    }
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const double x0 = za[3 * p], x1 = za[3 * p + 1], x2 = za[3 * p + 2];
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) M[6 * p + q] += x0 * B[3 * q] + x1 * B[3 * q + 1] + x2 * B[3 * q + 2];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- flush: pair blocks, camera diagonal / gradients ----
+        if (c_active) {
+            const int e = s_blk[cpair];
+            if (e >= 0) {
+                double* Bk = S + 36ll * e + 18 * half;
+                if (ca == cb) {
+                    // diagonal block: upper triangle only, finalize mirrors it
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+#pragma unroll
+                        for (int q = 0; q < 6; ++q)
+                            if (q >= p + 3 * half) red_add(&Bk[6 * p + q], -M[6 * p + q]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) red_add(&Bk[k], -M[k]);
+                }
+            }
+        }
+        {
+            // reduce U, g, rhs over the TL threads that share a slot, then one RED per value
+            double* red = s_Z;  // every consumer read of s_Z is behind the last barrier
+            if (p_active && pf >= 0) {
+#pragma unroll
+                for (int k = 0; k < 21; ++k) red[tid * 33 + k] = U[k];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    red[tid * 33 + 21 + k] = gpa[k];
+                    red[tid * 33 + 27 + k] = bpa[k];
+                }
+            }
+            __syncthreads();
+            // 33 values per slot: thread (slot, value)
+            for (int idx = tid; idx < L * 33; idx += G2_NT) {
+                const int i = idx / 33, k = idx - 33 * i;
+                const int f = s_free[i];
+                if (f < 0) continue;
+                double acc = 0.0;
+                const int nl = min(TL, nj);  // lanes beyond nj never produced
+                for (int q = 0; q < nl; ++q) acc += red[(i * TL + q) * 33 + k];
+                if (k < 21) {
+                    int a = 0, rem = k;
+                    while (rem >= 6 - a) {
+                        rem -= 6 - a;
+                        ++a;
+                    }
+                    red_add(&Bdiag[36ll * f + 6 * a + a + rem], acc);
+                } else if (k < 27) {
+                    red_add(&gp[6ll * f + (k - 21)], acc);
+                } else {
+                    red_add(&bp[6ll * f + (k - 27)], acc);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    block_atomic_sum(cost, &scal[SC_COST], s_redsum);
+}
+
 }  // namespace
 
 void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
                           double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
     if (n_items_small > 0) {
-        const int grid = n_items_small < 4 * kSMs ? n_items_small : 4 * kSMs;
-        schur_grouped_kernel<2><<<grid, 96, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+        static const int occ = [] {
+            const char* e = std::getenv("CSLAM_G2_OCC");  // tuning knob: resident CTAs per SM (2 or 3)
+            return e ? std::atoi(e) : 2;
+        }();
+        const int grid = n_items_small < occ * kSMs ? n_items_small : occ * kSMs;
+        if (occ == 2)
+            schur_grouped2_kernel<2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+        else
+            schur_grouped2_kernel<3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (g.n_items > n_items_small) {
