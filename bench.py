@@ -202,6 +202,22 @@ def bench_c4_windows(lib, n_windows=256, iters=6, reps=5):
                     "H2D + kernel + D2H through cslam_solve_batch"}
 
 
+def bench_phong_blocks(peak_gbs, reps=10):
+    """Lighting blocks of BASELINE.json config 3 (2 k poses x 200 k vertices, ~2 M observations):
+    one intensity block + one normal block per observation, residuals and Jacobians materialised
+    (the K1-style throughput figure for the Phong residuals)."""
+    tr = syn.add_phong(syn.make_track(2000, 100, 10, seed=42))
+    p, _ = syn.build_phong_problem(tr, backend="b200")
+    n = int(tr["obs_cam"].size)
+    ms = p.time_phong(reps)
+    p.close()
+    bytes_per_obs = 12 + 8 + 24 + 50 * 8  # indices, intensity, observed normal, 50 output doubles
+    gbs = bytes_per_obs * n / (ms * 1e-3) / 1e9
+    return {"observations": n, "ms": ms, "obs_per_s": n / (ms * 1e-3), "bytes_per_obs": bytes_per_obs,
+            "achieved_gbs": gbs, "frac_of_hbm": gbs / peak_gbs,
+            "note": "IntensityErrorPointLight + NormalError residuals and tangent-space Jacobians per observation"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,6 +229,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-phong", action="store_true")
     ap.add_argument("--linear", default="exact", choices=["exact", "iterative"],
                     help="reduced-system solve: exact = SPARSE_SCHUR-equivalent (banded direct solver), "
                          "iterative = ITERATIVE_SCHUR-equivalent (block-Jacobi PCG, eta = 0.1)")
@@ -315,8 +332,17 @@ def main():
     alg_flops = schur_algorithmic_flops(n_lm // world, L)
     fp64 = C.c_double(0)
     lib.measure_fp64_peak(local, C.byref(fp64))
-    roofline = {"kernel": "schur_build (fused residual/Jacobian + Schur elimination)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if world == 1 and args.scale == 1.0:
+            traffic = tj["schur_grouped2_kernel"]["bytes"]  # from the committed ncu --set full capture
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"kernel": "schur_grouped2_kernel (fused residual/Jacobian + Schur elimination)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "note": "by algorithmic count this kernel is FP64-bound, not HBM-bound (SURVEY.md 8d): see roofline_fp64",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": schur_ms}
     roofline_fp64 = {"kernel": "schur_build", "bound": "fp64", "achieved": alg_flops / (schur_ms * 1e-3) / 1e12,
                      "peak": fp64.value, "unit": "TFLOP/s", "frac": alg_flops / (schur_ms * 1e-3) / 1e12 / max(fp64.value, 1e-9),
@@ -333,6 +359,7 @@ def main():
                   "frac_of_hbm": 272 * n_obs / (rj_ms * 1e-3) / 1e9 / peak}
     p.close()
     c4 = bench_c4_windows(lib) if (rank == 0 and not args.no_c4) else None
+    phong = bench_phong_blocks(peak) if (rank == 0 and not args.no_phong) else None
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     e2e = None
@@ -369,7 +396,7 @@ def main():
             "obs_per_s": value * n_obs, "n_obs": n_obs, "n_landmarks": n_lm, "n_poses": n_cam,
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
-            "resjac": resjac, "step_profile_ms": step_profile, "c4_windows": c4,
+            "resjac": resjac, "step_profile_ms": step_profile, "c4_windows": c4, "phong_blocks": phong,
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},
             "setup_s": {"generate": gen_s, "upload_and_structure": upload_s},

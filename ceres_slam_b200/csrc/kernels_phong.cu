@@ -8,7 +8,7 @@
 // allocates two shared_ptr objects per functor call).  Per observation the kernel reads 12 B of
 // indices + 32 B of observations (+ pose / vertex / material gathers that live in L2) and writes
 // 50 doubles: HBM-bound.  Outputs are staged per 128-observation tile in shared memory and leave
-// as TMA bulk stores (cp.async.bulk.global.shared::cta), double buffered.
+// as TMA bulk stores (cp.async.bulk.global.shared::cta); several CTAs per SM overlap tiles.
 #include "kernels.cuh"
 
 namespace cslam {
@@ -17,7 +17,7 @@ namespace {
 
 constexpr int PH_TILE = 128;
 constexpr int PH_STAGE = PH_TILE * 50;  // r_I 1 | J_I 19 | r_N 3 | Jpose_N 18 | Jn_N 9 per observation
-constexpr size_t PH_SMEM = 2 * PH_STAGE * sizeof(double);
+constexpr size_t PH_SMEM = PH_STAGE * sizeof(double);  // one staging tile: 51 KB -> 3-4 CTAs per SM
 
 __global__ void __launch_bounds__(PH_TILE)
     phong_eval_kernel(PhongView v, double* __restrict__ out_rI, double* __restrict__ out_JI, double* __restrict__ out_rN,
@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(PH_TILE)
             cost += 0.5 * (rI * rI + rN[0] * rN[0] + rN[1] * rN[1] + rN[2] * rN[2]);
         }
         if (base + PH_TILE <= v.n) {
-            double* st = s_out + (it & 1) * PH_STAGE;
-            if (tid == 0) tma_store_wait_read<1>();  // the stores that read this stage two tiles ago
+            double* st = s_out;
+            if (tid == 0) tma_store_wait_read<0>();  // the bulk stores of the previous tile have read the stage
             __syncthreads();
             st[tid] = rI;
 #pragma unroll
@@ -109,7 +109,7 @@ void launch_phong_eval(cudaStream_t s, const PhongView& v, double* r_int, double
         attr_done = true;
     }
     const long long tiles = (v.n + PH_TILE - 1) / PH_TILE;
-    const int grid = int(tiles < 2ll * 148 ? tiles : 2ll * 148);  // persistent: 2 CTAs (100 KB each) per SM
+    const int grid = int(tiles < 3ll * 148 ? tiles : 3ll * 148);  // persistent: 3 CTAs per SM (registers)
     phong_eval_kernel<<<grid, PH_TILE, PH_SMEM, s>>>(v, r_int, J_int, r_normal, Jpose_normal, Jn_normal, cost);
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     CSLAM_CUDA(cudaGetLastError());
