@@ -116,6 +116,7 @@ _PRODUCT_ONLY = {
     "add_phong": (C.c_int, [_h, C.c_uint64, _u32p, _u32p, _dp, C.c_double, _dp, _dp]),
     "evaluate_phong": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp, _dp]),
     "time_phong": (C.c_int, [_h, C.c_int, _dp]),
+    "covariance_block": (C.c_int, [_h, C.c_uint32, _dp]),
     "upload": (C.c_int, [_h]),
     "lm_begin": (C.c_int, [_h]),
     "lm_iterate": (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(Summary)]),

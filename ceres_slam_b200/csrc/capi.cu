@@ -280,6 +280,13 @@ cslam_status cslam_solve_batch(cslam_problem** problems, int n, cslam_summary* s
     return guarded(problems[0], [&](Engine&) { cslam::solve_window_batch(es.data(), n, summaries); });
 }
 
+cslam_status cslam_covariance_block(cslam_problem* p, uint32_t cam, double* cov6x6) {
+    return guarded(p, [&](Engine& e) {
+        if (!cov6x6) throw std::invalid_argument("covariance: null output");
+        e.covariance_block(cam, cov6x6);
+    });
+}
+
 cslam_status cslam_get_iteration_log(const cslam_problem* p, double* rows, int max_rows, int* n_rows) {
     if (!p || !p->e) return CSLAM_ERR_INVALID;
     const int n = int(p->e->log.size());

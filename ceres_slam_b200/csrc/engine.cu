@@ -1282,6 +1282,53 @@ double Engine::time_phong(int reps) {
     return double(ms) / reps;
 }
 
+// -------------------------------------------------------------------------------------------------
+// marginal covariance of one pose block (dataset_vo_sun.cpp:159-183)
+// -------------------------------------------------------------------------------------------------
+void Engine::covariance_block(uint32_t cam, double* cov36) {
+    if (cam >= n_poses) throw std::invalid_argument("covariance: pose index out of range");
+    if (n_ranks > 1) throw std::invalid_argument("covariance: single-GPU problems only");
+    // the reduced system at the caller's current values, undamped, exact solve
+    const cslam_options keep = opt;
+    opt.linear_solver = 0;
+    try {
+        upload();
+        lm_begin();
+    } catch (...) {
+        opt = keep;
+        throw;
+    }
+    opt = keep;
+    const int f = cam_free_h[cam];
+    if (f < 0) throw std::invalid_argument("covariance: the pose block is constant");
+    lm.radius = std::numeric_limits<double>::infinity();  // D = 0
+    schur_pass();
+    double sc1[SC_COUNT];
+    read_scalars(d_scal, sc1, SC_COUNT);
+    if (sc1[SC_INVALID] != 0.0) throw std::domain_error("covariance: a landmark block is rank deficient");
+    double sp[6];
+    read_scalars(d_sc_p.p + 6ll * f, sp, 6);
+    // S^-1 e_c for the six columns of the block; un-scale: J = J_s diag(s)^-1  =>  cov = diag(s) cov_s diag(s)
+    for (int c = 0; c < 6; ++c) {
+        CSLAM_CUDA(cudaMemsetAsync(d_bp, 0, 6 * size_t(n_free) * sizeof(double), stream));
+        const double one = 1.0;
+        CSLAM_CUDA(cudaMemcpyAsync(d_bp + 6ll * f + c, &one, sizeof(double), cudaMemcpyHostToDevice, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+        int iters = 0;
+        bool ok = true;
+        const cslam_options keep2 = opt;
+        opt.linear_solver = 0;
+        run_pcg(&iters, &ok);
+        opt = keep2;
+        if (!ok) throw std::domain_error("covariance: the reduced camera system is not positive definite");
+        double col[6];
+        read_scalars(d_yp.p + 6ll * f, col, 6);
+        for (int r = 0; r < 6; ++r) cov36[6 * r + c] = sp[r] * col[r] * sp[c];
+    }
+    lm.have_system = false;
+    uploaded = begun = false;  // the device state no longer mirrors a solve in progress
+}
+
 double Engine::time_resjac(int reps) {
     ensure_user_copy();
     d_poses_cand.upload(h_poses, 12 * size_t(n_poses), stream);

@@ -178,6 +178,7 @@ class Engine {
     void evaluate(int apply_loss, double* cost, double* r_st, double* Jc_st, double* Jp_st, double* r_sun,
                   double* J_sun, double* r_pr, double* J_pr);
     double time_resjac(int reps);
+    void covariance_block(uint32_t cam, double* cov36);
     void evaluate_phong(double* cost, double* r_int, double* J_int, double* r_n, double* Jc_n, double* Jn_n);
     double time_phong(int reps);
     double time_schur(int reps);

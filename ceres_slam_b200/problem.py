@@ -155,6 +155,12 @@ class BAProblem:
         out["cost"] = cost.value
         return out
 
+    def covariance_block(self, cam):
+        """GetCovarianceBlockInTangentSpace(pose cam, pose cam) at the current parameter values."""
+        cov = np.zeros((6, 6))
+        self._check(self.lib.covariance_block(self._h, int(cam), capi.dptr(cov)))
+        return cov
+
     def time_phong(self, reps):
         ms = C.c_double(0)
         self._check(self.lib.time_phong(self._h, reps, C.byref(ms)))

@@ -198,6 +198,14 @@ cslam_status cslam_reset_state(cslam_problem* p);
  * in one launch per GPU.  Each problem must already hold its data. */
 cslam_status cslam_solve_batch(cslam_problem** problems, int n, cslam_summary* summaries);
 
+/* ceres::Covariance::Compute + GetCovarianceBlockInTangentSpace for one pose block
+ * (dataset_vo_sun.cpp:159-183: the covariance of pose k1+1 becomes the prior of the next window):
+ * the (cam, cam) 6x6 block of (J^T J)^-1 in tangent coordinates at the caller's current parameter
+ * values, loss-corrected Jacobians, no LM damping; computed as the (cam, cam) block of the inverse of
+ * the undamped reduced camera system.  Row-major 6x6.  Fails with CSLAM_ERR_INVALID for a constant
+ * pose and CSLAM_ERR_NUMERIC when the reduced system is not positive definite (rank-deficient J). */
+cslam_status cslam_covariance_block(cslam_problem* p, uint32_t cam, double* cov6x6);
+
 /* Iteration log of the last solve: up to max_rows rows of CSLAM_LOG_COLS doubles; returns the
  * number of rows available in *n_rows. */
 cslam_status cslam_get_iteration_log(const cslam_problem* p, double* rows, int max_rows, int* n_rows);

@@ -359,3 +359,83 @@ def test_phong_blocks(product, oracle, directional):
     # a meaningful scene: most vertices are lit and unsaturated
     lit = np.abs(eo["J_int"][:, 15]) > 0
     assert lit.mean() > 0.3
+
+
+def _oracle_covariance(track, poses, points, cam, constant, **kw):
+    """(J^T J)^-1 block of one pose from the ORACLE's tangent-space Jacobians (loss-corrected),
+    assembled sparse and factored with SuperLU: what ceres::Covariance computes
+    (dataset_vo_sun.cpp:159-183)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    tr = dict(track, poses=poses, points=points, constant=constant)
+    po, _, _ = syn.build_problem(tr, backend="oracle", hold_first=bool(constant[0]), **kw)
+    ev = po.evaluate(apply_loss=True)
+    n_p, n_l = poses.shape[0], points.shape[0]
+    free = np.flatnonzero(constant == 0)
+    col_of = -np.ones(n_p, dtype=np.int64)
+    col_of[free] = 6 * np.arange(free.size)
+    off_l = 6 * free.size
+    rows, cols, vals = [], [], []
+    r0 = 0
+
+    def add(block_rows, c0, J):
+        rr, cc = np.meshgrid(np.arange(J.shape[0]), np.arange(J.shape[1]), indexing="ij")
+        rows.append((block_rows + rr).ravel()); cols.append((c0 + cc).ravel()); vals.append(J.ravel())
+
+    for i in range(tr["obs_cam"].size):
+        k, j = int(tr["obs_cam"][i]), int(tr["obs_pt"][i])
+        if col_of[k] >= 0:
+            add(r0, col_of[k], ev["Jpose_stereo"][i])
+        add(r0, off_l + 3 * j, ev["Jpoint_stereo"][i])
+        r0 += 3
+    for i in range(ev["J_sun"].shape[0]):
+        k = int(tr["sun_cam"][i])
+        if col_of[k] >= 0:
+            add(r0, col_of[k], ev["J_sun"][i])
+        r0 += 2
+    if ev["J_prior"].shape[0]:
+        k = kw["prior"][0]
+        if col_of[k] >= 0:
+            add(r0, col_of[k], ev["J_prior"][0])
+        r0 += 6
+    n_cols = off_l + 3 * n_l
+    J = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(r0, n_cols)).tocsc()
+    used = np.flatnonzero(np.asarray(abs(J).sum(axis=0)).ravel() > 0)  # points without observations have no columns
+    H = (J.T @ J).tocsc()[used][:, used]
+    lu = spla.splu(H)
+    pos = {c: i for i, c in enumerate(used)}
+    E = np.zeros((used.size, 6))
+    for c in range(6):
+        E[pos[col_of[cam] + c], c] = 1.0
+    X = lu.solve(E)
+    return np.array([[X[pos[col_of[cam] + r], c] for c in range(6)] for r in range(6)])
+
+
+def test_covariance_block_window(product):
+    """the marginal covariance of the second pose of a dataset_vo_sun window
+    (sun blocks with Huber loss + pose prior), at the solution."""
+    tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42, per_obs_W=True))
+    w = syn.window_of(tr, 20, 22)
+    prior = (0, w["poses"][0].copy(), np.eye(6) * 1e3)
+    kw = dict(sun=True, prior=prior, huber=1.0)
+    pg, poses_g, points_g = syn.build_problem(w, backend="b200", hold_first=False, **kw)
+    pg.solve()
+    cov = pg.covariance_block(1)
+    ref = _oracle_covariance(w, poses_g.copy(), points_g.copy(), 1, np.zeros(2, dtype=np.uint8), **kw)
+    assert np.allclose(cov, cov.T, rtol=1e-9, atol=1e-18)
+    assert rel_err(cov, ref) < 1e-7
+    assert np.all(np.linalg.eigvalsh(cov) > 0)
+
+
+def test_covariance_block_full_batch(product):
+    """The same on a full-batch problem (first pose constant): banded direct solver path."""
+    tr = syn.make_track(60, 15, 6, seed=21)
+    pg, poses_g, points_g = syn.build_problem(tr, backend="b200", max_num_iterations=8)
+    pg.solve()
+    for cam in (1, 30, 59):
+        cov = pg.covariance_block(cam)
+        ref = _oracle_covariance(tr, poses_g.copy(), points_g.copy(), cam, tr["constant"])
+        assert rel_err(cov, ref) < 1e-7, cam
+    from ceres_slam_b200.problem import CslamError
+    with pytest.raises(CslamError):
+        pg.covariance_block(0)  # constant pose
