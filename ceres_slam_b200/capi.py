@@ -108,12 +108,14 @@ _COMMON = {
     "evaluate": (C.c_int, [_h, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "solve": (C.c_int, [_h, C.POINTER(Summary)]),
     "get_iteration_log": (C.c_int, [_h, _dp, C.c_int, _ip]),
-}
-_PRODUCT_ONLY = {
     "set_vertices": (C.c_int, [_h, C.c_uint32, _dp, _dp, _u32p]),
+    "set_textures": (C.c_int, [_h, C.c_uint32, _dp, _u32p]),
     "set_materials": (C.c_int, [_h, C.c_uint32, _dp]),
     "set_light": (C.c_int, [_h, _dp, C.c_int]),
+    "set_bounds": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "add_phong": (C.c_int, [_h, C.c_uint64, _u32p, _u32p, _dp, C.c_double, _dp, _dp]),
+}
+_PRODUCT_ONLY = {
     "evaluate_phong": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp, _dp]),
     "time_phong": (C.c_int, [_h, C.c_int, _dp]),
     "covariance_block": (C.c_int, [_h, C.c_uint32, _dp]),

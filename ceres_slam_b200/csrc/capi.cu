@@ -23,6 +23,9 @@ cslam_status guarded(cslam_problem* p, F&& f) {
     } catch (const cslam::CudaError& ex) {
         p->e->err = ex.what();
         return CSLAM_ERR_CUDA;
+    } catch (const cslam::NotImplemented& ex) {
+        p->e->err = ex.what();
+        return CSLAM_ERR_NOT_IMPL;
     } catch (const std::invalid_argument& ex) {
         p->e->err = ex.what();
         return CSLAM_ERR_INVALID;
@@ -194,7 +197,39 @@ cslam_status cslam_set_vertices(cslam_problem* p, uint32_t n, double* normals3, 
         e.h_textures = textures;
         e.h_material_id = material_id;
         e.n_vertices = n;
+        e.h_tex_shared = nullptr;
+        e.h_texture_id = nullptr;
+        e.n_tex_shared = 0;
         e.phong_ready = false;
+        e.uploaded = e.begun = false;
+    });
+}
+cslam_status cslam_set_textures(cslam_problem* p, uint32_t n_textures, double* kd, const uint32_t* vertex_texture_id) {
+    return guarded(p, [&](Engine& e) {
+        if (!kd || !vertex_texture_id || n_textures == 0) throw std::invalid_argument("textures: null or empty");
+        if (e.n_vertices == 0) throw std::invalid_argument("textures: call cslam_set_vertices first");
+        for (uint32_t j = 0; j < e.n_vertices; ++j)
+            if (vertex_texture_id[j] >= n_textures) throw std::invalid_argument("texture index out of range");
+        e.h_tex_shared = kd;
+        e.h_texture_id = vertex_texture_id;
+        e.n_tex_shared = n_textures;
+        e.phong_ready = false;
+        e.uploaded = e.begun = false;
+    });
+}
+cslam_status cslam_set_bounds(cslam_problem* p, int block_kind, const double* lower, const double* upper) {
+    return guarded(p, [&](Engine& e) {
+        if (!lower || !upper) throw std::invalid_argument("bounds: null");
+        if (block_kind == 0) {
+            for (int k = 0; k < 3; ++k) e.mat_lo[k] = lower[k], e.mat_hi[k] = upper[k];
+        } else if (block_kind == 1) {
+            e.tex_lo = lower[0];
+            e.tex_hi = upper[0];
+        } else {
+            throw std::invalid_argument("bounds: block_kind must be 0 (material) or 1 (texture)");
+        }
+        e.bounded = true;
+        e.uploaded = e.begun = false;
     });
 }
 cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double* phong3) {
@@ -202,6 +237,7 @@ cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double*
         if (!phong3 || n_materials == 0) throw std::invalid_argument("materials: null or empty");
         e.h_phong = phong3;
         e.n_materials = n_materials;
+        e.uploaded = e.begun = false;
     });
 }
 cslam_status cslam_set_light(cslam_problem* p, double* light3, int directional) {
@@ -209,6 +245,7 @@ cslam_status cslam_set_light(cslam_problem* p, double* light3, int directional) 
         if (!light3) throw std::invalid_argument("light: null");
         e.h_light = light3;
         e.light_directional = directional ? 1 : 0;
+        e.uploaded = e.begun = false;
     });
 }
 cslam_status cslam_add_phong(cslam_problem* p, uint64_t n, const uint32_t* cam, const uint32_t* vertex,
@@ -226,6 +263,7 @@ cslam_status cslam_add_phong(cslam_problem* p, uint64_t n, const uint32_t* cam, 
         e.ph_int_stiffness = int_stiffness;
         std::memcpy(e.ph_W_normal, W_normal9, 72);
         e.phong_ready = false;
+        e.uploaded = e.begun = false;
     });
 }
 cslam_status cslam_evaluate_phong(cslam_problem* p, double* cost, double* r_int, double* J_int, double* r_normal,
@@ -257,7 +295,7 @@ cslam_status cslam_reset_state(cslam_problem* p) {
 
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary) {
     return guarded(p, [&](Engine& e) {
-        if (e.window_eligible() || e.opt.window_path == 2) {
+        if (!e.lighting_in_solve() && (e.window_eligible() || e.opt.window_path == 2)) {
             // configs 1/2: a sliding window is one CTA with the LM loop on the device
             Engine* one = &e;
             cslam::solve_window_batch(&one, 1, summary);

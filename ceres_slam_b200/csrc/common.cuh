@@ -14,6 +14,10 @@ struct CudaError : std::runtime_error {
     explicit CudaError(const std::string& m) : std::runtime_error(m) {}
 };
 
+struct NotImplemented : std::logic_error {
+    explicit NotImplemented(const std::string& m) : std::logic_error(m) {}
+};
+
 #define CSLAM_CUDA(expr)                                                                     \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

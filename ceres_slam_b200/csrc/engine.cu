@@ -640,13 +640,28 @@ void Engine::upload() {
         d_lt_col.upload(ecb, stream);
     }
     pt.lap("  mirrored lists");
-    red_count = 36 * size_t(nnzU) + 36 * size_t(n_free) + 6 * size_t(n_free) + 6 * size_t(n_free) + SC_COUNT;
+    // the joint lighting solve appends its dense border [S_cg | S_gg | b_g | g_g | h_g] to the same buffer
+    ph.active = lighting_in_solve();
+    size_t gext = 0;
+    if (ph.active) {
+        check_phong_solve();
+        gext = size_t(ph.n_g) * 6 * size_t(n_free) + size_t(ph.n_g) * ph.n_g + 3 * size_t(ph.n_g);
+    }
+    red_count = 36 * size_t(nnzU) + 36 * size_t(n_free) + 6 * size_t(n_free) + 6 * size_t(n_free) + gext + SC_COUNT;
     d_red.alloc(red_count, stream);
     d_S = d_red.p;
     d_Bdiag = d_S + 36 * size_t(nnzU);
     d_bp = d_Bdiag + 36 * size_t(n_free);
     d_gp = d_bp + 6 * size_t(n_free);
     d_scal = d_gp + 6 * size_t(n_free);
+    if (ph.active) {
+        ph.Scg = d_scal;
+        ph.Sgg = ph.Scg + size_t(ph.n_g) * 6 * size_t(n_free);
+        ph.bg = ph.Sgg + size_t(ph.n_g) * ph.n_g;
+        ph.gg = ph.bg + ph.n_g;
+        ph.hg = ph.gg + ph.n_g;
+        d_scal = ph.hg + ph.n_g;
+    }
     d_Minv.alloc(36 * size_t(std::max(n_free, 1)), stream);
     d_diag_p.alloc(6 * size_t(std::max(n_free, 1)), stream);
     const size_t nv = 6 * size_t(std::max(n_free, 1));
@@ -664,6 +679,7 @@ void Engine::upload() {
     d_scal2.alloc(SC_COUNT, stream);
     if (!suns.empty()) d_suns.upload(suns, stream);
     if (!priors.empty()) d_priors.upload(priors, stream);
+    if (ph.active) setup_phong_solve();
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     pt.lap("  stream sync");
     d_raw_cam.release_async(stream);  // d_raw_pts stays: download() scatters the result into it
@@ -730,6 +746,15 @@ void Engine::reset_state() {
         CSLAM_CUDA(cudaMemcpyAsync(d_points.p, d_points_init.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
         CSLAM_CUDA(cudaMemcpyAsync(d_points_best.p, d_points_init.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
     }
+    if (ph.active) {
+        auto cp = [&](DBuf<double>& dst, const DBuf<double>& src) {
+            if (src.n) CSLAM_CUDA(cudaMemcpyAsync(dst.p, src.p, src.bytes(), cudaMemcpyDeviceToDevice, stream));
+        };
+        cp(ph.normals, ph.normals_init);
+        cp(ph.normals_best, ph.normals_init);
+        cp(ph.gx, ph.gx_init);
+        cp(ph.gx_best, ph.gx_init);
+    }
     begun = false;
 }
 
@@ -743,8 +768,158 @@ void Engine::download() {
         launch_scatter_points(stream, n_lm, d_lm_user.p, d_points_best.p, d_raw_pts.p);
         CSLAM_CUDA(cudaMemcpyAsync(h_points, d_raw_pts.p, 3 * size_t(n_points) * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
+    std::vector<double> nrm, gxh;
+    if (ph.active) {
+        nrm.resize(3 * size_t(n_lm));
+        gxh.resize(ph.n_g);
+        if (n_lm) CSLAM_CUDA(cudaMemcpyAsync(nrm.data(), ph.normals_best.p, nrm.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaMemcpyAsync(gxh.data(), ph.gx_best.p, gxh.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     for (int k : free_cams_h) std::memcpy(h_poses + 12 * size_t(k), &pos[12 * size_t(k)], 96);
+    if (ph.active) {
+        for (int j = 0; j < n_lm; ++j) std::memcpy(h_normals + 3 * size_t(lm_user_h[j]), &nrm[3 * size_t(j)], 24);
+        const int t0 = 3 * ph.n_mat, l0 = t0 + ph.n_tex;
+        for (int k = 0; k < ph.n_g; ++k) {
+            if (!ph.g_used_h[k]) continue;
+            if (k < t0)
+                h_phong[k] = gxh[k];
+            else if (k < l0)
+                h_tex_shared[k - t0] = gxh[k];
+            else
+                h_light[k - l0] = gxh[k];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Joint lighting solve (dataset_ba_phong.cpp:100-252): vertex = position + normal, shared blocks
+// -------------------------------------------------------------------------------------------------
+void Engine::check_phong_solve() {
+    auto not_impl = [](const char* m) { throw NotImplemented(m); };
+    if (n_ranks > 1) not_impl("lighting solve: single GPU only");
+    if (!h_normals || !h_material_id || !h_phong || !h_light) throw std::invalid_argument("vertices / materials / light not set");
+    if (n_vertices != n_points) throw std::invalid_argument("one normal / material id per point expected");
+    if (!h_tex_shared) not_impl("lighting solve: textures must be shared blocks (cslam_set_textures)");
+    if (n_ph != n_st || std::memcmp(ph_cam, st_cam, n_st * sizeof(uint32_t)) != 0 ||
+        std::memcmp(ph_vertex, st_pt, n_st * sizeof(uint32_t)) != 0)
+        not_impl("lighting solve: lighting blocks must pair one-to-one with the stereo blocks");
+    if (st_W_per_obs || !suns.empty() || !priors.empty()) not_impl("lighting solve: shared stereo stiffness, no sun / prior blocks");
+    for (uint32_t j = 0; j < n_vertices; ++j)
+        if (h_material_id[j] >= n_materials) throw std::invalid_argument("material id out of range");
+    ph.n_mat = int(n_materials);
+    ph.n_tex = int(n_tex_shared);
+    ph.n_g = 3 * ph.n_mat + ph.n_tex + 3;
+    if (ph.n_g > 96) not_impl("lighting solve: at most 96 shared columns (3 per material + 1 per texture + 3)");
+    for (int j = 0; j < n_lm; ++j)
+        if (lm_cnt_h[j] > 32) not_impl("lighting solve: at most 32 observations per vertex");
+}
+
+void Engine::setup_phong_solve() {
+    const size_t nl = size_t(std::max(n_lm, 1)), no = size_t(std::max<long long>(n_obs, 1));
+    std::vector<double> nrm(3 * nl, 0.0), gxh(ph.n_g), oI(no, 0.0), on(3 * no, 0.0);
+    std::vector<int> vm(nl, 0), vt(nl, 0);
+    ph.g_used_h.assign(ph.n_g, 0);
+    const int t0 = 3 * ph.n_mat, l0 = t0 + ph.n_tex;
+    for (int j = 0; j < n_lm; ++j) {
+        const uint32_t u = lm_user_h[j];
+        std::memcpy(&nrm[3 * size_t(j)], h_normals + 3 * size_t(u), 24);
+        vm[j] = int(h_material_id[u]);
+        vt[j] = int(h_texture_id[u]);
+        for (int k = 0; k < 3; ++k) ph.g_used_h[3 * vm[j] + k] = 1;
+        ph.g_used_h[t0 + vt[j]] = 1;
+    }
+    if (n_lm)
+        for (int k = 0; k < 3; ++k) ph.g_used_h[l0 + k] = 1;
+    for (long long e = 0; e < n_obs; ++e) {
+        const uint32_t u = obs_user_h[size_t(e)];
+        oI[size_t(e)] = ph_intensity[u];
+        for (int k = 0; k < 3; ++k) on[size_t(k) * no + size_t(e)] = ph_normal_obs[3 * size_t(u) + k];
+    }
+    std::memcpy(gxh.data(), h_phong, 3 * size_t(ph.n_mat) * sizeof(double));
+    std::memcpy(gxh.data() + t0, h_tex_shared, size_t(ph.n_tex) * sizeof(double));
+    std::memcpy(gxh.data() + l0, h_light, 24);
+    ph.normals_init.upload(nrm, stream);
+    ph.gx_init.upload(gxh, stream);
+    ph.v_mat.upload(vm, stream);
+    ph.v_tex.upload(vt, stream);
+    ph.g_used.upload(ph.g_used_h, stream);
+    ph.obs_I.upload(oI, stream);
+    ph.obs_n.upload(on, stream);
+    for (DBuf<double>* b : {&ph.normals, &ph.normals_cand, &ph.normals_best, &ph.sc_n, &ph.cn_n}) b->alloc(3 * nl, stream);
+    for (DBuf<double>* b : {&ph.gx, &ph.gx_cand, &ph.gx_best, &ph.sc_g, &ph.yg, &ph.diag_g, &ph.zero_g}) b->alloc(ph.n_g, stream);
+    ph.zero_g.zero(stream);
+    ph.gv.alloc(6 * nl, stream);
+    ph.yv.alloc(6 * nl, stream);
+    ph.X.alloc(size_t(ph.n_g + 1) * 6 * size_t(std::max(n_free, 1)), stream);
+    ph.T.alloc(size_t(ph.n_g) * (ph.n_g + 1), stream);
+    CSLAM_CUDA(cudaStreamSynchronize(stream));  // the host staging vectors go out of scope
+}
+
+PhongSolveView Engine::phong_solve_view(const double* normals, const double* gx) const {
+    PhongSolveView q;
+    q.normals = normals;
+    q.v_mat = ph.v_mat.p;
+    q.v_tex = ph.v_tex.p;
+    q.gx = gx;
+    q.obs_I = ph.obs_I.p;
+    q.obs_n = ph.obs_n.p;
+    q.sc_n = ph.sc_n.p;
+    q.sc_g = ph.sc_g.p;
+    q.g_used = ph.g_used.p;
+    std::memcpy(q.Wn, ph_W_normal, sizeof(q.Wn));
+    q.int_stiffness = ph_int_stiffness;
+    q.directional = light_directional;
+    q.n_mat = ph.n_mat;
+    q.n_tex = ph.n_tex;
+    q.n_g = ph.n_g;
+    for (int k = 0; k < 3; ++k) q.mat_lo[k] = mat_lo[k], q.mat_hi[k] = mat_hi[k];
+    q.tex_lo = tex_lo;
+    q.tex_hi = tex_hi;
+    return q;
+}
+
+PhongSystem Engine::phong_system() {
+    PhongSystem o;
+    o.S = d_S;
+    o.Bdiag = d_Bdiag;
+    o.bp = d_bp;
+    o.gp = d_gp;
+    o.Scg = ph.Scg;
+    o.Sgg = ph.Sgg;
+    o.bg = ph.bg;
+    o.gg = ph.gg;
+    o.hg = ph.hg;
+    o.gv = ph.gv.p;
+    o.cn_l = d_cn_l.p;
+    o.cn_n = ph.cn_n.p;
+    o.scal = d_scal;
+    return o;
+}
+
+// The arrowhead system [S_cc S_cg; S_cg^T S_gg]: n_g + 1 solves against S_cc (border columns and
+// b_c), then the dense n_g x n_g border system, then y_c = x_b - X_g y_g.
+void Engine::phong_linear_solve(int* iters, bool* ok) {
+    *iters = 1;
+    *ok = true;
+    prof_begin(CSLAM_K_PCG);
+    const size_t nf6 = 6 * size_t(n_free);
+    if (n_free > 0) {
+        for (int k = 0; k < ph.n_g; ++k) {
+            if (ph.g_used_h[k])
+                solve_reduced(ph.Scg + size_t(k) * nf6, ph.X.p + size_t(k) * nf6);
+            else
+                CSLAM_CUDA(cudaMemsetAsync(ph.X.p + size_t(k) * nf6, 0, nf6 * sizeof(double), stream));
+        }
+        solve_reduced(d_bp, ph.X.p + size_t(ph.n_g) * nf6);
+    } else {
+        launch_fill(stream, d_pscal.p, PS_COUNT, 0.0);
+    }
+    launch_phong_border_solve(stream, ph.n_g, int(nf6), ph.Scg, ph.X.p, ph.Sgg, ph.bg, ph.T.p, ph.yg.p, d_yp.p, d_pscal.p);
+    double ps[PS_COUNT];
+    read_scalars(d_pscal.p, ps, PS_COUNT);
+    prof_end(CSLAM_K_PCG);
+    *ok = ps[PS_FAIL] != 2.0;
 }
 
 void Engine::allreduce_system() {
@@ -766,14 +941,20 @@ void Engine::schur_pass() {
     DevView v = view(d_poses.p, d_points.p);
     prof_begin(CSLAM_K_SCHUR);
     d_red.zero(stream);
-    launch_schur(v, dg);
-    if (rank == 0)
-        launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
-                             d_scal);
+    if (ph.active) {
+        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, dg, phong_system(), true);
+    } else {
+        launch_schur(v, dg);
+        if (rank == 0)
+            launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
+                                 d_scal);
+    }
     prof_end(CSLAM_K_SCHUR);
     allreduce_system();
     prof_begin(CSLAM_K_FINALIZE);
     launch_finalize(stream, v, dg, opt.preconditioner, d_S, d_Bdiag, d_diag_p.p, d_Minv.p, d_scal);
+    if (ph.active)
+        launch_phong_gfinalize(stream, phong_solve_view(ph.normals.p, ph.gx.p), dg, ph.Sgg, ph.bg, ph.hg, ph.diag_g.p);
     prof_end(CSLAM_K_FINALIZE);
     lm.have_system = true;
 }
@@ -781,7 +962,12 @@ void Engine::schur_pass() {
 void Engine::gradient_norm_pass() {
     DevView v = view(d_poses.p, d_points.p);
     // SC_GRADMAX / SC_XNORM2_CUR are not touched by the Schur kernels
-    launch_gradnorm(stream, v, 0, n_lm, d_gp, d_gl.p, d_scal, rank == 0);
+    if (ph.active) {
+        launch_gradnorm(stream, v, 0, 0, d_gp, d_gl.p, d_scal, 1);
+        launch_phong_gradnorm(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, ph.gv.p, ph.gg, d_scal, 1);
+    } else {
+        launch_gradnorm(stream, v, 0, n_lm, d_gp, d_gl.p, d_scal, rank == 0);
+    }
     double loc[SC_COUNT];
     if (n_ranks > 1) {
         // max over ranks == max of the per-rank maxima: all-reduce the squared-norm slot with sum
@@ -795,7 +981,8 @@ void Engine::gradient_norm_pass() {
     lm.grad_fresh = true;
 }
 
-void Engine::run_pcg(int* iters, bool* ok) {
+// One solve S_cc y = rhs with the solver the options select (enqueue only; status in d_pscal)
+void Engine::solve_reduced(const double* rhs, double* y) {
     PcgBufs B;
     B.rowptr = d_s_rowptr.p;
     B.col = d_s_col.p;
@@ -803,16 +990,14 @@ void Engine::run_pcg(int* iters, bool* ok) {
     B.ent_cb = d_lt_col.p;
     B.S = d_S;
     B.Minv = d_Minv.p;
-    B.b = d_bp;
-    B.x = d_yp.p;
+    B.b = rhs;
+    B.x = y;
     B.r = d_pr.p;
     B.z = d_pz.p;
     B.p = d_pp.p;
     B.q = d_pq.p;
     B.ps = d_pscal.p;
     B.nf = n_free;
-    *iters = 0;
-    *ok = true;
     if (n_free == 0) return;
     double q_tol, r_tol;
     int max_it, min_it;
@@ -829,7 +1014,6 @@ void Engine::run_pcg(int* iters, bool* ok) {
         max_it = opt.max_linear_solver_iterations;
         min_it = opt.min_linear_solver_iterations;
     }
-    prof_begin(CSLAM_K_PCG);
     if (band_active) {
         BandView V;
         V.n = n_free;
@@ -838,7 +1022,7 @@ void Engine::run_pcg(int* iters, bool* ok) {
         V.m = band_m;
         V.band_idx = d_band_idx.p;
         V.S = d_S;
-        V.rhs = d_bp;
+        V.rhs = rhs;
         V.Lbuf = d_Lbuf.p;
         V.Xbuf = d_Xbuf.p;
         V.Ta = d_Ta.p;
@@ -846,13 +1030,21 @@ void Engine::run_pcg(int* iters, bool* ok) {
         V.fa = d_fa.p;
         V.Tb = d_Tb.p;
         V.fb = d_fb.p;
-        V.y = d_yp.p;
+        V.y = y;
         V.fail = d_band_fail.p;
         const BandScratch K{d_T2.p, d_rhs2.p, d_L2.p, d_X2.p, d_y2.p};
         launch_band_solve(stream, V, K, d_pscal.p);
     } else {
         launch_pcg_persistent(stream, B, d_pp2.p, d_prec.p, q_tol, r_tol, min_it, max_it, 10);
     }
+}
+
+void Engine::run_pcg(int* iters, bool* ok) {
+    *iters = 0;
+    *ok = true;
+    if (n_free == 0) return;
+    prof_begin(CSLAM_K_PCG);
+    solve_reduced(d_bp, d_yp.p);
     if (n_ranks > 1) {
         // every rank solved the same system; rank 0's iterate is adopted everywhere so that all
         // ranks keep bit-identical poses (and therefore take identical accept/reject decisions)
@@ -866,6 +1058,76 @@ void Engine::run_pcg(int* iters, bool* ok) {
     *ok = ps[PS_FAIL] != 2.0;
 }
 
+void Engine::copy_phong_best() {
+    if (!ph.active) return;
+    if (n_lm) CSLAM_CUDA(cudaMemcpyAsync(ph.normals_best.p, ph.normals.p, ph.normals.bytes(), cudaMemcpyDeviceToDevice, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(ph.gx_best.p, ph.gx.p, ph.gx.bytes(), cudaMemcpyDeviceToDevice, stream));
+}
+
+// Back-substitution of the vertex blocks, model cost change, candidate point and its cost; for a
+// bounded problem the Armijo search of TrustRegionMinimizer::DoLineSearch along the step (the
+// candidate is then x (+) alpha * delta).  sc2 receives the scalars of the accepted candidate.
+void Engine::phong_step(const LmDiag& dg, double* sc2) {
+    DevView v = view(d_poses.p, d_points.p);
+    const PhongSolveView q = phong_solve_view(ph.normals.p, ph.gx.p);
+    prof_begin(CSLAM_K_BACKSUB);
+    d_scal2.zero(stream);
+    launch_phong_backsub(stream, v, q, 0, n_lm, dg, d_yp.p, ph.yg.p, ph.gv.p, ph.yv.p, d_scal2.p);
+    if (bounded) {
+        launch_dot(stream, d_gp, d_yp.p, 6ll * n_free, d_scal2.p + SC_LS_GY);
+        launch_dot(stream, ph.gg, ph.yg.p, ph.n_g, d_scal2.p + SC_LS_GY);
+        launch_absmax_scaled(stream, d_yp.p, d_sc_p.p, 6ll * n_free, d_scal2.p + SC_LS_DMAX);
+        launch_absmax_scaled(stream, ph.yg.p, ph.sc_g.p, ph.n_g, d_scal2.p + SC_LS_DMAX);
+    }
+    launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p, d_points_cand.p,
+                           ph.normals_cand.p, d_scal2.p, 1);
+    read_scalars(d_scal2.p, sc2, SC_COUNT);
+    if (bounded && sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0) {
+        const double g0 = -sc2[SC_LS_GY], dmax = sc2[SC_LS_DMAX];
+        const double model = sc2[SC_MODEL];
+        double a_cur = 1.0, f_cur = sc2[SC_CAND_COST];
+        double first[SC_COUNT];
+        std::memcpy(first, sc2, sizeof(first));
+        bool success = true;
+        int ls_it = 0;
+        while (!std::isfinite(f_cur) || f_cur > lm.x_cost + 1e-4 * g0 * a_cur) {
+            if (++ls_it >= 20) {
+                success = false;
+                break;
+            }
+            const double lo = 1e-3 * a_cur, hi = 0.6 * a_cur;
+            double a_new;
+            if (!std::isfinite(f_cur)) {
+                a_new = std::min(std::max(0.5 * a_cur, lo), hi);
+            } else {
+                const double c2 = (f_cur - lm.x_cost - g0 * a_cur) / (a_cur * a_cur);
+                a_new = c2 > 0.0 ? -g0 / (2.0 * c2) : hi;
+                a_new = std::min(std::max(a_new, lo), hi);
+            }
+            if (a_new * dmax < 1e-9) {
+                success = false;
+                break;
+            }
+            a_cur = a_new;
+            d_scal2.zero(stream);
+            launch_phong_candidate(stream, v, q, 0, n_lm, a_cur, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p,
+                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1);
+            read_scalars(d_scal2.p, sc2, SC_COUNT);
+            f_cur = sc2[SC_CAND_COST];
+        }
+        if (!success && a_cur != 1.0) {
+            // the search failed: Ceres keeps the full step
+            d_scal2.zero(stream);
+            launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p,
+                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1);
+            read_scalars(d_scal2.p, sc2, SC_COUNT);
+        }
+        sc2[SC_MODEL] = model;
+        sc2[SC_NONFINITE] = first[SC_NONFINITE];
+    }
+    prof_end(CSLAM_K_BACKSUB);
+}
+
 // -------------------------------------------------------------------------------------------------
 // LM loop
 // -------------------------------------------------------------------------------------------------
@@ -876,13 +1138,31 @@ void Engine::lm_begin() {
     // unit scaling for the initial pass
     launch_fill(stream, d_sc_p.p, d_sc_p.n, 1.0);
     launch_fill(stream, d_sc_l.p, d_sc_l.n, 1.0);
+    if (ph.active) {
+        launch_fill(stream, ph.sc_n.p, ph.sc_n.n, 1.0);
+        launch_fill(stream, ph.sc_g.p, ph.sc_g.n, 1.0);
+        if (bounded) {
+            // IterationZero of a bounded problem: x <- Plus(x, 0), i.e. projected onto the box (and
+            // unit vectors re-normalised); poses and positions are unchanged by a zero step
+            launch_phong_project_initial(stream, phong_solve_view(ph.normals.p, ph.gx.p), n_lm, ph.normals.p, ph.gx_cand.p,
+                                         ph.zero_g.p);
+            CSLAM_CUDA(cudaMemcpyAsync(ph.gx.p, ph.gx_cand.p, ph.gx.bytes(), cudaMemcpyDeviceToDevice, stream));
+            CSLAM_CUDA(cudaMemcpyAsync(ph.gx_best.p, ph.gx.p, ph.gx.bytes(), cudaMemcpyDeviceToDevice, stream));
+            CSLAM_CUDA(cudaMemcpyAsync(ph.normals_best.p, ph.normals.p, ph.normals.bytes(), cudaMemcpyDeviceToDevice, stream));
+        }
+    }
     DevView v = view(d_poses.p, d_points.p);
     prof_begin(CSLAM_K_COLNORM);
     d_red.zero(stream);
-    launch_colnorm(stream, v, 0, n_lm, d_Bdiag, d_cn_l.p, d_gp, d_gl.p, d_scal);
-    if (rank == 0)
-        launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
-                             d_scal);
+    if (ph.active) {
+        const LmDiag unit{1.0, opt.min_lm_diagonal, opt.max_lm_diagonal};
+        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, unit, phong_system(), false);
+    } else {
+        launch_colnorm(stream, v, 0, n_lm, d_Bdiag, d_cn_l.p, d_gp, d_gl.p, d_scal);
+        if (rank == 0)
+            launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
+                                 d_scal);
+    }
     prof_end(CSLAM_K_COLNORM);
     allreduce_system();
     gradient_norm_pass();  // sc == 1: gp, gl are the unscaled gradient
@@ -890,6 +1170,10 @@ void Engine::lm_begin() {
     read_scalars(d_scal, loc, SC_COUNT);
     launch_jacobi_scale_cams(stream, d_Bdiag, d_sc_p.p, n_free, opt.jacobi_scaling);
     launch_jacobi_scale(stream, d_cn_l.p, d_sc_l.p, 3ll * n_lm, opt.jacobi_scaling);
+    if (ph.active) {
+        launch_jacobi_scale(stream, ph.cn_n.p, ph.sc_n.p, 3ll * n_lm, opt.jacobi_scaling);
+        launch_jacobi_scale(stream, ph.hg, ph.sc_g.p, ph.n_g, opt.jacobi_scaling);
+    }
     if (!std::isfinite(loc[SC_COST])) {
         lm.finished = true;
         lm.termination_type = 2;
@@ -945,6 +1229,7 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
                     CSLAM_CUDA(cudaMemcpyAsync(d_poses_best.p, d_poses.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
                     if (n_lm)
                         CSLAM_CUDA(cudaMemcpyAsync(d_points_best.p, d_points.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
+                    copy_phong_best();
                 }
             } else {
                 ++lm.num_unsuccessful;
@@ -977,13 +1262,22 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
         int lin_iters = 0;
         bool lin_ok = true;
         bool valid = sc1[SC_INVALID] == 0.0;
-        if (valid) run_pcg(&lin_iters, &lin_ok);
+        if (valid) {
+            if (ph.active)
+                phong_linear_solve(&lin_iters, &lin_ok);
+            else
+                run_pcg(&lin_iters, &lin_ok);
+        }
         valid = valid && lin_ok;
         row.v[7] = lin_iters;
         lm.total_linear += lin_iters;
         double sc2[SC_COUNT] = {0};
         const LmDiag dg{1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
-        if (valid) {
+        if (valid && ph.active) {
+            phong_step(dg, sc2);
+            if (sc2[SC_NONFINITE] != 0.0) valid = false;
+            if (!(sc2[SC_MODEL] > 0.0)) valid = false;
+        } else if (valid) {
             DevView v = view(d_poses.p, d_points.p);
             prof_begin(CSLAM_K_BACKSUB);
             d_scal2.zero(stream);
@@ -1047,6 +1341,10 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
         if (row.v[5] > opt.min_relative_decrease) {
             std::swap(d_poses.p, d_poses_cand.p);
             std::swap(d_points.p, d_points_cand.p);
+            if (ph.active) {
+                std::swap(ph.normals.p, ph.normals_cand.p);
+                std::swap(ph.gx.p, ph.gx_cand.p);
+            }
             lm.x_cost = cand_cost;
             lm.x_norm = std::sqrt(sc2[SC_XNORM2]);
             lm.step_ok_prev = true;
@@ -1092,6 +1390,7 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
             CSLAM_CUDA(cudaMemcpyAsync(d_poses_best.p, d_poses.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
             if (n_lm)
                 CSLAM_CUDA(cudaMemcpyAsync(d_points_best.p, d_points.p, d_points.bytes(), cudaMemcpyDeviceToDevice, stream));
+            copy_phong_best();
         }
     }
     CSLAM_CUDA(cudaEventRecord(ev_b, stream));
@@ -1224,7 +1523,14 @@ void Engine::ensure_phong() {
     d_ph_poses.upload(h_poses, 12 * size_t(n_poses), stream);
     d_ph_points.upload(h_points, 3 * size_t(n_points), stream);
     d_ph_normals.upload(h_normals, 3 * size_t(n_vertices), stream);
-    d_ph_tex.upload(h_textures, n_vertices, stream);
+    if (h_tex_shared) {
+        std::vector<double> tex(n_vertices);
+        for (uint32_t j = 0; j < n_vertices; ++j) tex[j] = h_tex_shared[h_texture_id[j]];
+        d_ph_tex.upload(tex, stream);
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        d_ph_tex.upload(h_textures, n_vertices, stream);
+    }
     d_ph_phong.upload(h_phong, 3 * size_t(n_materials), stream);
     d_ph_light.upload(h_light, 3, stream);
 }

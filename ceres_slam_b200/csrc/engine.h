@@ -23,6 +23,8 @@ enum Scal {
     SC_GRADMAX = 6,      // |x - Plus(x,-g)|_inf (bit-pattern max)
     SC_XNORM2_CUR = 7,   // |x|^2 at the current point (initial pass)
     SC_NONFINITE = 8,    // non-finite step entries
+    SC_LS_GY = 9,        // g . y (scaled coordinates): the line search's directional derivative is -g.y
+    SC_LS_DMAX = 10,     // |delta|_inf (bit-pattern max)
     SC_COUNT = 32
 };
 // PCG scalar slots
@@ -117,6 +119,36 @@ struct PhongView {
     int directional;
 };
 
+// Joint lighting solve (kernels_phong_solve.cu): the state the vertex-elimination kernels read in
+// addition to DevView (positions are DevView::points, their scaling DevView::sc_l).
+struct PhongSolveView {
+    const double* normals;   // [n_lm][3], internal landmark order
+    const int* v_mat;        // [n_lm] material of the vertex
+    const int* v_tex;        // [n_lm] texture block of the vertex
+    const double* gx;        // [n_g] shared blocks: [materials 3 n_mat | textures n_tex | light 3]
+    const double* obs_I;     // [n_obs] observed intensity, internal observation order
+    const double* obs_n;     // [3][n_obs] observed normal (camera frame), SoA
+    const double* sc_n;      // [3 n_lm] column scaling of the normal tangent
+    const double* sc_g;      // [n_g]
+    const int* g_used;       // [n_g] 1 when some vertex refers to the column
+    double Wn[9];
+    double int_stiffness;
+    int directional, n_mat, n_tex, n_g;
+    double mat_lo[3], mat_hi[3], tex_lo, tex_hi;
+};
+// Where the vertex-elimination kernel accumulates the arrowhead reduced system.
+struct PhongSystem {
+    double *S, *Bdiag, *bp, *gp;  // camera part, as in the stereo path
+    double* Scg;                  // [n_g][6 n_free] border, one column after the other
+    double* Sgg;                  // [n_g][n_g]
+    double* bg;                   // [n_g] reduced right-hand side
+    double* gg;                   // [n_g] gradient
+    double* hg;                   // [n_g] diag(J_g^T J_g): column norms / LM diagonal
+    double* gv;                   // [6 n_lm] vertex gradient [position 3 | normal 3]
+    double *cn_l, *cn_n;          // [3 n_lm] each: squared column norms of position / normal (initial pass)
+    double* scal;
+};
+
 // LM diagonal parameters: D^2 = clamp(diag, min, max) * inv_radius (levenberg_marquardt_strategy)
 struct LmDiag {
     double inv_radius, min_diag, max_diag;
@@ -153,6 +185,12 @@ class Engine {
     uint32_t n_vertices = 0;
     double* h_phong = nullptr;
     uint32_t n_materials = 0;
+    double* h_tex_shared = nullptr;           // cslam_set_textures: texture blocks shared between vertices
+    const uint32_t* h_texture_id = nullptr;
+    uint32_t n_tex_shared = 0;
+    double mat_lo[3] = {-1e308, -1e308, -1e308}, mat_hi[3] = {1e308, 1e308, 1e308};
+    double tex_lo = -1e308, tex_hi = 1e308;
+    bool bounded = false;                     // cslam_set_bounds was called
     double* h_light = nullptr;
     int light_directional = 0;
     uint64_t n_ph = 0;
@@ -192,6 +230,7 @@ class Engine {
     cslam_profile prof{};
     bool uploaded = false, begun = false;
     bool phong_ready = false;             // block-index arrays of the lighting blocks are on the device
+    bool lighting_in_solve() const { return n_ph > 0; }
 
     // small-problem description used by the batched window kernel
     bool window_eligible() const;
@@ -270,6 +309,26 @@ class Engine {
     PhongView phong_view();
     void ensure_phong();
     double* h_pinned = nullptr;            // pinned scalar read-back
+    // joint lighting solve (dataset_ba_phong stage 3): vertex = position + normal, shared blocks gx
+    struct PhongSolve {
+        bool active = false;
+        int n_g = 0, n_mat = 0, n_tex = 0;
+        DBuf<double> normals, normals_cand, normals_best, normals_init;
+        DBuf<double> gx, gx_cand, gx_best, gx_init;
+        DBuf<int> v_mat, v_tex, g_used;
+        DBuf<double> obs_I, obs_n;
+        DBuf<double> sc_n, sc_g, cn_n, gv, yv, yg, diag_g, X, T, zero_g;
+        double *Scg = nullptr, *Sgg = nullptr, *bg = nullptr, *gg = nullptr, *hg = nullptr;  // inside d_red
+        std::vector<int> g_used_h;
+    } ph;
+    void check_phong_solve();
+    void setup_phong_solve();
+    void copy_phong_best();
+    void phong_step(const LmDiag& dg, double* sc2);
+    PhongSolveView phong_solve_view(const double* normals, const double* gx) const;
+    PhongSystem phong_system();
+    void solve_reduced(const double* rhs, double* y);
+    void phong_linear_solve(int* iters, bool* ok);
 
     // LM state (mirrors oracle/problem.hpp::solve)
     struct Lm {

@@ -1,0 +1,971 @@
+// K2p / K4p — the joint solve of dataset_ba_phong (tests/dataset_ba_phong.cpp:26-255, stage 3): stereo,
+// intensity and normal blocks of every observation; parameter blocks pose (6, SE3Perturbation),
+// vertex = position + normal (3 + 3, UnitVectorPerturbation on the normal, perturbations.hpp:87-113)
+// and the blocks every vertex of a material shares: material [ka, ks, alpha], texture kd, light.
+//
+// The vertex blocks are eliminated exactly like the landmark blocks of the stereo path, only 6x6:
+//   V = sum A_v^T A_v + D^2,  W_k = A_c^T A_v (6x6),  G = a_g (x) A_v[intensity row]  (7x6)
+//   S_cc[a,b] -= W_a V^-1 W_b^T      block-sparse reduced camera system (same pattern as stereo)
+//   S_cg[a,:] += A_c[int]^T a_g - W_a V^-1 G^T      dense border, n_g = 3 n_mat + n_tex + 3 columns
+//   S_gg      += a_g a_g^T - G V^-1 G^T
+// which leaves an ARROWHEAD system [S_cc S_cg; S_cg^T S_gg]: banded camera part + a dense border of
+// a few dozen columns.  The border is eliminated with n_g + 1 solves against S_cc (engine.cu).
+//
+// One warp per vertex, one lane per observation (track length <= 32); the per-observation blocks
+// are the closed forms of closed_form.h.  FP64, no fast-math.
+#include "kernels.cuh"
+
+namespace cslam {
+
+namespace {
+
+constexpr int PB_WARPS = 4;
+
+__device__ __forceinline__ int find_block(const int* __restrict__ rowptr, const int* __restrict__ col, int a, int b) {
+    int lo = rowptr[a], hi = rowptr[a + 1] - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (col[mid] < b)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;  // the pattern is built from co-visibility, so the block exists
+}
+
+// Cholesky-based inverse of a symmetric positive definite 6x6 (full storage in, full out).
+__device__ __forceinline__ bool spd6_inverse(const double* A, double* Ainv) {
+    double L[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) L[i] = A[i];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = L[6 * j + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k];
+        if (!(d > 0.0) || !(d < 1.7976931348623157e308)) ok = false;
+        d = sqrt(d);
+        L[6 * j + j] = d;
+        const double id = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double s = L[6 * i + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k];
+            L[6 * i + j] = s * id;
+        }
+    }
+    // Li = L^-1 (lower), Ainv = Li^T Li
+    double Li[36];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i < c) {
+                Li[6 * i + c] = 0.0;
+            } else if (i == c) {
+                Li[6 * i + c] = 1.0 / L[6 * i + i];
+            } else {
+                double s = 0.0;
+#pragma unroll
+                for (int k = c; k < i; ++k) s -= L[6 * i + k] * Li[6 * k + c];
+                Li[6 * i + c] = s / L[6 * i + i];
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = b; k < 6; ++k) s += Li[6 * k + a] * Li[6 * k + b];
+            Ainv[6 * a + b] = Ainv[6 * b + a] = s;
+        }
+    return ok;
+}
+
+// The three blocks of one observation in tangent coordinates, columns scaled.
+struct PhObs {
+    double rs[3], rI, rN[3];
+    double Jcs[18], JIc[6], JNc[18];  // pose columns: stereo 3x6, intensity 1x6, normal 3x6
+    double S[9], ip[3];               // position columns: stereo 3x3, intensity 1x3
+    double in[3], N[9];               // normal columns: intensity 1x3, normal 3x3
+    double ag[7];                     // material 3 | texture 1 | light 3 (intensity row)
+    int f;
+};
+
+struct VertexCtx {
+    double p[3], n[3], phong[3], kd, light[3];
+    double sl[3], sn[3], sg[7];
+    int gi[7];
+};
+
+__device__ __forceinline__ void load_vertex(const DevView& v, const PhongSolveView& q, int j, VertexCtx& c) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c.p[k] = v.points[3ll * j + k];
+        c.n[k] = q.normals[3ll * j + k];
+        c.sl[k] = v.sc_l[3ll * j + k];
+        c.sn[k] = q.sc_n[3ll * j + k];
+    }
+    const int m = q.v_mat[j], t = q.v_tex[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c.gi[k] = 3 * m + k;
+        c.gi[4 + k] = 3 * q.n_mat + q.n_tex + k;
+    }
+    c.gi[3] = 3 * q.n_mat + t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c.phong[k] = q.gx[c.gi[k]];
+        c.light[k] = q.gx[c.gi[4 + k]];
+    }
+    c.kd = q.gx[c.gi[3]];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c.sg[k] = q.sc_g[c.gi[k]];
+}
+
+__device__ __forceinline__ void eval_phong_obs(const DevView& v, const PhongSolveView& q, long long e,
+                                               const VertexCtx& c, PhObs& o) {
+    const uint32_t cam = v.obs_cam[e];
+    const double* pose = v.poses + 12ll * cam;
+    o.f = v.cam_free[cam];
+    stereo_block<true>(v.cam, pose, c.p, v.obs_u[e], v.obs_v[e], v.obs_d[e], v.obs_W, o.rs, o.Jcs, o.S);
+    double Jk[3], Jt[1], Jl[3];
+    intensity_block(pose, c.p, c.n, c.phong, c.kd, c.light, q.obs_I[e], q.int_stiffness, q.directional != 0, &o.rI,
+                    o.JIc, o.ip, o.in, Jk, Jt, Jl);
+    const double nobs[3] = {q.obs_n[e], q.obs_n[v.n_obs + e], q.obs_n[2 * v.n_obs + e]};
+    normal_block(pose, c.n, nobs, q.Wn, o.rN, o.JNc, o.N);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            o.S[3 * k + b] *= c.sl[b];
+            o.N[3 * k + b] *= c.sn[b];
+        }
+        o.ip[k] *= c.sl[k];
+        o.in[k] *= c.sn[k];
+        o.ag[k] = Jk[k] * c.sg[k];
+        o.ag[4 + k] = Jl[k] * c.sg[4 + k];
+    }
+    o.ag[3] = Jt[0] * c.sg[3];
+    if (o.f >= 0) {
+        const double* sp = v.sc_p + 6ll * o.f;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double s = sp[a];
+            o.Jcs[a] *= s;
+            o.Jcs[6 + a] *= s;
+            o.Jcs[12 + a] *= s;
+            o.JIc[a] *= s;
+            o.JNc[a] *= s;
+            o.JNc[6 + a] *= s;
+            o.JNc[12 + a] *= s;
+        }
+    }
+}
+
+// residuals only, at arbitrary state arrays (candidate evaluation)
+__device__ __forceinline__ double phong_obs_cost(const DevView& v, const PhongSolveView& q, long long e,
+                                                 const double* poses, const double* p, const double* n,
+                                                 const double* phong, double kd, const double* light) {
+    const uint32_t cam = v.obs_cam[e];
+    const double* pose = poses + 12ll * cam;
+    double rs[3], rI, rN[3];
+    stereo_block<false>(v.cam, pose, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], v.obs_W, rs, nullptr, nullptr);
+    intensity_block(pose, p, n, phong, kd, light, q.obs_I[e], q.int_stiffness, q.directional != 0, &rI, nullptr,
+                    nullptr, nullptr, nullptr, nullptr, nullptr);
+    const double nobs[3] = {q.obs_n[e], q.obs_n[v.n_obs + e], q.obs_n[2 * v.n_obs + e]};
+    normal_block(pose, n, nobs, q.Wn, rN, nullptr, nullptr);
+    return 0.5 * (rs[0] * rs[0] + rs[1] * rs[1] + rs[2] * rs[2] + rI * rI + rN[0] * rN[0] + rN[1] * rN[1] + rN[2] * rN[2]);
+}
+
+// A_v^T A_v (upper 21, row-major order of the upper triangle) and A_v^T w for a 7-vector w
+__device__ __forceinline__ void vertex_normal_eq(const PhObs& o, const double* w, double* V21, double* g6) {
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+            V21[idx++] = o.S[a] * o.S[b] + o.S[3 + a] * o.S[3 + b] + o.S[6 + a] * o.S[6 + b] + o.ip[a] * o.ip[b];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) V21[idx++] = o.ip[a] * o.in[b];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+            V21[idx++] = o.in[a] * o.in[b] + o.N[a] * o.N[b] + o.N[3 + a] * o.N[3 + b] + o.N[6 + a] * o.N[6 + b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        g6[a] = o.S[a] * w[0] + o.S[3 + a] * w[1] + o.S[6 + a] * w[2] + o.ip[a] * w[3];
+        g6[3 + a] = o.in[a] * w[3] + o.N[a] * w[4] + o.N[3 + a] * w[5] + o.N[6 + a] * w[6];
+    }
+}
+
+__device__ __forceinline__ void unpack_sym6(const double* V21, double* V) {
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) {
+            V[6 * a + b] = V[6 * b + a] = V21[idx++];
+        }
+}
+
+__device__ __forceinline__ void add_lm_diag(double* V, const LmDiag& dg) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) V[7 * a] += fmin(fmax(V[7 * a], dg.min_diag), dg.max_diag) * dg.inv_radius;
+}
+
+// =============================================================================================
+// K2p — fused residual/Jacobian + elimination of the vertex blocks.
+// kSchur == false: the initial pass (cost, squared column norms, gradient) with unit scaling.
+// =============================================================================================
+template <bool kSchur>
+__global__ void __launch_bounds__(PB_WARPS * 32)
+    phong_build_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, LmDiag dg, PhongSystem o) {
+    __shared__ double sW[PB_WARPS][36 * 32];  // W of every lane, [k][lane]
+    __shared__ double sG[PB_WARPS][72];       // the vertex's global contributions, staged for the atomics
+    __shared__ int sF[PB_WARPS][32];
+    __shared__ double s_red[32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* myW = sW[wib];
+    double* myG = sG[wib];
+    int* myF = sF[wib];
+    const int nf6 = 6 * v.n_free;
+    double cost = 0.0;
+    const int warps_total = gridDim.x * PB_WARPS;
+    for (int j = lm_lo + blockIdx.x * PB_WARPS + wib; j < lm_hi; j += warps_total) {
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const int L = int(v.lm_cnt[j]);
+        VertexCtx c;
+        load_vertex(v, q, j, c);
+        PhObs ob;
+        ob.f = -1;
+        const bool act = lane < L;
+        double V21[21], gv[6], r7[7];
+        if (act) {
+            eval_phong_obs(v, q, e0 + lane * es, c, ob);
+            r7[0] = ob.rs[0], r7[1] = ob.rs[1], r7[2] = ob.rs[2], r7[3] = ob.rI;
+            r7[4] = ob.rN[0], r7[5] = ob.rN[1], r7[6] = ob.rN[2];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) cost += 0.5 * r7[k] * r7[k];
+            vertex_normal_eq(ob, r7, V21, gv);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 21; ++k) V21[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) gv[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) ob.ag[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ob.ip[k] = ob.in[k] = 0.0;
+            ob.rI = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 21; ++k) V21[k] = warp_sum(V21[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gv[k] = warp_sum(gv[k]);
+        // globals: gradient and diagonal (always), G and H_gg (Schur pass)
+        double ggl[7], hd[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            ggl[k] = warp_sum(ob.ag[k] * ob.rI);
+            hd[k] = warp_sum(ob.ag[k] * ob.ag[k]);
+        }
+        if (!kSchur) {
+            if (lane == 0) {
+                int idx = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    if (a < 3)
+                        o.cn_l[3ll * j + a] = V21[idx];
+                    else
+                        o.cn_n[3ll * j + a - 3] = V21[idx];
+                    idx += 6 - a;
+                    o.gv[6ll * j + a] = gv[a];
+                }
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    red_add(&o.gg[c.gi[k]], ggl[k]);
+                    red_add(&o.hg[c.gi[k]], hd[k]);
+                }
+            }
+            if (act && ob.f >= 0) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double cn = ob.Jcs[a] * ob.Jcs[a] + ob.Jcs[6 + a] * ob.Jcs[6 + a] + ob.Jcs[12 + a] * ob.Jcs[12 + a] +
+                                      ob.JIc[a] * ob.JIc[a] + ob.JNc[a] * ob.JNc[a] + ob.JNc[6 + a] * ob.JNc[6 + a] +
+                                      ob.JNc[12 + a] * ob.JNc[12 + a];
+                    const double ga = ob.Jcs[a] * r7[0] + ob.Jcs[6 + a] * r7[1] + ob.Jcs[12 + a] * r7[2] + ob.JIc[a] * r7[3] +
+                                      ob.JNc[a] * r7[4] + ob.JNc[6 + a] * r7[5] + ob.JNc[12 + a] * r7[6];
+                    red_add(&o.Bdiag[36ll * ob.f + 7 * a], cn);
+                    red_add(&o.gp[6ll * ob.f + a], ga);
+                }
+            }
+            continue;
+        }
+        // ---- Schur pass ---------------------------------------------------------------------
+        double G[42];  // G[q][p] = sum_obs ag[q] * Av[intensity row][p]
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                G[6 * k + a] = warp_sum(ob.ag[k] * ob.ip[a]);
+                G[6 * k + 3 + a] = warp_sum(ob.ag[k] * ob.in[a]);
+            }
+        }
+        double V[36], Vi[36];
+        unpack_sym6(V21, V);
+        add_lm_diag(V, dg);
+        const bool pd = spd6_inverse(V, Vi);
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) o.gv[6ll * j + a] = gv[a];
+            if (!pd) red_add(&o.scal[SC_INVALID], 1.0);
+        }
+        if (!pd) continue;
+        // GV = G Vi (7x6)
+        double GV[42];
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) s += G[6 * k + b] * Vi[6 * b + a];
+                GV[6 * k + a] = s;
+            }
+        // H_gg off-diagonal needs the pair sums ag_k ag_k2: 21 more reductions
+        __syncwarp();
+        {
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+#pragma unroll
+                for (int k2 = k; k2 < 7; ++k2) {
+                    double h = (k2 == k) ? hd[k] : warp_sum(ob.ag[k] * ob.ag[k2]);
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) h -= GV[6 * k + a] * G[6 * k2 + a];
+                    if (lane == 0) myG[idx] = h;
+                    ++idx;
+                }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                double bb = ggl[k];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) bb -= GV[6 * k + a] * gv[a];
+                if (lane == 0) {
+                    myG[28 + k] = bb;
+                    myG[35 + k] = ggl[k];
+                    myG[42 + k] = hd[k];
+                }
+            }
+        }
+        __syncwarp();
+        // 28 upper entries of the 7x7 block (mirrored), then rhs / gradient / diagonal
+        {
+            // lane -> (k, k2) of the upper triangle
+            if (lane < 28) {
+                int k = 0, rem = lane;
+                while (rem >= 7 - k) {
+                    rem -= 7 - k;
+                    ++k;
+                }
+                const int k2 = k + rem;
+                const double h = myG[lane];
+                const int gk = c.gi[k], gk2 = c.gi[k2];
+                red_add(&o.Sgg[(long long)gk * q.n_g + gk2], h);
+                if (gk != gk2) red_add(&o.Sgg[(long long)gk2 * q.n_g + gk], h);
+            }
+            if (lane < 7) {
+                red_add(&o.bg[c.gi[lane]], myG[28 + lane]);
+                red_add(&o.gg[c.gi[lane]], myG[35 + lane]);
+                red_add(&o.hg[c.gi[lane]], myG[42 + lane]);
+            }
+        }
+        // ---- camera part --------------------------------------------------------------------
+        double Y[36];
+        myF[lane] = act ? ob.f : -1;
+        if (act && ob.f >= 0) {
+            double W[36];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    W[6 * a + b] = ob.Jcs[a] * ob.S[b] + ob.Jcs[6 + a] * ob.S[3 + b] + ob.Jcs[12 + a] * ob.S[6 + b] +
+                                   ob.JIc[a] * ob.ip[b];
+                    W[6 * a + 3 + b] = ob.JIc[a] * ob.in[b] + ob.JNc[a] * ob.N[b] + ob.JNc[6 + a] * ob.N[3 + b] +
+                                       ob.JNc[12 + a] * ob.N[6 + b];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 36; ++k) myW[k * 32 + lane] = W[k];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s += W[6 * a + k] * Vi[6 * k + b];
+                    Y[6 * a + b] = s;
+                }
+            double* Bd = o.Bdiag + 36ll * ob.f;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                for (int b = a; b < 6; ++b)
+                    red_add(&Bd[6 * a + b], ob.Jcs[a] * ob.Jcs[b] + ob.Jcs[6 + a] * ob.Jcs[6 + b] + ob.Jcs[12 + a] * ob.Jcs[12 + b] +
+                                                ob.JIc[a] * ob.JIc[b] + ob.JNc[a] * ob.JNc[b] + ob.JNc[6 + a] * ob.JNc[6 + b] +
+                                                ob.JNc[12 + a] * ob.JNc[12 + b]);
+                const double ga = ob.Jcs[a] * r7[0] + ob.Jcs[6 + a] * r7[1] + ob.Jcs[12 + a] * r7[2] + ob.JIc[a] * r7[3] +
+                                  ob.JNc[a] * r7[4] + ob.JNc[6 + a] * r7[5] + ob.JNc[12 + a] * r7[6];
+                double yg = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) yg += Y[6 * a + k] * gv[k];
+                red_add(&o.gp[6ll * ob.f + a], ga);
+                red_add(&o.bp[6ll * ob.f + a], ga - yg);
+                // border: E - Y G^T
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    double s = ob.JIc[a] * ob.ag[k];
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) s -= Y[6 * a + b] * G[6 * k + b];
+                    red_add(&o.Scg[(long long)c.gi[k] * nf6 + 6 * ob.f + a], s);
+                }
+            }
+        }
+        __syncwarp();
+        // camera pairs: lane x takes the pairs (x, (x + s) mod L), s = 0 .. L/2 — every unordered
+        // pair once, all lanes busy
+        if (act && ob.f >= 0) {
+            const int fx = ob.f;
+            for (int s = 0; s <= L / 2; ++s) {
+                if (2 * s == L && lane >= s) break;  // even L: the antipodal pairs appear twice
+                int y = lane + s;
+                if (y >= L) y -= L;
+                const int fy = myF[y];
+                if (fy < 0) continue;
+                double Wy[36];
+#pragma unroll
+                for (int k = 0; k < 36; ++k) Wy[k] = myW[k * 32 + y];
+                const bool swap = fx > fy;
+                const int a = swap ? fy : fx, b = swap ? fx : fy;
+                double* B = o.S + 36ll * find_block(v.s_rowptr, v.s_col, a, b);
+                if (fx == fy) {
+                    const bool dup = s != 0;  // the same camera observing the vertex twice
+#pragma unroll
+                    for (int pp = 0; pp < 6; ++pp)
+#pragma unroll
+                        for (int qq = pp; qq < 6; ++qq) {
+                            double val = 0.0;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) val += Y[6 * pp + k] * Wy[6 * qq + k];
+                            if (dup)
+#pragma unroll
+                                for (int k = 0; k < 6; ++k) val += Y[6 * qq + k] * Wy[6 * pp + k];
+                            red_add(&B[6 * pp + qq], -val);
+                        }
+                } else {
+#pragma unroll
+                    for (int pp = 0; pp < 6; ++pp)
+#pragma unroll
+                        for (int qq = 0; qq < 6; ++qq) {
+                            double val = 0.0;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) val += Y[6 * pp + k] * Wy[6 * qq + k];
+                            red_add(swap ? &B[6 * qq + pp] : &B[6 * pp + qq], -val);
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    block_atomic_sum(cost, &o.scal[SC_COST], s_red);
+}
+
+// =============================================================================================
+// K4p — back-substitution of the vertex blocks and the model cost change
+// =============================================================================================
+__global__ void __launch_bounds__(PB_WARPS * 32)
+    phong_backsub_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, LmDiag dg, const double* __restrict__ yp,
+                         const double* __restrict__ yg, const double* __restrict__ gv, double* __restrict__ yv_out,
+                         double* __restrict__ scal2) {
+    __shared__ double s_red[32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double model = 0.0, bad = 0.0, gy = 0.0, dmax = 0.0;
+    const int warps_total = gridDim.x * PB_WARPS;
+    for (int j = lm_lo + blockIdx.x * PB_WARPS + wib; j < lm_hi; j += warps_total) {
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const int L = int(v.lm_cnt[j]);
+        VertexCtx c;
+        load_vertex(v, q, j, c);
+        PhObs ob;
+        ob.f = -1;
+        const bool act = lane < L;
+        double V21[21], t6[6], r7[7], Jy[7];
+        if (act) {
+            eval_phong_obs(v, q, e0 + lane * es, c, ob);
+            r7[0] = ob.rs[0], r7[1] = ob.rs[1], r7[2] = ob.rs[2], r7[3] = ob.rI;
+            r7[4] = ob.rN[0], r7[5] = ob.rN[1], r7[6] = ob.rN[2];
+            // J y restricted to the camera and global columns
+#pragma unroll
+            for (int k = 0; k < 7; ++k) Jy[k] = 0.0;
+            if (ob.f >= 0) {
+                const double* y = yp + 6ll * ob.f;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double ya = y[a];
+                    Jy[0] += ob.Jcs[a] * ya;
+                    Jy[1] += ob.Jcs[6 + a] * ya;
+                    Jy[2] += ob.Jcs[12 + a] * ya;
+                    Jy[3] += ob.JIc[a] * ya;
+                    Jy[4] += ob.JNc[a] * ya;
+                    Jy[5] += ob.JNc[6 + a] * ya;
+                    Jy[6] += ob.JNc[12 + a] * ya;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) Jy[3] += ob.ag[k] * yg[c.gi[k]];
+            double w[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) w[k] = r7[k] - Jy[k];
+            vertex_normal_eq(ob, w, V21, t6);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 21; ++k) V21[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) t6[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 21; ++k) V21[k] = warp_sum(V21[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t6[k] = warp_sum(t6[k]);
+        double V[36], Vi[36], yv[6];
+        unpack_sym6(V21, V);
+        add_lm_diag(V, dg);
+        const bool pd = spd6_inverse(V, Vi);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) s += Vi[6 * a + b] * t6[b];
+            yv[a] = pd ? s : 0.0;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                yv_out[6ll * j + a] = yv[a];
+                if (isnan(yv[a]) || isinf(yv[a])) bad = 1.0;
+                // line search of a bounded problem: g . y and |delta|_inf over the vertex blocks
+                gy += gv[6ll * j + a] * yv[a];
+                dmax = fmax(dmax, fabs(yv[a] * (a < 3 ? c.sl[a] : c.sn[a - 3])));
+            }
+        }
+        if (act) {
+            // m = -(J y) over all columns; model -= m . (r + m / 2)
+            double m[7];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                m[k] = -(Jy[k] + ob.S[3 * k] * yv[0] + ob.S[3 * k + 1] * yv[1] + ob.S[3 * k + 2] * yv[2]);
+                m[4 + k] = -(Jy[4 + k] + ob.N[3 * k] * yv[3] + ob.N[3 * k + 1] * yv[4] + ob.N[3 * k + 2] * yv[5]);
+            }
+            m[3] = -(Jy[3] + ob.ip[0] * yv[0] + ob.ip[1] * yv[1] + ob.ip[2] * yv[2] + ob.in[0] * yv[3] + ob.in[1] * yv[4] +
+                     ob.in[2] * yv[5]);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) model -= m[k] * (r7[k] + 0.5 * m[k]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if (lane == 0 && dmax > 0) atomic_max_nonneg(&scal2[SC_LS_DMAX], dmax);
+    block_atomic_sum(model, &scal2[SC_MODEL], s_red);
+    block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
+    block_atomic_sum(gy, &scal2[SC_LS_GY], s_red);
+}
+
+// Candidate vertices x (+) alpha * delta and the cost there (poses_cand / gx_cand already formed).
+__global__ void __launch_bounds__(PB_WARPS * 32)
+    phong_candidate_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, double alpha, const double* __restrict__ yv,
+                           const double* __restrict__ poses_cand, const double* __restrict__ gx_cand,
+                           double* __restrict__ points_cand, double* __restrict__ normals_cand, double* __restrict__ scal2) {
+    __shared__ double s_red[32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double ccost = 0.0, sn = 0.0, xn = 0.0;
+    const int warps_total = gridDim.x * PB_WARPS;
+    for (int j = lm_lo + blockIdx.x * PB_WARPS + wib; j < lm_hi; j += warps_total) {
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const int L = int(v.lm_cnt[j]);
+        VertexCtx c;
+        load_vertex(v, q, j, c);
+        double pn[3], dn[3], nn[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            pn[k] = c.p[k] + alpha * (-yv[6ll * j + k] * c.sl[k]);
+            dn[k] = alpha * (-yv[6ll * j + 3 + k] * c.sn[k]);
+        }
+        unit_plus(c.n, dn, nn);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                points_cand[3ll * j + k] = pn[k];
+                normals_cand[3ll * j + k] = nn[k];
+                sn += (c.p[k] - pn[k]) * (c.p[k] - pn[k]) + (c.n[k] - nn[k]) * (c.n[k] - nn[k]);
+                xn += pn[k] * pn[k] + nn[k] * nn[k];
+            }
+        }
+        if (lane < L) {
+            double phong[3], light[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                phong[k] = gx_cand[c.gi[k]];
+                light[k] = gx_cand[c.gi[4 + k]];
+            }
+            ccost += phong_obs_cost(v, q, e0 + lane * es, poses_cand, pn, nn, phong, gx_cand[c.gi[3]], light);
+        }
+    }
+    block_atomic_sum(ccost, &scal2[SC_CAND_COST], s_red);
+    block_atomic_sum(sn, &scal2[SC_STEP_NORM2], s_red);
+    block_atomic_sum(xn, &scal2[SC_XNORM2], s_red);
+}
+
+// Poses x (+) alpha * delta (launch_pose_plus with a step length)
+__global__ void phong_pose_plus_kernel(DevView v, double alpha, const double* __restrict__ yp, double* __restrict__ poses_cand,
+                                       double* __restrict__ scal2, int count) {
+    __shared__ double s_red[32];
+    const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    double sn = 0, xn = 0, bad = 0;
+    if (cidx < v.n_cams) {
+        const int ff = v.cam_free[cidx];
+        const double* x = v.poses + 12ll * cidx;
+        double* y = poses_cand + 12ll * cidx;
+        if (ff >= 0) {
+            double eps[6], out[12];
+            for (int k = 0; k < 6; ++k) {
+                eps[k] = alpha * (-yp[6ll * ff + k] * v.sc_p[6ll * ff + k]);
+                if (isnan(eps[k]) || isinf(eps[k])) bad = 1;
+            }
+            se3_plus(x, eps, out);
+            for (int k = 0; k < 12; ++k) {
+                y[k] = out[k];
+                sn += (x[k] - out[k]) * (x[k] - out[k]);
+                xn += out[k] * out[k];
+            }
+        } else {
+            for (int k = 0; k < 12; ++k) y[k] = x[k];
+        }
+    }
+    if (!count) sn = xn = 0;
+    block_atomic_sum(sn, &scal2[SC_STEP_NORM2], s_red);
+    block_atomic_sum(xn, &scal2[SC_XNORM2], s_red);
+    block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
+}
+
+// ParameterBlock::Plus on the shared blocks: x + alpha * delta projected onto the box (materials,
+// textures), UnitVectorPerturbation for a directional light.  One block.
+__device__ __forceinline__ double project_global(const PhongSolveView& q, int k, double x) {
+    if (k < 3 * q.n_mat) return fmin(fmax(x, q.mat_lo[k % 3]), q.mat_hi[k % 3]);
+    if (k < 3 * q.n_mat + q.n_tex) return fmin(fmax(x, q.tex_lo), q.tex_hi);
+    return x;
+}
+__global__ void phong_global_plus_kernel(PhongSolveView q, double alpha, double sign, const double* __restrict__ step,
+                                         int step_is_gradient, double* __restrict__ gx_out, double* __restrict__ scal,
+                                         int slot_step, int slot_xnorm, int slot_bad, int slot_max, int count) {
+    // step_is_gradient: delta = -g / sc (gradient-norm point); else delta = alpha * (-y * sc)
+    __shared__ double s_red[32];
+    const int k = threadIdx.x;
+    const int l0 = 3 * q.n_mat + q.n_tex;
+    double sn = 0, xn = 0, bad = 0, mx = 0;
+    if (k < q.n_g) {
+        const double x = q.gx[k];
+        double out = x;
+        if (q.g_used[k]) {
+            const double d = step_is_gradient ? sign * step[k] / q.sc_g[k] : alpha * (sign * step[k] * q.sc_g[k]);
+            if (isnan(d) || isinf(d)) bad = 1;
+            if (k >= l0 && q.directional) {
+                double dl[3], o3[3];
+                for (int a = 0; a < 3; ++a)
+                    dl[a] = step_is_gradient ? sign * step[l0 + a] / q.sc_g[l0 + a] : alpha * (sign * step[l0 + a] * q.sc_g[l0 + a]);
+                unit_plus(q.gx + l0, dl, o3);
+                out = o3[k - l0];
+            } else {
+                out = project_global(q, k, x + d);
+            }
+            sn = (x - out) * (x - out);
+            xn = step_is_gradient ? x * x : out * out;
+            mx = fabs(x - out);
+        }
+        if (gx_out) gx_out[k] = out;
+    }
+    if (!count) sn = xn = mx = 0;
+    if (slot_max >= 0) {
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0) atomic_max_nonneg(&scal[slot_max], mx);
+    }
+    if (slot_step >= 0) block_atomic_sum(sn, &scal[slot_step], s_red);
+    if (slot_xnorm >= 0) block_atomic_sum(xn, &scal[slot_xnorm], s_red);
+    if (slot_bad >= 0) block_atomic_sum(bad, &scal[slot_bad], s_red);
+}
+
+// |x - Plus(x, -g)|_inf and |x|^2 over the vertex blocks (thread per vertex)
+__global__ void phong_gradnorm_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, const double* __restrict__ gv,
+                                      double* __restrict__ scal) {
+    __shared__ double s_red[32];
+    const int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0, xn = 0;
+    if (j < lm_hi) {
+        double n[3], dn[3], nn[3];
+        for (int k = 0; k < 3; ++k) {
+            const double x = v.points[3ll * j + k];
+            const double g = gv[6ll * j + k] / v.sc_l[3ll * j + k];
+            m = fmax(m, fabs(x - (x - g)));
+            n[k] = q.normals[3ll * j + k];
+            dn[k] = -gv[6ll * j + 3 + k] / q.sc_n[3ll * j + k];
+            xn += x * x + n[k] * n[k];
+        }
+        unit_plus(n, dn, nn);
+        for (int k = 0; k < 3; ++k) m = fmax(m, fabs(n[k] - nn[k]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomic_max_nonneg(&scal[SC_GRADMAX], m);
+    block_atomic_sum(xn, &scal[SC_XNORM2_CUR], s_red);
+}
+
+// IterationZero of a bounded problem: x <- Plus(x, 0) (normals re-normalised; globals projected by
+// phong_global_plus_kernel)
+__global__ void phong_renormalize_kernel(int n_lm, double* __restrict__ normals) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_lm) return;
+    const double z[3] = {0, 0, 0};
+    double n[3] = {normals[3ll * j], normals[3ll * j + 1], normals[3ll * j + 2]}, o[3];
+    unit_plus(n, z, o);
+    for (int k = 0; k < 3; ++k) normals[3ll * j + k] = o[k];
+}
+
+// sum_i a[i] * b[i] into dst (grid-stride)
+__global__ void dot_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, double* dst) {
+    __shared__ double s_red[32];
+    double s = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s += a[i] * b[i];
+    block_atomic_sum(s, dst, s_red);
+}
+// max_i |y[i] * sc[i]| into dst (bit-pattern max)
+__global__ void absmax_scaled_kernel(const double* __restrict__ y, const double* __restrict__ sc, long long n, double* dst) {
+    double m = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(y[i] * sc[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomic_max_nonneg(dst, m);
+}
+
+// ---- the dense border --------------------------------------------------------------------------
+// LM diagonal on S_gg; unused columns become identity rows.  One block.
+__global__ void phong_gfinalize_kernel(PhongSolveView q, LmDiag dg, double* __restrict__ Sgg, double* __restrict__ bg,
+                                       const double* __restrict__ hg, double* __restrict__ diag_g) {
+    const int k = threadIdx.x;
+    if (k >= q.n_g) return;
+    if (!q.g_used[k]) {
+        Sgg[(long long)k * q.n_g + k] = 1.0;
+        bg[k] = 0.0;
+        return;
+    }
+    const double dd = fmin(fmax(hg[k], dg.min_diag), dg.max_diag);
+    diag_g[k] = dd;
+    Sgg[(long long)k * q.n_g + k] += dd * dg.inv_radius;
+}
+
+// T[q][q2] = S_gg[q][q2] - S_cg[:,q] . X[:,q2]   (q2 == n_g: the right-hand side column).
+// X holds n_g + 1 solves against S_cc: columns 0..n_g-1 for the border, column n_g for b_c.
+__global__ void __launch_bounds__(256)
+    phong_border_reduce_kernel(int n_g, int nf6, const double* __restrict__ Scg, const double* __restrict__ X,
+                               const double* __restrict__ Sgg, const double* __restrict__ bg, double* __restrict__ T) {
+    __shared__ double s_red[32];
+    const int qa = blockIdx.x / (n_g + 1), qb = blockIdx.x % (n_g + 1);
+    const double* a = Scg + (long long)qa * nf6;
+    const double* b = X + (long long)qb * nf6;
+    double s = 0;
+    for (int i = threadIdx.x; i < nf6; i += blockDim.x) s += a[i] * b[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_red[w];  // fixed order: deterministic
+        const double base = qb < n_g ? Sgg[(long long)qa * n_g + qb] : bg[qa];
+        T[(long long)qa * (n_g + 1) + qb] = base - t;
+    }
+}
+
+// Dense Cholesky solve of the n_g x n_g border system (one block); yg out, fail flag.
+__global__ void __launch_bounds__(128) phong_border_solve_kernel(int n_g, double* __restrict__ T, double* __restrict__ yg,
+                                                                 double* __restrict__ ps) {
+    extern __shared__ double sT[];  // [n_g][n_g + 1]
+    const int ld = n_g + 1;
+    for (int i = threadIdx.x; i < n_g * ld; i += blockDim.x) sT[i] = T[i];
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    // symmetrise from the accumulated (numerically almost symmetric) matrix: use the lower triangle
+    for (int j = 0; j < n_g; ++j) {
+        if (threadIdx.x == 0) {
+            const double d = sT[j * ld + j];
+            if (!(d > 0.0) || !(d < 1.7976931348623157e308)) ok = 0;
+            sT[j * ld + j] = sqrt(d);
+        }
+        __syncthreads();
+        const double djj = sT[j * ld + j];
+        for (int i = j + 1 + threadIdx.x; i < n_g; i += blockDim.x) sT[i * ld + j] /= djj;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < (n_g - j - 1) * (n_g - j - 1); idx += blockDim.x) {
+            const int i = j + 1 + idx / (n_g - j - 1), k = j + 1 + idx % (n_g - j - 1);
+            if (k <= i) sT[i * ld + k] -= sT[i * ld + j] * sT[k * ld + j];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // forward / backward substitution on the rhs column (index n_g)
+        for (int i = 0; i < n_g; ++i) {
+            double s = sT[i * ld + n_g];
+            for (int k = 0; k < i; ++k) s -= sT[i * ld + k] * sT[k * ld + n_g];
+            sT[i * ld + n_g] = s / sT[i * ld + i];
+        }
+        for (int i = n_g - 1; i >= 0; --i) {
+            double s = sT[i * ld + n_g];
+            for (int k = i + 1; k < n_g; ++k) s -= sT[k * ld + i] * sT[k * ld + n_g];
+            sT[i * ld + n_g] = s / sT[i * ld + i];
+        }
+        for (int i = 0; i < n_g; ++i) yg[i] = sT[i * ld + n_g];
+        if (!ok) ps[PS_FAIL] = 2.0;
+    }
+}
+
+// y_c = x_b - X_g y_g
+__global__ void phong_border_backsub_kernel(int n_g, int nf6, const double* __restrict__ X, const double* __restrict__ yg,
+                                            double* __restrict__ yc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf6) return;
+    double s = X[(long long)n_g * nf6 + i];
+    for (int k = 0; k < n_g; ++k) s -= X[(long long)k * nf6 + i] * yg[k];
+    yc[i] = s;
+}
+
+inline void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+inline int vertex_grid(int n) {
+    const int blocks = (n + PB_WARPS - 1) / PB_WARPS;
+    return blocks < 1 ? 1 : (blocks < 148 * 8 ? blocks : 148 * 8);
+}
+
+}  // namespace
+
+void launch_phong_build(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                        const PhongSystem& o, bool schur) {
+    if (lm_hi <= lm_lo) return;
+    const int grid = vertex_grid(lm_hi - lm_lo);
+    if (schur)
+        phong_build_kernel<true><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+    else
+        phong_build_kernel<false><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_gfinalize(cudaStream_t s, const PhongSolveView& q, LmDiag dg, double* Sgg, double* bg, const double* hg,
+                            double* diag_g) {
+    phong_gfinalize_kernel<<<1, ((q.n_g + 31) / 32) * 32, 0, s>>>(q, dg, Sgg, bg, hg, diag_g);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_border_solve(cudaStream_t s, int n_g, int nf6, const double* Scg, const double* X, const double* Sgg,
+                               const double* bg, double* T, double* yg, double* yc, double* ps) {
+    if (nf6 > 0) {
+        phong_border_reduce_kernel<<<n_g * (n_g + 1), 256, 0, s>>>(n_g, nf6, Scg, X, Sgg, bg, T);
+        count_launch();
+    } else {
+        // no free camera: T = [S_gg | b_g]
+        CSLAM_CUDA(cudaMemcpy2DAsync(T, (n_g + 1) * sizeof(double), Sgg, n_g * sizeof(double), n_g * sizeof(double), n_g,
+                                     cudaMemcpyDeviceToDevice, s));
+        CSLAM_CUDA(cudaMemcpy2DAsync(T + n_g, (n_g + 1) * sizeof(double), bg, sizeof(double), sizeof(double), n_g,
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    const size_t smem = size_t(n_g) * (n_g + 1) * sizeof(double);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        CSLAM_CUDA(cudaFuncSetAttribute(phong_border_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_set = smem;
+    }
+    phong_border_solve_kernel<<<1, 128, smem, s>>>(n_g, T, yg, ps);
+    count_launch();
+    if (nf6 > 0) {
+        phong_border_backsub_kernel<<<(nf6 + 255) / 256, 256, 0, s>>>(n_g, nf6, X, yg, yc);
+        count_launch();
+    }
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                          const double* yp, const double* yg, const double* gv, double* yv, double* scal2) {
+    if (lm_hi <= lm_lo) return;
+    phong_backsub_kernel<<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_candidate(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, double alpha,
+                            const double* yp, const double* yg, const double* yv, double* poses_cand, double* gx_cand,
+                            double* points_cand, double* normals_cand, double* scal2, int count_shared) {
+    phong_pose_plus_kernel<<<(v.n_cams + 127) / 128, 128, 0, s>>>(v, alpha, yp, poses_cand, scal2, count_shared);
+    count_launch();
+    phong_global_plus_kernel<<<1, ((q.n_g + 31) / 32) * 32, 0, s>>>(q, alpha, -1.0, yg, 0, gx_cand, scal2, SC_STEP_NORM2,
+                                                                     SC_XNORM2, SC_NONFINITE, -1, count_shared);
+    count_launch();
+    if (lm_hi > lm_lo) {
+        phong_candidate_kernel<<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, alpha, yv, poses_cand,
+                                                                                   gx_cand, points_cand, normals_cand, scal2);
+        count_launch();
+    }
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_gradnorm(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, const double* gv,
+                           const double* gg, double* scal, int count_shared) {
+    if (lm_hi > lm_lo) {
+        phong_gradnorm_kernel<<<(lm_hi - lm_lo + 127) / 128, 128, 0, s>>>(v, q, lm_lo, lm_hi, gv, scal);
+        count_launch();
+    }
+    phong_global_plus_kernel<<<1, ((q.n_g + 31) / 32) * 32, 0, s>>>(q, 1.0, -1.0, gg, 1, nullptr, scal, -1, SC_XNORM2_CUR, -1,
+                                                                     SC_GRADMAX, count_shared);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_project_initial(cudaStream_t s, const PhongSolveView& q, int n_lm, double* normals, double* gx, double* zero_g) {
+    if (n_lm > 0) {
+        phong_renormalize_kernel<<<(n_lm + 127) / 128, 128, 0, s>>>(n_lm, normals);
+        count_launch();
+    }
+    // Plus(x, 0) on the shared blocks: projection onto the box / re-normalised light direction
+    phong_global_plus_kernel<<<1, ((q.n_g + 31) / 32) * 32, 0, s>>>(q, 1.0, 1.0, zero_g, 0, gx, nullptr, -1, -1, -1, -1, 0);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_dot(cudaStream_t s, const double* a, const double* b, long long n, double* dst) {
+    if (n <= 0) return;
+    const int grid = int(std::min<long long>((n + 255) / 256, 148 * 4));
+    dot_kernel<<<grid, 256, 0, s>>>(a, b, n, dst);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+void launch_absmax_scaled(cudaStream_t s, const double* y, const double* sc, long long n, double* dst) {
+    if (n <= 0) return;
+    const int grid = int(std::min<long long>((n + 255) / 256, 148 * 4));
+    absmax_scaled_kernel<<<grid, 256, 0, s>>>(y, sc, n, dst);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+}  // namespace cslam

@@ -119,6 +119,22 @@ class BAProblem:
                                           capi.u32ptr(material_id)))
         return normals, textures
 
+    def set_textures(self, kd, vertex_texture_id):
+        """Texture blocks shared between vertices (one per material in the reference)."""
+        kd = np.ascontiguousarray(kd, dtype=np.float64).reshape(-1)
+        tid = np.ascontiguousarray(vertex_texture_id, dtype=np.uint32)
+        self._keep["textures"] = (kd, tid)
+        self._check(self.lib.set_textures(self._h, kd.size, capi.dptr(kd), capi.u32ptr(tid)))
+        return kd
+
+    def set_bounds(self, block_kind, lower, upper):
+        """SetParameterLowerBound / UpperBound on every material (3) or texture (1) block."""
+        kind = {"material": 0, "texture": 1}[block_kind]
+        lo = np.ascontiguousarray(lower, dtype=np.float64)
+        hi = np.ascontiguousarray(upper, dtype=np.float64)
+        assert lo.size == hi.size == (3 if kind == 0 else 1)
+        self._check(self.lib.set_bounds(self._h, kind, capi.dptr(lo), capi.dptr(hi)))
+
     def set_materials(self, phong):
         phong = np.ascontiguousarray(phong, dtype=np.float64).reshape(-1, 3)
         self._keep["materials"] = phong

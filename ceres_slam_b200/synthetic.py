@@ -141,12 +141,15 @@ def add_sun(track, seed=43, sigma_deg=2.0):
     return track
 
 
-def add_phong(track, seed=44, n_materials=8, directional=False, int_var=1e-4, normal_var=1e-4):
+def add_phong(track, seed=44, n_materials=8, directional=False, int_var=1e-4, normal_var=1e-4,
+              shared_textures=False):
     """Lighting data in the shape of dataset_ba_phong's input (dataset_problem_phong.cpp:29-117):
     per vertex a unit normal facing the cameras that see it, a diffuse texture kd and a material
     id; per material [ka, ks, alpha]; one point light at (-2, -2, 2) (light_test.cpp:49) or a
     directional light; per observation the rendered Phong intensity (+ noise, variance int_var)
-    and the normal in the camera frame (+ noise, variance normal_var)."""
+    and the normal in the camera frame (+ noise, variance normal_var).  `shared_textures`: one kd per
+    material, shared by its vertices, as the reference's reader builds them
+    (dataset_problem_phong.cpp:262-279, :342-343)."""
     rng = np.random.default_rng(seed)
     n_pts = track["n_points"]
     k, j = track["obs_cam"].astype(np.int64), track["obs_pt"].astype(np.int64)
@@ -162,6 +165,9 @@ def add_phong(track, seed=44, n_materials=8, directional=False, int_var=1e-4, no
     phong = np.stack([rng.uniform(0.0, 0.2, n_materials), rng.uniform(0.1, 0.5, n_materials),
                       rng.uniform(5.0, 30.0, n_materials)], axis=1)
     tex = rng.uniform(0.3, 0.9, n_pts)
+    tex_shared = rng.uniform(0.3, 0.9, n_materials)
+    if shared_textures:
+        tex = tex_shared[mat_id]
     if directional:
         light = np.array([0.2, -0.4, 0.9])
         light /= np.linalg.norm(light)
@@ -192,17 +198,29 @@ def add_phong(track, seed=44, n_materials=8, directional=False, int_var=1e-4, no
                  light_gt=light, light=light + (0 if directional else rng.normal(0, 0.05, 3)),
                  directional=bool(directional), intensity=inten, normal_obs=np.ascontiguousarray(nobs),
                  int_stiffness=1.0 / np.sqrt(int_var), W_normal=(np.eye(3) / np.sqrt(normal_var)).reshape(9))
+    if shared_textures:
+        track.update(tex_shared_gt=tex_shared, tex_shared=np.clip(tex_shared + rng.normal(0, 0.05, n_materials), 0, 1),
+                     texture_id=mat_id.copy())
+        track["textures"] = track["tex_shared"][mat_id]
     return track
 
 
-def build_phong_problem(track, backend="b200", **options):
-    """dataset_ba_phong's problem (stereo + intensity + normal blocks, first pose constant)."""
+def build_phong_problem(track, backend="b200", bounds=False, **options):
+    """dataset_ba_phong's problem (stereo + intensity + normal blocks, first pose constant).  With a
+    track made with `shared_textures` the texture blocks are shared per material
+    (cslam_set_textures) — the shape the joint solve takes; `bounds` adds the box constraints of
+    dataset_ba_phong.cpp:143-181."""
     p, poses, points = build_problem(track, backend=backend, **options)
     normals, textures = p.set_vertices(track["normals"].copy(), track["textures"].copy(), track["material_id"])
+    if "tex_shared" in track:
+        textures = p.set_textures(track["tex_shared"].copy(), track["texture_id"])
     phong = p.set_materials(track["phong"].copy())
     light = p.set_light(track["light"].copy(), track["directional"])
     p.add_phong(track["obs_cam"], track["obs_pt"], track["intensity"], track["int_stiffness"],
                 track["normal_obs"], track["W_normal"])
+    if bounds:
+        p.set_bounds("material", [0.0, 0.0, 1.0], [1.0, 1.0, np.inf])
+        p.set_bounds("texture", [0.0], [1.0])
     return p, dict(poses=poses, points=points, normals=normals, textures=textures, phong=phong, light=light)
 
 

@@ -160,7 +160,18 @@ cslam_status cslam_evaluate(cslam_problem* p, int apply_loss, double* cost, doub
  * The normal (and a directional light) carry UnitVectorPerturbation (perturbations.hpp:87-113). */
 cslam_status cslam_set_vertices(cslam_problem* p, uint32_t n, double* normals3, double* textures,
                                 const uint32_t* material_id);
+/* Texture blocks shared between vertices: vertex j uses kd[vertex_texture_id[j]].  The reference
+ * creates one Texture per material and hands the same shared_ptr to every vertex of that material
+ * (dataset_problem_phong.cpp:262-279, :342-343), so Ceres sees ONE parameter block per material;
+ * this call states that sharing (it replaces the per-vertex values of cslam_set_vertices).  In-out. */
+cslam_status cslam_set_textures(cslam_problem* p, uint32_t n_textures, double* kd, const uint32_t* vertex_texture_id);
 cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double* phong3);
+/* SetParameterLowerBound / SetParameterUpperBound on every block of one kind
+ * (dataset_ba_phong.cpp:143-181): block_kind 0 = material [ka, ks, alpha] (3 lower, 3 upper),
+ * 1 = texture kd (1, 1).  +-HUGE_VAL leaves a side open.  A bounded problem is solved the way Ceres
+ * does it: every Plus is projected onto the box and the trust-region step goes through an Armijo
+ * line search (see oracle/phong_problem.hpp for the stated deviation in the interpolation). */
+cslam_status cslam_set_bounds(cslam_problem* p, int block_kind, const double* lower, const double* upper);
 cslam_status cslam_set_light(cslam_problem* p, double* light3, int directional);
 /* n observations, each adding one IntensityError{Point,Directional}LightAutomatic block
  * (dataset_ba_phong.cpp:103-123: pose, position, normal, phong params, texture, light) and one
@@ -178,7 +189,14 @@ cslam_status cslam_evaluate_phong(cslam_problem* p, double* cost, double* r_int,
 cslam_status cslam_time_phong(cslam_problem* p, int reps, double* ms_per_launch);
 
 /* ceres::Solve (dataset_vo.cpp:81): uploads the problem, runs the LM loop on the device, writes
- * the best parameters back into the caller's pose / point arrays. */
+ * the best parameters back into the caller's pose / point arrays.
+ * With lighting blocks (cslam_add_phong) this is the joint solve of dataset_ba_phong.cpp:249-252:
+ * poses, vertex positions and normals, materials, textures and the light are optimised together and
+ * all of those arrays are updated in place.  The lighting blocks must pair one-to-one with the stereo
+ * blocks (the driver adds both while walking the same observations, :55-69 / :100-190), textures
+ * must be shared blocks (cslam_set_textures), tracks hold at most 32 observations per vertex and
+ * there are at most 96 shared columns (3 per material + 1 per texture + 3); anything else returns
+ * CSLAM_ERR_NOT_IMPL.  Single GPU. */
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary);
 
 /* The same, split so a caller can keep the problem resident in HBM:

@@ -7,12 +7,14 @@
 #include <string>
 
 #include "../include/cslam_b200.h"
+#include "phong_problem.hpp"
 #include "problem.hpp"
 
 using namespace oracle;
 
 struct cslam_oracle_problem {
     Problem prob;
+    PhongProblem ph;            // lighting blocks of dataset_ba_phong (filled by add_phong)
     Options opt;
     Summary last;
     std::string err;
@@ -178,8 +180,103 @@ int cslam_oracle_evaluate(cslam_oracle_problem* p, int apply_loss, double* cost,
     cp(J_prior, ev.J_pr);
     return CSLAM_OK;
 }
+// ---- lighting blocks (dataset_ba_phong.cpp:100-205) ------------------------------------------------
+int cslam_oracle_set_vertices(cslam_oracle_problem* p, uint32_t n, double* normals3, double* textures,
+                              const uint32_t* material_id) {
+    PhongProblem& q = p->ph;
+    q.n_vertices = int(n);
+    q.normals = normals3;
+    q.v_mat.assign(material_id, material_id + n);
+    // per-vertex texture values unless cslam_oracle_set_textures shares them
+    q.textures = textures;
+    q.n_tex = int(n);
+    q.v_tex.resize(n);
+    for (uint32_t j = 0; j < n; ++j) q.v_tex[j] = j;
+    return CSLAM_OK;
+}
+int cslam_oracle_set_textures(cslam_oracle_problem* p, uint32_t n_textures, double* kd, const uint32_t* vertex_texture_id) {
+    PhongProblem& q = p->ph;
+    for (int j = 0; j < q.n_vertices; ++j)
+        if (vertex_texture_id[j] >= n_textures) {
+            p->err = "texture index out of range";
+            return CSLAM_ERR_INVALID;
+        }
+    q.textures = kd;
+    q.n_tex = int(n_textures);
+    q.v_tex.assign(vertex_texture_id, vertex_texture_id + q.n_vertices);
+    return CSLAM_OK;
+}
+int cslam_oracle_set_materials(cslam_oracle_problem* p, uint32_t n, double* phong3) {
+    p->ph.materials = phong3;
+    p->ph.n_mat = int(n);
+    return CSLAM_OK;
+}
+int cslam_oracle_set_light(cslam_oracle_problem* p, double* light3, int directional) {
+    p->ph.light = light3;
+    p->ph.directional = directional != 0;
+    return CSLAM_OK;
+}
+int cslam_oracle_set_bounds(cslam_oracle_problem* p, int block_kind, const double* lower, const double* upper) {
+    PhongProblem& q = p->ph;
+    if (block_kind == 0) {
+        for (int k = 0; k < 3; ++k) q.mat_lo[k] = lower[k], q.mat_hi[k] = upper[k];
+    } else if (block_kind == 1) {
+        q.tex_lo = lower[0];
+        q.tex_hi = upper[0];
+    } else {
+        p->err = "set_bounds: block_kind must be 0 (material) or 1 (texture)";
+        return CSLAM_ERR_INVALID;
+    }
+    q.bounded = true;
+    return CSLAM_OK;
+}
+int cslam_oracle_add_phong(cslam_oracle_problem* p, uint64_t n, const uint32_t* cam, const uint32_t* vertex,
+                           const double* intensity, double int_stiffness, const double* normal_obs3,
+                           const double* W_normal9) {
+    PhongProblem& q = p->ph;
+    q.cam.assign(cam, cam + n);
+    q.vtx.assign(vertex, vertex + n);
+    q.intensity.assign(intensity, intensity + n);
+    q.normal_obs.assign(normal_obs3, normal_obs3 + 3 * n);
+    q.int_stiffness = int_stiffness;
+    std::memcpy(q.Wn, W_normal9, sizeof(q.Wn));
+    return CSLAM_OK;
+}
+// joins the stereo blocks (same (pose, vertex) list, dataset_ba_phong.cpp:55-69 and :100-190 walk the
+// same observations) with the lighting blocks
+static int bind_phong(cslam_oracle_problem* p) {
+    PhongProblem& q = p->ph;
+    const Problem& s = p->prob;
+    if (s.st_cam != q.cam || s.st_pt != q.vtx) {
+        p->err = "lighting blocks must pair one-to-one with the stereo blocks (same pose / vertex lists)";
+        return CSLAM_ERR_INVALID;
+    }
+    if (s.st_W_per_obs || !s.suns.empty() || !s.priors.empty()) {
+        p->err = "lighting solve: shared stereo stiffness, no sun / prior blocks";
+        return CSLAM_ERR_NOT_IMPL;
+    }
+    if (!q.normals || !q.materials || !q.light || q.n_vertices != s.n_points) {
+        p->err = "lighting solve: vertices / materials / light not set";
+        return CSLAM_ERR_INVALID;
+    }
+    q.camera = s.camera;
+    q.poses = s.poses;
+    q.n_poses = s.n_poses;
+    q.pose_const = s.pose_const;
+    q.positions = s.points;
+    q.uvd = s.st_uvd;
+    std::memcpy(q.W, s.st_W.data(), sizeof(q.W));
+    return CSLAM_OK;
+}
 int cslam_oracle_solve(cslam_oracle_problem* p, cslam_summary* s) {
-    bool ok = p->prob.solve(p->opt, p->last);
+    bool ok;
+    if (!p->ph.cam.empty()) {
+        const int st = bind_phong(p);
+        if (st != CSLAM_OK) return st;
+        ok = p->ph.solve(p->opt, p->last);
+    } else {
+        ok = p->prob.solve(p->opt, p->last);
+    }
     if (s) {
         std::memset(s, 0, sizeof(*s));
         s->initial_cost = p->last.initial_cost;

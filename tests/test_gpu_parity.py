@@ -439,3 +439,62 @@ def test_covariance_block_full_batch(product):
     from ceres_slam_b200.problem import CslamError
     with pytest.raises(CslamError):
         pg.covariance_block(0)  # constant pose
+
+
+def _phong_pair(tr, iters, bounds, **extra):
+    kw = dict(FIXED, max_num_iterations=iters, **extra)
+    pg, sg = syn.build_phong_problem(tr, backend="b200", bounds=bounds, **kw)
+    po, so = syn.build_phong_problem(tr, backend="oracle", bounds=bounds, num_threads=8, **kw)
+    return (pg, pg.solve(), sg), (po, po.solve(), so)
+
+
+@pytest.mark.parametrize("directional,bounds", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("shape", [(12, 20, 5), (40, 12, 6)])
+def test_lm_phong_joint(product, shape, directional, bounds):
+    """dataset_ba_phong's joint solve (stage 3, dataset_ba_phong.cpp:249-252): poses, vertex
+    positions and normals, materials, textures and the light after a fixed number of LM iterations,
+    against the oracle (cost trajectory, accept/reject pattern, every parameter block, 1e-6).
+    (12, 20, 5): the reduced camera system is too short for the banded solver (PCG run to 1e-15
+    for the border solves); (40, 12, 6): banded direct solver."""
+    tr = syn.add_phong(syn.make_track(*shape, seed=8), directional=directional, shared_textures=True)
+    (pg, sg, stg), (po, so, sto) = _phong_pair(tr, 6, bounds)
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape and sg.num_iterations == so.num_iterations
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory"
+    assert np.array_equal(lg[:, 9], lo[:, 9]), "accept/reject pattern"
+    assert np.allclose(lg[:, 6], lo[:, 6], rtol=1e-5, atol=0), "radius trajectory"
+    assert abs(sg.final_cost - so.final_cost) <= LM_TOL * so.final_cost
+    assert sg.final_cost < 0.1 * sg.initial_cost
+    for k in ("poses", "points", "normals", "phong", "textures", "light"):
+        assert rel_err(stg[k], sto[k]) < LM_TOL, k
+    # the lighting parameters moved, and towards the truth
+    assert np.abs(stg["light"] - tr["light"]).max() > 1e-4
+    if bounds:
+        assert np.all(stg["phong"][:, :2] >= 0) and np.all(stg["phong"][:, :2] <= 1) and np.all(stg["phong"][:, 2] >= 1)
+        assert np.all(stg["textures"] >= 0) and np.all(stg["textures"] <= 1)
+
+
+def test_lm_phong_bounds_active(product):
+    """The reference's own starting point (dataset_problem_phong.cpp:262-279): materials at
+    (0, 0, 1) — on the box — and the per-material median intensity as texture.  Exercises the
+    projection and the Armijo search of the bounded trust-region loop."""
+    tr = syn.add_phong(syn.make_track(30, 12, 6, seed=5), shared_textures=True)
+    tr["phong"] = np.tile(np.array([0.0, 0.0, 1.0]), (tr["phong"].shape[0], 1))
+    med = np.array([np.median(tr["intensity"][tr["material_id"][tr["obs_pt"]] == m]) for m in range(tr["phong"].shape[0])])
+    tr["tex_shared"] = np.clip(med, 0, 1)
+    (pg, sg, stg), (po, so, sto) = _phong_pair(tr, 8, True)
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory"
+    assert np.array_equal(lg[:, 9], lo[:, 9]), "accept/reject pattern"
+    for k in ("poses", "points", "normals", "phong", "textures", "light"):
+        assert rel_err(stg[k], sto[k]) < LM_TOL, k
+
+
+def test_phong_solve_refusals(product):
+    """What the joint solve does not take is refused loudly, not solved differently."""
+    from ceres_slam_b200.problem import CslamError
+    tr = syn.add_phong(syn.make_track(12, 20, 5, seed=8))       # per-vertex textures
+    pg, _ = syn.build_phong_problem(tr, backend="b200")
+    with pytest.raises(CslamError, match="status 3"):
+        pg.solve()
