@@ -39,6 +39,8 @@ Engine::~Engine() {
     if (ev_b) cudaEventDestroy(ev_b);
     if (ev_c) cudaEventDestroy(ev_c);
     if (ev_d) cudaEventDestroy(ev_d);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    band_sets.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
     if (own_stream && stream) cudaStreamDestroy(stream);
     if (nccl_comm) comm_destroy(nccl_comm);
@@ -75,7 +77,7 @@ static void ensure_device(Engine* e, cudaStream_t* stream, bool* own, cudaEvent_
         CSLAM_CUDA(cudaEventCreate(c));
         CSLAM_CUDA(cudaEventCreate(d));
     }
-    if (!*pinned) CSLAM_CUDA(cudaMallocHost(pinned, 64 * sizeof(double)));
+    if (!*pinned) CSLAM_CUDA(cudaMallocHost(pinned, 128 * sizeof(double)));
 }
 
 void Engine::prof_begin(int) {
@@ -738,6 +740,63 @@ void Engine::plan_band_solver() {
     band_active = true;
 }
 
+void Engine::alloc_band_sets(int count) {
+    band_sets.clear();
+    if (!band_active || count <= 0) return;
+    const int n = n_free, W = band_storage_width(band_w), P = band_P;
+    const size_t b = 6 * size_t(W), GC = P > 1 ? 1 + b : 1;
+    const size_t n2 = size_t(std::max(P - 1, 1)) * W, W2 = 2 * size_t(W) - 1;
+    const size_t per_set = (size_t(n) * (W + 1) * 36 + size_t(n) * 6 * GC + 3 * size_t(P) * b * b + 2 * n2 * (W2 + 1) * 36) * 8;
+    count = int(std::min<size_t>(size_t(count), std::max<size_t>(1, (size_t(2) << 30) / std::max<size_t>(per_set, 1))));
+    if (!ev_fork) CSLAM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    // one allocation for every set (hundreds of cudaMalloc calls cost seconds)
+    const size_t sizes[13] = {size_t(n) * (W + 1) * 36, size_t(n) * 6 * GC, size_t(P) * b * b, size_t(P) * b * b,
+                              size_t(P) * b * b,        size_t(P) * b,      size_t(P) * b,     n2 * (W2 + 1) * 36,
+                              n2 * (W2 + 1) * 36,       6 * n2,             6 * n2,            6 * n2,
+                              size_t(PS_COUNT)};
+    size_t set_doubles = 2;  // the fail flag
+    for (size_t z : sizes) set_doubles += (z + 1) & ~size_t(1);
+    band_pool.alloc(set_doubles * size_t(count), stream);
+    for (int i = 0; i < count; ++i) {
+        auto bs = std::make_unique<BandSet>();
+        CSLAM_CUDA(cudaStreamCreateWithFlags(&bs->stream, cudaStreamNonBlocking));
+        CSLAM_CUDA(cudaEventCreateWithFlags(&bs->done, cudaEventDisableTiming));
+        double* base = band_pool.p + set_doubles * size_t(i);
+        bs->fail = reinterpret_cast<int*>(base);
+        base += 2;
+        double** slots[13] = {&bs->Lbuf, &bs->Xbuf, &bs->Ta, &bs->Ca, &bs->Tb, &bs->fa, &bs->fb, &bs->T2,
+                              &bs->L2,   &bs->rhs2, &bs->X2, &bs->y2, &bs->ps};
+        for (int k = 0; k < 13; ++k) {
+            *slots[k] = base;
+            base += (sizes[k] + 1) & ~size_t(1);
+        }
+        band_sets.push_back(std::move(bs));
+    }
+}
+
+// One banded solve S_cc y = rhs on the set's own stream and scratch (enqueue only)
+void Engine::solve_reduced_on(BandSet& bs, const double* rhs, double* y) {
+    BandView V;
+    V.n = n_free;
+    V.w = band_w;
+    V.P = band_P;
+    V.m = band_m;
+    V.band_idx = d_band_idx.p;
+    V.S = d_S;
+    V.rhs = rhs;
+    V.Lbuf = bs.Lbuf;
+    V.Xbuf = bs.Xbuf;
+    V.Ta = bs.Ta;
+    V.Ca = bs.Ca;
+    V.fa = bs.fa;
+    V.Tb = bs.Tb;
+    V.fb = bs.fb;
+    V.y = y;
+    V.fail = bs.fail;
+    const BandScratch K{bs.T2, bs.rhs2, bs.L2, bs.X2, bs.y2};
+    launch_band_solve(bs.stream, V, K, bs.ps);
+}
+
 void Engine::reset_state() {
     if (!uploaded) throw std::invalid_argument("reset_state before upload");
     CSLAM_CUDA(cudaMemcpyAsync(d_poses.p, d_poses_init.p, d_poses.bytes(), cudaMemcpyDeviceToDevice, stream));
@@ -831,11 +890,13 @@ void Engine::setup_phong_solve() {
     }
     if (n_lm)
         for (int k = 0; k < 3; ++k) ph.g_used_h[l0 + k] = 1;
-    for (long long e = 0; e < n_obs; ++e) {
-        const uint32_t u = obs_user_h[size_t(e)];
-        oI[size_t(e)] = ph_intensity[u];
-        for (int k = 0; k < 3; ++k) on[size_t(k) * no + size_t(e)] = ph_normal_obs[3 * size_t(u) + k];
-    }
+    parallel_chunks(size_t(n_obs), size_t(1) << 16, [&](int, size_t c0, size_t c1) {
+        for (size_t e = c0; e < c1; ++e) {
+            const uint32_t u = obs_user_h[e];
+            oI[e] = ph_intensity[u];
+            for (int k = 0; k < 3; ++k) on[size_t(k) * no + e] = ph_normal_obs[3 * size_t(u) + k];
+        }
+    });
     std::memcpy(gxh.data(), h_phong, 3 * size_t(ph.n_mat) * sizeof(double));
     std::memcpy(gxh.data() + t0, h_tex_shared, size_t(ph.n_tex) * sizeof(double));
     std::memcpy(gxh.data() + l0, h_light, 24);
@@ -853,6 +914,7 @@ void Engine::setup_phong_solve() {
     ph.yv.alloc(6 * nl, stream);
     ph.X.alloc(size_t(ph.n_g + 1) * 6 * size_t(std::max(n_free, 1)), stream);
     ph.T.alloc(size_t(ph.n_g) * (ph.n_g + 1), stream);
+    alloc_band_sets(ph.n_g + 1);
     CSLAM_CUDA(cudaStreamSynchronize(stream));  // the host staging vectors go out of scope
 }
 
@@ -904,7 +966,30 @@ void Engine::phong_linear_solve(int* iters, bool* ok) {
     *ok = true;
     prof_begin(CSLAM_K_PCG);
     const size_t nf6 = 6 * size_t(n_free);
-    if (n_free > 0) {
+    bool side_fail = false;
+    if (n_free > 0 && band_active && !band_sets.empty()) {
+        // the n_g + 1 banded solves are independent: fan them out over the scratch sets' streams
+        CSLAM_CUDA(cudaEventRecord(ev_fork, stream));
+        for (auto& bs : band_sets) CSLAM_CUDA(cudaStreamWaitEvent(bs->stream, ev_fork, 0));
+        size_t slot = 0;
+        for (int k = 0; k <= ph.n_g; ++k) {
+            double* y = ph.X.p + size_t(k) * nf6;
+            if (k < ph.n_g && !ph.g_used_h[k]) {
+                CSLAM_CUDA(cudaMemsetAsync(y, 0, nf6 * sizeof(double), stream));
+                continue;
+            }
+            const double* rhs = k < ph.n_g ? ph.Scg + size_t(k) * nf6 : d_bp;
+            solve_reduced_on(*band_sets[slot++ % band_sets.size()], rhs, y);
+        }
+        for (auto& bs : band_sets) {
+            CSLAM_CUDA(cudaEventRecord(bs->done, bs->stream));
+            CSLAM_CUDA(cudaStreamWaitEvent(stream, bs->done, 0));
+        }
+        launch_fill(stream, d_pscal.p, PS_COUNT, 0.0);
+        // every solve factors the same S: one status tells them all
+        CSLAM_CUDA(cudaMemcpyAsync(h_pinned + 64, band_sets[0]->ps, PS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        side_fail = true;  // checked after the synchronising read below
+    } else if (n_free > 0) {
         for (int k = 0; k < ph.n_g; ++k) {
             if (ph.g_used_h[k])
                 solve_reduced(ph.Scg + size_t(k) * nf6, ph.X.p + size_t(k) * nf6);
@@ -920,6 +1005,7 @@ void Engine::phong_linear_solve(int* iters, bool* ok) {
     read_scalars(d_pscal.p, ps, PS_COUNT);
     prof_end(CSLAM_K_PCG);
     *ok = ps[PS_FAIL] != 2.0;
+    if (side_fail && h_pinned[64 + PS_FAIL] == 2.0) *ok = false;
 }
 
 void Engine::allreduce_system() {
@@ -1090,7 +1176,8 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
         std::memcpy(first, sc2, sizeof(first));
         bool success = true;
         int ls_it = 0;
-        while (!std::isfinite(f_cur) || f_cur > lm.x_cost + 1e-4 * g0 * a_cur) {
+        const double armijo = opt.line_search_sufficient_function_decrease;
+        while (!std::isfinite(f_cur) || f_cur > lm.x_cost + armijo * g0 * a_cur) {
             if (++ls_it >= 20) {
                 success = false;
                 break;

@@ -292,6 +292,25 @@ class Engine {
     DBuf<int> d_band_idx, d_band_fail;
     DBuf<double> d_Lbuf, d_Xbuf, d_Ta, d_Ca, d_fa, d_Tb, d_fb, d_T2, d_rhs2, d_L2, d_X2, d_y2;
     void plan_band_solver();
+    // extra scratch sets + streams so that independent solves against the same banded S run
+    // concurrently (the border columns of the lighting solve): each solve is a latency-bound chain
+    // on a handful of CTAs, so n_g + 1 of them fit side by side on 148 SMs
+    struct BandSet {
+        int* fail = nullptr;       // all pointers are slices of band_pool
+        double *Lbuf = nullptr, *Xbuf = nullptr, *Ta = nullptr, *Ca = nullptr, *fa = nullptr, *Tb = nullptr, *fb = nullptr,
+               *T2 = nullptr, *rhs2 = nullptr, *L2 = nullptr, *X2 = nullptr, *y2 = nullptr, *ps = nullptr;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        ~BandSet() {
+            if (done) cudaEventDestroy(done);
+            if (stream) cudaStreamDestroy(stream);
+        }
+    };
+    std::vector<std::unique_ptr<BandSet>> band_sets;
+    DBuf<double> band_pool;
+    cudaEvent_t ev_fork = nullptr;
+    void alloc_band_sets(int count);
+    void solve_reduced_on(BandSet& bs, const double* rhs, double* y);
     DBuf<double> d_scal2;                  // scalars of the back-substitution pass
     DBuf<SunBlockData> d_suns;
     DBuf<PriorBlockData> d_priors;

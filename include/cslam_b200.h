@@ -65,6 +65,8 @@ typedef struct cslam_options {
                                into (0 = auto) */
     int window_path;        /* small problems (<= 8 poses, exact solve): 0 = auto (one-CTA-per-window kernel
                                with the LM loop on the device), 1 = never, 2 = require it */
+    double line_search_sufficient_function_decrease; /* 1e-4: Armijo constant of the line search a
+                               bounded problem runs along the trust-region step */
 } cslam_options;
 
 typedef struct cslam_summary {

@@ -43,6 +43,8 @@ static Options to_options(const cslam_options* o) {
     r.max_linear_solver_iterations = o->max_linear_solver_iterations;
     r.min_linear_solver_iterations = o->min_linear_solver_iterations;
     r.num_threads = o->num_threads > 0 ? o->num_threads : 1;
+    if (o->line_search_sufficient_function_decrease > 0.0)
+        r.line_search_sufficient_function_decrease = o->line_search_sufficient_function_decrease;
     return r;
 }
 
@@ -71,6 +73,7 @@ void cslam_oracle_options_init(cslam_options* o) {
     o->max_linear_solver_iterations = d.max_linear_solver_iterations;
     o->min_linear_solver_iterations = d.min_linear_solver_iterations;
     o->num_threads = d.num_threads;
+    o->line_search_sufficient_function_decrease = d.line_search_sufficient_function_decrease;
 }
 
 int cslam_oracle_problem_create(cslam_oracle_problem** out, const cslam_options* opt) {

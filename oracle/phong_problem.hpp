@@ -709,7 +709,7 @@ class PhongProblem {
                 double a_cur = 1.0, f_cur = cand_cost;
                 bool success = true;
                 int ls_it = 0;
-                while (!std::isfinite(f_cur) || f_cur > x_cost + 1e-4 * g0 * a_cur) {
+                while (!std::isfinite(f_cur) || f_cur > x_cost + opt.line_search_sufficient_function_decrease * g0 * a_cur) {
                     if (++ls_it >= 20) {
                         success = false;
                         break;

@@ -43,6 +43,7 @@ struct Options {
     int max_linear_solver_iterations = 500;
     int min_linear_solver_iterations = 0;
     int num_threads = 8;        // dataset_vo.cpp:67
+    double line_search_sufficient_function_decrease = 1e-4;  // Ceres default (bounded problems)
 };
 
 enum Termination { CONVERGENCE = 0, NO_CONVERGENCE = 1, FAILURE = 2 };

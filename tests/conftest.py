@@ -18,7 +18,7 @@ def _build_oracle():
     """The oracle is the checker: make sure its library exists (g++ only, seconds)."""
     so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
     srcs = [os.path.join(ROOT, "oracle", f) for f in
-            ("oracle_capi.cpp", "jet.hpp", "geometry.hpp", "functors.hpp", "problem.hpp")]
+            ("oracle_capi.cpp", "jet.hpp", "geometry.hpp", "functors.hpp", "problem.hpp", "phong_problem.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     yield

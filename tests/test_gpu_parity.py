@@ -498,3 +498,20 @@ def test_phong_solve_refusals(product):
     pg, _ = syn.build_phong_problem(tr, backend="b200")
     with pytest.raises(CslamError, match="status 3"):
         pg.solve()
+
+
+def test_lm_phong_line_search_contracts(product):
+    """A stiff Armijo constant (Ceres' line_search_sufficient_function_decrease) makes the full
+    trust-region step fail the test, so the search contracts it: the scaled candidates, their costs
+    and the resulting trajectory must match the oracle's."""
+    tr = syn.add_phong(syn.make_track(20, 10, 6, seed=5), shared_textures=True)
+    tr["phong"] = np.tile(np.array([0.0, 0.0, 1.0]), (tr["phong"].shape[0], 1))
+    (pg, sg, stg), (po, so, sto) = _phong_pair(tr, 8, True, line_search_sufficient_function_decrease=0.9)
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape
+    assert np.all(lo[1:, 5] < 0.5), "the search must have shortened the steps"
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory"
+    assert np.allclose(lg[:, 4], lo[:, 4], rtol=1e-5, atol=0), "step norms (scaled by the search)"
+    assert np.array_equal(lg[:, 9], lo[:, 9])
+    for k in ("poses", "points", "normals", "phong", "textures", "light"):
+        assert rel_err(stg[k], sto[k]) < LM_TOL, k
