@@ -218,6 +218,48 @@ def bench_phong_blocks(peak_gbs, reps=10):
             "note": "IntensityErrorPointLight + NormalError residuals and tangent-space Jacobians per observation"}
 
 
+def bench_c3_phong_solve(iters=6, cpu=True):
+    """BASELINE.json config 3: dataset_ba_phong's joint solve (2 k poses x 200 k vertices, ~2 M
+    observations, each a stereo + an intensity + a normal block; 8 materials and textures, one point
+    light, the box of dataset_ba_phong.cpp:143-181).  LM iterations/s with the problem resident in
+    HBM, split by kernel class, next to the oracle on a bounded sample (scaled by observations)."""
+    fixed = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    tr = syn.add_phong(syn.make_track(2000, 100, 10, seed=42), shared_textures=True)
+    n = int(tr["obs_cam"].size)
+    p, _ = syn.build_phong_problem(tr, backend="b200", bounds=True, max_num_iterations=10 ** 6, profile_kernels=1, **fixed)
+    t0 = time.perf_counter()
+    p.upload()
+    up = time.perf_counter() - t0
+    p.lm_begin()
+    p.lm_iterate(3, ignore_convergence=True)
+    p.reset_profile()
+    s0 = p.lm_iterate(0, ignore_convergence=True).device_ms
+    s = p.lm_iterate(iters, ignore_convergence=True)
+    ms = (s.device_ms - s0) / iters
+    prof = {k: {"ms": v[0] / max(1, v[1]), "launches": v[1]} for k, v in p.profile().items() if v[1]}
+    log = p.iteration_log()
+    p.close()
+    out = {"poses": int(tr["n_poses"]), "vertices": int(tr["n_points"]), "observations": n, "shared_columns": 35,
+           "ms_per_lm_iteration": ms, "lm_iters_per_s": 1e3 / ms, "obs_per_s": n * 1e3 / ms, "step_profile_ms": prof,
+           "upload_and_structure_s": up, "cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
+           "note": "vertex (position + normal) blocks eliminated on the GPU, arrowhead reduced system: banded "
+                   "camera part + 35 dense border columns solved with 36 concurrent banded solves"}
+    if cpu:
+        trs = syn.add_phong(syn.make_track(60, 100, 10, seed=42), shared_textures=True)
+        threads = os.cpu_count() or 1
+        po, _ = syn.build_phong_problem(trs, backend="oracle", bounds=True, max_num_iterations=3, num_threads=threads, **fixed)
+        t0 = time.perf_counter()
+        so = po.solve()
+        dt = (time.perf_counter() - t0) / max(1, so.num_iterations)
+        po.close()
+        ns = int(trs["obs_cam"].size)
+        out["cpu_baseline"] = {"value": 1.0 / (dt * n / ns), "unit": "LM iter/s", "cores": threads, "kind": "port",
+                               "sample": f"60 poses / {ns} observations of the same track, {so.num_iterations} LM iterations, "
+                                         "scaled by observations (the oracle factors the reduced system densely, "
+                                         "which favours it at this size)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -360,6 +402,7 @@ def main():
     p.close()
     c4 = bench_c4_windows(lib) if (rank == 0 and not args.no_c4) else None
     phong = bench_phong_blocks(peak) if (rank == 0 and not args.no_phong) else None
+    c3 = bench_c3_phong_solve(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_phong) else None
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     e2e = None
@@ -397,6 +440,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
             "resjac": resjac, "step_profile_ms": step_profile, "c4_windows": c4, "phong_blocks": phong,
+            "c3_phong_solve": c3,
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},
             "setup_s": {"generate": gen_s, "upload_and_structure": upload_s},
