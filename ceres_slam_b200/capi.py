@@ -116,7 +116,10 @@ _COMMON = {
     "set_bounds": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "add_phong": (C.c_int, [_h, C.c_uint64, _u32p, _u32p, _dp, C.c_double, _dp, _dp]),
 }
+_RANSAC_SIG = (C.c_int, [C.c_int, C.c_uint32, _u32p, _dp, _dp, _dp, C.c_uint32, C.c_double, C.c_int, _dp, _u8p, _u32p])
+_COMMON["ransac_align"] = _RANSAC_SIG
 _PRODUCT_ONLY = {
+    "ransac_triples": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, _u32p]),
     "evaluate_phong": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp, _dp]),
     "time_phong": (C.c_int, [_h, C.c_int, _dp]),
     "covariance_block": (C.c_int, [_h, C.c_uint32, _dp]),
@@ -140,6 +143,8 @@ _PRODUCT_ONLY = {
     "attach_comm": (C.c_int, [_h, C.c_int, C.c_int, _u8p]),
 }
 _ORACLE_ONLY = {
+    "ransac_draws": (None, [C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p]),
+    "kabsch": (None, [C.c_uint32, _dp, _dp, _dp]),
     "so3_exp": (None, [_dp, _dp]),
     "so3_log": (None, [_dp, _dp]),
     "se3_exp": (None, [_dp, _dp]),

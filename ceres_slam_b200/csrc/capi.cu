@@ -381,6 +381,27 @@ cslam_status cslam_analyze(cslam_problem* p, int n_ranks, int rank, cslam_struct
     });
 }
 
+cslam_status cslam_ransac_align(int device, uint32_t n_pairs, const uint32_t* offsets, const double* pts0,
+                                const double* pts1, const double* intr5, uint32_t num_iters, double thresh,
+                                int rng_variant, double* T12_out, uint8_t* inlier_out, uint32_t* n_inliers_out) {
+    if (!offsets || !pts0 || !pts1 || !intr5 || !T12_out || num_iters == 0 || rng_variant < 0 || rng_variant > 1)
+        return CSLAM_ERR_INVALID;
+    for (uint32_t p = 0; p < n_pairs; ++p)
+        if (offsets[p + 1] < offsets[p]) return CSLAM_ERR_INVALID;
+    try {
+        cslam::ransac_align_batch(device, n_pairs, offsets, pts0, pts1, intr5, num_iters, thresh, rng_variant, T12_out,
+                                  inlier_out, n_inliers_out);
+        return CSLAM_OK;
+    } catch (...) {
+        return CSLAM_ERR_CUDA;
+    }
+}
+cslam_status cslam_ransac_triples(uint32_t n, uint32_t num_iters, int rng_variant, uint32_t* triples) {
+    if (n < 3 || !triples || rng_variant < 0 || rng_variant > 1) return CSLAM_ERR_INVALID;
+    cslam::ransac_triples(n, num_iters, rng_variant, triples);
+    return CSLAM_OK;
+}
+
 cslam_status cslam_get_launch_count(uint64_t* count) {
     if (!count) return CSLAM_ERR_INVALID;
     *count = cslam::g_kernel_launches.load();

@@ -102,6 +102,12 @@ void launch_phong_project_initial(cudaStream_t s, const PhongSolveView& q, int n
 void launch_dot(cudaStream_t s, const double* a, const double* b, long long n, double* dst);
 void launch_absmax_scaled(cudaStream_t s, const double* y, const double* sc, long long n, double* dst);
 
+// KR — batched 3-point RANSAC point-cloud alignment (ransac.cu); host arrays in and out
+void ransac_align_batch(int device, uint32_t n_pairs, const uint32_t* offsets, const double* pts0, const double* pts1,
+                        const double* intr5, uint32_t num_iters, double thresh, int rng_variant, double* T12_out,
+                        uint8_t* inlier_out, uint32_t* n_inliers_out);
+void ransac_triples(uint32_t n, uint32_t num_iters, int variant, uint32_t* out);
+
 double measure_fp64_peak_tflops(int device);
 extern std::atomic<unsigned long long> g_kernel_launches;  // every kernel this library launches
 

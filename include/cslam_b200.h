@@ -268,6 +268,26 @@ typedef struct cslam_structure_info {
 } cslam_structure_info;
 cslam_status cslam_analyze(cslam_problem* p, int n_ranks, int rank, cslam_structure_info* out);
 
+/* PointCloudAligner::compute_transformation_and_inliers (src/ceres_slam/point_cloud_aligner.cpp:64-136),
+ * the 3-point RANSAC `compute_initial_guess` runs on every consecutive pose pair
+ * (dataset_problem.cpp:239-242: 400 iterations, threshold 4; dataset_problem_phong.cpp:323-326:
+ * threshold 9), for a BATCH of independent pairs in one launch.  Pair p owns the correspondences
+ * [offsets[p], offsets[p+1]) of pts0 / pts1 (3 doubles each: the triangulated points in camera
+ * frame k-1 and k, index-aligned).  Every hypothesis aligns three correspondences whose indices are
+ * drawn exactly like the reference draws them: std::mt19937 seeded with 42 (:70-72) through
+ * std::uniform_int_distribution<uint>(0, n-1), re-drawing duplicates (:82-90).  rng_variant selects
+ * the libstdc++ algorithm of that distribution: 0 = scaling + rejection (GCC <= 10, the reference's
+ * era), 1 = Lemire (GCC >= 11).  The best hypothesis is the one with the most inliers (squared
+ * reprojection distance < thresh, :117-123), the earliest on ties (:127).
+ * Out: T12_out 12 doubles per pair [t | R row-major] (T_1_0), inlier_out one byte per correspondence
+ * (may be NULL), n_inliers_out per pair (may be NULL).  A pair with fewer than 3 correspondences, or
+ * whose hypotheses all have no inlier, returns the identity and no inliers.  intr5 = fu, fv, cu, cv, b. */
+cslam_status cslam_ransac_align(int device, uint32_t n_pairs, const uint32_t* offsets, const double* pts0,
+                                const double* pts1, const double* intr5, uint32_t num_iters, double thresh,
+                                int rng_variant, double* T12_out, uint8_t* inlier_out, uint32_t* n_inliers_out);
+/* The index triples of those hypotheses for a cloud of n correspondences (host only; n >= 3). */
+cslam_status cslam_ransac_triples(uint32_t n, uint32_t num_iters, int rng_variant, uint32_t* triples);
+
 /* Number of kernels this library has launched in this process (all handles). */
 cslam_status cslam_get_launch_count(uint64_t* count);
 

@@ -9,6 +9,7 @@
 #include "../include/cslam_b200.h"
 #include "phong_problem.hpp"
 #include "problem.hpp"
+#include "ransac.hpp"
 
 using namespace oracle;
 
@@ -299,6 +300,41 @@ int cslam_oracle_get_iteration_log(const cslam_oracle_problem* p, double* rows, 
     if (n_rows) *n_rows = n;
     for (int i = 0; i < n && i < max_rows; ++i) std::memcpy(rows + CSLAM_LOG_COLS * i, &p->last.rows[i], sizeof(IterationRow));
     return CSLAM_OK;
+}
+
+// ---- front end: 3-point RANSAC point-cloud alignment (point_cloud_aligner.cpp:64-136) ---------------
+int cslam_oracle_ransac_align(int, uint32_t n_pairs, const uint32_t* offsets, const double* pts0, const double* pts1,
+                              const double* intr5, uint32_t num_iters, double thresh, int rng_variant, double* T12_out,
+                              uint8_t* inlier_out, uint32_t* n_inliers_out) {
+    const Camera cam{intr5[0], intr5[1], intr5[2], intr5[3], intr5[4]};
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        const uint32_t o = offsets[p], n = offsets[p + 1] - o;
+        std::vector<uint32_t> in = ransac_align(cam, pts0 + 3 * size_t(o), pts1 + 3 * size_t(o), n, num_iters, thresh,
+                                                rng_variant, T12_out + 12 * size_t(p));
+        if (inlier_out) {
+            std::fill(inlier_out + o, inlier_out + o + n, uint8_t(0));
+            for (uint32_t i : in) inlier_out[o + i] = 1;
+        }
+        if (n_inliers_out) n_inliers_out[p] = uint32_t(in.size());
+    }
+    return CSLAM_OK;
+}
+// the draws of the restated distribution next to std::uniform_int_distribution of this compiler
+void cslam_oracle_ransac_draws(uint32_t n, uint32_t count, int variant, uint32_t* restated, uint32_t* libstdcxx) {
+    std::mt19937 a(42), b(42);
+    std::uniform_int_distribution<unsigned> d(0, n - 1);
+    for (uint32_t i = 0; i < count; ++i) {
+        restated[i] = ransac_draw(a, n, variant);
+        libstdcxx[i] = d(b);
+    }
+}
+void cslam_oracle_kabsch(uint32_t n, const double* pts0, const double* pts1, double* T12) {
+    std::vector<const double*> a, b;
+    for (uint32_t i = 0; i < n; ++i) {
+        a.push_back(pts0 + 3 * size_t(i));
+        b.push_back(pts1 + 3 * size_t(i));
+    }
+    kabsch(a, b, T12);
 }
 
 // ---- direct access to the restated geometry / models, for the known-answer tests ----------
