@@ -57,16 +57,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
-def build_host_driver():
-    """C++ host mirror + restated dataset_vo driver (links the C ABI library)."""
+def build_host_driver(name="dataset_vo_b200"):
+    """C++ host mirror + a restated driver (dataset_vo_b200, dataset_vo_sun_b200,
+    dataset_ba_phong_b200); links the C ABI library."""
     host = os.path.join(HERE, "host")
-    out = os.path.join(host, "dataset_vo_b200")
-    src = os.path.join(host, "dataset_vo_b200.cpp")
-    deps = [src, os.path.join(host, "cslam_problem.hpp"), OUT, os.path.join(os.path.dirname(HERE), "include", "cslam_b200.h")]
+    out = os.path.join(host, name)
+    src = os.path.join(host, name + ".cpp")
+    deps = [src, os.path.join(host, "cslam_problem.hpp"), os.path.join(host, "dataset.hpp"), OUT,
+            os.path.join(os.path.dirname(HERE), "include", "cslam_b200.h")]
     if _stale(out, deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + CSRC, "-lcslam_b200",
                                "-Wl,-rpath," + CSRC, "-Wl,-rpath,$ORIGIN/../csrc"])
     return out
+
+
+HOST_DRIVERS = ("dataset_vo_b200", "dataset_vo_sun_b200", "dataset_ba_phong_b200")
 
 
 def build_oracle():

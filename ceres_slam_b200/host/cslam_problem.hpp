@@ -61,6 +61,57 @@ class Problem {
         std::memcpy(p.W, W6, 288);
         priors_.push_back(p);
     }
+    // One observation of dataset_ba_phong (tests/dataset_ba_phong.cpp:103-190): the intensity block
+    //   AddResidualBlock(IntensityError*LightAutomatic::Create(I, w), NULL, pose, position, normal, phong, texture, light)
+    // and the normal block
+    //   AddResidualBlock(NormalErrorAutomatic::Create(n_obs, W), NULL, pose, normal)
+    // of the same (pose, vertex).  Must follow the AddStereoBlock of that observation: the back end
+    // pairs them one-to-one.  Shared blocks (material, texture, light) are recognised by pointer.
+    void AddLightingBlocks(double* pose12, double* position3, double* normal3, double* phong3, double* texture1,
+                           double* light3, double intensity, double int_stiffness, const double normal_obs[3],
+                           const double W_normal[9]) {
+        ph_cam_.push_back(pose_index(pose12));
+        const uint32_t j = point_index(position3);
+        ph_vtx_.push_back(j);
+        if (normal_ptr_.size() <= j) {
+            normal_ptr_.resize(j + 1, nullptr);
+            vertex_mat_.resize(j + 1, 0);
+            vertex_tex_.resize(j + 1, 0);
+        }
+        normal_ptr_[j] = normal3;
+        vertex_mat_[j] = shared_index(phong3, mat_id_, mat_ptr_);
+        vertex_tex_[j] = shared_index(texture1, tex_id_, tex_ptr_);
+        light_ptr_ = light3;
+        ph_int_.push_back(intensity);
+        ph_nobs_.insert(ph_nobs_.end(), normal_obs, normal_obs + 3);
+        int_stiffness_ = int_stiffness;
+        std::memcpy(Wn_, W_normal, 72);
+    }
+    // problem.SetParameterization(light_dir, UnitVectorPerturbation) (dataset_ba_phong.cpp:199-203)
+    void SetLightDirectional(bool directional) { directional_ = directional; }
+    // problem.SetParameterLowerBound / UpperBound on every material / texture block (:143-181)
+    void SetMaterialBounds(const double lo[3], const double hi[3]) {
+        std::memcpy(mat_lo_, lo, 24);
+        std::memcpy(mat_hi_, hi, 24);
+        mat_bounded_ = true;
+    }
+    void SetTextureBounds(double lo, double hi) {
+        tex_lo_ = lo;
+        tex_hi_ = hi;
+        tex_bounded_ = true;
+    }
+    // ceres::Covariance::Compute + GetCovarianceBlockInTangentSpace(pose, pose, cov) after Solve
+    // (dataset_vo_sun.cpp:159-183); false when the computation failed (rank-deficient Jacobian)
+    bool GetCovarianceBlockInTangentSpace(double* pose12, double* cov36) {
+        if (!handle_) return false;
+        return cslam_covariance_block(handle_, pose_index(pose12), cov36) == CSLAM_OK;
+    }
+    ~Problem() {
+        if (handle_) cslam_problem_destroy(handle_);
+    }
+    Problem(const Problem&) = delete;
+    Problem& operator=(const Problem&) = delete;
+
     // problem.SetParameterization(pose, SE3Perturbation) is implied for every pose block
     void AddPoseBlock(double* pose12) { pose_index(pose12); }
     // problem.SetParameterBlockConstant(pose)
@@ -69,12 +120,18 @@ class Problem {
     // ceres::Solve(options, &problem, &summary)
     void Solve(Summary* summary) {
         const uint32_t nc = uint32_t(pose_ptr_.size()), np = uint32_t(point_ptr_.size());
-        std::vector<double> poses(12 * size_t(nc)), points(3 * size_t(np));
+        std::vector<double>&poses = poses_, &points = points_;
+        poses.assign(12 * size_t(nc), 0.0);
+        points.assign(3 * size_t(np), 0.0);
         for (uint32_t k = 0; k < nc; ++k) std::memcpy(&poses[12 * size_t(k)], pose_ptr_[k], 96);
         for (uint32_t j = 0; j < np; ++j) std::memcpy(&points[3 * size_t(j)], point_ptr_[j], 24);
+        if (handle_) cslam_problem_destroy(handle_);
+        handle_ = nullptr;
         cslam_problem* p = nullptr;
         check(cslam_problem_create(&p, &options), p);
-        try {
+        handle_ = p;
+        const bool lighting = !ph_cam_.empty();
+        {
             check(cslam_set_camera(p, cam_.fu, cam_.fv, cam_.cu, cam_.cv, cam_.b), p);
             check(cslam_set_poses(p, nc, poses.data(), constant_.data()), p);
             check(cslam_set_points(p, np, points.data()), p);
@@ -87,16 +144,40 @@ class Problem {
                 check(cslam_add_sun(p, uint32_t(sun_cam_.size()), sun_cam_.data(), sun_obs_.data(), sun_ref_.data(), sun_W_.data(),
                                     az_, zen_, huber_), p);
             for (auto& pr : priors_) check(cslam_add_pose_prior(p, pr.cam, pr.Tref, pr.W), p);
+            if (lighting) {
+                if (normal_ptr_.size() != np) throw std::runtime_error("cslam_b200: every vertex needs lighting blocks");
+                normals_.assign(3 * size_t(np), 0.0);
+                for (uint32_t j = 0; j < np; ++j) {
+                    if (!normal_ptr_[j]) throw std::runtime_error("cslam_b200: vertex without a normal block");
+                    std::memcpy(&normals_[3 * size_t(j)], normal_ptr_[j], 24);
+                }
+                mats_.assign(3 * mat_ptr_.size(), 0.0);
+                for (size_t m = 0; m < mat_ptr_.size(); ++m) std::memcpy(&mats_[3 * m], mat_ptr_[m], 24);
+                texs_.assign(tex_ptr_.size(), 0.0);
+                for (size_t t = 0; t < tex_ptr_.size(); ++t) texs_[t] = *tex_ptr_[t];
+                std::memcpy(light_, light_ptr_, 24);
+                std::vector<double> kd_unused(np, 0.0);
+                check(cslam_set_vertices(p, np, normals_.data(), kd_unused.data(), vertex_mat_.data()), p);
+                check(cslam_set_textures(p, uint32_t(texs_.size()), texs_.data(), vertex_tex_.data()), p);
+                check(cslam_set_materials(p, uint32_t(mat_ptr_.size()), mats_.data()), p);
+                check(cslam_set_light(p, light_, directional_ ? 1 : 0), p);
+                check(cslam_add_phong(p, ph_cam_.size(), ph_cam_.data(), ph_vtx_.data(), ph_int_.data(), int_stiffness_,
+                                      ph_nobs_.data(), Wn_), p);
+                if (mat_bounded_) check(cslam_set_bounds(p, 0, mat_lo_, mat_hi_), p);
+                if (tex_bounded_) check(cslam_set_bounds(p, 1, &tex_lo_, &tex_hi_), p);
+            }
             cslam_summary s{};
             check(cslam_solve(p, &s), p);
             if (summary) summary->s = s;
-        } catch (...) {
-            cslam_problem_destroy(p);
-            throw;
         }
-        cslam_problem_destroy(p);
         for (uint32_t k = 0; k < nc; ++k) std::memcpy(pose_ptr_[k], &poses[12 * size_t(k)], 96);
         for (uint32_t j = 0; j < np; ++j) std::memcpy(point_ptr_[j], &points[3 * size_t(j)], 24);
+        if (lighting) {
+            for (uint32_t j = 0; j < np; ++j) std::memcpy(normal_ptr_[j], &normals_[3 * size_t(j)], 24);
+            for (size_t m = 0; m < mat_ptr_.size(); ++m) std::memcpy(mat_ptr_[m], &mats_[3 * m], 24);
+            for (size_t t = 0; t < tex_ptr_.size(); ++t) *tex_ptr_[t] = texs_[t];
+            std::memcpy(light_ptr_, light_, 24);
+        }
     }
 
    private:
@@ -127,6 +208,26 @@ class Problem {
         point_ptr_.push_back(ptr);
         return id;
     }
+    static uint32_t shared_index(double* ptr, std::map<double*, uint32_t>& ids, std::vector<double*>& ptrs) {
+        auto it = ids.find(ptr);
+        if (it != ids.end()) return it->second;
+        const uint32_t id = uint32_t(ptrs.size());
+        ids[ptr] = id;
+        ptrs.push_back(ptr);
+        return id;
+    }
+    cslam_problem* handle_ = nullptr;      // kept after Solve for the covariance query
+    std::vector<double> poses_, points_, normals_, mats_, texs_;
+    double light_[3] = {0, 0, 0};
+    // lighting blocks
+    std::vector<uint32_t> ph_cam_, ph_vtx_, vertex_mat_, vertex_tex_;
+    std::vector<double> ph_int_, ph_nobs_;
+    std::vector<double*> normal_ptr_, mat_ptr_, tex_ptr_;
+    std::map<double*, uint32_t> mat_id_, tex_id_;
+    double* light_ptr_ = nullptr;
+    double int_stiffness_ = 1.0, Wn_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    bool directional_ = false, mat_bounded_ = false, tex_bounded_ = false;
+    double mat_lo_[3] = {0, 0, 0}, mat_hi_[3] = {0, 0, 0}, tex_lo_ = 0, tex_hi_ = 0;
     std::map<double*, uint32_t> pose_id_, point_id_;
     std::vector<double*> pose_ptr_, point_ptr_;
     std::vector<uint8_t> constant_;

@@ -1,128 +1,122 @@
 // dataset_vo restated over the B200 back end: sliding-window stereo VO / BA on the reference's
 // plain track CSV (format: src/ceres_slam/dataset_problem.cpp:27-83; driver:
-// tests/dataset_vo.cpp:87-138).  The reference's front end (RANSAC point-cloud alignment,
-// dataset_problem.cpp:179-270) is out of scope for this build, so the initial guess is the
-// constant-pose model: pose k starts at the optimised pose k-1 and every point is triangulated
-// from its first observation in the window (stereo_camera.hpp:112-120).
+// tests/dataset_vo.cpp:87-138).  The initial guess is the reference's: per window
+// `compute_initial_guess(k1, k2)` (RANSAC point-cloud alignment of consecutive poses on the GPU,
+// dataset_problem.cpp:179-270), residual blocks only for the points it initialised
+// (dataset_vo.cpp:44), `reset_points()` after every window (:130).  `--init constant` keeps the
+// earlier front-end-free start (pose k starts at pose k-1, points triangulated from their first
+// observation in the window).
 //
-//   usage: dataset_vo_b200 <input_file> [--window N=0] [--max-iters M]
+//   usage: dataset_vo_b200 <input_file> [--window N=0] [--max-iters M=1000] [--init ransac|constant]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <fstream>
 #include <iostream>
-#include <sstream>
-#include <string>
-#include <vector>
 
 #include "cslam_problem.hpp"
+#include "dataset.hpp"
+
+using namespace cslam_b200;
 
 struct Track {
     unsigned num_states = 0, num_points = 0;
-    double fu, fv, cu, cv, b, var[3];
+    double intr[5], var[3];
     std::vector<double> poses;   // 12 per state, [t | R row-major]
     std::vector<double> points;  // 3 per point
-    std::vector<unsigned> k, j;
-    std::vector<double> uvd;
-    std::vector<std::vector<unsigned>> state_obs;
+    std::vector<char> initialized;
+    ObservationTable obs;
 };
-
-static std::vector<double> parse_line(const std::string& line) {
-    std::vector<double> v;
-    std::stringstream ss(line);
-    std::string tok;
-    while (std::getline(ss, tok, ',')) v.push_back(std::stod(tok));
-    return v;
-}
 
 static bool read_csv(const std::string& file, Track& t) {
     std::ifstream in(file);
     if (!in.is_open()) return false;
     std::string line;
     std::getline(in, line);
-    auto v = parse_line(line);
+    auto v = parse_csv_line(line);
     t.num_states = unsigned(v.at(0));
     t.num_points = unsigned(v.at(1));
     std::getline(in, line);
-    v = parse_line(line);
-    t.fu = v.at(0); t.fv = v.at(1); t.cu = v.at(2); t.cv = v.at(3); t.b = v.at(4);
+    v = parse_csv_line(line);
+    for (int i = 0; i < 5; ++i) t.intr[i] = v.at(i);
     std::getline(in, line);
-    v = parse_line(line);
+    v = parse_csv_line(line);
     for (int i = 0; i < 3; ++i) t.var[i] = v.at(i);
     std::getline(in, line);
-    v = parse_line(line);  // first pose, 4x4 row-major
+    v = parse_csv_line(line);  // first pose, 4x4 row-major; every pose starts there
     t.poses.assign(12 * size_t(t.num_states), 0.0);
-    for (unsigned s = 0; s < t.num_states; ++s) {
-        double* P = &t.poses[12 * size_t(s)];
-        for (int r = 0; r < 3; ++r) {
-            P[r] = v.at(4 * r + 3);
-            for (int c = 0; c < 3; ++c) P[3 + 3 * r + c] = v.at(4 * r + c);
-        }
-    }
+    for (unsigned s = 0; s < t.num_states; ++s) pose_from_matrix16(v, &t.poses[12 * size_t(s)]);
     t.points.assign(3 * size_t(t.num_points), 0.0);
-    t.state_obs.assign(t.num_states, {});
+    t.initialized.assign(t.num_points, 0);
+    t.obs.state_obs.assign(t.num_states, {});
     while (std::getline(in, line)) {
         if (line.empty()) continue;
-        v = parse_line(line);
-        t.state_obs.at(unsigned(v.at(0))).push_back(unsigned(t.k.size()));
-        t.k.push_back(unsigned(v.at(0)));
-        t.j.push_back(unsigned(v.at(1)));
-        t.uvd.insert(t.uvd.end(), {v.at(2), v.at(3), v.at(4)});
+        v = parse_csv_line(line);
+        t.obs.state_obs.at(unsigned(v.at(0))).push_back(unsigned(t.obs.k.size()));
+        t.obs.k.push_back(unsigned(v.at(0)));
+        t.obs.j.push_back(unsigned(v.at(1)));
+        t.obs.uvd.insert(t.obs.uvd.end(), {v.at(2), v.at(3), v.at(4)});
     }
     return true;
 }
 
-static void solveWindow(Track& t, unsigned k1, unsigned k2, int max_iters) {
-    std::cerr << "Working on interval [" << k1 << "," << k2 << ")" << std::endl;
-    cslam_b200::Problem problem;
-    problem.SetCamera(t.fu, t.fv, t.cu, t.cv, t.b);
-    // stiffness = diag(var)^-1/2  (dataset_vo.cpp:29-32)
-    double W[9] = {1 / std::sqrt(t.var[0]), 0, 0, 0, 1 / std::sqrt(t.var[1]), 0, 0, 0, 1 / std::sqrt(t.var[2])};
+static void constant_pose_guess(Track& t, unsigned k1, unsigned k2) {
     std::vector<unsigned> seen(t.num_points, 0);
     for (unsigned k = k1; k < k2; ++k)
-        for (unsigned i : t.state_obs[k]) seen[t.j[i]]++;
-    std::vector<char> init(t.num_points, 0);
+        for (unsigned i : t.obs.state_obs[k]) seen[t.obs.j[i]]++;
     for (unsigned k = k1; k < k2; ++k) {
-        if (k > k1) std::memcpy(&t.poses[12 * size_t(k)], &t.poses[12 * size_t(k - 1)], 96);  // constant-pose guess
-        double* P = &t.poses[12 * size_t(k)];
-        problem.AddPoseBlock(P);
-        for (unsigned i : t.state_obs[k]) {
-            const unsigned j = t.j[i];
-            if (seen[j] < 2 && k2 - k1 > 1) continue;  // only points shared inside the window
-            double* X = &t.points[3 * size_t(j)];
-            if (!init[j]) {
-                // triangulate in camera k, move to the base frame with T^-1 = (R^T, -R^T t)
-                const double* z = &t.uvd[3 * size_t(i)];
-                const double bod = t.b / z[2];
-                const double pc[3] = {(z[0] - t.cu) * bod, (z[1] - t.cv) * bod * t.fu / t.fv, t.fu * bod};
-                for (int c = 0; c < 3; ++c)
-                    X[c] = P[3 + c] * (pc[0] - P[0]) + P[6 + c] * (pc[1] - P[1]) + P[9 + c] * (pc[2] - P[2]);
-                init[j] = 1;
-            }
-            problem.AddStereoBlock(P, X, &t.uvd[3 * size_t(i)], W);
+        if (k > k1) std::memcpy(&t.poses[12 * size_t(k)], &t.poses[12 * size_t(k - 1)], 96);
+        const double* P = &t.poses[12 * size_t(k)];
+        for (unsigned i : t.obs.state_obs[k]) {
+            const unsigned j = t.obs.j[i];
+            if ((seen[j] < 2 && k2 - k1 > 1) || t.initialized[j]) continue;  // only points shared inside the window
+            double pc[3];
+            triangulate(t.intr, &t.obs.uvd[3 * size_t(i)], pc);
+            pose_inverse_apply(P, pc, false, &t.points[3 * size_t(j)]);
+            t.initialized[j] = 1;
         }
     }
-    problem.SetParameterBlockConstant(&t.poses[12 * size_t(k1)]);
+}
+
+static void solveWindow(Track& t, unsigned k1, unsigned k2, int max_iters) {
+    std::cerr << "Working on interval [" << k1 << "," << k2 << ")" << std::endl;
+    Problem problem;
+    problem.SetCamera(t.intr[0], t.intr[1], t.intr[2], t.intr[3], t.intr[4]);
+    // stiffness = diag(var)^-1/2  (dataset_vo.cpp:29-32)
+    const double cov[9] = {t.var[0], 0, 0, 0, t.var[1], 0, 0, 0, t.var[2]};
+    double W[9];
+    sym_inverse_sqrt(cov, 3, W);
+    for (unsigned k = k1; k < k2; ++k) {
+        double* P = &t.poses[12 * size_t(k)];
+        problem.AddPoseBlock(P);                                                  // :58
+        for (unsigned i : t.obs.state_obs[k]) {
+            const unsigned j = t.obs.j[i];
+            if (t.initialized[j])                                                // :44
+                problem.AddStereoBlock(P, &t.points[3 * size_t(j)], &t.obs.uvd[3 * size_t(i)], W);  // :46-53
+        }
+    }
+    problem.SetParameterBlockConstant(&t.poses[12 * size_t(k1)]);                // :62
     problem.options.max_num_iterations = max_iters;  // dataset_vo.cpp:69 uses 1000
     problem.options.use_nonmonotonic_steps = 1;      // dataset_vo.cpp:70
-    cslam_b200::Summary summary;
+    Summary summary;
     problem.Solve(&summary);
     std::cout << summary.BriefReport() << std::endl << std::endl;
 }
 
 int main(int argc, char** argv) {
-    const std::string usage("usage: dataset_vo_b200 <input_file> [--window N=0] [--max-iters M=1000]");
+    const std::string usage("usage: dataset_vo_b200 <input_file> [--window N=0] [--max-iters M=1000] [--init ransac|constant]");
     if (argc < 2) {
         std::cerr << usage << std::endl;
         return EXIT_FAILURE;
     }
     unsigned window = 0;
     int max_iters = 1000;
+    bool ransac = true;
     const std::string filename(argv[1]);
     for (int a = 2; a < argc; ++a) {
         const std::string flag(argv[a]);
         if (flag == "--window" && argc > a + 1) window = unsigned(std::atoi(argv[++a]));
         else if (flag == "--max-iters" && argc > a + 1) max_iters = std::atoi(argv[++a]);
+        else if (flag == "--init" && argc > a + 1) ransac = std::string(argv[++a]) != "constant";
         else {
             std::cerr << usage << std::endl;
             return EXIT_FAILURE;
@@ -131,16 +125,17 @@ int main(int argc, char** argv) {
     Track t;
     if (!read_csv(filename, t)) return EXIT_FAILURE;
     if (window == 0 || window > t.num_states) window = t.num_states;  // 0 = full batch (dataset_vo.cpp:118-121)
-    for (unsigned k1 = 0; k1 + window <= t.num_states; ++k1) solveWindow(t, k1, k1 + window, max_iters);
-    // <stem>_poses.csv with 16 values per row (dataset_problem.cpp:139-150); full precision here
-    const std::string stem = filename.substr(0, filename.find('.'));
-    std::ofstream out(stem + "_poses.csv");
-    out << "T_00, T_01, T_02, T_03,T_10, T_11, T_12, T_13,T_20, T_21, T_22, T_23,T_30, T_31, T_32, T_33\n";
-    out.precision(17);
-    for (unsigned s = 0; s < t.num_states; ++s) {
-        const double* P = &t.poses[12 * size_t(s)];
-        for (int r = 0; r < 3; ++r) out << P[3 + 3 * r] << "," << P[4 + 3 * r] << "," << P[5 + 3 * r] << "," << P[r] << ",";
-        out << "0,0,0,1\n";
+    std::cerr << "Computing VO" << std::endl;
+    for (unsigned k1 = 0; k1 + window <= t.num_states; ++k1) {
+        const unsigned k2 = k1 + window;
+        if (ransac)
+            compute_initial_guess(t.obs, t.intr, t.num_states, k1, k2, 4.0, false, t.poses, t.points, t.initialized,
+                                  [](unsigned, unsigned, const double*, unsigned) {});    // :127
+        else
+            constant_pose_guess(t, k1, k2);
+        solveWindow(t, k1, k2, max_iters);                                                  // :128
+        std::fill(t.initialized.begin(), t.initialized.end(), 0);                           // reset_points, :130
     }
+    write_poses_csv(file_stem(filename) + "_poses.csv", t.poses, t.num_states);
     return EXIT_SUCCESS;
 }

@@ -289,3 +289,59 @@ def write_track_csv(track, path):
         f.write(",".join(repr(float(v)) for v in T0.reshape(-1)) + "\n")
         for k, j, z in zip(track["obs_cam"], track["obs_pt"], track["uvd"]):
             f.write(f"{int(k)},{int(j)},{z[0]!r},{z[1]!r},{z[2]!r}\n".replace("np.float64(", "").replace(")", ""))
+
+
+def _fmt(values):
+    return ",".join(repr(float(v)) for v in values)
+
+
+def _first_pose_row(track):
+    T0 = np.eye(4)
+    T0[:3, :3] = track["poses_gt"][0, 3:].reshape(3, 3)
+    T0[:3, 3] = track["poses_gt"][0, :3]
+    return _fmt(T0.reshape(-1))
+
+
+def write_sun_csvs(track, track_path, ref_sun_path, obs_sun_path):
+    """The three files of dataset_vo_sun (dataset_problem_sun.cpp:33-175): track rows
+    `k,j,u,v,d,c00..c22` (no variance line), ephemeris `k,e,n,u`, observed sun
+    `k,x,y,z,c00,c01,c10,c11`.  Covariances are the inverse squares of the stiffness matrices."""
+    c = track["cam"]
+    W = np.asarray(track["W"])
+    W = np.tile(W.reshape(1, 9), (track["obs_cam"].size, 1)) if W.size == 9 else W.reshape(-1, 9)
+    with open(track_path, "w") as f:
+        f.write(f"{track['n_poses']},{track['n_points']}\n")
+        f.write(_fmt(c[k] for k in ("fu", "fv", "cu", "cv", "b")) + "\n")
+        f.write(_first_pose_row(track) + "\n")
+        for k, j, z, w in zip(track["obs_cam"], track["obs_pt"], track["uvd"], W):
+            Wm = w.reshape(3, 3)
+            cov = np.linalg.inv(Wm @ Wm)
+            cov = 0.5 * (cov + cov.T)
+            f.write(f"{int(k)},{int(j)},{_fmt(z)},{_fmt(cov.reshape(-1))}\n")
+    with open(ref_sun_path, "w") as f:
+        for k, e in zip(track["sun_cam"], track["sun_ref_g"]):
+            f.write(f"{int(k)},{_fmt(e)}\n")
+    with open(obs_sun_path, "w") as f:
+        for k, o, w in zip(track["sun_cam"], track["sun_obs_c"], track["sun_W"]):
+            Wm = w.reshape(2, 2)
+            cov = np.linalg.inv(Wm @ Wm)
+            f.write(f"{int(k)},{_fmt(o)},{_fmt(cov.reshape(-1))}\n")
+
+
+def write_phong_csv(track, path, int_var=1e-4, normal_var=1e-4):
+    """dataset_ba_phong's input (dataset_problem_phong.cpp:29-117): counts, intrinsics, the seven
+    variances, the initial light position / direction, the first pose, then rows
+    `t,j,mat_id,u,v,d,I,nx,ny,nz` grouped by timestamp."""
+    c = track["cam"]
+    W = np.asarray(track["W"]).reshape(-1)[:9].reshape(3, 3)
+    var = 1.0 / np.diag(W) ** 2
+    n_mat = track["phong"].shape[0]
+    with open(path, "w") as f:
+        f.write(f"{track['n_poses']},{track['n_points']},{n_mat}\n")
+        f.write(_fmt(c[k] for k in ("fu", "fv", "cu", "cv", "b")) + "\n")
+        f.write(_fmt(list(var) + [normal_var] * 3 + [int_var]) + "\n")
+        f.write(_fmt(track["light"]) + "\n")
+        f.write(_first_pose_row(track) + "\n")
+        for k, j, z, inten, nobs in zip(track["obs_cam"], track["obs_pt"], track["uvd"], track["intensity"],
+                                        track["normal_obs"]):
+            f.write(f"{float(k)!r},{int(j)},{int(track['material_id'][j])},{_fmt(z)},{float(inten)!r},{_fmt(nobs)}\n")

@@ -278,8 +278,8 @@ def test_lm_both_schur_paths(product, path):
 
 def test_cpp_driver_dataset_vo(product, tmp_path):
     """The C++ host mirror (host/cslam_problem.hpp) and the restated dataset_vo driver run the
-    reference's CSV format through the C ABI: full batch from a constant-pose initial guess must
-    land on the ground-truth track (noise-limited)."""
+    reference's CSV format through the C ABI, here from the front-end-free constant-pose start
+    (--init constant): sliding windows must land on the ground-truth track (noise-limited)."""
     import os
     import subprocess
     from ceres_slam_b200 import build as b
@@ -299,12 +299,12 @@ def test_cpp_driver_dataset_vo(product, tmp_path):
     # dataset_vo --window 2: 39 sequential windows, each one launch of the window kernel; every
     # window converges from the constant-pose guess and the chained track stays near ground truth
     # (drift-limited: the oracle run of the same sequence ends at 0.098 m / 0.005)
-    text, T = run("--window", "2", "--max-iters", "100")
+    text, T = run("--window", "2", "--max-iters", "100", "--init", "constant")
     assert text.count("Termination: CONVERGENCE") == 39, text
     assert np.abs(T[:, :3, 3] - gt_t).max() < 0.15
     assert np.abs(T[:, :3, :3] - gt_R).max() < 0.01
     # a longer window (5 poses, 4 free): still one CTA per window, dense 24x24 reduced system
-    text, T = run("--window", "5", "--max-iters", "100")
+    text, T = run("--window", "5", "--max-iters", "100", "--init", "constant")
     # (a few 5-pose windows need more than 100 iterations from the constant-pose guess)
     assert text.count("cslam_b200 Report") == 36 and text.count("Termination: CONVERGENCE") >= 30, text
     assert np.abs(T[:, :3, 3] - gt_t).max() < 0.5
@@ -515,3 +515,98 @@ def test_lm_phong_line_search_contracts(product):
     assert np.array_equal(lg[:, 9], lo[:, 9])
     for k in ("poses", "points", "normals", "phong", "textures", "light"):
         assert rel_err(stg[k], sto[k]) < LM_TOL, k
+
+
+def _run_driver(name, args, tmp_path, timeout=600):
+    import subprocess
+    from ceres_slam_b200 import build as b
+    exe = b.build_host_driver(name)
+    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout
+
+
+def _poses_csv(path, n):
+    T = np.loadtxt(path, delimiter=",", skiprows=1).reshape(-1, 4, 4)
+    assert T.shape[0] == n
+    return T
+
+
+def _steady_track(n_poses, seed, **kw):
+    """A track whose every consecutive pose pair shares enough points for the RANSAC front end: the
+    generator's ramp-up (first / last `track_len` frames) is cut off by re-basing the states."""
+    tr = syn.make_track(n_poses + 18, 15, 10, seed=seed, pix_sigma=0.25, **kw)
+    keep = (tr["obs_cam"] >= 9) & (tr["obs_cam"] < 9 + n_poses)
+    for k in ("obs_cam", "obs_pt", "uvd"):
+        tr[k] = np.ascontiguousarray(tr[k][keep])
+    if np.asarray(tr["W"]).size != 9:
+        tr["W"] = np.ascontiguousarray(tr["W"][keep])
+    tr["obs_cam"] = (tr["obs_cam"] - 9).astype(np.uint32)
+    for k in ("poses", "poses_gt"):
+        tr[k] = np.ascontiguousarray(tr[k][9:9 + n_poses])
+    tr["constant"] = tr["constant"][:n_poses].copy()
+    tr["n_poses"] = n_poses
+    return tr
+
+
+def test_cpp_driver_dataset_vo_ransac(product, tmp_path):
+    """dataset_vo with the reference's own front end: per window the GPU RANSAC initial guess
+    (compute_initial_guess), residual blocks for the inlier points only, LM on the window."""
+    import os
+    tr = _steady_track(30, seed=17)
+    csv = os.path.join(tmp_path, "track.csv")
+    syn.write_track_csv(tr, csv)
+    gt_t, gt_R = tr["poses_gt"][:, :3], tr["poses_gt"][:, 3:].reshape(-1, 3, 3)
+    text = _run_driver("dataset_vo_b200", [csv, "--window", "2", "--max-iters", "100"], tmp_path)
+    assert text.count("Termination: CONVERGENCE") == 29, text
+    T = _poses_csv(os.path.join(tmp_path, "track_poses.csv"), 30)
+    assert np.abs(T[:, :3, 3] - gt_t).max() < 0.1
+    assert np.abs(T[:, :3, :3] - gt_R).max() < 0.01
+    # full batch: one RANSAC launch over all 29 pairs, then one bundle adjustment
+    text = _run_driver("dataset_vo_b200", [csv, "--max-iters", "50"], tmp_path)
+    T = _poses_csv(os.path.join(tmp_path, "track_poses.csv"), 30)
+    assert np.abs(T[:, :3, 3] - gt_t).max() < 0.05
+    assert np.abs(T[:, :3, :3] - gt_R).max() < 0.005
+
+
+def test_cpp_driver_dataset_vo_sun(product, tmp_path):
+    """dataset_vo_sun restated: per-observation stereo covariances, sun blocks with Huber loss, pose
+    prior from the previous window's marginal covariance (cslam_covariance_block), both passes."""
+    import os
+    tr = syn.add_sun(_steady_track(25, seed=23, per_obs_W=True), sigma_deg=1.0)
+    paths = [os.path.join(tmp_path, n) for n in ("track.csv", "sun_ref.csv", "sun_obs.csv")]
+    syn.write_sun_csvs(tr, *paths)
+    text = _run_driver("dataset_vo_sun_b200", paths + ["--window", "2", "--huber-param", "1.0", "--max-iters", "100"], tmp_path)
+    assert text.count("cslam_b200 Report") == 48 and "Covariance computation failed" not in text, text
+    gt_t, gt_R = tr["poses_gt"][:, :3], tr["poses_gt"][:, 3:].reshape(-1, 3, 3)
+    Tv = _poses_csv(os.path.join(tmp_path, "track_poses.csv"), 25)          # pass 1: VO only
+    Ts = _poses_csv(os.path.join(tmp_path, "track_obs_poses.csv"), 25)      # pass 2: with the sun sensor
+    for T in (Tv, Ts):
+        assert np.abs(T[:, :3, 3] - gt_t).max() < 0.15
+        assert np.abs(T[:, :3, :3] - gt_R).max() < 0.02
+    assert np.abs(Ts - Tv).max() > 1e-6                                      # the sun blocks act
+
+
+def test_cpp_driver_dataset_ba_phong(product, tmp_path):
+    """dataset_ba_phong restated: RANSAC front end (positions, normals, materials of the vertices),
+    then the joint lighting solve from the reference's own start (materials (0, 0, 1), textures the
+    per-material median intensity)."""
+    import os
+    base = _steady_track(20, seed=29)
+    tr = syn.add_phong(base, shared_textures=True)
+    csv = os.path.join(tmp_path, "scene.csv")
+    syn.write_phong_csv(tr, csv)
+    text = _run_driver("dataset_ba_phong_b200", [csv, "--max-iters", "40", "--material-by-observation"], tmp_path)
+    assert "Termination: FAILURE" not in text and text.count("cslam_b200 Report") == 1, text
+    T = _poses_csv(os.path.join(tmp_path, "scene_poses.csv"), 20)
+    assert np.abs(T[:, :3, 3] - tr["poses_gt"][:, :3]).max() < 0.05
+    light = np.loadtxt(os.path.join(tmp_path, "scene_lights.csv"), delimiter=",", skiprows=1)
+    assert np.abs(light - tr["light_gt"]).max() < 0.15
+    m = np.loadtxt(os.path.join(tmp_path, "scene_map.csv"), delimiter=",", skiprows=1)
+    j = m[:, 0].astype(int)
+    assert j.size > 100
+    assert np.median(np.linalg.norm(m[:, 1:4] - tr["points_gt"][j], axis=1)) < 0.05
+    assert np.median(np.abs(m[:, 10] - tr["tex_shared_gt"][tr["material_id"][j]])) < 0.02
+    assert np.all(m[:, 8] >= 0) and np.all(m[:, 8] <= 1) and np.all(m[:, 9] >= 1)     # the box
+    # the reference's material indexing quirk (inlier index instead of observation) also runs
+    _run_driver("dataset_ba_phong_b200", [csv, "--max-iters", "5", "--nolight"], tmp_path)
