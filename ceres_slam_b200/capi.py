@@ -51,6 +51,7 @@ class Options(C.Structure):
         ("schur_path", C.c_int),
         ("band_leaves", C.c_int),
         ("window_path", C.c_int),
+        ("band_separator_solver", C.c_int),
         ("line_search_sufficient_function_decrease", C.c_double),
     ]
 

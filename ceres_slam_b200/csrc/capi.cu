@@ -68,6 +68,7 @@ void cslam_options_init(cslam_options* o) {
     o->schur_path = 0;
     o->band_leaves = 0;
     o->window_path = 0;
+    o->band_separator_solver = 0;
     o->line_search_sufficient_function_decrease = 1e-4;
 }
 

@@ -706,9 +706,14 @@ void Engine::plan_band_solver() {
     if (w == 0) w = 1;  // a single camera: treat as bandwidth 1 (absent blocks read as zero)
     const int n = n_free;
     const int W = band_storage_width(w);  // separators and the shared-memory window use this width
-    // leaves cost ~1.2 us per block row, the separator chain ~1.5 us per separator row
-    int P = opt.band_leaves > 0 ? opt.band_leaves : int(std::lround(std::sqrt(0.8 * double(n) / W)));
-    P = std::min(P, 148);
+    // separator system: block cyclic reduction (log depth) once there are enough separators for it to
+    // beat the sequential band factorisation
+    band_sep = opt.band_separator_solver == 0 ? (n >= 400 * W ? 2 : 1) : opt.band_separator_solver;
+    // leaves cost ~3 us per block row; the separator chain ~2.5 us per separator row when factored
+    // as a band on one CTA, ~45 us per level of the cyclic reduction
+    int P = opt.band_leaves > 0 ? opt.band_leaves
+                                : (band_sep == 2 ? 148 : int(std::lround(std::sqrt(0.8 * double(n) / W))));
+    P = std::min(P, band_sep == 2 ? 444 : 148);
     P = std::min(P, n / (4 * W));
     P = std::max(P, (n + 3499) / 3500);
     P = std::max(P, 1);
@@ -781,6 +786,7 @@ void Engine::solve_reduced_on(BandSet& bs, const double* rhs, double* y) {
     V.w = band_w;
     V.P = band_P;
     V.m = band_m;
+    V.sep_solver = band_sep;
     V.band_idx = d_band_idx.p;
     V.S = d_S;
     V.rhs = rhs;
@@ -1106,6 +1112,7 @@ void Engine::solve_reduced(const double* rhs, double* y) {
         V.w = band_w;
         V.P = band_P;
         V.m = band_m;
+        V.sep_solver = band_sep;
         V.band_idx = d_band_idx.p;
         V.S = d_S;
         V.rhs = rhs;

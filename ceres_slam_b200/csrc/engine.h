@@ -83,6 +83,7 @@ struct GroupView {
 constexpr int kBandWmax = 12;    // widest half-bandwidth (in 6x6 blocks) the direct solver takes
 struct BandView {
     int n, w, P, m;              // block rows, half-bandwidth, leaves, rows per leaf
+    int sep_solver;              // separator system: 1 = banded Cholesky on one CTA, 2 = block cyclic reduction
     const int* band_idx;         // [n][w+1] index of block (a, a+d) in the upper block-CSR, or -1
     const double* S;             // block values (diagonal blocks full symmetric)
     const double* rhs;           // [6 n]
@@ -287,7 +288,7 @@ class Engine {
     DBuf<double> d_yp, d_pr, d_pz, d_pp, d_pq, d_yl, d_pp2, d_prec;
     DBuf<double> d_pscal;
     // banded direct solver (linear_solver == 0 and S block-banded)
-    int band_w = 0, band_P = 0, band_m = 0;
+    int band_w = 0, band_P = 0, band_m = 0, band_sep = 1;
     bool band_active = false;
     DBuf<int> d_band_idx, d_band_fail;
     DBuf<double> d_Lbuf, d_Xbuf, d_Ta, d_Ca, d_fa, d_Tb, d_fb, d_T2, d_rhs2, d_L2, d_X2, d_y2;

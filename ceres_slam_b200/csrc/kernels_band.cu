@@ -501,6 +501,252 @@ void run_backsub(cudaStream_t s, const BandView& V, const double* ysep) {
     CSLAM_CUDA(cudaGetLastError());
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Separator system by block cyclic reduction.
+//
+// The separators form a block-TRIDIAGONAL system with b x b blocks, b = 6 W: separator q couples
+// only to q-1 and q+1 (through the leaf between them): D_q = Ta[q] - Tb[q], coupling
+// E(q, q-1) = Ca[q], right-hand side fa[q] - fb[q].  Factoring it as a band (above) is a chain of
+// (P-1) W dependent block steps on ONE CTA; cyclic reduction eliminates every other separator at
+// once — log2(P-1) levels of independent b x b factorisations — so the band can be cut into many
+// more, shorter leaves.  Level with stride s, "odd" rows i = s, 3s, 5s, ...:
+//     D_i = L L^T,  A = L^-1 E(i, i-s),  Bm = L^-1 E(i+s, i)^T,  g = L^-1 f_i,  Li = L^-1
+// "even" rows i = 0, 2s, 4s, ...:
+//     D_i -= Bm_{i-s}^T Bm_{i-s} + A_{i+s}^T A_{i+s},  f_i -= Bm_{i-s}^T g_{i-s} + A_{i+s}^T g_{i+s},
+//     E(i, i-2s) = -Bm_{i-s}^T A_{i-s}
+// and back down:  y_i = Li^T (g - A y_{i-s} - Bm y_{i+s}).
+// Storage reuses the band path's buffers: D in place of Ta, E in place of Ca, f = rhs2, A | Bm = T2,
+// Li = L2, g = X2, y = y2.
+// ---------------------------------------------------------------------------------------------
+struct BcrView {
+    int N, b;
+    double *D, *E, *f;         // [N][b*b], [N][b*b] (E[i] = coupling (i, i - s) of the current level), [N][b]
+    double *A, *Bm, *Li, *g;   // per eliminated row
+    double* y;                 // [N][b]
+    int* fail;
+};
+
+__global__ void bcr_init_kernel(BcrView R, const double* __restrict__ Tb, const double* __restrict__ fa,
+                                const double* __restrict__ fb) {
+    const long long bb = (long long)R.b * R.b, total = (long long)R.N * bb;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total + (long long)R.N * R.b;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (idx < total)
+            R.D[idx] -= Tb[idx];
+        else
+            R.f[idx - total] = fa[idx - total] - fb[idx - total];
+    }
+}
+
+// rows i = first + blockIdx.x * step; left / right neighbours at distance s (absent when out of range
+// or when s == 0: the last row standing).  Right-looking Cholesky of D_i with the border
+// [E_left | E_right^T | f | I] riding along; nothing is scaled in place (step k applies
+// M[r][c] -= M[r][k] M[c][k] / d), so a step is ONE barrier; row k of the border, scaled by
+// 1/sqrt(d), goes straight to the outputs A | Bm | g | Li.  32 x 32 threads: rows x columns.
+constexpr int BCR_T = 1024;
+__global__ void __launch_bounds__(BCR_T) bcr_odd_kernel(BcrView R, int first, int step, int s) {
+    extern __shared__ __align__(16) double smem_bcr[];
+    __shared__ int s_ok;
+    const int b = R.b, ld = 4 * b + 1, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int i = first + blockIdx.x * step;
+    const bool has_l = s > 0 && i - s >= 0, has_r = s > 0 && i + s < R.N;
+    const long long bb = (long long)b * b;
+    double* M = smem_bcr;  // [b][ld]: D | E_left | E_right^T | f | I
+    if (*R.fail) return;
+    const double* Di = R.D + i * bb;
+    const double* El = R.E + i * bb;
+    const double* Er = R.E + (long long)(i + s) * bb;
+    for (int r = ty; r < b; r += 32) {
+        double* Mr = M + r * ld;
+        for (int c = tx; c < b; c += 32) {
+            Mr[c] = Di[r * b + c];
+            Mr[b + c] = has_l ? El[r * b + c] : 0.0;
+            Mr[3 * b + 1 + c] = (c == r) ? 1.0 : 0.0;
+        }
+        if (tx == 0) Mr[3 * b] = R.f[(long long)i * b + r];
+    }
+    // E_right^T: read E(i+s, i) row-wise (coalesced), store transposed
+    for (int r = ty; r < b; r += 32)
+        for (int c = tx; c < b; c += 32) M[c * ld + 2 * b + r] = has_r ? Er[r * b + c] : 0.0;
+    __shared__ double s_piv[2][2];  // [parity][1/d, 1/sqrt(d)] of the pivot, written one step ahead
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+    if (tid == 0) {
+        const double d = M[0];
+        double inv = rsqrt(d);
+        inv = inv * (1.5 - 0.5 * d * inv * inv);  // one Newton step: full double precision
+        s_piv[0][0] = 1.0 / d;
+        s_piv[0][1] = inv;
+        if (!(d > 0.0) || !(d < 1.7976931348623157e308)) s_ok = 0;
+    }
+    __syncthreads();
+    double* Ai = R.A + i * bb;
+    double* Bi = R.Bm + i * bb;
+    double* Li = R.Li + i * bb;
+    for (int k = 0; k < b; ++k) {
+        if (!s_ok) break;  // uniform: written before the last barrier
+        const double w = s_piv[k & 1][0], inv = s_piv[k & 1][1];
+        const double* Mk = M + k * ld;
+        // outputs: row k of the border, scaled
+        if (ty == 31) {
+            for (int c = tx; c < b; c += 32) {
+                Ai[k * b + c] = Mk[b + c] * inv;
+                Bi[k * b + c] = Mk[2 * b + c] * inv;
+                Li[k * b + c] = Mk[3 * b + 1 + c] * inv;
+            }
+            if (tx == 0) R.g[(long long)i * b + k] = Mk[3 * b] * inv;
+        }
+        // trailing update
+        for (int r = k + 1 + ty; r < b; r += 32) {
+            double* Mr = M + r * ld;
+            const double lr = Mr[k] * w;
+            int c = k + 1 + tx;
+            for (; c < b; c += 32) Mr[c] -= lr * M[c * ld + k];
+            for (; c < ld; c += 32) Mr[c] -= lr * Mk[c];
+            if (r == k + 1 && tx == 0) {
+                // the next pivot is final now: its reciprocals for the step after the barrier
+                const double d = Mr[k + 1];
+                double iv = rsqrt(d);
+                iv = iv * (1.5 - 0.5 * d * iv * iv);
+                s_piv[(k + 1) & 1][0] = 1.0 / d;
+                s_piv[(k + 1) & 1][1] = iv;
+                if (!(d > 0.0) || !(d < 1.7976931348623157e308)) s_ok = 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (!s_ok && tid == 0) *R.fail = 1;
+}
+
+// rows i = blockIdx.x * 2s
+__global__ void __launch_bounds__(BCR_T) bcr_even_kernel(BcrView R, int s) {
+    extern __shared__ __align__(16) double smem_bcr[];
+    const int b = R.b, tid = threadIdx.x;
+    const int i = blockIdx.x * 2 * s;
+    const bool has_l = i - s >= 0, has_r = i + s < R.N, has_ll = i - 2 * s >= 0;
+    const long long bb = (long long)b * b;
+    if (*R.fail) return;
+    double* X1 = smem_bcr;          // Bm of the left odd neighbour
+    double* X2 = X1 + b * b;        // A of the left odd neighbour
+    double* X3 = X2 + b * b;        // A of the right odd neighbour
+    double* gl = X3 + b * b;
+    double* gr = gl + b;
+    for (int idx = tid; idx < b * b; idx += BCR_T) {
+        X1[idx] = has_l ? R.Bm[(long long)(i - s) * bb + idx] : 0.0;
+        X2[idx] = has_l ? R.A[(long long)(i - s) * bb + idx] : 0.0;
+        X3[idx] = has_r ? R.A[(long long)(i + s) * bb + idx] : 0.0;
+    }
+    for (int r = tid; r < b; r += BCR_T) {
+        gl[r] = has_l ? R.g[(long long)(i - s) * b + r] : 0.0;
+        gr[r] = has_r ? R.g[(long long)(i + s) * b + r] : 0.0;
+    }
+    __syncthreads();
+    double* Di = R.D + i * bb;
+    double* Ei = R.E + i * bb;
+    for (int idx = tid; idx < b * b; idx += BCR_T) {
+        const int r = idx / b, c = idx - r * b;
+        double dd = 0.0, ee = 0.0;
+#pragma unroll 6
+        for (int k = 0; k < b; ++k) {
+            const double x1 = X1[k * b + r];
+            dd += x1 * X1[k * b + c] + X3[k * b + r] * X3[k * b + c];
+            ee += x1 * X2[k * b + c];
+        }
+        Di[idx] -= dd;
+        if (has_ll) Ei[idx] = -ee;
+    }
+    for (int r = tid; r < b; r += BCR_T) {
+        double ff = 0.0;
+        for (int k = 0; k < b; ++k) ff += X1[k * b + r] * gl[k] + X3[k * b + r] * gr[k];
+        R.f[(long long)i * b + r] -= ff;
+    }
+}
+
+// y_i = Li^T (g - A y_{i-s} - Bm y_{i+s}): a warp per row for the two products (lanes along the row:
+// coalesced), then a thread per entry for the transposed triangular product
+__global__ void __launch_bounds__(256) bcr_backsub_kernel(BcrView R, int first, int step, int s) {
+    extern __shared__ __align__(16) double smem_bcr[];
+    const int b = R.b, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int i = first + blockIdx.x * step;
+    const bool has_l = s > 0 && i - s >= 0, has_r = s > 0 && i + s < R.N;
+    const long long bb = (long long)b * b;
+    if (*R.fail) return;
+    double* t = smem_bcr;
+    double* yl = t + b;
+    double* yr = yl + b;
+    for (int r = tid; r < b; r += 256) {
+        yl[r] = has_l ? R.y[(long long)(i - s) * b + r] : 0.0;
+        yr[r] = has_r ? R.y[(long long)(i + s) * b + r] : 0.0;
+    }
+    __syncthreads();
+    const double* Ai = R.A + i * bb;
+    const double* Bi = R.Bm + i * bb;
+    for (int r = wib; r < b; r += 8) {
+        double v = 0.0;
+        for (int k = lane; k < b; k += 32) v += Ai[r * b + k] * yl[k] + Bi[r * b + k] * yr[k];
+        v = warp_sum(v);
+        if (lane == 0) t[r] = R.g[(long long)i * b + r] - v;
+    }
+    __syncthreads();
+    const double* Li = R.Li + i * bb;
+    for (int r = tid; r < b; r += 256) {
+        double v = 0.0;
+#pragma unroll 6
+        for (int k = r; k < b; ++k) v += Li[k * b + r] * t[k];  // (L^-T t)_r, L^-1 lower triangular
+        R.y[(long long)i * b + r] = v;
+    }
+}
+
+static int bcr_solve(cudaStream_t st, const BandView& V, const BandScratch& K, int W) {
+    BcrView R;
+    R.N = V.P - 1;
+    R.b = 6 * W;
+    const long long bb = (long long)R.b * R.b;
+    R.D = V.Ta;
+    R.E = V.Ca;
+    R.f = K.rhs2;
+    R.A = K.T2;
+    R.Bm = K.T2 + R.N * bb;
+    R.Li = K.L2;
+    R.g = K.X2;
+    R.y = K.y2;
+    R.fail = V.fail;
+    const size_t smem_odd = sizeof(double) * size_t(R.b) * (4 * R.b + 1);
+    const size_t smem_even = sizeof(double) * (3 * size_t(bb) + 2 * R.b);
+    static size_t attr_odd = 0, attr_even = 0;
+    if (smem_odd > attr_odd) {
+        CSLAM_CUDA(cudaFuncSetAttribute(bcr_odd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_odd)));
+        attr_odd = smem_odd;
+    }
+    if (smem_even > attr_even) {
+        CSLAM_CUDA(cudaFuncSetAttribute(bcr_even_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_even)));
+        attr_even = smem_even;
+    }
+    int launched = 0;
+    const long long init_n = R.N * bb + (long long)R.N * R.b;
+    bcr_init_kernel<<<int(std::min<long long>((init_n + 255) / 256, 4 * 148)), 256, 0, st>>>(R, V.Tb, V.fa, V.fb);
+    ++launched;
+    int levels[32], nl = 0;
+    for (int s = 1; s < R.N; s *= 2) {
+        const int n_odd = (R.N - s - 1) / (2 * s) + 1, n_even = (R.N - 1) / (2 * s) + 1;
+        bcr_odd_kernel<<<n_odd, BCR_T, smem_odd, st>>>(R, s, 2 * s, s);
+        bcr_even_kernel<<<n_even, BCR_T, smem_even, st>>>(R, s);
+        launched += 2;
+        levels[nl++] = s;
+    }
+    bcr_odd_kernel<<<1, BCR_T, smem_odd, st>>>(R, 0, 1, 0);  // the last row standing
+    bcr_backsub_kernel<<<1, 256, 3 * R.b * sizeof(double), st>>>(R, 0, 1, 0);
+    launched += 2;
+    for (int l = nl - 1; l >= 0; --l) {
+        const int s = levels[l], n_odd = (R.N - s - 1) / (2 * s) + 1;
+        bcr_backsub_kernel<<<n_odd, 256, 3 * R.b * sizeof(double), st>>>(R, s, 2 * s, s);
+        ++launched;
+    }
+    CSLAM_CUDA(cudaGetLastError());
+    return launched;
+}
+
 // One solve with storage width W (>= true half-bandwidth V.w).
 template <int W>
 int band_solve_w(cudaStream_t s, const BandView& V, const BandScratch& K) {
@@ -511,6 +757,11 @@ int band_solve_w(cudaStream_t s, const BandView& V, const BandScratch& K) {
         return 2;
     }
     run_leaf<W, true>(s, V);
+    if (V.sep_solver == 2) {
+        const int launched = bcr_solve(s, V, K, W);
+        run_backsub<W, true>(s, V, K.y2);
+        return 2 + launched;
+    }
     const int n2 = (V.P - 1) * W;
     band_assemble_kernel<W><<<std::min(4 * 148, (n2 * (W2 + 1) * 36 + 255) / 256), 256, 0, s>>>(V, K.T2, K.rhs2);
     CSLAM_CUDA(cudaGetLastError());

@@ -65,6 +65,8 @@ typedef struct cslam_options {
                                into (0 = auto) */
     int window_path;        /* small problems (<= 8 poses, exact solve): 0 = auto (one-CTA-per-window kernel
                                with the LM loop on the device), 1 = never, 2 = require it */
+    int band_separator_solver; /* exact solve of a banded reduced system, separator system between the
+                               leaves: 0 = auto, 1 = banded Cholesky on one CTA, 2 = block cyclic reduction */
     double line_search_sufficient_function_decrease; /* 1e-4: Armijo constant of the line search a
                                bounded problem runs along the trust-region step */
 } cslam_options;

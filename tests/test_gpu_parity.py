@@ -610,3 +610,18 @@ def test_cpp_driver_dataset_ba_phong(product, tmp_path):
     assert np.all(m[:, 8] >= 0) and np.all(m[:, 8] <= 1) and np.all(m[:, 9] >= 1)     # the box
     # the reference's material indexing quirk (inlier index instead of observation) also runs
     _run_driver("dataset_ba_phong_b200", [csv, "--max-iters", "5", "--nolight"], tmp_path)
+
+
+@pytest.mark.parametrize("shape,leaves", [((100, 15, 10), 5), ((300, 6, 4), 25), ((300, 6, 4), 2), ((260, 8, 7), 9),
+                                          ((400, 5, 4), 33)])
+def test_band_solver_cyclic_reduction(product, shape, leaves):
+    """Exact reduced solve with the separator system factored by block cyclic reduction
+    (band_separator_solver = 2) for 1 .. 32 separators (odd and even counts, powers of two and not):
+    the LM trajectory must match the oracle's exact solve and the sequential separator path."""
+    tr = syn.make_track(*shape, seed=33)
+    kw = dict(FIXED, max_num_iterations=4, window_path=1)
+    g2, o = solve_pair(tr, 4, band_separator_solver=2, band_leaves=leaves, window_path=1)
+    check_lm(g2, o)
+    p1, poses1, points1 = syn.build_problem(tr, backend="b200", band_separator_solver=1, band_leaves=leaves, **kw)
+    p1.solve()
+    assert rel_err(g2[2], poses1) < 1e-9 and rel_err(g2[3], points1) < 1e-9
