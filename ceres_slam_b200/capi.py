@@ -52,6 +52,8 @@ class Options(C.Structure):
         ("band_leaves", C.c_int),
         ("window_path", C.c_int),
         ("band_separator_solver", C.c_int),
+        ("trust_region_strategy", C.c_int),
+        ("dogleg_type", C.c_int),
         ("line_search_sufficient_function_decrease", C.c_double),
     ]
 
@@ -144,6 +146,8 @@ _PRODUCT_ONLY = {
     "attach_comm": (C.c_int, [_h, C.c_int, C.c_int, _u8p]),
 }
 _ORACLE_ONLY = {
+    "poly_root_real_parts": (C.c_int, [_dp, C.c_int, _dp]),
+    "dogleg_boundary_minimum": (C.c_int, [_dp, _dp, C.c_double, _dp]),
     "ransac_draws": (None, [C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p]),
     "kabsch": (None, [C.c_uint32, _dp, _dp, _dp]),
     "so3_exp": (None, [_dp, _dp]),

@@ -69,6 +69,8 @@ void cslam_options_init(cslam_options* o) {
     o->band_leaves = 0;
     o->window_path = 0;
     o->band_separator_solver = 0;
+    o->trust_region_strategy = 0;
+    o->dogleg_type = 1;
     o->line_search_sufficient_function_decrease = 1e-4;
 }
 

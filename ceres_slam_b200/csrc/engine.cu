@@ -1029,7 +1029,7 @@ void Engine::allreduce_small(double* dev, int n) {
 // One Schur build at (x, radius): S, rhs, gradient, cost — leaves them in d_red
 // -------------------------------------------------------------------------------------------------
 void Engine::schur_pass() {
-    const LmDiag dg{1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+    const LmDiag dg = current_diag();
     DevView v = view(d_poses.p, d_points.p);
     prof_begin(CSLAM_K_SCHUR);
     d_red.zero(stream);
@@ -1222,12 +1222,95 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
     prof_end(CSLAM_K_BACKSUB);
 }
 
+// DoglegStrategy::ComputeStep + the candidate evaluation of the trust-region loop.  Per Jacobian: the
+// Gauss-Newton solve (J^T J + mu D^2) y = J^T r through the same Schur path as LM (mu in place of
+// 1/radius, raised tenfold while the factorisation fails), the back-substitution for the landmark
+// part, then ONE pass for the eight inner products the strategy needs.  Per trial radius (also
+// after a rejected step, when everything above is reused): two coefficients on the host, the
+// combined step, the candidate and its cost.
+void Engine::dogleg_step(int* lin_iters, bool* valid, double* sc2) {
+    DevView v = view(d_poses.p, d_points.p);
+    *lin_iters = 0;
+    if (!dl.reuse) {
+        bool solved = false;
+        while (dl.mu < 1.0) {
+            if (!lm.have_system) schur_pass();
+            double sc1[SC_COUNT];
+            read_scalars(d_scal, sc1, SC_COUNT);
+            int it = 0;
+            bool ok = sc1[SC_INVALID] == 0.0;
+            if (ok) run_pcg(&it, &ok);
+            if (ok) {
+                solved = true;
+                break;
+            }
+            dl.mu *= 10.0;
+            lm.have_system = false;
+        }
+        if (!solved) {
+            *valid = false;
+            return;
+        }
+        *lin_iters = 1;
+        const LmDiag dg = current_diag();
+        prof_begin(CSLAM_K_BACKSUB);
+        // landmark part of y (the kernel's candidate / model outputs are not used here)
+        d_scal2.zero(stream);
+        launch_pose_plus(stream, v, d_yp.p, d_poses_cand.p, d_scal2.p, rank == 0);
+        launch_backsub(stream, v, 0, n_lm, dg, d_yp.p, d_poses_cand.p, d_points_cand.p, d_yl.p, d_scal2.p);
+        d_dsums.zero(stream);
+        launch_dogleg_products(stream, v, 0, n_lm, dg, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_gp,
+                               d_diag_p.p, d_yp.p, d_gl.p, d_yl.p, d_diag_l.p, d_dsums.p, rank == 0);
+        prof_end(CSLAM_K_BACKSUB);
+        allreduce_small(d_dsums.p, DG_COUNT);
+        double sm[DG_COUNT];
+        read_scalars(d_dsums.p, sm, DG_COUNT);
+        DoglegModel& m = dl.model;
+        m.G11 = sm[DG_G11], m.G12 = sm[DG_G12], m.G22 = sm[DG_G22];
+        m.JGG = sm[DG_JGG], m.JGY = sm[DG_JGY], m.JYY = sm[DG_JYY], m.JGR = sm[DG_JGR], m.JYR = sm[DG_JYR];
+        bool finite = true;
+        for (double x : sm) finite = finite && std::isfinite(x);
+        if (!finite || !m.prepare(opt.dogleg_type == 1)) {
+            *valid = false;
+            return;
+        }
+        dl.reuse = true;
+    }
+    double c1, c2;
+    if (opt.dogleg_type == 1)
+        dl.model.subspace(lm.radius, &c1, &c2, &dl.step_norm);
+    else
+        dl.model.traditional(lm.radius, &c1, &c2, &dl.step_norm);
+    prof_begin(CSLAM_K_BACKSUB);
+    launch_dogleg_combine(stream, 6ll * n_free, c1, c2, d_gp, d_diag_p.p, d_yp.p, d_Yp.p);
+    launch_dogleg_combine(stream, 3ll * n_lm, c1, c2, d_gl.p, d_diag_l.p, d_yl.p, d_Yl.p);
+    d_scal2.zero(stream);
+    launch_pose_plus(stream, v, d_Yp.p, d_poses_cand.p, d_scal2.p, rank == 0);
+    launch_points_apply(stream, v, 0, n_lm, d_Yl.p, d_poses_cand.p, d_points_cand.p, d_scal2.p);
+    if (rank == 0)
+        launch_camonly_step(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Yp.p, d_poses_cand.p,
+                            d_scal2.p);
+    prof_end(CSLAM_K_BACKSUB);
+    allreduce_small(d_scal2.p, SC_COUNT);
+    read_scalars(d_scal2.p, sc2, SC_COUNT);
+    sc2[SC_MODEL] = dl.model.model_cost_change(c1, c2);
+    *valid = sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // LM loop
 // -------------------------------------------------------------------------------------------------
 void Engine::lm_begin() {
     if (!uploaded) throw std::invalid_argument("lm_begin before upload");
     lm = Lm();
+    dl = Dogleg();
+    if (dogleg()) {
+        if (ph.active) throw NotImplemented("DOGLEG: stereo / sun / prior problems only (the lighting solve runs Levenberg-Marquardt)");
+        d_diag_l.alloc(3 * size_t(std::max(n_lm, 1)), stream);
+        d_Yl.alloc(3 * size_t(std::max(n_lm, 1)), stream);
+        d_Yp.alloc(6 * size_t(std::max(n_free, 1)), stream);
+        d_dsums.alloc(DG_COUNT, stream);
+    }
     log.clear();
     // unit scaling for the initial pass
     launch_fill(stream, d_sc_p.p, d_sc_p.n, 1.0);
@@ -1356,7 +1439,8 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
         int lin_iters = 0;
         bool lin_ok = true;
         bool valid = sc1[SC_INVALID] == 0.0;
-        if (valid) {
+        const bool use_dogleg = dogleg() && !ph.active;
+        if (valid && !use_dogleg) {
             if (ph.active)
                 phong_linear_solve(&lin_iters, &lin_ok);
             else
@@ -1366,8 +1450,12 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
         row.v[7] = lin_iters;
         lm.total_linear += lin_iters;
         double sc2[SC_COUNT] = {0};
-        const LmDiag dg{1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
-        if (valid && ph.active) {
+        const LmDiag dg = current_diag();
+        if (use_dogleg) {
+            dogleg_step(&lin_iters, &valid, sc2);
+            row.v[7] = lin_iters;
+            lm.total_linear += lin_iters;
+        } else if (valid && ph.active) {
             phong_step(dg, sc2);
             if (sc2[SC_NONFINITE] != 0.0) valid = false;
             if (!(sc2[SC_MODEL] > 0.0)) valid = false;
@@ -1397,8 +1485,13 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
                 lm.finished = true;
                 break;
             }
-            lm.radius = lm.radius / lm.decrease_factor;
-            lm.decrease_factor *= 2.0;
+            if (use_dogleg) {
+                dl.mu *= 10.0;  // DoglegStrategy::StepIsInvalid
+                dl.reuse = false;
+            } else {
+                lm.radius = lm.radius / lm.decrease_factor;
+                lm.decrease_factor *= 2.0;
+            }
             lm.have_system = false;
             row.v[6] = lm.radius;
             log.push_back(row);
@@ -1445,9 +1538,20 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
             lm.have_system = false;
             lm.grad_fresh = false;
             row.v[9] = 1;
-            lm.radius = lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.v[5] - 1.0, 3));
-            lm.radius = std::min(opt.max_trust_region_radius, lm.radius);
-            lm.decrease_factor = 2.0;
+            if (use_dogleg) {
+                // DoglegStrategy::StepAccepted
+                if (row.v[5] < 0.25) lm.radius *= 0.5;
+                if (row.v[5] > 0.75) {
+                    lm.radius = std::max(lm.radius, 3.0 * dl.step_norm);
+                    lm.radius = std::min(lm.radius, opt.max_trust_region_radius);
+                }
+                dl.mu = std::max(1e-8, 2.0 * dl.mu / 10.0);
+                dl.reuse = false;
+            } else {
+                lm.radius = lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.v[5] - 1.0, 3));
+                lm.radius = std::min(opt.max_trust_region_radius, lm.radius);
+                lm.decrease_factor = 2.0;
+            }
             lm.se_current = cand_cost;
             lm.se_acc_cand += model_cost_change;
             lm.se_acc_ref += model_cost_change;
@@ -1467,6 +1571,9 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
                 lm.se_reference = lm.se_candidate;
                 lm.se_acc_ref = lm.se_acc_cand;
             }
+        } else if (use_dogleg) {
+            lm.radius *= 0.5;  // DoglegStrategy::StepRejected: the Gauss-Newton and gradient vectors stay valid
+            dl.reuse = true;
         } else {
             lm.radius = lm.radius / lm.decrease_factor;
             lm.decrease_factor *= 2.0;

@@ -9,6 +9,7 @@
 #include "../../include/cslam_b200.h"
 #include "closed_form.h"
 #include "common.cuh"
+#include "dogleg_host.h"
 
 namespace cslam {
 
@@ -369,6 +370,19 @@ class Engine {
         double initial_cost = 0;
         double device_ms = 0;
     } lm;
+
+    // DOGLEG trust-region strategy (opt.trust_region_strategy == 1), stereo / sun / prior problems
+    struct Dogleg {
+        double mu = 1e-8, step_norm = 0;
+        bool reuse = false;
+        DoglegModel model;
+    } dl;
+    DBuf<double> d_diag_l, d_Yp, d_Yl, d_dsums;
+    bool dogleg() const { return opt.trust_region_strategy == 1; }
+    LmDiag current_diag() const {
+        return LmDiag{dogleg() ? dl.mu : 1.0 / lm.radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+    }
+    void dogleg_step(int* lin_iters, bool* valid, double* sc2);
 
     DevView view(const double* poses, const double* points) const;
     void build_structure();

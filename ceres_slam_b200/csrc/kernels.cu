@@ -695,6 +695,153 @@ __global__ void __launch_bounds__(128)
     block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
 }
 
+
+// =============================================================================================
+// DOGLEG — DoglegStrategy of Ceres works in the coordinates step' = D step with
+// D = sqrt(clamp(diag(J^T J))).  Every vector it forms (scaled gradient g' = D^-1 g, Gauss-Newton
+// point gn' = -D y, the Cauchy point, the subspace basis, the final step) is a combination of g' and
+// gn', so the device only has to provide, once per Jacobian, eight sums:
+//   DG_G11 = g'.g'   DG_G12 = g'.gn'   DG_G22 = gn'.gn'
+//   DG_JGG = |J D^-2 g|^2   DG_JGY = (J D^-2 g).(J y)   DG_JYY = |J y|^2   DG_JGR, DG_JYR = their dots with r
+// and then the step Y = -c1 D^-2 g + c2 y for the coefficients the host picks (engine.cu).
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+    dogleg_products_kernel(DevView v, int lm_lo, int lm_hi, LmDiag dg, const double* __restrict__ gp,
+                           const double* __restrict__ diag_p, const double* __restrict__ yp, const double* __restrict__ gl,
+                           const double* __restrict__ yl, double* __restrict__ diag_l_out, double* __restrict__ sums) {
+    __shared__ double s_red[32];
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const long long e1 = e0 + es * v.lm_cnt[j];
+        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
+        const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
+        double d2[3] = {0, 0, 0};
+        ObsEval o;
+        for (long long e = e0; e < e1; e += es) {
+            eval_obs_scaled(v, e, p, sl, o);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) d2[q] += o.Jp[q] * o.Jp[q] + o.Jp[3 + q] * o.Jp[3 + q] + o.Jp[6 + q] * o.Jp[6 + q];
+        }
+        double tg[3], ty[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            d2[q] = fmin(fmax(d2[q], dg.min_diag), dg.max_diag);
+            diag_l_out[3ll * j + q] = d2[q];
+            const double g = gl[3ll * j + q], y = yl[3ll * j + q];
+            tg[q] = g / d2[q];
+            ty[q] = y;
+            acc[0] += g * g / d2[q];
+            acc[1] -= g * y;
+            acc[2] += d2[q] * y * y;
+        }
+        for (long long e = e0; e < e1; e += es) {
+            eval_obs_scaled(v, e, p, sl, o);
+            const double* gpf = o.f >= 0 ? gp + 6ll * o.f : nullptr;
+            const double* dpf = o.f >= 0 ? diag_p + 6ll * o.f : nullptr;
+            const double* ypf = o.f >= 0 ? yp + 6ll * o.f : nullptr;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double jg = o.Jp[3 * k] * tg[0] + o.Jp[3 * k + 1] * tg[1] + o.Jp[3 * k + 2] * tg[2];
+                double jy = o.Jp[3 * k] * ty[0] + o.Jp[3 * k + 1] * ty[1] + o.Jp[3 * k + 2] * ty[2];
+                if (o.f >= 0) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        jg += o.Jc[6 * k + a] * (gpf[a] / dpf[a]);
+                        jy += o.Jc[6 * k + a] * ypf[a];
+                    }
+                }
+                acc[3] += jg * jg;
+                acc[4] += jg * jy;
+                acc[5] += jy * jy;
+                acc[6] += jg * o.r[k];
+                acc[7] += jy * o.r[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) block_atomic_sum(acc[k], &sums[k], s_red);
+}
+
+// camera part of the three inner products and the camera-only blocks' rows (thread per camera,
+// then thread per block)
+__global__ void dogleg_products_cam_kernel(DevView v, const SunBlockData* suns, int n_sun, const PriorBlockData* priors,
+                                           int n_prior, const double* __restrict__ gp, const double* __restrict__ diag_p,
+                                           const double* __restrict__ yp, double* __restrict__ sums) {
+    __shared__ double s_red[32];
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.n_free) {
+        for (int a = 0; a < 6; ++a) {
+            const double g = gp[6ll * i + a], d2 = diag_p[6ll * i + a], y = yp[6ll * i + a];
+            acc[0] += g * g / d2;
+            acc[1] -= g * y;
+            acc[2] += d2 * y * y;
+        }
+    } else if (i - v.n_free < n_sun + n_prior) {
+        double r[6], J[36], cost;
+        int rows, cam;
+        camonly_eval(v, suns, n_sun, priors, i - v.n_free, v.poses, true, r, J, &rows, &cam, &cost);
+        const int f = v.cam_free[cam];
+        if (f >= 0)
+            for (int k = 0; k < rows; ++k) {
+                double jg = 0, jy = 0;
+                for (int a = 0; a < 6; ++a) {
+                    const double js = J[6 * k + a] * v.sc_p[6ll * f + a];
+                    jg += js * (gp[6ll * f + a] / diag_p[6ll * f + a]);
+                    jy += js * yp[6ll * f + a];
+                }
+                acc[3] += jg * jg;
+                acc[4] += jg * jy;
+                acc[5] += jy * jy;
+                acc[6] += jg * r[k];
+                acc[7] += jy * r[k];
+            }
+    }
+    for (int k = 0; k < 8; ++k) block_atomic_sum(acc[k], &sums[k], s_red);
+}
+
+// Y = -c1 g / D^2 + c2 y
+__global__ void dogleg_combine_kernel(long long n, double c1, double c2, const double* __restrict__ g,
+                                      const double* __restrict__ d2, const double* __restrict__ y, double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = -c1 * g[i] / d2[i] + c2 * y[i];
+}
+
+// candidate landmarks p - Y sl and the cost there
+__global__ void __launch_bounds__(128)
+    points_apply_kernel(DevView v, int lm_lo, int lm_hi, const double* __restrict__ Yl, const double* __restrict__ poses_cand,
+                        double* __restrict__ points_cand, double* __restrict__ scal2) {
+    __shared__ double s_red[32];
+    double ccost = 0, sn = 0, xn = 0, bad = 0;
+    for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const long long e1 = e0 + es * v.lm_cnt[j];
+        double p[3], pn[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            p[q] = v.points[3ll * j + q];
+            const double dl = -Yl[3ll * j + q] * v.sc_l[3ll * j + q];
+            if (isnan(dl) || isinf(dl)) bad = 1;
+            pn[q] = p[q] + dl;
+            points_cand[3ll * j + q] = pn[q];
+            sn += (p[q] - pn[q]) * (p[q] - pn[q]);
+            xn += pn[q] * pn[q];
+        }
+        for (long long e = e0; e < e1; e += es) {
+            double rc[3];
+            const uint32_t c = v.obs_cam[e];
+            stereo_block<false>(v.cam, poses_cand + 12ll * c, pn, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e), rc,
+                                nullptr, nullptr);
+            ccost += 0.5 * (rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2]);
+        }
+    }
+    block_atomic_sum(ccost, &scal2[SC_CAND_COST], s_red);
+    block_atomic_sum(sn, &scal2[SC_STEP_NORM2], s_red);
+    block_atomic_sum(xn, &scal2[SC_XNORM2], s_red);
+    block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
+}
+
 // |x - Plus(x, -g)|_inf (trust_region_minimizer: gradient norm in ambient coordinates) and |x|^2
 __global__ void gradnorm_kernel(DevView v, int lm_lo, int lm_hi, const double* __restrict__ gp_s,
                                 const double* __restrict__ gl_s, double* __restrict__ scal, int count_cams) {
@@ -947,6 +1094,36 @@ void launch_camonly_step(cudaStream_t s, const DevView& v, const SunBlockData* s
     const int n = n_sun + n_prior;
     if (n <= 0) return;
     camonly_step_kernel<<<(n + 63) / 64, 64, 0, s>>>(v, suns, n_sun, priors, n_prior, yp, poses_cand, scal2);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_dogleg_products(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, const SunBlockData* suns,
+                            int n_sun, const PriorBlockData* priors, int n_prior, const double* gp, const double* diag_p,
+                            const double* yp, const double* gl, const double* yl, double* diag_l, double* sums, int count_cams) {
+    if (lm_hi > lm_lo) {
+        dogleg_products_kernel<<<grid_for(lm_hi - lm_lo, 128, 8 * kSMs), 128, 0, s>>>(v, lm_lo, lm_hi, dg, gp, diag_p, yp, gl, yl,
+                                                                                     diag_l, sums);
+        CSLAM_LAUNCHED(1);
+    }
+    const int n = v.n_free + n_sun + n_prior;
+    if (count_cams && n > 0) {
+        dogleg_products_cam_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, suns, n_sun, priors, n_prior, gp, diag_p, yp, sums);
+        CSLAM_LAUNCHED(1);
+    }
+    CSLAM_CUDA(cudaGetLastError());
+}
+void launch_dogleg_combine(cudaStream_t s, long long n, double c1, double c2, const double* g, const double* d2, const double* y,
+                           double* out) {
+    if (n <= 0) return;
+    dogleg_combine_kernel<<<int((n + 255) / 256), 256, 0, s>>>(n, c1, c2, g, d2, y, out);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+}
+void launch_points_apply(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const double* Yl, const double* poses_cand,
+                         double* points_cand, double* scal2) {
+    if (lm_hi <= lm_lo) return;
+    points_apply_kernel<<<grid_for(lm_hi - lm_lo, 128, 8 * kSMs), 128, 0, s>>>(v, lm_lo, lm_hi, Yl, poses_cand, points_cand, scal2);
     CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }

@@ -69,6 +69,16 @@ void launch_camonly_step(cudaStream_t s, const DevView& v, const SunBlockData* s
 void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const double* gp_scaled,
                      const double* gl_scaled, double* scal, int count_cams);
 
+// DOGLEG: the eight sums of DoglegStrategy (see kernels.cu), the combined step, the candidate landmarks
+enum DoglegSum { DG_G11 = 0, DG_G12, DG_G22, DG_JGG, DG_JGY, DG_JYY, DG_JGR, DG_JYR, DG_COUNT };
+void launch_dogleg_products(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, const SunBlockData* suns,
+                            int n_sun, const PriorBlockData* priors, int n_prior, const double* gp, const double* diag_p,
+                            const double* yp, const double* gl, const double* yl, double* diag_l, double* sums, int count_cams);
+void launch_dogleg_combine(cudaStream_t s, long long n, double c1, double c2, const double* g, const double* d2, const double* y,
+                           double* out);
+void launch_points_apply(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const double* Yl, const double* poses_cand,
+                         double* points_cand, double* scal2);
+
 // layout: internal (landmark-major / slot-major) observation and landmark arrays gathered from the
 // caller-order arrays on the device; the reverse for the landmarks at download
 void launch_gather_layout(cudaStream_t s, long long n_obs, const uint32_t* obs_user, const uint32_t* raw_cam,

@@ -3,12 +3,12 @@
 // is the marginal covariance of that pose from the previous window, per-observation stereo
 // covariances.  Files: sun track CSV (dataset_problem_sun.cpp:33-103), ephemeris `k,e,n,u`
 // (:139-146), observed sun `k,x,y,z,c00,c01,c10,c11` (:162-175).
-// The trust-region strategy is Levenberg-Marquardt (the reference sets SUBSPACE_DOGLEG, :142-143:
-// SURVEY.md 8f-3).
+// Trust-region strategy: SUBSPACE_DOGLEG as the reference sets it (:142-143); `--strategy lm` runs
+// Levenberg-Marquardt instead (then the 2-pose windows take the one-CTA-per-window kernel).
 //
 //   usage: dataset_vo_sun_b200 <track_file> <ref_sun_file> <obs_sun_file> [--window (2)]
 //          [--huber-param (0)] [--az-err-thresh (1000)] [--zen-err-thresh (1000)] [--sun-only]
-//          [--max-iters (1000)]
+//          [--max-iters (1000)] [--strategy dogleg|lm]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -84,6 +84,8 @@ static bool read_csv(const std::string& track, const std::string& ref_sun, const
     return true;
 }
 
+static bool g_dogleg = true;
+
 static void solveWindow(SunDataset& d, unsigned k1, unsigned k2, bool use_sun, double huber, double az, double zen,
                         int max_iters) {
     std::cerr << "Working on interval [" << k1 << "," << k2 << ")/" << d.num_states << ": ";
@@ -116,6 +118,8 @@ static void solveWindow(SunDataset& d, unsigned k1, unsigned k2, bool use_sun, d
     problem.AddPosePrior(&d.poses[12 * size_t(k1)], Tref, W6);
     problem.options.max_num_iterations = max_iters;  // :140
     problem.options.use_nonmonotonic_steps = 1;      // :141
+    problem.options.trust_region_strategy = g_dogleg ? 1 : 0;  // :142 ceres::DOGLEG
+    problem.options.dogleg_type = 1;                 // :143 ceres::SUBSPACE_DOGLEG
     Summary summary;
     problem.Solve(&summary);
     std::cout << summary.BriefReport() << std::endl;
@@ -147,7 +151,7 @@ static void run_pass(SunDataset& d, unsigned window, bool use_sun, double huber,
 int main(int argc, char** argv) {
     const std::string usage(
         "usage: dataset_vo_sun_b200 <track_file> <ref_sun_file> <obs_sun_file> [--window (2)] [--huber-param (0)] "
-        "[--az-err-thresh (1000)] [--zen-err-thresh (1000)] [--sun-only] [--max-iters (1000)]");
+        "[--az-err-thresh (1000)] [--zen-err-thresh (1000)] [--sun-only] [--max-iters (1000)] [--strategy dogleg|lm]");
     if (argc < 4) {
         std::cerr << usage << std::endl;
         return EXIT_FAILURE;
@@ -166,6 +170,7 @@ int main(int argc, char** argv) {
         else if (flag == "--zen-err-thresh" && argc > a + 1) zen = std::stod(argv[++a]) * pi / 180.;
         else if (flag == "--sun-only") sun_only = true;
         else if (flag == "--max-iters" && argc > a + 1) max_iters = std::stoi(argv[++a]);
+        else if (flag == "--strategy" && argc > a + 1) g_dogleg = std::string(argv[++a]) != "lm";
         else {
             std::cerr << usage << std::endl;
             return EXIT_FAILURE;

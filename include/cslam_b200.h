@@ -67,6 +67,9 @@ typedef struct cslam_options {
                                with the LM loop on the device), 1 = never, 2 = require it */
     int band_separator_solver; /* exact solve of a banded reduced system, separator system between the
                                leaves: 0 = auto, 1 = banded Cholesky on one CTA, 2 = block cyclic reduction */
+    int trust_region_strategy;  /* 0 = LEVENBERG_MARQUARDT (Ceres default, dataset_vo.cpp),
+                               1 = DOGLEG (dataset_vo_sun.cpp:142, dataset_ba_phong.cpp:88) */
+    int dogleg_type;            /* 0 = TRADITIONAL_DOGLEG, 1 = SUBSPACE_DOGLEG (dataset_vo_sun.cpp:143) */
     double line_search_sufficient_function_decrease; /* 1e-4: Armijo constant of the line search a
                                bounded problem runs along the trust-region step */
 } cslam_options;

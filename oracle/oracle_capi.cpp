@@ -44,6 +44,8 @@ static Options to_options(const cslam_options* o) {
     r.max_linear_solver_iterations = o->max_linear_solver_iterations;
     r.min_linear_solver_iterations = o->min_linear_solver_iterations;
     r.num_threads = o->num_threads > 0 ? o->num_threads : 1;
+    r.trust_region_strategy = o->trust_region_strategy;
+    r.dogleg_type = o->dogleg_type;
     if (o->line_search_sufficient_function_decrease > 0.0)
         r.line_search_sufficient_function_decrease = o->line_search_sufficient_function_decrease;
     return r;
@@ -74,6 +76,8 @@ void cslam_oracle_options_init(cslam_options* o) {
     o->max_linear_solver_iterations = d.max_linear_solver_iterations;
     o->min_linear_solver_iterations = d.min_linear_solver_iterations;
     o->num_threads = d.num_threads;
+    o->trust_region_strategy = d.trust_region_strategy;
+    o->dogleg_type = d.dogleg_type;
     o->line_search_sufficient_function_decrease = d.line_search_sufficient_function_decrease;
 }
 
@@ -335,6 +339,16 @@ void cslam_oracle_kabsch(uint32_t n, const double* pts0, const double* pts1, dou
         b.push_back(pts1 + 3 * size_t(i));
     }
     kabsch(a, b, T12);
+}
+
+// ---- DOGLEG scalar pieces, for the known-answer tests ---------------------------------------------
+int cslam_oracle_poly_root_real_parts(const double* coeffs, int n_coeffs, double* out) {
+    const std::vector<double> r = polynomial_root_real_parts(std::vector<double>(coeffs, coeffs + n_coeffs));
+    for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];
+    return int(r.size());
+}
+int cslam_oracle_dogleg_boundary_minimum(const double* B4, const double* g2, double radius, double* x2) {
+    return dogleg_boundary_minimum(B4, g2, radius, x2) ? 1 : 0;
 }
 
 // ---- direct access to the restated geometry / models, for the known-answer tests ----------

@@ -11,6 +11,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <complex>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -44,6 +45,8 @@ struct Options {
     int min_linear_solver_iterations = 0;
     int num_threads = 8;        // dataset_vo.cpp:67
     double line_search_sufficient_function_decrease = 1e-4;  // Ceres default (bounded problems)
+    int trust_region_strategy = 0;  // 0 LEVENBERG_MARQUARDT, 1 DOGLEG (dataset_vo_sun.cpp:142)
+    int dogleg_type = 1;            // 0 TRADITIONAL_DOGLEG, 1 SUBSPACE_DOGLEG (dataset_vo_sun.cpp:143)
 };
 
 enum Termination { CONVERGENCE = 0, NO_CONVERGENCE = 1, FAILURE = 2 };
@@ -205,6 +208,76 @@ inline bool invert_spd3(const double* V, double* Vi) {
     Vi[5] = Vi[7] = (b * c - a * e) * id;
     Vi[8] = (a * d - b * b) * id;
     return true;
+}
+
+// Real parts of the roots of c[0] y^n + ... + c[n] (Ceres FindPolynomialRoots returns the
+// eigenvalues of the companion matrix; here Durand-Kerner in complex arithmetic — same roots).
+inline std::vector<double> polynomial_root_real_parts(std::vector<double> c) {
+    while (!c.empty() && c.front() == 0.0) c.erase(c.begin());
+    const int n = int(c.size()) - 1;
+    std::vector<double> out;
+    if (n < 1) return out;
+    using cd = std::complex<double>;
+    std::vector<cd> a(n + 1), z(n);
+    for (int i = 0; i <= n; ++i) a[i] = c[i] / c[0];
+    double rad = 0;
+    for (int i = 1; i <= n; ++i) rad = std::max(rad, std::pow(std::abs(a[i]), 1.0 / i));
+    rad = 2.0 * rad + 1e-300;
+    for (int i = 0; i < n; ++i) z[i] = std::polar(rad, 2.0 * 3.14159265358979323846 * i / n + 0.4);
+    for (int it = 0; it < 500; ++it) {
+        double delta = 0;
+        for (int i = 0; i < n; ++i) {
+            cd pv = a[0];
+            for (int k = 1; k <= n; ++k) pv = pv * z[i] + a[k];
+            cd den = 1.0;
+            for (int j = 0; j < n; ++j)
+                if (j != i) den *= (z[i] - z[j]);
+            if (std::abs(den) == 0.0) den = 1e-300;
+            const cd dz = pv / den;
+            z[i] -= dz;
+            delta = std::max(delta, std::abs(dz) / std::max(std::abs(z[i]), 1e-300));
+        }
+        if (delta < 1e-15) break;
+    }
+    for (int i = 0; i < n; ++i) out.push_back(z[i].real());
+    return out;
+}
+
+// DoglegStrategy::FindMinimumOnTrustRegionBoundary [Ceres 1.x dogleg_strategy.cc, from memory]:
+// stationary points of 1/2 x^T B x + g^T x on |x| = r through the quartic in the multiplier.
+inline bool dogleg_boundary_minimum(const double B[4], const double g[2], double r, double x_out[2]) {
+    const double detB = B[0] * B[3] - B[1] * B[2], trB = B[0] + B[3], r2 = r * r;
+    const double Ba[4] = {B[3], -B[1], -B[2], B[0]};  // adjugate
+    const double gg = g[0] * g[0] + g[1] * g[1];
+    const double Bag[2] = {Ba[0] * g[0] + Ba[1] * g[1], Ba[2] * g[0] + Ba[3] * g[1]};
+    std::vector<double> poly(5);
+    poly[0] = r2;
+    poly[1] = 2.0 * r2 * trB;
+    poly[2] = r2 * (trB * trB + 2.0 * detB) - gg;
+    poly[3] = -2.0 * ((g[0] * Bag[0] + g[1] * Bag[1]) - r2 * detB * trB);
+    poly[4] = r2 * detB * detB - (Bag[0] * Bag[0] + Bag[1] * Bag[1]);
+    const std::vector<double> roots = polynomial_root_real_parts(poly);
+    x_out[0] = x_out[1] = 0.0;
+    double best = std::numeric_limits<double>::max();
+    bool found = false;
+    for (double y : roots) {
+        // x(y) = -(B + y I)^-1 g
+        const double a = B[0] + y, b = B[1], c2 = B[2], d = B[3] + y;
+        const double det = a * d - b * c2;
+        if (det == 0.0 || !std::isfinite(det)) continue;
+        const double x[2] = {-(d * g[0] - b * g[1]) / det, -(-c2 * g[0] + a * g[1]) / det};
+        const double nx = std::sqrt(x[0] * x[0] + x[1] * x[1]);
+        if (!(nx > 0.0) || !std::isfinite(nx)) continue;
+        const double p[2] = {r / nx * x[0], r / nx * x[1]};
+        const double f = 0.5 * (p[0] * (B[0] * p[0] + B[1] * p[1]) + p[1] * (B[2] * p[0] + B[3] * p[1])) + g[0] * p[0] + g[1] * p[1];
+        found = true;
+        if (f < best) {
+            best = f;
+            x_out[0] = x[0];
+            x_out[1] = x[1];
+        }
+    }
+    return found;
 }
 
 class Problem {
@@ -870,6 +943,202 @@ class Problem {
         int iteration = 0;
         BlockSym S = st.S;
         std::vector<double> yp, yl, dp(6 * size_t(nf)), dl(3 * na);
+
+        // ---- DoglegStrategy [Ceres 1.x dogleg_strategy.cc, restated from memory] -------------------
+        // Works in the coordinates step' = D step, D = sqrt(clamp(diag(J^T J))) of the (Jacobi-scaled)
+        // Jacobian, where the trust region is a ball of radius `radius`.
+        double dl_mu = 1e-8, dl_alpha = 0.0, dl_step_norm = 0.0;
+        bool dl_reuse = false, dl_1d = false;
+        std::vector<double> dgp, dgl, ggp, ggl, nnp, nnl, u0p, u0l, u1p, u1l;
+        double sub_B[4] = {0, 0, 0, 0}, sub_g[2] = {0, 0};
+        // |J v|^2-type products with the scaled Jacobian: rows = stereo 3, sun 2, prior 6
+        auto jv = [&](const std::vector<double>& vp, const std::vector<double>& vl, std::vector<double>& out) {
+            out.assign(3 * n_stereo() + 2 * suns.size() + 6 * priors.size(), 0.0);
+            for (size_t i = 0; i < n_stereo(); ++i) {
+                const int f = st.cam_free[st_cam[i]];
+                const int a = st.pt_active[st_pt[i]];
+                for (int k = 0; k < 3; ++k) {
+                    double m = 0;
+                    if (f >= 0)
+                        for (int p = 0; p < 6; ++p) m += ev.Jc_st[18 * i + 6 * k + p] * sc_p[6 * size_t(f) + p] * vp[6 * size_t(f) + p];
+                    for (int q = 0; q < 3; ++q) m += ev.Jp_st[9 * i + 3 * k + q] * sc_l[3 * size_t(a) + q] * vl[3 * size_t(a) + q];
+                    out[3 * i + k] = m;
+                }
+            }
+            size_t o = 3 * n_stereo();
+            auto cam_only = [&](int f, const double* J, int rows) {
+                for (int k = 0; k < rows; ++k, ++o)
+                    if (f >= 0)
+                        for (int p = 0; p < 6; ++p) out[o] += J[6 * k + p] * sc_p[6 * size_t(f) + p] * vp[6 * size_t(f) + p];
+            };
+            for (size_t i = 0; i < suns.size(); ++i) cam_only(st.cam_free[suns[i].cam], &ev.J_sun[12 * i], 2);
+            for (size_t i = 0; i < priors.size(); ++i) cam_only(st.cam_free[priors[i].cam], &ev.J_pr[36 * i], 6);
+        };
+        auto dot2 = [](const std::vector<double>& a, const std::vector<double>& b) {
+            double v = 0;
+            for (size_t i = 0; i < a.size(); ++i) v += a[i] * b[i];
+            return v;
+        };
+        auto traditional_step = [&](std::vector<double>& sp, std::vector<double>& sl) {
+            // DoglegStrategy::ComputeTraditionalDoglegStep; result in D-scaled coordinates
+            const double gnorm = std::sqrt(dot2(ggp, ggp) + dot2(ggl, ggl));
+            const double nnorm = std::sqrt(dot2(nnp, nnp) + dot2(nnl, nnl));
+            double cg = 0, cn = 0;
+            if (nnorm <= radius) {
+                cn = 1.0;
+                dl_step_norm = nnorm;
+            } else if (gnorm * dl_alpha >= radius) {
+                cg = -(radius / gnorm);
+                dl_step_norm = radius;
+            } else {
+                const double b_dot_a = -dl_alpha * (dot2(ggp, nnp) + dot2(ggl, nnl));
+                const double a2 = std::pow(dl_alpha * gnorm, 2.0);
+                const double bma2 = a2 - 2 * b_dot_a + std::pow(nnorm, 2);
+                const double c = b_dot_a - a2;
+                const double d = std::sqrt(c * c + bma2 * (std::pow(radius, 2.0) - a2));
+                const double beta = (c <= 0) ? (d - c) / bma2 : (radius * radius - a2) / (d + c);
+                cg = -dl_alpha * (1.0 - beta);
+                cn = beta;
+                dl_step_norm = -1.0;  // norm of the combination, below
+            }
+            sp.resize(ggp.size());
+            sl.resize(ggl.size());
+            for (size_t i = 0; i < sp.size(); ++i) sp[i] = cg * ggp[i] + cn * nnp[i];
+            for (size_t i = 0; i < sl.size(); ++i) sl[i] = cg * ggl[i] + cn * nnl[i];
+            if (dl_step_norm < 0.0) dl_step_norm = std::sqrt(dot2(sp, sp) + dot2(sl, sl));
+        };
+        auto subspace_step = [&](std::vector<double>& sp, std::vector<double>& sl) {
+            // DoglegStrategy::ComputeSubspaceDoglegStep
+            const double nnorm = std::sqrt(dot2(nnp, nnp) + dot2(nnl, nnl));
+            if (nnorm <= radius) {
+                sp = nnp;
+                sl = nnl;
+                dl_step_norm = nnorm;
+                return;
+            }
+            if (dl_1d) {
+                const double gnorm = std::sqrt(dot2(ggp, ggp) + dot2(ggl, ggl));
+                sp.resize(ggp.size());
+                sl.resize(ggl.size());
+                for (size_t i = 0; i < sp.size(); ++i) sp[i] = -(radius / gnorm) * ggp[i];
+                for (size_t i = 0; i < sl.size(); ++i) sl[i] = -(radius / gnorm) * ggl[i];
+                dl_step_norm = radius;
+                return;
+            }
+            double x[2];
+            if (!dogleg_boundary_minimum(sub_B, sub_g, radius, x)) {
+                traditional_step(sp, sl);
+                return;
+            }
+            sp.resize(ggp.size());
+            sl.resize(ggl.size());
+            for (size_t i = 0; i < sp.size(); ++i) sp[i] = x[0] * u0p[i] + x[1] * u1p[i];
+            for (size_t i = 0; i < sl.size(); ++i) sl[i] = x[0] * u0l[i] + x[1] * u1l[i];
+            dl_step_norm = radius;
+        };
+        auto dogleg_compute_step = [&]() -> Linear {
+            Linear lin;
+            std::vector<double> sp, sl;
+            if (!dl_reuse) {
+                dl_reuse = true;
+                const size_t np6 = 6 * size_t(nf), nl3 = 3 * na;
+                dgp.resize(np6);
+                dgl.resize(nl3);
+                ggp.resize(np6);
+                ggl.resize(nl3);
+                for (size_t i = 0; i < np6; ++i) {
+                    dgp[i] = std::sqrt(std::min(std::max(cn_p[i] * sc_p[i] * sc_p[i], opt.min_lm_diagonal), opt.max_lm_diagonal));
+                    ggp[i] = gp[i] * sc_p[i] / dgp[i];  // ComputeGradient: D^-1 J^T r
+                }
+                for (size_t i = 0; i < nl3; ++i) {
+                    dgl[i] = std::sqrt(std::min(std::max(cn_l[i] * sc_l[i] * sc_l[i], opt.min_lm_diagonal), opt.max_lm_diagonal));
+                    ggl[i] = gl[i] * sc_l[i] / dgl[i];
+                }
+                // ComputeCauchyPoint: alpha = |g'|^2 / |J D^-1 g'|^2
+                std::vector<double> tp(np6), tl(nl3), Jg;
+                for (size_t i = 0; i < np6; ++i) tp[i] = ggp[i] / dgp[i];
+                for (size_t i = 0; i < nl3; ++i) tl[i] = ggl[i] / dgl[i];
+                jv(tp, tl, Jg);
+                dl_alpha = (dot2(ggp, ggp) + dot2(ggl, ggl)) / dot2(Jg, Jg);
+                // ComputeGaussNewtonStep: (J^T J + mu D^2) y = J^T r, mu raised on failure
+                lin.ok = false;
+                while (dl_mu < 1.0) {
+                    std::vector<double> Dp2(np6), Dl2(nl3);
+                    for (size_t i = 0; i < np6; ++i) Dp2[i] = dgp[i] * std::sqrt(dl_mu);
+                    for (size_t i = 0; i < nl3; ++i) Dl2[i] = dgl[i] * std::sqrt(dl_mu);
+                    lin = schur_solve(st, ev, sc_p, sc_l, Dp2, Dl2, opt, yp, yl, S);
+                    bool fin = lin.ok;
+                    if (fin)
+                        for (double v : yp) fin = fin && std::isfinite(v);
+                    if (fin)
+                        for (double v : yl) fin = fin && std::isfinite(v);
+                    if (!fin) {
+                        dl_mu *= 10.0;
+                        lin.ok = false;
+                        continue;
+                    }
+                    break;
+                }
+                if (!lin.ok) return lin;
+                nnp.resize(np6);
+                nnl.resize(nl3);
+                for (size_t i = 0; i < np6; ++i) nnp[i] = -dgp[i] * yp[i];
+                for (size_t i = 0; i < nl3; ++i) nnl[i] = -dgl[i] * yl[i];
+                if (opt.dogleg_type == 1) {
+                    // ComputeSubspaceModel: orthonormal basis of span{g', gn'} (column-pivoted QR: the
+                    // longer column first), rank test 2 eps |R00|
+                    const double ng2 = dot2(ggp, ggp) + dot2(ggl, ggl), nn2 = dot2(nnp, nnp) + dot2(nnl, nnl);
+                    const bool g_first = ng2 >= nn2;
+                    const std::vector<double>&ap = g_first ? ggp : nnp, &al = g_first ? ggl : nnl;
+                    const std::vector<double>&bp = g_first ? nnp : ggp, &bl = g_first ? nnl : ggl;
+                    const double r00 = std::sqrt(std::max(ng2, nn2));
+                    if (!(r00 > 0.0)) {
+                        lin.ok = false;
+                        return lin;
+                    }
+                    u0p.resize(np6);
+                    u0l.resize(nl3);
+                    u1p.resize(np6);
+                    u1l.resize(nl3);
+                    for (size_t i = 0; i < np6; ++i) u0p[i] = ap[i] / r00;
+                    for (size_t i = 0; i < nl3; ++i) u0l[i] = al[i] / r00;
+                    const double pr = dot2(u0p, bp) + dot2(u0l, bl);
+                    for (size_t i = 0; i < np6; ++i) u1p[i] = bp[i] - pr * u0p[i];
+                    for (size_t i = 0; i < nl3; ++i) u1l[i] = bl[i] - pr * u0l[i];
+                    const double r11 = std::sqrt(dot2(u1p, u1p) + dot2(u1l, u1l));
+                    dl_1d = !(r11 > 2.0 * std::numeric_limits<double>::epsilon() * r00);
+                    if (!dl_1d) {
+                        for (auto& v : u1p) v /= r11;
+                        for (auto& v : u1l) v /= r11;
+                        sub_g[0] = dot2(u0p, ggp) + dot2(u0l, ggl);
+                        sub_g[1] = dot2(u1p, ggp) + dot2(u1l, ggl);
+                        std::vector<double> J0, J1;
+                        for (size_t i = 0; i < np6; ++i) tp[i] = u0p[i] / dgp[i];
+                        for (size_t i = 0; i < nl3; ++i) tl[i] = u0l[i] / dgl[i];
+                        jv(tp, tl, J0);
+                        for (size_t i = 0; i < np6; ++i) tp[i] = u1p[i] / dgp[i];
+                        for (size_t i = 0; i < nl3; ++i) tl[i] = u1l[i] / dgl[i];
+                        jv(tp, tl, J1);
+                        sub_B[0] = dot2(J0, J0);
+                        sub_B[1] = sub_B[2] = dot2(J0, J1);
+                        sub_B[3] = dot2(J1, J1);
+                    }
+                }
+                lin.iterations = 1;
+            } else {
+                lin.iterations = 0;
+            }
+            if (opt.dogleg_type == 1)
+                subspace_step(sp, sl);
+            else
+                traditional_step(sp, sl);
+            // step = D^-1 step'; the minimiser's convention here is delta = -y (scaled coordinates)
+            yp.resize(sp.size());
+            yl.resize(sl.size());
+            for (size_t i = 0; i < sp.size(); ++i) yp[i] = -sp[i] / dgp[i];
+            for (size_t i = 0; i < sl.size(); ++i) yl[i] = -sl[i] / dgl[i];
+            return lin;
+        };
         for (;;) {
             // FinalizeIterationAndCheckIfMinimizerCanContinue
             if (iteration > 0) {
@@ -899,18 +1168,23 @@ class Problem {
             step_ok_prev = false;
             row = IterationRow{};
             row.iteration = iteration;
-            // ---- LevenbergMarquardtStrategy::ComputeStep ----
-            if (!reuse_diagonal) {
-                for (size_t i = 0; i < diag_p.size(); ++i)
-                    diag_p[i] = std::min(std::max(cn_p[i] * sc_p[i] * sc_p[i], opt.min_lm_diagonal),
-                                         opt.max_lm_diagonal);
-                for (size_t i = 0; i < diag_l.size(); ++i)
-                    diag_l[i] = std::min(std::max(cn_l[i] * sc_l[i] * sc_l[i], opt.min_lm_diagonal),
-                                         opt.max_lm_diagonal);
+            Linear lin;
+            if (opt.trust_region_strategy == 1) {
+                lin = dogleg_compute_step();
+            } else {
+                // ---- LevenbergMarquardtStrategy::ComputeStep ----
+                if (!reuse_diagonal) {
+                    for (size_t i = 0; i < diag_p.size(); ++i)
+                        diag_p[i] = std::min(std::max(cn_p[i] * sc_p[i] * sc_p[i], opt.min_lm_diagonal),
+                                             opt.max_lm_diagonal);
+                    for (size_t i = 0; i < diag_l.size(); ++i)
+                        diag_l[i] = std::min(std::max(cn_l[i] * sc_l[i] * sc_l[i], opt.min_lm_diagonal),
+                                             opt.max_lm_diagonal);
+                }
+                for (size_t i = 0; i < Dp.size(); ++i) Dp[i] = std::sqrt(diag_p[i] / radius);
+                for (size_t i = 0; i < Dl.size(); ++i) Dl[i] = std::sqrt(diag_l[i] / radius);
+                lin = schur_solve(st, ev, sc_p, sc_l, Dp, Dl, opt, yp, yl, S);
             }
-            for (size_t i = 0; i < Dp.size(); ++i) Dp[i] = std::sqrt(diag_p[i] / radius);
-            for (size_t i = 0; i < Dl.size(); ++i) Dl[i] = std::sqrt(diag_l[i] / radius);
-            Linear lin = schur_solve(st, ev, sc_p, sc_l, Dp, Dl, opt, yp, yl, S);
             reuse_diagonal = true;
             row.linear_iterations = lin.iterations;
             sum.total_linear_iterations += lin.iterations;
@@ -971,9 +1245,14 @@ class Problem {
                     finish(FAILURE, R_INVALID_STEPS);
                     break;
                 }
-                radius = radius / decrease_factor;  // StepIsInvalid == StepRejected(0)
-                decrease_factor *= 2.0;
-                reuse_diagonal = true;
+                if (opt.trust_region_strategy == 1) {
+                    dl_mu *= 10.0;  // DoglegStrategy::StepIsInvalid
+                    dl_reuse = false;
+                } else {
+                    radius = radius / decrease_factor;  // StepIsInvalid == StepRejected(0)
+                    decrease_factor *= 2.0;
+                    reuse_diagonal = true;
+                }
                 row.radius = radius;
                 sum.rows.push_back(row);
                 continue;
@@ -1034,10 +1313,20 @@ class Problem {
                 step_ok_prev = true;
                 row.step_is_successful = 1;
                 // strategy StepAccepted
-                radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
-                radius = std::min(opt.max_trust_region_radius, radius);
-                decrease_factor = 2.0;
-                reuse_diagonal = false;
+                if (opt.trust_region_strategy == 1) {
+                    if (row.relative_decrease < 0.25) radius *= 0.5;
+                    if (row.relative_decrease > 0.75) {
+                        radius = std::max(radius, 3.0 * dl_step_norm);
+                        radius = std::min(radius, opt.max_trust_region_radius);
+                    }
+                    dl_mu = std::max(1e-8, 2.0 * dl_mu / 10.0);
+                    dl_reuse = false;
+                } else {
+                    radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
+                    radius = std::min(opt.max_trust_region_radius, radius);
+                    decrease_factor = 2.0;
+                    reuse_diagonal = false;
+                }
                 // step evaluator StepAccepted(candidate_cost, model_cost_change)
                 se_current = cand_cost;
                 se_acc_cand += model_cost_change;
@@ -1058,6 +1347,9 @@ class Problem {
                     se_reference = se_candidate;
                     se_acc_ref = se_acc_cand;
                 }
+            } else if (opt.trust_region_strategy == 1) {
+                radius *= 0.5;  // DoglegStrategy::StepRejected
+                dl_reuse = true;
             } else {
                 radius = radius / decrease_factor;
                 decrease_factor *= 2.0;

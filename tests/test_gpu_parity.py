@@ -576,15 +576,21 @@ def test_cpp_driver_dataset_vo_sun(product, tmp_path):
     tr = syn.add_sun(_steady_track(25, seed=23, per_obs_W=True), sigma_deg=1.0)
     paths = [os.path.join(tmp_path, n) for n in ("track.csv", "sun_ref.csv", "sun_obs.csv")]
     syn.write_sun_csvs(tr, *paths)
-    text = _run_driver("dataset_vo_sun_b200", paths + ["--window", "2", "--huber-param", "1.0", "--max-iters", "100"], tmp_path)
-    assert text.count("cslam_b200 Report") == 48 and "Covariance computation failed" not in text, text
     gt_t, gt_R = tr["poses_gt"][:, :3], tr["poses_gt"][:, 3:].reshape(-1, 3, 3)
-    Tv = _poses_csv(os.path.join(tmp_path, "track_poses.csv"), 25)          # pass 1: VO only
-    Ts = _poses_csv(os.path.join(tmp_path, "track_obs_poses.csv"), 25)      # pass 2: with the sun sensor
-    for T in (Tv, Ts):
-        assert np.abs(T[:, :3, 3] - gt_t).max() < 0.15
-        assert np.abs(T[:, :3, :3] - gt_R).max() < 0.02
-    assert np.abs(Ts - Tv).max() > 1e-6                                      # the sun blocks act
+    results = {}
+    for strategy in ("dogleg", "lm"):      # the reference's SUBSPACE_DOGLEG (default) and Levenberg-Marquardt
+        text = _run_driver("dataset_vo_sun_b200", paths + ["--window", "2", "--huber-param", "1.0", "--max-iters", "100",
+                                                           "--strategy", strategy], tmp_path)
+        assert text.count("cslam_b200 Report") == 48 and "Covariance computation failed" not in text, text
+        Tv = _poses_csv(os.path.join(tmp_path, "track_poses.csv"), 25)          # pass 1: VO only
+        Ts = _poses_csv(os.path.join(tmp_path, "track_obs_poses.csv"), 25)      # pass 2: with the sun sensor
+        for T in (Tv, Ts):
+            assert np.abs(T[:, :3, 3] - gt_t).max() < 0.15
+            assert np.abs(T[:, :3, :3] - gt_R).max() < 0.02
+        assert np.abs(Ts - Tv).max() > 1e-6                                      # the sun blocks act
+        results[strategy] = Ts
+    # both strategies converge to the same window minima
+    assert np.abs(results["dogleg"] - results["lm"]).max() < 1e-3
 
 
 def test_cpp_driver_dataset_ba_phong(product, tmp_path):
@@ -625,3 +631,41 @@ def test_band_solver_cyclic_reduction(product, shape, leaves):
     p1, poses1, points1 = syn.build_problem(tr, backend="b200", band_separator_solver=1, band_leaves=leaves, **kw)
     p1.solve()
     assert rel_err(g2[2], poses1) < 1e-9 and rel_err(g2[3], points1) < 1e-9
+
+
+@pytest.mark.parametrize("dogleg_type", [0, 1])
+@pytest.mark.parametrize("radius", [1e4, 5.0, 0.5])
+def test_dogleg_full_batch(product, dogleg_type, radius):
+    """the DOGLEG trust-region strategy the reference's dataset_vo_sun /
+    dataset_ba_phong drivers set (TRADITIONAL and SUBSPACE), against the oracle's restatement of
+    Ceres' DoglegStrategy: Gauss-Newton point inside the region (radius 1e4), Cauchy-limited and
+    interpolated / subspace-boundary steps (small radii)."""
+    tr = syn.add_sun(syn.make_track(60, 12, 6, seed=21))
+    # (pure Gauss-Newton steps converge to a bit-exact fixed point within ~5 iterations: stay short of it)
+    g, o = solve_pair(tr, 4 if radius > 1e3 else 8, sun=True, trust_region_strategy=1, dogleg_type=dogleg_type,
+                      initial_trust_region_radius=radius)
+    check_lm(g, o)
+    lg = g[0].iteration_log()
+    assert np.allclose(lg[:, 4], o[0].iteration_log()[:, 4], rtol=1e-5), "step norms"
+    if radius < 1e3:
+        assert lg[1, 4] < 0.2 * lg[-1, 4] or lg[1, 6] > radius  # the first steps were limited by the region
+
+
+def test_dogleg_window_with_prior(product):
+    """A dataset_vo_sun window as the reference configures it: SUBSPACE_DOGLEG, no constant pose, pose
+    prior, sun blocks with Huber loss.  (DOGLEG problems go through the generic engine.)"""
+    tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42, per_obs_W=True))
+    w = syn.window_of(tr, 20, 22)
+    prior = (0, w["poses"][0].copy(), np.eye(6) * 1e6)
+    g, o = solve_pair(w, 6, sun=True, prior=prior, huber=1.0, hold_first=False, trust_region_strategy=1, dogleg_type=1)
+    check_lm(g, o)
+
+
+def test_dogleg_rejected_steps_reuse(product):
+    """A poor start with a large region: rejected steps halve the radius and reuse the Gauss-Newton /
+    gradient vectors (no new linear solve), invalid steps raise mu."""
+    tr = syn.make_track(60, 10, 6, seed=4, pose_sigma=(0.3, 0.08), point_sigma=0.5)
+    g, o = solve_pair(tr, 10, trust_region_strategy=1, dogleg_type=1)
+    check_lm(g, o)
+    lg, lo = g[0].iteration_log(), o[0].iteration_log()
+    assert np.array_equal(lg[:, 7], lo[:, 7]), "linear solves per iteration (0 when the vectors are reused)"
