@@ -260,6 +260,33 @@ def bench_c3_phong_solve(iters=6, cpu=True):
     return out
 
 
+def bench_ransac_front_end(n_poses=1000):
+    """the RANSAC front end (compute_initial_guess's 400-hypothesis point-cloud
+    alignment per consecutive pose pair) for a 1 k-pose track with ~900 matches per pair, all pairs
+    in ONE launch; wall time of cslam_ransac_align from host arrays (H2D + kernel + D2H)."""
+    from ceres_slam_b200 import initial_guess as ig
+    tr = syn.make_track(n_poses, 100, 10, seed=42, pix_sigma=0.25)
+    rng = ig.state_ranges(tr["obs_cam"], tr["n_poses"])
+    pt = tr["obs_pt"].astype(np.int64)
+    p0, p1 = [], []
+    for k in range(1, tr["n_poses"]):
+        kp, kc = ig.match_pair(pt[rng[k - 1]:rng[k]], pt[rng[k]:rng[k + 1]])
+        p0.append(ig.triangulate(tr["cam"], tr["uvd"][rng[k - 1]:rng[k]][kp]))
+        p1.append(ig.triangulate(tr["cam"], tr["uvd"][rng[k]:rng[k + 1]][kc]))
+    ig.ransac_align(p0[:8], p1[:8], tr["cam"], "b200")          # context / module warm-up
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        T, inl, cnt = ig.ransac_align(p0, p1, tr["cam"], "b200")
+        best = min(best, time.perf_counter() - t0)
+    n_pts = int(sum(p.shape[0] for p in p0))
+    hyp_pts = 400.0 * n_pts
+    return {"pose_pairs": len(p0), "correspondences": n_pts, "hypotheses_per_pair": 400, "wall_ms": best * 1e3,
+            "pairs_per_s": len(p0) / best, "hypothesis_point_tests_per_s": hyp_pts / best,
+            "median_inlier_fraction": float(np.median(cnt / np.maximum(1, [p.shape[0] for p in p0]))),
+            "note": "host lists -> one concatenation + H2D + one kernel launch + D2H (python packing included)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -403,6 +430,7 @@ def main():
     c4 = bench_c4_windows(lib) if (rank == 0 and not args.no_c4) else None
     phong = bench_phong_blocks(peak) if (rank == 0 and not args.no_phong) else None
     c3 = bench_c3_phong_solve(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_phong) else None
+    ransac = bench_ransac_front_end() if (rank == 0 and world == 1 and not args.no_c4) else None
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     e2e = None
@@ -440,7 +468,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
             "resjac": resjac, "step_profile_ms": step_profile, "c4_windows": c4, "phong_blocks": phong,
-            "c3_phong_solve": c3,
+            "c3_phong_solve": c3, "ransac_front_end": ransac,
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},
             "setup_s": {"generate": gen_s, "upload_and_structure": upload_s},
