@@ -153,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "LM iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "obs_per_s": value * full_obs,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def c5_obs_count():
@@ -287,6 +287,19 @@ def bench_ransac_front_end(n_poses=1000):
             "note": "host lists -> one concatenation + H2D + one kernel launch + D2H (python packing included)"}
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -303,6 +316,12 @@ def main():
                     help="reduced-system solve: exact = SPARSE_SCHUR-equivalent (banded direct solver), "
                          "iterative = ITERATIVE_SCHUR-equivalent (block-Jacobi PCG, eta = 0.1)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: libraries that print there on their own (NCCL
+    # with NCCL_DEBUG=VERSION does) are sent to stderr for the whole run
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     LM_OPTS.clear()
     LM_OPTS.update(LM_EXACT if args.linear == "exact" else LM_ITERATIVE)
     if args.impl == "reference":
@@ -322,6 +341,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.load_product()
     W = max(3, args.warmup)
@@ -473,7 +493,7 @@ def main():
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},
             "setup_s": {"generate": gen_s, "upload_and_structure": upload_s},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
