@@ -1,0 +1,76 @@
+"""BASELINE.json's full sizes on the GPU, through properties that do not need the (far too slow)
+oracle: two independent kernels must agree on the cost, permuting the caller's observation order
+must not change the result, the solve must decrease the cost monotonically within the trust-region
+rules, and the parameter blocks must stay in their domains."""
+import numpy as np
+import pytest
+
+from ceres_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+FIXED = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+
+
+@pytest.fixture(scope="module")
+def c5():
+    return syn.make_track(20000, 100, 10, seed=42)      # 20 k poses, 2 M landmarks, 20 M observations
+
+
+def test_c5_cost_agrees_between_kernels_and_numpy(product, c5):
+    """The materialised residual kernel (K1, caller's order), the fused Schur pass (K2, internal
+    grouped order) and a float64 numpy restatement of r = W (pi(R p + t) - z) agree on 1/2 |r|^2."""
+    p, poses, points = syn.build_problem(c5, backend="b200", max_num_iterations=1, **FIXED)
+    ev = p.evaluate(jacobians=False)
+    k, j = c5["obs_cam"].astype(np.int64), c5["obs_pt"].astype(np.int64)
+    R, t = syn.pose_R(c5["poses"]), syn.pose_t(c5["poses"])
+    cost = 0.0
+    for lo in range(0, k.size, 4_000_000):
+        sl = slice(lo, lo + 4_000_000)
+        pc = np.einsum("nij,nj->ni", R[k[sl]], c5["points"][j[sl]]) + t[k[sl]]
+        r = (syn.project(c5["cam"], pc) - c5["uvd"][sl]) @ np.asarray(c5["W"]).reshape(3, 3).T
+        assert np.abs(ev["r_stereo"][sl] - r).max() < 1e-9 * np.abs(r).max()
+        cost += 0.5 * float(np.sum(r * r))
+    assert abs(ev["cost"] - cost) < 1e-11 * cost
+    s = p.solve()
+    assert abs(s.initial_cost - cost) < 1e-11 * cost     # the fused Schur pass, internal order
+
+
+def test_c5_solve_properties_and_order_invariance(product, c5):
+    """Five LM iterations at full size: accepted steps decrease the cost, and a random permutation of the caller's observation order
+    (different staging, same internal layout) reproduces the solution to rounding."""
+    kw = dict(FIXED, max_num_iterations=5)
+    p, poses, points = syn.build_problem(c5, backend="b200", **kw)
+    s = p.solve()
+    log = p.iteration_log()
+    acc = log[1:, 9] == 1
+    assert acc.sum() >= 4 and np.all(np.diff(log[:, 1])[acc] < 0)
+    assert s.final_cost < 0.05 * s.initial_cost
+    # (absolute landmark error is not a property here: with one fixed pose on a 20 k-pose open chain
+    # the gauge drifts while the reprojection cost falls)
+    assert np.array_equal(poses[0], c5["poses"][0])       # the constant pose did not move
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(c5["obs_cam"].size)
+    tr2 = dict(c5)
+    for key in ("obs_cam", "obs_pt", "uvd"):
+        tr2[key] = np.ascontiguousarray(c5[key][perm])
+    p2, poses2, points2 = syn.build_problem(tr2, backend="b200", **kw)
+    s2 = p2.solve()
+    assert abs(s2.final_cost - s.final_cost) < 1e-9 * s.final_cost
+    assert np.abs(poses2 - poses).max() < 1e-8 and np.abs(points2 - points).max() < 1e-7
+
+
+def test_c3_lighting_solve_properties(product):
+    """Config 3 at full size (2 k poses, 199 k vertices, 2 M observations): the initial cost of the
+    joint solve equals stereo cost + lighting cost from the two evaluation kernels, the solve
+    decreases it, unit normals stay unit, the box holds."""
+    tr = syn.add_phong(syn.make_track(2000, 100, 10, seed=42), shared_textures=True)
+    p, st = syn.build_phong_problem(tr, backend="b200", bounds=True, max_num_iterations=5, **FIXED)
+    c_st = p.evaluate(jacobians=False)["cost"]
+    c_ph = p.evaluate_phong()["cost"]
+    s = p.solve()
+    assert abs(s.initial_cost - (c_st + c_ph)) < 1e-10 * s.initial_cost
+    assert s.final_cost < 0.1 * s.initial_cost and s.num_successful_steps >= 4
+    assert np.abs(np.linalg.norm(st["normals"], axis=1) - 1.0).max() < 1e-12
+    assert np.all(st["phong"][:, :2] >= 0) and np.all(st["phong"][:, :2] <= 1) and np.all(st["phong"][:, 2] >= 1)
+    assert np.all(st["textures"] >= 0) and np.all(st["textures"] <= 1)
+    assert np.abs(st["light"] - tr["light_gt"]).max() < np.abs(tr["light"] - tr["light_gt"]).max()
