@@ -540,15 +540,20 @@ __global__ void bcr_init_kernel(BcrView R, const double* __restrict__ Tb, const 
 }
 
 // rows i = first + blockIdx.x * step; left / right neighbours at distance s (absent when out of range
-// or when s == 0: the last row standing).  Right-looking Cholesky of D_i with the border
-// [E_left | E_right^T | f | I] riding along; nothing is scaled in place (step k applies
-// M[r][c] -= M[r][k] M[c][k] / d), so a step is ONE barrier; row k of the border, scaled by
-// 1/sqrt(d), goes straight to the outputs A | Bm | g | Li.  32 x 32 threads: rows x columns.
-constexpr int BCR_T = 1024;
+// or when s == 0: the last row standing).  Right-looking BLOCKED Cholesky of D_i (6x6 pivots, as
+// in the leaf kernel) with the border [E_left | E_right^T | f | I] riding along: W block steps of
+//   (1) pivot      Lkk, Lkk^-1 of the 6x6 pivot in registers (one thread)
+//   (2) panel      L_rk = A_rk Lkk^-T for the rows below, X_k = Lkk^-1 G_k for the border row block
+//   (3) trailing   A_rc -= L_rk . L_ck   (symmetric part)   /   G_rc -= L_rk . X_kc   (border)
+// i.e. 3 barriers per SIX pivots and rank-6 updates.  X_k is final after (2) and is written to
+// A | Bm | g | Li while (3) runs.
+constexpr int BCR_T = 512;
 __global__ void __launch_bounds__(BCR_T) bcr_odd_kernel(BcrView R, int first, int step, int s) {
     extern __shared__ __align__(16) double smem_bcr[];
+    __shared__ double sLi[72];  // Lkk^-1 of the current / next pivot block
     __shared__ int s_ok;
-    const int b = R.b, ld = 4 * b + 1, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int b = R.b, ld = 4 * b + 1, nbord = 3 * b + 1, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    constexpr int TY = BCR_T / 32;
     const int i = first + blockIdx.x * step;
     const bool has_l = s > 0 && i - s >= 0, has_r = s > 0 && i + s < R.N;
     const long long bb = (long long)b * b;
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(BCR_T) bcr_odd_kernel(BcrView R, int first, in
     const double* Di = R.D + i * bb;
     const double* El = R.E + i * bb;
     const double* Er = R.E + (long long)(i + s) * bb;
-    for (int r = ty; r < b; r += 32) {
+    for (int r = ty; r < b; r += TY) {
         double* Mr = M + r * ld;
         for (int c = tx; c < b; c += 32) {
             Mr[c] = Di[r * b + c];
@@ -567,51 +572,140 @@ __global__ void __launch_bounds__(BCR_T) bcr_odd_kernel(BcrView R, int first, in
         if (tx == 0) Mr[3 * b] = R.f[(long long)i * b + r];
     }
     // E_right^T: read E(i+s, i) row-wise (coalesced), store transposed
-    for (int r = ty; r < b; r += 32)
+    for (int r = ty; r < b; r += TY)
         for (int c = tx; c < b; c += 32) M[c * ld + 2 * b + r] = has_r ? Er[r * b + c] : 0.0;
-    __shared__ double s_piv[2][2];  // [parity][1/d, 1/sqrt(d)] of the pivot, written one step ahead
     if (tid == 0) s_ok = 1;
-    __syncthreads();
-    if (tid == 0) {
-        const double d = M[0];
-        double inv = rsqrt(d);
-        inv = inv * (1.5 - 0.5 * d * inv * inv);  // one Newton step: full double precision
-        s_piv[0][0] = 1.0 / d;
-        s_piv[0][1] = inv;
-        if (!(d > 0.0) || !(d < 1.7976931348623157e308)) s_ok = 0;
-    }
     __syncthreads();
     double* Ai = R.A + i * bb;
     double* Bi = R.Bm + i * bb;
     double* Li = R.Li + i * bb;
-    for (int k = 0; k < b; ++k) {
-        if (!s_ok) break;  // uniform: written before the last barrier
-        const double w = s_piv[k & 1][0], inv = s_piv[k & 1][1];
-        const double* Mk = M + k * ld;
-        // outputs: row k of the border, scaled
-        if (ty == 31) {
-            for (int c = tx; c < b; c += 32) {
-                Ai[k * b + c] = Mk[b + c] * inv;
-                Bi[k * b + c] = Mk[2 * b + c] * inv;
-                Li[k * b + c] = Mk[3 * b + 1 + c] * inv;
+    const int nblk = b / 6;
+    // pivot of block step 0
+    if (tid == 0) {
+        double P[36], L[36], Linv[36];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) P[6 * a + q] = M[a * ld + q];
+        if (!potrf6_inv_reg(P, L, Linv)) s_ok = 0;
+#pragma unroll
+        for (int q = 0; q < 36; ++q) sLi[q] = Linv[q];
+    }
+    __syncthreads();
+    for (int kb = 0; kb < nblk; ++kb) {
+        if (!s_ok) break;
+        const int k0 = 6 * kb;
+        const double* Lcur = sLi + 36 * (kb & 1);
+        double* Lnext = sLi + 36 * ((kb + 1) & 1);
+        // ---- (2) panel: rows below the pivot, and the pivot's border row block --------------------
+        {
+            const int nrow = b - k0 - 6;
+            for (int t = tid; t < nrow + nbord; t += BCR_T) {
+                double v[6], o[6];
+                if (t < nrow) {
+                    double* p = M + (k0 + 6 + t) * ld + k0;  // A_rk, 6 contiguous entries of row r
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] = p[q];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q)
+                            if (q <= a) acc += v[q] * Lcur[6 * a + q];
+                        o[a] = acc;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) p[q] = o[q];
+                } else {
+                    double* p = M + k0 * ld + b + (t - nrow);  // G_k column c, 6 entries with stride ld
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] = p[q * ld];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q)
+                            if (q <= a) acc += Lcur[6 * a + q] * v[q];
+                        o[a] = acc;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) p[q * ld] = o[q];
+                }
             }
-            if (tx == 0) R.g[(long long)i * b + k] = Mk[3 * b] * inv;
         }
-        // trailing update
-        for (int r = k + 1 + ty; r < b; r += 32) {
+        __syncthreads();
+        // ---- outputs: X_k (6 x border) is final -------------------------------------------------
+        for (int t = tid; t < 6 * nbord; t += BCR_T) {
+            const int a = t / nbord, c = t - a * nbord;
+            const double v = M[(k0 + a) * ld + b + c];
+            const int k = k0 + a;
+            if (c < b)
+                Ai[k * b + c] = v;
+            else if (c < 2 * b)
+                Bi[k * b + (c - b)] = v;
+            else if (c == 2 * b)
+                R.g[(long long)i * b + k] = v;
+            else
+                Li[k * b + (c - 2 * b - 1)] = v;
+        }
+        // ---- look-ahead: thread 0 brings the NEXT pivot block up to date and factors it while the
+        // other warps apply the trailing update (which leaves that 6x6 block to it) ---------------
+        if (tid == 0 && kb + 1 < nblk) {
+            double P[36], L[36], Linv[36];
+            const int k1 = k0 + 6;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int q = 0; q <= a; ++q) {
+                    double acc = M[(k1 + a) * ld + k1 + q];
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) acc -= M[(k1 + a) * ld + k0 + m] * M[(k1 + q) * ld + k0 + m];
+                    P[6 * a + q] = acc;
+                }
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int q = a + 1; q < 6; ++q) P[6 * a + q] = 0.0;
+            if (!potrf6_inv_reg(P, L, Linv)) s_ok = 0;
+#pragma unroll
+            for (int q = 0; q < 36; ++q) Lnext[q] = Linv[q];
+        }
+        // ---- (3) trailing update (two columns per pass: independent chains) -----------------------
+        // columns k0+6 .. k0+11 of rows k0+6 .. k0+11 belong to the look-ahead thread; the rest of those
+        // columns (rows below) is updated here as usual
+        for (int r = k0 + 6 + (ty - 1); ty > 0 && r < b; r += TY - 1) {  // warp 0 is the look-ahead warp
             double* Mr = M + r * ld;
-            const double lr = Mr[k] * w;
-            int c = k + 1 + tx;
-            for (; c < b; c += 32) Mr[c] -= lr * M[c * ld + k];
-            for (; c < ld; c += 32) Mr[c] -= lr * Mk[c];
-            if (r == k + 1 && tx == 0) {
-                // the next pivot is final now: its reciprocals for the step after the barrier
-                const double d = Mr[k + 1];
-                double iv = rsqrt(d);
-                iv = iv * (1.5 - 0.5 * d * iv * iv);
-                s_piv[(k + 1) & 1][0] = 1.0 / d;
-                s_piv[(k + 1) & 1][1] = iv;
-                if (!(d > 0.0) || !(d < 1.7976931348623157e308)) s_ok = 0;
+            double lr[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) lr[q] = Mr[k0 + q];
+            const bool in_next = r < k0 + 12;
+            int c = k0 + 6 + tx;
+            for (; c < b; c += 32) {
+                if (in_next && c < k0 + 12) continue;  // next pivot block: thread 0's
+                const double* Lc = M + c * ld + k0;
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) acc += lr[q] * Lc[q];
+                Mr[c] -= acc;
+            }
+            for (; c + 32 < ld; c += 64) {
+                const double* X0 = M + k0 * ld + c;
+                const double* X1 = X0 + 32;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    a0 += lr[q] * X0[q * ld];
+                    a1 += lr[q] * X1[q * ld];
+                }
+                Mr[c] -= a0;
+                Mr[c + 32] -= a1;
+            }
+            for (; c < ld; c += 32) {
+                const double* Xc = M + k0 * ld + c;
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) acc += lr[q] * Xc[q * ld];
+                Mr[c] -= acc;
             }
         }
         __syncthreads();
@@ -619,7 +713,8 @@ __global__ void __launch_bounds__(BCR_T) bcr_odd_kernel(BcrView R, int first, in
     if (!s_ok && tid == 0) *R.fail = 1;
 }
 
-// rows i = blockIdx.x * 2s
+// rows i = blockIdx.x * 2s.  The three b x b products are computed in 2 x 3 register tiles (six
+// independent accumulation chains per product and thread).
 __global__ void __launch_bounds__(BCR_T) bcr_even_kernel(BcrView R, int s) {
     extern __shared__ __align__(16) double smem_bcr[];
     const int b = R.b, tid = threadIdx.x;
@@ -644,17 +739,35 @@ __global__ void __launch_bounds__(BCR_T) bcr_even_kernel(BcrView R, int s) {
     __syncthreads();
     double* Di = R.D + i * bb;
     double* Ei = R.E + i * bb;
-    for (int idx = tid; idx < b * b; idx += BCR_T) {
-        const int r = idx / b, c = idx - r * b;
-        double dd = 0.0, ee = 0.0;
-#pragma unroll 6
+    const int tr = b / 2, tc = b / 3;  // b = 6 W: both divide
+    for (int t = tid; t < tr * tc; t += BCR_T) {
+        const int r0 = 2 * (t / tc), c0 = 3 * (t % tc);
+        double dd[2][3] = {{0, 0, 0}, {0, 0, 0}}, ee[2][3] = {{0, 0, 0}, {0, 0, 0}};
+#pragma unroll 2
         for (int k = 0; k < b; ++k) {
-            const double x1 = X1[k * b + r];
-            dd += x1 * X1[k * b + c] + X3[k * b + r] * X3[k * b + c];
-            ee += x1 * X2[k * b + c];
+            const double* x1 = X1 + k * b;
+            const double* x2 = X2 + k * b;
+            const double* x3 = X3 + k * b;
+            const double a1[2] = {x1[r0], x1[r0 + 1]}, a3[2] = {x3[r0], x3[r0 + 1]};
+            const double b1[3] = {x1[c0], x1[c0 + 1], x1[c0 + 2]};
+            const double b2[3] = {x2[c0], x2[c0 + 1], x2[c0 + 2]};
+            const double b3[3] = {x3[c0], x3[c0 + 1], x3[c0 + 2]};
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    dd[u][w] += a1[u] * b1[w] + a3[u] * b3[w];
+                    ee[u][w] += a1[u] * b2[w];
+                }
         }
-        Di[idx] -= dd;
-        if (has_ll) Ei[idx] = -ee;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int idx = (r0 + u) * b + c0 + w;
+                Di[idx] -= dd[u][w];
+                if (has_ll) Ei[idx] = -ee[u][w];
+            }
     }
     for (int r = tid; r < b; r += BCR_T) {
         double ff = 0.0;
@@ -663,37 +776,59 @@ __global__ void __launch_bounds__(BCR_T) bcr_even_kernel(BcrView R, int s) {
     }
 }
 
-// y_i = Li^T (g - A y_{i-s} - Bm y_{i+s}): a warp per row for the two products (lanes along the row:
-// coalesced), then a thread per entry for the transposed triangular product
+// y_i = Li^T (g - A y_{i-s} - Bm y_{i+s}).  A_i, Bm_i and Li_i are staged in shared memory with one
+// wave of coalesced loads (the products themselves are tiny; the kernel is load latency).
 __global__ void __launch_bounds__(256) bcr_backsub_kernel(BcrView R, int first, int step, int s) {
     extern __shared__ __align__(16) double smem_bcr[];
-    const int b = R.b, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int b = R.b, tid = threadIdx.x;
     const int i = first + blockIdx.x * step;
     const bool has_l = s > 0 && i - s >= 0, has_r = s > 0 && i + s < R.N;
     const long long bb = (long long)b * b;
     if (*R.fail) return;
-    double* t = smem_bcr;
+    double* sA = smem_bcr;
+    double* sB = sA + b * b;
+    double* sL = sB + b * b;
+    double* t = sL + b * b;
     double* yl = t + b;
     double* yr = yl + b;
+    const double* Ai = R.A + i * bb;
+    const double* Bi = R.Bm + i * bb;
+    const double* Li = R.Li + i * bb;
+    for (int idx = tid; idx < b * b; idx += 256) {
+        sA[idx] = Ai[idx];
+        sB[idx] = Bi[idx];
+        sL[idx] = Li[idx];
+    }
     for (int r = tid; r < b; r += 256) {
         yl[r] = has_l ? R.y[(long long)(i - s) * b + r] : 0.0;
         yr[r] = has_r ? R.y[(long long)(i + s) * b + r] : 0.0;
+        t[r] = R.g[(long long)i * b + r];
     }
     __syncthreads();
-    const double* Ai = R.A + i * bb;
-    const double* Bi = R.Bm + i * bb;
-    for (int r = wib; r < b; r += 8) {
+    // 4 threads per row for the two products
+    {
+        const int r = tid >> 2, part = tid & 3;
         double v = 0.0;
-        for (int k = lane; k < b; k += 32) v += Ai[r * b + k] * yl[k] + Bi[r * b + k] * yr[k];
-        v = warp_sum(v);
-        if (lane == 0) t[r] = R.g[(long long)i * b + r] - v;
+        if (r < b)
+            for (int k = part; k < b; k += 4) v += sA[r * b + k] * yl[k] + sB[r * b + k] * yr[k];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        __syncthreads();
+        if (r < b && part == 0) t[r] -= v;
+        // rows beyond 64 (b = 72)
+        for (int r2 = 64 + (tid >> 2); r2 < b; r2 += 64) {
+            double v2 = 0.0;
+            for (int k = part; k < b; k += 4) v2 += sA[r2 * b + k] * yl[k] + sB[r2 * b + k] * yr[k];
+            v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+            if (part == 0) t[r2] -= v2;
+        }
     }
     __syncthreads();
-    const double* Li = R.Li + i * bb;
     for (int r = tid; r < b; r += 256) {
         double v = 0.0;
 #pragma unroll 6
-        for (int k = r; k < b; ++k) v += Li[k * b + r] * t[k];  // (L^-T t)_r, L^-1 lower triangular
+        for (int k = r; k < b; ++k) v += sL[k * b + r] * t[k];  // (L^-T t)_r, L^-1 lower triangular
         R.y[(long long)i * b + r] = v;
     }
 }
@@ -736,11 +871,17 @@ static int bcr_solve(cudaStream_t st, const BandView& V, const BandScratch& K, i
         levels[nl++] = s;
     }
     bcr_odd_kernel<<<1, BCR_T, smem_odd, st>>>(R, 0, 1, 0);  // the last row standing
-    bcr_backsub_kernel<<<1, 256, 3 * R.b * sizeof(double), st>>>(R, 0, 1, 0);
+    const size_t smem_bs = sizeof(double) * (3 * size_t(bb) + 3 * R.b);
+    static size_t attr_bs = 0;
+    if (smem_bs > attr_bs) {
+        CSLAM_CUDA(cudaFuncSetAttribute(bcr_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bs)));
+        attr_bs = smem_bs;
+    }
+    bcr_backsub_kernel<<<1, 256, smem_bs, st>>>(R, 0, 1, 0);
     launched += 2;
     for (int l = nl - 1; l >= 0; --l) {
         const int s = levels[l], n_odd = (R.N - s - 1) / (2 * s) + 1;
-        bcr_backsub_kernel<<<n_odd, 256, 3 * R.b * sizeof(double), st>>>(R, s, 2 * s, s);
+        bcr_backsub_kernel<<<n_odd, 256, smem_bs, st>>>(R, s, 2 * s, s);
         ++launched;
     }
     CSLAM_CUDA(cudaGetLastError());
