@@ -876,8 +876,11 @@ void Engine::check_phong_solve() {
     ph.n_tex = int(n_tex_shared);
     ph.n_g = 3 * ph.n_mat + ph.n_tex + 3;
     if (ph.n_g > 96) not_impl("lighting solve: at most 96 shared columns (3 per material + 1 per texture + 3)");
-    for (int j = 0; j < n_lm; ++j)
+    ph.max_track = 0;
+    for (int j = 0; j < n_lm; ++j) {
         if (lm_cnt_h[j] > 32) not_impl("lighting solve: at most 32 observations per vertex");
+        ph.max_track = std::max(ph.max_track, int(lm_cnt_h[j]));
+    }
 }
 
 void Engine::setup_phong_solve() {
@@ -1034,7 +1037,7 @@ void Engine::schur_pass() {
     prof_begin(CSLAM_K_SCHUR);
     d_red.zero(stream);
     if (ph.active) {
-        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, dg, phong_system(), true);
+        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, dg, phong_system(), true, ph.max_track);
     } else {
         launch_schur(v, dg);
         if (rank == 0)
@@ -1165,7 +1168,7 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
     const PhongSolveView q = phong_solve_view(ph.normals.p, ph.gx.p);
     prof_begin(CSLAM_K_BACKSUB);
     d_scal2.zero(stream);
-    launch_phong_backsub(stream, v, q, 0, n_lm, dg, d_yp.p, ph.yg.p, ph.gv.p, ph.yv.p, d_scal2.p);
+    launch_phong_backsub(stream, v, q, 0, n_lm, dg, d_yp.p, ph.yg.p, ph.gv.p, ph.yv.p, d_scal2.p, ph.max_track);
     if (bounded) {
         launch_dot(stream, d_gp, d_yp.p, 6ll * n_free, d_scal2.p + SC_LS_GY);
         launch_dot(stream, ph.gg, ph.yg.p, ph.n_g, d_scal2.p + SC_LS_GY);
@@ -1173,7 +1176,7 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
         launch_absmax_scaled(stream, ph.yg.p, ph.sc_g.p, ph.n_g, d_scal2.p + SC_LS_DMAX);
     }
     launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p, d_points_cand.p,
-                           ph.normals_cand.p, d_scal2.p, 1);
+                           ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
     read_scalars(d_scal2.p, sc2, SC_COUNT);
     if (bounded && sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0) {
         const double g0 = -sc2[SC_LS_GY], dmax = sc2[SC_LS_DMAX];
@@ -1205,7 +1208,7 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
             a_cur = a_new;
             d_scal2.zero(stream);
             launch_phong_candidate(stream, v, q, 0, n_lm, a_cur, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p,
-                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1);
+                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
             read_scalars(d_scal2.p, sc2, SC_COUNT);
             f_cur = sc2[SC_CAND_COST];
         }
@@ -1213,7 +1216,7 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
             // the search failed: Ceres keeps the full step
             d_scal2.zero(stream);
             launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p,
-                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1);
+                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
             read_scalars(d_scal2.p, sc2, SC_COUNT);
         }
         sc2[SC_MODEL] = model;
@@ -1333,7 +1336,7 @@ void Engine::lm_begin() {
     d_red.zero(stream);
     if (ph.active) {
         const LmDiag unit{1.0, opt.min_lm_diagonal, opt.max_lm_diagonal};
-        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, unit, phong_system(), false);
+        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, unit, phong_system(), false, ph.max_track);
     } else {
         launch_colnorm(stream, v, 0, n_lm, d_Bdiag, d_cn_l.p, d_gp, d_gl.p, d_scal);
         if (rank == 0)

@@ -333,7 +333,7 @@ class Engine {
     // joint lighting solve (dataset_ba_phong stage 3): vertex = position + normal, shared blocks gx
     struct PhongSolve {
         bool active = false;
-        int n_g = 0, n_mat = 0, n_tex = 0;
+        int n_g = 0, n_mat = 0, n_tex = 0, max_track = 0;
         DBuf<double> normals, normals_cand, normals_best, normals_init;
         DBuf<double> gx, gx_cand, gx_best, gx_init;
         DBuf<int> v_mat, v_tex, g_used;

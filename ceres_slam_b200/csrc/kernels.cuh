@@ -94,17 +94,17 @@ void launch_phong_eval(cudaStream_t s, const PhongView& v, double* r_int, double
 
 // K2p / K4p — joint lighting solve (kernels_phong_solve.cu)
 void launch_phong_build(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
-                        const PhongSystem& o, bool schur);
+                        const PhongSystem& o, bool schur, int max_track_len);
 void launch_phong_gfinalize(cudaStream_t s, const PhongSolveView& q, LmDiag dg, double* Sgg, double* bg, const double* hg,
                             double* diag_g);
 // border elimination: X holds n_g + 1 solves against S_cc (border columns, then b_c)
 void launch_phong_border_solve(cudaStream_t s, int n_g, int nf6, const double* Scg, const double* X, const double* Sgg,
                                const double* bg, double* T, double* yg, double* yc, double* ps);
 void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
-                          const double* yp, const double* yg, const double* gv, double* yv, double* scal2);
+                          const double* yp, const double* yg, const double* gv, double* yv, double* scal2, int max_track_len);
 void launch_phong_candidate(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, double alpha,
                             const double* yp, const double* yg, const double* yv, double* poses_cand, double* gx_cand,
-                            double* points_cand, double* normals_cand, double* scal2, int count_shared);
+                            double* points_cand, double* normals_cand, double* scal2, int count_shared, int max_track_len);
 void launch_phong_gradnorm(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, const double* gv,
                            const double* gg, double* scal, int count_shared);
 void launch_phong_project_initial(cudaStream_t s, const PhongSolveView& q, int n_lm, double* normals, double* gx_out,

@@ -33,6 +33,14 @@ __device__ __forceinline__ int find_block(const int* __restrict__ rowptr, const 
     return lo;  // the pattern is built from co-visibility, so the block exists
 }
 
+// sum over the LW lanes of the caller's segment of the warp (LW = 32: the whole warp)
+template <int LW>
+__device__ __forceinline__ double seg_sum(double v) {
+#pragma unroll
+    for (int o = LW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // Cholesky-based inverse of a symmetric positive definite 6x6 (full storage in, full out).
 __device__ __forceinline__ bool spd6_inverse(const double* A, double* Ainv) {
     double L[36];
@@ -224,31 +232,35 @@ __device__ __forceinline__ void add_lm_diag(double* V, const LmDiag& dg) {
 // K2p — fused residual/Jacobian + elimination of the vertex blocks.
 // kSchur == false: the initial pass (cost, squared column norms, gradient) with unit scaling.
 // =============================================================================================
-template <bool kSchur>
+// LW lanes per vertex: 32 (tracks up to 32 observations) or 16 (two vertices per warp, one per half).
+template <bool kSchur, int LW>
 __global__ void __launch_bounds__(PB_WARPS * 32)
     phong_build_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, LmDiag dg, PhongSystem o) {
     __shared__ double sW[PB_WARPS][36 * 32];  // W of every lane, [k][lane]
-    __shared__ double sG[PB_WARPS][72];       // the vertex's global contributions, staged for the atomics
+    __shared__ double sG[PB_WARPS][32 / LW][72];  // the vertex's global contributions, staged for the atomics
     __shared__ int sF[PB_WARPS][32];
     __shared__ double s_red[32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NSUB = 32 / LW;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lv = lane % LW, sub = lane / LW, lbase = sub * LW;
     double* myW = sW[wib];
-    double* myG = sG[wib];
+    double* myG = sG[wib][sub];
     int* myF = sF[wib];
     const int nf6 = 6 * v.n_free;
     double cost = 0.0;
     const int warps_total = gridDim.x * PB_WARPS;
-    for (int j = lm_lo + blockIdx.x * PB_WARPS + wib; j < lm_hi; j += warps_total) {
+    for (int jb = lm_lo + (blockIdx.x * PB_WARPS + wib) * NSUB; jb < lm_hi; jb += warps_total * NSUB) {
+        const bool vok = jb + sub < lm_hi;
+        const int j = vok ? jb + sub : lm_hi - 1;  // an idle half re-reads the last vertex and writes nothing
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
-        const int L = int(v.lm_cnt[j]);
+        const int L = vok ? int(v.lm_cnt[j]) : 0;
         VertexCtx c;
         load_vertex(v, q, j, c);
         PhObs ob;
         ob.f = -1;
-        const bool act = lane < L;
+        const bool act = lv < L;
         double V21[21], gv[6], r7[7];
         if (act) {
-            eval_phong_obs(v, q, e0 + lane * es, c, ob);
+            eval_phong_obs(v, q, e0 + lv * es, c, ob);
             r7[0] = ob.rs[0], r7[1] = ob.rs[1], r7[2] = ob.rs[2], r7[3] = ob.rI;
             r7[4] = ob.rN[0], r7[5] = ob.rN[1], r7[6] = ob.rN[2];
 #pragma unroll
@@ -266,18 +278,18 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
             ob.rI = 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < 21; ++k) V21[k] = warp_sum(V21[k]);
+        for (int k = 0; k < 21; ++k) V21[k] = seg_sum<LW>(V21[k]);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) gv[k] = warp_sum(gv[k]);
+        for (int k = 0; k < 6; ++k) gv[k] = seg_sum<LW>(gv[k]);
         // globals: gradient and diagonal (always), G and H_gg (Schur pass)
         double ggl[7], hd[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
-            ggl[k] = warp_sum(ob.ag[k] * ob.rI);
-            hd[k] = warp_sum(ob.ag[k] * ob.ag[k]);
+            ggl[k] = seg_sum<LW>(ob.ag[k] * ob.rI);
+            hd[k] = seg_sum<LW>(ob.ag[k] * ob.ag[k]);
         }
         if (!kSchur) {
-            if (lane == 0) {
+            if (lv == 0 && vok) {
                 int idx = 0;
 #pragma unroll
                 for (int a = 0; a < 6; ++a) {
@@ -314,20 +326,20 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         for (int k = 0; k < 7; ++k) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                G[6 * k + a] = warp_sum(ob.ag[k] * ob.ip[a]);
-                G[6 * k + 3 + a] = warp_sum(ob.ag[k] * ob.in[a]);
+                G[6 * k + a] = seg_sum<LW>(ob.ag[k] * ob.ip[a]);
+                G[6 * k + 3 + a] = seg_sum<LW>(ob.ag[k] * ob.in[a]);
             }
         }
         double V[36], Vi[36];
         unpack_sym6(V21, V);
         add_lm_diag(V, dg);
-        const bool pd = spd6_inverse(V, Vi);
-        if (lane == 0) {
+        const bool pd = spd6_inverse(V, Vi) && vok;
+        if (lv == 0 && vok) {
 #pragma unroll
             for (int a = 0; a < 6; ++a) o.gv[6ll * j + a] = gv[a];
             if (!pd) red_add(&o.scal[SC_INVALID], 1.0);
         }
-        if (!pd) continue;
+        // (no early exit: the other half of the warp may hold a valid vertex; `pd` guards every write)
         // GV = G Vi (7x6)
         double GV[42];
 #pragma unroll
@@ -347,10 +359,10 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
             for (int k = 0; k < 7; ++k)
 #pragma unroll
                 for (int k2 = k; k2 < 7; ++k2) {
-                    double h = (k2 == k) ? hd[k] : warp_sum(ob.ag[k] * ob.ag[k2]);
+                    double h = (k2 == k) ? hd[k] : seg_sum<LW>(ob.ag[k] * ob.ag[k2]);
 #pragma unroll
                     for (int a = 0; a < 6; ++a) h -= GV[6 * k + a] * G[6 * k2 + a];
-                    if (lane == 0) myG[idx] = h;
+                    if (lv == 0) myG[idx] = h;
                     ++idx;
                 }
 #pragma unroll
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
                 double bb = ggl[k];
 #pragma unroll
                 for (int a = 0; a < 6; ++a) bb -= GV[6 * k + a] * gv[a];
-                if (lane == 0) {
+                if (lv == 0) {
                     myG[28 + k] = bb;
                     myG[35 + k] = ggl[k];
                     myG[42 + k] = hd[k];
@@ -368,29 +380,29 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         __syncwarp();
         // 28 upper entries of the 7x7 block (mirrored), then rhs / gradient / diagonal
         {
-            // lane -> (k, k2) of the upper triangle
-            if (lane < 28) {
-                int k = 0, rem = lane;
+            // entry -> (k, k2) of the upper triangle
+            for (int en = lv; en < 28 && pd; en += LW) {
+                int k = 0, rem = en;
                 while (rem >= 7 - k) {
                     rem -= 7 - k;
                     ++k;
                 }
                 const int k2 = k + rem;
-                const double h = myG[lane];
+                const double h = myG[en];
                 const int gk = c.gi[k], gk2 = c.gi[k2];
                 red_add(&o.Sgg[(long long)gk * q.n_g + gk2], h);
                 if (gk != gk2) red_add(&o.Sgg[(long long)gk2 * q.n_g + gk], h);
             }
-            if (lane < 7) {
-                red_add(&o.bg[c.gi[lane]], myG[28 + lane]);
-                red_add(&o.gg[c.gi[lane]], myG[35 + lane]);
-                red_add(&o.hg[c.gi[lane]], myG[42 + lane]);
+            if (lv < 7 && pd) {
+                red_add(&o.bg[c.gi[lv]], myG[28 + lv]);
+                red_add(&o.gg[c.gi[lv]], myG[35 + lv]);
+                red_add(&o.hg[c.gi[lv]], myG[42 + lv]);
             }
         }
         // ---- camera part --------------------------------------------------------------------
         double Y[36];
-        myF[lane] = act ? ob.f : -1;
-        if (act && ob.f >= 0) {
+        myF[lane] = (act && pd) ? ob.f : -1;
+        if (act && pd && ob.f >= 0) {
             double W[36];
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
@@ -441,12 +453,13 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         __syncwarp();
         // camera pairs: lane x takes the pairs (x, (x + s) mod L), s = 0 .. L/2 — every unordered
         // pair once, all lanes busy
-        if (act && ob.f >= 0) {
+        if (act && pd && ob.f >= 0) {
             const int fx = ob.f;
             for (int s = 0; s <= L / 2; ++s) {
-                if (2 * s == L && lane >= s) break;  // even L: the antipodal pairs appear twice
-                int y = lane + s;
+                if (2 * s == L && lv >= s) break;  // even L: the antipodal pairs appear twice
+                int y = lv + s;
                 if (y >= L) y -= L;
+                y += lbase;
                 const int fy = myF[y];
                 if (fy < 0) continue;
                 double Wy[36];
@@ -490,25 +503,29 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
 // =============================================================================================
 // K4p — back-substitution of the vertex blocks and the model cost change
 // =============================================================================================
+template <int LW>
 __global__ void __launch_bounds__(PB_WARPS * 32)
     phong_backsub_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, LmDiag dg, const double* __restrict__ yp,
                          const double* __restrict__ yg, const double* __restrict__ gv, double* __restrict__ yv_out,
                          double* __restrict__ scal2) {
     __shared__ double s_red[32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NSUB = 32 / LW;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lv = lane % LW, sub = lane / LW;
     double model = 0.0, bad = 0.0, gy = 0.0, dmax = 0.0;
     const int warps_total = gridDim.x * PB_WARPS;
-    for (int j = lm_lo + blockIdx.x * PB_WARPS + wib; j < lm_hi; j += warps_total) {
+    for (int jb = lm_lo + (blockIdx.x * PB_WARPS + wib) * NSUB; jb < lm_hi; jb += warps_total * NSUB) {
+        const bool vok = jb + sub < lm_hi;
+        const int j = vok ? jb + sub : lm_hi - 1;
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
-        const int L = int(v.lm_cnt[j]);
+        const int L = vok ? int(v.lm_cnt[j]) : 0;
         VertexCtx c;
         load_vertex(v, q, j, c);
         PhObs ob;
         ob.f = -1;
-        const bool act = lane < L;
+        const bool act = lv < L;
         double V21[21], t6[6], r7[7], Jy[7];
         if (act) {
-            eval_phong_obs(v, q, e0 + lane * es, c, ob);
+            eval_phong_obs(v, q, e0 + lv * es, c, ob);
             r7[0] = ob.rs[0], r7[1] = ob.rs[1], r7[2] = ob.rs[2], r7[3] = ob.rI;
             r7[4] = ob.rN[0], r7[5] = ob.rN[1], r7[6] = ob.rN[2];
             // J y restricted to the camera and global columns
@@ -541,9 +558,9 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
             for (int k = 0; k < 6; ++k) t6[k] = 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < 21; ++k) V21[k] = warp_sum(V21[k]);
+        for (int k = 0; k < 21; ++k) V21[k] = seg_sum<LW>(V21[k]);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) t6[k] = warp_sum(t6[k]);
+        for (int k = 0; k < 6; ++k) t6[k] = seg_sum<LW>(t6[k]);
         double V[36], Vi[36], yv[6];
         unpack_sym6(V21, V);
         add_lm_diag(V, dg);
@@ -555,7 +572,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
             for (int b = 0; b < 6; ++b) s += Vi[6 * a + b] * t6[b];
             yv[a] = pd ? s : 0.0;
         }
-        if (lane == 0) {
+        if (lv == 0 && vok) {
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
                 yv_out[6ll * j + a] = yv[a];
@@ -587,17 +604,21 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
 }
 
 // Candidate vertices x (+) alpha * delta and the cost there (poses_cand / gx_cand already formed).
+template <int LW>
 __global__ void __launch_bounds__(PB_WARPS * 32)
     phong_candidate_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, double alpha, const double* __restrict__ yv,
                            const double* __restrict__ poses_cand, const double* __restrict__ gx_cand,
                            double* __restrict__ points_cand, double* __restrict__ normals_cand, double* __restrict__ scal2) {
     __shared__ double s_red[32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NSUB = 32 / LW;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lv = lane % LW, sub = lane / LW;
     double ccost = 0.0, sn = 0.0, xn = 0.0;
     const int warps_total = gridDim.x * PB_WARPS;
-    for (int j = lm_lo + blockIdx.x * PB_WARPS + wib; j < lm_hi; j += warps_total) {
+    for (int jb = lm_lo + (blockIdx.x * PB_WARPS + wib) * NSUB; jb < lm_hi; jb += warps_total * NSUB) {
+        const bool vok = jb + sub < lm_hi;
+        const int j = vok ? jb + sub : lm_hi - 1;
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
-        const int L = int(v.lm_cnt[j]);
+        const int L = vok ? int(v.lm_cnt[j]) : 0;
         VertexCtx c;
         load_vertex(v, q, j, c);
         double pn[3], dn[3], nn[3];
@@ -607,7 +628,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
             dn[k] = alpha * (-yv[6ll * j + 3 + k] * c.sn[k]);
         }
         unit_plus(c.n, dn, nn);
-        if (lane == 0) {
+        if (lv == 0 && vok) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 points_cand[3ll * j + k] = pn[k];
@@ -616,14 +637,14 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
                 xn += pn[k] * pn[k] + nn[k] * nn[k];
             }
         }
-        if (lane < L) {
+        if (lv < L) {
             double phong[3], light[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 phong[k] = gx_cand[c.gi[k]];
                 light[k] = gx_cand[c.gi[4 + k]];
             }
-            ccost += phong_obs_cost(v, q, e0 + lane * es, poses_cand, pn, nn, phong, gx_cand[c.gi[3]], light);
+            ccost += phong_obs_cost(v, q, e0 + lv * es, poses_cand, pn, nn, phong, gx_cand[c.gi[3]], light);
         }
     }
     block_atomic_sum(ccost, &scal2[SC_CAND_COST], s_red);
@@ -861,13 +882,21 @@ inline int vertex_grid(int n) {
 }  // namespace
 
 void launch_phong_build(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
-                        const PhongSystem& o, bool schur) {
+                        const PhongSystem& o, bool schur, int max_track_len) {
     if (lm_hi <= lm_lo) return;
-    const int grid = vertex_grid(lm_hi - lm_lo);
-    if (schur)
-        phong_build_kernel<true><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
-    else
-        phong_build_kernel<false><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+    // tracks of at most 16 observations: two vertices per warp
+    const bool packed = max_track_len <= 16;
+    const int grid = vertex_grid(packed ? (lm_hi - lm_lo + 1) / 2 : lm_hi - lm_lo);
+    if (schur) {
+        if (packed)
+            phong_build_kernel<true, 16><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+        else
+            phong_build_kernel<true, 32><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+    } else if (packed) {
+        phong_build_kernel<false, 16><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+    } else {
+        phong_build_kernel<false, 32><<<grid, PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, o);
+    }
     count_launch();
     CSLAM_CUDA(cudaGetLastError());
 }
@@ -907,24 +936,31 @@ void launch_phong_border_solve(cudaStream_t s, int n_g, int nf6, const double* S
 }
 
 void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
-                          const double* yp, const double* yg, const double* gv, double* yv, double* scal2) {
+                          const double* yp, const double* yg, const double* gv, double* yv, double* scal2, int max_track_len) {
     if (lm_hi <= lm_lo) return;
-    phong_backsub_kernel<<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
+    if (max_track_len <= 16)
+        phong_backsub_kernel<16><<<vertex_grid((lm_hi - lm_lo + 1) / 2), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
+    else
+        phong_backsub_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
     count_launch();
     CSLAM_CUDA(cudaGetLastError());
 }
 
 void launch_phong_candidate(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, double alpha,
                             const double* yp, const double* yg, const double* yv, double* poses_cand, double* gx_cand,
-                            double* points_cand, double* normals_cand, double* scal2, int count_shared) {
+                            double* points_cand, double* normals_cand, double* scal2, int count_shared, int max_track_len) {
     phong_pose_plus_kernel<<<(v.n_cams + 127) / 128, 128, 0, s>>>(v, alpha, yp, poses_cand, scal2, count_shared);
     count_launch();
     phong_global_plus_kernel<<<1, ((q.n_g + 31) / 32) * 32, 0, s>>>(q, alpha, -1.0, yg, 0, gx_cand, scal2, SC_STEP_NORM2,
                                                                      SC_XNORM2, SC_NONFINITE, -1, count_shared);
     count_launch();
     if (lm_hi > lm_lo) {
-        phong_candidate_kernel<<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, alpha, yv, poses_cand,
-                                                                                   gx_cand, points_cand, normals_cand, scal2);
+        if (max_track_len <= 16)
+            phong_candidate_kernel<16><<<vertex_grid((lm_hi - lm_lo + 1) / 2), PB_WARPS * 32, 0, s>>>(
+                v, q, lm_lo, lm_hi, alpha, yv, poses_cand, gx_cand, points_cand, normals_cand, scal2);
+        else
+            phong_candidate_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(
+                v, q, lm_lo, lm_hi, alpha, yv, poses_cand, gx_cand, points_cand, normals_cand, scal2);
         count_launch();
     }
     CSLAM_CUDA(cudaGetLastError());
