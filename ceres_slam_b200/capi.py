@@ -117,6 +117,7 @@ _COMMON = {
     "set_materials": (C.c_int, [_h, C.c_uint32, _dp]),
     "set_light": (C.c_int, [_h, _dp, C.c_int]),
     "set_bounds": (C.c_int, [_h, C.c_int, _dp, _dp]),
+    "set_points_constant": (C.c_int, [_h, C.c_int]),
     "add_phong": (C.c_int, [_h, C.c_uint64, _u32p, _u32p, _dp, C.c_double, _dp, _dp]),
 }
 _RANSAC_SIG = (C.c_int, [C.c_int, C.c_uint32, _u32p, _dp, _dp, _dp, C.c_uint32, C.c_double, C.c_int, _dp, _u8p, _u32p])

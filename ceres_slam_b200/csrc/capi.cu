@@ -236,6 +236,12 @@ cslam_status cslam_set_bounds(cslam_problem* p, int block_kind, const double* lo
         e.uploaded = e.begun = false;
     });
 }
+cslam_status cslam_set_points_constant(cslam_problem* p, int constant) {
+    return guarded(p, [&](Engine& e) {
+        e.hold_positions = constant != 0;
+        e.uploaded = e.begun = false;
+    });
+}
 cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double* phong3) {
     return guarded(p, [&](Engine& e) {
         if (!phong3 || n_materials == 0) throw std::invalid_argument("materials: null or empty");
@@ -333,8 +339,10 @@ cslam_status cslam_get_iteration_log(const cslam_problem* p, double* rows, int m
     if (!p || !p->e) return CSLAM_ERR_INVALID;
     const int n = int(p->e->log.size());
     if (n_rows) *n_rows = n;
-    for (int i = 0; i < n && i < max_rows && rows; ++i)
+    for (int i = 0; i < n && i < max_rows && rows; ++i) {
         std::memcpy(rows + CSLAM_LOG_COLS * i, p->e->log[i].v, CSLAM_LOG_COLS * sizeof(double));
+        rows[CSLAM_LOG_COLS * i + 1] += p->e->fixed_cost();  // IterationSummary::cost includes Ceres' fixed_cost
+    }
     return CSLAM_OK;
 }
 

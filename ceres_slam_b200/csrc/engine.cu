@@ -40,6 +40,7 @@ Engine::~Engine() {
     if (ev_c) cudaEventDestroy(ev_c);
     if (ev_d) cudaEventDestroy(ev_d);
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ph.fan_graph) cudaGraphExecDestroy(ph.fan_graph);
     band_sets.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -746,6 +747,11 @@ void Engine::plan_band_solver() {
 }
 
 void Engine::alloc_band_sets(int count) {
+    if (ph.fan_graph) {
+        cudaGraphExecDestroy(ph.fan_graph);  // captured over the old buffers
+        ph.fan_graph = nullptr;
+    }
+    ph.fan_calls = 0;
     band_sets.clear();
     if (!band_active || count <= 0) return;
     const int n = n_free, W = band_storage_width(band_w), P = band_P;
@@ -944,6 +950,7 @@ PhongSolveView Engine::phong_solve_view(const double* normals, const double* gx)
     q.n_mat = ph.n_mat;
     q.n_tex = ph.n_tex;
     q.n_g = ph.n_g;
+    q.hold_positions = hold_positions ? 1 : 0;
     for (int k = 0; k < 3; ++k) q.mat_lo[k] = mat_lo[k], q.mat_hi[k] = mat_hi[k];
     q.tex_lo = tex_lo;
     q.tex_hi = tex_hi;
@@ -977,22 +984,48 @@ void Engine::phong_linear_solve(int* iters, bool* ok) {
     const size_t nf6 = 6 * size_t(n_free);
     bool side_fail = false;
     if (n_free > 0 && band_active && !band_sets.empty()) {
-        // the n_g + 1 banded solves are independent: fan them out over the scratch sets' streams
-        CSLAM_CUDA(cudaEventRecord(ev_fork, stream));
-        for (auto& bs : band_sets) CSLAM_CUDA(cudaStreamWaitEvent(bs->stream, ev_fork, 0));
-        size_t slot = 0;
-        for (int k = 0; k <= ph.n_g; ++k) {
-            double* y = ph.X.p + size_t(k) * nf6;
-            if (k < ph.n_g && !ph.g_used_h[k]) {
-                CSLAM_CUDA(cudaMemsetAsync(y, 0, nf6 * sizeof(double), stream));
-                continue;
+        // the n_g + 1 banded solves are independent: fan them out over the scratch sets' streams.
+        // ~300 small enqueues per LM iteration are host-bound, so from the second call on the
+        // fan-out is replayed as ONE captured CUDA graph (same buffers every iteration).
+        auto fan_out = [&]() {
+            CSLAM_CUDA(cudaEventRecord(ev_fork, stream));
+            for (auto& bs : band_sets) CSLAM_CUDA(cudaStreamWaitEvent(bs->stream, ev_fork, 0));
+            size_t slot = 0;
+            for (int k = 0; k <= ph.n_g; ++k) {
+                double* y = ph.X.p + size_t(k) * nf6;
+                if (k < ph.n_g && !ph.g_used_h[k]) {
+                    CSLAM_CUDA(cudaMemsetAsync(y, 0, nf6 * sizeof(double), stream));
+                    continue;
+                }
+                const double* rhs = k < ph.n_g ? ph.Scg + size_t(k) * nf6 : d_bp;
+                solve_reduced_on(*band_sets[slot++ % band_sets.size()], rhs, y);
             }
-            const double* rhs = k < ph.n_g ? ph.Scg + size_t(k) * nf6 : d_bp;
-            solve_reduced_on(*band_sets[slot++ % band_sets.size()], rhs, y);
-        }
-        for (auto& bs : band_sets) {
-            CSLAM_CUDA(cudaEventRecord(bs->done, bs->stream));
-            CSLAM_CUDA(cudaStreamWaitEvent(stream, bs->done, 0));
+            for (auto& bs : band_sets) {
+                CSLAM_CUDA(cudaEventRecord(bs->done, bs->stream));
+                CSLAM_CUDA(cudaStreamWaitEvent(stream, bs->done, 0));
+            }
+        };
+        if (ph.fan_graph) {
+            CSLAM_CUDA(cudaGraphLaunch(ph.fan_graph, stream));
+            g_kernel_launches.fetch_add(ph.fan_graph_kernels, std::memory_order_relaxed);
+        } else if (ph.fan_calls++ == 0) {
+            fan_out();  // plain the first time (function attributes, lazy module loading)
+        } else {
+            const unsigned long long k0 = g_kernel_launches.load();
+            CSLAM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            cudaGraph_t graph = nullptr;
+            try {
+                fan_out();
+            } catch (...) {
+                cudaStreamEndCapture(stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            CSLAM_CUDA(cudaStreamEndCapture(stream, &graph));
+            ph.fan_graph_kernels = g_kernel_launches.load() - k0;
+            CSLAM_CUDA(cudaGraphInstantiate(&ph.fan_graph, graph, 0));
+            CSLAM_CUDA(cudaGraphDestroy(graph));
+            CSLAM_CUDA(cudaGraphLaunch(ph.fan_graph, stream));
         }
         launch_fill(stream, d_pscal.p, PS_COUNT, 0.0);
         // every solve factors the same S: one status tells them all
@@ -1362,6 +1395,7 @@ void Engine::lm_begin() {
         throw std::domain_error("non-finite cost at the initial point");
     }
     lm.x_cost = lm.initial_cost = lm.minimum_cost = loc[SC_COST];
+    lm.fixed_cost = ph.active ? loc[SC_FIXED] : 0.0;
     lm.se_minimum = lm.se_current = lm.se_reference = lm.se_candidate = lm.x_cost;
     lm.radius = opt.initial_trust_region_radius;
     lm.decrease_factor = 2.0;
@@ -1378,8 +1412,8 @@ void Engine::lm_begin() {
 void Engine::fill_summary(cslam_summary* s) const {
     if (!s) return;
     std::memset(s, 0, sizeof(*s));
-    s->initial_cost = lm.initial_cost;
-    s->final_cost = lm.minimum_cost;
+    s->initial_cost = lm.initial_cost + lm.fixed_cost;
+    s->final_cost = lm.minimum_cost + lm.fixed_cost;
     s->num_iterations = lm.iteration;
     s->num_successful_steps = lm.num_successful;
     s->num_unsuccessful_steps = lm.num_unsuccessful;

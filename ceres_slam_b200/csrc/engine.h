@@ -26,6 +26,7 @@ enum Scal {
     SC_NONFINITE = 8,    // non-finite step entries
     SC_LS_GY = 9,        // g . y (scaled coordinates): the line search's directional derivative is -g.y
     SC_LS_DMAX = 10,     // |delta|_inf (bit-pattern max)
+    SC_FIXED = 11,       // cost of the residual blocks without a variable parameter block (Ceres' fixed_cost)
     SC_COUNT = 32
 };
 // PCG scalar slots
@@ -136,6 +137,8 @@ struct PhongSolveView {
     double Wn[9];
     double int_stiffness;
     int directional, n_mat, n_tex, n_g;
+    int hold_positions;      // every position block constant: its columns vanish; a stereo block whose
+                             // pose is constant too is dropped (its cost is Ceres' fixed_cost)
     double mat_lo[3], mat_hi[3], tex_lo, tex_hi;
 };
 // Where the vertex-elimination kernel accumulates the arrowhead reduced system.
@@ -193,6 +196,7 @@ class Engine {
     double mat_lo[3] = {-1e308, -1e308, -1e308}, mat_hi[3] = {1e308, 1e308, 1e308};
     double tex_lo = -1e308, tex_hi = 1e308;
     bool bounded = false;                     // cslam_set_bounds was called
+    bool hold_positions = false;              // cslam_set_points_constant
     double* h_light = nullptr;
     int light_directional = 0;
     uint64_t n_ph = 0;
@@ -228,6 +232,7 @@ class Engine {
     void set_stream(cudaStream_t s);
     void analyze(int n_ranks_, int rank_, cslam_structure_info* out);  // host only
 
+    double fixed_cost() const { return lm.fixed_cost; }
     std::vector<LmRow> log;
     cslam_profile prof{};
     bool uploaded = false, begun = false;
@@ -341,6 +346,9 @@ class Engine {
         DBuf<double> sc_n, sc_g, cn_n, gv, yv, yg, diag_g, X, T, zero_g;
         double *Scg = nullptr, *Sgg = nullptr, *bg = nullptr, *gg = nullptr, *hg = nullptr;  // inside d_red
         std::vector<int> g_used_h;
+        cudaGraphExec_t fan_graph = nullptr;   // the border solves' fan-out, captured on its second use
+        unsigned long long fan_graph_kernels = 0;
+        int fan_calls = 0;
     } ph;
     void check_phong_solve();
     void setup_phong_solve();
@@ -368,6 +376,7 @@ class Engine {
         int num_successful = 0, num_unsuccessful = 0, total_linear = 0;
         int termination_type = 1, termination_reason = 0;
         double initial_cost = 0;
+        double fixed_cost = 0;             // reported with every cost, no part in the decisions
         double device_ms = 0;
     } lm;
 

@@ -159,6 +159,13 @@ __device__ __forceinline__ void eval_phong_obs(const DevView& v, const PhongSolv
         o.ag[4 + k] = Jl[k] * c.sg[4 + k];
     }
     o.ag[3] = Jt[0] * c.sg[3];
+    if (q.hold_positions) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o.S[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.ip[k] = 0.0;
+        if (o.f < 0) o.rs[0] = o.rs[1] = o.rs[2] = 0.0;  // dropped block: no variable parameter left
+    }
     if (o.f >= 0) {
         const double* sp = v.sc_p + 6ll * o.f;
 #pragma unroll
@@ -183,6 +190,7 @@ __device__ __forceinline__ double phong_obs_cost(const DevView& v, const PhongSo
     const double* pose = poses + 12ll * cam;
     double rs[3], rI, rN[3];
     stereo_block<false>(v.cam, pose, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], v.obs_W, rs, nullptr, nullptr);
+    if (q.hold_positions && v.cam_free[cam] < 0) rs[0] = rs[1] = rs[2] = 0.0;
     intensity_block(pose, p, n, phong, kd, light, q.obs_I[e], q.int_stiffness, q.directional != 0, &rI, nullptr,
                     nullptr, nullptr, nullptr, nullptr, nullptr);
     const double nobs[3] = {q.obs_n[e], q.obs_n[v.n_obs + e], q.obs_n[2 * v.n_obs + e]};
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
     double* myG = sG[wib][sub];
     int* myF = sF[wib];
     const int nf6 = 6 * v.n_free;
-    double cost = 0.0;
+    double cost = 0.0, fixed = 0.0;
     const int warps_total = gridDim.x * PB_WARPS;
     for (int jb = lm_lo + (blockIdx.x * PB_WARPS + wib) * NSUB; jb < lm_hi; jb += warps_total * NSUB) {
         const bool vok = jb + sub < lm_hi;
@@ -265,6 +273,14 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
             r7[4] = ob.rN[0], r7[5] = ob.rN[1], r7[6] = ob.rN[2];
 #pragma unroll
             for (int k = 0; k < 7; ++k) cost += 0.5 * r7[k] * r7[k];
+            if (!kSchur && q.hold_positions && ob.f < 0) {
+                // the dropped stereo block's cost, once (initial pass): Ceres' fixed_cost
+                const long long e = e0 + lv * es;
+                double rs[3];
+                stereo_block<false>(v.cam, v.poses + 12ll * v.obs_cam[e], c.p, v.obs_u[e], v.obs_v[e], v.obs_d[e], v.obs_W, rs,
+                                    nullptr, nullptr);
+                fixed += 0.5 * (rs[0] * rs[0] + rs[1] * rs[1] + rs[2] * rs[2]);
+            }
             vertex_normal_eq(ob, r7, V21, gv);
         } else {
 #pragma unroll
@@ -498,6 +514,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         __syncwarp();
     }
     block_atomic_sum(cost, &o.scal[SC_COST], s_red);
+    if (!kSchur) block_atomic_sum(fixed, &o.scal[SC_FIXED], s_red);
 }
 
 // =============================================================================================
@@ -634,7 +651,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
                 points_cand[3ll * j + k] = pn[k];
                 normals_cand[3ll * j + k] = nn[k];
                 sn += (c.p[k] - pn[k]) * (c.p[k] - pn[k]) + (c.n[k] - nn[k]) * (c.n[k] - nn[k]);
-                xn += pn[k] * pn[k] + nn[k] * nn[k];
+                xn += (q.hold_positions ? 0.0 : pn[k] * pn[k]) + nn[k] * nn[k];
             }
         }
         if (lv < L) {
@@ -744,7 +761,7 @@ __global__ void phong_gradnorm_kernel(DevView v, PhongSolveView q, int lm_lo, in
             m = fmax(m, fabs(x - (x - g)));
             n[k] = q.normals[3ll * j + k];
             dn[k] = -gv[6ll * j + 3 + k] / q.sc_n[3ll * j + k];
-            xn += x * x + n[k] * n[k];
+            xn += (q.hold_positions ? 0.0 : x * x) + n[k] * n[k];
         }
         unit_plus(n, dn, nn);
         for (int k = 0; k < 3; ++k) m = fmax(m, fabs(n[k] - nn[k]));

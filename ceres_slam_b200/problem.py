@@ -135,6 +135,10 @@ class BAProblem:
         assert lo.size == hi.size == (3 if kind == 0 else 1)
         self._check(self.lib.set_bounds(self._h, kind, capi.dptr(lo), capi.dptr(hi)))
 
+    def set_points_constant(self, constant=True):
+        """SetParameterBlockConstant / Variable on every vertex position (lighting solves)."""
+        self._check(self.lib.set_points_constant(self._h, int(bool(constant))))
+
     def set_materials(self, phong):
         phong = np.ascontiguousarray(phong, dtype=np.float64).reshape(-1, 3)
         self._keep["materials"] = phong

@@ -180,6 +180,12 @@ cslam_status cslam_set_materials(cslam_problem* p, uint32_t n_materials, double*
  * line search (see oracle/phong_problem.hpp for the stated deviation in the interpolation). */
 cslam_status cslam_set_bounds(cslam_problem* p, int block_kind, const double* lower, const double* upper);
 cslam_status cslam_set_light(cslam_problem* p, double* light3, int directional);
+/* SetParameterBlockConstant / SetParameterBlockVariable on EVERY vertex position block (stage 2 of
+ * dataset_ba_phong --multistage, tests/dataset_ba_phong.cpp:209-220 and :236-239).  Lighting solves
+ * only.  With the poses constant as well (cslam_set_poses) the stereo blocks have no variable left:
+ * like Ceres, the solve drops them and carries their cost as a constant that is reported with every
+ * cost but takes no part in the minimiser's decisions. */
+cslam_status cslam_set_points_constant(cslam_problem* p, int constant);
 /* n observations, each adding one IntensityError{Point,Directional}LightAutomatic block
  * (dataset_ba_phong.cpp:103-123: pose, position, normal, phong params, texture, light) and one
  * NormalErrorAutomatic block (dataset_ba_phong.cpp:183-190: pose, normal).  int_stiffness =

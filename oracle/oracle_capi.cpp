@@ -238,6 +238,10 @@ int cslam_oracle_set_bounds(cslam_oracle_problem* p, int block_kind, const doubl
     q.bounded = true;
     return CSLAM_OK;
 }
+int cslam_oracle_set_points_constant(cslam_oracle_problem* p, int constant) {
+    p->ph.hold_positions = constant != 0;
+    return CSLAM_OK;
+}
 int cslam_oracle_add_phong(cslam_oracle_problem* p, uint64_t n, const uint32_t* cam, const uint32_t* vertex,
                            const double* intensity, double int_stiffness, const double* normal_obs3,
                            const double* W_normal9) {

@@ -51,6 +51,12 @@ class PhongProblem {
     bool directional = false;
     double mat_lo[3], mat_hi[3], tex_lo, tex_hi;
     bool bounded = false;
+    // SetParameterBlockConstant on every vertex position (stage 2 of --multistage,
+    // dataset_ba_phong.cpp:209-220): the position columns disappear, and a stereo block whose pose is
+    // constant too has no variable left — Ceres removes it from the reduced program and carries its
+    // cost as `fixed_cost`, which is reported but takes no part in the minimiser's decisions.
+    bool hold_positions = false;
+    double fixed_cost = 0.0;
 
     std::vector<uint32_t> cam, vtx;
     std::vector<double> uvd, intensity, normal_obs;
@@ -207,6 +213,12 @@ class PhongProblem {
                     else
                         for (int cc = 0; cc < 3; ++cc) ag[4 + cc] = Jl_i[cc];
                 }
+                if (hold_positions) {
+                    if (jac)
+                        for (int rr = 0; rr < 7; ++rr)
+                            for (int cc = 0; cc < 3; ++cc) L.Av[42 * i + 6 * rr + cc] = 0.0;
+                    if (pose_const[k]) r[0] = r[1] = r[2] = 0.0;  // dropped block (its cost is fixed_cost)
+                }
                 for (int q = 0; q < 7; ++q) c += 0.5 * r[q] * r[q];
             }
             partial[tid] += c;
@@ -228,7 +240,8 @@ class PhongProblem {
         }
         for (size_t a = 0; a < st.active_v.size(); ++a) {
             const size_t j = st.active_v[a];
-            for (int c = 0; c < 3; ++c) y.pos[3 * j + c] = x.pos[3 * j + c] + dv[6 * a + c];
+            if (!hold_positions)
+                for (int c = 0; c < 3; ++c) y.pos[3 * j + c] = x.pos[3 * j + c] + dv[6 * a + c];
             up(&x.nrm[3 * j], dv + 6 * a + 3, &y.nrm[3 * j]);
         }
         for (int m = 0; m < n_mat; ++m)
@@ -489,7 +502,17 @@ class PhongProblem {
             return false;
         }
         double x_cost = L.cost;
-        sum.initial_cost = x_cost;
+        fixed_cost = 0.0;
+        if (hold_positions) {
+            // cost of the removed blocks at the (never changing) constant parameters
+            const bool saved = hold_positions;
+            hold_positions = false;
+            Lin Lall;
+            evaluate(x, false, Lall, opt.num_threads);
+            hold_positions = saved;
+            fixed_cost = Lall.cost - L.cost;
+        }
+        sum.initial_cost = x_cost + fixed_cost;
         Scaling sc;
         sc.c.assign(6 * size_t(nf), 1.0);
         sc.v.assign(6 * na, 1.0);
@@ -507,7 +530,7 @@ class PhongProblem {
             for (size_t v = 0; v < na; ++v)
                 for (int c = 0; c < 3; ++c) {
                     const size_t idx = 3 * size_t(st.active_v[v]) + c;
-                    acc(a.pos[idx] - b2.pos[idx]);
+                    if (!hold_positions) acc(a.pos[idx] - b2.pos[idx]);
                     acc(a.nrm[idx] - b2.nrm[idx]);
                 }
             for (int q = 0; q < ng; ++q)
@@ -567,7 +590,7 @@ class PhongProblem {
             for (size_t v = 0; v < na; ++v)
                 for (int c = 0; c < 3; ++c) {
                     const size_t idx = 3 * size_t(st.active_v[v]) + c;
-                    s += a.pos[idx] * a.pos[idx] + a.nrm[idx] * a.nrm[idx];
+                    s += (hold_positions ? 0.0 : a.pos[idx] * a.pos[idx]) + a.nrm[idx] * a.nrm[idx];
                 }
             for (int q = 0; q < ng; ++q)
                 if (st.g_used[q]) s += a.g[q] * a.g[q];
@@ -804,8 +827,9 @@ class PhongProblem {
             sum.rows.push_back(row);
         }
         sum.num_iterations = iteration;
-        sum.final_cost = minimum_cost;
+        sum.final_cost = minimum_cost + fixed_cost;
         sum.final_radius = radius;
+        for (auto& rw : sum.rows) rw.cost += fixed_cost;  // IterationSummary::cost includes the fixed cost
         return sum.termination_type != FAILURE;
     }
 };
