@@ -87,6 +87,12 @@ class Problem {
         int_stiffness_ = int_stiffness;
         std::memcpy(Wn_, W_normal, 72);
     }
+    // problem.SetParameterBlockConstant / Variable on every vertex position (dataset_ba_phong.cpp:215-220, :236-239)
+    void SetPointsConstant(bool constant) { points_constant_ = constant; }
+    // problem.SetParameterBlockVariable(pose)
+    void SetParameterBlockVariable(double* pose12) { constant_[pose_index(pose12)] = 0; }
+    // drop the lighting blocks again (the stereo-only solve of stage 1 on the same Problem object)
+    bool HasLighting() const { return !ph_cam_.empty(); }
     // problem.SetParameterization(light_dir, UnitVectorPerturbation) (dataset_ba_phong.cpp:199-203)
     void SetLightDirectional(bool directional) { directional_ = directional; }
     // problem.SetParameterLowerBound / UpperBound on every material / texture block (:143-181)
@@ -163,6 +169,7 @@ class Problem {
                 check(cslam_set_light(p, light_, directional_ ? 1 : 0), p);
                 check(cslam_add_phong(p, ph_cam_.size(), ph_cam_.data(), ph_vtx_.data(), ph_int_.data(), int_stiffness_,
                                       ph_nobs_.data(), Wn_), p);
+                check(cslam_set_points_constant(p, points_constant_ ? 1 : 0), p);
                 if (mat_bounded_) check(cslam_set_bounds(p, 0, mat_lo_, mat_hi_), p);
                 if (tex_bounded_) check(cslam_set_bounds(p, 1, &tex_lo_, &tex_hi_), p);
             }
@@ -226,7 +233,7 @@ class Problem {
     std::map<double*, uint32_t> mat_id_, tex_id_;
     double* light_ptr_ = nullptr;
     double int_stiffness_ = 1.0, Wn_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    bool directional_ = false, mat_bounded_ = false, tex_bounded_ = false;
+    bool directional_ = false, mat_bounded_ = false, tex_bounded_ = false, points_constant_ = false;
     double mat_lo_[3] = {0, 0, 0}, mat_hi_[3] = {0, 0, 0}, tex_lo_ = 0, tex_hi_ = 0;
     std::map<double*, uint32_t> pose_id_, point_id_;
     std::vector<double*> pose_ptr_, point_ptr_;

@@ -5,11 +5,13 @@
 // intrinsics; `var_u,var_v,var_d,var_nx,var_ny,var_nz,var_I`; light position or direction; first
 // pose; rows `t,j,mat_id,u,v,d,I,nx,ny,nz` grouped by timestamp.
 // Trust-region strategy: Levenberg-Marquardt (the reference sets SUBSPACE_DOGLEG +
-// SPARSE_NORMAL_CHOLESKY, :87-90: SURVEY.md 8f-3).  --multistage (stage 2 holds poses and positions
-// constant, :207-246) is not built and is refused.
+// SPARSE_NORMAL_CHOLESKY, :87-90; DOGLEG is built for the stereo / sun / prior problems only).
+// --multistage runs the reference's three solves per window: stage 1 poses and points without
+// lighting (:94-98), stage 2 lighting only with every pose and position constant (:207-231), stage 3
+// everything jointly (:249-252).
 //
-//   usage: dataset_ba_phong_b200 <input_file> [--nolight | --dirlight] [--window N] [--max-iters M]
-//          [--material-by-observation]
+//   usage: dataset_ba_phong_b200 <input_file> [--nolight | --dirlight] [--window N] [--multistage]
+//          [--max-iters M] [--material-by-observation]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -116,8 +118,9 @@ static void initial_guess(PhongDataset& d, unsigned k1, unsigned k2, bool materi
                           });
 }
 
-static void solveWindow(PhongDataset& d, unsigned k1, unsigned k2, bool use_light, int max_iters) {
-    std::cerr << "Working on interval [" << k1 << "," << k2 << ")" << std::endl;
+// stage: 0 = the problem as the flags say (joint solve when use_light), 1 = stereo blocks only,
+// 2 = lighting only (every pose and vertex position constant)
+static void solve_stage(PhongDataset& d, unsigned k1, unsigned k2, bool use_light, int max_iters, int stage) {
     Problem problem;
     problem.SetCamera(d.intr[0], d.intr[1], d.intr[2], d.intr[3], d.intr[4]);
     const double cs[9] = {d.stereo_var[0], 0, 0, 0, d.stereo_var[1], 0, 0, 0, d.stereo_var[2]};
@@ -126,6 +129,7 @@ static void solveWindow(PhongDataset& d, unsigned k1, unsigned k2, bool use_ligh
     sym_inverse_sqrt(cs, 3, Ws);                      // :31-35
     sym_inverse_sqrt(cn, 3, Wn);                      // :37-41
     const double int_stiffness = 1. / std::sqrt(d.int_var);  // :43
+    const bool light = use_light && stage != 1;
     for (unsigned k = k1; k < k2; ++k) {
         double* P = &d.poses[12 * size_t(k)];
         problem.AddPoseBlock(P);                      // :72
@@ -134,7 +138,7 @@ static void solveWindow(PhongDataset& d, unsigned k1, unsigned k2, bool use_ligh
             if (!d.initialized[j]) continue;          // :57
             double* X = &d.positions[3 * size_t(j)];
             problem.AddStereoBlock(P, X, &d.obs.uvd[3 * size_t(i)], Ws);  // :59-67
-            if (use_light) {
+            if (light) {
                 const unsigned m = d.vertex_material[j];
                 problem.AddLightingBlocks(P, X, &d.normals[3 * size_t(j)], &d.materials[3 * size_t(m)], &d.textures[m], d.light,
                                           d.intensity[i], int_stiffness, &d.normal_obs[3 * size_t(i)], Wn);  // :103-190
@@ -142,7 +146,11 @@ static void solveWindow(PhongDataset& d, unsigned k1, unsigned k2, bool use_ligh
         }
     }
     problem.SetParameterBlockConstant(&d.poses[12 * size_t(k1)]);  // :76
-    if (use_light) {
+    if (stage == 2) {
+        for (unsigned k = k1; k < k2; ++k) problem.SetParameterBlockConstant(&d.poses[12 * size_t(k)]);  // :222
+        problem.SetPointsConstant(true);                                                                // :215-220
+    }
+    if (light) {
         const double lo[3] = {0., 0., 1.}, hi[3] = {1., 1., HUGE_VAL};
         problem.SetMaterialBounds(lo, hi);            // :143-172
         problem.SetTextureBounds(0., 1.);             // :177-181
@@ -150,10 +158,21 @@ static void solveWindow(PhongDataset& d, unsigned k1, unsigned k2, bool use_ligh
     }
     problem.options.max_num_iterations = max_iters;   // :85 (1000)
     problem.options.use_nonmonotonic_steps = 1;       // :86
-    std::cerr << "Solving SLAM and lighting jointly" << std::endl;
     Summary summary;
-    problem.Solve(&summary);                          // :249-252
+    problem.Solve(&summary);
     std::cout << summary.BriefReport() << std::endl << std::endl;
+}
+
+static void solveWindow(PhongDataset& d, unsigned k1, unsigned k2, bool use_light, bool multi_stage, int max_iters) {
+    std::cerr << "Working on interval [" << k1 << "," << k2 << ")" << std::endl;
+    if (multi_stage) {
+        std::cerr << "Solving stage 1: poses and points" << std::endl;   // :94-98
+        solve_stage(d, k1, k2, use_light, max_iters, 1);
+        std::cerr << "Solving stage 2: lighting" << std::endl;            // :226-229
+        solve_stage(d, k1, k2, use_light, max_iters, 2);
+    }
+    std::cerr << "Solving SLAM and lighting jointly" << std::endl;       // :249-252
+    solve_stage(d, k1, k2, use_light, max_iters, 0);
 }
 
 static void write_outputs(const PhongDataset& d, const std::string& filename) {
@@ -178,13 +197,13 @@ static void write_outputs(const PhongDataset& d, const std::string& filename) {
 
 int main(int argc, char** argv) {
     const std::string usage(
-        "usage: dataset_ba_phong_b200 <input_file> [--nolight | --dirlight] [--window N] [--max-iters M] "
+        "usage: dataset_ba_phong_b200 <input_file> [--nolight | --dirlight] [--window N] [--multistage] [--max-iters M] "
         "[--material-by-observation]");
     if (argc < 2) {
         std::cerr << usage << std::endl;
         return EXIT_FAILURE;
     }
-    bool use_light = true, directional = false, use_window = false, by_obs = false;
+    bool use_light = true, directional = false, use_window = false, by_obs = false, multi_stage = false;
     unsigned window = 0;
     int max_iters = 1000;
     const std::string filename(argv[1]);
@@ -192,10 +211,8 @@ int main(int argc, char** argv) {
         const std::string flag(argv[a]);
         if (flag == "--nolight") use_light = false, directional = false;
         else if (flag == "--dirlight") use_light = true, directional = true;
-        else if (flag == "--multistage") {
-            std::cerr << "--multistage is not built in the B200 back end (stage 2 of dataset_ba_phong.cpp:207-246)" << std::endl;
-            return EXIT_FAILURE;
-        } else if (flag == "--window" && argc > a + 1) use_window = true, window = unsigned(std::atoi(argv[++a]));
+        else if (flag == "--multistage") multi_stage = true, use_light = true;   // :283-285
+        else if (flag == "--window" && argc > a + 1) use_window = true, window = unsigned(std::atoi(argv[++a]));
         else if (flag == "--max-iters" && argc > a + 1) max_iters = std::atoi(argv[++a]);
         else if (flag == "--material-by-observation") by_obs = true;
         else {
@@ -214,7 +231,7 @@ int main(int argc, char** argv) {
         const unsigned k2 = k1 + window;
         if (k1 > 0) initial_guess(d, k2 - 1, k2, by_obs);           // :324-328 (a single pose: nothing to align)
         else initial_guess(d, k1, k2, by_obs);
-        solveWindow(d, k1, k2, use_light, max_iters);
+        solveWindow(d, k1, k2, use_light, multi_stage, max_iters);
     }
     std::cerr << "Outputting to file " << std::endl;
     write_outputs(d, filename);

@@ -614,8 +614,14 @@ def test_cpp_driver_dataset_ba_phong(product, tmp_path):
     assert np.median(np.linalg.norm(m[:, 1:4] - tr["points_gt"][j], axis=1)) < 0.05
     assert np.median(np.abs(m[:, 10] - tr["tex_shared_gt"][tr["material_id"][j]])) < 0.02
     assert np.all(m[:, 8] >= 0) and np.all(m[:, 8] <= 1) and np.all(m[:, 9] >= 1)     # the box
-    # the reference's material indexing quirk (inlier index instead of observation) also runs
+    # stereo only, and the three-stage solve (stage 1 poses + points, stage 2 lighting only, stage 3 joint)
     _run_driver("dataset_ba_phong_b200", [csv, "--max-iters", "5", "--nolight"], tmp_path)
+    text = _run_driver("dataset_ba_phong_b200", [csv, "--max-iters", "40", "--multistage", "--material-by-observation"], tmp_path)
+    assert "Termination: FAILURE" not in text and text.count("cslam_b200 Report") == 3, text
+    T3 = _poses_csv(os.path.join(tmp_path, "scene_poses.csv"), 20)
+    assert np.abs(T3[:, :3, 3] - tr["poses_gt"][:, :3]).max() < 0.05
+    light3 = np.loadtxt(os.path.join(tmp_path, "scene_lights.csv"), delimiter=",", skiprows=1)
+    assert np.abs(light3 - tr["light_gt"]).max() < 0.15
 
 
 @pytest.mark.parametrize("shape,leaves", [((100, 15, 10), 5), ((300, 6, 4), 25), ((300, 6, 4), 2), ((260, 8, 7), 9),
@@ -669,3 +675,26 @@ def test_dogleg_rejected_steps_reuse(product):
     check_lm(g, o)
     lg, lo = g[0].iteration_log(), o[0].iteration_log()
     assert np.array_equal(lg[:, 7], lo[:, 7]), "linear solves per iteration (0 when the vectors are reused)"
+
+
+@pytest.mark.parametrize("directional", [False, True])
+def test_lm_phong_stage2_lighting_only(product, directional):
+    """Stage 2 of --multistage: all poses and positions constant (no free camera, the reduced system
+    is the dense shared block alone), against the oracle."""
+    tr = syn.add_phong(syn.make_track(30, 12, 6, seed=5), directional=directional, shared_textures=True)
+    tr["constant"] = np.ones(tr["n_poses"], dtype=np.uint8)
+    kw = dict(FIXED, max_num_iterations=6)
+    pg, stg = syn.build_phong_problem(tr, backend="b200", bounds=True, **kw)
+    po, sto = syn.build_phong_problem(tr, backend="oracle", bounds=True, num_threads=8, **kw)
+    before = stg["points"].copy()
+    for p in (pg, po):
+        p.set_points_constant(True)
+    sg, so = pg.solve(), po.solve()
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory (incl. the fixed cost)"
+    assert np.array_equal(lg[:, 9], lo[:, 9])
+    assert abs(sg.initial_cost - so.initial_cost) <= 1e-10 * so.initial_cost
+    assert np.array_equal(stg["points"], before) and np.array_equal(stg["poses"], tr["poses"])
+    for k in ("normals", "phong", "textures", "light"):
+        assert rel_err(stg[k], sto[k]) < LM_TOL, k

@@ -79,3 +79,22 @@ def test_phong_oracle_refuses_unpaired_blocks():
                 tr["W_normal"])
     with pytest.raises(CslamError):
         p.solve()
+
+
+def test_phong_oracle_stage2_holds_poses_and_positions():
+    """Stage 2 of dataset_ba_phong --multistage (dataset_ba_phong.cpp:207-246): every pose and vertex
+    position constant, only the lighting parameters move; the stereo blocks are dropped and their
+    cost is carried as Ceres' fixed_cost."""
+    tr = syn.add_phong(syn.make_track(14, 20, 6, seed=9), shared_textures=True)
+    tr["constant"] = np.ones(tr["n_poses"], dtype=np.uint8)
+    p, st = syn.build_phong_problem(tr, backend="oracle", bounds=True, max_num_iterations=20, num_threads=4)
+    p.set_points_constant(True)
+    before = {k: st[k].copy() for k in st}
+    pj, _ = syn.build_phong_problem(tr, backend="oracle", bounds=True, max_num_iterations=0, num_threads=4)
+    s = p.solve()
+    assert np.array_equal(st["poses"], before["poses"]) and np.array_equal(st["points"], before["points"])
+    for k in ("normals", "phong", "textures", "light"):
+        assert np.abs(st[k] - before[k]).max() > 1e-6, k
+    assert s.final_cost < s.initial_cost
+    # the reported cost includes the dropped stereo blocks: same initial cost as the joint problem
+    assert abs(s.initial_cost - pj.solve().initial_cost) < 1e-9 * s.initial_cost
