@@ -122,3 +122,17 @@ def test_landmark_sharding_world_size_2_gloo(lib, tmp_path):
     outs = [pr.communicate(timeout=240)[0] for pr in procs]
     for r, (pr, out) in enumerate(zip(procs, outs)):
         assert pr.returncode == 0 and f"SHARD_OK {r}" in out, out
+
+
+def test_options_struct_layout_matches_the_header():
+    """The ctypes mirror of cslam_options must have the header's layout: the LAST field carries a
+    distinctive default, so any drift in the fields before it shows up there (both libraries)."""
+    import ctypes as C
+    from ceres_slam_b200 import capi
+    for lib in (capi.load_product(), capi.load_oracle()):
+        opt = capi.Options()
+        C.memset(C.byref(opt), 0xAB, C.sizeof(opt))
+        lib.options_init(C.byref(opt))
+        assert opt.line_search_sufficient_function_decrease == 1e-4
+        assert opt.max_num_iterations == 1000 and opt.dogleg_type == 1 and opt.trust_region_strategy == 0
+        assert opt.initial_trust_region_radius == 1e4
