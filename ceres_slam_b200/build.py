@@ -53,7 +53,9 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [os.path.join(bdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(OUT, objs):
-        run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+        # link beside the target and rename: a snapshot of the tree never sees a half-written library
+        run([nvcc, "-shared", "-o", OUT + ".tmp"] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+        os.replace(OUT + ".tmp", OUT)
     return OUT
 
 

@@ -325,16 +325,32 @@ __global__ void __launch_bounds__(32 * (1 + CW))
 
 
 // ---------------------------------------------------------------------------------------------
-// Variant for track length L <= 10 (two threads per camera pair fit in one 128-thread CTA).
+// Variant for track length L <= 10.
 // Every thread is producer AND consumer: in one step of the software pipeline a thread first
 // evaluates one observation of batch n+1 (camera slot fixed per thread: pose and scaling stay in
-// registers) and writes its Z = W C^-T to one half of a double-buffered shared tile, then
-// accumulates its half (three rows) of one pair block over the landmarks of batch n.  One CTA
-// barrier per batch; no warp is a serial bottleneck and all warps issue FP64 work throughout.
+// registers) and writes its Z = W C^-T to one half of a double-buffered shared tile; then the
+// CTA's four warps apply batch n to the tile with FP64 tensor-core MMAs:
+//      S_tile (6L x 6L, upper triangle) -= Z Z^T ,   Z = [6L rows] x [3 columns per landmark]
+// as DMMA m8n8k4 (mma.sync.aligned.m8n8k4.row.col.f64): the tile is cut into ceil(6L/8)^2 8x8
+// MMA tiles (they straddle the 6x6 camera blocks; the flush maps entries back), the upper
+// triangle of MMA tiles is dealt to the warps as two triangular and two rectangular sets so a
+// warp reuses each fragment 2..4 times, and because the update is symmetric the A fragment of
+// row tile i IS the B fragment of column tile i (one shared-memory word per thread per tile).
+// DMMA has the DFMA peak on B200 (scripts/micro/dmma_micro.cu: 36.7 vs 36.1 TFLOP/s, one pipe),
+// so the gain is issue slots and shared-memory traffic: 1 LDS feeds 8 FMAs per thread instead of 2.
+// One CTA barrier per batch.
 // ---------------------------------------------------------------------------------------------
 constexpr int G2_NT = 128;
 constexpr int G2_LMAX = 10;  // longest camera list this variant takes
 constexpr int G2_ZB = G2_NT * 18;  // doubles per Z buffer: one (landmark, slot) entry per thread
+constexpr int G2_ZPAD = 32;  // fragment rows of the last (partial) MMA row tile read past the batch
+
+// D(8x8) += A(8x4) B(4x8): lane (g = lane/4, t = lane%4) holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
 
 template <int MINB>
 __global__ void __launch_bounds__(G2_NT, MINB)
@@ -344,10 +360,11 @@ __global__ void __launch_bounds__(G2_NT, MINB)
     __shared__ __align__(128) double s_pose[G2_LMAX * 12];
     __shared__ double s_sp[G2_LMAX * 6];
     __shared__ double s_A[kItemMax * 9];
-    __shared__ __align__(16) double s_Z[2 * G2_ZB];
+    __shared__ __align__(16) double s_Z[2 * G2_ZB + G2_ZPAD];
     __shared__ double s_redsum[32];
     __shared__ int s_free[G2_LMAX];
     __shared__ int s_blk[G2_LMAX * (G2_LMAX + 1) / 2];
+    __shared__ double s_W[9];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x;
@@ -355,14 +372,10 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
+    if (tid < 9 && !v.W_per_obs) s_W[tid] = v.obs_W[tid];
     __syncthreads();
     uint32_t phase = 0;
     double cost = 0.0;
-    double Wsh[9];
-    if (!v.W_per_obs) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Wsh[k] = v.obs_W[k];
-    }
 
     for (int w = item_lo + blockIdx.x; w < item_hi; w += gridDim.x) {
         const int g = gv.item_group[w];
@@ -395,17 +408,64 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         phase ^= 1;
         __syncthreads();
 
+        // ---- roles of the pipeline below; the first observation is requested before pass 1 ----
+        // landmarks per batch (one observation per thread), a multiple of 4 so that a batch's
+        // 3 TL columns are whole k-steps of 4
+        const int TL = (G2_NT / L) & ~3;
+        const int nbatch = (nj + TL - 1) / TL;
+        const int pq = tid % TL, pi = tid / TL;
+        const bool p_active = pi < L;
+        const int pf = p_active ? s_free[pi] : -1;
+        const bool producing = p_active && pf >= 0;
+        // this thread's observation of the NEXT batch (u, v, d, point, point scaling), loaded one
+        // pipeline step ahead so the global-load latency hides behind the MMA stage
+        double nx[9];
+        auto prefetch = [&](int jl) {
+            if (producing && jl < nj) {
+                const long long j = lm0 + jl;
+                const long long e = obs0 + (long long)pi * G + jl;
+                nx[0] = v.obs_u[e]; nx[1] = v.obs_v[e]; nx[2] = v.obs_d[e];
+                nx[3] = v.points[3 * j]; nx[4] = v.points[3 * j + 1]; nx[5] = v.points[3 * j + 2];
+                nx[6] = v.sc_l[3 * j]; nx[7] = v.sc_l[3 * j + 1]; nx[8] = v.sc_l[3 * j + 2];
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < 9; ++k) nx[k] = 0.0;
+        prefetch(pq);
+
         // ---- pass 1: V_j = sum Jp^T Jp + D^2, Cholesky, A = C^-1, t = A g_l ----
         for (int jl = tid; jl < nj; jl += G2_NT) {
             const long long j = lm0 + jl;
             const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
             const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
             double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
+            // the L observations of a landmark are a chain of dependent global loads: keep three in flight
+            double qu[3], qv[3], qd[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const long long e = obs0 + (long long)min(k, L - 1) * G + jl;
+                qu[k] = v.obs_u[e];
+                qv[k] = v.obs_v[e];
+                qd[k] = v.obs_d[e];
+            }
+            double Wl[9];
+            if (!v.W_per_obs) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
+            }
             for (int i = 0; i < L; ++i) {
-                const long long e = obs0 + (long long)i * G + jl;
+                const double ou = qu[0], ov = qv[0], od = qd[0];
+                qu[0] = qu[1]; qv[0] = qv[1]; qd[0] = qd[1];
+                qu[1] = qu[2]; qv[1] = qv[2]; qd[1] = qd[2];
+                if (i + 3 < L) {
+                    const long long e3 = obs0 + (long long)(i + 3) * G + jl;
+                    qu[2] = v.obs_u[e3];
+                    qv[2] = v.obs_v[e3];
+                    qd[2] = v.obs_d[e3];
+                }
                 double r[3], Jp[9];
-                stereo_block_point(v.cam, s_pose + 12 * i, p, v.obs_u[e], v.obs_v[e], v.obs_d[e],
-                                   v.W_per_obs ? v.obs_W + 9 * e : Wsh, r, Jp);
+                stereo_block_point(v.cam, s_pose + 12 * i, p, ou, ov, od,
+                                   v.W_per_obs ? v.obs_W + 9 * (obs0 + (long long)i * G + jl) : Wl, r, Jp);
                 cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -451,59 +511,61 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         }
         __syncthreads();
 
-        // ---- pipeline: produce Z of batch n+1, accumulate Z_a Z_b^T of batch n ----
-        const int TL = G2_NT / L;            // landmarks per batch (one observation per thread)
-        const int nbatch = (nj + TL - 1) / TL;
-        const int pq = tid % TL, pi = tid / TL;
-        const bool p_active = pi < L;
-        int pf = -1;
-        double pose[12], sp[6];
+        // ---- pipeline: produce Z of batch n+1, apply batch n with DMMA ----
         double U[21], gpa[6], bpa[6];
-        if (p_active) {
-            pf = s_free[pi];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) pose[k] = s_pose[12 * pi + k];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) sp[k] = s_sp[6 * pi + k];
-        }
 #pragma unroll
         for (int k = 0; k < 21; ++k) U[k] = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) gpa[k] = bpa[k] = 0.0;
-        // consumer role: pair (a <= b) in row-major order of the upper triangle, half = rows 3h..3h+2
-        const int cpair = tid >> 1, half = tid & 1;
-        const bool c_active = cpair < P;
-        int ca = 0, cb = 0;
-        if (c_active) {
-            int rem = cpair;
-            while (rem >= L - ca) {
-                rem -= L - ca;
-                ++ca;
-            }
-            cb = ca + rem;
+        // consumer role (per warp): MMA row tiles [r0, r0 + nr) x column tiles [c0, c0 + nc); the
+        // triangular warps (0 and 3) own the tiles i <= j of a diagonal square, the rectangular
+        // warps (1 and 2) split the off-diagonal rectangle by rows.  nr <= 4 (2 for rectangles), nc <= 4.
+        const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, ft = lane & 3;
+        const int T8 = (6 * L + 7) >> 3, Th = (T8 + 1) >> 1, Th1 = (Th + 1) >> 1;
+        const bool tri = warp == 0 || warp == 3;
+        int r0, nr, c0, nc;
+        if (warp == 0) {
+            r0 = 0; nr = Th; c0 = 0; nc = Th;
+        } else if (warp == 3) {
+            r0 = Th; nr = T8 - Th; c0 = Th; nc = T8 - Th;
+        } else if (warp == 1) {
+            r0 = 0; nr = Th1; c0 = Th; nc = T8 - Th;
+        } else {
+            r0 = Th1; nr = Th - Th1; c0 = Th; nc = T8 - Th;
         }
-        double M[18];
+        const int zrow_r = 3 * (8 * r0 + fg), zrow_c = 3 * (8 * c0 + fg);  // + 24 per further tile
+        const int zlm = 18 * L;                                           // doubles per landmark
+        double M[20];  // triangular: tile (i, j >= i) at 4i - i(i-1)/2 + j - i; rectangular: 4i + j
 #pragma unroll
-        for (int k = 0; k < 18; ++k) M[k] = 0.0;
+        for (int k = 0; k < 20; ++k) M[k] = 0.0;
 
         for (int bt = 0; bt <= nbatch; ++bt) {
-            if (bt < nbatch && p_active && pf >= 0) {
+            if (bt < nbatch && producing) {
                 const int jl = bt * TL + pq;
                 if (jl < nj) {
                     double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
-                    const long long j = lm0 + jl;
+                    const double p[3] = {nx[3], nx[4], nx[5]};
+                    const double sl[3] = {nx[6], nx[7], nx[8]};
+                    const double ou = nx[0], ov = nx[1], od = nx[2];
                     const long long e = obs0 + (long long)pi * G + jl;
-                    const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
-                    const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
                     double r[3], Jc[18], Jp[9];
-                    stereo_block<true>(v.cam, pose, p, v.obs_u[e], v.obs_v[e], v.obs_d[e],
-                                       v.W_per_obs ? v.obs_W + 9 * e : Wsh, r, Jc, Jp);
+                    {
+                        double pose[12], Wl[9];
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) pose[k] = s_pose[12 * pi + k];
+                        if (!v.W_per_obs) {
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
+                        }
+                        stereo_block<true>(v.cam, pose, p, ou, ov, od, v.W_per_obs ? v.obs_W + 9 * e : Wl, r, Jc, Jp);
+                    }
+                    prefetch(jl + TL);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
 #pragma unroll
                         for (int q = 0; q < 3; ++q) Jp[3 * k + q] *= sl[q];
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= sp[q];
+                        for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= s_sp[6 * pi + q];
                     }
                     const double* A = s_A + 9 * jl;
                     const double a00 = A[0], a10 = A[1], a11 = A[2], a20 = A[3], a21 = A[4], a22 = A[5];
@@ -522,59 +584,90 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                         zt[3 * a + 2] = z2;
                         const double ga = Jc[a] * r[0] + Jc[6 + a] * r[1] + Jc[12 + a] * r[2];
                         gpa[a] += ga;
-                        bpa[a] += ga - (z0 * t0 + z1 * t1 + z2 * t2);
+                        bpa[a] = fma(-z0, t0, fma(-z1, t1, fma(-z2, t2, bpa[a] + ga)));
 #pragma unroll
                         for (int b = a; b < 6; ++b, ++u)
-                            U[u] += Jc[a] * Jc[b] + Jc[6 + a] * Jc[6 + b] + Jc[12 + a] * Jc[12 + b];
+                            U[u] = fma(Jc[a], Jc[b], fma(Jc[6 + a], Jc[6 + b], fma(Jc[12 + a], Jc[12 + b], U[u])));
                     }
+                } else {
+                    // a k-step of the last batch may reach one landmark past nj: zero columns
+                    double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
+#pragma unroll
+                    for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(0.0, 0.0);
                 }
             }
-            if (bt > 0 && c_active) {
+            if (bt > 0) {
                 const double* zt = s_Z + ((bt - 1) & 1) * G2_ZB;
                 const int nval = min(TL, nj - (bt - 1) * TL);
-                for (int jj = 0; jj < nval; ++jj) {
-                    const double* za = zt + (jj * L + ca) * 18 + 9 * half;
-                    const double* zb = zt + (jj * L + cb) * 18;
-                    double B[18];
+                const int nk = (3 * nval + 3) >> 2;
+                if (tri) {
+                    for (int ks = 0; ks < nk; ++ks) {
+                        const int kk = 4 * ks + ft, jj = kk / 3;
+                        const double* zb = zt + jj * zlm + (kk - 3 * jj) + zrow_r;
+                        double f[4];
 #pragma unroll
-                    for (int k = 0; k < 18; k += 2) {
-                        const double2 t = *reinterpret_cast<const double2*>(zb + k);
-                        B[k] = t.x;
-                        B[k + 1] = t.y;
+                        for (int i = 0; i < 4; ++i) f[i] = i < nr ? zb[24 * i] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = i; j < 4; ++j)
+                                if (j < nr) dmma884(M[2 * (4 * i - i * (i - 1) / 2 + j - i)], M[2 * (4 * i - i * (i - 1) / 2 + j - i) + 1], f[i], f[j]);
                     }
+                } else {
+                    for (int ks = 0; ks < nk; ++ks) {
+                        const int kk = 4 * ks + ft, jj = kk / 3;
+                        const double* zb = zt + jj * zlm + (kk - 3 * jj);
+                        double fr[2], fc[4];
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const double x0 = za[3 * p], x1 = za[3 * p + 1], x2 = za[3 * p + 2];
+                        for (int i = 0; i < 2; ++i) fr[i] = i < nr ? zb[zrow_r + 24 * i] : 0.0;
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) M[6 * p + q] += x0 * B[3 * q] + x1 * B[3 * q + 1] + x2 * B[3 * q + 2];
+                        for (int j = 0; j < 4; ++j) fc[j] = j < nc ? zb[zrow_c + 24 * j] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (i < nr && j < nc) dmma884(M[2 * (4 * i + j)], M[2 * (4 * i + j) + 1], fr[i], fc[j]);
                     }
                 }
             }
             __syncthreads();
         }
 
-        // ---- flush: pair blocks, camera diagonal / gradients ----
-        if (c_active) {
-            const int e = s_blk[cpair];
-            if (e >= 0) {
-                double* Bk = S + 36ll * e + 18 * half;
-                if (ca == cb) {
-                    // diagonal block: upper triangle only, finalize mirrors it
+        // ---- flush: MMA tile entries back to the 6x6 pair blocks, camera diagonal / gradients ----
+        {
+            // entry (row, col) of the 6L x 6L tile, row <= col: block (row/6, col/6), diagonal blocks
+            // upper triangle only (finalize mirrors it); one RED per entry per slice as before
+            auto flush_tile = [&](int mt, int nt, double m0, double m1) {
+                const int row = 8 * mt + fg;
+                if (row >= 6 * L) return;
+                const int a = row / 6, ra = row - 6 * a;
 #pragma unroll
-                    for (int p = 0; p < 3; ++p)
-#pragma unroll
-                        for (int q = 0; q < 6; ++q)
-                            if (q >= p + 3 * half) red_add(&Bk[6 * p + q], -M[6 * p + q]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 18; ++k) red_add(&Bk[k], -M[k]);
+                for (int h = 0; h < 2; ++h) {
+                    const int col = 8 * nt + 2 * ft + h;
+                    if (col >= 6 * L || col < row) continue;
+                    const int b = col / 6, rb = col - 6 * b;
+                    const int e = s_blk[a * L - a * (a - 1) / 2 + (b - a)];
+                    if (e >= 0) red_add(&S[36ll * e + 6 * ra + rb], h ? -m1 : -m0);
                 }
+            };
+            if (tri) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = i; j < 4; ++j)
+                        if (j < nr) flush_tile(r0 + i, r0 + j, M[2 * (4 * i - i * (i - 1) / 2 + j - i)], M[2 * (4 * i - i * (i - 1) / 2 + j - i) + 1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i < nr && j < nc) flush_tile(r0 + i, c0 + j, M[2 * (4 * i + j)], M[2 * (4 * i + j) + 1]);
             }
         }
         {
             // reduce U, g, rhs over the TL threads that share a slot, then one RED per value
             double* red = s_Z;  // every consumer read of s_Z is behind the last barrier
-            if (p_active && pf >= 0) {
+            if (producing) {
 #pragma unroll
                 for (int k = 0; k < 21; ++k) red[tid * 33 + k] = U[k];
 #pragma unroll

@@ -254,7 +254,8 @@ def _reduced(track, path, **kw):
     return p.reduced_system()
 
 
-@pytest.mark.parametrize("shape", [(60, 15, 6), (100, 15, 10), (80, 3, 14)])
+@pytest.mark.parametrize("shape", [(60, 15, 6), (100, 15, 10), (80, 3, 14), (30, 9, 2), (40, 10, 3), (40, 11, 4),
+                                   (40, 13, 5), (50, 12, 7), (50, 17, 8), (50, 140, 9), (40, 300, 10)])
 def test_schur_paths_agree(product, shape):
     """The grouped (SYRK-shaped) Schur kernel and the generic warp-per-landmark kernel build the
     same reduced camera system; both orders of summation agree to rounding."""
