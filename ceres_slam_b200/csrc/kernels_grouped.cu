@@ -352,8 +352,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(G2_NT, MINB)
+template <bool WPO>  // WPO: one 3x3 weight per observation (dataset_vo_sun.cpp:57-59) instead of a shared one
+__global__ void __launch_bounds__(G2_NT, 2)
     schur_grouped2_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
                           double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
                           double* __restrict__ gl, double* __restrict__ scal) {
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    if (tid < 9 && !v.W_per_obs) s_W[tid] = v.obs_W[tid];
+    if (tid < 9 && !WPO) s_W[tid] = v.obs_W[tid];
     __syncthreads();
     uint32_t phase = 0;
     double cost = 0.0;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                 qd[k] = v.obs_d[e];
             }
             double Wl[9];
-            if (!v.W_per_obs) {
+            if (!WPO) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
             }
@@ -464,8 +464,14 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                     qd[2] = v.obs_d[e3];
                 }
                 double r[3], Jp[9];
-                stereo_block_point(v.cam, s_pose + 12 * i, p, ou, ov, od,
-                                   v.W_per_obs ? v.obs_W + 9 * (obs0 + (long long)i * G + jl) : Wl, r, Jp);
+                if (WPO) {
+                    // (a predicated-off load in this loop would share a scoreboard with the prefetch
+                    // above and make every iteration wait for it: hence the template parameter)
+                    const double* Wg = v.obs_W + 9 * (obs0 + (long long)i * G + jl);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Wl[k] = Wg[k];
+                }
+                stereo_block_point(v.cam, s_pose + 12 * i, p, ou, ov, od, Wl, r, Jp);
                 cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -520,7 +526,8 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         // consumer role (per warp): MMA row tiles [r0, r0 + nr) x column tiles [c0, c0 + nc); the
         // triangular warps (0 and 3) own the tiles i <= j of a diagonal square, the rectangular
         // warps (1 and 2) split the off-diagonal rectangle by rows.  nr <= 4 (2 for rectangles), nc <= 4.
-        const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, ft = lane & 3;
+        const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the role is warp-uniform
+        const int lane = tid & 31, fg = lane >> 2, ft = lane & 3;
         const int T8 = (6 * L + 7) >> 3, Th = (T8 + 1) >> 1, Th1 = (Th + 1) >> 1;
         const bool tri = warp == 0 || warp == 3;
         int r0, nr, c0, nc;
@@ -553,11 +560,9 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                         double pose[12], Wl[9];
 #pragma unroll
                         for (int k = 0; k < 12; ++k) pose[k] = s_pose[12 * pi + k];
-                        if (!v.W_per_obs) {
 #pragma unroll
-                            for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
-                        }
-                        stereo_block<true>(v.cam, pose, p, ou, ov, od, v.W_per_obs ? v.obs_W + 9 * e : Wl, r, Jc, Jp);
+                        for (int k = 0; k < 9; ++k) Wl[k] = WPO ? v.obs_W[9 * e + k] : s_W[k];
+                        stereo_block<true>(v.cam, pose, p, ou, ov, od, Wl, r, Jc, Jp);
                     }
                     prefetch(jl + TL);
 #pragma unroll
@@ -710,15 +715,12 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
                           double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
     if (n_items_small > 0) {
-        static const int occ = [] {
-            const char* e = std::getenv("CSLAM_G2_OCC");  // tuning knob: resident CTAs per SM (2 or 3)
-            return e ? std::atoi(e) : 2;
-        }();
-        const int grid = n_items_small < occ * kSMs ? n_items_small : occ * kSMs;
-        if (occ == 2)
-            schur_grouped2_kernel<2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+        // two resident CTAs per SM (254 registers); three were measured slower (spills)
+        const int grid = n_items_small < 2 * kSMs ? n_items_small : 2 * kSMs;
+        if (v.W_per_obs)
+            schur_grouped2_kernel<true><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else
-            schur_grouped2_kernel<3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+            schur_grouped2_kernel<false><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (g.n_items > n_items_small) {
