@@ -717,6 +717,8 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
     if (n_items_small > 0) {
         // two resident CTAs per SM (254 registers); three were measured slower (spills)
         const int grid = n_items_small < 2 * kSMs ? n_items_small : 2 * kSMs;
+        // (a single-evaluation variant — V_j reduced through shared memory inside the pipeline, no pass 1 —
+        // was measured slower, 2.67 vs 2.50 ms on C5: its per-batch Cholesky chain is exposed latency)
         if (v.W_per_obs)
             schur_grouped2_kernel<true><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else
