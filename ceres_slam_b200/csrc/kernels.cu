@@ -619,7 +619,12 @@ __global__ void __launch_bounds__(128)
         const long long e1 = e0 + es * v.lm_cnt[j];
         const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
         const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
-        double V[6] = {0, 0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
+        // One Jacobian evaluation per observation.  With Jy_i = Jc_i y_p the pass accumulates
+        //   V0 = sum Jp^T Jp,  gl = sum Jp^T r,  q = sum Jp^T Jy (= W^T y_p),  a = sum Jy.r,  b = sum |Jy|^2
+        // so that, once y_l = V^-1 (gl - q) is known, the landmark's share of the model cost change
+        //   sum_i -(J s).(r + J s / 2),  s = -y,  J s = -(Jp y_l + Jy)
+        // is  y_l.gl + a - (y_l^T V0 y_l + 2 y_l.q + b) / 2  without a second pass over the Jacobians.
+        double V[6] = {0, 0, 0, 0, 0, 0}, tg[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, sa = 0, sb = 0;
         ObsEval o;
         for (long long e = e0; e < e1; e += es) {
             eval_obs_scaled(v, e, p, sl, o);
@@ -640,22 +645,36 @@ __global__ void __launch_bounds__(128)
                 V[3] += b * b;
                 V[4] += b * c;
                 V[5] += c * c;
-                // t = g_l - W^T yp = sum Jp^T (r - Jc yp)
-                const double w = o.r[k] - Jy[k];
-                t[0] += a * w;
-                t[1] += b * w;
-                t[2] += c * w;
+                tg[0] += a * o.r[k];
+                tg[1] += b * o.r[k];
+                tg[2] += c * o.r[k];
+                tq[0] += a * Jy[k];
+                tq[1] += b * Jy[k];
+                tq[2] += c * Jy[k];
+                sa += Jy[k] * o.r[k];
+                sb += Jy[k] * Jy[k];
             }
         }
+        const double V0[6] = {V[0], V[1], V[2], V[3], V[4], V[5]};
         V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
         V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
         V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
         double Vi[6];
         double yl[3] = {0, 0, 0};
         if (invert_sym3(V, Vi)) {
+            // t = g_l - W^T yp
+            const double t[3] = {tg[0] - tq[0], tg[1] - tq[1], tg[2] - tq[2]};
             yl[0] = Vi[0] * t[0] + Vi[1] * t[1] + Vi[2] * t[2];
             yl[1] = Vi[1] * t[0] + Vi[3] * t[1] + Vi[4] * t[2];
             yl[2] = Vi[2] * t[0] + Vi[4] * t[1] + Vi[5] * t[2];
+        }
+        {
+            const double yVy = yl[0] * (V0[0] * yl[0] + V0[1] * yl[1] + V0[2] * yl[2]) +
+                               yl[1] * (V0[1] * yl[0] + V0[3] * yl[1] + V0[4] * yl[2]) +
+                               yl[2] * (V0[2] * yl[0] + V0[4] * yl[1] + V0[5] * yl[2]);
+            const double yg = yl[0] * tg[0] + yl[1] * tg[1] + yl[2] * tg[2];
+            const double yq = yl[0] * tq[0] + yl[1] * tq[1] + yl[2] * tq[2];
+            model += yg + sa - 0.5 * (yVy + 2.0 * yq + sb);
         }
         double pn[3];
 #pragma unroll
@@ -668,19 +687,8 @@ __global__ void __launch_bounds__(128)
             sn += (p[q] - pn[q]) * (p[q] - pn[q]);
             xn += pn[q] * pn[q];
         }
-        // model cost change  -(J s).(r + J s / 2) with s = -y, and the cost at the candidate
+        // the cost at the candidate
         for (long long e = e0; e < e1; e += es) {
-            eval_obs_scaled(v, e, p, sl, o);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                double m = -(o.Jp[3 * k] * yl[0] + o.Jp[3 * k + 1] * yl[1] + o.Jp[3 * k + 2] * yl[2]);
-                if (o.f >= 0) {
-                    const double* y = yp + 6ll * o.f;
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) m -= o.Jc[6 * k + a] * y[a];
-                }
-                model -= m * (o.r[k] + 0.5 * m);
-            }
             double rc[3];
             const uint32_t c = v.obs_cam[e];
             stereo_block<false>(v.cam, poses_cand + 12ll * c, pn, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e), rc,
