@@ -491,6 +491,346 @@ void Engine::build_structure() {
     bt.lap("  remaining landmarks");
 }
 
+// Pageable host memory -> device, split over a few host threads and streams (the copy is bound by the
+// driver's staging memcpy, which one thread does not saturate).
+static void parallel_h2d(int device, void* dst, const void* src, size_t bytes, size_t max_threads = 8) {
+    if (!bytes) return;
+    const size_t kMin = size_t(8) << 20;
+    const size_t nt = std::max<size_t>(1, std::min(max_threads, bytes / kMin));
+    std::string err;
+    std::mutex mu;
+    auto work = [&](size_t t) {
+        const size_t c0 = (bytes * t / nt) & ~size_t(255), c1 = t + 1 == nt ? bytes : (bytes * (t + 1) / nt) & ~size_t(255);
+        cudaStream_t cs = nullptr;
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+        if (e == cudaSuccess && c1 > c0)
+            e = cudaMemcpyAsync(static_cast<char*>(dst) + c0, static_cast<const char*>(src) + c0, c1 - c0, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+        if (cs) cudaStreamDestroy(cs);
+        if (e != cudaSuccess) {
+            std::lock_guard<std::mutex> g(mu);
+            err = cudaGetErrorString(e);
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    if (!err.empty()) throw CudaError("H2D copy failed: " + err);
+}
+
+// Structure analysis with the O(n_obs) passes on the device (structure.cu); the host part below is the
+// O(n_landmarks) logic of build_structure(), unchanged, fed from per-landmark arrays instead of the
+// observation lists.  Same layout as the host analysis (CSLAM_VERIFY_STRUCTURE=1 checks the hashes).
+bool Engine::build_structure_gpu(cudaEvent_t) {
+    if (!h_poses || n_poses == 0) throw std::invalid_argument("poses not set");
+    if (n_st > 0 && (!h_points || n_points == 0)) throw std::invalid_argument("points not set");
+    if (n_st >= (1ull << 32)) throw std::invalid_argument("more than 2^32 stereo blocks");
+    PhaseTimer bt;
+    const int max_threads = 32;
+    const int kFarCap = 1 << 22;
+    DBuf<uint32_t> d_cnt, d_ptr, d_fill, d_mincam;
+    DBuf<uint8_t> d_used, d_kok, d_tmp;
+    DBuf<unsigned long long> d_ck, d_khash, d_mask;
+    DBuf<int> d_flags;
+    DBuf<int2> d_far;
+    auto free_all = [&]() {
+        d_cnt.release_async(stream); d_ptr.release_async(stream); d_fill.release_async(stream); d_mincam.release_async(stream);
+        d_used.release_async(stream); d_kok.release_async(stream); d_tmp.release_async(stream); d_ck.release_async(stream);
+        d_khash.release_async(stream); d_mask.release_async(stream); d_flags.release_async(stream); d_far.release_async(stream);
+    };
+    d_cnt.alloc(size_t(n_points) + 1, stream);
+    d_cnt.zero(stream);
+    d_used.alloc(n_poses, stream);
+    d_used.zero(stream);
+    d_flags.alloc(4, stream);
+    d_flags.zero(stream);
+    launch_st_count(stream, n_st, d_raw_cam.p, d_raw_pt.p, n_poses, n_points, d_cnt.p, d_used.p, d_flags.p);
+    std::vector<uint8_t> used(n_poses, 0);
+    int flags[4] = {0, 0, 0, 0};
+    CSLAM_CUDA(cudaMemcpyAsync(used.data(), d_used.p, n_poses, cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    if (flags[0]) {
+        free_all();
+        throw std::invalid_argument("stereo block index out of range");
+    }
+    for (auto& s : suns) {
+        if (s.cam >= n_poses) throw std::invalid_argument("sun block index out of range");
+        used[s.cam] = 1;
+    }
+    for (auto& p : priors) {
+        if (p.cam >= n_poses) throw std::invalid_argument("prior block index out of range");
+        used[p.cam] = 1;
+    }
+    cam_free_h.assign(n_poses, -1);
+    free_cams_h.clear();
+    for (uint32_t k = 0; k < n_poses; ++k)
+        if (used[k] && !pose_const[k]) {
+            cam_free_h[k] = int(free_cams_h.size());
+            free_cams_h.push_back(int(k));
+        }
+    n_free = int(free_cams_h.size());
+    d_cam_free.upload(cam_free_h, stream);
+    bt.lap("  [gpu] count / free cams");
+
+    // observation lists per point, sorted by (camera, block index); per-landmark facts; S pattern masks
+    d_ptr.alloc(size_t(n_points) + 1, stream);
+    launch_st_scan(stream, n_points, d_cnt.p, d_ptr.p, d_tmp);
+    d_fill.alloc(std::max<size_t>(n_points, 1), stream);
+    CSLAM_CUDA(cudaMemcpyAsync(d_fill.p, d_ptr.p, size_t(n_points) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    d_ck.alloc(std::max<size_t>(n_st, 1), stream);
+    launch_st_fill(stream, n_st, d_raw_cam.p, d_raw_pt.p, d_fill.p, d_ck.p);
+    d_mincam.alloc(std::max<size_t>(n_points, 1), stream);
+    d_khash.alloc(std::max<size_t>(n_points, 1), stream);
+    d_kok.alloc(std::max<size_t>(n_points, 1), stream);
+    d_mask.alloc(size_t(std::max(n_free, 1)), stream);
+    d_mask.zero(stream);
+    d_far.alloc(kFarCap, stream);
+    launch_st_landmarks(stream, n_points, d_cnt.p, d_ptr.p, d_ck.p, d_cam_free.p, kGroupLmax, opt.schur_path != 1, d_mincam.p,
+                        d_khash.p, d_kok.p, d_mask.p, d_far.p, kFarCap, d_flags.p);
+    std::vector<uint32_t> cnt(size_t(n_points) + 1), mincam(n_points);
+    std::vector<unsigned long long> khash_u(n_points), mask(size_t(std::max(n_free, 1)));
+    std::vector<uint8_t> kok_u(n_points);
+    CSLAM_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.p, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(mincam.data(), d_mincam.p, mincam.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(khash_u.data(), d_khash.p, khash_u.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(kok_u.data(), d_kok.p, kok_u.size(), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, mask.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    if (flags[2]) {
+        free_all();
+        return false;  // more far pairs than the list holds: host analysis
+    }
+    std::vector<std::pair<int, int>> far;
+    far.resize(size_t(flags[1]));
+    if (!far.empty()) {
+        static_assert(sizeof(std::pair<int, int>) == sizeof(int2), "pair layout");
+        CSLAM_CUDA(cudaMemcpyAsync(far.data(), d_far.p, far.size() * sizeof(int2), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+    }
+    bt.lap("  [gpu] lists / landmark facts");
+
+    // landmarks in order of the first camera that sees them (counting sort, stable in user id)
+    std::vector<uint32_t> bucket(size_t(n_poses) + 1, 0);
+    uint32_t n_active = 0;
+    for (uint32_t j = 0; j < n_points; ++j)
+        if (cnt[j]) {
+            bucket[mincam[j] + 1]++;
+            n_active++;
+        }
+    for (uint32_t k = 0; k < n_poses; ++k) bucket[k + 1] += bucket[k];
+    const std::vector<uint32_t> bstart(bucket);
+    std::vector<uint32_t> all_lm(n_active);
+    for (uint32_t j = 0; j < n_points; ++j)
+        if (cnt[j]) all_lm[bucket[mincam[j]]++] = j;
+    std::vector<uint32_t> all_ptr(size_t(n_active) + 1, 0);
+    for (uint32_t a = 0; a < n_active; ++a) all_ptr[a + 1] = all_ptr[a] + cnt[all_lm[a]];
+    auto lm_len = [&](uint32_t a) { return cnt[all_lm[a]]; };
+    bt.lap("  [gpu] landmark order (host)");
+
+    // reduced camera system pattern
+    {
+        std::sort(far.begin(), far.end());
+        far.erase(std::unique(far.begin(), far.end()), far.end());
+        s_rowptr_h.assign(size_t(n_free) + 1, 0);
+        s_col_h.clear();
+        size_t fx = 0;
+        for (int a = 0; a < n_free; ++a) {
+            s_col_h.push_back(a);
+            for (int d = 1; d < 64; ++d)
+                if (mask[a] >> d & 1) s_col_h.push_back(a + d);
+            for (; fx < far.size() && far[fx].first == a; ++fx) s_col_h.push_back(far[fx].second);
+            s_rowptr_h[a + 1] = int(s_col_h.size());
+        }
+        nnzU = int(s_col_h.size());
+    }
+
+    // this rank's shard
+    uint32_t lo = 0, hi = n_active;
+    if (n_ranks > 1) {
+        auto cut = [&](int r) -> uint32_t {
+            const uint64_t target = n_st * uint64_t(r) / uint64_t(n_ranks);
+            return uint32_t(std::lower_bound(all_ptr.begin(), all_ptr.end(), uint32_t(target)) - all_ptr.begin());
+        };
+        lo = std::min(cut(rank), n_active);
+        hi = rank == n_ranks - 1 ? n_active : std::min(cut(rank + 1), n_active);
+    }
+    n_lm = int(hi - lo);
+    lm_lo = 0;
+    lm_hi = n_lm;
+    n_obs = (long long)all_ptr[hi] - (long long)all_ptr[lo];
+
+    // groups: runs of equal (first camera, track length, camera-list hash); the lists themselves are
+    // compared on the device afterwards (st_verify_kernel)
+    const uint32_t nl = hi - lo;
+    auto khash = [&](uint32_t a) { return khash_u[all_lm[a]]; };
+    auto kok = [&](uint32_t a) { return kok_u[all_lm[a]]; };
+    std::vector<uint32_t> sorted_a(nl);
+    std::vector<uint32_t> sorted_off(size_t(n_poses) + 1, 0);
+    for (uint32_t c = 0; c < n_poses; ++c) {
+        const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
+        uint32_t k = 0;
+        for (uint32_t a = b0; a < b1; ++a) k += kok(a);
+        sorted_off[c + 1] = sorted_off[c] + k;
+    }
+    std::vector<uint8_t> run_start(nl, 0);
+    parallel_chunks(n_poses, 16, [&](int, size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; ++c) {
+            const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
+            uint32_t* out = sorted_a.data() + sorted_off[c];
+            uint32_t k = 0;
+            for (uint32_t a = b0; a < b1; ++a)
+                if (kok(a)) out[k++] = a;
+            std::sort(out, out + k, [&](uint32_t x, uint32_t y) {
+                const uint32_t lx = lm_len(x), ly = lm_len(y);
+                if (lx != ly) return lx < ly;
+                if (khash(x) != khash(y)) return khash(x) < khash(y);
+                return x < y;
+            });
+            for (uint32_t x = 0; x < k;) {
+                run_start[sorted_off[c] + x] = 1;
+                uint32_t y = x + 1;
+                while (y < k && lm_len(out[y]) == lm_len(out[x]) && khash(out[y]) == khash(out[x])) ++y;
+                x = y;
+            }
+        }
+    });
+    const uint32_t n_ok = sorted_off[n_poses];
+    const size_t min_group = opt.schur_path == 2 ? 1 : 4;
+    g_L_h.clear(); g_G_h.clear(); g_lm0_h.clear(); g_obs0_h.clear(); g_off_h.clear(); g_cams_h.clear();
+    g_blk_off_h.clear(); g_blk_h.clear(); item_group_h.clear(); item_j0_h.clear(); item_n_h.clear();
+    std::vector<uint32_t> g_first;
+    std::vector<uint8_t> grouped(nl, 0);
+    uint32_t obs_cursor = 0, lm_cursor = 0;
+    int cams_cursor = 0, blk_cursor = 0;
+    std::vector<std::pair<int, int>> items_small, items_large;
+    for (uint32_t x = 0; x < n_ok;) {
+        uint32_t y = x + 1;
+        while (y < n_ok && !run_start[y]) ++y;
+        const uint32_t G = y - x;
+        if (G >= min_group) {
+            const int L = int(lm_len(sorted_a[x]));
+            const int gid = int(g_L_h.size());
+            g_L_h.push_back(L);
+            g_G_h.push_back(int(G));
+            g_lm0_h.push_back(int(lm_cursor));
+            g_obs0_h.push_back(obs_cursor);
+            g_off_h.push_back(cams_cursor);
+            g_blk_off_h.push_back(blk_cursor);
+            g_first.push_back(x);
+            cams_cursor += L;
+            blk_cursor += L * (L + 1) / 2;
+            lm_cursor += G;
+            obs_cursor += G * uint32_t(L);
+            for (uint32_t j0 = 0; j0 < G; j0 += kItemMax) (L <= 10 ? items_small : items_large).push_back({gid, int(j0)});
+            max_group_L = std::max(max_group_L, L);
+        }
+        x = y;
+    }
+    const size_t n_groups = g_L_h.size();
+    n_lm_grouped = int(lm_cursor);
+    n_items_small = int(items_small.size());
+    for (auto* lst : {&items_small, &items_large})
+        for (auto& it : *lst) {
+            item_group_h.push_back(it.first);
+            item_j0_h.push_back(it.second);
+            item_n_h.push_back(std::min(kItemMax, g_G_h[it.first] - it.second));
+        }
+    // camera list of every group from its first landmark (device), then the pair -> block tables (host)
+    g_cams_h.assign(size_t(cams_cursor), 0);
+    DBuf<uint32_t> d_gfirst;
+    DBuf<int> d_goff, d_gL, d_gG, d_glm0, d_gcams;
+    if (n_groups) {
+        std::vector<uint32_t> g_first_user(n_groups);
+        for (size_t g = 0; g < n_groups; ++g) g_first_user[g] = all_lm[sorted_a[g_first[g]]];
+        d_gfirst.upload(g_first_user, stream);
+        d_goff.upload(g_off_h, stream);
+        d_gL.upload(g_L_h, stream);
+        d_gcams.alloc(std::max<size_t>(size_t(cams_cursor), 1), stream);
+        launch_st_group_cams(stream, int(n_groups), d_gfirst.p, d_goff.p, d_gL.p, d_ptr.p, d_ck.p, d_gcams.p);
+        CSLAM_CUDA(cudaMemcpyAsync(g_cams_h.data(), d_gcams.p, g_cams_h.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+    }
+    g_blk_h.assign(size_t(blk_cursor), -1);
+    lm_user_h.assign(nl, 0);
+    lm_base_h.assign(nl, 0);
+    lm_stride_h.assign(nl, 0);
+    lm_cnt_h.assign(nl, 0);
+    obs_user_n = size_t(n_obs);
+    obs_user_h.reset();
+    parallel_chunks(n_groups, 8, [&](int, size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; ++g) {
+            const uint32_t x = g_first[g], G = uint32_t(g_G_h[g]);
+            const int L = g_L_h[g];
+            int fr[kGroupLmax];
+            for (int i = 0; i < L; ++i) fr[i] = cam_free_h[g_cams_h[size_t(g_off_h[g]) + i]];
+            int t = g_blk_off_h[g];
+            for (int i = 0; i < L; ++i)
+                for (int k = i; k < L; ++k) {
+                    int e = -1;
+                    if (fr[i] >= 0 && fr[k] >= 0) {
+                        auto b0 = s_col_h.begin() + s_rowptr_h[fr[i]], b1 = s_col_h.begin() + s_rowptr_h[fr[i] + 1];
+                        e = int(std::lower_bound(b0, b1, fr[k]) - s_col_h.begin());
+                    }
+                    g_blk_h[size_t(t++)] = e;
+                }
+            const uint32_t base = g_obs0_h[g];
+            for (uint32_t jl = 0; jl < G; ++jl) {
+                const uint32_t a = sorted_a[x + jl];
+                const size_t li = size_t(g_lm0_h[g]) + jl;
+                grouped[a - lo] = 1;
+                lm_user_h[li] = all_lm[a];
+                lm_base_h[li] = base + jl;
+                lm_stride_h[li] = G;
+                lm_cnt_h[li] = uint32_t(L);
+            }
+        }
+    });
+    // the remaining landmarks, landmark-major, in first-camera order
+    {
+        std::vector<uint32_t> rest;
+        for (uint32_t x = 0; x < nl; ++x)
+            if (!grouped[x]) rest.push_back(lo + x);
+        uint32_t off = obs_cursor;
+        for (size_t r = 0; r < rest.size(); ++r) {
+            const uint32_t a = rest[r], len = lm_len(a);
+            const size_t li = size_t(n_lm_grouped) + r;
+            lm_user_h[li] = all_lm[a];
+            lm_base_h[li] = off;
+            lm_stride_h[li] = 1;
+            lm_cnt_h[li] = len;
+            off += len;
+        }
+    }
+    bt.lap("  [gpu] groups / layout tables (host)");
+
+    // layout tables to the device, the observation permutation there, and the check of the groups
+    auto up_u = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) { d.upload(h.empty() ? std::vector<uint32_t>(1, 0) : h, stream); };
+    up_u(d_lm_base, lm_base_h);
+    up_u(d_lm_stride, lm_stride_h);
+    up_u(d_lm_cnt, lm_cnt_h);
+    up_u(d_lm_user, lm_user_h);
+    d_obs_user.alloc(std::max<size_t>(obs_user_n, 1), stream);
+    launch_st_perm(stream, n_lm, d_lm_user.p, d_lm_base.p, d_lm_stride.p, d_lm_cnt.p, d_ptr.p, d_ck.p, d_obs_user.p);
+    if (n_groups) {
+        d_gG.upload(g_G_h, stream);
+        d_glm0.upload(g_lm0_h, stream);
+        launch_st_verify(stream, int(n_groups), d_gL.p, d_gG.p, d_glm0.p, d_goff.p, d_gcams.p, d_lm_user.p, d_ptr.p, d_ck.p, d_flags.p);
+    }
+    CSLAM_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    d_gfirst.release_async(stream); d_goff.release_async(stream); d_gL.release_async(stream); d_gG.release_async(stream);
+    d_glm0.release_async(stream); d_gcams.release_async(stream);
+    free_all();
+    bt.lap("  [gpu] permutation + group check");
+    if (flags[3]) return false;  // two camera lists with one 64-bit hash: host analysis
+    structure_on_device = true;
+    return true;
+}
+
 GroupView Engine::group_view() const {
     GroupView g;
     g.n_items = int(item_group_h.size());
@@ -517,54 +857,119 @@ void Engine::launch_schur(const DevView& v, const LmDiag& dg) {
 
 void Engine::upload() {
     PhaseTimer pt;
+    const auto t_upload = std::chrono::steady_clock::now();
     ensure_device(this, &stream, &own_stream, &ev_a, &ev_b, &ev_c, &ev_d, &h_pinned);
     pt.lap("ensure_device");
-    // The caller's arrays go to the device as they are, from a second host thread, while this
-    // thread analyses the structure; the landmark-major SoA layout is then gathered on the GPU.
-    cudaStream_t copy_stream = nullptr;
-    CSLAM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    d_raw_cam.alloc(std::max<size_t>(n_st, 1), stream);
-    d_raw_uvd.alloc(3 * std::max<size_t>(n_st, 1), stream);
-    d_raw_W.alloc(st_W_per_obs ? 9 * std::max<size_t>(n_st, 1) : 9, stream);
-    d_raw_pts.alloc(3 * std::max<size_t>(n_points, 1), stream);
-    CSLAM_CUDA(cudaStreamSynchronize(stream));  // the copy stream may touch them from here on
-    std::string copy_err;
-    const int dev = opt.device;
-    std::thread copier([&, dev]() {
-        auto chk = [&](cudaError_t e) {
-            if (e != cudaSuccess && copy_err.empty()) copy_err = cudaGetErrorString(e);
-        };
-        chk(cudaSetDevice(dev));
-        if (n_st) {
-            chk(cudaMemcpyAsync(d_raw_cam.p, st_cam, n_st * sizeof(uint32_t), cudaMemcpyHostToDevice, copy_stream));
-            chk(cudaMemcpyAsync(d_raw_uvd.p, st_uvd, 3 * n_st * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
-            chk(cudaMemcpyAsync(d_raw_W.p, st_W, (st_W_per_obs ? 9 * n_st : 9) * sizeof(double), cudaMemcpyHostToDevice,
-                                copy_stream));
+    // Large problems: the index arrays go up first (several host threads), the structure is analysed on
+    // the device while the measurements follow.  Otherwise (and for the lighting solve, whose setup reads
+    // the host-side permutation) the host analyses the structure while a second thread uploads.
+    structure_on_device = false;
+    const size_t gpu_min = [] {  // CSLAM_HOST_STRUCTURE=1 keeps the host analysis; ..._MIN moves the size threshold
+        if (std::getenv("CSLAM_HOST_STRUCTURE")) return ~size_t(0);
+        const char* e = std::getenv("CSLAM_GPU_STRUCTURE_MIN");
+        return e ? size_t(std::atoll(e)) : (size_t(1) << 20);
+    }();
+    const bool gpu_structure = n_st >= gpu_min && n_st > 0 && !lighting_in_solve();
+    if (gpu_structure) {
+        const int dev = opt.device;
+        d_raw_cam.alloc(n_st, stream);
+        d_raw_pt.alloc(n_st, stream);
+        d_raw_uvd.alloc(3 * n_st, stream);
+        d_raw_W.alloc(st_W_per_obs ? 9 * n_st : 9, stream);
+        d_raw_pts.alloc(3 * std::max<size_t>(n_points, 1), stream);
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+        parallel_h2d(dev, d_raw_cam.p, st_cam, n_st * sizeof(uint32_t));
+        parallel_h2d(dev, d_raw_pt.p, st_pt, n_st * sizeof(uint32_t));
+        pt.lap("index H2D");
+        std::exception_ptr rest_err;
+        std::thread rest([&, dev]() {
+            try {
+                parallel_h2d(dev, d_raw_uvd.p, st_uvd, 3 * n_st * sizeof(double));
+                parallel_h2d(dev, d_raw_W.p, st_W, (st_W_per_obs ? 9 * n_st : 9) * sizeof(double));
+                if (n_points) parallel_h2d(dev, d_raw_pts.p, h_points, 3 * size_t(n_points) * sizeof(double));
+                if (pt.on)
+                    std::fprintf(stderr, "[cslam timing] %-28s %8.2f ms (second thread, from the start of upload)\n", "  raw H2D done",
+                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload).count());
+            } catch (...) {
+                rest_err = std::current_exception();
+            }
+        });
+        bool ok = false;
+        try {
+            ok = build_structure_gpu(nullptr);
+            if (!ok) build_structure();
+        } catch (...) {
+            rest.join();
+            throw;
         }
-        if (n_points)
-            chk(cudaMemcpyAsync(d_raw_pts.p, h_points, 3 * size_t(n_points) * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
-        chk(cudaStreamSynchronize(copy_stream));
-    });
-    try {
-        build_structure();
-    } catch (...) {
+        pt.lap(ok ? "build_structure_gpu" : "build_structure (host fallback)");
+        rest.join();
+        if (rest_err) std::rethrow_exception(rest_err);
+        pt.lap("wait for raw H2D");
+        if (ok && std::getenv("CSLAM_VERIFY_STRUCTURE")) {
+            // debugging / tests: the host analysis must produce exactly the layout the device built
+            obs_user_h.reset(new uint32_t[std::max<size_t>(obs_user_n, 1)]);
+            CSLAM_CUDA(cudaMemcpyAsync(obs_user_h.get(), d_obs_user.p, obs_user_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CSLAM_CUDA(cudaStreamSynchronize(stream));
+            const unsigned long long h_dev = layout_hash();
+            const std::vector<int> rp(s_rowptr_h), cl(s_col_h);
+            build_structure();
+            if (layout_hash() != h_dev || rp != s_rowptr_h || cl != s_col_h)
+                throw std::runtime_error("device and host structure analyses disagree");
+        }
+    } else {
+        // The caller's arrays go to the device as they are, from a second host thread, while this
+        // thread analyses the structure; the landmark-major SoA layout is then gathered on the GPU.
+        cudaStream_t copy_stream = nullptr;
+        CSLAM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        d_raw_cam.alloc(std::max<size_t>(n_st, 1), stream);
+        d_raw_uvd.alloc(3 * std::max<size_t>(n_st, 1), stream);
+        d_raw_W.alloc(st_W_per_obs ? 9 * std::max<size_t>(n_st, 1) : 9, stream);
+        d_raw_pts.alloc(3 * std::max<size_t>(n_points, 1), stream);
+        CSLAM_CUDA(cudaStreamSynchronize(stream));  // the copy stream may touch them from here on
+        std::string copy_err;
+        const int dev = opt.device;
+        std::thread copier([&, dev]() {
+            auto chk = [&](cudaError_t e) {
+                if (e != cudaSuccess && copy_err.empty()) copy_err = cudaGetErrorString(e);
+            };
+            chk(cudaSetDevice(dev));
+            if (n_st) {
+                chk(cudaMemcpyAsync(d_raw_cam.p, st_cam, n_st * sizeof(uint32_t), cudaMemcpyHostToDevice, copy_stream));
+                chk(cudaMemcpyAsync(d_raw_uvd.p, st_uvd, 3 * n_st * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+                chk(cudaMemcpyAsync(d_raw_W.p, st_W, (st_W_per_obs ? 9 * n_st : 9) * sizeof(double), cudaMemcpyHostToDevice,
+                                    copy_stream));
+            }
+            if (n_points)
+                chk(cudaMemcpyAsync(d_raw_pts.p, h_points, 3 * size_t(n_points) * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+            chk(cudaStreamSynchronize(copy_stream));
+            if (pt.on)
+                std::fprintf(stderr, "[cslam timing] %-28s %8.2f ms (second thread, from the start of upload)\n", "  raw H2D done",
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload).count());
+        });
+        try {
+            build_structure();
+        } catch (...) {
+            copier.join();
+            cudaStreamDestroy(copy_stream);
+            throw;
+        }
+        pt.lap("build_structure");
         copier.join();
         cudaStreamDestroy(copy_stream);
-        throw;
+        if (!copy_err.empty()) throw CudaError("raw H2D copy failed: " + copy_err);
+        pt.lap("wait for raw H2D");
     }
-    pt.lap("build_structure");
-    copier.join();
-    cudaStreamDestroy(copy_stream);
-    if (!copy_err.empty()) throw CudaError("raw H2D copy failed: " + copy_err);
-    pt.lap("wait for raw H2D");
-    d_cam_free.upload(cam_free_h, stream);
+    if (!structure_on_device) d_cam_free.upload(cam_free_h, stream);
     auto up_i = [&](DBuf<int>& d, const std::vector<int>& h) { d.upload(h.empty() ? std::vector<int>(1, 0) : h, stream); };
     auto up_u = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) {
         d.upload(h.empty() ? std::vector<uint32_t>(1, 0) : h, stream);
     };
-    up_u(d_lm_base, lm_base_h);
-    up_u(d_lm_stride, lm_stride_h);
-    up_u(d_lm_cnt, lm_cnt_h);
+    if (!structure_on_device) {
+        up_u(d_lm_base, lm_base_h);
+        up_u(d_lm_stride, lm_stride_h);
+        up_u(d_lm_cnt, lm_cnt_h);
+    }
     up_i(d_item_group, item_group_h);
     up_i(d_item_j0, item_j0_h);
     up_i(d_item_n, item_n_h);
@@ -578,9 +983,9 @@ void Engine::upload() {
     up_i(d_g_blk, g_blk_h);
     // internal order <- caller's order, on the device
     const size_t no = size_t(std::max<long long>(n_obs, 1));
-    d_obs_user.alloc(std::max<size_t>(obs_user_n, 1), stream);
-    CSLAM_CUDA(cudaStreamSynchronize(stream));
-    {
+    if (!structure_on_device) {
+        d_obs_user.alloc(std::max<size_t>(obs_user_n, 1), stream);
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
         // pageable H2D is bound by the host-side staging copy: split it over a few threads / streams
         std::string perr;
         const int dev = opt.device;
@@ -595,8 +1000,8 @@ void Engine::upload() {
             if (e != cudaSuccess) perr = cudaGetErrorString(e);
         });
         if (!perr.empty()) throw CudaError("layout H2D failed: " + perr);
+        d_lm_user.upload(lm_user_h.empty() ? std::vector<uint32_t>(1, 0) : lm_user_h, stream);
     }
-    d_lm_user.upload(lm_user_h.empty() ? std::vector<uint32_t>(1, 0) : lm_user_h, stream);
     pt.lap("  small arrays + perm H2D (enqueue)");
     d_obs_cam.alloc(no, stream);
     d_obs_u.alloc(no, stream);
@@ -686,6 +1091,7 @@ void Engine::upload() {
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     pt.lap("  stream sync");
     d_raw_cam.release_async(stream);  // d_raw_pts stays: download() scatters the result into it
+    d_raw_pt.release_async(stream);
     d_raw_uvd.release_async(stream);
     d_raw_W.release_async(stream);
     d_obs_user.release_async(stream);
@@ -1933,6 +2339,23 @@ void Engine::get_reduced_system(int* rowptr, int* col, double* values, double* r
     CSLAM_CUDA(cudaStreamSynchronize(stream));
 }
 
+unsigned long long Engine::layout_hash() const {
+    unsigned long long lh = 1469598103934665603ull;
+    auto mix = [&](const auto& vec) {
+        for (auto v : vec) lh = (lh ^ (unsigned long long)(unsigned)v) * 1099511628211ull;
+        lh = (lh ^ 0xffull) * 1099511628211ull;
+    };
+    mix(cam_free_h); mix(free_cams_h); mix(lm_user_h); mix(lm_base_h); mix(lm_stride_h); mix(lm_cnt_h);
+    for (size_t i = 0; i < obs_user_n; ++i) lh = (lh ^ (unsigned long long)obs_user_h[i]) * 1099511628211ull;
+    lh = (lh ^ 0xffull) * 1099511628211ull;
+    mix(item_group_h); mix(item_j0_h); mix(item_n_h); mix(g_L_h); mix(g_G_h); mix(g_lm0_h);
+    mix(g_obs0_h); mix(g_off_h); mix(g_cams_h); mix(g_blk_off_h); mix(g_blk_h);
+    lh = (lh ^ (unsigned long long)n_lm_grouped) * 1099511628211ull;
+    lh = (lh ^ (unsigned long long)n_items_small) * 1099511628211ull;
+    lh = (lh ^ (unsigned long long)max_group_L) * 1099511628211ull;
+    return lh;
+}
+
 void Engine::analyze(int n_ranks_, int rank_, cslam_structure_info* out) {
     const int keep_n = n_ranks, keep_r = rank;
     n_ranks = n_ranks_;
@@ -1961,19 +2384,7 @@ void Engine::analyze(int n_ranks_, int rank_, cslam_structure_info* out) {
     unsigned long long s = 0;
     for (uint32_t id : lm_user_h) s += id;
     out->landmark_id_sum = s;
-    unsigned long long lh = 1469598103934665603ull;
-    auto mix = [&](const auto& vec) {
-        for (auto v : vec) lh = (lh ^ (unsigned long long)(unsigned)v) * 1099511628211ull;
-        lh = (lh ^ 0xffull) * 1099511628211ull;
-    };
-    mix(cam_free_h); mix(free_cams_h); mix(lm_user_h); mix(lm_base_h); mix(lm_stride_h); mix(lm_cnt_h);
-    for (size_t i = 0; i < obs_user_n; ++i) lh = (lh ^ (unsigned long long)obs_user_h[i]) * 1099511628211ull;
-    lh = (lh ^ 0xffull) * 1099511628211ull;
-    mix(item_group_h); mix(item_j0_h); mix(item_n_h); mix(g_L_h); mix(g_G_h); mix(g_lm0_h);
-    mix(g_obs0_h); mix(g_off_h); mix(g_cams_h); mix(g_blk_off_h); mix(g_blk_h);
-    lh = (lh ^ (unsigned long long)n_lm_grouped) * 1099511628211ull;
-    lh = (lh ^ (unsigned long long)n_items_small) * 1099511628211ull;
-    lh = (lh ^ (unsigned long long)max_group_L) * 1099511628211ull;
+    const unsigned long long lh = layout_hash();
     out->layout_hash = lh;
 }
 

@@ -271,7 +271,8 @@ class Engine {
     DBuf<int> d_cam_free;
     DBuf<uint32_t> d_lm_base, d_lm_stride, d_lm_cnt, d_obs_cam;
     // caller-order staging on the device (upload gathers from it, download scatters into d_raw_pts)
-    DBuf<uint32_t> d_raw_cam, d_obs_user, d_lm_user;
+    DBuf<uint32_t> d_raw_cam, d_raw_pt, d_obs_user, d_lm_user;
+    bool structure_on_device = false;  // layout tables and the observation permutation were built on the device
     DBuf<double> d_raw_uvd, d_raw_W, d_raw_pts;
     // grouped Schur path
     std::vector<int> item_group_h, item_j0_h, item_n_h, g_L_h, g_G_h, g_lm0_h, g_off_h, g_cams_h, g_blk_off_h, g_blk_h;
@@ -395,6 +396,8 @@ class Engine {
 
     DevView view(const double* poses, const double* points) const;
     void build_structure();
+    bool build_structure_gpu(cudaEvent_t idx_ready);  // false: fall back to the host analysis
+    unsigned long long layout_hash() const;
     void ensure_user_copy();
     void schur_pass();
     void run_pcg(int* iters, bool* ok);

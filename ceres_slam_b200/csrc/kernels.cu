@@ -242,6 +242,28 @@ __device__ __forceinline__ void eval_obs_scaled(const DevView& v, long long e, c
     }
 }
 
+// the same with the observation's camera index and measurement already loaded (software prefetch)
+__device__ __forceinline__ void eval_obs_scaled_pre(const DevView& v, long long e, uint32_t c, double ou, double ov, double od,
+                                                    const double* p, const double* sl, ObsEval& o) {
+    stereo_block<true>(v.cam, v.poses + 12ll * c, p, ou, ov, od, obs_W_ptr(v, e), o.r, o.Jc, o.Jp);
+    o.f = v.cam_free[c];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o.Jp[3 * k + q] *= sl[q];
+    }
+    if (o.f >= 0) {
+        const double* sp = v.sc_p + 6ll * o.f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double s = sp[q];
+            o.Jc[q] *= s;
+            o.Jc[6 + q] *= s;
+            o.Jc[12 + q] *= s;
+        }
+    }
+}
+
 // W = Jc^T Jp (6x3 row-major)
 __device__ __forceinline__ void form_W(const ObsEval& o, double* W) {
 #pragma unroll
@@ -626,8 +648,25 @@ __global__ void __launch_bounds__(128)
         // is  y_l.gl + a - (y_l^T V0 y_l + 2 y_l.q + b) / 2  without a second pass over the Jacobians.
         double V[6] = {0, 0, 0, 0, 0, 0}, tg[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, sa = 0, sb = 0;
         ObsEval o;
+        // the next observation's camera index and measurement are requested one iteration ahead
+        uint32_t nc = 0;
+        double nu = 0, nv = 0, nd = 0;
+        if (e0 < e1) {
+            nc = v.obs_cam[e0];
+            nu = v.obs_u[e0];
+            nv = v.obs_v[e0];
+            nd = v.obs_d[e0];
+        }
         for (long long e = e0; e < e1; e += es) {
-            eval_obs_scaled(v, e, p, sl, o);
+            const uint32_t cc = nc;
+            const double cu = nu, cv = nv, cd = nd;
+            if (e + es < e1) {
+                nc = v.obs_cam[e + es];
+                nu = v.obs_u[e + es];
+                nv = v.obs_v[e + es];
+                nd = v.obs_d[e + es];
+            }
+            eval_obs_scaled_pre(v, e, cc, cu, cv, cd, p, sl, o);
             double Jy[3] = {0, 0, 0};
             if (o.f >= 0) {
                 const double* y = yp + 6ll * o.f;
@@ -688,10 +727,23 @@ __global__ void __launch_bounds__(128)
             xn += pn[q] * pn[q];
         }
         // the cost at the candidate
+        if (e0 < e1) {
+            nc = v.obs_cam[e0];
+            nu = v.obs_u[e0];
+            nv = v.obs_v[e0];
+            nd = v.obs_d[e0];
+        }
         for (long long e = e0; e < e1; e += es) {
             double rc[3];
-            const uint32_t c = v.obs_cam[e];
-            stereo_block<false>(v.cam, poses_cand + 12ll * c, pn, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e), rc,
+            const uint32_t c = nc;
+            const double cu = nu, cv = nv, cd = nd;
+            if (e + es < e1) {
+                nc = v.obs_cam[e + es];
+                nu = v.obs_u[e + es];
+                nv = v.obs_v[e + es];
+                nd = v.obs_d[e + es];
+            }
+            stereo_block<false>(v.cam, poses_cand + 12ll * c, pn, cu, cv, cd, obs_W_ptr(v, e), rc,
                                 nullptr, nullptr);
             ccost += 0.5 * (rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2]);
         }

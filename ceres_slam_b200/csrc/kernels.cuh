@@ -118,6 +118,21 @@ void ransac_align_batch(int device, uint32_t n_pairs, const uint32_t* offsets, c
                         uint8_t* inlier_out, uint32_t* n_inliers_out);
 void ransac_triples(uint32_t n, uint32_t num_iters, int variant, uint32_t* out);
 
+// structure analysis on the device (structure.cu): see Engine::build_structure_gpu
+void launch_st_count(cudaStream_t s, size_t n, const uint32_t* cam, const uint32_t* pt, uint32_t n_poses, uint32_t n_points,
+                     uint32_t* cnt, uint8_t* used, int* flags);
+void launch_st_scan(cudaStream_t s, uint32_t n_points, const uint32_t* cnt, uint32_t* ptr, DBuf<uint8_t>& tmp);
+void launch_st_fill(cudaStream_t s, size_t n, const uint32_t* cam, const uint32_t* pt, uint32_t* fill, unsigned long long* ck);
+void launch_st_landmarks(cudaStream_t s, uint32_t n_points, const uint32_t* cnt, const uint32_t* ptr, unsigned long long* ck,
+                         const int* cam_free, int group_lmax, int allow_groups, uint32_t* mincam, unsigned long long* khash,
+                         uint8_t* kok, unsigned long long* mask, int2* far, int far_cap, int* flags);
+void launch_st_group_cams(cudaStream_t s, int n_groups, const uint32_t* g_first_user, const int* g_off, const int* g_L,
+                          const uint32_t* ptr, const unsigned long long* ck, int* g_cams);
+void launch_st_perm(cudaStream_t s, int n_lm, const uint32_t* lm_user, const uint32_t* lm_base, const uint32_t* lm_stride,
+                    const uint32_t* lm_cnt, const uint32_t* ptr, const unsigned long long* ck, uint32_t* obs_user);
+void launch_st_verify(cudaStream_t s, int n_groups, const int* g_L, const int* g_G, const int* g_lm0, const int* g_off,
+                      const int* g_cams, const uint32_t* lm_user, const uint32_t* ptr, const unsigned long long* ck, int* flags);
+
 double measure_fp64_peak_tflops(int device);
 extern std::atomic<unsigned long long> g_kernel_launches;  // every kernel this library launches
 

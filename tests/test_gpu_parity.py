@@ -699,3 +699,64 @@ def test_lm_phong_stage2_lighting_only(product, directional):
     assert np.array_equal(stg["points"], before) and np.array_equal(stg["poses"], tr["poses"])
     for k in ("normals", "phong", "textures", "light"):
         assert rel_err(stg[k], sto[k]) < LM_TOL, k
+
+
+def _shuffled(track, seed):
+    """The same track with its stereo blocks in random order (the analysis must not depend on it)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(len(track["obs_cam"]))
+    tr = dict(track)
+    for k in ("obs_cam", "obs_pt", "uvd"):
+        tr[k] = np.ascontiguousarray(track[k][perm])
+    if np.asarray(track["W"]).size > 9:
+        tr["W"] = np.ascontiguousarray(np.asarray(track["W"]).reshape(-1, 9)[perm])
+    return tr
+
+
+@pytest.mark.parametrize("case", ["plain", "per_obs_W", "sun_prior", "generic_only", "grouped_forced", "far_pairs",
+                                  "long_tracks", "shuffled", "free_first"])
+def test_device_structure_analysis_matches_host(product, monkeypatch, case):
+    """Large problems analyse their structure on the device (structure.cu).  Forced here at small sizes with
+    CSLAM_VERIFY_STRUCTURE=1, which makes upload() rebuild the structure on the host and throw unless the
+    layout hash, the reduced system's pattern and every table agree; the solves must then agree too."""
+    kw = dict(max_num_iterations=4, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    bkw = {}
+    if case == "plain":
+        tr = syn.make_track(60, 15, 8, seed=5)
+    elif case == "per_obs_W":
+        tr = syn.make_track(50, 12, 6, seed=6, per_obs_W=True)
+    elif case == "sun_prior":
+        tr = syn.add_sun(syn.make_track(40, 8, 5, seed=7))
+        bkw = dict(sun=True, prior=(1, tr["poses_gt"][1].copy(), np.eye(6) * 10.0))
+    elif case == "generic_only":
+        tr = syn.make_track(40, 9, 7, seed=8)
+        kw["schur_path"] = 1
+    elif case == "grouped_forced":
+        tr = syn.make_track(40, 2, 9, seed=9)
+        kw["schur_path"] = 2
+    elif case == "far_pairs":
+        # a few landmarks re-observed 80+ poses later: co-visibility beyond the 64-wide masks
+        tr = syn.make_track(120, 6, 5, seed=10)
+        extra = 40
+        tr["obs_cam"] = np.ascontiguousarray(np.concatenate([tr["obs_cam"], (tr["obs_cam"][:extra] + 90).astype(tr["obs_cam"].dtype)]))
+        tr["obs_pt"] = np.ascontiguousarray(np.concatenate([tr["obs_pt"], tr["obs_pt"][:extra]]))
+        tr["uvd"] = np.ascontiguousarray(np.concatenate([tr["uvd"], tr["uvd"][:extra]]))
+        kw["max_num_iterations"] = 1
+    elif case == "long_tracks":
+        tr = syn.make_track(90, 2, 70, seed=11)   # tracks longer than the in-thread insertion sort takes
+    elif case == "shuffled":
+        tr = _shuffled(syn.make_track(60, 14, 10, seed=12), 3)
+    else:
+        tr = syn.make_track(50, 10, 6, seed=13)
+        bkw = dict(hold_first=False)
+    monkeypatch.setenv("CSLAM_GPU_STRUCTURE_MIN", "0")
+    monkeypatch.setenv("CSLAM_VERIFY_STRUCTURE", "1")
+    pd, poses_d, points_d = syn.build_problem(tr, backend="b200", **bkw, **kw)
+    sd = pd.solve()       # upload() throws if the two analyses disagree
+    monkeypatch.delenv("CSLAM_VERIFY_STRUCTURE")
+    monkeypatch.setenv("CSLAM_HOST_STRUCTURE", "1")
+    ph, poses_h, points_h = syn.build_problem(tr, backend="b200", **bkw, **kw)
+    sh = ph.solve()
+    assert sd.num_iterations == sh.num_iterations
+    assert abs(sd.final_cost - sh.final_cost) <= 1e-9 * abs(sh.final_cost)
+    assert rel_err(poses_d, poses_h) < 1e-8 and rel_err(points_d, points_h) < 1e-8
