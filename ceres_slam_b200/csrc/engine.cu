@@ -32,6 +32,30 @@ struct PhaseTimer {
 };
 }  // namespace
 
+// The 1 KB pinned read-back block of a handle comes from a process-wide free list: cudaMallocHost was
+// measured at 3..28 ms per call next to a busy device, which is most of a small solve.
+namespace {
+std::mutex g_pinned_mu;
+std::vector<double*> g_pinned_free;
+double* pinned_scalars_get() {
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        if (!g_pinned_free.empty()) {
+            double* p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    double* p = nullptr;
+    CSLAM_CUDA(cudaMallocHost(&p, 128 * sizeof(double)));
+    return p;
+}
+void pinned_scalars_put(double* p) {
+    std::lock_guard<std::mutex> g(g_pinned_mu);
+    g_pinned_free.push_back(p);
+}
+}  // namespace
+
 Engine::Engine(const cslam_options& o) : opt(o) {}
 
 Engine::~Engine() {
@@ -42,7 +66,10 @@ Engine::~Engine() {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ph.fan_graph) cudaGraphExecDestroy(ph.fan_graph);
     band_sets.clear();
-    if (h_pinned) cudaFreeHost(h_pinned);
+    if (h_pinned) {
+        if (stream) cudaStreamSynchronize(stream);  // nothing of this handle may still write into the block
+        pinned_scalars_put(h_pinned);
+    }
     if (own_stream && stream) cudaStreamDestroy(stream);
     if (nccl_comm) comm_destroy(nccl_comm);
 }
@@ -55,6 +82,7 @@ void Engine::set_stream(cudaStream_t s) {
 
 static void ensure_device(Engine* e, cudaStream_t* stream, bool* own, cudaEvent_t* a, cudaEvent_t* b, cudaEvent_t* c,
                           cudaEvent_t* d, double** pinned) {
+    PhaseTimer et;
     int count = 0;
     cudaError_t st = cudaGetDeviceCount(&count);
     if (st != cudaSuccess || count == 0)
@@ -68,17 +96,21 @@ static void ensure_device(Engine* e, cudaStream_t* stream, bool* own, cudaEvent_
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
+    et.lap("  device / pool");
     if (!*stream) {
         CSLAM_CUDA(cudaStreamCreateWithFlags(stream, cudaStreamNonBlocking));
         *own = true;
     }
+    et.lap("  stream");
     if (!*a) {
         CSLAM_CUDA(cudaEventCreate(a));
         CSLAM_CUDA(cudaEventCreate(b));
         CSLAM_CUDA(cudaEventCreate(c));
         CSLAM_CUDA(cudaEventCreate(d));
     }
-    if (!*pinned) CSLAM_CUDA(cudaMallocHost(pinned, 128 * sizeof(double)));
+    et.lap("  events");
+    if (!*pinned) *pinned = pinned_scalars_get();
+    et.lap("  pinned scalars");
 }
 
 void Engine::prof_begin(int) {
@@ -491,30 +523,67 @@ void Engine::build_structure() {
     bt.lap("  remaining landmarks");
 }
 
-// Pageable host memory -> device, split over a few host threads and streams (the copy is bound by the
-// driver's staging memcpy, which one thread does not saturate).
-static void parallel_h2d(int device, void* dst, const void* src, size_t bytes, size_t max_threads = 8) {
+// Pageable host memory -> device.  cudaMemcpy from pageable memory goes through the driver's own
+// staging and tops out near 10 GB/s however many threads issue it (measured); here a few host threads
+// copy 4 MB pieces into their own pinned buffers (allocated once per process, double-buffered) and
+// DMA them from there, which is bound by the host memcpy and PCIe instead.
+namespace {
+struct H2DPool {
+    static constexpr int kThreads = 8;
+    static constexpr size_t kPiece = size_t(4) << 20;
+    std::mutex mu;  // one transfer at a time
+    int device = -1;
+    char* buf[kThreads][2] = {};
+    cudaStream_t st[kThreads] = {};
+    cudaEvent_t ev[kThreads][2] = {};
+    bool ensure(int dev) {
+        if (device == dev) return true;
+        if (device != -1) return false;  // the pool belongs to another device of this process
+        for (int t = 0; t < kThreads; ++t) {
+            if (cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking) != cudaSuccess) return false;
+            for (int b = 0; b < 2; ++b) {
+                if (cudaHostAlloc(reinterpret_cast<void**>(&buf[t][b]), kPiece, cudaHostAllocDefault) != cudaSuccess) return false;
+                if (cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming) != cudaSuccess) return false;
+            }
+        }
+        device = dev;
+        return true;
+    }
+};
+H2DPool g_h2d;
+}  // namespace
+
+static void parallel_h2d(int device, void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
-    const size_t kMin = size_t(8) << 20;
-    const size_t nt = std::max<size_t>(1, std::min(max_threads, bytes / kMin));
+    std::lock_guard<std::mutex> lock(g_h2d.mu);
+    CSLAM_CUDA(cudaSetDevice(device));
+    if (bytes < (size_t(1) << 20) || !g_h2d.ensure(device)) {
+        CSLAM_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+        return;
+    }
+    const size_t n_piece = (bytes + H2DPool::kPiece - 1) / H2DPool::kPiece;
+    const int nt = int(std::min<size_t>(H2DPool::kThreads, n_piece));
     std::string err;
     std::mutex mu;
-    auto work = [&](size_t t) {
-        const size_t c0 = (bytes * t / nt) & ~size_t(255), c1 = t + 1 == nt ? bytes : (bytes * (t + 1) / nt) & ~size_t(255);
-        cudaStream_t cs = nullptr;
+    auto work = [&](int t) {
         cudaError_t e = cudaSetDevice(device);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
-        if (e == cudaSuccess && c1 > c0)
-            e = cudaMemcpyAsync(static_cast<char*>(dst) + c0, static_cast<const char*>(src) + c0, c1 - c0, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
-        if (cs) cudaStreamDestroy(cs);
+        int b = 0;
+        for (size_t pc = size_t(t); pc < n_piece && e == cudaSuccess; pc += size_t(nt), b ^= 1) {
+            const size_t off = pc * H2DPool::kPiece, n = std::min(H2DPool::kPiece, bytes - off);
+            e = cudaEventSynchronize(g_h2d.ev[t][b]);  // the DMA that last read this buffer
+            if (e != cudaSuccess) break;
+            std::memcpy(g_h2d.buf[t][b], static_cast<const char*>(src) + off, n);
+            e = cudaMemcpyAsync(static_cast<char*>(dst) + off, g_h2d.buf[t][b], n, cudaMemcpyHostToDevice, g_h2d.st[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(g_h2d.ev[t][b], g_h2d.st[t]);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_h2d.st[t]);
         if (e != cudaSuccess) {
             std::lock_guard<std::mutex> g(mu);
             err = cudaGetErrorString(e);
         }
     };
     std::vector<std::thread> th;
-    for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
     work(0);
     for (auto& x : th) x.join();
     if (!err.empty()) throw CudaError("H2D copy failed: " + err);
@@ -590,18 +659,44 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
     d_far.alloc(kFarCap, stream);
     launch_st_landmarks(stream, n_points, d_cnt.p, d_ptr.p, d_ck.p, d_cam_free.p, kGroupLmax, opt.schur_path != 1, d_mincam.p,
                         d_khash.p, d_kok.p, d_mask.p, d_far.p, kFarCap, d_flags.p);
-    std::vector<uint32_t> cnt(size_t(n_points) + 1), mincam(n_points);
-    std::vector<unsigned long long> khash_u(n_points), mask(size_t(std::max(n_free, 1)));
-    std::vector<uint8_t> kok_u(n_points);
-    CSLAM_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.p, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CSLAM_CUDA(cudaMemcpyAsync(mincam.data(), d_mincam.p, mincam.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CSLAM_CUDA(cudaMemcpyAsync(khash_u.data(), d_khash.p, khash_u.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    CSLAM_CUDA(cudaMemcpyAsync(kok_u.data(), d_kok.p, kok_u.size(), cudaMemcpyDeviceToHost, stream));
+    if (n_poses >= (1u << 26)) {
+        free_all();
+        return false;  // the grouping key packs the first camera into 26 bits
+    }
+    // landmarks in order of the first camera that sees them (stable in the point index), on the device
+    const size_t np1 = size_t(n_points) + 1;
+    DBuf<uint32_t> d_keyt, d_valt, d_mincam_s, d_all_lm, d_counts, d_len_a, d_all_ptr, d_key2, d_key2b, d_key2s, d_val_a, d_val_b,
+        d_sorted_a, d_run_pos, d_run_L, d_rflag, d_rlen, d_ridx, d_roff, d_gx, d_gobs0;
+    DBuf<unsigned long long> d_keyh, d_keyh2;
+    DBuf<uint8_t> d_run_flag, d_grouped;
+    DBuf<int> d_goff, d_gL, d_gG, d_glm0, d_gcams;
+    auto free_more = [&]() {
+        for (DBuf<uint32_t>* d : {&d_keyt, &d_valt, &d_mincam_s, &d_all_lm, &d_counts, &d_len_a, &d_all_ptr, &d_key2, &d_key2b, &d_key2s,
+                                  &d_val_a, &d_val_b, &d_sorted_a, &d_run_pos, &d_run_L, &d_rflag, &d_rlen, &d_ridx, &d_roff, &d_gx, &d_gobs0})
+            d->release_async(stream);
+        d_keyh.release_async(stream); d_keyh2.release_async(stream); d_run_flag.release_async(stream); d_grouped.release_async(stream);
+        for (DBuf<int>* d : {&d_goff, &d_gL, &d_gG, &d_glm0, &d_gcams}) d->release_async(stream);
+        free_all();
+    };
+    for (DBuf<uint32_t>* d : {&d_keyt, &d_valt, &d_mincam_s, &d_all_lm, &d_key2, &d_key2b, &d_key2s, &d_val_a, &d_val_b, &d_sorted_a,
+                              &d_run_pos, &d_rflag, &d_rlen, &d_ridx, &d_roff})
+        d->alloc(std::max<size_t>(n_points, 1), stream);
+    d_len_a.alloc(np1, stream);
+    d_all_ptr.alloc(np1, stream);
+    d_counts.alloc(4, stream);
+    d_keyh.alloc(std::max<size_t>(n_points, 1), stream);
+    d_keyh2.alloc(std::max<size_t>(n_points, 1), stream);
+    d_run_flag.alloc(std::max<size_t>(n_points, 1), stream);
+    d_grouped.alloc(std::max<size_t>(n_points, 1), stream);
+    launch_st_order(stream, n_points, n_poses, d_cnt.p, d_mincam.p, d_keyt.p, d_valt.p, d_mincam_s.p, d_all_lm.p, d_counts.p + 2, d_tmp);
+    std::vector<unsigned long long> mask(size_t(std::max(n_free, 1)));
+    uint32_t counts[4] = {0, 0, 0, 0};  // n_ok, n_runs, n_active
     CSLAM_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, mask.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(counts + 2, d_counts.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     if (flags[2]) {
-        free_all();
+        free_more();
         return false;  // more far pairs than the list holds: host analysis
     }
     std::vector<std::pair<int, int>> far;
@@ -611,25 +706,8 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
         CSLAM_CUDA(cudaMemcpyAsync(far.data(), d_far.p, far.size() * sizeof(int2), cudaMemcpyDeviceToHost, stream));
         CSLAM_CUDA(cudaStreamSynchronize(stream));
     }
-    bt.lap("  [gpu] lists / landmark facts");
-
-    // landmarks in order of the first camera that sees them (counting sort, stable in user id)
-    std::vector<uint32_t> bucket(size_t(n_poses) + 1, 0);
-    uint32_t n_active = 0;
-    for (uint32_t j = 0; j < n_points; ++j)
-        if (cnt[j]) {
-            bucket[mincam[j] + 1]++;
-            n_active++;
-        }
-    for (uint32_t k = 0; k < n_poses; ++k) bucket[k + 1] += bucket[k];
-    const std::vector<uint32_t> bstart(bucket);
-    std::vector<uint32_t> all_lm(n_active);
-    for (uint32_t j = 0; j < n_points; ++j)
-        if (cnt[j]) all_lm[bucket[mincam[j]]++] = j;
-    std::vector<uint32_t> all_ptr(size_t(n_active) + 1, 0);
-    for (uint32_t a = 0; a < n_active; ++a) all_ptr[a + 1] = all_ptr[a] + cnt[all_lm[a]];
-    auto lm_len = [&](uint32_t a) { return cnt[all_lm[a]]; };
-    bt.lap("  [gpu] landmark order (host)");
+    const uint32_t n_active = counts[2];
+    bt.lap("  [gpu] lists / facts / order");
 
     // reduced camera system pattern
     {
@@ -648,9 +726,18 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
         nnzU = int(s_col_h.size());
     }
 
-    // this rank's shard
+    // this rank's shard: contiguous landmark range balanced by observation count (needs the prefix sums
+    // of the track lengths on the host; a single rank takes everything)
     uint32_t lo = 0, hi = n_active;
+    std::vector<uint32_t> all_ptr;
     if (n_ranks > 1) {
+        // track lengths and their prefix sums come out of the grouping pass; run it once over everything to get them
+        launch_st_group_sort(stream, n_points, 0, n_active, d_all_lm.p, d_mincam_s.p, d_cnt.p, d_kok.p, d_khash.p, d_len_a.p,
+                             d_all_ptr.p, d_key2.p, d_keyh.p, d_keyh2.p, d_val_a.p, d_val_b.p, d_key2b.p, d_key2s.p, d_sorted_a.p,
+                             d_run_flag.p, d_run_pos.p, d_counts.p, d_tmp);
+        all_ptr.resize(size_t(n_active) + 1);
+        CSLAM_CUDA(cudaMemcpyAsync(all_ptr.data(), d_all_ptr.p, all_ptr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
         auto cut = [&](int r) -> uint32_t {
             const uint64_t target = n_st * uint64_t(r) / uint64_t(n_ranks);
             return uint32_t(std::lower_bound(all_ptr.begin(), all_ptr.end(), uint32_t(target)) - all_ptr.begin());
@@ -658,61 +745,44 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
         lo = std::min(cut(rank), n_active);
         hi = rank == n_ranks - 1 ? n_active : std::min(cut(rank + 1), n_active);
     }
+    // groups: runs of equal (first camera, track length, camera-list hash) among the eligible landmarks of
+    // the shard, sorted on the device; the lists themselves are compared afterwards (st_verify_kernel)
+    launch_st_group_sort(stream, n_points, lo, hi, d_all_lm.p, d_mincam_s.p, d_cnt.p, d_kok.p, d_khash.p, d_len_a.p, d_all_ptr.p,
+                         d_key2.p, d_keyh.p, d_keyh2.p, d_val_a.p, d_val_b.p, d_key2b.p, d_key2s.p, d_sorted_a.p, d_run_flag.p,
+                         d_run_pos.p, d_counts.p, d_tmp);
+    uint32_t ptr_lo_hi[2] = {0, 0};
+    CSLAM_CUDA(cudaMemcpyAsync(counts, d_counts.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(&ptr_lo_hi[0], d_all_ptr.p + lo, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(&ptr_lo_hi[1], d_all_ptr.p + hi, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t n_ok = counts[0], n_runs = counts[1];
     n_lm = int(hi - lo);
     lm_lo = 0;
     lm_hi = n_lm;
-    n_obs = (long long)all_ptr[hi] - (long long)all_ptr[lo];
-
-    // groups: runs of equal (first camera, track length, camera-list hash); the lists themselves are
-    // compared on the device afterwards (st_verify_kernel)
+    n_obs = (long long)ptr_lo_hi[1] - (long long)ptr_lo_hi[0];
     const uint32_t nl = hi - lo;
-    auto khash = [&](uint32_t a) { return khash_u[all_lm[a]]; };
-    auto kok = [&](uint32_t a) { return kok_u[all_lm[a]]; };
-    std::vector<uint32_t> sorted_a(nl);
-    std::vector<uint32_t> sorted_off(size_t(n_poses) + 1, 0);
-    for (uint32_t c = 0; c < n_poses; ++c) {
-        const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
-        uint32_t k = 0;
-        for (uint32_t a = b0; a < b1; ++a) k += kok(a);
-        sorted_off[c + 1] = sorted_off[c] + k;
+    std::vector<uint32_t> run_pos(n_runs), run_L(n_runs);
+    if (n_runs) {
+        d_run_L.alloc(n_runs, stream);
+        launch_st_run_len(stream, n_runs, d_run_pos.p, d_key2s.p, d_run_L.p);
+        CSLAM_CUDA(cudaMemcpyAsync(run_pos.data(), d_run_pos.p, n_runs * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaMemcpyAsync(run_L.data(), d_run_L.p, n_runs * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
     }
-    std::vector<uint8_t> run_start(nl, 0);
-    parallel_chunks(n_poses, 16, [&](int, size_t c0, size_t c1) {
-        for (size_t c = c0; c < c1; ++c) {
-            const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
-            uint32_t* out = sorted_a.data() + sorted_off[c];
-            uint32_t k = 0;
-            for (uint32_t a = b0; a < b1; ++a)
-                if (kok(a)) out[k++] = a;
-            std::sort(out, out + k, [&](uint32_t x, uint32_t y) {
-                const uint32_t lx = lm_len(x), ly = lm_len(y);
-                if (lx != ly) return lx < ly;
-                if (khash(x) != khash(y)) return khash(x) < khash(y);
-                return x < y;
-            });
-            for (uint32_t x = 0; x < k;) {
-                run_start[sorted_off[c] + x] = 1;
-                uint32_t y = x + 1;
-                while (y < k && lm_len(out[y]) == lm_len(out[x]) && khash(out[y]) == khash(out[x])) ++y;
-                x = y;
-            }
-        }
-    });
-    const uint32_t n_ok = sorted_off[n_poses];
+    bt.lap("  [gpu] grouping sort");
+
     const size_t min_group = opt.schur_path == 2 ? 1 : 4;
     g_L_h.clear(); g_G_h.clear(); g_lm0_h.clear(); g_obs0_h.clear(); g_off_h.clear(); g_cams_h.clear();
     g_blk_off_h.clear(); g_blk_h.clear(); item_group_h.clear(); item_j0_h.clear(); item_n_h.clear();
-    std::vector<uint32_t> g_first;
-    std::vector<uint8_t> grouped(nl, 0);
+    std::vector<uint32_t> g_first;  // position of each group's first landmark in the sorted order
     uint32_t obs_cursor = 0, lm_cursor = 0;
     int cams_cursor = 0, blk_cursor = 0;
     std::vector<std::pair<int, int>> items_small, items_large;
-    for (uint32_t x = 0; x < n_ok;) {
-        uint32_t y = x + 1;
-        while (y < n_ok && !run_start[y]) ++y;
-        const uint32_t G = y - x;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const uint32_t x = run_pos[r];
+        const uint32_t G = (r + 1 < n_runs ? run_pos[r + 1] : n_ok) - x;
         if (G >= min_group) {
-            const int L = int(lm_len(sorted_a[x]));
+            const int L = int(run_L[r]);
             const int gid = int(g_L_h.size());
             g_L_h.push_back(L);
             g_G_h.push_back(int(G));
@@ -728,7 +798,6 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
             for (uint32_t j0 = 0; j0 < G; j0 += kItemMax) (L <= 10 ? items_small : items_large).push_back({gid, int(j0)});
             max_group_L = std::max(max_group_L, L);
         }
-        x = y;
     }
     const size_t n_groups = g_L_h.size();
     n_lm_grouped = int(lm_cursor);
@@ -739,31 +808,32 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
             item_j0_h.push_back(it.second);
             item_n_h.push_back(std::min(kItemMax, g_G_h[it.first] - it.second));
         }
-    // camera list of every group from its first landmark (device), then the pair -> block tables (host)
+    // layout rows of every landmark and the groups' camera lists, on the device
     g_cams_h.assign(size_t(cams_cursor), 0);
-    DBuf<uint32_t> d_gfirst;
-    DBuf<int> d_goff, d_gL, d_gG, d_glm0, d_gcams;
+    d_lm_user.alloc(std::max<size_t>(nl, 1), stream);
+    d_lm_base.alloc(std::max<size_t>(nl, 1), stream);
+    d_lm_stride.alloc(std::max<size_t>(nl, 1), stream);
+    d_lm_cnt.alloc(std::max<size_t>(nl, 1), stream);
     if (n_groups) {
-        std::vector<uint32_t> g_first_user(n_groups);
-        for (size_t g = 0; g < n_groups; ++g) g_first_user[g] = all_lm[sorted_a[g_first[g]]];
-        d_gfirst.upload(g_first_user, stream);
+        d_gx.upload(g_first, stream);
+        d_gobs0.upload(g_obs0_h, stream);
         d_goff.upload(g_off_h, stream);
         d_gL.upload(g_L_h, stream);
-        d_gcams.alloc(std::max<size_t>(size_t(cams_cursor), 1), stream);
-        launch_st_group_cams(stream, int(n_groups), d_gfirst.p, d_goff.p, d_gL.p, d_ptr.p, d_ck.p, d_gcams.p);
+        d_gG.upload(g_G_h, stream);
+        d_glm0.upload(g_lm0_h, stream);
+    }
+    d_gcams.alloc(std::max<size_t>(size_t(cams_cursor), 1), stream);
+    launch_st_layout(stream, n_points, lo, hi, int(n_groups), d_gx.p, d_gG.p, d_gL.p, d_glm0.p, d_gobs0.p, d_goff.p, d_sorted_a.p,
+                     d_all_lm.p, d_len_a.p, d_ptr.p, d_ck.p, uint32_t(n_lm_grouped), obs_cursor, d_lm_user.p, d_lm_base.p,
+                     d_lm_stride.p, d_lm_cnt.p, d_grouped.p, d_gcams.p, d_rflag.p, d_rlen.p, d_ridx.p, d_roff.p, d_tmp);
+    if (n_groups) {
         CSLAM_CUDA(cudaMemcpyAsync(g_cams_h.data(), d_gcams.p, g_cams_h.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
         CSLAM_CUDA(cudaStreamSynchronize(stream));
     }
+    // pair -> block tables of the groups (host: binary searches in the pattern)
     g_blk_h.assign(size_t(blk_cursor), -1);
-    lm_user_h.assign(nl, 0);
-    lm_base_h.assign(nl, 0);
-    lm_stride_h.assign(nl, 0);
-    lm_cnt_h.assign(nl, 0);
-    obs_user_n = size_t(n_obs);
-    obs_user_h.reset();
     parallel_chunks(n_groups, 8, [&](int, size_t g0, size_t g1) {
         for (size_t g = g0; g < g1; ++g) {
-            const uint32_t x = g_first[g], G = uint32_t(g_G_h[g]);
             const int L = g_L_h[g];
             int fr[kGroupLmax];
             for (int i = 0; i < L; ++i) fr[i] = cam_free_h[g_cams_h[size_t(g_off_h[g]) + i]];
@@ -777,54 +847,30 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
                     }
                     g_blk_h[size_t(t++)] = e;
                 }
-            const uint32_t base = g_obs0_h[g];
-            for (uint32_t jl = 0; jl < G; ++jl) {
-                const uint32_t a = sorted_a[x + jl];
-                const size_t li = size_t(g_lm0_h[g]) + jl;
-                grouped[a - lo] = 1;
-                lm_user_h[li] = all_lm[a];
-                lm_base_h[li] = base + jl;
-                lm_stride_h[li] = G;
-                lm_cnt_h[li] = uint32_t(L);
-            }
         }
     });
-    // the remaining landmarks, landmark-major, in first-camera order
-    {
-        std::vector<uint32_t> rest;
-        for (uint32_t x = 0; x < nl; ++x)
-            if (!grouped[x]) rest.push_back(lo + x);
-        uint32_t off = obs_cursor;
-        for (size_t r = 0; r < rest.size(); ++r) {
-            const uint32_t a = rest[r], len = lm_len(a);
-            const size_t li = size_t(n_lm_grouped) + r;
-            lm_user_h[li] = all_lm[a];
-            lm_base_h[li] = off;
-            lm_stride_h[li] = 1;
-            lm_cnt_h[li] = len;
-            off += len;
-        }
-    }
-    bt.lap("  [gpu] groups / layout tables (host)");
+    bt.lap("  [gpu] groups / layout tables");
 
-    // layout tables to the device, the observation permutation there, and the check of the groups
-    auto up_u = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) { d.upload(h.empty() ? std::vector<uint32_t>(1, 0) : h, stream); };
-    up_u(d_lm_base, lm_base_h);
-    up_u(d_lm_stride, lm_stride_h);
-    up_u(d_lm_cnt, lm_cnt_h);
-    up_u(d_lm_user, lm_user_h);
+    // the observation permutation and the check of the groups; host copies of the layout rows only on request
+    obs_user_n = size_t(n_obs);
+    obs_user_h.reset();
+    lm_user_h.clear(); lm_base_h.clear(); lm_stride_h.clear(); lm_cnt_h.clear();
     d_obs_user.alloc(std::max<size_t>(obs_user_n, 1), stream);
     launch_st_perm(stream, n_lm, d_lm_user.p, d_lm_base.p, d_lm_stride.p, d_lm_cnt.p, d_ptr.p, d_ck.p, d_obs_user.p);
-    if (n_groups) {
-        d_gG.upload(g_G_h, stream);
-        d_glm0.upload(g_lm0_h, stream);
+    if (n_groups)
         launch_st_verify(stream, int(n_groups), d_gL.p, d_gG.p, d_glm0.p, d_goff.p, d_gcams.p, d_lm_user.p, d_ptr.p, d_ck.p, d_flags.p);
-    }
     CSLAM_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+    if (std::getenv("CSLAM_VERIFY_STRUCTURE")) {
+        lm_user_h.resize(nl); lm_base_h.resize(nl); lm_stride_h.resize(nl); lm_cnt_h.resize(nl);
+        if (nl) {
+            CSLAM_CUDA(cudaMemcpyAsync(lm_user_h.data(), d_lm_user.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CSLAM_CUDA(cudaMemcpyAsync(lm_base_h.data(), d_lm_base.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CSLAM_CUDA(cudaMemcpyAsync(lm_stride_h.data(), d_lm_stride.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CSLAM_CUDA(cudaMemcpyAsync(lm_cnt_h.data(), d_lm_cnt.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        }
+    }
     CSLAM_CUDA(cudaStreamSynchronize(stream));
-    d_gfirst.release_async(stream); d_goff.release_async(stream); d_gL.release_async(stream); d_gG.release_async(stream);
-    d_glm0.release_async(stream); d_gcams.release_async(stream);
-    free_all();
+    free_more();
     bt.lap("  [gpu] permutation + group check");
     if (flags[3]) return false;  // two camera lists with one 64-bit hash: host analysis
     structure_on_device = true;

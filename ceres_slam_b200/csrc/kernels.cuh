@@ -130,6 +130,21 @@ void launch_st_group_cams(cudaStream_t s, int n_groups, const uint32_t* g_first_
                           const uint32_t* ptr, const unsigned long long* ck, int* g_cams);
 void launch_st_perm(cudaStream_t s, int n_lm, const uint32_t* lm_user, const uint32_t* lm_base, const uint32_t* lm_stride,
                     const uint32_t* lm_cnt, const uint32_t* ptr, const unsigned long long* ck, uint32_t* obs_user);
+void launch_st_order(cudaStream_t s, uint32_t n_points, uint32_t n_poses, const uint32_t* cnt, const uint32_t* mincam,
+                     uint32_t* key_tmp, uint32_t* val_tmp, uint32_t* mincam_s, uint32_t* all_lm, uint32_t* n_active_out,
+                     DBuf<uint8_t>& tmp);
+void launch_st_group_sort(cudaStream_t s, uint32_t n_points, uint32_t lo, uint32_t hi, const uint32_t* all_lm,
+                          const uint32_t* mincam_s, const uint32_t* cnt, const uint8_t* kok, const unsigned long long* khash,
+                          uint32_t* len_a, uint32_t* all_ptr, uint32_t* key2, unsigned long long* keyh,
+                          unsigned long long* keyh_tmp, uint32_t* val_a, uint32_t* val_b, uint32_t* key2_b, uint32_t* key2_s,
+                          uint32_t* sorted_a, uint8_t* run_flag, uint32_t* run_pos, uint32_t* counts, DBuf<uint8_t>& tmp);
+void launch_st_run_len(cudaStream_t s, uint32_t n_runs, const uint32_t* run_pos, const uint32_t* key2_s, uint32_t* run_L);
+void launch_st_layout(cudaStream_t s, uint32_t n_points, uint32_t lo, uint32_t hi, int n_groups, const uint32_t* g_x,
+                      const int* g_G, const int* g_L, const int* g_lm0, const uint32_t* g_obs0, const int* g_off,
+                      const uint32_t* sorted_a, const uint32_t* all_lm, const uint32_t* len_a, const uint32_t* ptr,
+                      const unsigned long long* ck, uint32_t n_lm_grouped, uint32_t obs_cursor, uint32_t* lm_user,
+                      uint32_t* lm_base, uint32_t* lm_stride, uint32_t* lm_cnt, uint8_t* grouped, int* g_cams, uint32_t* rflag,
+                      uint32_t* rlen, uint32_t* ridx, uint32_t* roff, DBuf<uint8_t>& tmp);
 void launch_st_verify(cudaStream_t s, int n_groups, const int* g_L, const int* g_G, const int* g_lm0, const int* g_off,
                       const int* g_cams, const uint32_t* lm_user, const uint32_t* ptr, const unsigned long long* ck, int* flags);
 
