@@ -439,7 +439,9 @@ __global__ void __launch_bounds__(G2_NT, 2)
             const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
             const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
             double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
-            // the L observations of a landmark are a chain of dependent global loads: keep three in flight
+            // the L observations of a landmark are a chain of dependent global loads: keep three in
+            // flight.  The queue is three named slots used in rotation by a loop unrolled three times —
+            // rotating it with register moves would make each move wait for the load it forwards.
             double qu[3], qv[3], qd[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -453,15 +455,13 @@ __global__ void __launch_bounds__(G2_NT, 2)
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
             }
-            for (int i = 0; i < L; ++i) {
-                const double ou = qu[0], ov = qv[0], od = qd[0];
-                qu[0] = qu[1]; qv[0] = qv[1]; qd[0] = qd[1];
-                qu[1] = qu[2]; qv[1] = qv[2]; qd[1] = qd[2];
+            auto step = [&](double& su, double& sv, double& sd, int i) {
+                const double ou = su, ov = sv, od = sd;
                 if (i + 3 < L) {
                     const long long e3 = obs0 + (long long)(i + 3) * G + jl;
-                    qu[2] = v.obs_u[e3];
-                    qv[2] = v.obs_v[e3];
-                    qd[2] = v.obs_d[e3];
+                    su = v.obs_u[e3];
+                    sv = v.obs_v[e3];
+                    sd = v.obs_d[e3];
                 }
                 double r[3], Jp[9];
                 if (WPO) {
@@ -479,6 +479,11 @@ __global__ void __launch_bounds__(G2_NT, 2)
                     V[0] += a * a; V[1] += a * b; V[2] += a * c; V[3] += b * b; V[4] += b * c; V[5] += c * c;
                     gq[0] += a * r[k]; gq[1] += b * r[k]; gq[2] += c * r[k];
                 }
+            };
+            for (int i = 0; i < L; i += 3) {
+                step(qu[0], qv[0], qd[0], i);
+                if (i + 1 < L) step(qu[1], qv[1], qd[1], i + 1);
+                if (i + 2 < L) step(qu[2], qv[2], qd[2], i + 2);
             }
             V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
             V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
