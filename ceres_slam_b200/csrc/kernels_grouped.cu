@@ -352,8 +352,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <bool WPO>  // WPO: one 3x3 weight per observation (dataset_vo_sun.cpp:57-59) instead of a shared one
-__global__ void __launch_bounds__(G2_NT, 2)
+template <bool WPO, int MINB>  // WPO: one 3x3 weight per observation (dataset_vo_sun.cpp:57-59) instead of a shared one
+__global__ void __launch_bounds__(G2_NT, MINB)
     schur_grouped2_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
                           double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
                           double* __restrict__ gl, double* __restrict__ scal) {
@@ -720,14 +720,19 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
                           double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
     if (n_items_small > 0) {
-        // two resident CTAs per SM (254 registers); three were measured slower (spills)
-        const int grid = n_items_small < 2 * kSMs ? n_items_small : 2 * kSMs;
+        static const int occ = [] {
+            const char* e = std::getenv("CSLAM_G2_OCC");  // A/B knob: resident CTAs per SM
+            return e && std::atoi(e) == 3 ? 3 : 2;
+        }();
+        const int grid = n_items_small < occ * kSMs ? n_items_small : occ * kSMs;
         // (a single-evaluation variant — V_j reduced through shared memory inside the pipeline, no pass 1 —
         // was measured slower, 2.67 vs 2.50 ms on C5: its per-batch Cholesky chain is exposed latency)
         if (v.W_per_obs)
-            schur_grouped2_kernel<true><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+            schur_grouped2_kernel<true, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+        else if (occ == 3)
+            schur_grouped2_kernel<false, 3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else
-            schur_grouped2_kernel<false><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+            schur_grouped2_kernel<false, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (g.n_items > n_items_small) {

@@ -74,3 +74,21 @@ def test_c3_lighting_solve_properties(product):
     assert np.all(st["phong"][:, :2] >= 0) and np.all(st["phong"][:, :2] <= 1) and np.all(st["phong"][:, 2] >= 1)
     assert np.all(st["textures"] >= 0) and np.all(st["textures"] <= 1)
     assert np.abs(st["light"] - tr["light_gt"]).max() < np.abs(tr["light"] - tr["light_gt"]).max()
+
+
+def test_c5_device_structure_analysis_equals_host(product, c5, monkeypatch):
+    """At this size the structure is analysed on the device (structure.cu).  With CSLAM_VERIFY_STRUCTURE=1
+    upload() rebuilds it on the host and throws unless the layout hash, the reduced system's pattern and every
+    table agree — here on the full 20 M observations, in the caller's order and in a random one."""
+    monkeypatch.setenv("CSLAM_VERIFY_STRUCTURE", "1")
+    p, _, _ = syn.build_problem(c5, backend="b200", max_num_iterations=1, **FIXED)
+    p.upload()
+    info = p.analyze()                                   # host-only analysis of the same problem
+    assert info["n_observations"] == c5["obs_cam"].size and info["n_groups"] > 19000
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(c5["obs_cam"].size)
+    tr = dict(c5)
+    for k in ("obs_cam", "obs_pt", "uvd"):
+        tr[k] = np.ascontiguousarray(c5[k][perm])
+    p2, _, _ = syn.build_problem(tr, backend="b200", max_num_iterations=1, **FIXED)
+    p2.upload()
