@@ -715,415 +715,17 @@ __global__ void __launch_bounds__(G2_NT, MINB)
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Warp-specialised variant (L <= 10).  One 384-thread CTA per SM: warpgroup 0 (4 warps) only applies
-// Z tiles with DMMA, warpgroups 1 and 2 (8 warps) only evaluate observations — pass 1 split over all
-// 256 producer threads (two threads per landmark), then the two groups produce alternate batches
-// into a ring of four Z buffers with full/empty mbarriers per buffer — the only synchronisation
-// between the roles: the producers stage, run pass 1 and reduce on their own and run ahead into
-// the next slice while the consumers still apply and flush the previous one (168 registers, no spills: the
-// accumulators of the two roles no longer share a thread).  The produce stage is a latency-bound chain
-// and the MMA stage is pipe-bound: running them on different warps lets the scheduler fill the first
-// with the second all the time instead of only when the two resident CTAs happen to be out of phase.
-// ---------------------------------------------------------------------------------------------
-constexpr int WS_NT = 384;
-constexpr int WS_NB = 4;                       // Z ring buffers
-constexpr int WS_ZB = G2_ZB + G2_ZPAD;         // doubles per ring buffer
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-struct WsShared {
-    double pose[G2_LMAX * 12];   // 128-byte aligned: first member
-    double sp[G2_LMAX * 6];
-    double A[kItemMax * 9];
-    double W[9];
-    double redsum[32];
-    int free_[G2_LMAX];
-    uint64_t bar;
-    uint64_t full[WS_NB];
-    uint64_t empty[WS_NB];
-};
-
-template <bool WPO>
-__global__ void __launch_bounds__(WS_NT, 1)
-    schur_grouped_ws_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
-                            double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
-                            double* __restrict__ gl, double* __restrict__ scal) {
-    extern __shared__ __align__(128) unsigned char ws_raw[];
-    WsShared& sh = *reinterpret_cast<WsShared*>(ws_raw);
-    double* const ring = reinterpret_cast<double*>(ws_raw + ((sizeof(WsShared) + 127) & ~size_t(127)));
-    double* const scratch = ring + WS_NB * WS_ZB;  // the producers' reduction scratch, 256 x 33
-
-    const int tid = threadIdx.x;
-    const bool consumer = tid < 128;
-    if (tid == 0) {
-        mbar_init(&sh.bar, 1);
-        for (int b = 0; b < WS_NB; ++b) {
-            mbar_init(&sh.full[b], 128);
-            mbar_init(&sh.empty[b], 128);
-        }
-        fence_mbar_init();
-    }
-    if (tid < 9 && !WPO) sh.W[tid] = v.obs_W[tid];
-    __syncthreads();
-    uint32_t phase = 0;
-    uint32_t seq0 = 0;  // batches this CTA has pushed through the ring so far
-    double cost = 0.0;
-
-    if (consumer) {
-        const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-        const int lane = tid & 31, fg = lane >> 2, ft = lane & 3;
-        for (int w = item_lo + blockIdx.x; w < item_hi; w += gridDim.x) {
-            const int g = gv.item_group[w];
-            const int L = gv.g_L[g];
-            const int nj = gv.item_n[w];
-            const int* __restrict__ blk = gv.g_blk + gv.g_blk_off[g];  // read at the flush only
-            const int TL = (G2_NT / L) & ~3;
-            const int nbatch = (nj + TL - 1) / TL;
-            const int T8 = (6 * L + 7) >> 3, Th = (T8 + 1) >> 1, Th1 = (Th + 1) >> 1;
-            const bool tri = warp == 0 || warp == 3;
-            int r0, nr, c0, nc;
-            if (warp == 0) {
-                r0 = 0; nr = Th; c0 = 0; nc = Th;
-            } else if (warp == 3) {
-                r0 = Th; nr = T8 - Th; c0 = Th; nc = T8 - Th;
-            } else if (warp == 1) {
-                r0 = 0; nr = Th1; c0 = Th; nc = T8 - Th;
-            } else {
-                r0 = Th1; nr = Th - Th1; c0 = Th; nc = T8 - Th;
-            }
-            const int zrow_r = 3 * (8 * r0 + fg), zrow_c = 3 * (8 * c0 + fg);
-            const int zlm = 18 * L;
-            double M[20];
-#pragma unroll
-            for (int k = 0; k < 20; ++k) M[k] = 0.0;
-
-            for (int bt = 0; bt < nbatch; ++bt) {
-                const uint32_t seq = seq0 + uint32_t(bt);
-                const int b = int(seq % WS_NB);
-                mbar_wait(&sh.full[b], (seq / WS_NB) & 1u);
-                const double* zt = ring + b * WS_ZB;
-                const int nval = min(TL, nj - bt * TL);
-                const int nk = (3 * nval + 3) >> 2;
-                if (tri) {
-                    for (int ks = 0; ks < nk; ++ks) {
-                        const int kk = 4 * ks + ft, jj = kk / 3;
-                        const double* zb = zt + jj * zlm + (kk - 3 * jj) + zrow_r;
-                        double f[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) f[i] = i < nr ? zb[24 * i] : 0.0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = i; j < 4; ++j)
-                                if (j < nr) dmma884(M[2 * (4 * i - i * (i - 1) / 2 + j - i)], M[2 * (4 * i - i * (i - 1) / 2 + j - i) + 1], f[i], f[j]);
-                    }
-                } else {
-                    for (int ks = 0; ks < nk; ++ks) {
-                        const int kk = 4 * ks + ft, jj = kk / 3;
-                        const double* zb = zt + jj * zlm + (kk - 3 * jj);
-                        double fr[2], fc[4];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) fr[i] = i < nr ? zb[zrow_r + 24 * i] : 0.0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) fc[j] = j < nc ? zb[zrow_c + 24 * j] : 0.0;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (i < nr && j < nc) dmma884(M[2 * (4 * i + j)], M[2 * (4 * i + j) + 1], fr[i], fc[j]);
-                    }
-                }
-                mbar_arrive(&sh.empty[b]);
-            }
-            seq0 += uint32_t(nbatch);
-            {
-                auto flush_tile = [&](int mt, int nt, double m0, double m1) {
-                    const int row = 8 * mt + fg;
-                    if (row >= 6 * L) return;
-                    const int a = row / 6, ra = row - 6 * a;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = 8 * nt + 2 * ft + h;
-                        if (col >= 6 * L || col < row) continue;
-                        const int b = col / 6, rb = col - 6 * b;
-                        const int e = blk[a * L - a * (a - 1) / 2 + (b - a)];
-                        if (e >= 0) red_add(&S[36ll * e + 6 * ra + rb], h ? -m1 : -m0);
-                    }
-                };
-                if (tri) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = i; j < 4; ++j)
-                            if (j < nr) flush_tile(r0 + i, r0 + j, M[2 * (4 * i - i * (i - 1) / 2 + j - i)], M[2 * (4 * i - i * (i - 1) / 2 + j - i) + 1]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (i < nr && j < nc) flush_tile(r0 + i, c0 + j, M[2 * (4 * i + j)], M[2 * (4 * i + j) + 1]);
-                }
-            }
-        }
-    } else {
-        const int pt = tid - 128;          // 0..255
-        const int grp = pt >> 7, gt = pt & 127;
-        for (int w = item_lo + blockIdx.x; w < item_hi; w += gridDim.x) {
-            const int g = gv.item_group[w];
-            const int L = gv.g_L[g], G = gv.g_G[g];
-            const int j0 = gv.item_j0[w], nj = gv.item_n[w];
-            const int lm0 = gv.g_lm0[g] + j0;
-            const long long obs0 = (long long)gv.g_obs0[g] + j0;
-            const int* __restrict__ cams = gv.g_cams + gv.g_off[g];
-            // ---- stage the slice's cameras: free index, scaling, poses (TMA); producers only ----
-            if (pt < L) {
-                const int f = v.cam_free[cams[pt]];
-                sh.free_[pt] = f;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) sh.sp[6 * pt + k] = f >= 0 ? v.sc_p[6ll * f + k] : 0.0;
-            }
-            if (pt == 0) {
-                const int c0 = cams[0];
-                mbar_expect_tx(&sh.bar, L * 96);
-                if (cams[L - 1] - c0 == L - 1) {
-                    tma_load_1d(sh.pose, v.poses + 12ll * c0, L * 96, &sh.bar);
-                } else {
-                    for (int i = 0; i < L; ++i) tma_load_1d(sh.pose + 12 * i, v.poses + 12ll * cams[i], 96, &sh.bar);
-                }
-            }
-            mbar_wait(&sh.bar, phase);
-            phase ^= 1;
-            named_bar_sync(1, 256);
-
-            const int TL = (G2_NT / L) & ~3;
-            const int nbatch = (nj + TL - 1) / TL;
-            const int pq = gt % TL, pi = gt / TL;
-            const bool p_active = pi < L;
-            const int pf = p_active ? sh.free_[pi] : -1;
-            double nx[9];
-            auto prefetch = [&](int jl) {
-                if (p_active && jl < nj) {
-                    const long long j = lm0 + jl;
-                    const long long e = obs0 + (long long)pi * G + jl;
-                    nx[0] = v.obs_u[e]; nx[1] = v.obs_v[e]; nx[2] = v.obs_d[e];
-                    nx[3] = v.points[3 * j]; nx[4] = v.points[3 * j + 1]; nx[5] = v.points[3 * j + 2];
-                    nx[6] = v.sc_l[3 * j]; nx[7] = v.sc_l[3 * j + 1]; nx[8] = v.sc_l[3 * j + 2];
-                }
-            };
-#pragma unroll
-            for (int k = 0; k < 9; ++k) nx[k] = 0.0;
-            prefetch(grp * TL + pq);
-
-            // ---- pass 1, two threads per landmark (slots of one parity each), combined by a shuffle ----
-            {
-                const int jl = pt >> 1, half = pt & 1;
-                const bool have = jl < nj;
-                const long long j = lm0 + (have ? jl : 0);
-                const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
-                const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
-                double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
-                if (have) {
-                    double Wl[9];
-                    if (!WPO) {
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) Wl[k] = sh.W[k];
-                    }
-                    // two observations in flight: named slots, loop unrolled by two
-                    double qu[2], qv[2], qd[2];
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const long long e = obs0 + (long long)min(half + 2 * k, L - 1) * G + jl;
-                        qu[k] = v.obs_u[e];
-                        qv[k] = v.obs_v[e];
-                        qd[k] = v.obs_d[e];
-                    }
-                    auto step = [&](double& su, double& sv, double& sd, int i) {
-                        const double ou = su, ov = sv, od = sd;
-                        if (i + 4 < L) {
-                            const long long e4 = obs0 + (long long)(i + 4) * G + jl;
-                            su = v.obs_u[e4];
-                            sv = v.obs_v[e4];
-                            sd = v.obs_d[e4];
-                        }
-                        double r[3], Jp[9];
-                        if (WPO) {
-                            const double* Wg = v.obs_W + 9 * (obs0 + (long long)i * G + jl);
-#pragma unroll
-                            for (int k = 0; k < 9; ++k) Wl[k] = Wg[k];
-                        }
-                        stereo_block_point(v.cam, sh.pose + 12 * i, p, ou, ov, od, Wl, r, Jp);
-                        cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const double a = Jp[3 * k] * sl[0], b = Jp[3 * k + 1] * sl[1], c = Jp[3 * k + 2] * sl[2];
-                            V[0] += a * a; V[1] += a * b; V[2] += a * c; V[3] += b * b; V[4] += b * c; V[5] += c * c;
-                            gq[0] += a * r[k]; gq[1] += b * r[k]; gq[2] += c * r[k];
-                        }
-                    };
-                    for (int i = half; i < L; i += 4) {
-                        step(qu[0], qv[0], qd[0], i);
-                        if (i + 2 < L) step(qu[1], qv[1], qd[1], i + 2);
-                    }
-                }
-                // the partner thread (adjacent lane) holds the other parity's sums
-#pragma unroll
-                for (int k = 0; k < 6; ++k) V[k] += __shfl_xor_sync(0xffffffffu, V[k], 1);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) gq[k] += __shfl_xor_sync(0xffffffffu, gq[k], 1);
-                if (have && half == 0) {
-                    V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
-                    V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
-                    V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
-                    double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    bool pd = V[0] > 0.0;
-                    if (pd) {
-                        const double c00 = sqrt(V[0]);
-                        const double c10 = V[1] / c00, c20 = V[2] / c00;
-                        const double d1 = V[3] - c10 * c10;
-                        pd = d1 > 0.0;
-                        if (pd) {
-                            const double c11 = sqrt(d1);
-                            const double c21 = (V[4] - c20 * c10) / c11;
-                            const double d2 = V[5] - c20 * c20 - c21 * c21;
-                            pd = d2 > 0.0 && d2 < 1.7976931348623157e308;
-                            if (pd) {
-                                const double c22 = sqrt(d2);
-                                const double a00 = 1.0 / c00, a11 = 1.0 / c11, a22 = 1.0 / c22;
-                                const double a10 = -c10 * a00 * a11;
-                                const double a21 = -c21 * a11 * a22;
-                                const double a20 = -(c20 * a00 + c21 * a10) * a22;
-                                A[0] = a00; A[1] = a10; A[2] = a11; A[3] = a20; A[4] = a21; A[5] = a22;
-                                A[6] = a00 * gq[0];
-                                A[7] = a10 * gq[0] + a11 * gq[1];
-                                A[8] = a20 * gq[0] + a21 * gq[1] + a22 * gq[2];
-                            }
-                        }
-                    }
-                    if (!pd) red_add(&scal[SC_INVALID], 1.0);
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) sh.A[9 * jl + k] = A[k];
-                    gl[3 * j] = gq[0];
-                    gl[3 * j + 1] = gq[1];
-                    gl[3 * j + 2] = gq[2];
-                }
-            }
-            named_bar_sync(1, 256);  // the inverse factors of every landmark are in shared memory
-
-            // ---- produce: this group's batches (every other one) into the ring ----
-            double U[21], gpa[6], bpa[6];
-#pragma unroll
-            for (int k = 0; k < 21; ++k) U[k] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) gpa[k] = bpa[k] = 0.0;
-            for (int bt = grp; bt < nbatch; bt += 2) {
-                const uint32_t seq = seq0 + uint32_t(bt);
-                const int b = int(seq % WS_NB);
-                mbar_wait(&sh.empty[b], ((seq / WS_NB) & 1u) ^ 1u);
-                const int jl = bt * TL + pq;
-                if (p_active) {
-                    double* zt = ring + b * WS_ZB + (pq * L + pi) * 18;
-                    if (jl < nj && pf >= 0) {
-                        const double p[3] = {nx[3], nx[4], nx[5]};
-                        const double sl[3] = {nx[6], nx[7], nx[8]};
-                        const double ou = nx[0], ov = nx[1], od = nx[2];
-                        const long long e = obs0 + (long long)pi * G + jl;
-                        double r[3], Jc[18], Jp[9];
-                        {
-                            double pose[12], Wl[9];
-#pragma unroll
-                            for (int k = 0; k < 12; ++k) pose[k] = sh.pose[12 * pi + k];
-#pragma unroll
-                            for (int k = 0; k < 9; ++k) Wl[k] = WPO ? v.obs_W[9 * e + k] : sh.W[k];
-                            stereo_block<true>(v.cam, pose, p, ou, ov, od, Wl, r, Jc, Jp);
-                        }
-                        prefetch(jl + 2 * TL);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) Jp[3 * k + q] *= sl[q];
-#pragma unroll
-                            for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= sh.sp[6 * pi + q];
-                        }
-                        const double* A = sh.A + 9 * jl;
-                        const double a00 = A[0], a10 = A[1], a11 = A[2], a20 = A[3], a21 = A[4], a22 = A[5];
-                        const double t0 = A[6], t1 = A[7], t2 = A[8];
-                        int u = 0;
-#pragma unroll
-                        for (int a = 0; a < 6; ++a) {
-                            const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3] + Jc[12 + a] * Jp[6];
-                            const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4] + Jc[12 + a] * Jp[7];
-                            const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5] + Jc[12 + a] * Jp[8];
-                            const double z0 = w0 * a00;
-                            const double z1 = w0 * a10 + w1 * a11;
-                            const double z2 = w0 * a20 + w1 * a21 + w2 * a22;
-                            zt[3 * a] = z0;
-                            zt[3 * a + 1] = z1;
-                            zt[3 * a + 2] = z2;
-                            const double ga = Jc[a] * r[0] + Jc[6 + a] * r[1] + Jc[12 + a] * r[2];
-                            gpa[a] += ga;
-                            bpa[a] = fma(-z0, t0, fma(-z1, t1, fma(-z2, t2, bpa[a] + ga)));
-#pragma unroll
-                            for (int b2 = a; b2 < 6; ++b2, ++u)
-                                U[u] = fma(Jc[a], Jc[b2], fma(Jc[6 + a], Jc[6 + b2], fma(Jc[12 + a], Jc[12 + b2], U[u])));
-                        }
-                    } else {
-                        // beyond nj (a k-step may reach one landmark past it) and constant cameras: zero rows
-#pragma unroll
-                        for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(0.0, 0.0);
-                    }
-                }
-                mbar_arrive(&sh.full[b]);
-            }
-            seq0 += uint32_t(nbatch);
-            {
-                // reduce U, g, rhs over the threads of both groups that share a slot, one RED per value
-                double* red = scratch;
-#pragma unroll
-                for (int k = 0; k < 21; ++k) red[pt * 33 + k] = U[k];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    red[pt * 33 + 21 + k] = gpa[k];
-                    red[pt * 33 + 27 + k] = bpa[k];
-                }
-                named_bar_sync(1, 256);
-                for (int idx = pt; idx < L * 33; idx += 256) {
-                    const int i = idx / 33, k = idx - 33 * i;
-                    const int f = sh.free_[i];
-                    if (f < 0) continue;
-                    double acc = 0.0;
-                    for (int q = 0; q < TL; ++q) acc += red[(i * TL + q) * 33 + k] + red[(128 + i * TL + q) * 33 + k];
-                    if (k < 21) {
-                        int a = 0, rem = k;
-                        while (rem >= 6 - a) {
-                            rem -= 6 - a;
-                            ++a;
-                        }
-                        red_add(&Bdiag[36ll * f + 6 * a + a + rem], acc);
-                    } else if (k < 27) {
-                        red_add(&gp[6ll * f + (k - 21)], acc);
-                    } else {
-                        red_add(&bp[6ll * f + (k - 27)], acc);
-                    }
-                }
-            }
-            named_bar_sync(1, 256);  // staging buffers and the scratch are free again
-        }
-    }
-    block_atomic_sum(cost, &scal[SC_COST], sh.redsum);
-}
-
 }  // namespace
 
 void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
                           double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
     if (n_items_small > 0) {
+        // Two resident CTAs per SM.  Measured alternatives on C5 (this kernel: 2.47 ms): three CTAs per SM
+        // (CSLAM_G2_OCC=3: 168 registers, spills) 2.78 ms; a warp-specialised 384-thread CTA (4 DMMA warps +
+        // 8 producer warps, Z ring with full/empty mbarriers; commit "K2 experiment") 2.63 ms — it hides the MMA
+        // stage completely but leaves the producers' staging / pass 1 / reduction bubbles of a slice exposed,
+        // which a second resident CTA covers for free.
         static const int occ = [] {
             const char* e = std::getenv("CSLAM_G2_OCC");  // A/B knob: resident CTAs per SM
             return e && std::atoi(e) == 3 ? 3 : 2;
@@ -1131,18 +733,7 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
         const int grid = n_items_small < occ * kSMs ? n_items_small : occ * kSMs;
         // (a single-evaluation variant — V_j reduced through shared memory inside the pipeline, no pass 1 —
         // was measured slower, 2.67 vs 2.50 ms on C5: its per-batch Cholesky chain is exposed latency)
-        static const bool ws = std::getenv("CSLAM_G2_WS") != nullptr;  // A/B: warp-specialised variant
-        if (ws) {
-            const size_t smem = ((sizeof(WsShared) + 127) & ~size_t(127)) + (size_t(WS_NB) * WS_ZB + 256 * 33) * sizeof(double);
-            const int wgrid = n_items_small < kSMs ? n_items_small : kSMs;
-            if (v.W_per_obs) {
-                CSLAM_CUDA(cudaFuncSetAttribute(schur_grouped_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                schur_grouped_ws_kernel<true><<<wgrid, WS_NT, smem, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
-            } else {
-                CSLAM_CUDA(cudaFuncSetAttribute(schur_grouped_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                schur_grouped_ws_kernel<false><<<wgrid, WS_NT, smem, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
-            }
-        } else if (v.W_per_obs)
+        if (v.W_per_obs)
             schur_grouped2_kernel<true, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else if (occ == 3)
             schur_grouped2_kernel<false, 3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
