@@ -616,14 +616,22 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
     d_flags.alloc(4, stream);
     d_flags.zero(stream);
     launch_st_count(stream, n_st, d_raw_cam.p, d_raw_pt.p, n_poses, n_points, d_cnt.p, d_used.p, d_flags.p);
+    d_fill.alloc(std::max<size_t>(n_points, 1), stream);
+    launch_st_max_track(stream, n_points, d_cnt.p, d_fill.p, d_tmp);  // d_fill[0] <- longest track (buffer reused below)
     std::vector<uint8_t> used(n_poses, 0);
     int flags[4] = {0, 0, 0, 0};
+    uint32_t max_track = 0;
+    CSLAM_CUDA(cudaMemcpyAsync(&max_track, d_fill.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaMemcpyAsync(used.data(), d_used.p, n_poses, cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     if (flags[0]) {
         free_all();
         throw std::invalid_argument("stereo block index out of range");
+    }
+    if (max_track > 4096) {
+        free_all();
+        return false;  // one thread per point sorts its list and walks its camera pairs: host analysis
     }
     for (auto& s : suns) {
         if (s.cam >= n_poses) throw std::invalid_argument("sun block index out of range");

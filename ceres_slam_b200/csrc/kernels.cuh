@@ -138,6 +138,7 @@ void launch_st_group_sort(cudaStream_t s, uint32_t n_points, uint32_t lo, uint32
                           uint32_t* len_a, uint32_t* all_ptr, uint32_t* key2, unsigned long long* keyh,
                           unsigned long long* keyh_tmp, uint32_t* val_a, uint32_t* val_b, uint32_t* key2_b, uint32_t* key2_s,
                           uint32_t* sorted_a, uint8_t* run_flag, uint32_t* run_pos, uint32_t* counts, DBuf<uint8_t>& tmp);
+void launch_st_max_track(cudaStream_t s, uint32_t n_points, const uint32_t* cnt, uint32_t* out, DBuf<uint8_t>& tmp);
 void launch_st_run_len(cudaStream_t s, uint32_t n_runs, const uint32_t* run_pos, const uint32_t* key2_s, uint32_t* run_L);
 void launch_st_layout(cudaStream_t s, uint32_t n_points, uint32_t lo, uint32_t hi, int n_groups, const uint32_t* g_x,
                       const int* g_G, const int* g_L, const int* g_lm0, const uint32_t* g_obs0, const int* g_off,

@@ -417,6 +417,13 @@ void launch_st_group_sort(cudaStream_t s, uint32_t n_points, uint32_t lo, uint32
     CSLAM_CUDA(cudaGetLastError());
 }
 
+// longest track (a single thread sorts a point's list and walks its camera pairs: very long tracks go to
+// the host analysis instead)
+void launch_st_max_track(cudaStream_t s, uint32_t n_points, const uint32_t* cnt, uint32_t* out, DBuf<uint8_t>& tmp) {
+    if (!n_points) return;
+    cub_call(s, tmp, [&](void* t, size_t& b) { return cub::DeviceReduce::Max(t, b, cnt, out, int(n_points), s); });
+}
+
 void launch_st_run_len(cudaStream_t s, uint32_t n_runs, const uint32_t* run_pos, const uint32_t* key2_s, uint32_t* run_L) {
     if (!n_runs) return;
     st_run_len_kernel<<<(n_runs + 255) / 256, 256, 0, s>>>(n_runs, run_pos, key2_s, run_L);
