@@ -629,7 +629,11 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
         free_all();
         throw std::invalid_argument("stereo block index out of range");
     }
-    if (max_track > 4096) {
+    const uint32_t max_track_gpu = [] {  // (the knob exists for the test of this hand-over)
+        const char* e = std::getenv("CSLAM_GPU_STRUCTURE_MAX_TRACK");
+        return e ? uint32_t(std::atoll(e)) : 4096u;
+    }();
+    if (max_track > max_track_gpu) {
         free_all();
         return false;  // one thread per point sorts its list and walks its camera pairs: host analysis
     }
@@ -904,7 +908,7 @@ GroupView Engine::group_view() const {
 
 void Engine::launch_schur(const DevView& v, const LmDiag& dg) {
     if (!item_group_h.empty())
-        launch_schur_grouped(stream, v, group_view(), n_items_small, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal, d_afac.p, n_lm_grouped);
+        launch_schur_grouped(stream, v, group_view(), n_items_small, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
     if (n_lm > n_lm_grouped)
         launch_schur_generic(stream, v, n_lm_grouped, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
 }
@@ -1077,7 +1081,6 @@ void Engine::upload() {
     d_sc_l.alloc(3 * size_t(std::max(n_lm, 1)), stream);
     d_cn_l.alloc(3 * size_t(std::max(n_lm, 1)), stream);
     d_gl.alloc(3 * size_t(std::max(n_lm, 1)), stream);
-    d_afac.alloc(9 * size_t(std::max(n_lm_grouped, 1)), stream);
     d_yl.alloc(3 * size_t(std::max(n_lm, 1)), stream);
     d_s_rowptr.upload(s_rowptr_h, stream);
     d_s_col.upload(s_col_h.empty() ? std::vector<int>(1, 0) : s_col_h, stream);

@@ -285,7 +285,6 @@ class Engine {
     DBuf<double> d_obs_u, d_obs_v, d_obs_d, d_obs_W;
     DBuf<double> d_sc_p, d_sc_l, d_cn_p, d_cn_l;
     DBuf<double> d_gl;                     // scaled point gradient from the last Schur pass
-    DBuf<double> d_afac;                   // per grouped landmark: inverse Cholesky factor of V_j and C^-1 g_l (9 doubles)
     DBuf<int> d_s_rowptr, d_s_col, d_lt_rowptr, d_lt_col, d_lt_blk;
     // [ S values (36 nnzU) | Bdiag (36 nf) | rhs (6 nf) | gp (6 nf) | scalars (SC_COUNT) ] — one
     // contiguous buffer so a single all-reduce sums every rank's partial reduced system

@@ -30,7 +30,7 @@ void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi
 // a producer warp forms Z = W chol(V)^-T per observation, consumer warps keep the 6x6 pair
 // blocks of the slice in registers and flush them once (SYRK-shaped, output stationary)
 void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
-                          double* Bdiag, double* bp, double* gp, double* gl, double* scal, double* afac, int n_lm_grouped);
+                          double* Bdiag, double* bp, double* gp, double* gl, double* scal);
 // sun-sensor and pose-prior blocks (camera-only): adds to Bdiag, bp, gp and the cost
 void launch_camonly_build(cudaStream_t s, const DevView& v, const SunBlockData* suns, int n_sun,
                           const PriorBlockData* priors, int n_prior, double* Bdiag, double* bp, double* gp,

@@ -325,109 +325,6 @@ __global__ void __launch_bounds__(32 * (1 + CW))
 
 
 // ---------------------------------------------------------------------------------------------
-// Pass 1 of the elimination for the grouped landmarks with L <= 10, as a kernel of its own:
-//   V_j = sum_i Jp_i^T Jp_i + D^2,  V_j = C C^T,  A = C^-1,  t = A g_l,  cost
-// one thread per landmark at full occupancy (inside the MMA kernel it was a latency-bound phase of
-// 100 busy threads at two warps per scheduler).  Three observations in flight per thread (named
-// slots, loop unrolled by three).  afac[9 j] = [a00 a10 a11 a20 a21 a22 | t0 t1 t2].
-// ---------------------------------------------------------------------------------------------
-template <bool WPO>
-__global__ void __launch_bounds__(128)
-    landmark_factor_kernel(DevView v, int n_lm, int lmax, LmDiag dg, double* __restrict__ afac, double* __restrict__ gl,
-                           double* __restrict__ scal) {
-    __shared__ double s_redsum[32];
-    double cost = 0.0;
-    double Wl[9];
-    if (!WPO) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Wl[k] = v.obs_W[k];
-    }
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_lm; j += gridDim.x * blockDim.x) {
-        const int L = int(v.lm_cnt[j]);
-        if (L > lmax) continue;  // longer camera lists: the kernel that takes them runs its own pass 1
-        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
-        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
-        const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
-        double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
-        uint32_t qc[3];
-        double qu[3], qv[3], qd[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const long long e = e0 + (long long)min(k, L - 1) * es;
-            qc[k] = v.obs_cam[e];
-            qu[k] = v.obs_u[e];
-            qv[k] = v.obs_v[e];
-            qd[k] = v.obs_d[e];
-        }
-        auto step = [&](uint32_t& sc, double& su, double& sv, double& sd, int i) {
-            const uint32_t c = sc;
-            const double ou = su, ov = sv, od = sd;
-            if (i + 3 < L) {
-                const long long e3 = e0 + (long long)(i + 3) * es;
-                sc = v.obs_cam[e3];
-                su = v.obs_u[e3];
-                sv = v.obs_v[e3];
-                sd = v.obs_d[e3];
-            }
-            double r[3], Jp[9];
-            if (WPO) {
-                const double* Wg = v.obs_W + 9 * (e0 + (long long)i * es);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) Wl[k] = Wg[k];
-            }
-            stereo_block_point(v.cam, v.poses + 12ll * c, p, ou, ov, od, Wl, r, Jp);
-            cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double a = Jp[3 * k] * sl[0], b = Jp[3 * k + 1] * sl[1], cc = Jp[3 * k + 2] * sl[2];
-                V[0] += a * a; V[1] += a * b; V[2] += a * cc; V[3] += b * b; V[4] += b * cc; V[5] += cc * cc;
-                gq[0] += a * r[k]; gq[1] += b * r[k]; gq[2] += cc * r[k];
-            }
-        };
-        for (int i = 0; i < L; i += 3) {
-            step(qc[0], qu[0], qv[0], qd[0], i);
-            if (i + 1 < L) step(qc[1], qu[1], qv[1], qd[1], i + 1);
-            if (i + 2 < L) step(qc[2], qu[2], qv[2], qd[2], i + 2);
-        }
-        V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
-        V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
-        V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
-        double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        bool pd = V[0] > 0.0;
-        if (pd) {
-            const double c00 = sqrt(V[0]);
-            const double c10 = V[1] / c00, c20 = V[2] / c00;
-            const double d1 = V[3] - c10 * c10;
-            pd = d1 > 0.0;
-            if (pd) {
-                const double c11 = sqrt(d1);
-                const double c21 = (V[4] - c20 * c10) / c11;
-                const double d2 = V[5] - c20 * c20 - c21 * c21;
-                pd = d2 > 0.0 && d2 < 1.7976931348623157e308;
-                if (pd) {
-                    const double c22 = sqrt(d2);
-                    const double a00 = 1.0 / c00, a11 = 1.0 / c11, a22 = 1.0 / c22;
-                    const double a10 = -c10 * a00 * a11;
-                    const double a21 = -c21 * a11 * a22;
-                    const double a20 = -(c20 * a00 + c21 * a10) * a22;
-                    A[0] = a00; A[1] = a10; A[2] = a11; A[3] = a20; A[4] = a21; A[5] = a22;
-                    A[6] = a00 * gq[0];
-                    A[7] = a10 * gq[0] + a11 * gq[1];
-                    A[8] = a20 * gq[0] + a21 * gq[1] + a22 * gq[2];
-                }
-            }
-        }
-        if (!pd) red_add(&scal[SC_INVALID], 1.0);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) afac[9ll * j + k] = A[k];
-        gl[3ll * j] = gq[0];
-        gl[3ll * j + 1] = gq[1];
-        gl[3ll * j + 2] = gq[2];
-    }
-    block_atomic_sum(cost, &scal[SC_COST], s_redsum);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Variant for track length L <= 10.
 // Every thread is producer AND consumer: in one step of the software pipeline a thread first
 // evaluates one observation of batch n+1 (camera slot fixed per thread: pose and scaling stay in
@@ -459,7 +356,7 @@ template <bool WPO, int MINB>  // WPO: one 3x3 weight per observation (dataset_v
 __global__ void __launch_bounds__(G2_NT, MINB)
     schur_grouped2_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
                           double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
-                          double* __restrict__ gl, double* __restrict__ scal, const double* __restrict__ afac) {
+                          double* __restrict__ gl, double* __restrict__ scal) {
     __shared__ __align__(128) double s_pose[G2_LMAX * 12];
     __shared__ double s_sp[G2_LMAX * 6];
     __shared__ double s_A[kItemMax * 9];
@@ -536,8 +433,93 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         for (int k = 0; k < 9; ++k) nx[k] = 0.0;
         prefetch(pq);
 
-        // ---- the landmarks' inverse Cholesky factors and t = C^-1 g_l (landmark_factor_kernel) ----
-        for (int k = tid; k < 9 * nj; k += G2_NT) s_A[k] = afac[9ll * lm0 + k];
+        // ---- pass 1: V_j = sum Jp^T Jp + D^2, Cholesky, A = C^-1, t = A g_l ----
+        for (int jl = tid; jl < nj; jl += G2_NT) {
+            const long long j = lm0 + jl;
+            const double p[3] = {v.points[3 * j], v.points[3 * j + 1], v.points[3 * j + 2]};
+            const double sl[3] = {v.sc_l[3 * j], v.sc_l[3 * j + 1], v.sc_l[3 * j + 2]};
+            double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
+            // the L observations of a landmark are a chain of dependent global loads: keep three in
+            // flight.  The queue is three named slots used in rotation by a loop unrolled three times —
+            // rotating it with register moves would make each move wait for the load it forwards.
+            double qu[3], qv[3], qd[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const long long e = obs0 + (long long)min(k, L - 1) * G + jl;
+                qu[k] = v.obs_u[e];
+                qv[k] = v.obs_v[e];
+                qd[k] = v.obs_d[e];
+            }
+            double Wl[9];
+            if (!WPO) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
+            }
+            auto step = [&](double& su, double& sv, double& sd, int i) {
+                const double ou = su, ov = sv, od = sd;
+                if (i + 3 < L) {
+                    const long long e3 = obs0 + (long long)(i + 3) * G + jl;
+                    su = v.obs_u[e3];
+                    sv = v.obs_v[e3];
+                    sd = v.obs_d[e3];
+                }
+                double r[3], Jp[9];
+                if (WPO) {
+                    // (a predicated-off load in this loop would share a scoreboard with the prefetch
+                    // above and make every iteration wait for it: hence the template parameter)
+                    const double* Wg = v.obs_W + 9 * (obs0 + (long long)i * G + jl);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Wl[k] = Wg[k];
+                }
+                stereo_block_point(v.cam, s_pose + 12 * i, p, ou, ov, od, Wl, r, Jp);
+                cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double a = Jp[3 * k] * sl[0], b = Jp[3 * k + 1] * sl[1], c = Jp[3 * k + 2] * sl[2];
+                    V[0] += a * a; V[1] += a * b; V[2] += a * c; V[3] += b * b; V[4] += b * c; V[5] += c * c;
+                    gq[0] += a * r[k]; gq[1] += b * r[k]; gq[2] += c * r[k];
+                }
+            };
+            for (int i = 0; i < L; i += 3) {
+                step(qu[0], qv[0], qd[0], i);
+                if (i + 1 < L) step(qu[1], qv[1], qd[1], i + 1);
+                if (i + 2 < L) step(qu[2], qv[2], qd[2], i + 2);
+            }
+            V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+            double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            bool pd = V[0] > 0.0;
+            if (pd) {
+                const double c00 = sqrt(V[0]);
+                const double c10 = V[1] / c00, c20 = V[2] / c00;
+                const double d1 = V[3] - c10 * c10;
+                pd = d1 > 0.0;
+                if (pd) {
+                    const double c11 = sqrt(d1);
+                    const double c21 = (V[4] - c20 * c10) / c11;
+                    const double d2 = V[5] - c20 * c20 - c21 * c21;
+                    pd = d2 > 0.0 && d2 < 1.7976931348623157e308;
+                    if (pd) {
+                        const double c22 = sqrt(d2);
+                        const double a00 = 1.0 / c00, a11 = 1.0 / c11, a22 = 1.0 / c22;
+                        const double a10 = -c10 * a00 * a11;
+                        const double a21 = -c21 * a11 * a22;
+                        const double a20 = -(c20 * a00 + c21 * a10) * a22;
+                        A[0] = a00; A[1] = a10; A[2] = a11; A[3] = a20; A[4] = a21; A[5] = a22;
+                        A[6] = a00 * gq[0];
+                        A[7] = a10 * gq[0] + a11 * gq[1];
+                        A[8] = a20 * gq[0] + a21 * gq[1] + a22 * gq[2];
+                    }
+                }
+            }
+            if (!pd) red_add(&scal[SC_INVALID], 1.0);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s_A[9 * jl + k] = A[k];
+            gl[3 * j] = gq[0];
+            gl[3 * j + 1] = gq[1];
+            gl[3 * j + 2] = gq[2];
+        }
         __syncthreads();
 
         // ---- pipeline: produce Z of batch n+1, apply batch n with DMMA ----
@@ -736,36 +718,28 @@ __global__ void __launch_bounds__(G2_NT, MINB)
 }  // namespace
 
 void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
-                          double* Bdiag, double* bp, double* gp, double* gl, double* scal, double* afac, int n_lm_grouped) {
+                          double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
     if (n_items_small > 0) {
         // Two resident CTAs per SM.  Measured alternatives on C5 (this kernel: 2.47 ms): three CTAs per SM
         // (CSLAM_G2_OCC=3: 168 registers, spills) 2.78 ms; a warp-specialised 384-thread CTA (4 DMMA warps +
         // 8 producer warps, Z ring with full/empty mbarriers; commit "K2 experiment") 2.63 ms — it hides the MMA
         // stage completely but leaves the producers' staging / pass 1 / reduction bubbles of a slice exposed,
-        // which a second resident CTA covers for free.
+        // which a second resident CTA covers for free; pass 1 as a full-occupancy kernel of its own (factors
+        // through global memory) 2.60 ms in total — inside this kernel it hides behind the other CTA's MMA stage.
         static const int occ = [] {
             const char* e = std::getenv("CSLAM_G2_OCC");  // A/B knob: resident CTAs per SM
             return e && std::atoi(e) == 3 ? 3 : 2;
         }();
         const int grid = n_items_small < occ * kSMs ? n_items_small : occ * kSMs;
-        {
-            // pass 1 for every grouped landmark with L <= 10 (grouped landmarks come first in the internal order)
-            const int fgrid = std::max(1, std::min((n_lm_grouped + 127) / 128, 16 * kSMs));
-            if (v.W_per_obs)
-                landmark_factor_kernel<true><<<fgrid, 128, 0, s>>>(v, n_lm_grouped, G2_LMAX, dg, afac, gl, scal);
-            else
-                landmark_factor_kernel<false><<<fgrid, 128, 0, s>>>(v, n_lm_grouped, G2_LMAX, dg, afac, gl, scal);
-            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-        }
         // (a single-evaluation variant — V_j reduced through shared memory inside the pipeline, no pass 1 —
         // was measured slower, 2.67 vs 2.50 ms on C5: its per-batch Cholesky chain is exposed latency)
         if (v.W_per_obs)
-            schur_grouped2_kernel<true, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal, afac);
+            schur_grouped2_kernel<true, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else if (occ == 3)
-            schur_grouped2_kernel<false, 3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal, afac);
+            schur_grouped2_kernel<false, 3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else
-            schur_grouped2_kernel<false, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal, afac);
+            schur_grouped2_kernel<false, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (g.n_items > n_items_small) {

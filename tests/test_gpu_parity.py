@@ -747,13 +747,9 @@ def test_device_structure_analysis_matches_host(product, monkeypatch, case):
     elif case == "shuffled":
         tr = _shuffled(syn.make_track(60, 14, 10, seed=12), 3)
     elif case == "very_long_track":
-        # one point seen by every pose (> 4096 observations): the device analysis hands over to the host one
-        tr = syn.make_track(4200, 1, 3, seed=14)
-        n = tr["n_poses"]
-        tr["obs_cam"] = np.ascontiguousarray(np.concatenate([tr["obs_cam"], np.arange(n).astype(tr["obs_cam"].dtype)]))
-        tr["obs_pt"] = np.ascontiguousarray(np.concatenate([tr["obs_pt"], np.zeros(n, dtype=tr["obs_pt"].dtype)]))
-        tr["uvd"] = np.ascontiguousarray(np.concatenate([tr["uvd"], np.tile(tr["uvd"][:1], (n, 1))]))
-        kw["max_num_iterations"] = 1
+        # tracks above the limit (4096 observations; lowered here): the device analysis hands over to the host one
+        tr = syn.make_track(90, 2, 70, seed=15)
+        monkeypatch.setenv("CSLAM_GPU_STRUCTURE_MAX_TRACK", "32")
     else:
         tr = syn.make_track(50, 10, 6, seed=13)
         bkw = dict(hold_first=False)
