@@ -457,8 +457,10 @@ __global__ void __launch_bounds__(G2_NT, MINB)
             }
             auto step = [&](double& su, double& sv, double& sd, int i) {
                 const double ou = su, ov = sv, od = sd;
-                if (i + 3 < L) {
-                    const long long e3 = obs0 + (long long)(i + 3) * G + jl;
+                {
+                    // unconditional (index clamped): a predicated load goes to a temporary and is forwarded
+                    // into the slot by a move that waits for it
+                    const long long e3 = obs0 + (long long)min(i + 3, L - 1) * G + jl;
                     su = v.obs_u[e3];
                     sv = v.obs_v[e3];
                     sd = v.obs_d[e3];
