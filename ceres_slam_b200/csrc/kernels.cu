@@ -630,7 +630,7 @@ __global__ void pose_plus_kernel(DevView v, const double* __restrict__ yp, doubl
     block_atomic_sum(bad, &scal2[SC_NONFINITE], s_red);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     backsub_kernel(DevView v, int lm_lo, int lm_hi, LmDiag dg, const double* __restrict__ yp,
                    const double* __restrict__ poses_cand, double* __restrict__ points_cand,
                    double* __restrict__ yl_out, double* __restrict__ scal2) {
