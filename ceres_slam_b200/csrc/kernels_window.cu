@@ -14,6 +14,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <mutex>
+
 #include "kernels.cuh"
 
 namespace cslam {
@@ -923,6 +925,55 @@ bool Engine::window_eligible() const {
 
 // Pack the windows into flat batch arrays, one launch, unpack.  Results are written into each
 // engine's caller-owned pose / point arrays, its iteration log and `summaries`.
+// Per-call resources of solve_window_batch, pooled process-wide: a pinned staging block (grow-only), a stream
+// and two events.  Concurrent callers get different arenas.
+struct WindowArena {
+    int device = -1;
+    char* pinned = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+static std::mutex g_arena_mu;
+static std::vector<WindowArena*> g_arena_free;
+
+static WindowArena* window_arena_take(int device, size_t bytes) {
+    WindowArena* a = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_arena_mu);
+        for (size_t i = 0; i < g_arena_free.size(); ++i)
+            if (g_arena_free[i]->device == device) {
+                a = g_arena_free[i];
+                g_arena_free.erase(g_arena_free.begin() + long(i));
+                break;
+            }
+    }
+    if (!a) {
+        a = new WindowArena;
+        a->device = device;
+        CSLAM_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+        CSLAM_CUDA(cudaEventCreate(&a->ev0));
+        CSLAM_CUDA(cudaEventCreate(&a->ev1));
+    }
+    if (a->cap < bytes) {
+        if (a->pinned) cudaFreeHost(a->pinned);
+        a->pinned = nullptr;
+        a->cap = 0;
+        const size_t want = std::max(bytes + bytes / 2, size_t(1) << 20);
+        if (cudaMallocHost(reinterpret_cast<void**>(&a->pinned), want) != cudaSuccess) {
+            std::lock_guard<std::mutex> g(g_arena_mu);
+            g_arena_free.push_back(a);
+            throw CudaError("pinned staging allocation failed");
+        }
+        a->cap = want;
+    }
+    return a;
+}
+static void window_arena_give(WindowArena* a) {
+    std::lock_guard<std::mutex> g(g_arena_mu);
+    g_arena_free.push_back(a);
+}
+
 void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
     // windows the kernel does not take go through the generic engine
     std::vector<int> take;
@@ -1034,86 +1085,104 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         log_total += d.log_cap;
     }
 
-    cudaStream_t stream = nullptr;
-    CSLAM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    CSLAM_CUDA(cudaEventCreate(&ev0));
-    CSLAM_CUDA(cudaEventCreate(&ev1));
-    try {
-        DBuf<WinDesc> d_desc;
-        DBuf<double> d_poses, d_pts, d_pts_cand, d_pts_best, d_ou, d_ov, d_od, d_oW, d_scl, d_gl, d_logs;
-        DBuf<int> d_cam_free, d_log_rows;
-        DBuf<uint32_t> d_lm_ptr;
-        DBuf<uint8_t> d_ocam;
-        DBuf<SunBlockData> d_suns;
-        DBuf<PriorBlockData> d_priors;
-        DBuf<cslam_summary> d_sum;
-        auto pad1 = [](auto& v) {
-            if (v.empty()) v.resize(1);
-        };
-        pad1(pts); pad1(ou); pad1(ov); pad1(od); pad1(oW); pad1(ocam); pad1(suns); pad1(priors);
-        d_desc.upload(desc, stream);
-        d_poses.upload(poses, stream);
-        d_cam_free.upload(cam_free, stream);
-        d_pts.upload(pts, stream);
-        d_pts_cand.alloc(pts.size(), stream);
-        d_pts_best.alloc(pts.size(), stream);
-        d_scl.alloc(pts.size(), stream);
-        d_gl.alloc(pts.size(), stream);
-        d_lm_ptr.upload(lm_ptr, stream);
-        d_ocam.upload(ocam, stream);
-        d_ou.upload(ou, stream);
-        d_ov.upload(ov, stream);
-        d_od.upload(od, stream);
-        d_oW.upload(oW, stream);
-        d_suns.upload(suns, stream);
-        d_priors.upload(priors, stream);
-        d_sum.alloc(nw, stream);
-        d_logs.alloc(size_t(log_total) * CSLAM_LOG_COLS, stream);
-        d_log_rows.alloc(nw, stream);
+    // One pinned staging block, one device block, ONE host-to-device copy and ONE device-to-host copy per
+    // batch (a window is a few KB: a dozen separate copies and allocations cost more than the kernel).
+    // Layout (256-byte aligned pieces):  [inputs ... | poses | best points | summaries | logs | log rows | scratch]
+    // The copy up covers inputs + poses, the copy back poses .. log rows.
+    auto pad1 = [](auto& v) {
+        if (v.empty()) v.resize(1);
+    };
+    pad1(pts); pad1(ou); pad1(ov); pad1(od); pad1(oW); pad1(ocam); pad1(suns); pad1(priors);
+    size_t cursor = 0;
+    auto place = [&](size_t bytes) {
+        const size_t off = cursor;
+        cursor = (cursor + bytes + 255) & ~size_t(255);
+        return off;
+    };
+    const size_t o_desc = place(desc.size() * sizeof(WinDesc)), o_camfree = place(cam_free.size() * sizeof(int)),
+                 o_pts = place(pts.size() * 8), o_lmptr = place(lm_ptr.size() * sizeof(uint32_t)), o_ocam = place(ocam.size()),
+                 o_ou = place(ou.size() * 8), o_ov = place(ov.size() * 8), o_od = place(od.size() * 8), o_oW = place(oW.size() * 8),
+                 o_suns = place(suns.size() * sizeof(SunBlockData)), o_priors = place(priors.size() * sizeof(PriorBlockData));
+    const size_t o_poses = place(poses.size() * 8);
+    const size_t up_bytes = cursor;
+    const size_t o_best = place(pts.size() * 8), o_sum = place(size_t(nw) * sizeof(cslam_summary)),
+                 o_logs = place(size_t(log_total) * CSLAM_LOG_COLS * 8), o_rows = place(size_t(nw) * sizeof(int));
+    const size_t down_end = cursor;
+    const size_t o_cand = place(pts.size() * 8), o_scl = place(pts.size() * 8), o_gl = place(pts.size() * 8);
+    const size_t total = cursor;
+
+    WindowArena* arena = window_arena_take(first.opt.device, down_end);
+    struct Give {
+        WindowArena* a;
+        ~Give() { window_arena_give(a); }
+    } give{arena};
+    cudaStream_t stream = arena->stream;
+    cudaEvent_t ev0 = arena->ev0, ev1 = arena->ev1;
+    char* hp = arena->pinned;
+    auto put = [&](size_t off, const void* src, size_t bytes) { std::memcpy(hp + off, src, bytes); };
+    put(o_desc, desc.data(), desc.size() * sizeof(WinDesc));
+    put(o_camfree, cam_free.data(), cam_free.size() * sizeof(int));
+    put(o_pts, pts.data(), pts.size() * 8);
+    put(o_lmptr, lm_ptr.data(), lm_ptr.size() * sizeof(uint32_t));
+    put(o_ocam, ocam.data(), ocam.size());
+    put(o_ou, ou.data(), ou.size() * 8);
+    put(o_ov, ov.data(), ov.size() * 8);
+    put(o_od, od.data(), od.size() * 8);
+    put(o_oW, oW.data(), oW.size() * 8);
+    put(o_suns, suns.data(), suns.size() * sizeof(SunBlockData));
+    put(o_priors, priors.data(), priors.size() * sizeof(PriorBlockData));
+    put(o_poses, poses.data(), poses.size() * 8);
+    {
+        DBuf<uint8_t> d_all;
+        d_all.alloc(total, stream);
+        struct Free {
+            DBuf<uint8_t>& d;
+            cudaStream_t s;
+            ~Free() { d.release_async(s); }
+        } free_all{d_all, stream};
+        uint8_t* dp = d_all.p;
+        CSLAM_CUDA(cudaMemcpyAsync(dp, hp, up_bytes, cudaMemcpyHostToDevice, stream));
         WinBufs B;
-        B.desc = d_desc.p;
-        B.poses = d_poses.p;
-        B.cam_free = d_cam_free.p;
-        B.pts = d_pts.p;
-        B.pts_cand = d_pts_cand.p;
-        B.pts_best = d_pts_best.p;
-        B.lm_ptr = d_lm_ptr.p;
-        B.obs_cam = d_ocam.p;
-        B.obs_u = d_ou.p;
-        B.obs_v = d_ov.p;
-        B.obs_d = d_od.p;
-        B.obs_W = d_oW.p;
-        B.sc_l = d_scl.p;
-        B.gl = d_gl.p;
-        B.suns = d_suns.p;
-        B.priors = d_priors.p;
-        B.summaries = d_sum.p;
-        B.logs = d_logs.p;
-        B.log_rows = d_log_rows.p;
+        B.desc = reinterpret_cast<WinDesc*>(dp + o_desc);
+        B.poses = reinterpret_cast<double*>(dp + o_poses);
+        B.cam_free = reinterpret_cast<int*>(dp + o_camfree);
+        B.pts = reinterpret_cast<double*>(dp + o_pts);
+        B.pts_cand = reinterpret_cast<double*>(dp + o_cand);
+        B.pts_best = reinterpret_cast<double*>(dp + o_best);
+        B.lm_ptr = reinterpret_cast<uint32_t*>(dp + o_lmptr);
+        B.obs_cam = dp + o_ocam;
+        B.obs_u = reinterpret_cast<double*>(dp + o_ou);
+        B.obs_v = reinterpret_cast<double*>(dp + o_ov);
+        B.obs_d = reinterpret_cast<double*>(dp + o_od);
+        B.obs_W = reinterpret_cast<double*>(dp + o_oW);
+        B.sc_l = reinterpret_cast<double*>(dp + o_scl);
+        B.gl = reinterpret_cast<double*>(dp + o_gl);
+        B.suns = reinterpret_cast<SunBlockData*>(dp + o_suns);
+        B.priors = reinterpret_cast<PriorBlockData*>(dp + o_priors);
+        B.summaries = reinterpret_cast<cslam_summary*>(dp + o_sum);
+        B.logs = reinterpret_cast<double*>(dp + o_logs);
+        B.log_rows = reinterpret_cast<int*>(dp + o_rows);
         CSLAM_CUDA(cudaEventRecord(ev0, stream));
         window_lm_kernel<<<nw, WIN_THREADS, 0, stream>>>(B);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         CSLAM_CUDA(cudaGetLastError());
         CSLAM_CUDA(cudaEventRecord(ev1, stream));
-        std::vector<cslam_summary> sums(nw);
-        std::vector<double> logs(size_t(log_total) * CSLAM_LOG_COLS);
-        std::vector<int> log_rows(nw);
-        std::vector<double> pts_out(pts.size());
-        CSLAM_CUDA(cudaMemcpyAsync(poses.data(), d_poses.p, poses.size() * 8, cudaMemcpyDeviceToHost, stream));
-        CSLAM_CUDA(cudaMemcpyAsync(pts_out.data(), d_pts_best.p, pts.size() * 8, cudaMemcpyDeviceToHost, stream));
-        CSLAM_CUDA(cudaMemcpyAsync(sums.data(), d_sum.p, nw * sizeof(cslam_summary), cudaMemcpyDeviceToHost, stream));
-        CSLAM_CUDA(cudaMemcpyAsync(logs.data(), d_logs.p, logs.size() * 8, cudaMemcpyDeviceToHost, stream));
-        CSLAM_CUDA(cudaMemcpyAsync(log_rows.data(), d_log_rows.p, nw * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaMemcpyAsync(hp + o_poses, dp + o_poses, down_end - o_poses, cudaMemcpyDeviceToHost, stream));
         CSLAM_CUDA(cudaStreamSynchronize(stream));
         float ms = 0;
         CSLAM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        const double* poses_out = reinterpret_cast<const double*>(hp + o_poses);
+        const double* pts_out = reinterpret_cast<const double*>(hp + o_best);
+        const cslam_summary* sums_in = reinterpret_cast<const cslam_summary*>(hp + o_sum);
+        const double* logs = reinterpret_cast<const double*>(hp + o_logs);
+        const int* log_rows = reinterpret_cast<const int*>(hp + o_rows);
+        std::vector<cslam_summary> sums(sums_in, sums_in + nw);
         for (int wi = 0; wi < nw; ++wi) {
             Engine& e = *engines[take[wi]];
             const WinDesc& d = desc[wi];
             for (uint32_t k = 0; k < e.n_poses; ++k)
                 if (cam_free[size_t(d.pose_off) + k] >= 0)
-                    std::memcpy(e.h_poses + 12 * size_t(k), &poses[12 * (size_t(d.pose_off) + k)], 96);
+                    std::memcpy(e.h_poses + 12 * size_t(k), &poses_out[12 * (size_t(d.pose_off) + k)], 96);
             for (int a = 0; a < d.n_lm; ++a)
                 std::memcpy(e.h_points + 3 * size_t(lm_user[wi][a]), &pts_out[3 * (size_t(d.lm_off) + a)], 24);
             e.log.clear();
@@ -1128,15 +1197,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
             e.prof.launches[CSLAM_K_WINDOW] += wi == 0 ? 1 : 0;
             if (summaries) summaries[take[wi]] = sums[wi];
         }
-    } catch (...) {
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
-        cudaStreamDestroy(stream);
-        throw;
     }
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    cudaStreamDestroy(stream);
 }
 
 }  // namespace cslam
