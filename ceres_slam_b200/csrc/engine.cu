@@ -589,6 +589,53 @@ static void parallel_h2d(int device, void* dst, const void* src, size_t bytes) {
     if (!err.empty()) throw CudaError("H2D copy failed: " + err);
 }
 
+// The way back: device -> pageable host memory through the same pinned pieces (DMA into a piece, then a
+// host thread copies it out while the next piece is in flight).
+static void parallel_d2h(int device, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    std::lock_guard<std::mutex> lock(g_h2d.mu);
+    CSLAM_CUDA(cudaSetDevice(device));
+    if (bytes < (size_t(1) << 20) || !g_h2d.ensure(device)) {
+        CSLAM_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+        return;
+    }
+    const size_t n_piece = (bytes + H2DPool::kPiece - 1) / H2DPool::kPiece;
+    const int nt = int(std::min<size_t>(H2DPool::kThreads, n_piece));
+    std::string err;
+    std::mutex mu;
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(device);
+        int b = 0;
+        size_t prev_off = 0, prev_n = 0;
+        bool have_prev = false;
+        for (size_t pc = size_t(t); pc < n_piece && e == cudaSuccess; pc += size_t(nt), b ^= 1) {
+            const size_t off = pc * H2DPool::kPiece, n = std::min(H2DPool::kPiece, bytes - off);
+            e = cudaMemcpyAsync(g_h2d.buf[t][b], static_cast<const char*>(src) + off, n, cudaMemcpyDeviceToHost, g_h2d.st[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(g_h2d.ev[t][b], g_h2d.st[t]);
+            if (have_prev && e == cudaSuccess) {
+                e = cudaEventSynchronize(g_h2d.ev[t][b ^ 1]);
+                if (e == cudaSuccess) std::memcpy(static_cast<char*>(dst) + prev_off, g_h2d.buf[t][b ^ 1], prev_n);
+            }
+            prev_off = off;
+            prev_n = n;
+            have_prev = true;
+        }
+        if (have_prev && e == cudaSuccess) {
+            e = cudaEventSynchronize(g_h2d.ev[t][b ^ 1]);
+            if (e == cudaSuccess) std::memcpy(static_cast<char*>(dst) + prev_off, g_h2d.buf[t][b ^ 1], prev_n);
+        }
+        if (e != cudaSuccess) {
+            std::lock_guard<std::mutex> g(mu);
+            err = cudaGetErrorString(e);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    if (!err.empty()) throw CudaError("D2H copy failed: " + err);
+}
+
 // Structure analysis with the O(n_obs) passes on the device (structure.cu); the host part below is the
 // O(n_landmarks) logic of build_structure(), unchanged, fed from per-landmark arrays instead of the
 // observation lists.  Same layout as the host analysis (CSLAM_VERIFY_STRUCTURE=1 checks the hashes).
@@ -820,6 +867,7 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
             item_j0_h.push_back(it.second);
             item_n_h.push_back(std::min(kItemMax, g_G_h[it.first] - it.second));
         }
+    bt.lap("    runs -> groups (host)");
     // layout rows of every landmark and the groups' camera lists, on the device
     g_cams_h.assign(size_t(cams_cursor), 0);
     d_lm_user.alloc(std::max<size_t>(nl, 1), stream);
@@ -842,6 +890,7 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
         CSLAM_CUDA(cudaMemcpyAsync(g_cams_h.data(), d_gcams.p, g_cams_h.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
         CSLAM_CUDA(cudaStreamSynchronize(stream));
     }
+    bt.lap("    layout kernels + camera lists back");
     // pair -> block tables of the groups (host: binary searches in the pattern)
     g_blk_h.assign(size_t(blk_cursor), -1);
     parallel_chunks(n_groups, 8, [&](int, size_t g0, size_t g1) {
@@ -1301,7 +1350,8 @@ void Engine::download() {
         // best landmarks back into the caller's point order on the device, then one copy straight
         // into the caller's array (points this rank does not own keep the values it uploaded)
         launch_scatter_points(stream, n_lm, d_lm_user.p, d_points_best.p, d_raw_pts.p);
-        CSLAM_CUDA(cudaMemcpyAsync(h_points, d_raw_pts.p, 3 * size_t(n_points) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+        parallel_d2h(opt.device, h_points, d_raw_pts.p, 3 * size_t(n_points) * sizeof(double));
     }
     std::vector<double> nrm, gxh;
     if (ph.active) {
