@@ -168,35 +168,77 @@ __global__ void __launch_bounds__(256)
                    double* __restrict__ gp, double* __restrict__ gl, double* __restrict__ scal) {
     __shared__ double s_red[32];
     double cost = 0.0;
-    for (int j = lm_lo + blockIdx.x * blockDim.x + threadIdx.x; j < lm_hi; j += gridDim.x * blockDim.x) {
-        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
+    const int lane = threadIdx.x & 31;
+    // whole warps walk the landmarks together (a lane past the end idles) so that the camera sums can be
+    // reduced in the warp: inside a group the 32 landmarks of a warp see the same camera at step k, and
+    // one RED per value instead of 32 to the same address is what this pass is bound by
+    const int n_lm = lm_hi - lm_lo;
+    const int n_round = (n_lm + int(gridDim.x * blockDim.x) - 1) / int(gridDim.x * blockDim.x);
+    for (int rd = 0; rd < n_round; ++rd) {
+        const int j = lm_lo + rd * int(gridDim.x * blockDim.x) + int(blockIdx.x * blockDim.x + threadIdx.x);
+        const bool valid = j < lm_hi;
+        const int jj = valid ? j : lm_hi - 1;
+        const double p[3] = {v.points[3ll * jj], v.points[3ll * jj + 1], v.points[3ll * jj + 2]};
         double cl[3] = {0, 0, 0}, g[3] = {0, 0, 0};
-        const uint32_t cnt = v.lm_cnt[j], stride = v.lm_stride[j];
-        uint32_t e = v.lm_base[j];
-        for (uint32_t k = 0; k < cnt; ++k, e += stride) {
-            const uint32_t c = v.obs_cam[e];
-            double r[3], Jc[18], Jp[9];
-            stereo_block<true>(v.cam, v.poses + 12ll * c, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e),
-                               r, Jc, Jp);
-            cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        const uint32_t cnt = valid ? v.lm_cnt[jj] : 0u, stride = v.lm_stride[jj];
+        uint32_t e = v.lm_base[jj];
+        const uint32_t cmax = __reduce_max_sync(0xffffffffu, cnt);
+        for (uint32_t k = 0; k < cmax; ++k, e += stride) {
+            const bool act = k < cnt;
+            int f = -1;
+            double cn[6] = {0, 0, 0, 0, 0, 0}, gc[6] = {0, 0, 0, 0, 0, 0};
+            if (act) {
+                const uint32_t c = v.obs_cam[e];
+                double r[3], Jc[18], Jp[9];
+                stereo_block<true>(v.cam, v.poses + 12ll * c, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], obs_W_ptr(v, e),
+                                   r, Jc, Jp);
+                cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                cl[q] += Jp[q] * Jp[q] + Jp[3 + q] * Jp[3 + q] + Jp[6 + q] * Jp[6 + q];
-                g[q] += Jp[q] * r[0] + Jp[3 + q] * r[1] + Jp[6 + q] * r[2];
+                for (int q = 0; q < 3; ++q) {
+                    cl[q] += Jp[q] * Jp[q] + Jp[3 + q] * Jp[3 + q] + Jp[6 + q] * Jp[6 + q];
+                    g[q] += Jp[q] * r[0] + Jp[3 + q] * r[1] + Jp[6 + q] * r[2];
+                }
+                f = v.cam_free[c];
+                if (f >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        cn[q] = Jc[q] * Jc[q] + Jc[6 + q] * Jc[6 + q] + Jc[12 + q] * Jc[12 + q];
+                        gc[q] = Jc[q] * r[0] + Jc[6 + q] * r[1] + Jc[12 + q] * r[2];
+                    }
+                }
             }
-            const int f = v.cam_free[c];
-            if (f >= 0) {
+            // do all lanes that contribute name the same camera?
+            const unsigned contrib = __ballot_sync(0xffffffffu, f >= 0);
+            if (contrib == 0u) continue;
+            const int leader = __ffs(int(contrib)) - 1;
+            const int f0 = __shfl_sync(0xffffffffu, f, leader);
+            if (__all_sync(0xffffffffu, f < 0 || f == f0)) {
 #pragma unroll
                 for (int q = 0; q < 6; ++q) {
-                    red_add(&cn_p[36ll * f + 7 * q], Jc[q] * Jc[q] + Jc[6 + q] * Jc[6 + q] + Jc[12 + q] * Jc[12 + q]);
-                    red_add(&gp[6ll * f + q], Jc[q] * r[0] + Jc[6 + q] * r[1] + Jc[12 + q] * r[2]);
+                    cn[q] = warp_sum(cn[q]);
+                    gc[q] = warp_sum(gc[q]);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        red_add(&cn_p[36ll * f0 + 7 * q], cn[q]);
+                        red_add(&gp[6ll * f0 + q], gc[q]);
+                    }
+                }
+            } else if (f >= 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    red_add(&cn_p[36ll * f + 7 * q], cn[q]);
+                    red_add(&gp[6ll * f + q], gc[q]);
                 }
             }
         }
+        if (valid) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            cn_l[3ll * j + q] = cl[q];
-            gl[3ll * j + q] = g[q];
+            for (int q = 0; q < 3; ++q) {
+                cn_l[3ll * j + q] = cl[q];
+                gl[3ll * j + q] = g[q];
+            }
         }
     }
     block_atomic_sum(cost, &scal[SC_COST], s_red);
