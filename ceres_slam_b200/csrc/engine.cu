@@ -2,6 +2,7 @@
 // Levenberg-Marquardt loop that drives the kernels (Ceres trust-region semantics, SURVEY.md
 // App. B; the same rules the oracle restates in oracle/problem.hpp::solve).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -551,6 +552,9 @@ struct H2DPool {
     }
 };
 H2DPool g_h2d;
+// staging threads per transfer: all of them for a single process, fewer when several ranks of one job share
+// the host (8 ranks x 8 threads only fight over the cores and the memory bus)
+std::atomic<int> g_stage_threads{H2DPool::kThreads};
 }  // namespace
 
 static void parallel_h2d(int device, void* dst, const void* src, size_t bytes) {
@@ -562,7 +566,7 @@ static void parallel_h2d(int device, void* dst, const void* src, size_t bytes) {
         return;
     }
     const size_t n_piece = (bytes + H2DPool::kPiece - 1) / H2DPool::kPiece;
-    const int nt = int(std::min<size_t>(H2DPool::kThreads, n_piece));
+    const int nt = int(std::min<size_t>(size_t(g_stage_threads.load()), n_piece));
     std::string err;
     std::mutex mu;
     auto work = [&](int t) {
@@ -600,7 +604,7 @@ static void parallel_d2h(int device, void* dst, const void* src, size_t bytes) {
         return;
     }
     const size_t n_piece = (bytes + H2DPool::kPiece - 1) / H2DPool::kPiece;
-    const int nt = int(std::min<size_t>(H2DPool::kThreads, n_piece));
+    const int nt = int(std::min<size_t>(size_t(g_stage_threads.load()), n_piece));
     std::string err;
     std::mutex mu;
     auto work = [&](int t) {
@@ -971,6 +975,7 @@ void Engine::upload() {
     // the device while the measurements follow.  Otherwise (and for the lighting solve, whose setup reads
     // the host-side permutation) the host analyses the structure while a second thread uploads.
     structure_on_device = false;
+    g_stage_threads.store(std::max(2, H2DPool::kThreads / std::max(1, n_ranks)));
     const size_t gpu_min = [] {  // CSLAM_HOST_STRUCTURE=1 keeps the host analysis; ..._MIN moves the size threshold
         if (std::getenv("CSLAM_HOST_STRUCTURE")) return ~size_t(0);
         const char* e = std::getenv("CSLAM_GPU_STRUCTURE_MIN");
