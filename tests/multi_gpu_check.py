@@ -24,10 +24,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.load_product()
-    tr = syn.add_sun(syn.make_track(300, 40, 8, seed=77))
+    tr_shared = syn.add_sun(syn.make_track(300, 40, 8, seed=77))
+    tr_per_obs = syn.add_sun(syn.make_track(200, 30, 6, seed=78, per_obs_W=True))   # a weight per observation
     kw = dict(max_num_iterations=6, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0,
               device=local, sun=True)
-    for linear_solver in (0, 1):
+    # (with CSLAM_GPU_STRUCTURE_MIN=0 the ranks analyse the structure on their GPUs; CSLAM_VERIFY_STRUCTURE=1
+    # checks that layout against the host analysis)
+    for linear_solver, tr in ((0, tr_shared), (1, tr_shared), (0, tr_per_obs)):
         # reference: the whole problem on this rank's GPU
         p1, poses1, points1 = syn.build_problem(tr, backend="b200", linear_solver=linear_solver, **kw)
         s1 = p1.solve()
