@@ -65,7 +65,8 @@ def build_host_driver(name="dataset_vo_b200"):
     host = os.path.join(HERE, "host")
     out = os.path.join(host, name)
     src = os.path.join(host, name + ".cpp")
-    deps = [src, os.path.join(host, "cslam_problem.hpp"), os.path.join(host, "dataset.hpp"), OUT,
+    deps = [src, os.path.join(host, "cslam_problem.hpp"), os.path.join(host, "dataset.hpp"),
+            os.path.join(host, "sun_dataset.hpp"), OUT,
             os.path.join(os.path.dirname(HERE), "include", "cslam_b200.h")]
     if _stale(out, deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + CSRC, "-lcslam_b200",
@@ -73,7 +74,7 @@ def build_host_driver(name="dataset_vo_b200"):
     return out
 
 
-HOST_DRIVERS = ("dataset_vo_b200", "dataset_vo_sun_b200", "dataset_ba_phong_b200")
+HOST_DRIVERS = ("dataset_vo_b200", "dataset_vo_sun_b200", "dataset_ba_phong_b200", "ba_all_b200")
 
 
 def build_oracle():

@@ -125,6 +125,35 @@ class Problem {
 
     // ceres::Solve(options, &problem, &summary)
     void Solve(Summary* summary) {
+        Prepare();
+        cslam_summary s{};
+        check(cslam_solve(handle_, &s), handle_);
+        if (summary) summary->s = s;
+        Finish();
+    }
+
+    // Many independent problems in one call (scripts/ba_all_*.sh run many (trajectory x sun file) jobs; window w
+    // of every job is independent of the others): cslam_solve_batch packs the window-eligible ones into one
+    // launch.  Same effect on every problem as its own Solve().
+    static void SolveBatch(const std::vector<Problem*>& problems, std::vector<Summary>* summaries) {
+        if (problems.empty()) return;
+        std::vector<cslam_problem*> handles;
+        for (Problem* q : problems) {
+            q->Prepare();
+            handles.push_back(q->handle_);
+        }
+        std::vector<cslam_summary> sums(problems.size());
+        check(cslam_solve_batch(handles.data(), int(handles.size()), sums.data()), handles[0]);
+        if (summaries) {
+            summaries->resize(problems.size());
+            for (size_t i = 0; i < problems.size(); ++i) (*summaries)[i].s = sums[i];
+        }
+        for (Problem* q : problems) q->Finish();
+    }
+
+   private:
+    // gather the blocks' current values and state the problem through the C ABI
+    void Prepare() {
         const uint32_t nc = uint32_t(pose_ptr_.size()), np = uint32_t(point_ptr_.size());
         std::vector<double>&poses = poses_, &points = points_;
         poses.assign(12 * size_t(nc), 0.0);
@@ -137,49 +166,48 @@ class Problem {
         check(cslam_problem_create(&p, &options), p);
         handle_ = p;
         const bool lighting = !ph_cam_.empty();
-        {
-            check(cslam_set_camera(p, cam_.fu, cam_.fv, cam_.cu, cam_.cv, cam_.b), p);
-            check(cslam_set_poses(p, nc, poses.data(), constant_.data()), p);
-            check(cslam_set_points(p, np, points.data()), p);
-            // one shared W if all blocks carry the same matrix (dataset_vo.cpp:29-32)
-            bool shared = true;
-            for (size_t i = 1; i < st_cam_.size() && shared; ++i)
-                shared = std::memcmp(&st_W_[0], &st_W_[9 * i], 72) == 0;
-            check(cslam_add_stereo(p, st_cam_.size(), st_cam_.data(), st_pt_.data(), st_uvd_.data(), st_W_.data(), shared ? 0 : 1), p);
-            if (!sun_cam_.empty())
-                check(cslam_add_sun(p, uint32_t(sun_cam_.size()), sun_cam_.data(), sun_obs_.data(), sun_ref_.data(), sun_W_.data(),
-                                    az_, zen_, huber_), p);
-            for (auto& pr : priors_) check(cslam_add_pose_prior(p, pr.cam, pr.Tref, pr.W), p);
-            if (lighting) {
-                if (normal_ptr_.size() != np) throw std::runtime_error("cslam_b200: every vertex needs lighting blocks");
-                normals_.assign(3 * size_t(np), 0.0);
-                for (uint32_t j = 0; j < np; ++j) {
-                    if (!normal_ptr_[j]) throw std::runtime_error("cslam_b200: vertex without a normal block");
-                    std::memcpy(&normals_[3 * size_t(j)], normal_ptr_[j], 24);
-                }
-                mats_.assign(3 * mat_ptr_.size(), 0.0);
-                for (size_t m = 0; m < mat_ptr_.size(); ++m) std::memcpy(&mats_[3 * m], mat_ptr_[m], 24);
-                texs_.assign(tex_ptr_.size(), 0.0);
-                for (size_t t = 0; t < tex_ptr_.size(); ++t) texs_[t] = *tex_ptr_[t];
-                std::memcpy(light_, light_ptr_, 24);
-                std::vector<double> kd_unused(np, 0.0);
-                check(cslam_set_vertices(p, np, normals_.data(), kd_unused.data(), vertex_mat_.data()), p);
-                check(cslam_set_textures(p, uint32_t(texs_.size()), texs_.data(), vertex_tex_.data()), p);
-                check(cslam_set_materials(p, uint32_t(mat_ptr_.size()), mats_.data()), p);
-                check(cslam_set_light(p, light_, directional_ ? 1 : 0), p);
-                check(cslam_add_phong(p, ph_cam_.size(), ph_cam_.data(), ph_vtx_.data(), ph_int_.data(), int_stiffness_,
-                                      ph_nobs_.data(), Wn_), p);
-                check(cslam_set_points_constant(p, points_constant_ ? 1 : 0), p);
-                if (mat_bounded_) check(cslam_set_bounds(p, 0, mat_lo_, mat_hi_), p);
-                if (tex_bounded_) check(cslam_set_bounds(p, 1, &tex_lo_, &tex_hi_), p);
-            }
-            cslam_summary s{};
-            check(cslam_solve(p, &s), p);
-            if (summary) summary->s = s;
-        }
-        for (uint32_t k = 0; k < nc; ++k) std::memcpy(pose_ptr_[k], &poses[12 * size_t(k)], 96);
-        for (uint32_t j = 0; j < np; ++j) std::memcpy(point_ptr_[j], &points[3 * size_t(j)], 24);
+        check(cslam_set_camera(p, cam_.fu, cam_.fv, cam_.cu, cam_.cv, cam_.b), p);
+        check(cslam_set_poses(p, nc, poses.data(), constant_.data()), p);
+        check(cslam_set_points(p, np, points.data()), p);
+        // one shared W if all blocks carry the same matrix (dataset_vo.cpp:29-32)
+        bool shared = true;
+        for (size_t i = 1; i < st_cam_.size() && shared; ++i)
+            shared = std::memcmp(&st_W_[0], &st_W_[9 * i], 72) == 0;
+        check(cslam_add_stereo(p, st_cam_.size(), st_cam_.data(), st_pt_.data(), st_uvd_.data(), st_W_.data(), shared ? 0 : 1), p);
+        if (!sun_cam_.empty())
+            check(cslam_add_sun(p, uint32_t(sun_cam_.size()), sun_cam_.data(), sun_obs_.data(), sun_ref_.data(), sun_W_.data(),
+                                az_, zen_, huber_), p);
+        for (auto& pr : priors_) check(cslam_add_pose_prior(p, pr.cam, pr.Tref, pr.W), p);
         if (lighting) {
+            if (normal_ptr_.size() != np) throw std::runtime_error("cslam_b200: every vertex needs lighting blocks");
+            normals_.assign(3 * size_t(np), 0.0);
+            for (uint32_t j = 0; j < np; ++j) {
+                if (!normal_ptr_[j]) throw std::runtime_error("cslam_b200: vertex without a normal block");
+                std::memcpy(&normals_[3 * size_t(j)], normal_ptr_[j], 24);
+            }
+            mats_.assign(3 * mat_ptr_.size(), 0.0);
+            for (size_t m = 0; m < mat_ptr_.size(); ++m) std::memcpy(&mats_[3 * m], mat_ptr_[m], 24);
+            texs_.assign(tex_ptr_.size(), 0.0);
+            for (size_t t = 0; t < tex_ptr_.size(); ++t) texs_[t] = *tex_ptr_[t];
+            std::memcpy(light_, light_ptr_, 24);
+            std::vector<double> kd_unused(np, 0.0);
+            check(cslam_set_vertices(p, np, normals_.data(), kd_unused.data(), vertex_mat_.data()), p);
+            check(cslam_set_textures(p, uint32_t(texs_.size()), texs_.data(), vertex_tex_.data()), p);
+            check(cslam_set_materials(p, uint32_t(mat_ptr_.size()), mats_.data()), p);
+            check(cslam_set_light(p, light_, directional_ ? 1 : 0), p);
+            check(cslam_add_phong(p, ph_cam_.size(), ph_cam_.data(), ph_vtx_.data(), ph_int_.data(), int_stiffness_,
+                                  ph_nobs_.data(), Wn_), p);
+            check(cslam_set_points_constant(p, points_constant_ ? 1 : 0), p);
+            if (mat_bounded_) check(cslam_set_bounds(p, 0, mat_lo_, mat_hi_), p);
+            if (tex_bounded_) check(cslam_set_bounds(p, 1, &tex_lo_, &tex_hi_), p);
+        }
+    }
+    // the library wrote the solution into poses_ / points_ / ...: back into the caller's blocks, like Ceres
+    void Finish() {
+        const uint32_t nc = uint32_t(pose_ptr_.size()), np = uint32_t(point_ptr_.size());
+        for (uint32_t k = 0; k < nc; ++k) std::memcpy(pose_ptr_[k], &poses_[12 * size_t(k)], 96);
+        for (uint32_t j = 0; j < np; ++j) std::memcpy(point_ptr_[j], &points_[3 * size_t(j)], 24);
+        if (!ph_cam_.empty()) {
             for (uint32_t j = 0; j < np; ++j) std::memcpy(normal_ptr_[j], &normals_[3 * size_t(j)], 24);
             for (size_t m = 0; m < mat_ptr_.size(); ++m) std::memcpy(mat_ptr_[m], &mats_[3 * m], 24);
             for (size_t t = 0; t < tex_ptr_.size(); ++t) *tex_ptr_[t] = texs_[t];
@@ -187,7 +215,6 @@ class Problem {
         }
     }
 
-   private:
     struct Cam {
         double fu = 1, fv = 1, cu = 0, cv = 0, b = 1;
     } cam_;

@@ -594,6 +594,36 @@ def test_cpp_driver_dataset_vo_sun(product, tmp_path):
     assert np.abs(results["dogleg"] - results["lm"]).max() < 1e-3
 
 
+def test_cpp_batch_runner_ba_all(product, tmp_path):
+    """ba_all_b200 (scripts/ba_all_*.sh: many (trajectory x sun file) jobs): the jobs advance in lock-step and
+    window w of every job goes through ONE cslam_solve_batch call; each job must come out exactly as its own
+    dataset_vo_sun_b200 run does."""
+    import os
+    jobs, ref = [], {}
+    for n, (seed, n_poses) in enumerate(((41, 14), (42, 12), (43, 14))):
+        d = os.path.join(tmp_path, f"job{n}")
+        os.makedirs(d)
+        tr = syn.add_sun(_steady_track(n_poses, seed=seed, per_obs_W=True), sigma_deg=1.0)
+        paths = [os.path.join(d, f) for f in ("track.csv", "sun_ref.csv", "sun_obs.csv")]
+        syn.write_sun_csvs(tr, *paths)
+        flags = ["--window", "2", "--huber-param", "1.0", "--max-iters", "100", "--strategy", "lm"]
+        _run_driver("dataset_vo_sun_b200", paths + flags, d)
+        ref[n] = (_poses_csv(os.path.join(d, "track_poses.csv"), n_poses), _poses_csv(os.path.join(d, "track_obs_poses.csv"), n_poses))
+        os.remove(os.path.join(d, "track_poses.csv"))
+        os.remove(os.path.join(d, "track_obs_poses.csv"))
+        jobs.append((paths, n_poses, d))
+    jf = os.path.join(tmp_path, "jobs.txt")
+    with open(jf, "w") as f:
+        for paths, _, _ in jobs:
+            f.write(" ".join(paths) + "\n")
+    text = _run_driver("ba_all_b200", [jf, "--window", "2", "--huber-param", "1.0", "--max-iters", "100", "--strategy", "lm"], tmp_path)
+    assert text.count("cslam_b200 Report") == 2 * (13 + 11 + 13), text
+    for n, (paths, n_poses, d) in enumerate(jobs):
+        Tv = _poses_csv(os.path.join(d, "track_poses.csv"), n_poses)
+        Ts = _poses_csv(os.path.join(d, "track_obs_poses.csv"), n_poses)
+        assert np.abs(Tv - ref[n][0]).max() < 1e-9 and np.abs(Ts - ref[n][1]).max() < 1e-9
+
+
 def test_cpp_driver_dataset_ba_phong(product, tmp_path):
     """dataset_ba_phong restated: RANSAC front end (positions, normals, materials of the vertices),
     then the joint lighting solve from the reference's own start (materials (0, 0, 1), textures the
