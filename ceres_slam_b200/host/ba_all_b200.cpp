@@ -28,20 +28,36 @@ static void run_pass_all(std::vector<Job>& jobs, unsigned window, bool use_sun, 
         std::vector<std::unique_ptr<Problem>> problems;
         std::vector<Problem*> batch;
         std::vector<Job*> owner;
-        for (auto& j : jobs) {
-            SunDataset& d = j.d;
-            if (k2 > d.num_states) continue;
-            const InitialGuessStats st = compute_initial_guess(d.obs, d.intr, d.num_states, k1, k2, 4.0, true, d.poses, d.points,
-                                                               d.initialized, [](unsigned, unsigned, const double*, unsigned) {});
-            if (st.ok) {
-                problems.emplace_back(new Problem);
-                buildWindow(d, k1, k2, use_sun, huber, az, zen, max_iters, *problems.back());
-                batch.push_back(problems.back().get());
-                owner.push_back(&j);
-            } else {
-                std::cerr << "WARNING: Initial guess failed. Copying previous pose and covariance." << std::endl;
-                std::memcpy(&d.poses[12 * size_t(k2 - 1)], &d.poses[12 * size_t(k1)], 96);
-                std::memcpy(&d.pose_covars[36 * size_t(k2 - 1)], &d.pose_covars[36 * size_t(k1)], 288);
+        // the RANSAC front end of every job's window in one cslam_ransac_align call per set of intrinsics
+        std::vector<Job*> live;
+        for (auto& j : jobs)
+            if (k2 <= j.d.num_states) live.push_back(&j);
+        std::vector<char> done(live.size(), 0);
+        for (size_t a = 0; a < live.size(); ++a) {
+            if (done[a]) continue;
+            std::vector<InitialGuessJob> ig;
+            std::vector<size_t> who;
+            for (size_t b = a; b < live.size(); ++b)
+                if (!done[b] && std::memcmp(live[b]->d.intr, live[a]->d.intr, sizeof(live[a]->d.intr)) == 0) {
+                    SunDataset& d = live[b]->d;
+                    ig.push_back(InitialGuessJob{&d.obs, d.num_states, k1, k2, &d.poses, &d.points, &d.initialized, {}});
+                    who.push_back(b);
+                    done[b] = 1;
+                }
+            compute_initial_guess_batch(ig, live[a]->d.intr, 4.0, true);
+            for (size_t i = 0; i < ig.size(); ++i) {
+                Job& j = *live[who[i]];
+                SunDataset& d = j.d;
+                if (ig[i].stats.ok) {
+                    problems.emplace_back(new Problem);
+                    buildWindow(d, k1, k2, use_sun, huber, az, zen, max_iters, *problems.back());
+                    batch.push_back(problems.back().get());
+                    owner.push_back(&j);
+                } else {
+                    std::cerr << "WARNING: Initial guess failed. Copying previous pose and covariance." << std::endl;
+                    std::memcpy(&d.poses[12 * size_t(k2 - 1)], &d.poses[12 * size_t(k1)], 96);
+                    std::memcpy(&d.pose_covars[36 * size_t(k2 - 1)], &d.pose_covars[36 * size_t(k1)], 288);
+                }
             }
         }
         std::vector<Summary> sums;

@@ -118,21 +118,27 @@ struct InitialGuessStats {
 // `require_three_inliers`: the sun variant gives up (returns ok = false) when a pair has fewer
 // than 3 inliers (dataset_problem_sun.cpp:323-326); the others carry on.
 // All pose pairs of the call go to the GPU as one batch; the chaining is sequential afterwards.
-template <class OnInit>
-inline InitialGuessStats compute_initial_guess(const ObservationTable& obs, const double intr[5], unsigned num_states,
-                                               unsigned k1, unsigned k2, double thresh, bool require_three_inliers,
-                                               std::vector<double>& poses, std::vector<double>& points,
-                                               std::vector<char>& initialized, OnInit on_init, int rng_variant = 0) {
-    InitialGuessStats st;
+// The three stages are separate functions so that a batch runner can put the pairs of MANY jobs into one
+// cslam_ransac_align call (ba_all_b200): matches -> alignment (GPU) -> chaining.
+struct InitialGuessPairs {
+    unsigned k1 = 0, k2 = 0, n_pairs = 0;
+    std::vector<uint32_t> offsets;   // n_pairs + 1, in correspondences
+    std::vector<double> p0, p1;      // triangulated points of the two states, 3 per correspondence
+    std::vector<unsigned> idx0, jid; // per correspondence: observation index in state k-1, point id
+};
+
+inline InitialGuessPairs initial_guess_pairs(const ObservationTable& obs, const double intr[5], unsigned num_states, unsigned k1,
+                                             unsigned k2) {
+    InitialGuessPairs q;
     if (k1 >= k2) {
         k1 = 0;
         k2 = num_states;
     }
-    if (k2 - k1 < 2) return st;
-    const unsigned n_pairs = k2 - k1 - 1;
-    std::vector<uint32_t> offsets(n_pairs + 1, 0);
-    std::vector<double> p0, p1;
-    std::vector<unsigned> idx0, jid;  // per correspondence: observation index in state k-1, point id
+    q.k1 = k1;
+    q.k2 = k2;
+    if (k2 - k1 < 2) return q;
+    q.n_pairs = k2 - k1 - 1;
+    q.offsets.assign(q.n_pairs + 1, 0);
     for (unsigned k = k1 + 1; k < k2; ++k) {
         // reciprocal matches, each list in its own order, paired by position (:207-229)
         std::vector<unsigned> a = obs.state_obs[k - 1], b = obs.state_obs[k];
@@ -148,27 +154,26 @@ inline InitialGuessStats compute_initial_guess(const ObservationTable& obs, cons
         for (size_t i = 0; i < n; ++i) {
             double x[3];
             triangulate(intr, &obs.uvd[3 * size_t(ka[i])], x);
-            p0.insert(p0.end(), x, x + 3);
+            q.p0.insert(q.p0.end(), x, x + 3);
             triangulate(intr, &obs.uvd[3 * size_t(kb[i])], x);
-            p1.insert(p1.end(), x, x + 3);
-            idx0.push_back(ka[i]);
-            jid.push_back(obs.j[ka[i]]);
+            q.p1.insert(q.p1.end(), x, x + 3);
+            q.idx0.push_back(ka[i]);
+            q.jid.push_back(obs.j[ka[i]]);
         }
-        offsets[k - k1] = uint32_t(p0.size() / 3);
+        q.offsets[k - k1] = uint32_t(q.p0.size() / 3);
     }
-    if (p0.empty()) {
-        p0.assign(3, 0.0);
-        p1.assign(3, 0.0);
-    }
-    std::vector<double> T(12 * size_t(n_pairs));
-    std::vector<uint8_t> inl(std::max<size_t>(offsets[n_pairs], 1));
-    std::vector<uint32_t> cnt(n_pairs);
-    if (cslam_ransac_align(0, n_pairs, offsets.data(), p0.data(), p1.data(), intr, 400, thresh, rng_variant, T.data(),
-                           inl.data(), cnt.data()) != CSLAM_OK)
-        throw std::runtime_error("cslam_ransac_align failed (no CUDA device?)");
-    st.pairs = n_pairs;
-    for (unsigned k = k1 + 1; k < k2; ++k) {
-        const unsigned p = k - k1 - 1;
+    return q;
+}
+
+// T: 12 per pair, inl: one flag per correspondence, cnt: inliers per pair — this job's slices of the alignment's output
+template <class OnInit>
+inline InitialGuessStats initial_guess_chain(const InitialGuessPairs& q, const double* T, const uint8_t* inl, const uint32_t* cnt,
+                                             bool require_three_inliers, std::vector<double>& poses, std::vector<double>& points,
+                                             std::vector<char>& initialized, OnInit on_init) {
+    InitialGuessStats st;
+    st.pairs = q.n_pairs;
+    for (unsigned k = q.k1 + 1; k < q.k2; ++k) {
+        const unsigned p = k - q.k1 - 1;
         if (require_three_inliers && cnt[p] < 3) {
             st.ok = false;
             st.failed_pair = k;
@@ -176,14 +181,79 @@ inline InitialGuessStats compute_initial_guess(const ObservationTable& obs, cons
         }
         const double* Pm1 = &poses[12 * size_t(k - 1)];
         pose_mul(&T[12 * size_t(p)], Pm1, &poses[12 * size_t(k)]);  // poses[k] = T_k_km1 * poses[k-1]
-        for (uint32_t c = offsets[p]; c < offsets[p + 1]; ++c) {
-            if (!inl[c] || initialized[jid[c]]) continue;
-            pose_inverse_apply(Pm1, &p0[3 * size_t(c)], false, &points[3 * size_t(jid[c])]);
-            initialized[jid[c]] = 1;
-            on_init(idx0[c], jid[c], Pm1, c - offsets[p]);
+        for (uint32_t c = q.offsets[p]; c < q.offsets[p + 1]; ++c) {
+            if (!inl[c] || initialized[q.jid[c]]) continue;
+            pose_inverse_apply(Pm1, &q.p0[3 * size_t(c)], false, &points[3 * size_t(q.jid[c])]);
+            initialized[q.jid[c]] = 1;
+            on_init(q.idx0[c], q.jid[c], Pm1, c - q.offsets[p]);
         }
     }
     return st;
+}
+
+template <class OnInit>
+inline InitialGuessStats compute_initial_guess(const ObservationTable& obs, const double intr[5], unsigned num_states,
+                                               unsigned k1, unsigned k2, double thresh, bool require_three_inliers,
+                                               std::vector<double>& poses, std::vector<double>& points,
+                                               std::vector<char>& initialized, OnInit on_init, int rng_variant = 0) {
+    InitialGuessPairs q = initial_guess_pairs(obs, intr, num_states, k1, k2);
+    if (q.n_pairs == 0) return InitialGuessStats();
+    if (q.p0.empty()) {
+        q.p0.assign(3, 0.0);
+        q.p1.assign(3, 0.0);
+    }
+    std::vector<double> T(12 * size_t(q.n_pairs));
+    std::vector<uint8_t> inl(std::max<size_t>(q.offsets[q.n_pairs], 1));
+    std::vector<uint32_t> cnt(q.n_pairs);
+    if (cslam_ransac_align(0, q.n_pairs, q.offsets.data(), q.p0.data(), q.p1.data(), intr, 400, thresh, rng_variant, T.data(),
+                           inl.data(), cnt.data()) != CSLAM_OK)
+        throw std::runtime_error("cslam_ransac_align failed (no CUDA device?)");
+    return initial_guess_chain(q, T.data(), inl.data(), cnt.data(), require_three_inliers, poses, points, initialized, on_init);
+}
+
+// The same for several independent jobs that share the intrinsics: the pairs of all of them in ONE alignment call.
+struct InitialGuessJob {
+    const ObservationTable* obs;
+    unsigned num_states, k1, k2;
+    std::vector<double>* poses;
+    std::vector<double>* points;
+    std::vector<char>* initialized;
+    InitialGuessStats stats;
+};
+inline void compute_initial_guess_batch(std::vector<InitialGuessJob>& jobs, const double intr[5], double thresh,
+                                        bool require_three_inliers, int rng_variant = 0) {
+    std::vector<InitialGuessPairs> qs;
+    std::vector<uint32_t> offsets(1, 0);
+    std::vector<double> p0, p1;
+    for (auto& j : jobs) {
+        qs.push_back(initial_guess_pairs(*j.obs, intr, j.num_states, j.k1, j.k2));
+        const InitialGuessPairs& q = qs.back();
+        const uint32_t base = uint32_t(p0.size() / 3);
+        for (unsigned p = 0; p < q.n_pairs; ++p) offsets.push_back(base + q.offsets[p + 1]);
+        p0.insert(p0.end(), q.p0.begin(), q.p0.end());
+        p1.insert(p1.end(), q.p1.begin(), q.p1.end());
+    }
+    const uint32_t n_pairs = uint32_t(offsets.size() - 1);
+    if (n_pairs == 0) return;
+    if (p0.empty()) {
+        p0.assign(3, 0.0);
+        p1.assign(3, 0.0);
+    }
+    std::vector<double> T(12 * size_t(n_pairs));
+    std::vector<uint8_t> inl(std::max<size_t>(offsets[n_pairs], 1));
+    std::vector<uint32_t> cnt(n_pairs);
+    if (cslam_ransac_align(0, n_pairs, offsets.data(), p0.data(), p1.data(), intr, 400, thresh, rng_variant, T.data(), inl.data(),
+                           cnt.data()) != CSLAM_OK)
+        throw std::runtime_error("cslam_ransac_align failed (no CUDA device?)");
+    uint32_t pair0 = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const InitialGuessPairs& q = qs[i];
+        if (q.n_pairs == 0) continue;
+        jobs[i].stats = initial_guess_chain(q, &T[12 * size_t(pair0)], &inl[offsets[pair0]], &cnt[pair0], require_three_inliers,
+                                            *jobs[i].poses, *jobs[i].points, *jobs[i].initialized,
+                                            [](unsigned, unsigned, const double*, unsigned) {});
+        pair0 += q.n_pairs;
+    }
 }
 
 inline void write_poses_csv(const std::string& path, const std::vector<double>& poses, unsigned num_states) {
