@@ -948,23 +948,24 @@ __global__ void __launch_bounds__(128)
 __global__ void gradnorm_kernel(DevView v, int lm_lo, int lm_hi, const double* __restrict__ gp_s,
                                 const double* __restrict__ gl_s, double* __restrict__ scal, int count_cams) {
     __shared__ double s_red[32];
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // grid-stride: a few CTAs per SM, so that the two reductions end in ~1 k atomics instead of one per 256 elements
+    const long long n = (long long)v.n_cams + (lm_hi - lm_lo);
     double m = 0, xn = 0;
-    if (i < v.n_cams) {
-        const int f = v.cam_free[i];
-        if (f >= 0 && count_cams) {
-            const double* x = v.poses + 12ll * i;
-            double eps[6], out[12];
-            for (int k = 0; k < 6; ++k) eps[k] = -gp_s[6ll * f + k] / v.sc_p[6ll * f + k];
-            se3_plus(x, eps, out);
-            for (int k = 0; k < 12; ++k) {
-                m = fmax(m, fabs(x[k] - out[k]));
-                xn += x[k] * x[k];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (i < v.n_cams) {
+            const int f = v.cam_free[i];
+            if (f >= 0 && count_cams) {
+                const double* x = v.poses + 12ll * i;
+                double eps[6], out[12];
+                for (int k = 0; k < 6; ++k) eps[k] = -gp_s[6ll * f + k] / v.sc_p[6ll * f + k];
+                se3_plus(x, eps, out);
+                for (int k = 0; k < 12; ++k) {
+                    m = fmax(m, fabs(x[k] - out[k]));
+                    xn += x[k] * x[k];
+                }
             }
-        }
-    } else {
-        const long long j = lm_lo + (i - v.n_cams);
-        if (j < lm_hi) {
+        } else {
+            const long long j = lm_lo + (i - v.n_cams);
             for (int q = 0; q < 3; ++q) {
                 const double x = v.points[3 * j + q];
                 const double g = gl_s[3 * j + q] / v.sc_l[3 * j + q];
@@ -1234,7 +1235,8 @@ void launch_gradnorm(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, con
                      const double* gl_scaled, double* scal, int count_cams) {
     const long long n = (long long)v.n_cams + (lm_hi - lm_lo);
     if (n <= 0) return;
-    gradnorm_kernel<<<int((n + 255) / 256), 256, 0, s>>>(v, lm_lo, lm_hi, gp_scaled, gl_scaled, scal, count_cams);
+    gradnorm_kernel<<<int(std::min<long long>((n + 255) / 256, 8 * kSMs)), 256, 0, s>>>(v, lm_lo, lm_hi, gp_scaled, gl_scaled, scal,
+                                                                                         count_cams);
     CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }
