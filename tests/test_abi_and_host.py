@@ -136,3 +136,26 @@ def test_options_struct_layout_matches_the_header():
         assert opt.line_search_sufficient_function_decrease == 1e-4
         assert opt.max_num_iterations == 1000 and opt.dogleg_type == 1 and opt.trust_region_strategy == 0
         assert opt.initial_trust_region_radius == 1e4
+
+
+def test_host_mirror_and_drivers_compile_and_refuse_without_a_gpu(lib, tmp_path):
+    """The C++ host mirror (host/cslam_problem.hpp), the restated drivers and the ba_all batch runner build against
+    the C ABI with g++ alone; without a CUDA device a driver must fail loudly (no CPU fallback), not produce output."""
+    import os
+    import subprocess
+    from ceres_slam_b200 import build as b
+    from ceres_slam_b200 import synthetic as syn
+    exes = {n: b.build_host_driver(n) for n in b.HOST_DRIVERS}
+    assert set(exes) == {"dataset_vo_b200", "dataset_vo_sun_b200", "dataset_ba_phong_b200", "ba_all_b200"}
+    for exe in exes.values():
+        assert os.access(exe, os.X_OK)
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert out.returncode != 0 and "usage" in out.stderr      # no arguments: usage, like the reference's drivers
+    import torch
+    if not torch.cuda.is_available():
+        tr = syn.make_track(12, 8, 5, seed=3)
+        csv = os.path.join(tmp_path, "track.csv")
+        syn.write_track_csv(tr, csv)
+        out = subprocess.run([exes["dataset_vo_b200"], csv, "--window", "2", "--init", "constant"], capture_output=True, text=True,
+                             timeout=120, cwd=tmp_path)
+        assert out.returncode != 0 and not os.path.exists(os.path.join(tmp_path, "track_poses.csv")), out.stdout + out.stderr
