@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from ceres_slam_b200 import synthetic as syn  # noqa: E402
+from oracle import pybinding as orc
 
 METRIC = "BA LM iterations/s (full-batch stereo BA, C5: 20k poses x 2M landmarks x 20M obs)"
 LM_EXACT = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0, linear_solver=0)
@@ -116,11 +117,11 @@ def cpu_oracle_run(steps, warmup, threads, sample_scale):
     # warm-up + timed in separate solves from the same start (the oracle has no resume entry)
     t_w = 0.0
     if warmup > 0:
-        p, _, _ = syn.build_problem(tr, backend="oracle", max_num_iterations=warmup, **opts)
+        p, _, _ = orc.build_problem(tr, max_num_iterations=warmup, **opts)
         t0 = time.perf_counter()
         p.solve()
         t_w = time.perf_counter() - t0
-    p, _, _ = syn.build_problem(tr, backend="oracle", max_num_iterations=warmup + steps, **opts)
+    p, _, _ = orc.build_problem(tr, max_num_iterations=warmup + steps, **opts)
     t0 = time.perf_counter()
     s = p.solve()
     t_all = time.perf_counter() - t0
@@ -185,7 +186,7 @@ def bench_c4_windows(lib, n_windows=256, iters=6, reps=5):
     kw = dict(max_num_iterations=iters, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
     best_wall, dev_ms, n_it, n_obs = None, None, 0, sum(int(w["obs_cam"].size) for w in wins)
     for rep in range(reps + 1):
-        probs = [syn.build_problem(w, backend="b200", **kw)[0] for w in wins]
+        probs = [syn.build_problem(w, **kw)[0] for w in wins]
         t0 = time.perf_counter()
         sums = solve_batch(probs)
         wall = time.perf_counter() - t0
@@ -207,7 +208,7 @@ def bench_phong_blocks(peak_gbs, reps=10):
     one intensity block + one normal block per observation, residuals and Jacobians materialised
     (the K1-style throughput figure for the Phong residuals)."""
     tr = syn.add_phong(syn.make_track(2000, 100, 10, seed=42))
-    p, _ = syn.build_phong_problem(tr, backend="b200")
+    p, _ = syn.build_phong_problem(tr)
     n = int(tr["obs_cam"].size)
     ms = p.time_phong(reps)
     p.close()
@@ -226,7 +227,7 @@ def bench_c3_phong_solve(iters=6, cpu=True):
     fixed = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
     tr = syn.add_phong(syn.make_track(2000, 100, 10, seed=42), shared_textures=True)
     n = int(tr["obs_cam"].size)
-    p, _ = syn.build_phong_problem(tr, backend="b200", bounds=True, max_num_iterations=10 ** 6, profile_kernels=1, **fixed)
+    p, _ = syn.build_phong_problem(tr, bounds=True, max_num_iterations=10 ** 6, profile_kernels=1, **fixed)
     t0 = time.perf_counter()
     p.upload()
     up = time.perf_counter() - t0
@@ -247,7 +248,7 @@ def bench_c3_phong_solve(iters=6, cpu=True):
     if cpu:
         trs = syn.add_phong(syn.make_track(60, 100, 10, seed=42), shared_textures=True)
         threads = os.cpu_count() or 1
-        po, _ = syn.build_phong_problem(trs, backend="oracle", bounds=True, max_num_iterations=3, num_threads=threads, **fixed)
+        po, _ = orc.build_phong_problem(trs, bounds=True, max_num_iterations=3, num_threads=threads, **fixed)
         t0 = time.perf_counter()
         so = po.solve()
         dt = (time.perf_counter() - t0) / max(1, so.num_iterations)
@@ -273,11 +274,11 @@ def bench_ransac_front_end(n_poses=1000):
         kp, kc = ig.match_pair(pt[rng[k - 1]:rng[k]], pt[rng[k]:rng[k + 1]])
         p0.append(ig.triangulate(tr["cam"], tr["uvd"][rng[k - 1]:rng[k]][kp]))
         p1.append(ig.triangulate(tr["cam"], tr["uvd"][rng[k]:rng[k + 1]][kc]))
-    ig.ransac_align(p0[:8], p1[:8], tr["cam"], "b200")          # context / module warm-up
+    ig.ransac_align(p0[:8], p1[:8], tr["cam"])          # context / module warm-up
     best = 1e30
     for _ in range(3):
         t0 = time.perf_counter()
-        T, inl, cnt = ig.ransac_align(p0, p1, tr["cam"], "b200")
+        T, inl, cnt = ig.ransac_align(p0, p1, tr["cam"])
         best = min(best, time.perf_counter() - t0)
     n_pts = int(sum(p.shape[0] for p in p0))
     hyp_pts = 400.0 * n_pts
@@ -353,7 +354,7 @@ def main():
     gen_s = time.perf_counter() - t0
 
     def make_problem(**extra):
-        p, poses, points = syn.build_problem(tr, backend="b200", device=local, **dict(LM_OPTS, **extra))
+        p, poses, points = syn.build_problem(tr, device=local, **dict(LM_OPTS, **extra))
         if world > 1:
             uid = torch.zeros(128, dtype=torch.uint8)
             if rank == 0:

@@ -77,9 +77,5 @@ def build_host_driver(name="dataset_vo_b200"):
 HOST_DRIVERS = ("dataset_vo_b200", "dataset_vo_sun_b200", "dataset_ba_phong_b200", "ba_all_b200")
 
 
-def build_oracle():
-    subprocess.check_call(["make", "-C", os.path.join(os.path.dirname(HERE), "oracle")])
-
-
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -1,9 +1,9 @@
 """ctypes binding of the C ABI in include/cslam_b200.h.
 
-The same signatures exist twice: `libcslam_b200.so` (the product: hand-written sm_100a CUDA
-kernels behind the C ABI) and `oracle/_build/liboracle.so` (prefix `cslam_oracle_`, the CPU
-restatement used only as the checker and CPU baseline).  `load_product()` fails loudly when the
-CUDA library has not been built — there is no CPU fallback.
+`load_product()` binds `libcslam_b200.so` — hand-written sm_100a CUDA kernels behind the C ABI — and
+fails loudly when it has not been built: there is no CPU fallback and nothing in this package
+knows of any other implementation.  (`PROBLEM_API` is the signature table of the problem-building
+entry points; the test-side checker under `oracle/` binds its own library with the same table.)
 """
 import ctypes as C
 import os
@@ -12,7 +12,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT_SO = os.path.join(ROOT, "ceres_slam_b200", "csrc", "libcslam_b200.so")
-ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 
 LOG_COLS = 10
 LOG_NAMES = ("iteration", "cost", "cost_change", "gradient_max_norm", "step_norm",
@@ -96,8 +95,8 @@ _u8p = C.POINTER(C.c_uint8)
 _ip = C.POINTER(C.c_int)
 _h = C.c_void_p
 
-# name -> (restype, argtypes); shared by both libraries
-_COMMON = {
+# name -> (restype, argtypes): the problem-building entry points of include/cslam_b200.h
+PROBLEM_API = {
     "options_init": (None, [C.POINTER(Options)]),
     "problem_create": (C.c_int, [C.POINTER(_h), C.POINTER(Options)]),
     "problem_destroy": (None, [_h]),
@@ -121,7 +120,7 @@ _COMMON = {
     "add_phong": (C.c_int, [_h, C.c_uint64, _u32p, _u32p, _dp, C.c_double, _dp, _dp]),
 }
 _RANSAC_SIG = (C.c_int, [C.c_int, C.c_uint32, _u32p, _dp, _dp, _dp, C.c_uint32, C.c_double, C.c_int, _dp, _u8p, _u32p])
-_COMMON["ransac_align"] = _RANSAC_SIG
+PROBLEM_API["ransac_align"] = _RANSAC_SIG
 _PRODUCT_ONLY = {
     "ransac_triples": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, _u32p]),
     "evaluate_phong": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp, _dp]),
@@ -146,31 +145,7 @@ _PRODUCT_ONLY = {
     "comm_unique_id": (C.c_int, [_u8p]),
     "attach_comm": (C.c_int, [_h, C.c_int, C.c_int, _u8p]),
 }
-_ORACLE_ONLY = {
-    "poly_root_real_parts": (C.c_int, [_dp, C.c_int, _dp]),
-    "dogleg_boundary_minimum": (C.c_int, [_dp, _dp, C.c_double, _dp]),
-    "ransac_draws": (None, [C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p]),
-    "kabsch": (None, [C.c_uint32, _dp, _dp, _dp]),
-    "so3_exp": (None, [_dp, _dp]),
-    "so3_log": (None, [_dp, _dp]),
-    "se3_exp": (None, [_dp, _dp]),
-    "se3_log": (None, [_dp, _dp]),
-    "se3_mul": (None, [_dp, _dp, _dp]),
-    "se3_inverse": (None, [_dp, _dp]),
-    "se3_adjoint": (None, [_dp, _dp]),
-    "se3_transform": (None, [_dp, _dp, C.c_int, _dp]),
-    "se3_plus": (None, [_dp, _dp, _dp]),
-    "se3_plus_jacobian": (None, [_dp, _dp]),
-    "unit_plus": (None, [_dp, _dp, _dp]),
-    "unit_plus_jacobian": (None, [_dp, _dp]),
-    "camera_project": (None, [_dp, _dp, _dp]),
-    "camera_triangulate": (None, [_dp, _dp, _dp]),
-    "point_light_shade": (C.c_double, [_dp, _dp, _dp, _dp, C.c_double, _dp]),
-    "intensity_block": (C.c_int, [_dp] * 6 + [C.c_double, C.c_double, C.c_int] + [_dp] * 7),
-    "normal_block": (C.c_int, [_dp] * 7),
-}
-
-PRODUCT_SYMBOLS = sorted("cslam_" + n for n in list(_COMMON) + list(_PRODUCT_ONLY))
+PRODUCT_SYMBOLS = sorted("cslam_" + n for n in list(PROBLEM_API) + list(_PRODUCT_ONLY))
 
 
 class Lib:
@@ -197,15 +172,8 @@ _cache = {}
 
 def load_product():
     if "product" not in _cache:
-        _cache["product"] = Lib(PRODUCT_SO, "cslam_", (_COMMON, _PRODUCT_ONLY))
+        _cache["product"] = Lib(PRODUCT_SO, "cslam_", (PROBLEM_API, _PRODUCT_ONLY))
     return _cache["product"]
-
-
-def load_oracle():
-    """CPU restatement — test infrastructure only."""
-    if "oracle" not in _cache:
-        _cache["oracle"] = Lib(ORACLE_SO, "cslam_oracle_", (_COMMON, _ORACLE_ONLY))
-    return _cache["oracle"]
 
 
 def dptr(a):

@@ -6,7 +6,7 @@ triangulate both clouds, run the 3-point RANSAC (400 hypotheses, threshold 4), c
 `poses[k] = T_k_km1 * poses[k-1]` and initialise every inlier point that has no guess yet from the
 first cloud.  The RANSAC of a pair only reads observations, so all pairs of a call go to the GPU as
 ONE launch; the chaining and the point initialisation are then a cheap sequential pass on the host
-in the reference's order.  `backend="oracle"` runs the CPU restatement (tests only).
+in the reference's order.
 """
 import ctypes as C
 
@@ -38,9 +38,10 @@ def match_pair(ids_prev, ids_cur):
     return keep_prev, keep_cur
 
 
-def ransac_align(pairs0, pairs1, cam, backend="b200", num_iters=400, thresh=4.0, rng_variant=0, device=0):
-    """Batched compute_transformation_and_inliers.  pairs0/pairs1: lists of (n_i, 3) arrays."""
-    lib = capi.load_product() if backend == "b200" else capi.load_oracle()
+def ransac_align(pairs0, pairs1, cam, num_iters=400, thresh=4.0, rng_variant=0, device=0, entry=None):
+    """Batched compute_transformation_and_inliers.  pairs0/pairs1: lists of (n_i, 3) arrays.
+    `entry` is the C entry point to call (default: the library's `cslam_ransac_align`)."""
+    entry = entry or capi.load_product().ransac_align
     n_pairs = len(pairs0)
     sizes = np.array([p.shape[0] for p in pairs0], dtype=np.int64)
     offsets = np.zeros(n_pairs + 1, dtype=np.uint32)
@@ -52,15 +53,15 @@ def ransac_align(pairs0, pairs1, cam, backend="b200", num_iters=400, thresh=4.0,
     T = np.zeros((max(n_pairs, 1), 12))
     inl = np.zeros(max(total, 1), dtype=np.uint8)
     cnt = np.zeros(max(n_pairs, 1), dtype=np.uint32)
-    st = lib.ransac_align(device, n_pairs, capi.u32ptr(offsets), capi.dptr(p0), capi.dptr(p1), capi.dptr(intr),
+    st = entry(device, n_pairs, capi.u32ptr(offsets), capi.dptr(p0), capi.dptr(p1), capi.dptr(intr),
                           num_iters, float(thresh), rng_variant, capi.dptr(T), capi.u8ptr(inl), capi.u32ptr(cnt))
     if st != 0:
         raise RuntimeError(f"cslam_ransac_align status {st}")
     return T[:n_pairs], [inl[offsets[i]:offsets[i + 1]].astype(bool) for i in range(n_pairs)], cnt[:n_pairs]
 
 
-def compute_initial_guess(track, poses, points, initialized, k1=0, k2=None, backend="b200", num_iters=400,
-                          thresh=4.0, rng_variant=0, device=0):
+def compute_initial_guess(track, poses, points, initialized, k1=0, k2=None, num_iters=400,
+                          thresh=4.0, rng_variant=0, device=0, entry=None):
     """dataset_problem.cpp:179-270.  `poses` (n, 12) [t | R], `points` (m, 3) and the boolean
     `initialized` (m,) are updated in place; poses[k1] is the anchor.  Returns per-pair statistics."""
     n_states = track["n_poses"]
@@ -79,7 +80,7 @@ def compute_initial_guess(track, poses, points, initialized, k1=0, k2=None, back
         pairs0.append(triangulate(cam, uvd[a0:a1][kp]))
         pairs1.append(triangulate(cam, uvd[b0:b1][kc]))
         ids.append(pt[a0:a1][kp])
-    T, inl, cnt = ransac_align(pairs0, pairs1, cam, backend, num_iters, thresh, rng_variant, device)
+    T, inl, cnt = ransac_align(pairs0, pairs1, cam, num_iters, thresh, rng_variant, device, entry)
     for i, k in enumerate(range(k1 + 1, k2)):
         Rr, tr = T[i, 3:].reshape(3, 3), T[i, :3]
         Rp, tp = poses[k - 1, 3:].reshape(3, 3), poses[k - 1, :3]

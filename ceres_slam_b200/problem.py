@@ -2,8 +2,7 @@
 
 `BAProblem` plays the role `ceres::Problem` + `ceres::Solve` play inside the reference's
 `solveWindow` (tests/dataset_vo.cpp:22-85): parameter blocks are numpy arrays owned by the
-caller and are updated in place by `solve()`.  The same class drives the CUDA library
-(`backend="b200"`) and, for tests and CPU baselines only, the oracle (`backend="oracle"`).
+caller and are updated in place by `solve()`.  It binds the CUDA library and nothing else.
 """
 import ctypes as C
 
@@ -17,7 +16,7 @@ class CslamError(RuntimeError):
 
 
 def default_options(lib=None, **overrides):
-    lib = lib or capi.load_oracle()
+    lib = lib or capi.load_product()
     opt = capi.Options()
     lib.options_init(C.byref(opt))
     for k, v in overrides.items():
@@ -28,9 +27,8 @@ def default_options(lib=None, **overrides):
 
 
 class BAProblem:
-    def __init__(self, backend="b200", **options):
-        self.backend = backend
-        self.lib = capi.load_product() if backend == "b200" else capi.load_oracle()
+    def __init__(self, **options):
+        self.lib = self._library()
         self.options = default_options(self.lib, **options)
         self._h = capi._h()
         self._check(self.lib.problem_create(C.byref(self._h), C.byref(self.options)))
@@ -38,6 +36,10 @@ class BAProblem:
         self.n_stereo = self.n_sun = self.n_prior = self.n_phong = 0
 
     # -- plumbing ---------------------------------------------------------------------------
+    @staticmethod
+    def _library():
+        return capi.load_product()
+
     def _check(self, status):
         if status != 0:
             msg = self.lib.last_error(self._h) if self._h else b""

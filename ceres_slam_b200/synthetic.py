@@ -205,12 +205,12 @@ def add_phong(track, seed=44, n_materials=8, directional=False, int_var=1e-4, no
     return track
 
 
-def build_phong_problem(track, backend="b200", bounds=False, **options):
+def build_phong_problem(track, bounds=False, problem_cls=None, **options):
     """dataset_ba_phong's problem (stereo + intensity + normal blocks, first pose constant).  With a
     track made with `shared_textures` the texture blocks are shared per material
     (cslam_set_textures) — the shape the joint solve takes; `bounds` adds the box constraints of
     dataset_ba_phong.cpp:143-181."""
-    p, poses, points = build_problem(track, backend=backend, **options)
+    p, poses, points = build_problem(track, problem_cls=problem_cls, **options)
     normals, textures = p.set_vertices(track["normals"].copy(), track["textures"].copy(), track["material_id"])
     if "tex_shared" in track:
         textures = p.set_textures(track["tex_shared"].copy(), track["texture_id"])
@@ -254,11 +254,11 @@ def window_of(track, k1, k2):
     return out
 
 
-def build_problem(track, backend="b200", sun=False, prior=None, huber=0.0, hold_first=True, **options):
+def build_problem(track, sun=False, prior=None, huber=0.0, hold_first=True, problem_cls=None, **options):
     """Assemble the problem the way the reference drivers do (dataset_vo.cpp:40-62 /
     dataset_vo_sun.cpp:49-129).  Returns (BAProblem, poses array, points array)."""
     from .problem import BAProblem
-    p = BAProblem(backend, **options)
+    p = (problem_cls or BAProblem)(**options)
     c = track["cam"]
     p.set_camera(c["fu"], c["fv"], c["cu"], c["cv"], c["b"])
     const = track["constant"] if hold_first else np.zeros(track["n_poses"], dtype=np.uint8)

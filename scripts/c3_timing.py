@@ -11,7 +11,7 @@ t0 = time.perf_counter()
 tr = syn.add_phong(syn.make_track(n_poses, 100, 10, seed=42), shared_textures=True)
 print("generate %.1f s: %d poses, %d vertices, %d obs" % (time.perf_counter() - t0, tr["n_poses"], tr["n_points"], tr["obs_cam"].size), file=sys.stderr)
 FIXED = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
-p, st = syn.build_phong_problem(tr, backend="b200", bounds=True, max_num_iterations=iters, profile_kernels=1, **FIXED)
+p, st = syn.build_phong_problem(tr, bounds=True, max_num_iterations=iters, profile_kernels=1, **FIXED)
 t0 = time.perf_counter(); p.upload(); t1 = time.perf_counter()
 print("upload %.1f ms" % ((t1 - t0) * 1e3), file=sys.stderr)
 p.lm_begin()

@@ -6,7 +6,7 @@ kw = dict(max_num_iterations=6, function_tolerance=0.0, parameter_tolerance=0.0,
 for ls in (0, 1):
     res = []
     for rep in range(4):
-        p, poses, points = syn.build_problem(tr, backend="b200", linear_solver=ls, **kw)
+        p, poses, points = syn.build_problem(tr, linear_solver=ls, **kw)
         s = p.solve()
         res.append((poses.copy(), points.copy(), p.iteration_log()))
     for rep in range(1, 4):

@@ -6,7 +6,7 @@ from ceres_slam_b200 import synthetic as syn
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.25
 tr = bench.c5_track(scale)
 for strat in (1, 0):
-    p, _, _ = syn.build_problem(tr, backend="b200", max_num_iterations=10 ** 6, profile_kernels=1, trust_region_strategy=strat,
+    p, _, _ = syn.build_problem(tr, max_num_iterations=10 ** 6, profile_kernels=1, trust_region_strategy=strat,
                                 dogleg_type=1, **bench.LM_EXACT)
     p.upload(); p.lm_begin(); p.lm_iterate(3, True); p.reset_profile()
     s0 = p.lm_iterate(0, True).device_ms

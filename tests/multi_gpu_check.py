@@ -32,11 +32,11 @@ def main():
     # checks that layout against the host analysis)
     for linear_solver, tr in ((0, tr_shared), (1, tr_shared), (0, tr_per_obs)):
         # reference: the whole problem on this rank's GPU
-        p1, poses1, points1 = syn.build_problem(tr, backend="b200", linear_solver=linear_solver, **kw)
+        p1, poses1, points1 = syn.build_problem(tr, linear_solver=linear_solver, **kw)
         s1 = p1.solve()
         log1 = p1.iteration_log()
         # sharded
-        pn, posesn, pointsn = syn.build_problem(tr, backend="b200", linear_solver=linear_solver, **kw)
+        pn, posesn, pointsn = syn.build_problem(tr, linear_solver=linear_solver, **kw)
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             buf = (C.c_uint8 * 128)()

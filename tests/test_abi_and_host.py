@@ -38,7 +38,7 @@ def test_no_cpu_fallback(lib):
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     tr = syn.make_track(40, 5, 4, seed=1)
-    p, _, _ = syn.build_problem(tr, backend="b200")
+    p, _, _ = syn.build_problem(tr)
     with pytest.raises(CslamError, match="no CUDA device|cuda"):
         p.solve()
     with pytest.raises(CslamError):
@@ -46,18 +46,38 @@ def test_no_cpu_fallback(lib):
 
 
 def test_product_never_imports_oracle():
-    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "ceres_slam_b200")):
-        for f in files:
-            if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp")):
-                for line in open(os.path.join(dirpath, f)):
-                    if line.lstrip().startswith("#include") or "dlopen" in line:
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/: nothing in the
+    product package or the public header includes, dlopens, imports or names the checker's libraries."""
+    import re
+    code_ref = re.compile(r"liboracle|libcslam_ref|cslam_oracle_|cslam_ref_|load_oracle|pybinding|ref_standin"
+                          r"|^\s*(from|import)\s+oracle\b|[\"'/]oracle[/\"']")
+    roots = [os.path.join(ROOT, "ceres_slam_b200"), os.path.join(ROOT, "include")]
+    seen = 0
+    for root in roots:
+        for dirpath, dirs, files in os.walk(root):
+            dirs[:] = [x for x in dirs if x not in ("build", "__pycache__", ".pytest_cache")]
+            for f in files:
+                if not f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py")):
+                    continue
+                seen += 1
+                for line in open(os.path.join(dirpath, f), errors="replace"):
+                    assert not code_ref.search(line), (f, line)
+                    if line.lstrip().startswith("#include") or "dlopen" in line or "CDLL" in line:
                         assert "oracle" not in line, (f, line)
+    assert seen > 20
+    # and at run time: importing the whole package maps neither checker library
+    import subprocess, sys
+    code = ("import ceres_slam_b200, ceres_slam_b200.problem, ceres_slam_b200.initial_guess, ceres_slam_b200.synthetic;"
+            "from ceres_slam_b200 import capi; capi.load_product(); import sys;"
+            "maps = open('/proc/self/maps').read();"
+            "assert 'libcslam_b200' in maps; assert 'liboracle' not in maps and 'libcslam_ref' not in maps;"
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
 
 
 def test_structure_analysis_single_rank(lib):
     tr = syn.make_track(100, 15, 10, seed=3)
-    p, _, _ = syn.build_problem(tr, backend="b200")
+    p, _, _ = syn.build_problem(tr)
     info = p.analyze()
     n_obs = tr["obs_cam"].size
     seen = np.unique(tr["obs_pt"])
@@ -82,7 +102,7 @@ def test_structure_analysis_single_rank(lib):
     assert info["nnz_blocks"] == len(pairs)
     assert info["n_grouped_landmarks"] > 0.5 * info["n_landmarks"]
     # forcing the generic path leaves no groups
-    p1, _, _ = syn.build_problem(tr, backend="b200", schur_path=1)
+    p1, _, _ = syn.build_problem(tr, schur_path=1)
     assert p1.analyze()["n_groups"] == 0
 
 
@@ -94,7 +114,7 @@ from ceres_slam_b200 import synthetic as syn
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
 tr = syn.make_track(120, 20, 8, seed=5)
-p, _, _ = syn.build_problem(tr, backend="b200")
+p, _, _ = syn.build_problem(tr)
 whole = p.analyze(1, 0)
 mine = p.analyze(2, rank)
 t = torch.tensor([mine["n_landmarks"], mine["n_observations"], mine["landmark_id_sum"], mine["nnz_blocks"],
@@ -129,7 +149,8 @@ def test_options_struct_layout_matches_the_header():
     distinctive default, so any drift in the fields before it shows up there (both libraries)."""
     import ctypes as C
     from ceres_slam_b200 import capi
-    for lib in (capi.load_product(), capi.load_oracle()):
+    from oracle import pybinding
+    for lib in (capi.load_product(), pybinding.load_oracle()):
         opt = capi.Options()
         C.memset(C.byref(opt), 0xAB, C.sizeof(opt))
         lib.options_init(C.byref(opt))

@@ -12,6 +12,7 @@ import pytest
 
 from ceres_slam_b200 import capi
 from ceres_slam_b200 import synthetic as syn
+from oracle import pybinding as orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 d = capi.dptr
@@ -42,7 +43,7 @@ def blockwise_close(a, b, rtol=RTOL):
 
 def test_stereo_closed_form_vs_autodiff(cf):
     tr = syn.make_track(60, 4, 6, seed=1, per_obs_W=True)
-    p, poses, points = syn.build_problem(tr, backend="oracle", hold_first=False)
+    p, poses, points = orc.build_problem(tr, hold_first=False)
     ev = p.evaluate()
     intr = np.array([tr["cam"][k] for k in ("fu", "fv", "cu", "cv", "b")])
     n = tr["obs_cam"].size
@@ -74,7 +75,7 @@ def test_sun_closed_form_vs_autodiff(cf, oracle):
         W2 = (A @ A.T + np.eye(2)).reshape(4)
         # a third of the trials exercise the hard thresholds (sun_sensor_error.hpp:87-93)
         az_t, zen_t = (1000.0, 1000.0) if trial % 3 else (0.8, 0.5)
-        p = BAProblem("oracle")
+        p = orc.OracleProblem()
         p.set_camera(1, 1, 0, 0, 1)
         p.set_poses(pose[None, :].copy())
         p.set_points(np.zeros((1, 3)))
@@ -100,7 +101,7 @@ def test_prior_closed_form_vs_autodiff(cf, oracle, offset_scale):
         oracle.se3_plus(d(Tref), d(eps), d(pose))
         A = rng.normal(size=(6, 6))
         W6 = (A @ A.T + 6 * np.eye(6)) * (1e6 if trial % 2 else 1.0)   # Sigma0 = 1e-12 I -> W = 1e6 I
-        p = BAProblem("oracle")
+        p = orc.OracleProblem()
         p.set_camera(1, 1, 0, 0, 1)
         p.set_poses(pose[None, :].copy())
         p.set_points(np.zeros((1, 3)))

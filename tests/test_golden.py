@@ -15,6 +15,7 @@ import pytest
 
 from ceres_slam_b200 import capi
 from ceres_slam_b200.problem import BAProblem
+from oracle import pybinding as orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 d = capi.dptr
@@ -25,24 +26,6 @@ RTOL = 1e-10
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "functors_mp60.json")) as f:
         return json.load(f)
-
-
-@pytest.fixture(scope="module")
-def cf():
-    so = os.path.join(ROOT, "tests", "_build", "libclosedform_host.so")
-    srcs = [os.path.join(ROOT, "tests", "closed_form_host.cpp"),
-            os.path.join(ROOT, "ceres_slam_b200", "csrc", "closed_form.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-o", so, srcs[0]])
-    lib = C.CDLL(so)
-    for name in ("cf_stereo_block", "cf_sun_block", "cf_prior_block", "cf_se3_plus", "cf_so3_log",
-                 "cf_normal_block", "cf_intensity_block", "cf_unit_plus"):
-        getattr(lib, name).restype = None
-    lib.cf_sun_block.argtypes = [capi._dp] * 4 + [C.c_double, C.c_double] + [capi._dp] * 2
-    lib.cf_intensity_block.argtypes = [capi._dp] * 6 + [C.c_double, C.c_double, C.c_int] + [capi._dp] * 7
-    return lib
 
 
 def A(x):
@@ -56,7 +39,7 @@ def close(a, b, rtol=RTOL, floor=0.0):
 
 
 def one_pose_problem(backend, g, pose, point=None):
-    p = BAProblem(backend=backend)
+    p = (orc.OracleProblem if backend == "oracle" else BAProblem)()
     p.set_camera(*g["camera"])
     poses = p.set_poses(A(pose).reshape(1, 12).copy(), np.zeros(1, dtype=np.uint8))
     pts = p.set_points(A(point if point is not None else [0, 0, 5]).reshape(1, 3).copy())

@@ -19,7 +19,7 @@ def c5():
 def test_c5_cost_agrees_between_kernels_and_numpy(product, c5):
     """The materialised residual kernel (K1, caller's order), the fused Schur pass (K2, internal
     grouped order) and a float64 numpy restatement of r = W (pi(R p + t) - z) agree on 1/2 |r|^2."""
-    p, poses, points = syn.build_problem(c5, backend="b200", max_num_iterations=1, **FIXED)
+    p, poses, points = syn.build_problem(c5, max_num_iterations=1, **FIXED)
     ev = p.evaluate(jacobians=False)
     k, j = c5["obs_cam"].astype(np.int64), c5["obs_pt"].astype(np.int64)
     R, t = syn.pose_R(c5["poses"]), syn.pose_t(c5["poses"])
@@ -39,7 +39,7 @@ def test_c5_solve_properties_and_order_invariance(product, c5):
     """Five LM iterations at full size: accepted steps decrease the cost, and a random permutation of the caller's observation order
     (different staging, same internal layout) reproduces the solution to rounding."""
     kw = dict(FIXED, max_num_iterations=5)
-    p, poses, points = syn.build_problem(c5, backend="b200", **kw)
+    p, poses, points = syn.build_problem(c5, **kw)
     s = p.solve()
     log = p.iteration_log()
     acc = log[1:, 9] == 1
@@ -53,7 +53,7 @@ def test_c5_solve_properties_and_order_invariance(product, c5):
     tr2 = dict(c5)
     for key in ("obs_cam", "obs_pt", "uvd"):
         tr2[key] = np.ascontiguousarray(c5[key][perm])
-    p2, poses2, points2 = syn.build_problem(tr2, backend="b200", **kw)
+    p2, poses2, points2 = syn.build_problem(tr2, **kw)
     s2 = p2.solve()
     assert abs(s2.final_cost - s.final_cost) < 1e-9 * s.final_cost
     assert np.abs(poses2 - poses).max() < 1e-8 and np.abs(points2 - points).max() < 1e-7
@@ -64,7 +64,7 @@ def test_c3_lighting_solve_properties(product):
     joint solve equals stereo cost + lighting cost from the two evaluation kernels, the solve
     decreases it, unit normals stay unit, the box holds."""
     tr = syn.add_phong(syn.make_track(2000, 100, 10, seed=42), shared_textures=True)
-    p, st = syn.build_phong_problem(tr, backend="b200", bounds=True, max_num_iterations=5, **FIXED)
+    p, st = syn.build_phong_problem(tr, bounds=True, max_num_iterations=5, **FIXED)
     c_st = p.evaluate(jacobians=False)["cost"]
     c_ph = p.evaluate_phong()["cost"]
     s = p.solve()
@@ -81,7 +81,7 @@ def test_c5_device_structure_analysis_equals_host(product, c5, monkeypatch):
     upload() rebuilds it on the host and throws unless the layout hash, the reduced system's pattern and every
     table agree — here on the full 20 M observations, in the caller's order and in a random one."""
     monkeypatch.setenv("CSLAM_VERIFY_STRUCTURE", "1")
-    p, _, _ = syn.build_problem(c5, backend="b200", max_num_iterations=1, **FIXED)
+    p, _, _ = syn.build_problem(c5, max_num_iterations=1, **FIXED)
     p.upload()
     info = p.analyze()                                   # host-only analysis of the same problem
     assert info["n_observations"] == c5["obs_cam"].size and info["n_groups"] > 19000
@@ -90,5 +90,5 @@ def test_c5_device_structure_analysis_equals_host(product, c5, monkeypatch):
     tr = dict(c5)
     for k in ("obs_cam", "obs_pt", "uvd"):
         tr[k] = np.ascontiguousarray(c5[k][perm])
-    p2, _, _ = syn.build_problem(tr, backend="b200", max_num_iterations=1, **FIXED)
+    p2, _, _ = syn.build_problem(tr, max_num_iterations=1, **FIXED)
     p2.upload()

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from ceres_slam_b200 import synthetic as syn
+from oracle import pybinding as orc
 
 pytestmark = pytest.mark.gpu
 
@@ -19,8 +20,8 @@ def rel_err(a, b):
 
 
 def eval_pair(track, **kw):
-    pg, _, _ = syn.build_problem(track, backend="b200", **kw)
-    po, _, _ = syn.build_problem(track, backend="oracle", **kw)
+    pg, _, _ = syn.build_problem(track, **kw)
+    po, _, _ = orc.build_problem(track, **kw)
     return pg.evaluate(), po.evaluate()
 
 
@@ -64,8 +65,8 @@ def test_resjac_sun_and_prior(product, huber):
 
 def solve_pair(track, iters, **kw):
     kw = dict(FIXED, max_num_iterations=iters, **kw)
-    pg, poses_g, points_g = syn.build_problem(track, backend="b200", **kw)
-    po, poses_o, points_o = syn.build_problem(track, backend="oracle", **kw)
+    pg, poses_g, points_g = syn.build_problem(track, **kw)
+    po, poses_o, points_o = orc.build_problem(track, **kw)
     sg, so = pg.solve(), po.solve()
     return (pg, sg, poses_g, points_g), (po, so, poses_o, points_o)
 
@@ -154,12 +155,12 @@ def test_window_batch(product):
     from ceres_slam_b200.problem import solve_batch
     cases = _window_cases()
     kw = dict(FIXED, max_num_iterations=6)
-    gpu = [syn.build_problem(w, backend="b200", **dict(kw, **extra)) for w, extra in cases]
+    gpu = [syn.build_problem(w, **dict(kw, **extra)) for w, extra in cases]
     launches0 = product_launches(product)
     sums = solve_batch([g[0] for g in gpu])
     assert product_launches(product) - launches0 == 1, "the whole batch must be one kernel launch"
     for (w, extra), (pg, poses_g, points_g), sg in zip(cases, gpu, sums):
-        po, poses_o, points_o = syn.build_problem(w, backend="oracle", **dict(kw, **extra))
+        po, poses_o, points_o = orc.build_problem(w, **dict(kw, **extra))
         so = po.solve()
         check_lm((pg, sg, poses_g, points_g), (po, so, poses_o, points_o), tol=1e-5 if "initial_trust_region_radius" in extra else LM_TOL)
 
@@ -168,8 +169,8 @@ def test_window_convergence(product):
     """With Ceres' default tolerances the in-kernel loop must stop where the oracle stops."""
     tr = syn.make_track(100, 15, 10, seed=42)
     w = syn.window_of(tr, 10, 12)
-    pg, poses_g, points_g = syn.build_problem(w, backend="b200", window_path=2)
-    po, poses_o, points_o = syn.build_problem(w, backend="oracle")
+    pg, poses_g, points_g = syn.build_problem(w, window_path=2)
+    po, poses_o, points_o = orc.build_problem(w)
     sg, so = pg.solve(), po.solve()
     assert (sg.termination_type, sg.termination_reason) == (so.termination_type, so.termination_reason)
     check_lm((pg, sg, poses_g, points_g), (po, so, poses_o, points_o))
@@ -237,7 +238,7 @@ def test_rejected_step_path(product):
 
 def test_errors(product):
     from ceres_slam_b200.problem import BAProblem, CslamError
-    p = BAProblem("b200")
+    p = BAProblem()
     p.set_camera(1, 1, 0, 0, 1)
     p.set_poses(np.zeros((2, 12)))
     p.set_points(np.zeros((3, 3)))
@@ -248,7 +249,7 @@ def test_errors(product):
 
 
 def _reduced(track, path, **kw):
-    p, _, _ = syn.build_problem(track, backend="b200", schur_path=path, **kw)
+    p, _, _ = syn.build_problem(track, schur_path=path, **kw)
     p.upload()
     p.lm_begin()
     return p.reduced_system()
@@ -346,7 +347,7 @@ def test_phong_blocks(product, oracle, directional):
     tr = syn.add_phong(syn.make_track(40, 12, 6, seed=8), directional=directional)
     n = tr["obs_cam"].size
     assert n > 2000 and n % 128 != 0
-    p, st = syn.build_phong_problem(tr, backend="b200")
+    p, st = syn.build_phong_problem(tr)
     eg = p.evaluate_phong()
     eo = _oracle_phong(tr, st, oracle)
     assert rel_err(eg["r_int"], eo["r_int"]) < RJ_TOL
@@ -369,7 +370,7 @@ def _oracle_covariance(track, poses, points, cam, constant, **kw):
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     tr = dict(track, poses=poses, points=points, constant=constant)
-    po, _, _ = syn.build_problem(tr, backend="oracle", hold_first=bool(constant[0]), **kw)
+    po, _, _ = orc.build_problem(tr, hold_first=bool(constant[0]), **kw)
     ev = po.evaluate(apply_loss=True)
     n_p, n_l = poses.shape[0], points.shape[0]
     free = np.flatnonzero(constant == 0)
@@ -419,7 +420,7 @@ def test_covariance_block_window(product):
     w = syn.window_of(tr, 20, 22)
     prior = (0, w["poses"][0].copy(), np.eye(6) * 1e3)
     kw = dict(sun=True, prior=prior, huber=1.0)
-    pg, poses_g, points_g = syn.build_problem(w, backend="b200", hold_first=False, **kw)
+    pg, poses_g, points_g = syn.build_problem(w, hold_first=False, **kw)
     pg.solve()
     cov = pg.covariance_block(1)
     ref = _oracle_covariance(w, poses_g.copy(), points_g.copy(), 1, np.zeros(2, dtype=np.uint8), **kw)
@@ -431,7 +432,7 @@ def test_covariance_block_window(product):
 def test_covariance_block_full_batch(product):
     """The same on a full-batch problem (first pose constant): banded direct solver path."""
     tr = syn.make_track(60, 15, 6, seed=21)
-    pg, poses_g, points_g = syn.build_problem(tr, backend="b200", max_num_iterations=8)
+    pg, poses_g, points_g = syn.build_problem(tr, max_num_iterations=8)
     pg.solve()
     for cam in (1, 30, 59):
         cov = pg.covariance_block(cam)
@@ -444,8 +445,8 @@ def test_covariance_block_full_batch(product):
 
 def _phong_pair(tr, iters, bounds, **extra):
     kw = dict(FIXED, max_num_iterations=iters, **extra)
-    pg, sg = syn.build_phong_problem(tr, backend="b200", bounds=bounds, **kw)
-    po, so = syn.build_phong_problem(tr, backend="oracle", bounds=bounds, num_threads=8, **kw)
+    pg, sg = syn.build_phong_problem(tr, bounds=bounds, **kw)
+    po, so = orc.build_phong_problem(tr, bounds=bounds, num_threads=8, **kw)
     return (pg, pg.solve(), sg), (po, po.solve(), so)
 
 
@@ -496,7 +497,7 @@ def test_phong_solve_refusals(product):
     """What the joint solve does not take is refused loudly, not solved differently."""
     from ceres_slam_b200.problem import CslamError
     tr = syn.add_phong(syn.make_track(12, 20, 5, seed=8))       # per-vertex textures
-    pg, _ = syn.build_phong_problem(tr, backend="b200")
+    pg, _ = syn.build_phong_problem(tr)
     with pytest.raises(CslamError, match="status 3"):
         pg.solve()
 
@@ -665,7 +666,7 @@ def test_band_solver_cyclic_reduction(product, shape, leaves):
     kw = dict(FIXED, max_num_iterations=4, window_path=1)
     g2, o = solve_pair(tr, 4, band_separator_solver=2, band_leaves=leaves, window_path=1)
     check_lm(g2, o)
-    p1, poses1, points1 = syn.build_problem(tr, backend="b200", band_separator_solver=1, band_leaves=leaves, **kw)
+    p1, poses1, points1 = syn.build_problem(tr, band_separator_solver=1, band_leaves=leaves, **kw)
     p1.solve()
     assert rel_err(g2[2], poses1) < 1e-9 and rel_err(g2[3], points1) < 1e-9
 
@@ -715,8 +716,8 @@ def test_lm_phong_stage2_lighting_only(product, directional):
     tr = syn.add_phong(syn.make_track(30, 12, 6, seed=5), directional=directional, shared_textures=True)
     tr["constant"] = np.ones(tr["n_poses"], dtype=np.uint8)
     kw = dict(FIXED, max_num_iterations=6)
-    pg, stg = syn.build_phong_problem(tr, backend="b200", bounds=True, **kw)
-    po, sto = syn.build_phong_problem(tr, backend="oracle", bounds=True, num_threads=8, **kw)
+    pg, stg = syn.build_phong_problem(tr, bounds=True, **kw)
+    po, sto = orc.build_phong_problem(tr, bounds=True, num_threads=8, **kw)
     before = stg["points"].copy()
     for p in (pg, po):
         p.set_points_constant(True)
@@ -785,11 +786,11 @@ def test_device_structure_analysis_matches_host(product, monkeypatch, case):
         bkw = dict(hold_first=False)
     monkeypatch.setenv("CSLAM_GPU_STRUCTURE_MIN", "0")
     monkeypatch.setenv("CSLAM_VERIFY_STRUCTURE", "1")
-    pd, poses_d, points_d = syn.build_problem(tr, backend="b200", **bkw, **kw)
+    pd, poses_d, points_d = syn.build_problem(tr, **bkw, **kw)
     sd = pd.solve()       # upload() throws if the two analyses disagree
     monkeypatch.delenv("CSLAM_VERIFY_STRUCTURE")
     monkeypatch.setenv("CSLAM_HOST_STRUCTURE", "1")
-    ph, poses_h, points_h = syn.build_problem(tr, backend="b200", **bkw, **kw)
+    ph, poses_h, points_h = syn.build_problem(tr, **bkw, **kw)
     sh = ph.solve()
     assert sd.num_iterations == sh.num_iterations
     assert abs(sd.final_cost - sh.final_cost) <= 1e-9 * abs(sh.final_cost)

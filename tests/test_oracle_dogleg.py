@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from ceres_slam_b200 import capi, synthetic as syn
+from oracle import pybinding as orc
 
 
 def test_polynomial_roots_match_numpy(oracle):
@@ -42,7 +43,7 @@ def test_dogleg_and_lm_reach_the_same_minimum(dogleg_type):
     tr = syn.add_sun(syn.make_track(40, 12, 6, seed=21))
     out = {}
     for strat in (0, 1):
-        p, poses, points = syn.build_problem(tr, backend="oracle", sun=True, max_num_iterations=50, num_threads=4,
+        p, poses, points = orc.build_problem(tr, sun=True, max_num_iterations=50, num_threads=4,
                                              trust_region_strategy=strat, dogleg_type=dogleg_type,
                                              initial_trust_region_radius=2.0)
         s = p.solve()

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from ceres_slam_b200 import synthetic as syn
+from oracle import pybinding as orc
 from ceres_slam_b200.problem import CslamError
 
 FIXED = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
@@ -20,8 +21,8 @@ def test_phong_oracle_reduces_to_stereo_oracle():
     tr["int_stiffness"] = 0.0
     tr["W_normal"] = np.zeros(9)
     kw = dict(FIXED, max_num_iterations=5, num_threads=4)
-    pj, sj = syn.build_phong_problem(tr, backend="oracle", **kw)
-    ps, poses_s, points_s = syn.build_problem(tr, backend="oracle", **kw)
+    pj, sj = orc.build_phong_problem(tr, **kw)
+    ps, poses_s, points_s = orc.build_problem(tr, **kw)
     before = {k: sj[k].copy() for k in ("normals", "phong", "textures", "light")}
     rj, rs = pj.solve(), ps.solve()
     lj, ls = pj.iteration_log(), ps.iteration_log()
@@ -48,7 +49,7 @@ def test_phong_oracle_recovers_noise_free_scene(directional):
     clean = syn.add_phong(dict(base), directional=directional, int_var=1e-30, normal_var=1e-30, shared_textures=True)
     for key in ("intensity", "normal_obs"):
         tr[key] = clean[key]
-    p, st = syn.build_phong_problem(tr, backend="oracle", bounds=True, max_num_iterations=60, num_threads=8)
+    p, st = orc.build_phong_problem(tr, bounds=True, max_num_iterations=60, num_threads=8)
     s = p.solve()
     assert s.final_cost < 1e-6 * s.initial_cost
     assert np.abs(st["light"] - tr["light_gt"]).max() < 1e-3
@@ -63,7 +64,7 @@ def test_phong_oracle_box_and_reference_start():
     on the box of dataset_ba_phong.cpp:143-181; every iterate stays inside it."""
     tr = syn.add_phong(syn.make_track(20, 12, 6, seed=5), shared_textures=True)
     tr["phong"] = np.tile(np.array([0.0, 0.0, 1.0]), (tr["phong"].shape[0], 1))
-    p, st = syn.build_phong_problem(tr, backend="oracle", bounds=True, max_num_iterations=10, num_threads=8, **FIXED)
+    p, st = orc.build_phong_problem(tr, bounds=True, max_num_iterations=10, num_threads=8, **FIXED)
     s = p.solve()
     assert s.final_cost < 0.1 * s.initial_cost
     assert np.all(st["phong"][:, :2] >= 0) and np.all(st["phong"][:, :2] <= 1) and np.all(st["phong"][:, 2] >= 1)
@@ -73,7 +74,7 @@ def test_phong_oracle_box_and_reference_start():
 
 def test_phong_oracle_refuses_unpaired_blocks():
     tr = syn.add_phong(syn.make_track(10, 8, 4, seed=2), shared_textures=True)
-    p, _ = syn.build_phong_problem(tr, backend="oracle")
+    p, _ = orc.build_phong_problem(tr)
     n = tr["obs_cam"].size - 3
     p.add_phong(tr["obs_cam"][:n], tr["obs_pt"][:n], tr["intensity"][:n], tr["int_stiffness"], tr["normal_obs"][:n],
                 tr["W_normal"])
@@ -87,10 +88,10 @@ def test_phong_oracle_stage2_holds_poses_and_positions():
     cost is carried as Ceres' fixed_cost."""
     tr = syn.add_phong(syn.make_track(14, 20, 6, seed=9), shared_textures=True)
     tr["constant"] = np.ones(tr["n_poses"], dtype=np.uint8)
-    p, st = syn.build_phong_problem(tr, backend="oracle", bounds=True, max_num_iterations=20, num_threads=4)
+    p, st = orc.build_phong_problem(tr, bounds=True, max_num_iterations=20, num_threads=4)
     p.set_points_constant(True)
     before = {k: st[k].copy() for k in st}
-    pj, _ = syn.build_phong_problem(tr, backend="oracle", bounds=True, max_num_iterations=0, num_threads=4)
+    pj, _ = orc.build_phong_problem(tr, bounds=True, max_num_iterations=0, num_threads=4)
     s = p.solve()
     assert np.array_equal(st["poses"], before["poses"]) and np.array_equal(st["points"], before["points"])
     for k in ("normals", "phong", "textures", "light"):

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from ceres_slam_b200 import capi, initial_guess as ig, synthetic as syn
+from oracle import pybinding as orc
 
 
 def _draws(oracle, n, count, variant):
@@ -110,7 +111,7 @@ def test_initial_guess_oracle_follows_ground_truth():
     poses = np.tile(tr["poses_gt"][k1], (tr["n_poses"], 1))
     points = np.zeros((tr["n_points"], 3))
     init = np.zeros(tr["n_points"], dtype=bool)
-    st = ig.compute_initial_guess(tr, poses, points, init, k1=k1, k2=k2, backend="oracle")
+    st = orc.compute_initial_guess(tr, poses, points, init, k1=k1, k2=k2)
     assert st["n_matches"].min() >= 40 and np.all(st["n_inliers"] >= 0.5 * st["n_matches"])
     assert np.abs(poses[k1:k2, :3] - tr["poses_gt"][k1:k2, :3]).max() < 0.3
     assert np.abs(poses[k1:k2, 3:] - tr["poses_gt"][k1:k2, 3:]).max() < 0.03
@@ -136,8 +137,8 @@ def test_ransac_gpu_matches_oracle(product, variant):
     tri0 = np.array([[1.0, 0.5, 9.0], [-2.0, 0.3, 14.0], [0.5, -1.0, 20.0]])
     pairs0 += [pairs0[0][:2], pairs0[1][:0], tri0]               # 2, 0 and exactly 3 (rigid) correspondences
     pairs1 += [pairs1[0][:2], pairs1[1][:0], tri0 @ R.T + np.array([0.1, 0.0, -0.3])]
-    Tg, ig_in, cg = ig.ransac_align(pairs0, pairs1, tr["cam"], "b200", rng_variant=variant)
-    To, io_in, co = ig.ransac_align(pairs0, pairs1, tr["cam"], "oracle", rng_variant=variant)
+    Tg, ig_in, cg = ig.ransac_align(pairs0, pairs1, tr["cam"], rng_variant=variant)
+    To, io_in, co = orc.ransac_align(pairs0, pairs1, tr["cam"], rng_variant=variant)
     assert np.array_equal(cg, co)
     assert cg[-3] == 0 and cg[-2] == 0 and cg[-1] == 3
     for a, b in zip(ig_in, io_in):
@@ -155,7 +156,7 @@ def test_initial_guess_gpu_matches_oracle(product):
         poses = np.tile(tr["poses_gt"][0], (tr["n_poses"], 1))
         points = np.zeros((tr["n_points"], 3))
         init = np.zeros(tr["n_points"], dtype=bool)
-        ig.compute_initial_guess(tr, poses, points, init, backend=backend)
+        (ig if backend == "b200" else orc).compute_initial_guess(tr, poses, points, init)
         out[backend] = (poses, points, init)
     assert np.array_equal(out["b200"][2], out["oracle"][2])
     assert np.abs(out["b200"][0] - out["oracle"][0]).max() < 1e-8
