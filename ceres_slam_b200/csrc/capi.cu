@@ -305,7 +305,7 @@ cslam_status cslam_reset_state(cslam_problem* p) {
 
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary) {
     return guarded(p, [&](Engine& e) {
-        if (!e.lighting_in_solve() && (e.window_eligible() || e.opt.window_path == 2)) {
+        if (e.window_eligible() || (e.opt.window_path == 2 && !e.lighting_in_solve())) {
             // configs 1/2: a sliding window is one CTA with the LM loop on the device
             Engine* one = &e;
             cslam::solve_window_batch(&one, 1, summary);

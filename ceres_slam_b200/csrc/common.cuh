@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -25,6 +26,24 @@ struct NotImplemented : std::logic_error {
             throw ::cslam::CudaError(std::string(#expr) + " -> " + cudaGetErrorString(_e) +  \
                                      " (" __FILE__ ":" + std::to_string(__LINE__) + ")");    \
     } while (0)
+
+// Function attributes (opt-in dynamic shared memory, occupancy) are PER DEVICE, and the ABI lets a
+// process solve on several devices (cslam_options.device).  A call site keeps one PerDevice flag /
+// value set: `first_use()` is true until `mark()` was called for the CURRENT device.  Setting an
+// attribute twice from racing handles is harmless (idempotent), launching before it is set is not:
+// so set first, mark after.
+struct PerDevice {
+    std::atomic<unsigned long long> done{0};
+    int value[64] = {0};   // optional per-device cached integers (e.g. occupancy), guarded by `done`
+    int value2[64] = {0};
+    static int current() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        return dev & 63;
+    }
+    bool first_use(int dev) const { return !(done.load(std::memory_order_acquire) & (1ull << dev)); }
+    void mark(int dev) { done.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 // Device buffer with explicit lifetime; no implicit copies.
 template <class T>

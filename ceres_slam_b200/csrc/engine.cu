@@ -1351,10 +1351,22 @@ void Engine::download() {
     if (!uploaded) throw std::invalid_argument("download before upload");
     std::vector<double> pos(12 * size_t(n_poses));
     CSLAM_CUDA(cudaMemcpyAsync(pos.data(), d_poses_best.p, d_poses_best.bytes(), cudaMemcpyDeviceToHost, stream));
-    if (n_lm) {
+    if (n_lm || (n_ranks > 1 && n_points)) {
         // best landmarks back into the caller's point order on the device, then one copy straight
-        // into the caller's array (points this rank does not own keep the values it uploaded)
-        launch_scatter_points(stream, n_lm, d_lm_user.p, d_points_best.p, d_raw_pts.p);
+        // into the caller's array
+        if (n_ranks > 1) {
+            // every rank returns the COMPLETE solution: the shards' landmarks are summed over the ranks
+            // (collective: all ranks of the communicator call download / cslam_solve together)
+            DBuf<double> z4;
+            z4.alloc(4 * size_t(n_points), stream);
+            CSLAM_CUDA(cudaMemsetAsync(z4.p, 0, z4.bytes(), stream));
+            launch_scatter_points4(stream, n_lm, d_lm_user.p, d_points_best.p, z4.p);
+            comm_allreduce_sum(nccl_comm, z4.p, 4 * size_t(n_points), stream);
+            launch_merge_points4(stream, (long long)n_points, z4.p, d_raw_pts.p);
+            z4.release_async(stream);
+        } else {
+            launch_scatter_points(stream, n_lm, d_lm_user.p, d_points_best.p, d_raw_pts.p);
+        }
         CSLAM_CUDA(cudaStreamSynchronize(stream));
         parallel_d2h(opt.device, h_points, d_raw_pts.p, 3 * size_t(n_points) * sizeof(double));
     }

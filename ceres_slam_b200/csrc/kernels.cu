@@ -1072,6 +1072,27 @@ __global__ void scatter_points_kernel(int n_lm, const uint32_t* __restrict__ lm_
         raw_pts[3 * j + 2] = points[3ll * a + 2];
     }
 }
+// multi-GPU download: owned landmarks go into a zeroed [x y z flag] buffer that is summed over the
+// ranks (every point has at most one owner, and x + 0 = x exactly), then merged where flag > 0
+__global__ void scatter_points4_kernel(int n_lm, const uint32_t* __restrict__ lm_user, const double* __restrict__ points,
+                                       double* __restrict__ z4) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n_lm) {
+        const long long j = lm_user[a];
+        z4[4 * j] = points[3ll * a];
+        z4[4 * j + 1] = points[3ll * a + 1];
+        z4[4 * j + 2] = points[3ll * a + 2];
+        z4[4 * j + 3] = 1.0;
+    }
+}
+__global__ void merge_points4_kernel(long long n_points, const double* __restrict__ z4, double* __restrict__ raw_pts) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j < n_points && z4[4 * j + 3] > 0.0) {
+        raw_pts[3 * j] = z4[4 * j];
+        raw_pts[3 * j + 1] = z4[4 * j + 1];
+        raw_pts[3 * j + 2] = z4[4 * j + 2];
+    }
+}
 __global__ void fill_kernel(double* p, size_t n, double value) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = value;
 }
@@ -1093,11 +1114,12 @@ void launch_resjac(cudaStream_t s, const CameraIntrinsics& cam, long long n, con
                    int W_per_obs, const double* poses, const double* points, const int* cam_free, const int* tile_lo,
                    const int* tile_n, double* r, double* Jc, double* Jp, double* cost) {
     if (n <= 0) return;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDevice attr_done;
+    const int dev_ = PerDevice::current();
+    if (attr_done.first_use(dev_)) {
         CSLAM_CUDA(cudaFuncSetAttribute(resjac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RJ_SMEM)));
         CSLAM_CUDA(cudaFuncSetAttribute(resjac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RJ_SMEM)));
-        attr_done = true;
+        attr_done.mark(dev_);
     }
     const long long tiles = (n + RJ_TILE - 1) / RJ_TILE;
     const int grid = int(tiles < 3ll * kSMs ? tiles : 3ll * kSMs);  // persistent: 3 CTAs per SM
@@ -1147,10 +1169,11 @@ void launch_camonly_eval(cudaStream_t s, const DevView& v, const SunBlockData* s
 void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, double* S, double* Bdiag,
                           double* bp, double* gp, double* gl, double* scal) {
     if (lm_hi <= lm_lo) return;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDevice attr_done;
+    const int dev_ = PerDevice::current();
+    if (attr_done.first_use(dev_)) {
         CSLAM_CUDA(cudaFuncSetAttribute(schur_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SG_SMEM)));
-        attr_done = true;
+        attr_done.mark(dev_);
     }
     const int grid = grid_for(lm_hi - lm_lo, SG_WARPS, 4 * kSMs);
     schur_generic_kernel<<<grid, SG_WARPS * 32, SG_SMEM, s>>>(v, lm_lo, lm_hi, dg, S, Bdiag, bp, gp, gl, scal);
@@ -1259,6 +1282,20 @@ void launch_gather_layout(cudaStream_t s, long long n_obs, const uint32_t* obs_u
 void launch_scatter_points(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* raw_pts) {
     if (n_lm <= 0) return;
     scatter_points_kernel<<<(n_lm + 255) / 256, 256, 0, s>>>(n_lm, lm_user, points, raw_pts);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_scatter_points4(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* z4) {
+    if (n_lm <= 0) return;
+    scatter_points4_kernel<<<(n_lm + 255) / 256, 256, 0, s>>>(n_lm, lm_user, points, z4);
+    CSLAM_LAUNCHED(1);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_merge_points4(cudaStream_t s, long long n_points, const double* z4, double* raw_pts) {
+    if (n_points <= 0) return;
+    merge_points4_kernel<<<int((n_points + 255) / 256), 256, 0, s>>>(n_points, z4, raw_pts);
     CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }

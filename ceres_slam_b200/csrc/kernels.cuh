@@ -86,6 +86,8 @@ void launch_gather_layout(cudaStream_t s, long long n_obs, const uint32_t* obs_u
                           double* v, double* d, double* W, int n_lm, const uint32_t* lm_user, const double* raw_pts,
                           double* points);
 void launch_scatter_points(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* raw_pts);
+void launch_scatter_points4(cudaStream_t s, int n_lm, const uint32_t* lm_user, const double* points, double* z4);
+void launch_merge_points4(cudaStream_t s, long long n_points, const double* z4, double* raw_pts);
 void launch_fill(cudaStream_t s, double* p, size_t n, double value);
 
 // K1-phong — materialised residuals / Jacobians of the intensity and normal blocks

@@ -479,11 +479,12 @@ size_t leaf_smem() {
 
 template <int W, bool kSpike>
 void run_leaf(cudaStream_t s, const BandView& V) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice attr;
+    const int dev_ = PerDevice::current();
+    if (attr.first_use(dev_)) {
         CSLAM_CUDA(cudaFuncSetAttribute(band_leaf_kernel<W, kSpike>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         int(leaf_smem<W, kSpike>())));
-        attr = true;
+        attr.mark(dev_);
     }
     band_leaf_kernel<W, kSpike><<<V.P, BL_THREADS, leaf_smem<W, kSpike>(), s>>>(V);
     CSLAM_CUDA(cudaGetLastError());
@@ -491,10 +492,11 @@ void run_leaf(cudaStream_t s, const BandView& V) {
 
 template <int W, bool kSpike>
 void run_backsub(cudaStream_t s, const BandView& V, const double* ysep) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice attr;
+    const int dev_ = PerDevice::current();
+    if (attr.first_use(dev_)) {
         CSLAM_CUDA(cudaFuncSetAttribute(band_backsub_kernel<W, kSpike>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr = true;
+        attr.mark(dev_);
     }
     const size_t smem = sizeof(double) * (8 * size_t(W + 1) * 36 + 6 * size_t(V.m + W) + 6 * size_t(W));
     band_backsub_kernel<W, kSpike><<<V.P, 128, smem, s>>>(V, ysep);
@@ -849,15 +851,9 @@ static int bcr_solve(cudaStream_t st, const BandView& V, const BandScratch& K, i
     R.fail = V.fail;
     const size_t smem_odd = sizeof(double) * size_t(R.b) * (4 * R.b + 1);
     const size_t smem_even = sizeof(double) * (3 * size_t(bb) + 2 * R.b);
-    static size_t attr_odd = 0, attr_even = 0;
-    if (smem_odd > attr_odd) {
-        CSLAM_CUDA(cudaFuncSetAttribute(bcr_odd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_odd)));
-        attr_odd = smem_odd;
-    }
-    if (smem_even > attr_even) {
-        CSLAM_CUDA(cudaFuncSetAttribute(bcr_even_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_even)));
-        attr_even = smem_even;
-    }
+    // per device and size dependent: set on every solve (a host-side call of ~1 us; no process-wide cache)
+    CSLAM_CUDA(cudaFuncSetAttribute(bcr_odd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_odd)));
+    CSLAM_CUDA(cudaFuncSetAttribute(bcr_even_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_even)));
     int launched = 0;
     const long long init_n = R.N * bb + (long long)R.N * R.b;
     bcr_init_kernel<<<int(std::min<long long>((init_n + 255) / 256, 4 * 148)), 256, 0, st>>>(R, V.Tb, V.fa, V.fb);
@@ -872,11 +868,7 @@ static int bcr_solve(cudaStream_t st, const BandView& V, const BandScratch& K, i
     }
     bcr_odd_kernel<<<1, BCR_T, smem_odd, st>>>(R, 0, 1, 0);  // the last row standing
     const size_t smem_bs = sizeof(double) * (3 * size_t(bb) + 3 * R.b);
-    static size_t attr_bs = 0;
-    if (smem_bs > attr_bs) {
-        CSLAM_CUDA(cudaFuncSetAttribute(bcr_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bs)));
-        attr_bs = smem_bs;
-    }
+    CSLAM_CUDA(cudaFuncSetAttribute(bcr_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bs)));
     bcr_backsub_kernel<<<1, 256, smem_bs, st>>>(R, 0, 1, 0);
     launched += 2;
     for (int l = nl - 1; l >= 0; --l) {

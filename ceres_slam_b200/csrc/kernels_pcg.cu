@@ -440,16 +440,20 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 
 void launch_pcg_persistent(cudaStream_t s, const PcgBufs& B, double* pbuf2, double* rec3, double q_tol, double r_tol,
                            int min_iters, int max_iters, int reset_period) {
-    static int max_blocks_per_sm = 0, n_sms = 0;
+    static PerDevice cache;   // value = SM count, value2 = resident CTAs per SM, both of the current device
     const int smem = int(sizeof(PcgSmem));
-    if (!max_blocks_per_sm) {
-        int dev = 0;
-        CSLAM_CUDA(cudaGetDevice(&dev));
-        CSLAM_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    const int dev = PerDevice::current();
+    if (cache.first_use(dev)) {
+        int sms = 0, per_sm = 0;
+        CSLAM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         CSLAM_CUDA(cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CSLAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, pcg_persistent_kernel, PCG_THREADS, smem));
-        if (max_blocks_per_sm < 1) throw CudaError("pcg_persistent_kernel does not fit on an SM");
+        CSLAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_persistent_kernel, PCG_THREADS, smem));
+        if (per_sm < 1) throw CudaError("pcg_persistent_kernel does not fit on an SM");
+        cache.value[dev] = sms;
+        cache.value2[dev] = per_sm;
+        cache.mark(dev);
     }
+    const int n_sms = cache.value[dev];
     CSLAM_CUDA(cudaMemsetAsync(B.ps, 0, PS_COUNT * sizeof(double), s));
     CSLAM_CUDA(cudaMemsetAsync(rec3, 0, 3 * sizeof(Rec) + 16, s));
     // at least 32 block rows per CTA (one per warp); never more CTAs than can be co-resident

@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(PH_TILE)
 void launch_phong_eval(cudaStream_t s, const PhongView& v, double* r_int, double* J_int, double* r_normal,
                        double* Jpose_normal, double* Jn_normal, double* cost) {
     if (v.n <= 0) return;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDevice attr_done;
+    const int dev_ = PerDevice::current();
+    if (attr_done.first_use(dev_)) {
         CSLAM_CUDA(cudaFuncSetAttribute(phong_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PH_SMEM)));
-        attr_done = true;
+        attr_done.mark(dev_);
     }
     const long long tiles = (v.n + PH_TILE - 1) / PH_TILE;
     const int grid = int(tiles < 3ll * 148 ? tiles : 3ll * 148);  // persistent: 3 CTAs per SM (registers)

@@ -938,11 +938,8 @@ void launch_phong_border_solve(cudaStream_t s, int n_g, int nf6, const double* S
                                      cudaMemcpyDeviceToDevice, s));
     }
     const size_t smem = size_t(n_g) * (n_g + 1) * sizeof(double);
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
+    if (smem > 48 * 1024)   // per device: no process-wide cache
         CSLAM_CUDA(cudaFuncSetAttribute(phong_border_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        attr_set = smem;
-    }
     phong_border_solve_kernel<<<1, 128, smem, s>>>(n_g, T, yg, ps);
     count_launch();
     if (nf6 > 0) {

@@ -916,6 +916,9 @@ void append(std::vector<T>& dst, const T* src, size_t n) {
 
 bool Engine::window_eligible() const {
     if (opt.window_path == 1 || opt.trust_region_strategy != 0) return false;
+    // the one-CTA window kernel has no lighting terms, no box projection and no held positions:
+    // such problems take the generic engine (also inside cslam_solve_batch)
+    if (lighting_in_solve() || bounded || hold_positions) return false;
     if (n_ranks > 1 || opt.linear_solver != 0) return false;
     if (n_poses == 0 || n_poses > uint32_t(WIN_PMAX)) return false;
     if (suns.size() + priors.size() > size_t(WIN_THREADS)) return false;

@@ -304,6 +304,9 @@ cslam_status cslam_get_launch_count(uint64_t* count);
 
 /* Multi-GPU (config 5): every rank holds all poses and its own shard of landmarks and
  * observations; each Schur build is followed by one all-reduce of [S | rhs | scalars].
+ * cslam_solve / cslam_download are then COLLECTIVE calls (every rank of the communicator makes
+ * them) and every rank's pose and point arrays receive the complete solution: the landmarks a
+ * rank does not own are gathered from their owners before the write-back.
  * The 128-byte id comes from rank 0 and is distributed by the launcher (torch.distributed). */
 cslam_status cslam_comm_unique_id(uint8_t id[128]);
 cslam_status cslam_attach_comm(cslam_problem* p, int n_ranks, int rank, const uint8_t id[128]);

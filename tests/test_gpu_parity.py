@@ -795,3 +795,44 @@ def test_device_structure_analysis_matches_host(product, monkeypatch, case):
     assert sd.num_iterations == sh.num_iterations
     assert abs(sd.final_cost - sh.final_cost) <= 1e-9 * abs(sh.final_cost)
     assert rel_err(poses_d, poses_h) < 1e-8 and rel_err(points_d, points_h) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_matches_single_gpu(product, world):
+    """tests/multi_gpu_check.py under torch.distributed.run: landmark shards + NCCL all-reduce of the
+    reduced system give the single-GPU iterates (exact solves 1e-9, PCG 1e-5), every rank returns the
+    complete solution.  Skipped when fewer than `world` GPUs are visible."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29540 + world), os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_solve_batch_routes_lighting_problems_to_the_generic_engine(product):
+    """A problem small enough for the one-CTA window kernel (<= 8 poses) that carries lighting blocks,
+    bounds or held positions is NOT window-eligible: inside cslam_solve_batch it takes the generic engine
+    and gives exactly what cslam_solve gives (normals, materials and light are updated)."""
+    from ceres_slam_b200.problem import solve_batch
+    kw = dict(bounds=True, max_num_iterations=5, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    tr = syn.add_phong(syn.make_track(8, 20, 4, seed=91), shared_textures=True)
+    p1, st1 = syn.build_phong_problem(tr, **kw)
+    s1 = p1.solve()
+    p2, st2 = syn.build_phong_problem(tr, **kw)
+    w = syn.window_of(syn.make_track(30, 10, 5, seed=92), 3, 6)
+    p3, poses3, points3 = syn.build_problem(w, max_num_iterations=5)   # a plain window next to it in the same batch
+    s2, s3 = solve_batch([p2, p3])
+    assert s2.num_iterations == s1.num_iterations == 5
+    assert s2.final_cost == s1.final_cost
+    for k in ("poses", "points", "normals", "phong", "textures", "light"):
+        assert np.array_equal(st1[k], st2[k]), k
+    assert np.abs(st2["normals"] - tr["normals"]).max() > 0 and np.abs(st2["phong"] - tr["phong"]).max() > 0
+    assert s3.final_cost < s3.initial_cost
