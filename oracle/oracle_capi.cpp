@@ -310,6 +310,14 @@ int cslam_oracle_get_iteration_log(const cslam_oracle_problem* p, double* rows, 
     return CSLAM_OK;
 }
 
+// wall-clock stamp (seconds, steady clock) of every logged iteration row of the last solve
+int cslam_oracle_get_iteration_seconds(const cslam_oracle_problem* p, double* t, int max_rows, int* n_rows) {
+    const int n = int(p->last.row_seconds.size());
+    if (n_rows) *n_rows = n;
+    for (int i = 0; i < n && i < max_rows; ++i) t[i] = p->last.row_seconds[i];
+    return CSLAM_OK;
+}
+
 // ---- front end: 3-point RANSAC point-cloud alignment (point_cloud_aligner.cpp:64-136) ---------------
 int cslam_oracle_ransac_align(int, uint32_t n_pairs, const uint32_t* offsets, const double* pts0, const double* pts1,
                               const double* intr5, uint32_t num_iters, double thresh, int rng_variant, double* T12_out,

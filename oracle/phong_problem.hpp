@@ -610,7 +610,7 @@ class PhongProblem {
         row.cost = x_cost;
         row.gradient_max_norm = gradient_max_norm;
         row.radius = radius;
-        sum.rows.push_back(row);
+        sum.push_row(row);
         bool step_ok_prev = false;
         auto finish = [&](int type, int reason) {
             sum.termination_type = type;
@@ -690,14 +690,14 @@ class PhongProblem {
                 row.gradient_max_norm = gradient_max_norm;
                 if (++invalid_steps >= opt.max_num_consecutive_invalid_steps) {
                     row.radius = radius;
-                    sum.rows.push_back(row);
+                    sum.push_row(row);
                     finish(FAILURE, R_INVALID_STEPS);
                     break;
                 }
                 radius = radius / decrease_factor;
                 decrease_factor *= 2.0;
                 row.radius = radius;
-                sum.rows.push_back(row);
+                sum.push_row(row);
                 continue;
             }
             invalid_steps = 0;
@@ -767,7 +767,7 @@ class PhongProblem {
                 row.cost = x_cost;
                 row.gradient_max_norm = gradient_max_norm;
                 row.radius = radius;
-                sum.rows.push_back(row);
+                sum.push_row(row);
                 finish(CONVERGENCE, R_PARAMETER_TOL);
                 break;
             }
@@ -775,7 +775,7 @@ class PhongProblem {
                 row.cost = x_cost;
                 row.gradient_max_norm = gradient_max_norm;
                 row.radius = radius;
-                sum.rows.push_back(row);
+                sum.push_row(row);
                 finish(CONVERGENCE, R_FUNCTION_TOL);
                 break;
             }
@@ -824,7 +824,7 @@ class PhongProblem {
             row.cost = x_cost;
             row.gradient_max_norm = gradient_max_norm;
             row.radius = radius;
-            sum.rows.push_back(row);
+            sum.push_row(row);
         }
         sum.num_iterations = iteration;
         sum.final_cost = minimum_cost + fixed_cost;

@@ -11,6 +11,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <complex>
 #include <cstdint>
 #include <cstring>
@@ -74,6 +75,12 @@ struct Summary {
     double final_radius = 0;
     int total_linear_iterations = 0;
     std::vector<IterationRow> rows;
+    std::vector<double> row_seconds;  // wall clock (steady) when each row was logged: bench.py's CPU arm times
+                                      // K iterations after W warm-up iterations inside ONE solve
+    void push_row(const IterationRow& r) {
+        rows.push_back(r);
+        row_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count());
+    }
 };
 
 inline void parallel_for(size_t n, int nthreads, const std::function<void(size_t, size_t, int)>& fn) {
@@ -933,7 +940,7 @@ class Problem {
         row.gradient_max_norm = gradient_max_norm;
         row.radius = radius;
         row.step_is_valid = row.step_is_successful = 0;
-        sum.rows.push_back(row);
+        sum.push_row(row);
         bool step_ok_prev = false;
 
         auto finish = [&](int type, int reason) {
@@ -1241,7 +1248,7 @@ class Problem {
                 row.gradient_max_norm = gradient_max_norm;
                 if (++invalid_steps >= opt.max_num_consecutive_invalid_steps) {
                     row.radius = radius;
-                    sum.rows.push_back(row);
+                    sum.push_row(row);
                     finish(FAILURE, R_INVALID_STEPS);
                     break;
                 }
@@ -1254,7 +1261,7 @@ class Problem {
                     reuse_diagonal = true;
                 }
                 row.radius = radius;
-                sum.rows.push_back(row);
+                sum.push_row(row);
                 continue;
             }
             invalid_steps = 0;
@@ -1283,7 +1290,7 @@ class Problem {
                 row.cost = x_cost;
                 row.gradient_max_norm = gradient_max_norm;
                 row.radius = radius;
-                sum.rows.push_back(row);
+                sum.push_row(row);
                 finish(CONVERGENCE, R_PARAMETER_TOL);
                 break;
             }
@@ -1292,7 +1299,7 @@ class Problem {
                 row.cost = x_cost;
                 row.gradient_max_norm = gradient_max_norm;
                 row.radius = radius;
-                sum.rows.push_back(row);
+                sum.push_row(row);
                 finish(CONVERGENCE, R_FUNCTION_TOL);
                 break;
             }
@@ -1358,7 +1365,7 @@ class Problem {
             row.cost = x_cost;
             row.gradient_max_norm = gradient_max_norm;
             row.radius = radius;
-            sum.rows.push_back(row);
+            sum.push_row(row);
         }
         sum.num_iterations = iteration;
         sum.final_cost = minimum_cost;

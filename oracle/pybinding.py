@@ -22,6 +22,7 @@ REF_SO = os.path.join(HERE, "_ref", "libcslam_ref.so")
 REFERENCE_INCLUDE = "/root/reference/include"
 
 _ORACLE_ONLY = {
+    "get_iteration_seconds": (C.c_int, [capi._h, _dp, C.c_int, capi._ip]),
     "poly_root_real_parts": (C.c_int, [_dp, C.c_int, _dp]),
     "dogleg_boundary_minimum": (C.c_int, [_dp, _dp, C.c_double, _dp]),
     "ransac_draws": (None, [C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p]),
@@ -113,6 +114,16 @@ class OracleProblem(BAProblem):
     @staticmethod
     def _library():
         return load_oracle()
+
+    def iteration_seconds(self):
+        """Steady-clock stamp of every row of iteration_log() (row 0 = the initial evaluation)."""
+        import numpy as np
+        n = C.c_int(0)
+        self.lib.get_iteration_seconds(self._h, None, 0, C.byref(n))
+        t = np.zeros(n.value)
+        if n.value:
+            self.lib.get_iteration_seconds(self._h, capi.dptr(t), n.value, C.byref(n))
+        return t
 
 
 def build_problem(track, **kw):
