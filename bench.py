@@ -350,8 +350,8 @@ def _cut_states(tr, k0, n):
 def _driver_timing(stderr):
     out = []
     for line in stderr.splitlines():
-        if line.startswith("cslam_b200 timing:"):
-            kv = dict(t.split("=") for t in line.split(":", 1)[1].split())
+        if "cslam_b200 timing:" in line:      # (may follow an unterminated progress message on the same line)
+            kv = dict(t.split("=") for t in line.split("cslam_b200 timing:", 1)[1].split())
             out.append((int(kv["windows"]), float(kv["loop_s"]), kv.get("pass", "vo")))
     return out
 

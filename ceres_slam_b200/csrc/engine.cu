@@ -1601,7 +1601,19 @@ void Engine::schur_pass() {
     prof_begin(CSLAM_K_SCHUR);
     d_red.zero(stream);
     if (ph.active) {
-        launch_phong_build(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, dg, phong_system(), true, ph.max_track);
+        // grouped vertices: one CTA per work item, the 6L x 6L tile of the group in DMMA accumulators
+        // (CSLAM_PHONG_GROUPED=0: every vertex through the warp-per-vertex kernel, for A/B runs and tests)
+        static const bool use_grouped = [] {
+            const char* e = std::getenv("CSLAM_PHONG_GROUPED");
+            return !(e && std::atoi(e) == 0);
+        }();
+        const PhongSolveView pq = phong_solve_view(ph.normals.p, ph.gx.p);
+        int first_rest = 0;
+        if (use_grouped && !item_group_h.empty()) {
+            launch_phong_build_grouped(stream, v, pq, group_view(), n_items_small, dg, phong_system());
+            first_rest = n_lm_grouped;
+        }
+        launch_phong_build(stream, v, pq, first_rest, n_lm, dg, phong_system(), true, ph.max_track);
     } else {
         launch_schur(v, dg);
         if (rank == 0)

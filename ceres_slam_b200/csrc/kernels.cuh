@@ -95,6 +95,9 @@ void launch_phong_eval(cudaStream_t s, const PhongView& v, double* r_int, double
                        double* Jpose_normal, double* Jn_normal, double* cost);
 
 // K2p / K4p — joint lighting solve (kernels_phong_solve.cu)
+// K2p for grouped vertices (kernels_phong_grouped.cu): items [0, n_items_small) have L <= 10, the rest L <= 16
+void launch_phong_build_grouped(cudaStream_t s, const DevView& v, const PhongSolveView& q, const GroupView& g, int n_items_small,
+                                LmDiag dg, const PhongSystem& o);
 void launch_phong_build(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
                         const PhongSystem& o, bool schur, int max_track_len);
 void launch_phong_gfinalize(cudaStream_t s, const PhongSolveView& q, LmDiag dg, double* Sgg, double* bg, const double* hg,

@@ -34,9 +34,10 @@ def test_c5_scaled_default_paths_match_oracle(product):
         sg = pg.solve()
     finally:
         del os.environ["CSLAM_GPU_STRUCTURE_MIN"]
-    # every landmark of this workload falls into a group of identical camera lists: the grouped (DMMA) kernel ran
+    # (nearly) every landmark of this workload falls into a group of identical camera lists: the grouped (DMMA)
+    # kernel ran on them, the generic kernel on the few whose list is unique after the visibility filter
     info = pg.analyze()
-    assert info["n_grouped_landmarks"] == info["n_landmarks"] > 90_000 and info["n_groups"] > 900
+    assert info["n_landmarks"] > 90_000 and info["n_grouped_landmarks"] >= 0.99 * info["n_landmarks"] and info["n_groups"] > 900
     po, poses_o, points_o = orc.build_problem(tr, num_threads=os.cpu_count() or 8, **kw)
     so = po.solve()
     check_lm((pg, sg, poses_g, points_g), (po, so, poses_o, points_o))

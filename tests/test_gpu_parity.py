@@ -831,8 +831,9 @@ def test_solve_batch_routes_lighting_problems_to_the_generic_engine(product):
     p3, poses3, points3 = syn.build_problem(w, max_num_iterations=5)   # a plain window next to it in the same batch
     s2, s3 = solve_batch([p2, p3])
     assert s2.num_iterations == s1.num_iterations == 5
-    assert s2.final_cost == s1.final_cost
+    # (same kernels, same order of work; the RED.ADD accumulation order differs from run to run)
+    assert abs(s2.final_cost - s1.final_cost) <= 1e-7 * s1.final_cost
     for k in ("poses", "points", "normals", "phong", "textures", "light"):
-        assert np.array_equal(st1[k], st2[k]), k
+        assert np.abs(st1[k] - st2[k]).max() <= 1e-6 * max(1.0, np.abs(st1[k]).max()), k
     assert np.abs(st2["normals"] - tr["normals"]).max() > 0 and np.abs(st2["phong"] - tr["phong"]).max() > 0
     assert s3.final_cost < s3.initial_cost
