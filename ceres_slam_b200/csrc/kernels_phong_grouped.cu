@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(PG_THREADS)
     extern __shared__ __align__(16) double smem_pg[];
     double* Zt = smem_pg;                         // [PG_K][LD]   Zt[k][row] = Z[row][k]
     double* sAcc = Zt + PG_K * LD;                // [PG_NV][LMAX][PG_SLOT_ACC]
+    double* sW = sAcc + PG_NV * LMAX * PG_SLOT_ACC;   // [36][PG_THREADS]  W = A_c^T A_v of the lane's observation
+    double* sTile = sW + 36 * PG_THREADS;         // [2 NACC][PG_THREADS]  the MMA accumulators, parked during `produce`
     __shared__ double s_pose_unused[1];
     __shared__ double sG[PG_NV][56];              // a vertex's shared-block contributions, staged for the REDs
     __shared__ int s_free[16];
@@ -121,9 +123,8 @@ __global__ void __launch_bounds__(PG_THREADS)
         for (int k = tid; k < P; k += PG_THREADS) s_blk[k] = blk[k];
         for (int k = tid; k < PG_K * LD; k += PG_THREADS) Zt[k] = 0.0;
         for (int k = tid; k < PG_NV * LMAX * PG_SLOT_ACC; k += PG_THREADS) sAcc[k] = 0.0;
-        double acc[NACC][2];
 #pragma unroll
-        for (int u = 0; u < NACC; ++u) acc[u][0] = acc[u][1] = 0.0;
+        for (int u = 0; u < 2 * NACC; ++u) sTile[u * PG_THREADS + tid] = 0.0;
         __syncthreads();
 
         for (int rb = 0; rb < nj; rb += PG_NV) {
@@ -148,6 +149,30 @@ __global__ void __launch_bounds__(PG_THREADS)
 #pragma unroll
                     for (int k = 0; k < 7; ++k) cost += 0.5 * r7[k] * r7[k];
                     vertex_normal_eq(ob, r7, V21, gvv);
+                    if (ob.f >= 0) {
+                        // everything that needs the pose columns, now: W = A_c^T A_v (parked in shared memory),
+                        // U = A_c^T A_c and the gradient (slot accumulators).  The pose Jacobians die here.
+                        int u = 0;
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                            for (int b = 0; b < 3; ++b) {
+                                sW[(6 * a + b) * PG_THREADS + tid] = ob.Jcs[a] * ob.S[b] + ob.Jcs[6 + a] * ob.S[3 + b] +
+                                                                     ob.Jcs[12 + a] * ob.S[6 + b] + ob.JIc[a] * ob.ip[b];
+                                sW[(6 * a + 3 + b) * PG_THREADS + tid] = ob.JIc[a] * ob.in[b] + ob.JNc[a] * ob.N[b] +
+                                                                         ob.JNc[6 + a] * ob.N[3 + b] + ob.JNc[12 + a] * ob.N[6 + b];
+                            }
+#pragma unroll
+                            for (int b = a; b < 6; ++b, ++u)
+                                myAcc[u] += ob.Jcs[a] * ob.Jcs[b] + ob.Jcs[6 + a] * ob.Jcs[6 + b] + ob.Jcs[12 + a] * ob.Jcs[12 + b] +
+                                            ob.JIc[a] * ob.JIc[b] + ob.JNc[a] * ob.JNc[b] + ob.JNc[6 + a] * ob.JNc[6 + b] +
+                                            ob.JNc[12 + a] * ob.JNc[12 + b];
+                            const double ga = ob.Jcs[a] * r7[0] + ob.Jcs[6 + a] * r7[1] + ob.Jcs[12 + a] * r7[2] + ob.JIc[a] * r7[3] +
+                                              ob.JNc[a] * r7[4] + ob.JNc[6 + a] * r7[5] + ob.JNc[12 + a] * r7[6];
+                            myAcc[21 + a] += ga;
+                            myAcc[27 + a] += ga;      // reduced rhs: - Z t follows once the vertex block is factored
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 21; ++k) V21[k] = 0.0;
@@ -250,47 +275,28 @@ __global__ void __launch_bounds__(PG_THREADS)
             if (lv < L) {
                 double* zc = Zt + (6 * qv) * LD + 6 * lv;   // Zt[6 qv + c][6 lv + a]
                 if (act && pd && ob.f >= 0) {
-                    double Z[36];
 #pragma unroll
                     for (int a = 0; a < 6; ++a) {
-                        double Wr[6];
+                        double Wr[6], Zr[6];
 #pragma unroll
-                        for (int b = 0; b < 3; ++b) {
-                            Wr[b] = ob.Jcs[a] * ob.S[b] + ob.Jcs[6 + a] * ob.S[3 + b] + ob.Jcs[12 + a] * ob.S[6 + b] +
-                                    ob.JIc[a] * ob.ip[b];
-                            Wr[3 + b] = ob.JIc[a] * ob.in[b] + ob.JNc[a] * ob.N[b] + ob.JNc[6 + a] * ob.N[3 + b] +
-                                        ob.JNc[12 + a] * ob.N[6 + b];
-                        }
-#pragma unroll
-                        for (int cc = 0; cc < 6; ++cc) {
-                            double s = 0.0;
-#pragma unroll
-                            for (int b = 0; b <= cc; ++b) s += Wr[b] * A[6 * cc + b];
-                            Z[6 * a + cc] = s;
-                            zc[cc * LD + a] = s;
-                        }
-                    }
-                    int u = 0;
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-                        for (int b = a; b < 6; ++b, ++u)
-                            myAcc[u] += ob.Jcs[a] * ob.Jcs[b] + ob.Jcs[6 + a] * ob.Jcs[6 + b] + ob.Jcs[12 + a] * ob.Jcs[12 + b] +
-                                        ob.JIc[a] * ob.JIc[b] + ob.JNc[a] * ob.JNc[b] + ob.JNc[6 + a] * ob.JNc[6 + b] +
-                                        ob.JNc[12 + a] * ob.JNc[12 + b];
-                        const double ga = ob.Jcs[a] * r7[0] + ob.Jcs[6 + a] * r7[1] + ob.Jcs[12 + a] * r7[2] + ob.JIc[a] * r7[3] +
-                                          ob.JNc[a] * r7[4] + ob.JNc[6 + a] * r7[5] + ob.JNc[12 + a] * r7[6];
+                        for (int b = 0; b < 6; ++b) Wr[b] = sW[(6 * a + b) * PG_THREADS + tid];
                         double zt = 0.0;
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) zt += Z[6 * a + k] * tq[k];
-                        myAcc[21 + a] += ga;
-                        myAcc[27 + a] += ga - zt;
+                        for (int cc = 0; cc < 6; ++cc) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int b = 0; b <= cc; ++b) sacc += Wr[b] * A[6 * cc + b];
+                            Zr[cc] = sacc;
+                            zc[cc * LD + a] = sacc;
+                            zt += sacc * tq[cc];
+                        }
+                        myAcc[27 + a] -= zt;
 #pragma unroll
                         for (int k = 0; k < 7; ++k) {
-                            double s = ob.JIc[a] * ob.ag[k];
+                            double sb = ob.JIc[a] * ob.ag[k];
 #pragma unroll
-                            for (int b = 0; b < 6; ++b) s -= Z[6 * a + b] * GA[6 * k + b];
-                            red_add(&o.Scg[(long long)c.gi[k] * nf6 + 6 * ob.f + a], s);
+                            for (int b = 0; b < 6; ++b) sb -= Zr[b] * GA[6 * k + b];
+                            red_add(&o.Scg[(long long)c.gi[k] * nf6 + 6 * ob.f + a], sb);
                         }
                     }
                 } else {
@@ -302,6 +308,12 @@ __global__ void __launch_bounds__(PG_THREADS)
             }
             __syncthreads();
             // ================= consume: tile += Z Z^T over the round's 48 columns =================
+            double acc[NACC][2];
+#pragma unroll
+            for (int u = 0; u < NACC; ++u) {
+                acc[u][0] = sTile[(2 * u) * PG_THREADS + tid];
+                acc[u][1] = sTile[(2 * u + 1) * PG_THREADS + tid];
+            }
 #pragma unroll 2
             for (int ks = 0; ks < PG_K / 4; ++ks) {
                 const double* zr = Zt + (4 * ks + ft) * LD + fg;
@@ -324,6 +336,11 @@ __global__ void __launch_bounds__(PG_THREADS)
                     }
                     dmma884(acc[u][0], acc[u][1], a, zr[8 * J]);
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < NACC; ++u) {
+                sTile[(2 * u) * PG_THREADS + tid] = acc[u][0];
+                sTile[(2 * u + 1) * PG_THREADS + tid] = acc[u][1];
             }
             __syncthreads();
         }
@@ -350,7 +367,7 @@ __global__ void __launch_bounds__(PG_THREADS)
                 if (R > Cc || Cc >= 6 * L) continue;      // upper storage; rows / columns beyond the tile are padding
                 const int sa = R / 6, sb = Cc / 6;
                 const int e = s_blk[sa * L - sa * (sa - 1) / 2 + (sb - sa)];
-                if (e >= 0) red_add(&o.S[36ll * e + 6 * (R - 6 * sa) + (Cc - 6 * sb)], -acc[u][h]);
+                if (e >= 0) red_add(&o.S[36ll * e + 6 * (R - 6 * sa) + (Cc - 6 * sb)], -sTile[(2 * u + h) * PG_THREADS + tid]);
             }
         }
         for (int idx = tid; idx < L * PG_SLOT_ACC; idx += PG_THREADS) {
@@ -382,7 +399,9 @@ void launch_pg(cudaStream_t s, const DevView& v, const PhongSolveView& q, const 
                const PhongSystem& o) {
     if (hi <= lo) return;
     constexpr int LD = 8 * NT + 4, LMAX = NT == 8 ? 10 : 16;
-    const size_t smem = sizeof(double) * (size_t(PG_K) * LD + size_t(PG_NV) * LMAX * PG_SLOT_ACC);
+    constexpr int NACC = NT == 8 ? 9 : 21;
+    const size_t smem = sizeof(double) * (size_t(PG_K) * LD + size_t(PG_NV) * LMAX * PG_SLOT_ACC + 36 * size_t(PG_THREADS) +
+                                          2 * size_t(NACC) * PG_THREADS);
     static PerDevice attr;
     const int dev = PerDevice::current();
     if (attr.first_use(dev)) {

@@ -1,5 +1,6 @@
 """Where a sequential sliding window's wall time goes on the host side of the C ABI (configs 1/2)."""
-import time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from ceres_slam_b200 import synthetic as syn, initial_guess as ig
