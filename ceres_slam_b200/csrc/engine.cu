@@ -1231,8 +1231,8 @@ void Engine::plan_band_solver() {
     // leaves cost ~3 us per block row; the separator chain ~2.5 us per separator row when factored
     // as a band on one CTA, ~45 us per level of the cyclic reduction
     int P = opt.band_leaves > 0 ? opt.band_leaves
-                                : (band_sep == 2 ? 148 : int(std::lround(std::sqrt(0.8 * double(n) / W))));
-    P = std::min(P, band_sep == 2 ? 444 : 148);
+                                : (band_sep >= 2 ? 148 : int(std::lround(std::sqrt(0.8 * double(n) / W))));
+    P = std::min(P, band_sep >= 2 ? 444 : 148);
     P = std::min(P, n / (4 * W));
     P = std::max(P, (n + 3499) / 3500);
     P = std::max(P, 1);

@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(BL_THREADS) band_leaf_kernel(BandView B) {
             else
                 v = Awin[((j % W1) * W1 + (i % W1)) * 36 + 6 * (Cc % 6) + (R % 6)];
             B.Ta[(long long)p * b * b + idx] = v;
-            B.Ca[(long long)p * b * b + idx] = has_left ? Gwin[((i % W1) * 6 + R % 6) * GC + (kSpike ? 1 + Cc : 0)] : 0.0;
+            // cyclic reduction (second generation) reads the coupling of an even separator transposed
+            const int cidx = (B.sep_solver == 2 && W <= 9 && !(p & 1)) ? Cc * b + R : idx;
+            B.Ca[(long long)p * b * b + cidx] = has_left ? Gwin[((i % W1) * 6 + R % 6) * GC + (kSpike ? 1 + Cc : 0)] : 0.0;
         }
         for (int R = tid; R < b; R += BL_THREADS) B.fa[(long long)p * b + R] = Gwin[(((ie + R / 6) % W1) * 6 + R % 6) * GC];
     }
@@ -835,6 +837,391 @@ __global__ void __launch_bounds__(256) bcr_backsub_kernel(BcrView R, int first, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cyclic reduction, second generation (sep_solver == 2).  One level used to cost ~65 us (odd 34 +
+// even 24 + back-substitution 7): everything in it is latency, so the kernels are organised around
+// the one chain that cannot be shortened — the B dependent pivots of the B x B Cholesky.
+//
+// bcr_odd2_kernel<B>: the first (B+31)/32 warps own the ROWS of D_i in registers (lane r: a[c] =
+//   D[r][c], c <= r, statically indexed because the pivot loop is fully unrolled) and run a scalar
+//   right-looking Cholesky whose per-pivot chain is  1/L_kk broadcast -> l = a[k] / L_kk ->
+//   diag -= l^2 -> rsqrt  (the row's own diagonal lives in a register of its own, so the next pivot
+//   never waits for shared memory); the rank-1 update of the other columns is issued behind the
+//   rsqrt of the next pivot and fills its latency.  Column k of L is published in shared memory
+//   (Lt[k][r]) together with a progress counter (release / acquire).
+//   The border [E_left | E_right^T | f | I] is NOT part of that factorisation: every border column
+//   belongs to one thread of the remaining warps, which keeps the whole column (B doubles) in
+//   registers and performs the forward substitution x = L^-1 g right-looking, trailing the factor
+//   warps by one pivot: x_k *= 1/L_kk, x_r -= L_rk x_k (r > k) with L_rk broadcast from shared
+//   memory.  No barrier between the two roles, no shared-memory traffic for the border itself.
+// bcr_even2_kernel<B>: the three B x B products of a surviving row are cut into (row, D | E,
+//   strip-of-rows) tasks, one CTA each, so that late levels (a handful of rows) still use the chip.
+// The coupling block E[j] is stored row-major when row j is eliminated at the level it is built
+//   for ("odd": read as E_left) and transposed otherwise (read as E_right^T by its odd neighbour):
+//   both reads of the odd kernel are then coalesced across the column threads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double id = rsqrt(d);
+    return id * (1.5 - 0.5 * d * id * id);
+}
+
+template <int B>
+struct Odd2 {
+    static constexpr int FW = (B + 31) / 32;        // factor warps (B <= 64)
+    static constexpr int R0 = B < 32 ? B : 32;      // rows of warp 0
+    static constexpr int NCOL = 3 * B + 1;          // border columns
+    static constexpr int BW = (NCOL + 31) / 32;     // border warps
+    static constexpr int THREADS = 32 * (FW + BW);
+};
+
+// Pivots [k_lo, k_hi) of one factor warp; lane = row `r` of D_i, NC = number of columns its rows can
+// reach (32 for warp 0, B for warp 1).  Registers: b[j] = A[r][k - 1 + j], not yet updated by pivot
+// k-1 — the rank-1 update writes b[j] <- b[j+1] - l L, i.e. the row slides down by one register per
+// pivot, so every register index is static while k is a run-time loop variable: the body is ~100
+// instructions and stays in the instruction cache (a fully unrolled version of this kernel spent
+// most of its time fetching instructions).
+//   CHAIN: the pivot row belongs to this warp.  The chain per pivot is  shuffle 1/L_kk and L_{k,k-1}
+//     from the pivot lane -> l = a / L_kk -> diag -= l^2 -> rsqrt;  the rest of the previous pivot's
+//     update is issued behind the rsqrt and hides in its latency.  Nothing on the chain touches
+//     shared memory or a CTA barrier.
+//   !CHAIN (warp 1 while the pivot is still among warp 0's rows): waits for warp 0's column.
+// After publishing column k (Lt2 row k+1; 1/L of the next pivot in sInv) every lane arrives on
+// `done[k]`: consumers (warp 1, the border warps) wait on these single-use mbarriers — a hardware
+// wait, no polling traffic that would sit in front of the chain's own shared-memory accesses.
+template <int B, int NC, int WID, bool CHAIN>
+__device__ __forceinline__ void odd2_factor_phase(double (&b)[NC + 1], double& diag, double& lprev, double& nid, int k_lo,
+                                                  int k_hi, int r, int lane_base, bool act, double* Lt2, double* sInv,
+                                                  uint64_t* wait_on, uint64_t* done, int* s_bad) {
+    for (int k = k_lo; k < k_hi; ++k) {
+        const double* Lp = Lt2 + k * B;  // column k-1 of L from row k on (row 0 of Lt2 is zeros)
+        double id, lpo;
+        if (CHAIN) {
+            id = __shfl_sync(0xffffffffu, nid, k - lane_base);
+            lpo = __shfl_sync(0xffffffffu, lprev, k - lane_base);
+        } else {
+            // warp 0 has published column k-1 and 1 / L_kk — and column k as well, so that this warp's
+            // own arrival on done[k] tells the border that column k is complete
+            mbar_wait(wait_on + (k + 1 < Odd2<B>::R0 ? k + 1 : Odd2<B>::R0 - 1), 0);
+            id = sInv[k];
+            lpo = Lp[0];
+        }
+        const double a0 = b[1] - lprev * lpo;
+        const double l = a0 * id;
+        if (r > k) diag -= l * l;
+        if (CHAIN || k + 1 >= lane_base) nid = rsqrt_nr(diag);  // the next pivot's reciprocal root (row k+1 owns it)
+        b[0] = a0;
+#pragma unroll
+        for (int j = 1; j + 1 < WID; ++j) b[j] = b[j + 1] - lprev * Lp[j];
+        if (act && r > k) Lt2[(k + 1) * B + (r - k - 1)] = l;
+        if (r == k + 1) {
+            if (!(diag > 0.0) || !(diag < 1.7976931348623157e308)) *s_bad = 1;
+            sInv[k + 1] = nid;
+        }
+        __syncwarp();
+        mbar_arrive(done + k);
+        lprev = l;
+    }
+}
+
+// Border columns: x[j] = X[k + j]; pivot k finishes x[0], writes it out and slides the rest.
+template <int B, int WID>
+__device__ __forceinline__ void odd2_border_phase(double (&x)[B], int k_lo, int k_hi, const double* Lt2, const double* sInv,
+                                                  uint64_t* col_done, double* outp, int ostride) {
+    for (int k = k_lo; k < k_hi; ++k) {
+        mbar_wait(col_done + k, 0);
+        const double xk = x[0] * sInv[k];
+        if (outp) outp[(long long)k * ostride] = xk;
+        const double2* Lp = reinterpret_cast<const double2*>(Lt2 + (k + 1) * B);  // column k of L from row k+1 on
+#pragma unroll
+        for (int j = 0; j + 1 < WID; j += 2) {
+            const double2 lv = Lp[j >> 1];
+            x[j] = x[j + 1] - lv.x * xk;
+            if (j + 2 < WID) x[j + 1] = x[j + 2] - lv.y * xk;
+        }
+    }
+}
+
+// raw != 0: the level-0 inputs have not been combined yet (D = Ta - Tb, f = fa - fb).
+template <int B>
+__global__ void __launch_bounds__(Odd2<B>::THREADS, 1)
+    bcr_odd2_kernel(BcrView R, int first, int step, int s, int raw, const double* __restrict__ Tb,
+                    const double* __restrict__ fa, const double* __restrict__ fb) {
+    using C = Odd2<B>;
+    constexpr int FW = C::FW, R0 = C::R0;
+    // Lt2[(k + 1) * B + j] = L[k + 1 + j][k]; row 0 is zeros (pivot "-1"), one spare row behind
+    __shared__ __align__(16) double Lt2[(B + 2) * B];
+    __shared__ double sInv[B + 2];                 // 1 / L[k][k]
+    __shared__ __align__(8) uint64_t done0[B + 1];  // done0[k + 1]: warp 0 published column k; done0[0]: 1 / L_00
+    __shared__ __align__(8) uint64_t done1[B];      // done1[k]: warp 1 published column k (B > 32)
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i = first + blockIdx.x * step;
+    const bool has_l = s > 0 && i - s >= 0, has_r = s > 0 && i + s < R.N;
+    constexpr long long bb = (long long)B * B;
+    if (*R.fail) return;
+    if (tid == 0) s_bad = 0;
+    for (int j = tid; j < B + 1; j += C::THREADS) {
+        if (j < B) {
+            Lt2[j] = 0.0;
+            mbar_init(&done1[j], 32);
+        }
+        mbar_init(&done0[j], 32);
+    }
+    fence_mbar_init();
+    __syncthreads();
+    uint64_t* col_done = FW > 1 ? done1 : done0 + 1;  // what the border waits on: column k complete
+    const double* Di = R.D + i * bb;
+    const double* Tbi = Tb + i * bb;
+    if (warp == 0) {
+        // ---------------- factor warp 0: rows 0 .. R0-1, it never needs anything from other warps ----------------
+        const int r = lane;
+        const bool act = r < R0;
+        const int rr = act ? r : 0;
+        double b[R0 + 1];
+        b[0] = 0.0;
+#pragma unroll
+        for (int c = 0; c < R0; ++c) b[c + 1] = Di[c * B + rr];  // D symmetric: column read, coalesced over the lanes
+        double diag = Di[rr * B + rr];
+        if (raw) {
+#pragma unroll
+            for (int c = 0; c < R0; ++c) b[c + 1] -= Tbi[c * B + rr];
+            diag -= Tbi[rr * B + rr];
+        }
+        if (!act) diag = 1.0;
+        double nid = rsqrt_nr(diag);
+        if (r == 0) {
+            if (!(diag > 0.0) || !(diag < 1.7976931348623157e308)) s_bad = 1;
+            sInv[0] = nid;
+        }
+        __syncwarp();
+        mbar_arrive(done0);
+        double lprev = 0.0;
+        constexpr int KH = R0 / 2;
+        odd2_factor_phase<B, R0, R0 + 1, true>(b, diag, lprev, nid, 0, KH, r, 0, act, Lt2, sInv, nullptr, done0 + 1, &s_bad);
+        odd2_factor_phase<B, R0, R0 + 2 - KH, true>(b, diag, lprev, nid, KH, FW > 1 ? R0 - 1 : R0, r, 0, act, Lt2, sInv, nullptr,
+                                                    done0 + 1, &s_bad);
+        if (FW == 1 && lane == 0 && s_bad) *R.fail = 1;
+    } else if (FW > 1 && warp == 1) {
+        // ---------------- factor warp 1: rows 32 .. B-1; trails warp 0, then owns the chain ----------------
+        const int r = 32 + lane;
+        const bool act = r < B;
+        const int rr = act ? r : 0;
+        double b[B + 1];
+        b[0] = 0.0;
+#pragma unroll
+        for (int c = 0; c < B; ++c) b[c + 1] = Di[c * B + rr];
+        double diag = Di[rr * B + rr];
+        if (raw) {
+#pragma unroll
+            for (int c = 0; c < B; ++c) b[c + 1] -= Tbi[c * B + rr];
+            diag -= Tbi[rr * B + rr];
+        }
+        if (!act) diag = 1.0;
+        double nid = 1.0, lprev = 0.0;
+        odd2_factor_phase<B, B, B + 1, false>(b, diag, lprev, nid, 0, 16, r, 32, act, Lt2, sInv, done0, done1, &s_bad);
+        odd2_factor_phase<B, B, B + 1 - 15, false>(b, diag, lprev, nid, 16, 32, r, 32, act, Lt2, sInv, done0, done1, &s_bad);
+        odd2_factor_phase<B, B, B + 1 - 31, true>(b, diag, lprev, nid, 32, B, r, 32, act, Lt2, sInv, nullptr, done1, &s_bad);
+        if (lane == 0 && s_bad) *R.fail = 1;
+    } else {
+        // ---------------- border warps: one column of [E_left | E_right^T | f | I] per thread ----------------
+        const int col = 32 * (warp - FW) + lane;
+        double x[B];
+        double* outp = nullptr;
+        int ostride = B;
+        if (col < B) {
+            const double* El = R.E + i * bb;  // row-major
+#pragma unroll
+            for (int r = 0; r < B; ++r) x[r] = has_l ? El[r * B + col] : 0.0;
+            outp = R.A + i * bb + col;
+        } else if (col < 2 * B) {
+            const double* Ert = R.E + (long long)(i + s) * bb;  // stored transposed
+#pragma unroll
+            for (int r = 0; r < B; ++r) x[r] = has_r ? Ert[r * B + (col - B)] : 0.0;
+            outp = R.Bm + i * bb + (col - B);
+        } else if (col == 2 * B) {
+            if (raw) {
+#pragma unroll
+                for (int r = 0; r < B; ++r) x[r] = fa[(long long)i * B + r] - fb[(long long)i * B + r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < B; ++r) x[r] = R.f[(long long)i * B + r];
+            }
+            outp = R.g + (long long)i * B;
+            ostride = 1;
+        } else {
+#pragma unroll
+            for (int r = 0; r < B; ++r) x[r] = (r == col - 2 * B - 1) ? 1.0 : 0.0;
+            if (col < C::NCOL) outp = R.Li + i * bb + (col - 2 * B - 1);
+        }
+        constexpr int K1 = B / 3, K2 = 2 * B / 3;
+        odd2_border_phase<B, B>(x, 0, K1, Lt2, sInv, col_done, outp, ostride);
+        odd2_border_phase<B, B - K1>(x, K1, K2, Lt2, sInv, col_done, outp, ostride);
+        odd2_border_phase<B, B - K2>(x, K2, B, Lt2, sInv, col_done, outp, ostride);
+    }
+}
+
+// One CTA = (surviving row i = e * 2s, task D | E, strip of B / nstrip rows).
+//   task 0:  D_i[strip, :] -= Bm_{i-s}^T Bm_{i-s} + A_{i+s}^T A_{i+s},  f_i[strip] -= Bm_{i-s}^T g_{i-s} + A_{i+s}^T g_{i+s}
+//   task 1:  E(i, i-2s)[strip, :] = -Bm_{i-s}^T A_{i-s}
+template <int B>
+__global__ void __launch_bounds__(256) bcr_even2_kernel(BcrView R, int s, int nstrip, int raw, const double* __restrict__ Tb,
+                                                         const double* __restrict__ fa, const double* __restrict__ fb) {
+    extern __shared__ __align__(16) double smem_bcr[];
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % nstrip, task = (blockIdx.x / nstrip) & 1, e = blockIdx.x / (2 * nstrip);
+    const int i = e * 2 * s;
+    const bool has_l = i - s >= 0, has_r = i + s < R.N, has_ll = i - 2 * s >= 0;
+    constexpr long long bb = (long long)B * B;
+    if (*R.fail) return;
+    if (task == 1 && !has_ll) return;
+    double* X = smem_bcr;   // task 0: Bm of the left odd neighbour   task 1: the same
+    double* Y = X + B * B;  // task 0: A of the right odd neighbour   task 1: A of the left odd neighbour
+    double* gx = Y + B * B;
+    double* gy = gx + B;
+    const bool use_x = has_l, use_y = task == 0 ? has_r : has_l;
+    {
+        const double2* Xs = reinterpret_cast<const double2*>(R.Bm + (long long)(i - s) * bb);
+        const double2* Ys = reinterpret_cast<const double2*>(task == 0 ? R.A + (long long)(i + s) * bb : R.A + (long long)(i - s) * bb);
+        double2* X2 = reinterpret_cast<double2*>(X);
+        double2* Y2 = reinterpret_cast<double2*>(Y);
+        const double2 z = make_double2(0.0, 0.0);
+        for (int idx = tid; idx < B * B / 2; idx += 256) {
+            X2[idx] = use_x ? Xs[idx] : z;
+            Y2[idx] = use_y ? Ys[idx] : z;
+        }
+        if (task == 0)
+            for (int r = tid; r < B; r += 256) {
+                gx[r] = has_l ? R.g[(long long)(i - s) * B + r] : 0.0;
+                gy[r] = has_r ? R.g[(long long)(i + s) * B + r] : 0.0;
+            }
+    }
+    __syncthreads();
+    const int rs = B / nstrip, row0 = strip * rs;  // rs is a multiple of 6
+    constexpr int TC = B / 3;
+    const int ntile = (rs / 2) * TC;
+    for (int t = tid; t < ntile; t += 256) {
+        const int r0 = row0 + 2 * (t / TC), c0 = 3 * (t % TC);
+        double acc[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        if (task == 0) {
+#pragma unroll 3
+            for (int k = 0; k < B; ++k) {
+                const double* xr = X + k * B;
+                const double* yr = Y + k * B;
+                const double2 ax = *reinterpret_cast<const double2*>(xr + r0);
+                const double2 ay = *reinterpret_cast<const double2*>(yr + r0);
+                const double bx0 = xr[c0], bx1 = xr[c0 + 1], bx2 = xr[c0 + 2];
+                const double by0 = yr[c0], by1 = yr[c0 + 1], by2 = yr[c0 + 2];
+                acc[0][0] += ax.x * bx0 + ay.x * by0;
+                acc[0][1] += ax.x * bx1 + ay.x * by1;
+                acc[0][2] += ax.x * bx2 + ay.x * by2;
+                acc[1][0] += ax.y * bx0 + ay.y * by0;
+                acc[1][1] += ax.y * bx1 + ay.y * by1;
+                acc[1][2] += ax.y * bx2 + ay.y * by2;
+            }
+            double* Di = R.D + i * bb;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    const int idx = (r0 + u) * B + c0 + w;
+                    double d = Di[idx];
+                    if (raw) d -= Tb[i * bb + idx];
+                    Di[idx] = d - acc[u][w];
+                }
+        } else {
+#pragma unroll 3
+            for (int k = 0; k < B; ++k) {
+                const double* xr = X + k * B;
+                const double* yr = Y + k * B;
+                const double2 ax = *reinterpret_cast<const double2*>(xr + r0);
+                const double by0 = yr[c0], by1 = yr[c0 + 1], by2 = yr[c0 + 2];
+                acc[0][0] += ax.x * by0;
+                acc[0][1] += ax.x * by1;
+                acc[0][2] += ax.x * by2;
+                acc[1][0] += ax.y * by0;
+                acc[1][1] += ax.y * by1;
+                acc[1][2] += ax.y * by2;
+            }
+            // row-major when row i is eliminated at the next level (stride 2s), transposed otherwise
+            const bool odd_next = ((i / (2 * s)) & 1) != 0;
+            double* Ei = R.E + i * bb;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    const int rr = r0 + u, cc = c0 + w;
+                    Ei[odd_next ? rr * B + cc : cc * B + rr] = -acc[u][w];
+                }
+        }
+    }
+    if (task == 0) {
+        for (int r = row0 + tid; r < row0 + rs; r += 256) {
+            double ff = 0.0;
+            for (int k = 0; k < B; ++k) ff += X[k * B + r] * gx[k] + Y[k * B + r] * gy[k];
+            double f0 = raw ? fa[(long long)i * B + r] - fb[(long long)i * B + r] : R.f[(long long)i * B + r];
+            R.f[(long long)i * B + r] = f0 - ff;
+        }
+    }
+}
+
+template <int B>
+static int bcr2_solve(cudaStream_t st, const BandView& V, const BandScratch& K) {
+    BcrView R;
+    R.N = V.P - 1;
+    R.b = B;
+    const long long bb = (long long)B * B;
+    R.D = V.Ta;
+    R.E = V.Ca;
+    R.f = K.rhs2;
+    R.A = K.T2;
+    R.Bm = K.T2 + R.N * bb;
+    R.Li = K.L2;
+    R.g = K.X2;
+    R.y = K.y2;
+    R.fail = V.fail;
+    const size_t smem_even = sizeof(double) * (2 * size_t(bb) + 2 * B);
+    CSLAM_CUDA(cudaFuncSetAttribute(bcr_even2_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_even)));
+    int launched = 0;
+    int levels[32], nl = 0;
+    int raw = 1;
+    constexpr int W = B / 6;
+    for (int s = 1; s < R.N; s *= 2) {
+        const int n_odd = (R.N - s - 1) / (2 * s) + 1, n_even = (R.N - 1) / (2 * s) + 1;
+        bcr_odd2_kernel<B><<<n_odd, Odd2<B>::THREADS, 0, st>>>(R, s, 2 * s, s, raw, V.Tb, V.fa, V.fb);
+        int nstrip = 1;
+        for (int d = 1; d <= W; ++d)
+            if (W % d == 0 && n_even * 2 * d <= 444) nstrip = d;
+        bcr_even2_kernel<B><<<n_even * 2 * nstrip, 256, smem_even, st>>>(R, s, nstrip, raw, V.Tb, V.fa, V.fb);
+        raw = 0;
+        launched += 2;
+        levels[nl++] = s;
+    }
+    bcr_odd2_kernel<B><<<1, Odd2<B>::THREADS, 0, st>>>(R, 0, 1, 0, raw, V.Tb, V.fa, V.fb);  // the last row standing
+    const size_t smem_bs = sizeof(double) * (3 * size_t(bb) + 3 * B);
+    CSLAM_CUDA(cudaFuncSetAttribute(bcr_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bs)));
+    bcr_backsub_kernel<<<1, 256, smem_bs, st>>>(R, 0, 1, 0);
+    launched += 2;
+    for (int l = nl - 1; l >= 0; --l) {
+        const int s = levels[l], n_odd = (R.N - s - 1) / (2 * s) + 1;
+        bcr_backsub_kernel<<<n_odd, 256, smem_bs, st>>>(R, s, 2 * s, s);
+        ++launched;
+    }
+    CSLAM_CUDA(cudaGetLastError());
+    return launched;
+}
+
 static int bcr_solve(cudaStream_t st, const BandView& V, const BandScratch& K, int W) {
     BcrView R;
     R.N = V.P - 1;
@@ -890,8 +1277,13 @@ int band_solve_w(cudaStream_t s, const BandView& V, const BandScratch& K) {
         return 2;
     }
     run_leaf<W, true>(s, V);
-    if (V.sep_solver == 2) {
-        const int launched = bcr_solve(s, V, K, W);
+    if (V.sep_solver == 2 || V.sep_solver == 3) {
+        // W = 12 (B = 72) keeps the first-generation kernels: its unrolled columns do not fit the register file
+        int launched;
+        if constexpr (W <= 9)
+            launched = V.sep_solver == 2 ? bcr2_solve<6 * W>(s, V, K) : bcr_solve(s, V, K, W);
+        else
+            launched = bcr_solve(s, V, K, W);
         run_backsub<W, true>(s, V, K.y2);
         return 2 + launched;
     }
