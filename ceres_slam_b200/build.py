@@ -13,6 +13,8 @@ HEADERS = ["closed_form.h", "common.cuh", "engine.h", "kernels.cuh", "comm.h", "
            os.path.join("..", "..", "include", "cslam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--fmad=true"]
+# diagnostic builds only (e.g. CSLAM_NVCC_EXTRA=-DCSLAM_ODD2_PROF); combine with force=True
+NVCC_FLAGS += os.environ.get("CSLAM_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -49,8 +49,7 @@ __device__ __forceinline__ bool potrf6_inv_reg(const double* A, double* Lout, do
         for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
         if (!(d > 0.0) || !(d < 1.7976931348623157e308)) ok = false;
         // one reciprocal square root per pivot (FP64 sqrt and divide are long software sequences)
-        double id = rsqrt(d);
-        id = id * (1.5 - 0.5 * d * id * id);  // one Newton step: full double precision
+        const double id = rsqrt(d);  // 1 ulp
         inv[j] = id;
         L[j][j] = d * id;
 #pragma unroll
@@ -872,10 +871,18 @@ __device__ __forceinline__ int ld_acquire_cta(const int* p) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Reciprocal square root without the library's special-case branch: the approximation instruction
+// (MUFU.RSQ64H, ~2^-22) and one third-order correction, the same five FP64 operations rsqrt() performs on
+// its fast path.  Branch-free matters more than the count: the compiler can then interleave the rank-1
+// update with this dependent sequence, which is what the pivot chain waits for.  Callers reject pivots
+// outside [1e-290, 1e290] (where the approximation's flush-to-zero / overflow handling would matter).
 __device__ __forceinline__ double rsqrt_nr(double d) {
-    double id = rsqrt(d);
-    return id * (1.5 - 0.5 * d * id * id);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(y * y), d, 1.0);
+    return fma(fma(e, 0.375, 0.5), y * e, y);
 }
+__device__ __forceinline__ bool pivot_ok(double d) { return d > 1e-290 && d < 1e290; }
 
 template <int B>
 struct Odd2 {
@@ -903,7 +910,7 @@ struct Odd2 {
 template <int B, int NC, int WID, bool CHAIN>
 __device__ __forceinline__ void odd2_factor_phase(double (&b)[NC + 1], double& diag, double& lprev, double& nid, int k_lo,
                                                   int k_hi, int r, int lane_base, bool act, double* Lt2, double* sInv,
-                                                  uint64_t* wait_on, uint64_t* done, int* s_bad) {
+                                                  uint64_t* wait_on, uint64_t* done, bool& bad) {
     for (int k = k_lo; k < k_hi; ++k) {
         const double* Lp = Lt2 + k * B;  // column k-1 of L from row k on (row 0 of Lt2 is zeros)
         double id, lpo;
@@ -924,13 +931,12 @@ __device__ __forceinline__ void odd2_factor_phase(double (&b)[NC + 1], double& d
         b[0] = a0;
 #pragma unroll
         for (int j = 1; j + 1 < WID; ++j) b[j] = b[j + 1] - lprev * Lp[j];
+        // column k-1 (stored one pivot ago, long complete): the release of this arrive costs nothing now
+        if (k > 0) mbar_arrive(done + k - 1);
         if (act && r > k) Lt2[(k + 1) * B + (r - k - 1)] = l;
-        if (r == k + 1) {
-            if (!(diag > 0.0) || !(diag < 1.7976931348623157e308)) *s_bad = 1;
-            sInv[k + 1] = nid;
-        }
+        if (r == k + 1) sInv[k + 1] = nid;
+        bad |= (r == k + 1) && !pivot_ok(diag);
         __syncwarp();
-        mbar_arrive(done + k);
         lprev = l;
     }
 }
@@ -940,7 +946,8 @@ template <int B, int WID>
 __device__ __forceinline__ void odd2_border_phase(double (&x)[B], int k_lo, int k_hi, const double* Lt2, const double* sInv,
                                                   uint64_t* col_done, double* outp, int ostride) {
     for (int k = k_lo; k < k_hi; ++k) {
-        mbar_wait(col_done + k, 0);
+        // a completed barrier still costs ~90 cycles to test: look two columns ahead, every third pivot
+        if ((k - k_lo) % 3 == 0) mbar_wait(col_done + (k + 2 < B ? k + 2 : B - 1), 0);
         const double xk = x[0] * sInv[k];
         if (outp) outp[(long long)k * ostride] = xk;
         const double2* Lp = reinterpret_cast<const double2*>(Lt2 + (k + 1) * B);  // column k of L from row k+1 on
@@ -965,13 +972,11 @@ __global__ void __launch_bounds__(Odd2<B>::THREADS, 1)
     __shared__ double sInv[B + 2];                 // 1 / L[k][k]
     __shared__ __align__(8) uint64_t done0[B + 1];  // done0[k + 1]: warp 0 published column k; done0[0]: 1 / L_00
     __shared__ __align__(8) uint64_t done1[B];      // done1[k]: warp 1 published column k (B > 32)
-    __shared__ int s_bad;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int i = first + blockIdx.x * step;
     const bool has_l = s > 0 && i - s >= 0, has_r = s > 0 && i + s < R.N;
     constexpr long long bb = (long long)B * B;
     if (*R.fail) return;
-    if (tid == 0) s_bad = 0;
     for (int j = tid; j < B + 1; j += C::THREADS) {
         if (j < B) {
             Lt2[j] = 0.0;
@@ -984,6 +989,14 @@ __global__ void __launch_bounds__(Odd2<B>::THREADS, 1)
     uint64_t* col_done = FW > 1 ? done1 : done0 + 1;  // what the border waits on: column k complete
     const double* Di = R.D + i * bb;
     const double* Tbi = Tb + i * bb;
+#ifdef CSLAM_ODD2_PROF
+    const long long t_entry = clock64();
+#define ODD2_T(name) const long long name = clock64();
+#define ODD2_P(...) if (lane == 0 && blockIdx.x == 0 && s == 4) printf(__VA_ARGS__);
+#else
+#define ODD2_T(name)
+#define ODD2_P(...)
+#endif
     if (warp == 0) {
         // ---------------- factor warp 0: rows 0 .. R0-1, it never needs anything from other warps ----------------
         const int r = lane;
@@ -1001,18 +1014,25 @@ __global__ void __launch_bounds__(Odd2<B>::THREADS, 1)
         }
         if (!act) diag = 1.0;
         double nid = rsqrt_nr(diag);
+        bool bad = false;
         if (r == 0) {
-            if (!(diag > 0.0) || !(diag < 1.7976931348623157e308)) s_bad = 1;
+            bad = !pivot_ok(diag);
             sInv[0] = nid;
         }
         __syncwarp();
         mbar_arrive(done0);
         double lprev = 0.0;
         constexpr int KH = R0 / 2;
-        odd2_factor_phase<B, R0, R0 + 1, true>(b, diag, lprev, nid, 0, KH, r, 0, act, Lt2, sInv, nullptr, done0 + 1, &s_bad);
+        ODD2_T(t0)
+        odd2_factor_phase<B, R0, R0 + 1, true>(b, diag, lprev, nid, 0, KH, r, 0, act, Lt2, sInv, nullptr, done0 + 1, bad);
+        ODD2_T(t1)
         odd2_factor_phase<B, R0, R0 + 2 - KH, true>(b, diag, lprev, nid, KH, FW > 1 ? R0 - 1 : R0, r, 0, act, Lt2, sInv, nullptr,
-                                                    done0 + 1, &s_bad);
-        if (FW == 1 && lane == 0 && s_bad) *R.fail = 1;
+                                                    done0 + 1, bad);
+        ODD2_T(t2)
+        ODD2_P("odd2 warp0: load %lld  k0-15 %lld  k16-30 %lld\n", t0 - t_entry, t1 - t0, t2 - t1)
+        __syncwarp();
+        mbar_arrive(done0 + (FW > 1 ? R0 - 1 : R0));  // the last column (arrivals run one pivot behind)
+        if (__any_sync(0xffffffffu, bad) && lane == 0) *R.fail = 1;
     } else if (FW > 1 && warp == 1) {
         // ---------------- factor warp 1: rows 32 .. B-1; trails warp 0, then owns the chain ----------------
         const int r = 32 + lane;
@@ -1030,10 +1050,18 @@ __global__ void __launch_bounds__(Odd2<B>::THREADS, 1)
         }
         if (!act) diag = 1.0;
         double nid = 1.0, lprev = 0.0;
-        odd2_factor_phase<B, B, B + 1, false>(b, diag, lprev, nid, 0, 16, r, 32, act, Lt2, sInv, done0, done1, &s_bad);
-        odd2_factor_phase<B, B, B + 1 - 15, false>(b, diag, lprev, nid, 16, 32, r, 32, act, Lt2, sInv, done0, done1, &s_bad);
-        odd2_factor_phase<B, B, B + 1 - 31, true>(b, diag, lprev, nid, 32, B, r, 32, act, Lt2, sInv, nullptr, done1, &s_bad);
-        if (lane == 0 && s_bad) *R.fail = 1;
+        bool bad = false;
+        ODD2_T(t0)
+        odd2_factor_phase<B, B, B + 1, false>(b, diag, lprev, nid, 0, 16, r, 32, act, Lt2, sInv, done0, done1, bad);
+        ODD2_T(t1)
+        odd2_factor_phase<B, B, B + 1 - 15, false>(b, diag, lprev, nid, 16, 32, r, 32, act, Lt2, sInv, done0, done1, bad);
+        ODD2_T(t2)
+        odd2_factor_phase<B, B, B + 1 - 31, true>(b, diag, lprev, nid, 32, B, r, 32, act, Lt2, sInv, nullptr, done1, bad);
+        ODD2_T(t3)
+        ODD2_P("odd2 warp1: load %lld  k0-15 %lld  k16-31 %lld  k32-53 %lld\n", t0 - t_entry, t1 - t0, t2 - t1, t3 - t2)
+        __syncwarp();
+        mbar_arrive(done1 + B - 1);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) *R.fail = 1;
     } else {
         // ---------------- border warps: one column of [E_left | E_right^T | f | I] per thread ----------------
         const int col = 32 * (warp - FW) + lane;
@@ -1066,9 +1094,12 @@ __global__ void __launch_bounds__(Odd2<B>::THREADS, 1)
             if (col < C::NCOL) outp = R.Li + i * bb + (col - 2 * B - 1);
         }
         constexpr int K1 = B / 3, K2 = 2 * B / 3;
+        ODD2_T(t0)
         odd2_border_phase<B, B>(x, 0, K1, Lt2, sInv, col_done, outp, ostride);
         odd2_border_phase<B, B - K1>(x, K1, K2, Lt2, sInv, col_done, outp, ostride);
         odd2_border_phase<B, B - K2>(x, K2, B, Lt2, sInv, col_done, outp, ostride);
+        ODD2_T(t3)
+        ODD2_P("odd2 border warp %d: load %lld  solve %lld\n", warp, t0 - t_entry, t3 - t0)
     }
 }
 
