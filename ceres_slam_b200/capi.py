@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_SO = os.path.join(ROOT, "ceres_slam_b200", "csrc", "libcslam_b200.so")
+PRODUCT_SO = os.environ.get("CSLAM_B200_LIB") or os.path.join(ROOT, "ceres_slam_b200", "csrc", "libcslam_b200.so")
 
 LOG_COLS = 10
 LOG_NAMES = ("iteration", "cost", "cost_change", "gradient_max_norm", "step_norm",

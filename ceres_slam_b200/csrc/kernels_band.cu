@@ -33,8 +33,24 @@ namespace {
 constexpr int BL_THREADS = 512;
 constexpr int BL_WORKERS = BL_THREADS - 32;  // warps 1..7 do the bulk update, warp 0 the look-ahead
 
+// Reciprocal square root without the library's special-case branch: the approximation instruction
+// (MUFU.RSQ64H, ~2^-22) and one third-order correction, the same five FP64 operations rsqrt() performs on
+// its fast path.  Branch-free matters more than the count: the compiler can then interleave independent
+// work with this dependent sequence, which is what every pivot chain in this file waits for.  Callers
+// reject pivots outside [1e-290, 1e290] (where flush-to-zero / overflow handling would matter).
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(y * y), d, 1.0);
+    return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+__device__ __forceinline__ bool pivot_ok(double d) { return d > 1e-290 && d < 1e290; }
+
 // 6x6 Cholesky of a symmetric block (lower triangle read from `A`, row-major) entirely in
 // registers: L (lower, zeros above) and Li = L^-1.  Returns false when a pivot is not positive.
+// Right-looking: the only dependent chain is  rsqrt -> scale the next row's entry -> its diagonal
+// (~85 cycles per pivot; the left-looking dot products it replaces were chains of up to five FMAs
+// in front of every rsqrt).
 __device__ __forceinline__ bool potrf6_inv_reg(const double* A, double* Lout, double* Liout) {
     double L[6][6], inv[6];
 #pragma unroll
@@ -44,21 +60,17 @@ __device__ __forceinline__ bool potrf6_inv_reg(const double* A, double* Lout, do
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double d = L[j][j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-        if (!(d > 0.0) || !(d < 1.7976931348623157e308)) ok = false;
-        // one reciprocal square root per pivot (FP64 sqrt and divide are long software sequences)
-        const double id = rsqrt(d);  // 1 ulp
+        const double d = L[j][j];
+        ok = ok && pivot_ok(d);
+        const double id = rsqrt_nr(d);
         inv[j] = id;
         L[j][j] = d * id;
 #pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
-            double s = L[i][j];
+        for (int i = j + 1; i < 6; ++i) L[i][j] *= id;
 #pragma unroll
-            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-            L[i][j] = s * id;
-        }
+        for (int i = j + 1; i < 6; ++i)
+#pragma unroll
+            for (int c = j + 1; c <= i; ++c) L[i][c] -= L[i][j] * L[c][j];
     }
     double Li[6][6];
 #pragma unroll
@@ -860,30 +872,6 @@ __global__ void __launch_bounds__(256) bcr_backsub_kernel(BcrView R, int first, 
 //   for ("odd": read as E_left) and transposed otherwise (read as E_right^T by its odd neighbour):
 //   both reads of the odd kernel are then coalesced across the column threads.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_cta(int* p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_cta(const int* p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// Reciprocal square root without the library's special-case branch: the approximation instruction
-// (MUFU.RSQ64H, ~2^-22) and one third-order correction, the same five FP64 operations rsqrt() performs on
-// its fast path.  Branch-free matters more than the count: the compiler can then interleave the rank-1
-// update with this dependent sequence, which is what the pivot chain waits for.  Callers reject pivots
-// outside [1e-290, 1e290] (where the approximation's flush-to-zero / overflow handling would matter).
-__device__ __forceinline__ double rsqrt_nr(double d) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    const double e = fma(-(y * y), d, 1.0);
-    return fma(fma(e, 0.375, 0.5), y * e, y);
-}
-__device__ __forceinline__ bool pivot_ok(double d) { return d > 1e-290 && d < 1e290; }
-
 template <int B>
 struct Odd2 {
     static constexpr int FW = (B + 31) / 32;        // factor warps (B <= 64)
