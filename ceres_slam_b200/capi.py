@@ -54,6 +54,7 @@ class Options(C.Structure):
         ("trust_region_strategy", C.c_int),
         ("dogleg_type", C.c_int),
         ("line_search_sufficient_function_decrease", C.c_double),
+        ("dense_solver", C.c_int),
     ]
 
 

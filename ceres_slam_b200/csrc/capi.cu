@@ -72,6 +72,7 @@ void cslam_options_init(cslam_options* o) {
     o->trust_region_strategy = 0;
     o->dogleg_type = 1;
     o->line_search_sufficient_function_decrease = 1e-4;
+    o->dense_solver = 0;
 }
 
 cslam_status cslam_problem_create(cslam_problem** out, const cslam_options* opt) {

@@ -1195,6 +1195,7 @@ void Engine::upload() {
     d_pscal.alloc(PS_COUNT, stream);
     pt.lap("  reduced system allocs");
     plan_band_solver();
+    plan_dense_solver();
     pt.lap("  plan_band_solver");
     d_scal2.alloc(SC_COUNT, stream);
     if (!suns.empty()) d_suns.upload(suns, stream);
@@ -1262,6 +1263,30 @@ void Engine::plan_band_solver() {
     d_X2.alloc(6 * n2, stream);
     d_y2.alloc(6 * n2, stream);
     band_active = true;
+}
+
+// The exact solve of a reduced system that is not a narrow band: dense Cholesky when it is small (PCG run
+// to 1e-15 needs hundreds of iterations there and is not exact) or dense enough to be a real contraction.
+void Engine::plan_dense_solver() {
+    dense_active = false;
+    if (opt.linear_solver != 0 || n_free <= 0 || opt.dense_solver < 0 || ph.active) return;
+    const long long n = 6ll * n_free;
+    if (n > kDenseMaxN) return;
+    if (opt.dense_solver == 0) {
+        if (band_active) return;
+        const double nnz = double(s_col_h.size()), full = 0.5 * double(n_free) * double(n_free + 1);
+        if (n > kDenseAutoSmallN && nnz < 0.1 * full) return;
+    }
+    const int nb = dense_panel_width();
+    dense_npad = int((n + nb - 1) / nb) * nb;
+    dense_ld = dense_npad + 8;
+    d_dense_A.alloc(size_t(dense_ld) * size_t(dense_npad + 1), stream);
+    d_dense_Ld.alloc(size_t(dense_npad / nb) * nb * nb, stream);
+    d_dense_inv.alloc(size_t(dense_npad), stream);
+    d_dense_xw.alloc(size_t(dense_npad), stream);
+    if (!d_band_fail.p) d_band_fail.alloc(1, stream);
+    dense_active = true;
+    band_active = false;
 }
 
 void Engine::alloc_band_sets(int count) {
@@ -1685,7 +1710,22 @@ void Engine::solve_reduced(const double* rhs, double* y) {
         max_it = opt.max_linear_solver_iterations;
         min_it = opt.min_linear_solver_iterations;
     }
-    if (band_active) {
+    if (dense_active) {
+        DenseView V;
+        V.n = 6 * n_free;
+        V.n_pad = dense_npad;
+        V.ld = dense_ld;
+        V.rowptr = d_s_rowptr.p;
+        V.col = d_s_col.p;
+        V.S = d_S;
+        V.rhs = rhs;
+        V.A = d_dense_A.p;
+        V.Ldiag = d_dense_Ld.p;
+        V.invd = d_dense_inv.p;
+        V.y = y;
+        V.fail = d_band_fail.p;
+        launch_dense_solve(stream, V, d_dense_xw.p, d_pscal.p);
+    } else if (band_active) {
         BandView V;
         V.n = n_free;
         V.w = band_w;

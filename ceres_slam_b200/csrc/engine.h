@@ -102,6 +102,23 @@ struct BandScratch {
 };
 int band_storage_width(int w);   // 3, 6, 9 or 12: the compiled window widths
 
+// Dense Cholesky of the reduced camera system (kernels_dense.cu): lower triangle, column-major, leading
+// dimension ld, n = 6 x free poses padded to n_pad (a multiple of the panel width); row n_pad = right-hand side.
+constexpr int kDenseMaxN = 12288;     // 1.2 GB of FP64
+constexpr int kDenseAutoSmallN = 3072;  // below this the dense solve replaces PCG whatever the density
+struct DenseView {
+    int n, n_pad, ld;
+    const int *rowptr, *col;     // upper block-CSR of S
+    const double* S;
+    const double* rhs;           // [n]
+    double* A;                   // [n_pad + 1][ld]
+    double* Ldiag;               // [n_pad / 48][48][48] factors of the diagonal blocks
+    double* invd;                // [n_pad] 1 / L[k][k]
+    double* y;                   // [n] solution
+    int* fail;
+};
+int dense_panel_width();
+
 struct SunBlockData {
     uint32_t cam;
     double obs_c[3], ref_g[3], W[4], az_thresh, zen_thresh, huber;
@@ -300,6 +317,11 @@ class Engine {
     DBuf<int> d_band_idx, d_band_fail;
     DBuf<double> d_Lbuf, d_Xbuf, d_Ta, d_Ca, d_fa, d_Tb, d_fb, d_T2, d_rhs2, d_L2, d_X2, d_y2;
     void plan_band_solver();
+    // dense direct solver (linear_solver == 0, S not banded, small or dense enough)
+    bool dense_active = false;
+    int dense_npad = 0, dense_ld = 0;
+    DBuf<double> d_dense_A, d_dense_Ld, d_dense_inv, d_dense_xw;
+    void plan_dense_solver();
     // extra scratch sets + streams so that independent solves against the same banded S run
     // concurrently (the border columns of the lighting solve): each solve is a latency-bound chain
     // on a handful of CTAs, so n_g + 1 of them fit side by side on 148 SMs

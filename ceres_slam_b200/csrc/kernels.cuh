@@ -56,6 +56,8 @@ void launch_pcg_persistent(cudaStream_t s, const PcgBufs& B, double* pbuf2, doub
 // K3b — direct solve of a block-banded reduced system (leaves + separators, kernels_band.cu);
 // writes ps[PS_ITERS] = 1 and ps[PS_FAIL] = 2 when a pivot is not positive
 void launch_band_solve(cudaStream_t s, const BandView& B, const BandScratch& K, double* ps);
+// K3d — dense Cholesky of a reduced system that is not a narrow band (kernels_dense.cu); xw: [n_pad] work vector
+void launch_dense_solve(cudaStream_t s, const DenseView& V, double* xw, double* ps);
 
 // K4 — Plus on the poses, back-substitution, model cost change, candidate cost
 void launch_pose_plus(cudaStream_t s, const DevView& v, const double* yp, double* poses_cand, double* scal2,

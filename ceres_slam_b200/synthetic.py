@@ -68,21 +68,26 @@ def project(cam, pc):
 
 
 def make_track(n_poses, new_per_frame, track_len, seed=42, pix_sigma=1.0, pose_sigma=(0.02, 0.01),
-               point_sigma=0.05, spacing=0.3, per_obs_W=False, cam=None):
+               point_sigma=0.05, spacing=0.3, per_obs_W=False, cam=None, closed=False):
     """A sims-style stereo track.
 
     Every frame sees `new_per_frame` new landmarks, each tracked over `track_len` consecutive
     poses, i.e. about new_per_frame * track_len observations per frame in steady state
     (C1/C2: 15 x 10; C5: 100 x 10 -> 20 k poses, 2 M landmarks, 20 M observations).
+
+    closed=True closes the loop the way the reference's simulated trajectories do
+    (scripts/ba_all_sims.sh:8-13: triangle / square / penta / circle tracks): the tracks of the last
+    frames run on into the first ones, so the last poses share landmarks with the first and the
+    reduced camera system gets blocks far from its diagonal.
     """
     cam = dict(cam or KITTI)
     rng = np.random.default_rng(seed)
     poses_gt = loop_poses(n_poses, spacing)
-    n_starts = n_poses - track_len + 1
+    n_starts = n_poses if closed else n_poses - track_len + 1
     n_pts = n_starts * new_per_frame
     first = np.repeat(np.arange(n_starts, dtype=np.int64), new_per_frame)
     # place each landmark in the frustum of the middle pose of its track
-    mid = first + track_len // 2
+    mid = (first + track_len // 2) % n_poses
     u = rng.uniform(150.0, IMG_W - 150.0, n_pts)
     v = rng.uniform(60.0, IMG_H - 60.0, n_pts)
     z = rng.uniform(4.0, 30.0, n_pts)
@@ -90,7 +95,7 @@ def make_track(n_poses, new_per_frame, track_len, seed=42, pix_sigma=1.0, pose_s
     Rm, tm = pose_R(poses_gt)[mid], pose_t(poses_gt)[mid]
     points_gt = np.einsum("nji,nj->ni", Rm, pc - tm)  # R^T (p_c - t)
     # observations, pose-major
-    k = (first[:, None] + np.arange(track_len)[None, :]).reshape(-1)
+    k = ((first[:, None] + np.arange(track_len)[None, :]) % n_poses).reshape(-1)
     j = np.repeat(np.arange(n_pts, dtype=np.int64), track_len)
     order = np.argsort(k, kind="stable")
     k, j = k[order], j[order]

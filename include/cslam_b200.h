@@ -72,6 +72,11 @@ typedef struct cslam_options {
     int dogleg_type;            /* 0 = TRADITIONAL_DOGLEG, 1 = SUBSPACE_DOGLEG (dataset_vo_sun.cpp:143) */
     double line_search_sufficient_function_decrease; /* 1e-4: Armijo constant of the line search a
                                bounded problem runs along the trust-region step */
+    int dense_solver;       /* exact solve (linear_solver 0) of a reduced system that is NOT a narrow band (loop
+                               closures, tracks longer than 13 frames): 0 = auto (dense FP64 Cholesky on the
+                               DMMA tensor cores when 6 x free poses <= 3072, or <= 12288 and at least 10 % of
+                               the blocks are present; PCG run to 1e-15 otherwise), 1 = dense whenever it fits
+                               (also instead of the banded solver), -1 = never */
 } cslam_options;
 
 typedef struct cslam_summary {

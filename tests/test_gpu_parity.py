@@ -202,11 +202,39 @@ def test_band_direct_solver_wide(product):
 
 
 def test_exact_solve_fallback_pcg(product):
-    """Half-bandwidth 13 > 12: the exact solve falls back to PCG run to 1e-15."""
+    """Half-bandwidth 13 > 12 with the dense solver switched off: the exact solve falls back to PCG
+    run to 1e-15."""
     tr = syn.make_track(80, 3, 14, seed=17)
-    g, o = solve_pair(tr, 4)
+    g, o = solve_pair(tr, 4, dense_solver=-1)
     check_lm(g, o)
     assert g[0].iteration_log()[1:, 7].max() > 1
+
+
+@pytest.mark.parametrize("shape,closed", [((80, 3, 14), False), ((120, 10, 6), True), ((57, 12, 9), True),
+                                          ((260, 6, 5), True)])
+def test_dense_cholesky_exact_solve(product, shape, closed):
+    """north_star (3): a reduced camera system that is not a narrow band — tracks longer than the banded
+    solver takes, and closed loops whose last poses re-observe the landmarks of the first
+    (scripts/ba_all_sims.sh:8-13) — is solved by the dense FP64 Cholesky (DMMA trailing updates):
+    one direct solve per LM iteration and the oracle's exact trajectory.  Sizes are not multiples
+    of the 48-column panel."""
+    tr = syn.make_track(*shape, seed=29, closed=closed)
+    g, o = solve_pair(tr, 5)
+    check_lm(g, o)
+    lg = g[0].iteration_log()
+    assert np.all(lg[1:, 7] == 1), "one direct solve per LM iteration"
+
+
+def test_dense_cholesky_matches_band(product):
+    """dense_solver = 1 takes the dense path even for a banded system: same iterates as the banded
+    direct solver."""
+    tr = syn.make_track(150, 8, 7, seed=31)
+    kw = dict(FIXED, max_num_iterations=5, window_path=1)
+    p1, poses1, points1 = syn.build_problem(tr, dense_solver=1, **kw)
+    p2, poses2, points2 = syn.build_problem(tr, **kw)
+    p1.solve()
+    p2.solve()
+    assert rel_err(poses1, poses2) < 1e-9 and rel_err(points1, points2) < 1e-9
 
 
 def test_lm_iterative_schur(product):
