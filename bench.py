@@ -306,6 +306,37 @@ def bench_c3_phong_solve(iters=6, cpu=True):
     return out
 
 
+def bench_loop_closure(iters=6, n_poses=500):
+    """Closed-loop full batch (scripts/ba_all_sims.sh:8-13 runs closed trajectories; dataset_vo.cpp:118-121
+    --window 0): the last poses re-observe the first landmarks, so the reduced camera system has blocks
+    far from its diagonal and the exact solve is the dense FP64 Cholesky (DMMA trailing update) instead
+    of the banded solver; the PCG fallback run to 1e-15 (dense_solver = -1) is timed beside it."""
+    fixed = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    tr = syn.make_track(n_poses, 100, 10, seed=42, closed=True)
+    out = {"poses": n_poses, "landmarks": int(tr["n_points"]), "observations": int(tr["obs_cam"].size),
+           "reduced_dimension": 6 * (n_poses - 1)}
+    for name, ds in (("dense_cholesky", 0), ("pcg_1e-15", -1)):
+        p, _, _ = syn.build_problem(tr, max_num_iterations=10 ** 6, profile_kernels=1, dense_solver=ds, **fixed)
+        p.upload()
+        p.lm_begin()
+        p.lm_iterate(2, ignore_convergence=True)
+        p.reset_profile()
+        s0 = p.lm_iterate(0, ignore_convergence=True).device_ms
+        s = p.lm_iterate(iters, ignore_convergence=True)
+        prof = {k: v[0] / max(1, v[1]) for k, v in p.profile().items() if v[1]}
+        log = p.iteration_log()
+        out[name] = {"ms_per_lm_iteration": (s.device_ms - s0) / iters, "linear_solve_ms": prof.get("linear_solve"),
+                     "schur_ms": prof.get("schur"), "linear_iterations_per_solve": float(log[-iters:, 7].mean()),
+                     "cost_last": float(log[-1, 1])}
+        p.close()
+    n = out["reduced_dimension"]
+    ms = out["dense_cholesky"]["linear_solve_ms"]
+    if ms:
+        out["dense_cholesky"]["factor_tflops"] = 2.0 * n ** 3 / 3.0 / (ms * 1e-3) / 1e12
+    out["note"] = "factor_tflops = (n^3 / 3 FMA) / whole reduced solve (fill + panels + DMMA updates + both substitutions)"
+    return out
+
+
 def bench_ransac_front_end(n_poses=1000):
     """the RANSAC front end (compute_initial_guess's 400-hypothesis point-cloud
     alignment per consecutive pose pair) for a 1 k-pose track with ~900 matches per pair, all pairs
@@ -624,6 +655,7 @@ def main():
     phong = bench_phong_blocks(peak) if (rank == 0 and not args.no_phong) else None
     c3 = bench_c3_phong_solve(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_phong) else None
     ransac = bench_ransac_front_end() if (rank == 0 and world == 1 and not args.no_c4) else None
+    loop = bench_loop_closure() if (rank == 0 and world == 1 and not args.no_c4) else None
     drivers = bench_c1_c2_drivers(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_c4) else None
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
@@ -682,7 +714,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "resjac": resjac, "step_profile_ms": step_profile, "allreduce": allreduce, "c4_windows": c4, "phong_blocks": phong,
-            "c3_phong_solve": c3, "ransac_front_end": ransac,
+            "c3_phong_solve": c3, "ransac_front_end": ransac, "loop_closure_dense_solve": loop,
             "c1_dataset_vo": (drivers or {}).get("c1_dataset_vo"), "c2_dataset_vo_sun": (drivers or {}).get("c2_dataset_vo_sun"),
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},

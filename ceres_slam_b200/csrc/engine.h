@@ -105,7 +105,6 @@ int band_storage_width(int w);   // 3, 6, 9 or 12: the compiled window widths
 // Dense Cholesky of the reduced camera system (kernels_dense.cu): lower triangle, column-major, leading
 // dimension ld, n = 6 x free poses padded to n_pad (a multiple of the panel width); row n_pad = right-hand side.
 constexpr int kDenseMaxN = 12288;     // 1.2 GB of FP64
-constexpr int kDenseAutoSmallN = 3072;  // below this the dense solve replaces PCG whatever the density
 struct DenseView {
     int n, n_pad, ld;
     const int *rowptr, *col;     // upper block-CSR of S

@@ -74,9 +74,9 @@ typedef struct cslam_options {
                                bounded problem runs along the trust-region step */
     int dense_solver;       /* exact solve (linear_solver 0) of a reduced system that is NOT a narrow band (loop
                                closures, tracks longer than 13 frames): 0 = auto (dense FP64 Cholesky on the
-                               DMMA tensor cores when 6 x free poses <= 3072, or <= 12288 and at least 10 % of
-                               the blocks are present; PCG run to 1e-15 otherwise), 1 = dense whenever it fits
-                               (also instead of the banded solver), -1 = never */
+                               DMMA tensor cores when 6 x free poses <= 12288, i.e. a factor of at most 1.2 GB;
+                               PCG run to 1e-15 beyond that), 1 = dense whenever it fits (also instead of the
+                               banded solver), -1 = never */
 } cslam_options;
 
 typedef struct cslam_summary {
