@@ -1792,7 +1792,16 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
     launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p, d_points_cand.p,
                            ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
     read_scalars(d_scal2.p, sc2, SC_COUNT);
-    if (bounded && sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0) {
+    if (bounded && sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0) phong_line_search(d_yp.p, ph.yg.p, ph.yv.p, sc2);
+    prof_end(CSLAM_K_BACKSUB);
+}
+
+// TrustRegionMinimizer::DoLineSearch for a bounded problem: Armijo search along the step (yp, yg, yv), starting
+// from the full step whose scalars are in sc2 (SC_LS_GY = g . y, SC_LS_DMAX = |delta|_inf, SC_MODEL, SC_CAND_COST).
+void Engine::phong_line_search(const double* yp, const double* yg, const double* yv, double* sc2) {
+    DevView v = view(d_poses.p, d_points.p);
+    const PhongSolveView q = phong_solve_view(ph.normals.p, ph.gx.p);
+    {
         const double g0 = -sc2[SC_LS_GY], dmax = sc2[SC_LS_DMAX];
         const double model = sc2[SC_MODEL];
         double a_cur = 1.0, f_cur = sc2[SC_CAND_COST];
@@ -1821,7 +1830,7 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
             }
             a_cur = a_new;
             d_scal2.zero(stream);
-            launch_phong_candidate(stream, v, q, 0, n_lm, a_cur, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p,
+            launch_phong_candidate(stream, v, q, 0, n_lm, a_cur, yp, yg, yv, d_poses_cand.p, ph.gx_cand.p,
                                    d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
             read_scalars(d_scal2.p, sc2, SC_COUNT);
             f_cur = sc2[SC_CAND_COST];
@@ -1829,13 +1838,89 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
         if (!success && a_cur != 1.0) {
             // the search failed: Ceres keeps the full step
             d_scal2.zero(stream);
-            launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p,
+            launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, yp, yg, yv, d_poses_cand.p, ph.gx_cand.p,
                                    d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
             read_scalars(d_scal2.p, sc2, SC_COUNT);
         }
         sc2[SC_MODEL] = model;
         sc2[SC_NONFINITE] = first[SC_NONFINITE];
     }
+}
+
+// DOGLEG for the lighting solve (dataset_ba_phong.cpp:88-89): DoglegStrategy::ComputeStep over
+// [poses | vertices | shared blocks] and the candidate evaluation (same structure as dogleg_step).
+void Engine::phong_dogleg_step(int* lin_iters, bool* valid, double* sc2) {
+    DevView v = view(d_poses.p, d_points.p);
+    const PhongSolveView q = phong_solve_view(ph.normals.p, ph.gx.p);
+    *lin_iters = 0;
+    if (!dl.reuse) {
+        bool solved = false;
+        while (dl.mu < 1.0) {
+            if (!lm.have_system) schur_pass();
+            double sc1[SC_COUNT];
+            read_scalars(d_scal, sc1, SC_COUNT);
+            int it = 0;
+            bool ok = sc1[SC_INVALID] == 0.0;
+            if (ok) phong_linear_solve(&it, &ok);
+            if (ok) {
+                solved = true;
+                break;
+            }
+            dl.mu *= 10.0;
+            lm.have_system = false;
+        }
+        if (!solved) {
+            *valid = false;
+            return;
+        }
+        *lin_iters = 1;
+        const LmDiag dg = current_diag();
+        prof_begin(CSLAM_K_BACKSUB);
+        d_scal2.zero(stream);  // (the back-substitution's model / line-search outputs are not used here)
+        launch_phong_backsub(stream, v, q, 0, n_lm, dg, d_yp.p, ph.yg.p, ph.gv.p, ph.yv.p, d_scal2.p, ph.max_track);
+        d_dsums.zero(stream);
+        launch_dogleg_products(stream, v, 0, 0, dg, nullptr, 0, nullptr, 0, d_gp, d_diag_p.p, d_yp.p, nullptr, nullptr, nullptr,
+                               d_dsums.p, 1);
+        launch_phong_dogleg_products(stream, v, q, 0, n_lm, dg, d_gp, d_diag_p.p, d_yp.p, ph.gg, ph.diag_g.p, ph.yg.p, ph.gv.p,
+                                     ph.yv.p, ph.diag_v.p, ph.sc_v.p, d_dsums.p, ph.max_track);
+        prof_end(CSLAM_K_BACKSUB);
+        double sm[DG_COUNT];
+        read_scalars(d_dsums.p, sm, DG_COUNT);
+        DoglegModel& m = dl.model;
+        m.G11 = sm[DG_G11], m.G12 = sm[DG_G12], m.G22 = sm[DG_G22];
+        m.JGG = sm[DG_JGG], m.JGY = sm[DG_JGY], m.JYY = sm[DG_JYY], m.JGR = sm[DG_JGR], m.JYR = sm[DG_JYR];
+        bool finite = true;
+        for (double x : sm) finite = finite && std::isfinite(x);
+        if (!finite || !m.prepare(opt.dogleg_type == 1)) {
+            *valid = false;
+            return;
+        }
+        dl.reuse = true;
+    }
+    double c1, c2;
+    if (opt.dogleg_type == 1)
+        dl.model.subspace(lm.radius, &c1, &c2, &dl.step_norm);
+    else
+        dl.model.traditional(lm.radius, &c1, &c2, &dl.step_norm);
+    prof_begin(CSLAM_K_BACKSUB);
+    launch_dogleg_combine(stream, 6ll * n_free, c1, c2, d_gp, d_diag_p.p, d_yp.p, d_Yp.p);
+    launch_dogleg_combine(stream, ph.n_g, c1, c2, ph.gg, ph.diag_g.p, ph.yg.p, ph.Yg.p);
+    launch_dogleg_combine(stream, 6ll * n_lm, c1, c2, ph.gv.p, ph.diag_v.p, ph.yv.p, ph.Yv.p);
+    d_scal2.zero(stream);
+    if (bounded) {
+        launch_dot(stream, d_gp, d_Yp.p, 6ll * n_free, d_scal2.p + SC_LS_GY);
+        launch_dot(stream, ph.gg, ph.Yg.p, ph.n_g, d_scal2.p + SC_LS_GY);
+        launch_dot(stream, ph.gv.p, ph.Yv.p, 6ll * n_lm, d_scal2.p + SC_LS_GY);
+        launch_absmax_scaled(stream, d_Yp.p, d_sc_p.p, 6ll * n_free, d_scal2.p + SC_LS_DMAX);
+        launch_absmax_scaled(stream, ph.Yg.p, ph.sc_g.p, ph.n_g, d_scal2.p + SC_LS_DMAX);
+        launch_absmax_scaled(stream, ph.Yv.p, ph.sc_v.p, 6ll * n_lm, d_scal2.p + SC_LS_DMAX);
+    }
+    launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_Yp.p, ph.Yg.p, ph.Yv.p, d_poses_cand.p, ph.gx_cand.p, d_points_cand.p,
+                           ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
+    read_scalars(d_scal2.p, sc2, SC_COUNT);
+    sc2[SC_MODEL] = dl.model.model_cost_change(c1, c2);
+    *valid = sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0;
+    if (bounded && *valid) phong_line_search(d_Yp.p, ph.Yg.p, ph.Yv.p, sc2);
     prof_end(CSLAM_K_BACKSUB);
 }
 
@@ -1922,7 +2007,12 @@ void Engine::lm_begin() {
     lm = Lm();
     dl = Dogleg();
     if (dogleg()) {
-        if (ph.active) throw NotImplemented("DOGLEG: stereo / sun / prior problems only (the lighting solve runs Levenberg-Marquardt)");
+        if (ph.active) {
+            ph.diag_v.alloc(6 * size_t(std::max(n_lm, 1)), stream);
+            ph.sc_v.alloc(6 * size_t(std::max(n_lm, 1)), stream);
+            ph.Yv.alloc(6 * size_t(std::max(n_lm, 1)), stream);
+            ph.Yg.alloc(size_t(std::max(ph.n_g, 1)), stream);
+        }
         d_diag_l.alloc(3 * size_t(std::max(n_lm, 1)), stream);
         d_Yl.alloc(3 * size_t(std::max(n_lm, 1)), stream);
         d_Yp.alloc(6 * size_t(std::max(n_free, 1)), stream);
@@ -2057,7 +2147,7 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
         int lin_iters = 0;
         bool lin_ok = true;
         bool valid = sc1[SC_INVALID] == 0.0;
-        const bool use_dogleg = dogleg() && !ph.active;
+        const bool use_dogleg = dogleg();
         if (valid && !use_dogleg) {
             if (ph.active)
                 phong_linear_solve(&lin_iters, &lin_ok);
@@ -2069,7 +2159,11 @@ void Engine::lm_iterate(int n, bool ignore_convergence, cslam_summary* s) {
         lm.total_linear += lin_iters;
         double sc2[SC_COUNT] = {0};
         const LmDiag dg = current_diag();
-        if (use_dogleg) {
+        if (use_dogleg && ph.active) {
+            if (valid) phong_dogleg_step(&lin_iters, &valid, sc2);
+            row.v[7] = lin_iters;
+            lm.total_linear += lin_iters;
+        } else if (use_dogleg) {
             dogleg_step(&lin_iters, &valid, sc2);
             row.v[7] = lin_iters;
             lm.total_linear += lin_iters;

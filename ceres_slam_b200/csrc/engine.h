@@ -366,6 +366,7 @@ class Engine {
         DBuf<int> v_mat, v_tex, g_used;
         DBuf<double> obs_I, obs_n;
         DBuf<double> sc_n, sc_g, cn_n, gv, yv, yg, diag_g, X, T, zero_g;
+        DBuf<double> diag_v, sc_v, Yv, Yg;      // DOGLEG: clamp(diag(J^T J)) and column scaling per vertex, combined step
         double *Scg = nullptr, *Sgg = nullptr, *bg = nullptr, *gg = nullptr, *hg = nullptr;  // inside d_red
         std::vector<int> g_used_h;
         cudaGraphExec_t fan_graph = nullptr;   // the border solves' fan-out, captured on its second use
@@ -376,6 +377,8 @@ class Engine {
     void setup_phong_solve();
     void copy_phong_best();
     void phong_step(const LmDiag& dg, double* sc2);
+    void phong_line_search(const double* yp, const double* yg, const double* yv, double* sc2);
+    void phong_dogleg_step(int* lin_iters, bool* valid, double* sc2);
     PhongSolveView phong_solve_view(const double* normals, const double* gx) const;
     PhongSystem phong_system();
     void solve_reduced(const double* rhs, double* y);

@@ -109,6 +109,12 @@ void launch_phong_border_solve(cudaStream_t s, int n_g, int nf6, const double* S
                                const double* bg, double* T, double* yg, double* yc, double* ps);
 void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
                           const double* yp, const double* yg, const double* gv, double* yv, double* scal2, int max_track_len);
+// DOGLEG for the lighting solve: the strategy's eight sums (vertex and observation terms + shared-block terms;
+// the pose terms come from launch_dogleg_products with an empty landmark range), diag_v / sc_v as by-products
+void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                                  const double* gp, const double* diag_p, const double* yp, const double* gg, const double* diag_g,
+                                  const double* yg, const double* gv, const double* yv, double* diag_v, double* sc_v, double* sums,
+                                  int max_track_len);
 void launch_phong_candidate(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, double alpha,
                             const double* yp, const double* yg, const double* yv, double* poses_cand, double* gx_cand,
                             double* points_cand, double* normals_cand, double* scal2, int count_shared, int max_track_len);

@@ -404,6 +404,136 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
     block_atomic_sum(gy, &scal2[SC_LS_GY], s_red);
 }
 
+// =============================================================================================
+// DOGLEG for the lighting solve (dataset_ba_phong.cpp:88-89): the eight inner products of
+// DoglegStrategy over [poses | vertices | shared blocks] — see dogleg_products_kernel in kernels.cu
+// for the stereo path — with the vertex part of D^2 = clamp(diag(J^T J)) formed on the fly and
+// written out (diag_v, and the interleaved column scaling sc_v) for the combine / line-search passes.
+//   sums: 0 g'.g'  1 g'.gn'  2 gn'.gn'  3 |J D^-2 g|^2  4 (J D^-2 g).(J y)  5 |J y|^2  6 (J D^-2 g).r  7 (J y).r
+// The pose and shared-block terms of sums 0..2 are added by their own small kernels.
+// =============================================================================================
+template <int LW>
+__global__ void __launch_bounds__(PB_WARPS * 32)
+    phong_dogleg_products_kernel(DevView v, PhongSolveView q, int lm_lo, int lm_hi, LmDiag dg, const double* __restrict__ gp,
+                                 const double* __restrict__ diag_p, const double* __restrict__ yp,
+                                 const double* __restrict__ gg, const double* __restrict__ diag_g,
+                                 const double* __restrict__ yg, const double* __restrict__ gv, const double* __restrict__ yv,
+                                 double* __restrict__ diag_v_out, double* __restrict__ sc_v_out, double* __restrict__ sums) {
+    __shared__ double s_red[32];
+    constexpr int NSUB = 32 / LW;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lv = lane % LW, sub = lane / LW;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int warps_total = gridDim.x * PB_WARPS;
+    for (int jb = lm_lo + (blockIdx.x * PB_WARPS + wib) * NSUB; jb < lm_hi; jb += warps_total * NSUB) {
+        const bool vok = jb + sub < lm_hi;
+        const int j = vok ? jb + sub : lm_hi - 1;
+        const long long e0 = v.lm_base[j], es = v.lm_stride[j];
+        const int L = vok ? int(v.lm_cnt[j]) : 0;
+        VertexCtx c;
+        load_vertex(v, q, j, c);
+        PhObs ob;
+        ob.f = -1;
+        const bool act = lv < L;
+        double V21[21], t6[6], r7[7];
+        if (act) {
+            eval_phong_obs(v, q, e0 + lv * es, c, ob);
+            r7[0] = ob.rs[0], r7[1] = ob.rs[1], r7[2] = ob.rs[2], r7[3] = ob.rI;
+            r7[4] = ob.rN[0], r7[5] = ob.rN[1], r7[6] = ob.rN[2];
+            vertex_normal_eq(ob, r7, V21, t6);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 21; ++k) V21[k] = 0.0;
+        }
+        // diagonal of V = sum A_v^T A_v: packed entries 0, 6, 11, 15, 18, 20
+        double d2[6];
+        d2[0] = seg_sum<LW>(V21[0]);
+        d2[1] = seg_sum<LW>(V21[6]);
+        d2[2] = seg_sum<LW>(V21[11]);
+        d2[3] = seg_sum<LW>(V21[15]);
+        d2[4] = seg_sum<LW>(V21[18]);
+        d2[5] = seg_sum<LW>(V21[20]);
+        double tg[6], ty[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            d2[a] = fmin(fmax(d2[a], dg.min_diag), dg.max_diag);
+            const double g = gv[6ll * j + a], y = yv[6ll * j + a];
+            tg[a] = g / d2[a];
+            ty[a] = y;
+            if (lv == 0 && vok) {
+                diag_v_out[6ll * j + a] = d2[a];
+                sc_v_out[6ll * j + a] = a < 3 ? c.sl[a] : c.sn[a - 3];
+                acc[0] += g * g / d2[a];
+                acc[1] -= g * y;
+                acc[2] += d2[a] * y * y;
+            }
+        }
+        if (act) {
+            double jg[7], jy[7];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                jg[k] = ob.S[3 * k] * tg[0] + ob.S[3 * k + 1] * tg[1] + ob.S[3 * k + 2] * tg[2];
+                jy[k] = ob.S[3 * k] * ty[0] + ob.S[3 * k + 1] * ty[1] + ob.S[3 * k + 2] * ty[2];
+                jg[4 + k] = ob.N[3 * k] * tg[3] + ob.N[3 * k + 1] * tg[4] + ob.N[3 * k + 2] * tg[5];
+                jy[4 + k] = ob.N[3 * k] * ty[3] + ob.N[3 * k + 1] * ty[4] + ob.N[3 * k + 2] * ty[5];
+            }
+            jg[3] = ob.ip[0] * tg[0] + ob.ip[1] * tg[1] + ob.ip[2] * tg[2] + ob.in[0] * tg[3] + ob.in[1] * tg[4] + ob.in[2] * tg[5];
+            jy[3] = ob.ip[0] * ty[0] + ob.ip[1] * ty[1] + ob.ip[2] * ty[2] + ob.in[0] * ty[3] + ob.in[1] * ty[4] + ob.in[2] * ty[5];
+            if (ob.f >= 0) {
+                const double* g6 = gp + 6ll * ob.f;
+                const double* d6 = diag_p + 6ll * ob.f;
+                const double* y6 = yp + 6ll * ob.f;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double ga = g6[a] / d6[a], ya = y6[a];
+                    jg[0] += ob.Jcs[a] * ga, jy[0] += ob.Jcs[a] * ya;
+                    jg[1] += ob.Jcs[6 + a] * ga, jy[1] += ob.Jcs[6 + a] * ya;
+                    jg[2] += ob.Jcs[12 + a] * ga, jy[2] += ob.Jcs[12 + a] * ya;
+                    jg[3] += ob.JIc[a] * ga, jy[3] += ob.JIc[a] * ya;
+                    jg[4] += ob.JNc[a] * ga, jy[4] += ob.JNc[a] * ya;
+                    jg[5] += ob.JNc[6 + a] * ga, jy[5] += ob.JNc[6 + a] * ya;
+                    jg[6] += ob.JNc[12 + a] * ga, jy[6] += ob.JNc[12 + a] * ya;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int gi = c.gi[k];
+                jg[3] += ob.ag[k] * (gg[gi] / diag_g[gi]);
+                jy[3] += ob.ag[k] * yg[gi];
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                acc[3] += jg[k] * jg[k];
+                acc[4] += jg[k] * jy[k];
+                acc[5] += jy[k] * jy[k];
+                acc[6] += jg[k] * r7[k];
+                acc[7] += jy[k] * r7[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) block_atomic_sum(acc[k], &sums[k], s_red);
+}
+
+// shared-block terms of g'.g', g'.gn', gn'.gn'
+__global__ void phong_dogleg_global_kernel(int n_g, const int* __restrict__ g_used, const double* __restrict__ gg,
+                                           const double* __restrict__ diag_g, const double* __restrict__ yg,
+                                           double* __restrict__ sums) {
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int k = threadIdx.x; k < n_g; k += blockDim.x)
+        if (g_used[k]) {
+            const double g = gg[k], d2 = diag_g[k], y = yg[k];
+            a0 += g * g / d2;
+            a1 -= g * y;
+            a2 += d2 * y * y;
+        }
+    a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[0], a0);
+        atomicAdd(&sums[1], a1);
+        atomicAdd(&sums[2], a2);
+    }
+}
+
 // Candidate vertices x (+) alpha * delta and the cost there (poses_cand / gx_cand already formed).
 template <int LW>
 __global__ void __launch_bounds__(PB_WARPS * 32)
@@ -592,6 +722,7 @@ __global__ void phong_gfinalize_kernel(PhongSolveView q, LmDiag dg, double* __re
     if (!q.g_used[k]) {
         Sgg[(long long)k * q.n_g + k] = 1.0;
         bg[k] = 0.0;
+        diag_g[k] = 1.0;
         return;
     }
     const double dd = fmin(fmax(hg[k], dg.min_diag), dg.max_diag);
@@ -740,6 +871,24 @@ void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView
         phong_backsub_kernel<16><<<vertex_grid((lm_hi - lm_lo + 1) / 2), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
     else
         phong_backsub_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
+    count_launch();
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                                  const double* gp, const double* diag_p, const double* yp, const double* gg, const double* diag_g,
+                                  const double* yg, const double* gv, const double* yv, double* diag_v, double* sc_v, double* sums,
+                                  int max_track_len) {
+    if (lm_hi > lm_lo) {
+        if (max_track_len <= 16)
+            phong_dogleg_products_kernel<16><<<vertex_grid((lm_hi - lm_lo + 1) / 2), PB_WARPS * 32, 0, s>>>(
+                v, q, lm_lo, lm_hi, dg, gp, diag_p, yp, gg, diag_g, yg, gv, yv, diag_v, sc_v, sums);
+        else
+            phong_dogleg_products_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(
+                v, q, lm_lo, lm_hi, dg, gp, diag_p, yp, gg, diag_g, yg, gv, yv, diag_v, sc_v, sums);
+        count_launch();
+    }
+    phong_dogleg_global_kernel<<<1, 128, 0, s>>>(q.n_g, q.g_used, gg, diag_g, yg, sums);
     count_launch();
     CSLAM_CUDA(cudaGetLastError());
 }

@@ -4,14 +4,14 @@
 // File: Phong CSV (dataset_problem_phong.cpp:29-117): `num_states,num_vertices,num_materials`;
 // intrinsics; `var_u,var_v,var_d,var_nx,var_ny,var_nz,var_I`; light position or direction; first
 // pose; rows `t,j,mat_id,u,v,d,I,nx,ny,nz` grouped by timestamp.
-// Trust-region strategy: Levenberg-Marquardt (the reference sets SUBSPACE_DOGLEG +
-// SPARSE_NORMAL_CHOLESKY, :87-90; DOGLEG is built for the stereo / sun / prior problems only).
+// Trust-region strategy: SUBSPACE_DOGLEG with an exact (SPARSE_NORMAL_CHOLESKY-equivalent) linear solve, as the
+// reference sets it (:85-87); `--strategy lm` runs Levenberg-Marquardt instead.
 // --multistage runs the reference's three solves per window: stage 1 poses and points without
 // lighting (:94-98), stage 2 lighting only with every pose and position constant (:207-231), stage 3
 // everything jointly (:249-252).
 //
 //   usage: dataset_ba_phong_b200 <input_file> [--nolight | --dirlight] [--window N] [--multistage]
-//          [--max-iters M] [--material-by-observation]
+//          [--max-iters M] [--material-by-observation] [--strategy dogleg|lm]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +21,8 @@
 #include "dataset.hpp"
 
 using namespace cslam_b200;
+
+static bool g_dogleg = true;
 
 struct PhongDataset {
     unsigned num_states = 0, num_vertices = 0, num_materials = 0;
@@ -156,8 +158,10 @@ static void solve_stage(PhongDataset& d, unsigned k1, unsigned k2, bool use_ligh
         problem.SetTextureBounds(0., 1.);             // :177-181
         problem.SetLightDirectional(d.directional);   // :199-203
     }
-    problem.options.max_num_iterations = max_iters;   // :85 (1000)
-    problem.options.use_nonmonotonic_steps = 1;       // :86
+    problem.options.max_num_iterations = max_iters;   // :83 (1000)
+    problem.options.use_nonmonotonic_steps = 1;       // :84
+    problem.options.trust_region_strategy = g_dogleg ? 1 : 0;  // :85 ceres::DOGLEG
+    problem.options.dogleg_type = 1;                  // :86 ceres::SUBSPACE_DOGLEG
     Summary summary;
     problem.Solve(&summary);
     std::cout << summary.BriefReport() << std::endl << std::endl;
@@ -198,7 +202,7 @@ static void write_outputs(const PhongDataset& d, const std::string& filename) {
 int main(int argc, char** argv) {
     const std::string usage(
         "usage: dataset_ba_phong_b200 <input_file> [--nolight | --dirlight] [--window N] [--multistage] [--max-iters M] "
-        "[--material-by-observation]");
+        "[--material-by-observation] [--strategy dogleg|lm]");
     if (argc < 2) {
         std::cerr << usage << std::endl;
         return EXIT_FAILURE;
@@ -215,6 +219,7 @@ int main(int argc, char** argv) {
         else if (flag == "--window" && argc > a + 1) use_window = true, window = unsigned(std::atoi(argv[++a]));
         else if (flag == "--max-iters" && argc > a + 1) max_iters = std::atoi(argv[++a]);
         else if (flag == "--material-by-observation") by_obs = true;
+        else if (flag == "--strategy" && argc > a + 1) g_dogleg = std::string(argv[++a]) != "lm";
         else {
             std::cerr << usage << std::endl;
             return EXIT_FAILURE;

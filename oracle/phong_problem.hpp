@@ -23,7 +23,8 @@
 // The linear solve eliminates each vertex's (position, normal) 6x6 block exactly and factors the
 // dense reduced system over [free poses | materials | textures | light] with Cholesky — an exact
 // solve of the normal equations, i.e. what SPARSE_SCHUR / SPARSE_NORMAL_CHOLESKY return up to
-// rounding.  DOGLEG (what the driver sets, :88-89) is SURVEY.md §8f-3.
+// rounding.  trust_region_strategy = 1: Ceres' DoglegStrategy (what the driver sets, :88-89), the same
+// restatement as problem.hpp's over [poses | vertices | shared blocks].
 #pragma once
 #include "problem.hpp"
 
@@ -619,6 +620,170 @@ class PhongProblem {
         auto clampd = [&](double v) { return std::min(std::max(v, opt.min_lm_diagonal), opt.max_lm_diagonal); };
         int iteration = 0;
         std::vector<double> yc, yv, yg, dc(6 * size_t(nf)), dv(6 * na), dg(ng), sdc, sdv, sdg;
+
+        // ---- DoglegStrategy (dataset_ba_phong.cpp:88-89 sets DOGLEG / SUBSPACE_DOGLEG) ------------------
+        // The same restatement as problem.hpp's, over the flat vector [poses | vertices | shared blocks] in
+        // the coordinates step' = D step, D = sqrt(clamp(diag(J^T J))) of the Jacobi-scaled Jacobian.
+        const size_t NC = 6 * size_t(nf), NV = 6 * na, NT = NC + NV + size_t(ng);
+        double dl_mu = 1e-8, dl_alpha = 0.0, dl_step_norm = 0.0;
+        bool dl_reuse = false, dl_1d = false;
+        std::vector<double> dlD, dlg, dln, dlu0, dlu1;
+        double sub_B[4] = {0, 0, 0, 0}, sub_g[2] = {0, 0};
+        auto jv_flat = [&](const std::vector<double>& t, std::vector<double>& out) {
+            out.assign(7 * n_obs(), 0.0);
+            for (size_t i = 0; i < n_obs(); ++i) {
+                const int f = st.cam_free[cam[i]], a = st.v_active[vtx[i]];
+                int gi[7];
+                gidx_of(vtx[i], gi);
+                for (int rr = 0; rr < 7; ++rr) {
+                    double m = 0;
+                    for (int c = 0; c < 6; ++c) {
+                        if (f >= 0) m += L.Ac[42 * i + 6 * rr + c] * sc.c[6 * size_t(f) + c] * t[6 * size_t(f) + c];
+                        m += L.Av[42 * i + 6 * rr + c] * sc.v[6 * size_t(a) + c] * t[NC + 6 * size_t(a) + c];
+                    }
+                    if (rr == 3)
+                        for (int q = 0; q < 7; ++q) m += L.ag[7 * i + q] * sc.g[gi[q]] * t[NC + NV + gi[q]];
+                    out[7 * i + rr] = m;
+                }
+            }
+        };
+        auto dotf = [](const std::vector<double>& a, const std::vector<double>& b2) {
+            double v = 0;
+            for (size_t i = 0; i < a.size(); ++i) v += a[i] * b2[i];
+            return v;
+        };
+        auto traditional_step = [&](std::vector<double>& sp) {
+            const double gnorm = std::sqrt(dotf(dlg, dlg)), nnorm = std::sqrt(dotf(dln, dln));
+            double cg = 0, cn = 0;
+            if (nnorm <= radius) {
+                cn = 1.0;
+                dl_step_norm = nnorm;
+            } else if (gnorm * dl_alpha >= radius) {
+                cg = -(radius / gnorm);
+                dl_step_norm = radius;
+            } else {
+                const double b_dot_a = -dl_alpha * dotf(dlg, dln);
+                const double a2 = std::pow(dl_alpha * gnorm, 2.0);
+                const double bma2 = a2 - 2 * b_dot_a + std::pow(nnorm, 2);
+                const double c = b_dot_a - a2;
+                const double d = std::sqrt(c * c + bma2 * (std::pow(radius, 2.0) - a2));
+                const double beta = (c <= 0) ? (d - c) / bma2 : (radius * radius - a2) / (d + c);
+                cg = -dl_alpha * (1.0 - beta);
+                cn = beta;
+                dl_step_norm = -1.0;
+            }
+            sp.resize(NT);
+            for (size_t i = 0; i < NT; ++i) sp[i] = cg * dlg[i] + cn * dln[i];
+            if (dl_step_norm < 0.0) dl_step_norm = std::sqrt(dotf(sp, sp));
+        };
+        auto subspace_step = [&](std::vector<double>& sp) {
+            const double nnorm = std::sqrt(dotf(dln, dln));
+            if (nnorm <= radius) {
+                sp = dln;
+                dl_step_norm = nnorm;
+                return;
+            }
+            if (dl_1d) {
+                const double gnorm = std::sqrt(dotf(dlg, dlg));
+                sp.resize(NT);
+                for (size_t i = 0; i < NT; ++i) sp[i] = -(radius / gnorm) * dlg[i];
+                dl_step_norm = radius;
+                return;
+            }
+            double xb[2];
+            if (!dogleg_boundary_minimum(sub_B, sub_g, radius, xb)) {
+                traditional_step(sp);
+                return;
+            }
+            sp.resize(NT);
+            for (size_t i = 0; i < NT; ++i) sp[i] = xb[0] * dlu0[i] + xb[1] * dlu1[i];
+            dl_step_norm = radius;
+        };
+        // returns false when no valid step exists; sets lin_it to the number of linear solves
+        auto dogleg_compute_step = [&](int& lin_it) -> bool {
+            lin_it = 0;
+            if (!dl_reuse) {
+                dl_reuse = true;
+                dlD.resize(NT);
+                dlg.resize(NT);
+                for (size_t i = 0; i < NC; ++i) {
+                    dlD[i] = std::sqrt(clampd(cn_c[i] * sc.c[i] * sc.c[i]));
+                    dlg[i] = gc[i] * sc.c[i] / dlD[i];
+                }
+                for (size_t i = 0; i < NV; ++i) {
+                    dlD[NC + i] = std::sqrt(clampd(cn_v[i] * sc.v[i] * sc.v[i]));
+                    dlg[NC + i] = gv[i] * sc.v[i] / dlD[NC + i];
+                }
+                for (int q = 0; q < ng; ++q) {
+                    dlD[NC + NV + q] = std::sqrt(clampd(cn_g[q] * sc.g[q] * sc.g[q]));
+                    dlg[NC + NV + q] = gg[q] * sc.g[q] / dlD[NC + NV + q];
+                }
+                std::vector<double> t(NT), Jg;
+                for (size_t i = 0; i < NT; ++i) t[i] = dlg[i] / dlD[i];
+                jv_flat(t, Jg);
+                dl_alpha = dotf(dlg, dlg) / dotf(Jg, Jg);
+                bool ok = false;
+                while (dl_mu < 1.0) {
+                    for (size_t i = 0; i < NC; ++i) Dc[i] = dlD[i] * std::sqrt(dl_mu);
+                    for (size_t i = 0; i < NV; ++i) Dv[i] = dlD[NC + i] * std::sqrt(dl_mu);
+                    for (int q = 0; q < ng; ++q) Dg[q] = dlD[NC + NV + q] * std::sqrt(dl_mu);
+                    ok = schur_solve(st, L, sc, Dc, Dv, Dg, opt.num_threads, yc, yv, yg);
+                    if (ok) {
+                        for (double v : yc) ok = ok && std::isfinite(v);
+                        for (double v : yv) ok = ok && std::isfinite(v);
+                        for (double v : yg) ok = ok && std::isfinite(v);
+                    }
+                    if (ok) break;
+                    dl_mu *= 10.0;
+                }
+                if (!ok) return false;
+                dln.resize(NT);
+                for (size_t i = 0; i < NC; ++i) dln[i] = -dlD[i] * yc[i];
+                for (size_t i = 0; i < NV; ++i) dln[NC + i] = -dlD[NC + i] * yv[i];
+                for (int q = 0; q < ng; ++q) dln[NC + NV + q] = -dlD[NC + NV + q] * yg[q];
+                if (opt.dogleg_type == 1) {
+                    const double ng2 = dotf(dlg, dlg), nn2 = dotf(dln, dln);
+                    const bool g_first = ng2 >= nn2;
+                    const std::vector<double>&av = g_first ? dlg : dln, &bv = g_first ? dln : dlg;
+                    const double r00 = std::sqrt(std::max(ng2, nn2));
+                    if (!(r00 > 0.0)) return false;
+                    dlu0.resize(NT);
+                    dlu1.resize(NT);
+                    for (size_t i = 0; i < NT; ++i) dlu0[i] = av[i] / r00;
+                    const double pr = dotf(dlu0, bv);
+                    for (size_t i = 0; i < NT; ++i) dlu1[i] = bv[i] - pr * dlu0[i];
+                    const double r11 = std::sqrt(dotf(dlu1, dlu1));
+                    dl_1d = !(r11 > 2.0 * std::numeric_limits<double>::epsilon() * r00);
+                    if (!dl_1d) {
+                        for (auto& v : dlu1) v /= r11;
+                        sub_g[0] = dotf(dlu0, dlg);
+                        sub_g[1] = dotf(dlu1, dlg);
+                        std::vector<double> J0, J1;
+                        for (size_t i = 0; i < NT; ++i) t[i] = dlu0[i] / dlD[i];
+                        jv_flat(t, J0);
+                        for (size_t i = 0; i < NT; ++i) t[i] = dlu1[i] / dlD[i];
+                        jv_flat(t, J1);
+                        sub_B[0] = dotf(J0, J0);
+                        sub_B[1] = sub_B[2] = dotf(J0, J1);
+                        sub_B[3] = dotf(J1, J1);
+                    }
+                }
+                lin_it = 1;
+            }
+            std::vector<double> sp;
+            if (opt.dogleg_type == 1)
+                subspace_step(sp);
+            else
+                traditional_step(sp);
+            yc.resize(NC);
+            yv.resize(NV);
+            yg.resize(size_t(ng));
+            for (size_t i = 0; i < NC; ++i) yc[i] = -sp[i] / dlD[i];
+            for (size_t i = 0; i < NV; ++i) yv[i] = -sp[NC + i] / dlD[NC + i];
+            for (int q = 0; q < ng; ++q) yg[q] = -sp[NC + NV + q] / dlD[NC + NV + q];
+            return true;
+        };
+        const bool use_dogleg = opt.trust_region_strategy == 1;
         for (;;) {
             if (iteration > 0) {
                 if (step_ok_prev) {
@@ -647,18 +812,26 @@ class PhongProblem {
             step_ok_prev = false;
             row = IterationRow{};
             row.iteration = iteration;
-            if (!reuse_diagonal) {
-                for (size_t i = 0; i < diag_c.size(); ++i) diag_c[i] = clampd(cn_c[i] * sc.c[i] * sc.c[i]);
-                for (size_t i = 0; i < diag_v.size(); ++i) diag_v[i] = clampd(cn_v[i] * sc.v[i] * sc.v[i]);
-                for (size_t i = 0; i < diag_g.size(); ++i) diag_g[i] = clampd(cn_g[i] * sc.g[i] * sc.g[i]);
+            bool valid;
+            if (use_dogleg) {
+                int lin_it = 0;
+                valid = dogleg_compute_step(lin_it);
+                row.linear_iterations = lin_it;
+                sum.total_linear_iterations += lin_it;
+            } else {
+                if (!reuse_diagonal) {
+                    for (size_t i = 0; i < diag_c.size(); ++i) diag_c[i] = clampd(cn_c[i] * sc.c[i] * sc.c[i]);
+                    for (size_t i = 0; i < diag_v.size(); ++i) diag_v[i] = clampd(cn_v[i] * sc.v[i] * sc.v[i]);
+                    for (size_t i = 0; i < diag_g.size(); ++i) diag_g[i] = clampd(cn_g[i] * sc.g[i] * sc.g[i]);
+                }
+                for (size_t i = 0; i < Dc.size(); ++i) Dc[i] = std::sqrt(diag_c[i] / radius);
+                for (size_t i = 0; i < Dv.size(); ++i) Dv[i] = std::sqrt(diag_v[i] / radius);
+                for (size_t i = 0; i < Dg.size(); ++i) Dg[i] = std::sqrt(diag_g[i] / radius);
+                valid = schur_solve(st, L, sc, Dc, Dv, Dg, opt.num_threads, yc, yv, yg);
+                row.linear_iterations = 1;
+                sum.total_linear_iterations += 1;
             }
-            for (size_t i = 0; i < Dc.size(); ++i) Dc[i] = std::sqrt(diag_c[i] / radius);
-            for (size_t i = 0; i < Dv.size(); ++i) Dv[i] = std::sqrt(diag_v[i] / radius);
-            for (size_t i = 0; i < Dg.size(); ++i) Dg[i] = std::sqrt(diag_g[i] / radius);
-            bool valid = schur_solve(st, L, sc, Dc, Dv, Dg, opt.num_threads, yc, yv, yg);
             reuse_diagonal = true;
-            row.linear_iterations = 1;
-            sum.total_linear_iterations += 1;
             if (valid) {
                 for (double v : yc) valid = valid && std::isfinite(v);
                 for (double v : yv) valid = valid && std::isfinite(v);
@@ -694,8 +867,13 @@ class PhongProblem {
                     finish(FAILURE, R_INVALID_STEPS);
                     break;
                 }
-                radius = radius / decrease_factor;
-                decrease_factor *= 2.0;
+                if (use_dogleg) {
+                    dl_mu *= 10.0;  // DoglegStrategy::StepIsInvalid
+                    dl_reuse = false;
+                } else {
+                    radius = radius / decrease_factor;
+                    decrease_factor *= 2.0;
+                }
                 row.radius = radius;
                 sum.push_row(row);
                 continue;
@@ -793,10 +971,21 @@ class PhongProblem {
                 column_norms_and_gradient();
                 step_ok_prev = true;
                 row.step_is_successful = 1;
-                radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
-                radius = std::min(opt.max_trust_region_radius, radius);
-                decrease_factor = 2.0;
-                reuse_diagonal = false;
+                if (use_dogleg) {
+                    // DoglegStrategy::StepAccepted
+                    if (row.relative_decrease < 0.25) radius *= 0.5;
+                    if (row.relative_decrease > 0.75) {
+                        radius = std::max(radius, 3.0 * dl_step_norm);
+                        radius = std::min(radius, opt.max_trust_region_radius);
+                    }
+                    dl_mu = std::max(1e-8, 2.0 * dl_mu / 10.0);
+                    dl_reuse = false;
+                } else {
+                    radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * row.relative_decrease - 1.0, 3));
+                    radius = std::min(opt.max_trust_region_radius, radius);
+                    decrease_factor = 2.0;
+                    reuse_diagonal = false;
+                }
                 se_current = cand_cost;
                 se_acc_cand += model_cost_change;
                 se_acc_ref += model_cost_change;
@@ -816,6 +1005,9 @@ class PhongProblem {
                     se_reference = se_candidate;
                     se_acc_ref = se_acc_cand;
                 }
+            } else if (use_dogleg) {
+                radius *= 0.5;  // DoglegStrategy::StepRejected
+                dl_reuse = true;
             } else {
                 radius = radius / decrease_factor;
                 decrease_factor *= 2.0;

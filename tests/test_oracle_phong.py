@@ -99,3 +99,35 @@ def test_phong_oracle_stage2_holds_poses_and_positions():
     assert s.final_cost < s.initial_cost
     # the reported cost includes the dropped stereo blocks: same initial cost as the joint problem
     assert abs(s.initial_cost - pj.solve().initial_cost) < 1e-9 * s.initial_cost
+
+
+@pytest.mark.parametrize("dogleg_type", [0, 1])
+def test_phong_oracle_dogleg(dogleg_type):
+    """dataset_ba_phong.cpp:88-89 sets DOGLEG / SUBSPACE_DOGLEG.  (a) With zero lighting stiffness the
+    lighting oracle's DOGLEG trajectory equals the stereo oracle's (an independent implementation of the
+    same strategy); (b) on a bounded lighting problem LM and DOGLEG reach the same basin."""
+    tr = syn.add_phong(syn.make_track(25, 6, 5, seed=3), shared_textures=True)
+    tr["int_stiffness"] = 0.0
+    tr["W_normal"] = np.zeros(9)
+    kw = dict(max_num_iterations=6, num_threads=4, trust_region_strategy=1, dogleg_type=dogleg_type,
+              initial_trust_region_radius=2.0, **FIXED)
+    pj, sj = orc.build_phong_problem(tr, **kw)
+    summ_j = pj.solve()
+    ps, poses_s, points_s = orc.build_problem(tr, **kw)
+    summ_s = ps.solve()
+    lj, ls = pj.iteration_log(), ps.iteration_log()
+    assert lj.shape == ls.shape
+    assert np.allclose(lj[:, 1], ls[:, 1], rtol=1e-9), "cost trajectory"
+    assert np.allclose(lj[:, 6], ls[:, 6], rtol=1e-7), "radius trajectory"
+    assert np.array_equal(lj[:, 9], ls[:, 9])
+    tr = syn.add_phong(syn.make_track(25, 6, 5, seed=4))
+    out = {}
+    for strat in (0, 1):
+        p, st = orc.build_phong_problem(tr, bounds=True, max_num_iterations=80, num_threads=4, trust_region_strategy=strat,
+                                        dogleg_type=dogleg_type)
+        s = p.solve()
+        assert s.termination_type in (0, 1)
+        out[strat] = s.final_cost
+    # with a material parameter on its bound the projected Gauss-Newton steps of DOGLEG crawl along the face
+    # (every step accepted, tiny): both strategies get within 2 % of each other, far below the initial cost
+    assert abs(out[0] - out[1]) < 2e-2 * out[0] and out[1] < 0.05 * s.initial_cost
