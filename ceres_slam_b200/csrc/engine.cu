@@ -1198,6 +1198,7 @@ void Engine::upload() {
     plan_dense_solver();
     pt.lap("  plan_band_solver");
     d_scal2.alloc(SC_COUNT, stream);
+    d_dmax_tmp.alloc(1, stream);
     if (!suns.empty()) d_suns.upload(suns, stream);
     if (!priors.empty()) d_priors.upload(priors, stream);
     if (ph.active) setup_phong_solve();
@@ -1393,17 +1394,34 @@ void Engine::download() {
         CSLAM_CUDA(cudaStreamSynchronize(stream));
         parallel_d2h(opt.device, h_points, d_raw_pts.p, 3 * size_t(n_points) * sizeof(double));
     }
-    std::vector<double> nrm, gxh;
+    std::vector<double> nrm, gxh, nrm_all;
     if (ph.active) {
         nrm.resize(3 * size_t(n_lm));
         gxh.resize(ph.n_g);
+        if (n_ranks > 1) {
+            // the shards' normals are summed over the ranks into the caller's order, like the points above
+            DBuf<double> z4;
+            z4.alloc(4 * size_t(n_points), stream);
+            CSLAM_CUDA(cudaMemsetAsync(z4.p, 0, z4.bytes(), stream));
+            launch_scatter_points4(stream, n_lm, d_lm_user.p, ph.normals_best.p, z4.p);
+            comm_allreduce_sum(nccl_comm, z4.p, 4 * size_t(n_points), stream);
+            nrm_all.resize(4 * size_t(n_points));
+            CSLAM_CUDA(cudaMemcpyAsync(nrm_all.data(), z4.p, nrm_all.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CSLAM_CUDA(cudaStreamSynchronize(stream));
+            z4.release_async(stream);
+        }
         if (n_lm) CSLAM_CUDA(cudaMemcpyAsync(nrm.data(), ph.normals_best.p, nrm.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CSLAM_CUDA(cudaMemcpyAsync(gxh.data(), ph.gx_best.p, gxh.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     for (int k : free_cams_h) std::memcpy(h_poses + 12 * size_t(k), &pos[12 * size_t(k)], 96);
     if (ph.active) {
-        for (int j = 0; j < n_lm; ++j) std::memcpy(h_normals + 3 * size_t(lm_user_h[j]), &nrm[3 * size_t(j)], 24);
+        if (n_ranks > 1) {
+            for (size_t j = 0; j < size_t(n_points); ++j)
+                if (nrm_all[4 * j + 3] != 0.0) std::memcpy(h_normals + 3 * j, &nrm_all[4 * j], 24);  // weight slot: owned by some rank
+        } else {
+            for (int j = 0; j < n_lm; ++j) std::memcpy(h_normals + 3 * size_t(lm_user_h[j]), &nrm[3 * size_t(j)], 24);
+        }
         const int t0 = 3 * ph.n_mat, l0 = t0 + ph.n_tex;
         for (int k = 0; k < ph.n_g; ++k) {
             if (!ph.g_used_h[k]) continue;
@@ -1422,7 +1440,6 @@ void Engine::download() {
 // -------------------------------------------------------------------------------------------------
 void Engine::check_phong_solve() {
     auto not_impl = [](const char* m) { throw NotImplemented(m); };
-    if (n_ranks > 1) not_impl("lighting solve: single GPU only");
     if (!h_normals || !h_material_id || !h_phong || !h_light) throw std::invalid_argument("vertices / materials / light not set");
     if (n_vertices != n_points) throw std::invalid_argument("one normal / material id per point expected");
     if (!h_tex_shared) not_impl("lighting solve: textures must be shared blocks (cslam_set_textures)");
@@ -1457,7 +1474,16 @@ void Engine::setup_phong_solve() {
         for (int k = 0; k < 3; ++k) ph.g_used_h[3 * vm[j] + k] = 1;
         ph.g_used_h[t0 + vt[j]] = 1;
     }
-    if (n_lm)
+    if (n_ranks > 1) {
+        // the set of referenced shared columns must be the same on every rank (it decides which columns of the
+        // all-reduced border exist): take it from every observed vertex, not from this rank's shard
+        for (uint64_t i = 0; i < n_st; ++i) {
+            const uint32_t u = st_pt[i];
+            for (int k = 0; k < 3; ++k) ph.g_used_h[3 * int(h_material_id[u]) + k] = 1;
+            ph.g_used_h[t0 + int(h_texture_id[u])] = 1;
+        }
+    }
+    if (n_lm || (n_ranks > 1 && n_st))
         for (int k = 0; k < 3; ++k) ph.g_used_h[l0 + k] = 1;
     parallel_chunks(size_t(n_obs), size_t(1) << 16, [&](int, size_t c0, size_t c1) {
         for (size_t e = c0; e < c1; ++e) {
@@ -1597,6 +1623,13 @@ void Engine::phong_linear_solve(int* iters, bool* ok) {
         launch_fill(stream, d_pscal.p, PS_COUNT, 0.0);
     }
     launch_phong_border_solve(stream, ph.n_g, int(nf6), ph.Scg, ph.X.p, ph.Sgg, ph.bg, ph.T.p, ph.yg.p, d_yp.p, d_pscal.p);
+    if (n_ranks > 1) {
+        // every rank solved the same (all-reduced) system; rank 0's iterate is adopted everywhere so that the
+        // ranks stay bit-identical (same accept / reject decisions), as in run_pcg
+        if (nf6) comm_broadcast(nccl_comm, d_yp.p, nf6, 0, stream);
+        comm_broadcast(nccl_comm, ph.yg.p, size_t(ph.n_g), 0, stream);
+        comm_broadcast(nccl_comm, d_pscal.p, PS_COUNT, 0, stream);
+    }
     double ps[PS_COUNT];
     read_scalars(d_pscal.p, ps, PS_COUNT);
     prof_end(CSLAM_K_PCG);
@@ -1657,8 +1690,8 @@ void Engine::gradient_norm_pass() {
     DevView v = view(d_poses.p, d_points.p);
     // SC_GRADMAX / SC_XNORM2_CUR are not touched by the Schur kernels
     if (ph.active) {
-        launch_gradnorm(stream, v, 0, 0, d_gp, d_gl.p, d_scal, 1);
-        launch_phong_gradnorm(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, ph.gv.p, ph.gg, d_scal, 1);
+        launch_gradnorm(stream, v, 0, 0, d_gp, d_gl.p, d_scal, rank == 0);
+        launch_phong_gradnorm(stream, v, phong_solve_view(ph.normals.p, ph.gx.p), 0, n_lm, ph.gv.p, ph.gg, d_scal, rank == 0);
     } else {
         launch_gradnorm(stream, v, 0, n_lm, d_gp, d_gl.p, d_scal, rank == 0);
     }
@@ -1783,17 +1816,28 @@ void Engine::phong_step(const LmDiag& dg, double* sc2) {
     prof_begin(CSLAM_K_BACKSUB);
     d_scal2.zero(stream);
     launch_phong_backsub(stream, v, q, 0, n_lm, dg, d_yp.p, ph.yg.p, ph.gv.p, ph.yv.p, d_scal2.p, ph.max_track);
-    if (bounded) {
+    if (bounded && rank == 0) {
         launch_dot(stream, d_gp, d_yp.p, 6ll * n_free, d_scal2.p + SC_LS_GY);
         launch_dot(stream, ph.gg, ph.yg.p, ph.n_g, d_scal2.p + SC_LS_GY);
         launch_absmax_scaled(stream, d_yp.p, d_sc_p.p, 6ll * n_free, d_scal2.p + SC_LS_DMAX);
         launch_absmax_scaled(stream, ph.yg.p, ph.sc_g.p, ph.n_g, d_scal2.p + SC_LS_DMAX);
     }
     launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_yp.p, ph.yg.p, ph.yv.p, d_poses_cand.p, ph.gx_cand.p, d_points_cand.p,
-                           ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
+                           ph.normals_cand.p, d_scal2.p, rank == 0, ph.max_track);
+    phong_reduce_scal2();
     read_scalars(d_scal2.p, sc2, SC_COUNT);
     if (bounded && sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0) phong_line_search(d_yp.p, ph.yg.p, ph.yv.p, sc2);
     prof_end(CSLAM_K_BACKSUB);
+}
+
+// Candidate / model scalars over the ranks: everything is a sum except the line search's |delta|_inf
+void Engine::phong_reduce_scal2() {
+    if (n_ranks <= 1) return;
+    // the max slot is reduced on its own copy, then written back over the (meaningless) sum
+    CSLAM_CUDA(cudaMemcpyAsync(d_dmax_tmp.p, d_scal2.p + SC_LS_DMAX, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    comm_allreduce_max(nccl_comm, d_dmax_tmp.p, 1, stream);
+    comm_allreduce_sum(nccl_comm, d_scal2.p, SC_COUNT, stream);
+    CSLAM_CUDA(cudaMemcpyAsync(d_scal2.p + SC_LS_DMAX, d_dmax_tmp.p, sizeof(double), cudaMemcpyDeviceToDevice, stream));
 }
 
 // TrustRegionMinimizer::DoLineSearch for a bounded problem: Armijo search along the step (yp, yg, yv), starting
@@ -1831,7 +1875,8 @@ void Engine::phong_line_search(const double* yp, const double* yg, const double*
             a_cur = a_new;
             d_scal2.zero(stream);
             launch_phong_candidate(stream, v, q, 0, n_lm, a_cur, yp, yg, yv, d_poses_cand.p, ph.gx_cand.p,
-                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
+                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, rank == 0, ph.max_track);
+            phong_reduce_scal2();
             read_scalars(d_scal2.p, sc2, SC_COUNT);
             f_cur = sc2[SC_CAND_COST];
         }
@@ -1839,7 +1884,8 @@ void Engine::phong_line_search(const double* yp, const double* yg, const double*
             // the search failed: Ceres keeps the full step
             d_scal2.zero(stream);
             launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, yp, yg, yv, d_poses_cand.p, ph.gx_cand.p,
-                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
+                                   d_points_cand.p, ph.normals_cand.p, d_scal2.p, rank == 0, ph.max_track);
+            phong_reduce_scal2();
             read_scalars(d_scal2.p, sc2, SC_COUNT);
         }
         sc2[SC_MODEL] = model;
@@ -1880,10 +1926,11 @@ void Engine::phong_dogleg_step(int* lin_iters, bool* valid, double* sc2) {
         launch_phong_backsub(stream, v, q, 0, n_lm, dg, d_yp.p, ph.yg.p, ph.gv.p, ph.yv.p, d_scal2.p, ph.max_track);
         d_dsums.zero(stream);
         launch_dogleg_products(stream, v, 0, 0, dg, nullptr, 0, nullptr, 0, d_gp, d_diag_p.p, d_yp.p, nullptr, nullptr, nullptr,
-                               d_dsums.p, 1);
+                               d_dsums.p, rank == 0);
         launch_phong_dogleg_products(stream, v, q, 0, n_lm, dg, d_gp, d_diag_p.p, d_yp.p, ph.gg, ph.diag_g.p, ph.yg.p, ph.gv.p,
-                                     ph.yv.p, ph.diag_v.p, ph.sc_v.p, d_dsums.p, ph.max_track);
+                                     ph.yv.p, ph.diag_v.p, ph.sc_v.p, d_dsums.p, ph.max_track, rank == 0);
         prof_end(CSLAM_K_BACKSUB);
+        allreduce_small(d_dsums.p, DG_COUNT);
         double sm[DG_COUNT];
         read_scalars(d_dsums.p, sm, DG_COUNT);
         DoglegModel& m = dl.model;
@@ -1908,15 +1955,18 @@ void Engine::phong_dogleg_step(int* lin_iters, bool* valid, double* sc2) {
     launch_dogleg_combine(stream, 6ll * n_lm, c1, c2, ph.gv.p, ph.diag_v.p, ph.yv.p, ph.Yv.p);
     d_scal2.zero(stream);
     if (bounded) {
-        launch_dot(stream, d_gp, d_Yp.p, 6ll * n_free, d_scal2.p + SC_LS_GY);
-        launch_dot(stream, ph.gg, ph.Yg.p, ph.n_g, d_scal2.p + SC_LS_GY);
+        if (rank == 0) {
+            launch_dot(stream, d_gp, d_Yp.p, 6ll * n_free, d_scal2.p + SC_LS_GY);
+            launch_dot(stream, ph.gg, ph.Yg.p, ph.n_g, d_scal2.p + SC_LS_GY);
+            launch_absmax_scaled(stream, d_Yp.p, d_sc_p.p, 6ll * n_free, d_scal2.p + SC_LS_DMAX);
+            launch_absmax_scaled(stream, ph.Yg.p, ph.sc_g.p, ph.n_g, d_scal2.p + SC_LS_DMAX);
+        }
         launch_dot(stream, ph.gv.p, ph.Yv.p, 6ll * n_lm, d_scal2.p + SC_LS_GY);
-        launch_absmax_scaled(stream, d_Yp.p, d_sc_p.p, 6ll * n_free, d_scal2.p + SC_LS_DMAX);
-        launch_absmax_scaled(stream, ph.Yg.p, ph.sc_g.p, ph.n_g, d_scal2.p + SC_LS_DMAX);
         launch_absmax_scaled(stream, ph.Yv.p, ph.sc_v.p, 6ll * n_lm, d_scal2.p + SC_LS_DMAX);
     }
     launch_phong_candidate(stream, v, q, 0, n_lm, 1.0, d_Yp.p, ph.Yg.p, ph.Yv.p, d_poses_cand.p, ph.gx_cand.p, d_points_cand.p,
-                           ph.normals_cand.p, d_scal2.p, 1, ph.max_track);
+                           ph.normals_cand.p, d_scal2.p, rank == 0, ph.max_track);
+    phong_reduce_scal2();
     read_scalars(d_scal2.p, sc2, SC_COUNT);
     sc2[SC_MODEL] = dl.model.model_cost_change(c1, c2);
     *valid = sc2[SC_NONFINITE] == 0.0 && sc2[SC_MODEL] > 0.0;

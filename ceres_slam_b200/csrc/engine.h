@@ -378,6 +378,8 @@ class Engine {
     void copy_phong_best();
     void phong_step(const LmDiag& dg, double* sc2);
     void phong_line_search(const double* yp, const double* yg, const double* yv, double* sc2);
+    void phong_reduce_scal2();
+    DBuf<double> d_dmax_tmp;
     void phong_dogleg_step(int* lin_iters, bool* valid, double* sc2);
     PhongSolveView phong_solve_view(const double* normals, const double* gx) const;
     PhongSystem phong_system();

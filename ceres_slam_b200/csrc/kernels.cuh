@@ -114,7 +114,7 @@ void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView
 void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
                                   const double* gp, const double* diag_p, const double* yp, const double* gg, const double* diag_g,
                                   const double* yg, const double* gv, const double* yv, double* diag_v, double* sc_v, double* sums,
-                                  int max_track_len);
+                                  int max_track_len, int count_shared);
 void launch_phong_candidate(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, double alpha,
                             const double* yp, const double* yg, const double* yv, double* poses_cand, double* gx_cand,
                             double* points_cand, double* normals_cand, double* scal2, int count_shared, int max_track_len);

@@ -878,7 +878,7 @@ void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView
 void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
                                   const double* gp, const double* diag_p, const double* yp, const double* gg, const double* diag_g,
                                   const double* yg, const double* gv, const double* yv, double* diag_v, double* sc_v, double* sums,
-                                  int max_track_len) {
+                                  int max_track_len, int count_shared) {
     if (lm_hi > lm_lo) {
         if (max_track_len <= 16)
             phong_dogleg_products_kernel<16><<<vertex_grid((lm_hi - lm_lo + 1) / 2), PB_WARPS * 32, 0, s>>>(
@@ -888,8 +888,10 @@ void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongS
                 v, q, lm_lo, lm_hi, dg, gp, diag_p, yp, gg, diag_g, yg, gv, yv, diag_v, sc_v, sums);
         count_launch();
     }
-    phong_dogleg_global_kernel<<<1, 128, 0, s>>>(q.n_g, q.g_used, gg, diag_g, yg, sums);
-    count_launch();
+    if (count_shared) {
+        phong_dogleg_global_kernel<<<1, 128, 0, s>>>(q.n_g, q.g_used, gg, diag_g, yg, sums);
+        count_launch();
+    }
     CSLAM_CUDA(cudaGetLastError());
 }
 

@@ -72,6 +72,38 @@ def main():
         if rank == 0:
             print(f"linear_solver={linear_solver}: {world}-GPU solve matches 1-GPU "
                   f"(cost {sn.initial_cost:.6e} -> {sn.final_cost:.6e}, {sn.num_iterations} iterations)")
+    # the joint lighting solve of dataset_ba_phong (config 3): vertices sharded, the arrowhead reduced system
+    # [S_cc S_cg; S_gc S_gg] all-reduced; LM with the box and SUBSPACE_DOGLEG as the reference sets it
+    trp = syn.add_phong(syn.make_track(120, 30, 6, seed=79), shared_textures=True)
+    for strategy in (0, 1):
+        kwp = dict(max_num_iterations=5, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0, device=local,
+                   trust_region_strategy=strategy, dogleg_type=1)
+        p1, st1 = syn.build_phong_problem(trp, bounds=True, **kwp)
+        s1 = p1.solve()
+        log1 = p1.iteration_log()
+        pn, stn = syn.build_phong_problem(trp, bounds=True, **kwp)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            assert lib.comm_unique_id(buf) == 0
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        pn.attach_comm(world, rank, uid.cpu().numpy())
+        sn = pn.solve()
+        logn = pn.iteration_log()
+        assert sn.num_iterations == s1.num_iterations, (sn.num_iterations, s1.num_iterations)
+        assert np.allclose(logn[:, 1], log1[:, 1], rtol=1e-9), (logn[:, 1], log1[:, 1])
+        assert np.array_equal(logn[:, 9], log1[:, 9])
+        for k in ("poses", "points", "normals", "phong", "textures", "light"):
+            assert np.abs(stn[k] - st1[k]).max() <= 1e-8 * max(1.0, np.abs(st1[k]).max()), k
+            t = torch.from_numpy(np.ascontiguousarray(stn[k], dtype=np.float64).copy()).cuda()
+            t0 = t.clone()
+            dist.broadcast(t0, 0)
+            assert torch.equal(t, t0), k          # every rank returns the complete, identical solution
+        if rank == 0:
+            print(f"lighting solve, strategy {strategy}: {world}-GPU solve matches 1-GPU "
+                  f"(cost {sn.initial_cost:.6e} -> {sn.final_cost:.6e}, {sn.num_iterations} iterations)")
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_OK")
