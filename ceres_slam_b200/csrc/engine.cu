@@ -1452,7 +1452,8 @@ void Engine::check_phong_solve() {
     ph.n_mat = int(n_materials);
     ph.n_tex = int(n_tex_shared);
     ph.n_g = 3 * ph.n_mat + ph.n_tex + 3;
-    if (ph.n_g > 96) not_impl("lighting solve: at most 96 shared columns (3 per material + 1 per texture + 3)");
+    // the dense border system [n_g][n_g + 1] is factored inside one CTA's shared memory (227 KB)
+    if (ph.n_g > 160) not_impl("lighting solve: at most 160 shared columns (3 per material + 1 per texture + 3)");
     ph.max_track = 0;
     for (int j = 0; j < n_lm; ++j) {
         if (lm_cnt_h[j] > 32) not_impl("lighting solve: at most 32 observations per vertex");

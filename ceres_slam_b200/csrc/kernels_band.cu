@@ -23,6 +23,7 @@
 // block steps, which is why the chain is cut and why the step is kept to two CTA barriers.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "chol_chain.cuh"
@@ -328,6 +329,304 @@ __global__ void __launch_bounds__(BL_THREADS) band_leaf_kernel(BandView B) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Leaf kernel, second generation (leaves with a left spike, W <= 9).
+//
+// band_leaf_kernel above keeps the window in shared memory and spends ~7 instructions per FMA on index
+// arithmetic and shared-memory round trips (ncu: 43 % of the issue slots, 17 % of the FP64 pipe, 2.8 us
+// per block step).  Here every COLUMN of the moving window belongs to one thread that keeps it in
+// registers, statically indexed, sliding down by six registers per block step (the same trick as the
+// cyclic-reduction kernel), and the step is a pipeline of five warp roles joined by named barriers:
+//   A (2 warps)  one thread per scalar column of the band window [6 (W+1) rows]: rank-6 trailing update
+//                a[i] -= L_col[i] . L_col[j]; the columns of the NEXT pivot block are updated first and
+//                handed to the pivot warp while the rest of the update is still running (look-ahead);
+//   pivot        6x6 Cholesky of the pivot block and its inverse (potrf6_inv_reg);
+//   panel        L_ik = A_ik Lkk^-T for the block column (written to shared memory and to Lbuf);
+//   G (2 warps)  one thread per border column [rhs | left spike]: X_k = Lkk^-1 G_k, then the same
+//                rank-6 update of its column;
+//   T (2 warps)  one thread per border column: X_left^T [x_r | X_left] accumulated in registers.
+// A, G and T each issue 6 (6W) FMAs per thread and step against L broadcast from shared memory:
+// ~1 LDS.128 per 4 FMAs and no address arithmetic.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+struct Leaf2 {
+    static constexpr int W1 = W + 1, NR = 6 * W1, NB = 6 * W, GC = 1 + 6 * W;
+    static constexpr int XLD = 2 + NB;  // X_k row in shared memory: [x_r, pad, spike columns] (even stride)
+    static constexpr int THREADS = 256;
+};
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int W>
+__global__ void __launch_bounds__(256, 1) band_leaf2_kernel(BandView B) {
+    using C = Leaf2<W>;
+    constexpr int W1 = C::W1, NR = C::NR, NB = C::NB, GC = C::GC, XLD = C::XLD, b = 6 * W;
+    // barrier ids and thread counts (arrivals + waiters)
+    constexpr int B1A = 1, B1B = 2, B2 = 3, B3 = 4, B4 = 5, B5 = 6;
+    constexpr int N1A = 64 + 32, N1B = 64 + 64 + 32 + 32, N2 = 32 + 32 + 64, N3 = 32 + 64 + 64, N4 = 128, N5 = 128;
+    __shared__ __align__(16) double Pcol[NR * 6];   // the pivot block's columns: Pcol[row][c]
+    __shared__ __align__(16) double Linv[36];
+    __shared__ __align__(16) double Lcol[NB * 6];   // L_{k+d,k} rows below the pivot block
+    __shared__ __align__(16) double Xk[6 * XLD];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, role = tid >> 6, t = tid & 63;
+    const int p = blockIdx.x;
+    const int s = p * B.m;
+    const int e = min(B.n, s + B.m);
+    const bool has_left = p > 0, has_right = p < B.P - 1;
+    const int ie = has_right ? e - W : e;
+    if (tid == 0) s_bad = 0;
+    // A[6 I + rr][6 J + c] for block row I >= block column J inside the band (0 outside the leaf or the band)
+    auto band_val = [&](int I, int J, int rr, int c) -> double {
+        if (I >= e || I - J > B.w || J < 0) return 0.0;
+        const int ent = B.band_idx[(long long)J * (B.w + 1) + (I - J)];
+        return ent < 0 ? 0.0 : B.S[36ll * ent + 6 * c + rr];
+    };
+    __syncthreads();
+    if (ie <= s) {
+        // nothing to eliminate (cannot happen with the leaf sizes the planner picks); fall through to the outputs
+    }
+    if (role == 0) {
+        // ================= A: window columns =================
+        const bool live = t < NR;
+        int jj = t;                      // window-relative column index
+        int J = s + t / 6;               // block column
+        const int c = t % 6;
+        double a[NR];
+#pragma unroll
+        for (int ii = 0; ii < NR; ++ii) a[ii] = (live && ii >= jj) ? band_val(s + ii / 6, J, ii % 6, c) : 0.0;
+        if (ie > s) {
+            if (live && jj < 6) {
+#pragma unroll
+                for (int ii = 0; ii < NR; ++ii) Pcol[ii * 6 + jj] = a[ii];
+            }
+            nbar_arrive(B1A, N1A);
+            nbar_arrive(B1B, N1B);
+        }
+        for (int k = s; k < ie; ++k) {
+            // the row block entering the window: A[k+W+1][J] (issued before the wait)
+            const int In = k + W1;
+            const bool retiring = jj < 6;
+            const int Jn = retiring ? In : J;  // a retiring thread takes over the first column block of the new rows
+            double nw[6];
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) nw[rr] = 0.0;
+            if (live && In < e && In - Jn <= B.w) {
+                const int ent = B.band_idx[(long long)Jn * (B.w + 1) + (In - Jn)];
+                if (ent >= 0) {
+                    const double2* src = reinterpret_cast<const double2*>(B.S + 36ll * ent + 6 * c);
+                    const double2 v0 = src[0], v1 = src[1], v2 = src[2];
+                    nw[0] = v0.x, nw[1] = v0.y, nw[2] = v1.x, nw[3] = v1.y, nw[4] = v2.x, nw[5] = v2.y;
+                }
+            }
+            nbar_sync(B3, N3);  // L_col of step k
+            double myL[6];
+            {
+                const int rj = (live && !retiring) ? jj - 6 : 0;
+                const double2* lp = reinterpret_cast<const double2*>(Lcol + rj * 6);
+                const double2 l0 = lp[0], l1 = lp[1], l2 = lp[2];
+                const double m = (live && !retiring) ? 1.0 : 0.0;
+                myL[0] = m * l0.x, myL[1] = m * l0.y, myL[2] = m * l1.x, myL[3] = m * l1.y, myL[4] = m * l2.x, myL[5] = m * l2.y;
+            }
+            const bool next_pivot = live && jj >= 6 && jj < 12 && k + 1 < ie;
+            // part 1: the rows of the next pivot block
+#pragma unroll
+            for (int ii = 6; ii < 12; ++ii) {
+                const double2* lp = reinterpret_cast<const double2*>(Lcol + (ii - 6) * 6);
+                const double2 l0 = lp[0], l1 = lp[1], l2 = lp[2];
+                a[ii - 6] = a[ii] - (l0.x * myL[0] + l0.y * myL[1] + l1.x * myL[2] + l1.y * myL[3] + l2.x * myL[4] + l2.y * myL[5]);
+            }
+            if (next_pivot) {
+#pragma unroll
+                for (int ii = 0; ii < 6; ++ii) Pcol[ii * 6 + (jj - 6)] = a[ii];
+            }
+            if (k + 1 < ie) nbar_arrive(B1A, N1A);
+            // part 2: the rest
+#pragma unroll
+            for (int ii = 12; ii < NR; ++ii) {
+                const double2* lp = reinterpret_cast<const double2*>(Lcol + (ii - 6) * 6);
+                const double2 l0 = lp[0], l1 = lp[1], l2 = lp[2];
+                a[ii - 6] = a[ii] - (l0.x * myL[0] + l0.y * myL[1] + l1.x * myL[2] + l1.y * myL[3] + l2.x * myL[4] + l2.y * myL[5]);
+            }
+            if (retiring) {
+#pragma unroll
+                for (int ii = 0; ii < NR - 6; ++ii) a[ii] = 0.0;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) a[NR - 6 + rr] = nw[rr];
+            if (next_pivot) {
+#pragma unroll
+                for (int ii = 6; ii < NR; ++ii) Pcol[ii * 6 + (jj - 6)] = a[ii];
+            }
+            if (k + 1 < ie) nbar_arrive(B1B, N1B);
+            jj -= 6;
+            if (jj < 0) {
+                jj += NR;
+                J += W1;
+            }
+        }
+        // the window now starts at block row ie: separator block (lower triangle, mirrored)
+        if (has_right && live && jj < NB) {
+#pragma unroll
+            for (int ii = 0; ii < NB; ++ii)
+                if (ii >= jj) {
+                    B.Ta[(long long)p * b * b + ii * b + jj] = a[ii];
+                    B.Ta[(long long)p * b * b + jj * b + ii] = a[ii];
+                }
+        }
+    } else if (role == 1) {
+        // ================= G: border columns [rhs | left spike] =================
+        const bool live = t < GC;
+        const int xc = t == 0 ? 0 : 1 + t;  // position in an X_k row of shared memory
+        const int cb = s - W + (t - 1) / 6, cq = (t - 1) % 6;  // spike column: block / component of the separator before
+        double g[NR];
+#pragma unroll
+        for (int ii = 0; ii < NR; ++ii) {
+            const int I = s + ii / 6, rr = ii % 6;
+            double v = 0.0;
+            if (live && I < e) {
+                if (t == 0)
+                    v = B.rhs[6ll * I + rr];
+                else if (has_left)
+                    v = band_val(I, cb, rr, cq);
+            }
+            g[ii] = v;
+        }
+        if (ie > s) nbar_arrive(B1B, N1B);
+        for (int k = s; k < ie; ++k) {
+            const int In = k + W1;
+            double nw[6];
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) nw[rr] = (live && t == 0 && In < e) ? B.rhs[6ll * In + rr] : 0.0;
+            nbar_sync(B2, N2);  // Lkk^-1
+            double x[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q <= r; ++q) v += Linv[6 * r + q] * g[q];
+                x[r] = v;
+            }
+            if (k > s) nbar_sync(B5, N5);  // the T warps have read the previous X_k
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    Xk[q * XLD + xc] = x[q];
+                    B.Xbuf[(long long)k * 6 * GC + q * GC + t] = x[q];
+                }
+            }
+            nbar_arrive(B4, N4);
+            nbar_sync(B3, N3);  // L_col of step k
+#pragma unroll
+            for (int ii = 6; ii < NR; ++ii) {
+                const double2* lp = reinterpret_cast<const double2*>(Lcol + (ii - 6) * 6);
+                const double2 l0 = lp[0], l1 = lp[1], l2 = lp[2];
+                g[ii - 6] = g[ii] - (l0.x * x[0] + l0.y * x[1] + l1.x * x[2] + l1.y * x[3] + l2.x * x[4] + l2.y * x[5]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) g[NR - 6 + rr] = nw[rr];
+            if (k + 1 < ie) nbar_arrive(B1B, N1B);
+        }
+        if (has_right && live) {
+            if (t == 0) {
+#pragma unroll
+                for (int ii = 0; ii < NB; ++ii) B.fa[(long long)p * b + ii] = g[ii];
+            } else {
+                // cyclic reduction (second generation) reads the coupling of an even separator transposed
+                const bool tr = B.sep_solver == 2 && !(p & 1);
+#pragma unroll
+                for (int ii = 0; ii < NB; ++ii)
+                    B.Ca[(long long)p * b * b + (tr ? (t - 1) * b + ii : ii * b + (t - 1))] = has_left ? g[ii] : 0.0;
+            }
+        }
+    } else if (role == 2) {
+        // ================= T: X_left^T [x_r | X_left] =================
+        const bool live = t < GC;
+        const int xc = t == 0 ? 0 : 1 + t;
+        double acc[NB];
+#pragma unroll
+        for (int c1 = 0; c1 < NB; ++c1) acc[c1] = 0.0;
+        for (int k = s; k < ie; ++k) {
+            nbar_sync(B4, N4);
+            if (has_left && live) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const double xq = Xk[q * XLD + xc];
+                    const double2* xr = reinterpret_cast<const double2*>(Xk + q * XLD + 2);
+#pragma unroll
+                    for (int c1 = 0; c1 < NB; c1 += 2) {
+                        const double2 xv = xr[c1 >> 1];
+                        acc[c1] += xv.x * xq;
+                        acc[c1 + 1] += xv.y * xq;
+                    }
+                }
+            }
+            nbar_arrive(B5, N5);
+        }
+        if (has_left && live) {
+            if (t == 0) {
+#pragma unroll
+                for (int c1 = 0; c1 < NB; ++c1) B.fb[(long long)(p - 1) * b + c1] = acc[c1];
+            } else {
+#pragma unroll
+                for (int c1 = 0; c1 < NB; ++c1) B.Tb[(long long)(p - 1) * b * b + c1 * b + (t - 1)] = acc[c1];
+            }
+        }
+    } else if (t < 32) {
+        // ================= panel warp =================
+        for (int k = s; k < ie; ++k) {
+            nbar_sync(B1B, N1B);  // the pivot block's columns are complete
+            nbar_sync(B2, N2);    // Lkk^-1
+            const int nb = min(k + W, e - 1) - k;
+#pragma unroll
+            for (int u = 0; u < (NB + 31) / 32; ++u) {
+                const int r = t + 32 * u;
+                if (r < NB) {
+                    const double2* pp = reinterpret_cast<const double2*>(Pcol + (6 + r) * 6);
+                    const double2 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+                    const double pr[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};
+                    double l[6];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int q = 0; q <= c; ++q) v += pr[q] * Linv[6 * c + q];
+                        l[c] = v;
+                    }
+                    double2* lo = reinterpret_cast<double2*>(Lcol + r * 6);
+                    lo[0] = make_double2(l[0], l[1]);
+                    lo[1] = make_double2(l[2], l[3]);
+                    lo[2] = make_double2(l[4], l[5]);
+                    if (r / 6 < nb) {
+                        double2* go = reinterpret_cast<double2*>(B.Lbuf + ((long long)k * W1 + 1 + r / 6) * 36 + 6 * (r % 6));
+                        go[0] = make_double2(l[0], l[1]);
+                        go[1] = make_double2(l[2], l[3]);
+                        go[2] = make_double2(l[4], l[5]);
+                    }
+                }
+            }
+            nbar_arrive(B3, N3);
+        }
+    } else {
+        // ================= pivot warp =================
+        const int lane = t - 32;
+        for (int k = s; k < ie; ++k) {
+            nbar_sync(B1A, N1A);  // rows 0..5 of the pivot block's columns
+            if (lane == 0) {
+                double Lkk[36], Li[36];
+                if (!potrf6_inv_reg(Pcol, Lkk, Li)) s_bad = 1;
+#pragma unroll
+                for (int q = 0; q < 36; ++q) Linv[q] = Li[q];
+            }
+            __syncwarp();
+            for (int idx = lane; idx < 36; idx += 32) B.Lbuf[((long long)k * W1) * 36 + idx] = Linv[idx];  // inverse of the pivot block first
+            nbar_sync(B1B, N1B);  // everyone is done with step k-1 (keeps the arrivals below one phase apart)
+            nbar_arrive(B2, N2);
+        }
+        if (lane == 0 && s_bad) *B.fail = 1;
+    }
+}
+
 // Separator system in dense band storage: n2 = (P-1) W block rows, half-bandwidth W2 = 2W-1.
 //   block (a, a+d), a = q W + i:  inside separator q (i + d < W): (Ta - Tb)[q] tile (i, i+d);
 //   into separator q+1 (j = i + d - W < W): T[sep q row i, sep q+1 row j] = Ca[q+1] tile (j, i)^T.
@@ -476,6 +775,12 @@ template <int W, bool kSpike>
 size_t leaf_smem() {
     constexpr int W1 = W + 1, GC = kSpike ? 1 + 6 * W : 1;
     return sizeof(double) * (size_t(W1) * W1 * 36 + size_t(W1) * 6 * GC + 6 * GC + size_t(W1) * 36 + 144);
+}
+
+template <int W>
+void run_leaf2(cudaStream_t s, const BandView& V) {
+    band_leaf2_kernel<W><<<V.P, 256, 0, s>>>(V);
+    CSLAM_CUDA(cudaGetLastError());
 }
 
 template <int W, bool kSpike>
@@ -1207,7 +1512,19 @@ int band_solve_w(cudaStream_t s, const BandView& V, const BandScratch& K) {
         run_backsub<W, false>(s, V, nullptr);
         return 2;
     }
-    run_leaf<W, true>(s, V);
+    // second-generation leaf kernel (register-resident window columns); CSLAM_BAND_LEAF1=1 keeps the first one (A/B runs)
+    static const bool leaf1 = [] {
+        const char* e = std::getenv("CSLAM_BAND_LEAF1");
+        return e && std::atoi(e) != 0;
+    }();
+    if constexpr (W <= 9) {
+        if (leaf1 || V.band_idx == nullptr)
+            run_leaf<W, true>(s, V);
+        else
+            run_leaf2<W>(s, V);
+    } else {
+        run_leaf<W, true>(s, V);
+    }
     if (V.sep_solver == 2 || V.sep_solver == 3) {
         // W = 12 (B = 72) keeps the first-generation kernels: its unrolled columns do not fit the register file
         int launched;

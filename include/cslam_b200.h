@@ -213,7 +213,7 @@ cslam_status cslam_time_phong(cslam_problem* p, int reps, double* ms_per_launch)
  * all of those arrays are updated in place.  The lighting blocks must pair one-to-one with the stereo
  * blocks (the driver adds both while walking the same observations, :55-69 / :100-190), textures
  * must be shared blocks (cslam_set_textures), tracks hold at most 32 observations per vertex and
- * there are at most 96 shared columns (3 per material + 1 per texture + 3); anything else returns
+ * there are at most 160 shared columns (3 per material + 1 per texture + 3); anything else returns
  * CSLAM_ERR_NOT_IMPL.  Single GPU. */
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary);
 

@@ -549,6 +549,19 @@ def test_lm_phong_bounds_active(product):
         assert rel_err(stg[k], sto[k]) < LM_TOL, k
 
 
+def test_lm_phong_many_materials(product):
+    """36 materials and textures: 3 * 36 + 36 + 3 = 147 shared columns (the border system is factored in one
+    CTA's shared memory, up to 160 columns)."""
+    tr = syn.add_phong(syn.make_track(40, 30, 6, seed=12), n_materials=36, shared_textures=True)
+    (pg, sg, stg), (po, so, sto) = _phong_pair(tr, 5, True)
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory"
+    assert np.array_equal(lg[:, 9], lo[:, 9])
+    for k in ("poses", "points", "normals", "phong", "textures", "light"):
+        assert rel_err(stg[k], sto[k]) < LM_TOL, k
+
+
 def test_phong_solve_refusals(product):
     """What the joint solve does not take is refused loudly, not solved differently."""
     from ceres_slam_b200.problem import CslamError
