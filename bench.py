@@ -337,6 +337,37 @@ def bench_loop_closure(iters=6, n_poses=500):
     return out
 
 
+def bench_ragged(iters=5, n_poses=5000, mean=8.0, lmax=30, drop=0.1):
+    """Tracks as a stereo front end produces them — lengths 2 + Geometric clipped to `lmax`, 10 % drop-outs — next
+    to the regular track (every landmark seen by exactly 10 consecutive frames) with the same number of poses and
+    landmarks per frame: how many landmarks reach the grouped DMMA Schur kernel (landmarks that share their
+    camera list exactly, or whose cameras fit a common window of at most 10), and what an LM iteration costs."""
+    fixed = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    out = {"poses": n_poses, "landmarks_per_frame": 100,
+           "ragged": {"mean_length": mean, "max_length": lmax, "dropout": drop}}
+    for name, rg in (("regular", None), ("ragged", dict(mean=mean, max=lmax, drop=drop))):
+        tr = syn.make_track(n_poses, 100, 10, seed=42, ragged=rg)
+        p, _, _ = syn.build_problem(tr, max_num_iterations=10 ** 6, profile_kernels=1, **dict(LM_EXACT, **fixed))
+        info = p.analyze()
+        p.upload()
+        p.lm_begin()
+        p.lm_iterate(2, ignore_convergence=True)
+        p.reset_profile()
+        s0 = p.lm_iterate(0, ignore_convergence=True).device_ms
+        s = p.lm_iterate(iters, ignore_convergence=True)
+        prof = {k: v[0] / max(1, v[1]) for k, v in p.profile().items() if v[1]}
+        log = p.iteration_log()
+        n_obs = int(tr["obs_cam"].size)
+        out[name] = {"observations": n_obs, "landmarks": int(info["n_landmarks"]),
+                     "grouped_fraction": info["n_grouped_landmarks"] / max(1, info["n_landmarks"]),
+                     "groups": int(info["n_groups"]), "ms_per_lm_iteration": (s.device_ms - s0) / iters,
+                     "step_profile_ms": prof, "ns_per_observation": (s.device_ms - s0) / iters * 1e6 / n_obs,
+                     "cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1])}
+        p.close()
+    out["ragged_over_regular_per_observation"] = out["ragged"]["ns_per_observation"] / out["regular"]["ns_per_observation"]
+    return out
+
+
 def bench_ransac_front_end(n_poses=1000):
     """the RANSAC front end (compute_initial_guess's 400-hypothesis point-cloud
     alignment per consecutive pose pair) for a 1 k-pose track with ~900 matches per pair, all pairs
@@ -656,6 +687,7 @@ def main():
     c3 = bench_c3_phong_solve(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_phong) else None
     ransac = bench_ransac_front_end() if (rank == 0 and world == 1 and not args.no_c4) else None
     loop = bench_loop_closure() if (rank == 0 and world == 1 and not args.no_c4) else None
+    ragged = bench_ragged() if (rank == 0 and world == 1 and not args.no_c4) else None
     drivers = bench_c1_c2_drivers(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_c4) else None
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
@@ -714,7 +746,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "resjac": resjac, "step_profile_ms": step_profile, "allreduce": allreduce, "c4_windows": c4, "phong_blocks": phong,
-            "c3_phong_solve": c3, "ransac_front_end": ransac, "loop_closure_dense_solve": loop,
+            "c3_phong_solve": c3, "ransac_front_end": ransac, "loop_closure_dense_solve": loop, "c5_ragged": ragged,
             "c1_dataset_vo": (drivers or {}).get("c1_dataset_vo"), "c2_dataset_vo_sun": (drivers or {}).get("c2_dataset_vo_sun"),
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),
                    "linear_iterations_timed": int(log[-K:, 7].sum()), "accepted_timed": int(log[-K:, 9].sum())},

@@ -55,6 +55,7 @@ class Options(C.Structure):
         ("dogleg_type", C.c_int),
         ("line_search_sufficient_function_decrease", C.c_double),
         ("dense_solver", C.c_int),
+        ("bandpc_solver", C.c_int),
     ]
 
 

@@ -73,6 +73,7 @@ void cslam_options_init(cslam_options* o) {
     o->dogleg_type = 1;
     o->line_search_sufficient_function_decrease = 1e-4;
     o->dense_solver = 0;
+    o->bandpc_solver = 0;
 }
 
 cslam_status cslam_problem_create(cslam_problem** out, const cslam_options* opt) {

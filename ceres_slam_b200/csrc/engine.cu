@@ -447,10 +447,65 @@ void Engine::build_structure() {
         }
         x = y;
     }
-    const size_t n_groups = g_L_h.size();
+    const size_t n_exact = g_L_h.size();
+    // ---- second pass: "ragged" groups.  A landmark needs no identical twin: the still ungrouped landmarks
+    // of a first-camera bucket whose cameras all lie within a window of 10 (the DMMA kernel's tile) form one
+    // group whose camera list is the union of theirs; each landmark sees a subset (per-landmark slot maps).
+    // Real stereo tracks (variable length, drop-outs) almost never share an exact list.
+    struct RagGroup {
+        std::vector<uint32_t> lms;
+        std::vector<int> cams;
+        int K = 0;
+    };
+    std::vector<RagGroup> rag;
+    g_map_off_h.assign(n_exact, -1);
+    std::vector<std::pair<int, int>> items_rag;
+    long long map_cursor = 0;
+    if (want_ragged && opt.schur_path != 1 && !lighting_in_solve()) {
+        std::vector<uint8_t> primary(nl, 0);
+        for (size_t g = 0; g < n_exact; ++g)
+            for (int jl = 0; jl < g_G_h[g]; ++jl) primary[sorted_a[g_first[g] + jl] - lo] = 1;
+        constexpr int kRagWindow = 10;
+        for (uint32_t c = 0; c < n_poses; ++c) {
+            const uint32_t b0 = std::max(bstart[c], lo), b1 = std::min(bstart[c + 1], hi);
+            RagGroup rg;
+            for (uint32_t a = b0; a < b1; ++a) {
+                if (!kok[a - lo] || primary[a - lo]) continue;
+                const uint32_t* ob = lm_obs(a);
+                const uint32_t len = lm_len(a);
+                if (st_cam[ob[len - 1]] - c >= uint32_t(kRagWindow)) continue;   // (camera lists are ascending)
+                rg.lms.push_back(a);
+                rg.K = std::max(rg.K, int(len));
+                for (uint32_t k = 0; k < len; ++k) rg.cams.push_back(int(st_cam[ob[k]]));
+            }
+            if (rg.lms.size() < min_group) continue;
+            std::sort(rg.cams.begin(), rg.cams.end());
+            rg.cams.erase(std::unique(rg.cams.begin(), rg.cams.end()), rg.cams.end());
+            const int L = int(rg.cams.size()), G = int(rg.lms.size());
+            const int gid = int(g_L_h.size());
+            g_L_h.push_back(L);
+            g_G_h.push_back(G);
+            g_lm0_h.push_back(int(lm_cursor));
+            g_obs0_h.push_back(obs_cursor);
+            g_off_h.push_back(cams_cursor);
+            g_blk_off_h.push_back(blk_cursor);
+            g_map_off_h.push_back(int(map_cursor));
+            cams_cursor += L;
+            blk_cursor += L * (L + 1) / 2;
+            lm_cursor += uint32_t(G);
+            obs_cursor += uint32_t(G) * uint32_t(rg.K);
+            map_cursor += (long long)(L + rg.K) * G;
+            for (int j0 = 0; j0 < G; j0 += kItemMax) items_rag.push_back({gid, j0});
+            max_group_L = std::max(max_group_L, L);
+            rag.push_back(std::move(rg));
+        }
+    }
+    n_items_rag = int(items_rag.size());
+    g_map_h.assign(size_t(std::max<long long>(map_cursor, 1)), 0xff);
+    const size_t n_groups = n_exact;
     n_lm_grouped = int(lm_cursor);
     n_items_small = int(items_small.size());
-    for (auto* lst : {&items_small, &items_large})
+    for (auto* lst : {&items_small, &items_large, &items_rag})
         for (auto& it : *lst) {
             item_group_h.push_back(it.first);
             item_j0_h.push_back(it.second);
@@ -462,8 +517,67 @@ void Engine::build_structure() {
     lm_base_h.assign(nl, 0);
     lm_stride_h.assign(nl, 0);
     lm_cnt_h.assign(nl, 0);
+    // ragged groups store K rows per landmark column (K = the longest member): their padding counts as storage
+    n_obs_true = n_obs;
+    {
+        long long rest_obs = 0;
+        std::vector<uint8_t> in_group(nl, 0);
+        for (size_t g = 0; g < n_exact; ++g)
+            for (int jl = 0; jl < g_G_h[g]; ++jl) in_group[sorted_a[g_first[g] + jl] - lo] = 1;
+        for (auto& rg : rag)
+            for (uint32_t a : rg.lms) in_group[a - lo] = 1;
+        for (uint32_t x = 0; x < nl; ++x)
+            if (!in_group[x]) rest_obs += lm_len(lo + x);
+        n_obs = (long long)obs_cursor + rest_obs;
+    }
     obs_user_n = size_t(n_obs);
     obs_user_h.reset(new uint32_t[std::max<size_t>(obs_user_n, 1)]);
+    // pair -> block table of a camera list (-1: a constant camera, or a pair no landmark co-observes)
+    auto fill_blocks = [&](int t, const int* fr, int L) {
+        for (int i = 0; i < L; ++i)
+            for (int k = i; k < L; ++k) {
+                int e = -1;
+                if (fr[i] >= 0 && fr[k] >= 0) {
+                    auto b0 = s_col_h.begin() + s_rowptr_h[fr[i]], b1 = s_col_h.begin() + s_rowptr_h[fr[i] + 1];
+                    auto it = std::lower_bound(b0, b1, fr[k]);
+                    if (it != b1 && *it == fr[k]) e = int(it - s_col_h.begin());
+                }
+                g_blk_h[size_t(t++)] = e;
+            }
+    };
+    parallel_chunks(rag.size(), 8, [&](int, size_t r0, size_t r1) {
+        for (size_t r = r0; r < r1; ++r) {
+            const size_t g = n_exact + r;
+            const RagGroup& rg = rag[r];
+            const int L = g_L_h[g], G = g_G_h[g], K = rg.K;
+            int fr[kGroupLmax];
+            for (int i = 0; i < L; ++i) {
+                g_cams_h[size_t(g_off_h[g]) + i] = rg.cams[i];
+                fr[i] = cam_free_h[rg.cams[i]];
+            }
+            fill_blocks(g_blk_off_h[g], fr, L);
+            const uint32_t base = g_obs0_h[g];
+            unsigned char* inv = g_map_h.data() + g_map_off_h[g];
+            unsigned char* fwd = inv + size_t(L) * G;
+            for (int jl = 0; jl < G; ++jl) {
+                const uint32_t a = rg.lms[jl];
+                const size_t li = size_t(g_lm0_h[g]) + jl;
+                grouped[a - lo] = 1;
+                const uint32_t* ob = lm_obs(a);
+                const int len = int(lm_len(a));
+                lm_user_h[li] = all_lm[a];
+                lm_base_h[li] = base + jl;
+                lm_stride_h[li] = uint32_t(G);
+                lm_cnt_h[li] = uint32_t(len);
+                for (int k = 0; k < K; ++k) obs_user_h[size_t(base) + size_t(k) * G + jl] = ob[k < len ? k : 0];
+                for (int k = 0; k < len; ++k) {
+                    const int slot = int(std::lower_bound(rg.cams.begin(), rg.cams.end(), int(st_cam[ob[k]])) - rg.cams.begin());
+                    fwd[size_t(k) * G + jl] = (unsigned char)slot;
+                    inv[size_t(slot) * G + jl] = (unsigned char)k;
+                }
+            }
+        }
+    });
     parallel_chunks(n_groups, 8, [&](int, size_t g0, size_t g1) {
         for (size_t g = g0; g < g1; ++g) {
             const uint32_t x = g_first[g], G = uint32_t(g_G_h[g]);
@@ -872,6 +986,10 @@ bool Engine::build_structure_gpu(cudaEvent_t) {
             item_n_h.push_back(std::min(kItemMax, g_G_h[it.first] - it.second));
         }
     bt.lap("    runs -> groups (host)");
+    g_map_off_h.assign(g_L_h.size(), -1);   // the device analysis forms exact groups only
+    g_map_h.assign(1, 0xff);
+    n_items_rag = 0;
+    n_obs_true = n_obs;
     // layout rows of every landmark and the groups' camera lists, on the device
     g_cams_h.assign(size_t(cams_cursor), 0);
     d_lm_user.alloc(std::max<size_t>(nl, 1), stream);
@@ -956,14 +1074,21 @@ GroupView Engine::group_view() const {
     g.g_cams = d_g_cams.p;
     g.g_blk_off = d_g_blk_off.p;
     g.g_blk = d_g_blk.p;
+    g.g_map_off = d_g_map_off.p;
+    g.g_map = d_g_map.p;
+    g.g_long = bandpc_active ? d_g_long.p : nullptr;
+    g.S_long = bandpc_active ? d_S2.p : nullptr;
+    g.Bdiag_long = bandpc_active ? d_Bdiag2.p : nullptr;
     return g;
 }
 
 void Engine::launch_schur(const DevView& v, const LmDiag& dg) {
     if (!item_group_h.empty())
-        launch_schur_grouped(stream, v, group_view(), n_items_small, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+        launch_schur_grouped(stream, v, group_view(), n_items_small, n_items_rag, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+    // (the landmarks no group takes are mostly the long tracks: beyond the banded preconditioner's window)
     if (n_lm > n_lm_grouped)
-        launch_schur_generic(stream, v, n_lm_grouped, n_lm, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
+        launch_schur_generic(stream, v, n_lm_grouped, n_lm, dg, bandpc_active ? d_S2.p : d_S, bandpc_active ? d_Bdiag2.p : d_Bdiag,
+                             d_bp, d_gp, d_gl.p, d_scal);
 }
 
 void Engine::upload() {
@@ -1009,6 +1134,12 @@ void Engine::upload() {
         bool ok = false;
         try {
             ok = build_structure_gpu(nullptr);
+            // the device analysis only forms groups of identical camera lists; when more than 5 % of the landmarks
+            // stay outside them (ragged tracks), the host analysis — which also forms ragged groups — takes over
+            if (ok && !std::getenv("CSLAM_VERIFY_STRUCTURE") && (n_lm - n_lm_grouped) > n_lm / 20) {
+                structure_on_device = false;
+                ok = false;
+            }
             if (!ok) build_structure();
         } catch (...) {
             rest.join();
@@ -1025,7 +1156,9 @@ void Engine::upload() {
             CSLAM_CUDA(cudaStreamSynchronize(stream));
             const unsigned long long h_dev = layout_hash();
             const std::vector<int> rp(s_rowptr_h), cl(s_col_h);
+            want_ragged = false;   // (the device analysis forms no ragged groups)
             build_structure();
+            want_ragged = true;
             if (layout_hash() != h_dev || rp != s_rowptr_h || cl != s_col_h)
                 throw std::runtime_error("device and host structure analyses disagree");
         }
@@ -1093,6 +1226,8 @@ void Engine::upload() {
     up_i(d_g_cams, g_cams_h);
     up_i(d_g_blk_off, g_blk_off_h);
     up_i(d_g_blk, g_blk_h);
+    up_i(d_g_map_off, g_map_off_h);
+    d_g_map.upload(g_map_h.empty() ? std::vector<unsigned char>(1, 0xff) : g_map_h, stream);
     // internal order <- caller's order, on the device
     const size_t no = size_t(std::max<long long>(n_obs, 1));
     if (!structure_on_device) {
@@ -1223,7 +1358,15 @@ void Engine::plan_band_solver() {
     int w = 0;
     for (int a = 0; a < n_free; ++a)
         if (s_rowptr_h[a + 1] > s_rowptr_h[a]) w = std::max(w, s_col_h[s_rowptr_h[a + 1] - 1] - a);
-    if (w > kBandWmax) return;
+    bandpc_active = false;
+    if (w > kBandWmax) {
+        // Not a narrow band.  Too large for the dense factorisation as well: conjugate gradients preconditioned
+        // with the banded solve of the short-track landmarks' part of the system (kernels_bandpcg.cu).
+        if (6ll * n_free <= kDenseMaxN || opt.dense_solver > 0 || opt.bandpc_solver < 0 || n_free < 64 * kBandPcW || ph.active)
+            return;
+        bandpc_active = true;
+        w = kBandPcW;
+    }
     if (w == 0) w = 1;  // a single camera: treat as bandwidth 1 (absent blocks read as zero)
     const int n = n_free;
     const int W = band_storage_width(w);  // separators and the shared-memory window use this width
@@ -1240,13 +1383,42 @@ void Engine::plan_band_solver() {
     P = std::max(P, 1);
     int m = (n + P - 1) / P;
     P = (n + m - 1) / m;
-    if (P > 1 && (m < 2 * W || n - (P - 1) * m < 1)) return;
+    if (P > 1 && (m < 2 * W || n - (P - 1) * m < 1)) {
+        bandpc_active = false;
+        return;
+    }
     band_w = w;
     band_P = P;
     band_m = m;
     std::vector<int> idx(size_t(n) * (w + 1), -1);
-    for (int a = 0; a < n; ++a)
-        for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) idx[size_t(a) * (w + 1) + (s_col_h[e] - a)] = e;
+    if (bandpc_active) {
+        // the preconditioner's matrix lives in dense band storage [n][w + 1][36] (rebuilt from S before every solve)
+        for (int a = 0; a < n; ++a)
+            for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) {
+                const int d = s_col_h[e] - a;
+                if (d <= w) idx[size_t(a) * (w + 1) + d] = a * (w + 1) + d;
+            }
+        d_bpc_S.alloc(size_t(n) * (w + 1) * 36, stream);
+        d_bpc_scal.alloc(4, stream);
+        // which groups reach beyond the window (distance between their first and last FREE camera)
+        std::vector<int> glong(std::max<size_t>(g_L_h.size(), 1), 0);
+        for (size_t g = 0; g < g_L_h.size(); ++g) {
+            int f0 = -1, f1 = -1;
+            for (int i = 0; i < g_L_h[g]; ++i) {
+                const int f = cam_free_h[g_cams_h[size_t(g_off_h[g]) + i]];
+                if (f < 0) continue;
+                if (f0 < 0) f0 = f;
+                f1 = f;
+            }
+            glong[g] = (f0 >= 0 && f1 - f0 > w) ? 1 : 0;
+        }
+        d_g_long.upload(glong, stream);
+        d_S2.alloc(36 * size_t(std::max(nnzU, 1)), stream);
+        d_Bdiag2.alloc(36 * size_t(n), stream);
+    } else {
+        for (int a = 0; a < n; ++a)
+            for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) idx[size_t(a) * (w + 1) + (s_col_h[e] - a)] = e;
+    }
     d_band_idx.upload(idx, stream);
     d_band_fail.alloc(1, stream);
     const size_t b = 6 * size_t(W), GC = P > 1 ? 1 + b : 1;
@@ -1263,7 +1435,79 @@ void Engine::plan_band_solver() {
     d_rhs2.alloc(6 * n2, stream);
     d_X2.alloc(6 * n2, stream);
     d_y2.alloc(6 * n2, stream);
-    band_active = true;
+    band_active = !bandpc_active;
+}
+
+// Conjugate gradients on S y = rhs preconditioned with the banded direct solve (kernels_bandpcg.cu).  Host-driven:
+// three scalar read-backs per iteration, ~10 iterations.  Status in d_pscal like the other solvers.
+void Engine::bandpc_solve(const double* rhs, double* y) {
+    const int n = n_free;
+    const long long n6 = 6ll * n;
+    BandView V;   // (the preconditioner's matrix d_bpc_S was formed in schur_pass)
+    V.n = n;
+    V.w = band_w;
+    V.P = band_P;
+    V.m = band_m;
+    V.sep_solver = band_sep;
+    V.band_idx = d_band_idx.p;
+    V.S = d_bpc_S.p;
+    V.Lbuf = d_Lbuf.p;
+    V.Xbuf = d_Xbuf.p;
+    V.Ta = d_Ta.p;
+    V.Ca = d_Ca.p;
+    V.fa = d_fa.p;
+    V.Tb = d_Tb.p;
+    V.fb = d_fb.p;
+    V.fail = d_band_fail.p;
+    const BandScratch K{d_T2.p, d_rhs2.p, d_L2.p, d_X2.p, d_y2.p};
+    double *r = d_pr.p, *z = d_pz.p, *pv = d_pp.p, *q = d_pq.p;
+    CSLAM_CUDA(cudaMemsetAsync(y, 0, n6 * sizeof(double), stream));
+    CSLAM_CUDA(cudaMemcpyAsync(r, rhs, n6 * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    auto dot = [&](const double* a, const double* b) {
+        CSLAM_CUDA(cudaMemsetAsync(d_bpc_scal.p, 0, sizeof(double), stream));
+        launch_dot(stream, a, b, n6, d_bpc_scal.p);
+        double v;
+        read_scalars(d_bpc_scal.p, &v, 1);
+        return v;
+    };
+    const double normb2 = dot(rhs, rhs);
+    const double tol2 = 1e-15 * 1e-15 * normb2;
+    double rho_old = 0.0;
+    int it = 0;
+    bool fail = false;
+    const int max_it = 2000;
+    if (normb2 > 0.0)
+        for (; it < max_it;) {
+            V.rhs = r;
+            V.y = z;
+            launch_band_solve(stream, V, K, d_pscal.p);
+            const double rho = dot(r, z);
+            double ps[PS_COUNT];
+            read_scalars(d_pscal.p, ps, PS_COUNT);
+            if (ps[PS_FAIL] == 2.0 || !std::isfinite(rho) || !(rho > 0.0)) {
+                fail = !(rho == 0.0);
+                break;
+            }
+            launch_bpc_xpby(stream, n6, z, it == 0 ? 0.0 : rho / rho_old, pv);
+            launch_bpc_spmv(stream, n, d_s_rowptr.p, d_s_col.p, d_lt_rowptr.p, d_lt_col.p, d_S, pv, q);
+            const double pq = dot(pv, q);
+            if (!std::isfinite(pq) || !(pq > 0.0)) {
+                fail = true;
+                break;
+            }
+            launch_bpc_update(stream, n6, rho / pq, pv, q, y, r);
+            rho_old = rho;
+            ++it;
+            const double nr2 = dot(r, r);
+            static const bool dbg = std::getenv("CSLAM_BPC_DEBUG") != nullptr;
+            if (dbg) std::fprintf(stderr, "[bandpc] it %d  |r|/|b| %.3e  rho %.3e  pq %.3e\n", it, std::sqrt(nr2 / normb2), rho, pq);
+            if (nr2 <= tol2) break;
+        }
+    double ps[PS_COUNT] = {0};
+    ps[PS_ITERS] = double(std::max(it, 1));
+    ps[PS_FAIL] = fail ? 2.0 : 0.0;
+    CSLAM_CUDA(cudaMemcpyAsync(d_pscal.p, ps, sizeof(ps), cudaMemcpyHostToDevice, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
 }
 
 // The exact solve of a reduced system that is not a narrow band: dense Cholesky when it is small (PCG run
@@ -1672,6 +1916,10 @@ void Engine::schur_pass() {
         }
         launch_phong_build(stream, v, pq, first_rest, n_lm, dg, phong_system(), true, ph.max_track);
     } else {
+        if (bandpc_active) {
+            d_S2.zero(stream);
+            d_Bdiag2.zero(stream);
+        }
         launch_schur(v, dg);
         if (rank == 0)
             launch_camonly_build(stream, v, d_suns.p, int(suns.size()), d_priors.p, int(priors.size()), d_Bdiag, d_bp, d_gp,
@@ -1679,6 +1927,17 @@ void Engine::schur_pass() {
     }
     prof_end(CSLAM_K_SCHUR);
     allreduce_system();
+    if (bandpc_active) {
+        if (n_ranks > 1) {
+            comm_allreduce_sum(nccl_comm, d_S2.p, d_S2.n, stream);
+            comm_allreduce_sum(nccl_comm, d_Bdiag2.p, d_Bdiag2.n, stream);
+        }
+        // preconditioner M = [short-track landmarks' Schur terms] + damping, in dense band storage; then S, Bdiag get
+        // the long tracks' terms
+        launch_bpc_build(stream, n_free, band_w, d_s_rowptr.p, d_s_col.p, d_S, d_Bdiag, d_Bdiag2.p, dg, d_bpc_S.p);
+        launch_bpc_add(stream, 36ll * nnzU, d_S2.p, d_S);
+        launch_bpc_add(stream, 36ll * n_free, d_Bdiag2.p, d_Bdiag);
+    }
     prof_begin(CSLAM_K_FINALIZE);
     launch_finalize(stream, v, dg, opt.preconditioner, d_S, d_Bdiag, d_diag_p.p, d_Minv.p, d_scal);
     if (ph.active)
@@ -1742,7 +2001,9 @@ void Engine::solve_reduced(const double* rhs, double* y) {
         max_it = opt.max_linear_solver_iterations;
         min_it = opt.min_linear_solver_iterations;
     }
-    if (dense_active) {
+    if (bandpc_active) {
+        bandpc_solve(rhs, y);
+    } else if (dense_active) {
         DenseView V;
         V.n = 6 * n_free;
         V.n_pad = dense_npad;
@@ -2669,7 +2930,7 @@ unsigned long long Engine::layout_hash() const {
     for (size_t i = 0; i < obs_user_n; ++i) lh = (lh ^ (unsigned long long)obs_user_h[i]) * 1099511628211ull;
     lh = (lh ^ 0xffull) * 1099511628211ull;
     mix(item_group_h); mix(item_j0_h); mix(item_n_h); mix(g_L_h); mix(g_G_h); mix(g_lm0_h);
-    mix(g_obs0_h); mix(g_off_h); mix(g_cams_h); mix(g_blk_off_h); mix(g_blk_h);
+    mix(g_obs0_h); mix(g_off_h); mix(g_cams_h); mix(g_blk_off_h); mix(g_blk_h); mix(g_map_off_h);
     lh = (lh ^ (unsigned long long)n_lm_grouped) * 1099511628211ull;
     lh = (lh ^ (unsigned long long)n_items_small) * 1099511628211ull;
     lh = (lh ^ (unsigned long long)max_group_L) * 1099511628211ull;
@@ -2692,7 +2953,7 @@ void Engine::analyze(int n_ranks_, int rank_, cslam_structure_info* out) {
     uploaded = begun = false;
     out->n_free_cams = n_free;
     out->n_landmarks = n_lm;
-    out->n_observations = n_obs;
+    out->n_observations = n_obs_true;
     out->nnz_blocks = nnzU;
     unsigned long long h = 1469598103934665603ull;
     for (int v : s_rowptr_h) h = (h ^ (unsigned long long)(unsigned)v) * 1099511628211ull;

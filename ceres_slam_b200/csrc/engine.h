@@ -79,6 +79,10 @@ struct GroupView {
     const int* g_cams;           // camera ids, ascending
     const int* g_blk_off;        // offset of the group's pair table in g_blk
     const int* g_blk;            // S block index for slot pair (a <= b), -1 if a camera is constant
+    const int* g_long;           // per group: 1 = accumulate into S_long / Bdiag_long (nullptr: everything into S / Bdiag)
+    double *S_long, *Bdiag_long;
+    const int* g_map_off;        // ragged groups: offset of [inv: L x G | fwd: K x G] in g_map, -1 for an exact group
+    const unsigned char* g_map;  // inv[i][j]: observation index of landmark j in camera slot i (0xff none); fwd[k][j]: slot of observation k
 };
 
 // Direct solve of a block-banded reduced camera system (kernels_band.cu).
@@ -104,6 +108,7 @@ int band_storage_width(int w);   // 3, 6, 9 or 12: the compiled window widths
 
 // Dense Cholesky of the reduced camera system (kernels_dense.cu): lower triangle, column-major, leading
 // dimension ld, n = 6 x free poses padded to n_pad (a multiple of the panel width); row n_pad = right-hand side.
+constexpr int kBandPcW = 9;           // half-bandwidth kept by the banded preconditioner (the widest the fast leaf / BCR kernels take)
 constexpr int kDenseMaxN = 12288;     // 1.2 GB of FP64
 struct DenseView {
     int n, n_pad, ld;
@@ -292,6 +297,14 @@ class Engine {
     DBuf<double> d_raw_uvd, d_raw_W, d_raw_pts;
     // grouped Schur path
     std::vector<int> item_group_h, item_j0_h, item_n_h, g_L_h, g_G_h, g_lm0_h, g_off_h, g_cams_h, g_blk_off_h, g_blk_h;
+    // ragged groups (landmarks whose cameras fit a common window of <= 10 without sharing the exact list)
+    std::vector<int> g_map_off_h;
+    std::vector<unsigned char> g_map_h;
+    int n_items_rag = 0;
+    bool want_ragged = true;       // false while a host analysis is only rebuilt to verify the device one
+    long long n_obs_true = 0;      // observations without the padding rows of ragged groups
+    DBuf<int> d_g_map_off;
+    DBuf<unsigned char> d_g_map;
     std::vector<uint32_t> g_obs0_h;
     DBuf<int> d_item_group, d_item_j0, d_item_n, d_g_L, d_g_G, d_g_lm0, d_g_off, d_g_cams, d_g_blk_off, d_g_blk;
     DBuf<uint32_t> d_g_obs0;
@@ -316,6 +329,11 @@ class Engine {
     DBuf<int> d_band_idx, d_band_fail;
     DBuf<double> d_Lbuf, d_Xbuf, d_Ta, d_Ca, d_fa, d_Tb, d_fb, d_T2, d_rhs2, d_L2, d_X2, d_y2;
     void plan_band_solver();
+    // CG preconditioned with the banded solver (S neither a narrow band nor small enough for the dense factorisation)
+    bool bandpc_active = false;
+    DBuf<double> d_bpc_S, d_bpc_scal, d_S2, d_Bdiag2;   // S2 / Bdiag2: contributions of the landmarks beyond the window
+    DBuf<int> d_g_long;
+    void bandpc_solve(const double* rhs, double* y);
     // dense direct solver (linear_solver == 0, S not banded, small or dense enough)
     bool dense_active = false;
     int dense_npad = 0, dense_ld = 0;

@@ -29,8 +29,8 @@ void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi
 // K2 (fast path) — landmarks grouped by identical camera list: one CTA per slice of a group,
 // a producer warp forms Z = W chol(V)^-T per observation, consumer warps keep the 6x6 pair
 // blocks of the slice in registers and flush them once (SYRK-shaped, output stationary)
-void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
-                          double* Bdiag, double* bp, double* gp, double* gl, double* scal);
+void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, int n_items_rag, LmDiag dg,
+                          double* S, double* Bdiag, double* bp, double* gp, double* gl, double* scal);
 // sun-sensor and pose-prior blocks (camera-only): adds to Bdiag, bp, gp and the cost
 void launch_camonly_build(cudaStream_t s, const DevView& v, const SunBlockData* suns, int n_sun,
                           const PriorBlockData* priors, int n_prior, double* Bdiag, double* bp, double* gp,
@@ -56,6 +56,14 @@ void launch_pcg_persistent(cudaStream_t s, const PcgBufs& B, double* pbuf2, doub
 // K3b — direct solve of a block-banded reduced system (leaves + separators, kernels_band.cu);
 // writes ps[PS_ITERS] = 1 and ps[PS_FAIL] = 2 when a pivot is not positive
 void launch_band_solve(cudaStream_t s, const BandView& B, const BandScratch& K, double* ps);
+// K3c — CG preconditioned with the banded direct solver (kernels_bandpcg.cu); the loop itself is in engine.cu
+void launch_bpc_build(cudaStream_t s, int n, int W, const int* rowptr, const int* col, const double* S1, const double* U1,
+                      const double* U2, LmDiag dg, double* Sband);
+void launch_bpc_add(cudaStream_t s, long long n, const double* a, double* b);
+void launch_bpc_spmv(cudaStream_t s, int n, const int* rowptr, const int* col, const int* ent_ptr, const int* ent_cb,
+                     const double* S, const double* p, double* q);
+void launch_bpc_xpby(cudaStream_t s, long long n, const double* z, double beta, double* p);
+void launch_bpc_update(cudaStream_t s, long long n, double alpha, const double* p, const double* q, double* x, double* r);
 // K3d — dense Cholesky of a reduced system that is not a narrow band (kernels_dense.cu); xw: [n_pad] work vector
 void launch_dense_solve(cudaStream_t s, const DenseView& V, double* xw, double* ps);
 

@@ -352,7 +352,10 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <bool WPO, int MINB>  // WPO: one 3x3 weight per observation (dataset_vo_sun.cpp:57-59) instead of a shared one
+// RAG: a "ragged" group — its landmarks see SUBSETS of the group's camera list (variable track lengths, drop-outs):
+// observation k of landmark j sits in camera slot fwd[k][j], slot i of landmark j holds observation inv[i][j] (0xff:
+// the landmark is not seen from that camera; its rows of Z are zero).  Everything downstream of Z is unchanged.
+template <bool WPO, int MINB, bool RAG = false>  // WPO: one 3x3 weight per observation (dataset_vo_sun.cpp:57-59) instead of a shared one
 __global__ void __launch_bounds__(G2_NT, MINB)
     schur_grouped2_kernel(DevView v, GroupView gv, int item_lo, int item_hi, LmDiag dg, double* __restrict__ S,
                           double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
@@ -386,6 +389,13 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         const int* __restrict__ cams = gv.g_cams + gv.g_off[g];
         const int* __restrict__ blk = gv.g_blk + gv.g_blk_off[g];
         const int P = L * (L + 1) / 2;
+        // a group whose cameras span more than the banded preconditioner's window accumulates into the second pair
+        // of buffers (engine.cu bandpc_*): S = S_short + S_long, the preconditioner is built from S_short alone
+        const bool to_long = gv.g_long != nullptr && gv.g_long[g] != 0;
+        double* __restrict__ Sg = to_long ? gv.S_long : S;
+        double* __restrict__ Bg = to_long ? gv.Bdiag_long : Bdiag;
+        const unsigned char* __restrict__ inv = RAG ? gv.g_map + gv.g_map_off[g] + j0 : nullptr;   // [i * G + jl]
+        const unsigned char* __restrict__ fwd = RAG ? inv + (long long)L * G : nullptr;            // [k * G + jl]
 
         // ---- stage the slice's cameras: free index, scaling, pair->block table, poses (TMA) ----
         if (tid < L) {
@@ -420,10 +430,12 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         // this thread's observation of the NEXT batch (u, v, d, point, point scaling), loaded one
         // pipeline step ahead so the global-load latency hides behind the MMA stage
         double nx[9];
+        int nx_k = 0;  // RAG: which observation of the landmark this slot holds (0xff: none)
         auto prefetch = [&](int jl) {
             if (producing && jl < nj) {
                 const long long j = lm0 + jl;
-                const long long e = obs0 + (long long)pi * G + jl;
+                if (RAG) nx_k = inv[(long long)pi * G + jl];
+                const long long e = obs0 + (long long)(RAG ? (nx_k == 0xff ? 0 : nx_k) : pi) * G + jl;
                 nx[0] = v.obs_u[e]; nx[1] = v.obs_v[e]; nx[2] = v.obs_d[e];
                 nx[3] = v.points[3 * j]; nx[4] = v.points[3 * j + 1]; nx[5] = v.points[3 * j + 2];
                 nx[6] = v.sc_l[3 * j]; nx[7] = v.sc_l[3 * j + 1]; nx[8] = v.sc_l[3 * j + 2];
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
             double qu[3], qv[3], qd[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const long long e = obs0 + (long long)min(k, L - 1) * G + jl;
+                const long long e = obs0 + (long long)(RAG ? 0 : min(k, L - 1)) * G + jl;  // (RAG: the queue is not used)
                 qu[k] = v.obs_u[e];
                 qv[k] = v.obs_v[e];
                 qd[k] = v.obs_d[e];
@@ -454,6 +466,27 @@ __global__ void __launch_bounds__(G2_NT, MINB)
             if (!WPO) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Wl[k] = s_W[k];
+            }
+            if (RAG) {
+                // the landmark's own observations, each in the camera slot the map names
+                const int cnt = int(v.lm_cnt[j]);
+                for (int k = 0; k < cnt; ++k) {
+                    const long long e = obs0 + (long long)k * G + jl;
+                    const int ci = fwd[(long long)k * G + jl];
+                    if (WPO) {
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) Wl[q] = v.obs_W[9 * e + q];
+                    }
+                    double r[3], Jp[9];
+                    stereo_block_point(v.cam, s_pose + 12 * ci, p, v.obs_u[e], v.obs_v[e], v.obs_d[e], Wl, r, Jp);
+                    cost += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const double a = Jp[3 * q] * sl[0], b = Jp[3 * q + 1] * sl[1], c = Jp[3 * q + 2] * sl[2];
+                        V[0] += a * a; V[1] += a * b; V[2] += a * c; V[3] += b * b; V[4] += b * c; V[5] += c * c;
+                        gq[0] += a * r[q]; gq[1] += b * r[q]; gq[2] += c * r[q];
+                    }
+                }
             }
             auto step = [&](double& su, double& sv, double& sd, int i) {
                 const double ou = su, ov = sv, od = sd;
@@ -482,7 +515,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                     gq[0] += a * r[k]; gq[1] += b * r[k]; gq[2] += c * r[k];
                 }
             };
-            for (int i = 0; i < L; i += 3) {
+            for (int i = 0; i < L && !RAG; i += 3) {
                 step(qu[0], qv[0], qd[0], i);
                 if (i + 1 < L) step(qu[1], qv[1], qd[1], i + 1);
                 if (i + 2 < L) step(qu[2], qv[2], qd[2], i + 2);
@@ -556,12 +589,18 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         for (int bt = 0; bt <= nbatch; ++bt) {
             if (bt < nbatch && producing) {
                 const int jl = bt * TL + pq;
-                if (jl < nj) {
+                if (RAG && jl < nj && nx_k == 0xff) {
+                    // the landmark is not seen from this camera: zero rows
+                    double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
+#pragma unroll
+                    for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(0.0, 0.0);
+                    prefetch(jl + TL);
+                } else if (jl < nj) {
                     double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
                     const double p[3] = {nx[3], nx[4], nx[5]};
                     const double sl[3] = {nx[6], nx[7], nx[8]};
                     const double ou = nx[0], ov = nx[1], od = nx[2];
-                    const long long e = obs0 + (long long)pi * G + jl;
+                    const long long e = obs0 + (long long)(RAG ? nx_k : pi) * G + jl;
                     double r[3], Jc[18], Jp[9];
                     {
                         double pose[12], Wl[9];
@@ -659,7 +698,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                     if (col >= 6 * L || col < row) continue;
                     const int b = col / 6, rb = col - 6 * b;
                     const int e = s_blk[a * L - a * (a - 1) / 2 + (b - a)];
-                    if (e >= 0) red_add(&S[36ll * e + 6 * ra + rb], h ? -m1 : -m0);
+                    if (e >= 0) red_add(&Sg[36ll * e + 6 * ra + rb], h ? -m1 : -m0);
                 }
             };
             if (tri) {
@@ -703,7 +742,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                         rem -= 6 - a;
                         ++a;
                     }
-                    red_add(&Bdiag[36ll * f + 6 * a + a + rem], acc);
+                    red_add(&Bg[36ll * f + 6 * a + a + rem], acc);
                 } else if (k < 27) {
                     red_add(&gp[6ll * f + (k - 21)], acc);
                 } else {
@@ -719,8 +758,19 @@ __global__ void __launch_bounds__(G2_NT, MINB)
 
 }  // namespace
 
-void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, LmDiag dg, double* S,
-                          double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
+void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, int n_items_rag, LmDiag dg,
+                          double* S, double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
+    // items: [0, n_items_small) exact groups with L <= 10, then exact groups with 10 < L <= 16, then the last
+    // n_items_rag items: ragged groups (camera window <= 10)
+    if (n_items_rag > 0) {
+        const int lo = g.n_items - n_items_rag;
+        const int grid = n_items_rag < 2 * kSMs ? n_items_rag : 2 * kSMs;
+        if (v.W_per_obs)
+            schur_grouped2_kernel<true, 2, true><<<grid, G2_NT, 0, s>>>(v, g, lo, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
+        else
+            schur_grouped2_kernel<false, 2, true><<<grid, G2_NT, 0, s>>>(v, g, lo, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
     if (n_items_small > 0) {
         // Two resident CTAs per SM.  Measured alternatives on C5 (this kernel: 2.47 ms): three CTAs per SM
@@ -744,10 +794,12 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
             schur_grouped2_kernel<false, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    if (g.n_items > n_items_small) {
-        const int n = g.n_items - n_items_small;
+    if (g.n_items - n_items_rag > n_items_small) {
+        const int n = g.n_items - n_items_rag - n_items_small;
         const int grid = n < 2 * kSMs ? n : 2 * kSMs;
-        schur_grouped_kernel<5><<<grid, 192, 0, s>>>(v, g, n_items_small, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
+        // (more than 10 cameras: always beyond the preconditioner's window)
+        schur_grouped_kernel<5><<<grid, 192, 0, s>>>(v, g, n_items_small, g.n_items - n_items_rag, dg, g.S_long ? g.S_long : S,
+                                                      g.S_long ? g.Bdiag_long : Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     CSLAM_CUDA(cudaGetLastError());

@@ -68,7 +68,7 @@ def project(cam, pc):
 
 
 def make_track(n_poses, new_per_frame, track_len, seed=42, pix_sigma=1.0, pose_sigma=(0.02, 0.01),
-               point_sigma=0.05, spacing=0.3, per_obs_W=False, cam=None, closed=False):
+               point_sigma=0.05, spacing=0.3, per_obs_W=False, cam=None, closed=False, ragged=None):
     """A sims-style stereo track.
 
     Every frame sees `new_per_frame` new landmarks, each tracked over `track_len` consecutive
@@ -79,6 +79,11 @@ def make_track(n_poses, new_per_frame, track_len, seed=42, pix_sigma=1.0, pose_s
     (scripts/ba_all_sims.sh:8-13: triangle / square / penta / circle tracks): the tracks of the last
     frames run on into the first ones, so the last poses share landmarks with the first and the
     reduced camera system gets blocks far from its diagonal.
+
+    ragged=dict(mean=..., max=..., drop=...) makes the tracks what a real stereo front end produces
+    instead of `track_len` consecutive frames each: lengths 2 + Geometric(1 / (mean - 2)) clipped to
+    `max` (default 30), and every observation after the first dropped with probability `drop`
+    (default 0.1; at least two are kept).  `track_len` is then only the mean used when `mean` is absent.
     """
     cam = dict(cam or KITTI)
     rng = np.random.default_rng(seed)
@@ -95,8 +100,34 @@ def make_track(n_poses, new_per_frame, track_len, seed=42, pix_sigma=1.0, pose_s
     Rm, tm = pose_R(poses_gt)[mid], pose_t(poses_gt)[mid]
     points_gt = np.einsum("nji,nj->ni", Rm, pc - tm)  # R^T (p_c - t)
     # observations, pose-major
-    k = ((first[:, None] + np.arange(track_len)[None, :]) % n_poses).reshape(-1)
-    j = np.repeat(np.arange(n_pts, dtype=np.int64), track_len)
+    if ragged is None:
+        k = ((first[:, None] + np.arange(track_len)[None, :]) % n_poses).reshape(-1)
+        j = np.repeat(np.arange(n_pts, dtype=np.int64), track_len)
+    else:
+        mean = float(ragged.get("mean", track_len))
+        lmax = int(ragged.get("max", 30))
+        drop = float(ragged.get("drop", 0.1))
+        n_starts = n_poses if closed else n_poses - 1
+        n_pts = n_starts * new_per_frame
+        first = np.repeat(np.arange(n_starts, dtype=np.int64), new_per_frame)
+        length = np.minimum(2 + rng.geometric(1.0 / max(mean - 2.0, 1e-9), n_pts) - 1, lmax)
+        if not closed:
+            length = np.minimum(length, n_poses - first)
+        # the landmark sits in the frustum of the middle frame of ITS track
+        mid = (first + length // 2) % n_poses
+        u = rng.uniform(150.0, IMG_W - 150.0, n_pts)
+        v = rng.uniform(60.0, IMG_H - 60.0, n_pts)
+        z = rng.uniform(4.0, 30.0, n_pts)
+        pc = np.stack([(u - cam["cu"]) * z / cam["fu"], (v - cam["cv"]) * z / cam["fv"], z], axis=1)
+        Rm, tm = pose_R(poses_gt)[mid], pose_t(poses_gt)[mid]
+        points_gt = np.einsum("nji,nj->ni", Rm, pc - tm)
+        off = np.arange(lmax)[None, :]
+        keep = off < length[:, None]
+        dropped = (rng.random((n_pts, lmax)) < drop) & (off >= 2)   # the first two observations always stay
+        keep &= ~dropped
+        jj, oo = np.nonzero(keep)
+        k = (first[jj] + oo) % n_poses
+        j = jj.astype(np.int64)
     order = np.argsort(k, kind="stable")
     k, j = k[order], j[order]
     pck = np.einsum("nij,nj->ni", pose_R(poses_gt)[k], points_gt[j]) + pose_t(poses_gt)[k]

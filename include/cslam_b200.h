@@ -77,6 +77,10 @@ typedef struct cslam_options {
                                DMMA tensor cores when 6 x free poses <= 12288, i.e. a factor of at most 1.2 GB;
                                PCG run to 1e-15 beyond that), 1 = dense whenever it fits (also instead of the
                                banded solver), -1 = never */
+    int bandpc_solver;      /* exact solve of a reduced system that is neither a narrow band nor small enough for the dense
+                               factorisation (long tracks / loop closures on a large problem): 0 = auto (conjugate gradients
+                               preconditioned with the banded direct solve of the short-track landmarks' part of the
+                               system, run to a 1e-15 residual), -1 = never (block-Jacobi PCG run to 1e-15) */
 } cslam_options;
 
 typedef struct cslam_summary {

@@ -225,6 +225,37 @@ def test_dense_cholesky_exact_solve(product, shape, closed):
     assert np.all(lg[1:, 7] == 1), "one direct solve per LM iteration"
 
 
+@pytest.mark.parametrize("per_obs_W", [False, True])
+def test_ragged_track_groups(product, per_obs_W):
+    """Tracks of variable length with drop-outs (what a stereo front end produces): hardly any two landmarks share
+    their exact camera list, so the grouped DMMA Schur kernel takes them as RAGGED groups — the landmarks of a
+    first-camera bucket whose cameras fit a window of 10, each seeing a subset of the group's camera list — and
+    the result must still be the oracle's."""
+    tr = syn.make_track(150, 30, 6, seed=41, per_obs_W=per_obs_W, ragged=dict(mean=5, max=9, drop=0.15))
+    pg, _, _ = syn.build_problem(tr, **FIXED)
+    info = pg.analyze()
+    assert info["n_grouped_landmarks"] > 0.9 * info["n_landmarks"], info
+    assert info["n_observations"] == tr["obs_cam"].size
+    g, o = solve_pair(tr, 5)
+    check_lm(g, o)
+    # the generic per-landmark kernel (schur_path = 1) must agree with the grouped one
+    p1, poses1, points1 = syn.build_problem(tr, schur_path=1, **dict(FIXED, max_num_iterations=5))
+    p1.solve()
+    assert rel_err(g[2], poses1) < 1e-9 and rel_err(g[3], points1) < 1e-9
+
+
+def test_band_preconditioned_cg(product):
+    """Ragged tracks as a stereo front end produces them (lengths 2 .. 20 with drop-outs) on a problem too large for
+    the dense factorisation: the reduced system is a band plus weak far blocks, and the exact solve is conjugate
+    gradients preconditioned with the banded direct solver (band-truncated, diagonally compensated system) run to a
+    1e-15 residual — the oracle's exact trajectory in a handful of iterations per solve instead of thousands."""
+    tr = syn.make_track(2300, 6, 6, seed=37, ragged=dict(mean=6, max=20, drop=0.1))
+    g, o = solve_pair(tr, 4)
+    check_lm(g, o)
+    lin = g[0].iteration_log()[1:, 7]
+    assert lin.min() >= 2 and lin.max() <= 400, lin   # (block-Jacobi PCG needs several thousand here)
+
+
 def test_dense_cholesky_matches_band(product):
     """dense_solver = 1 takes the dense path even for a banded system: same iterates as the banded
     direct solver."""
