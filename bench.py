@@ -178,10 +178,12 @@ def run_reference(args):
 
 
 def e2e_transfer_bytes(world, n_obs, n_lm, n_cam):
-    """Bytes one cslam_solve call moves, summed over the ranks (what csrc/engine.cu::upload / download copy):
-    every rank uploads the two index arrays (8 B / observation), the measurements (24 B / observation), the
-    points and the poses of the WHOLE problem; every rank downloads all poses and all points."""
-    h2d = world * (n_obs * (8 + 24) + 24 * n_lm + 96 * n_cam)
+    """Bytes one cslam_solve call moves between host and devices, summed over the ranks (what
+    csrc/engine.cu::upload / download copy): the two index arrays (8 B / observation), the measurements
+    (24 B / observation) and the points cross PCIe ONCE — rank r uploads the r-th slice of each and the slices
+    are exchanged over NVLink (in-place all-gather) — the poses go to every rank; every rank downloads all
+    poses and all points."""
+    h2d = n_obs * (8 + 24) + 24 * n_lm + world * 96 * n_cam
     d2h = world * (96 * n_cam + 24 * n_lm)
     return h2d, d2h
 

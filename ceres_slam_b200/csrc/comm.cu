@@ -18,6 +18,7 @@ typedef int (*CommInitRankFn)(void**, int, NcclId, int);
 typedef int (*CommDestroyFn)(void*);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*BroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*GetErrorStringFn)(int);
 
 struct Api {
@@ -27,6 +28,7 @@ struct Api {
     CommDestroyFn comm_destroy = nullptr;
     AllReduceFn all_reduce = nullptr;
     BroadcastFn broadcast = nullptr;
+    AllGatherFn all_gather = nullptr;
     GetErrorStringFn error_string = nullptr;
 };
 
@@ -44,8 +46,9 @@ Api& api() {
     a.comm_destroy = (CommDestroyFn)dlsym(a.handle, "ncclCommDestroy");
     a.all_reduce = (AllReduceFn)dlsym(a.handle, "ncclAllReduce");
     a.broadcast = (BroadcastFn)dlsym(a.handle, "ncclBroadcast");
+    a.all_gather = (AllGatherFn)dlsym(a.handle, "ncclAllGather");
     a.error_string = (GetErrorStringFn)dlsym(a.handle, "ncclGetErrorString");
-    if (!a.get_unique_id || !a.comm_init_rank || !a.comm_destroy || !a.all_reduce || !a.broadcast)
+    if (!a.get_unique_id || !a.comm_init_rank || !a.comm_destroy || !a.all_reduce || !a.broadcast || !a.all_gather)
         throw std::runtime_error("libnccl is missing required symbols");
     return a;
 }
@@ -80,5 +83,9 @@ void comm_allreduce_max(void* comm, double* buf, size_t count, cudaStream_t s) {
 }
 void comm_broadcast(void* comm, double* buf, size_t count, int root, cudaStream_t s) {
     check(api().broadcast(buf, buf, count, /*ncclFloat64*/ 8, root, comm, s), "ncclBroadcast");
+}
+void comm_allgather_bytes(void* comm, void* buf, size_t chunk_bytes, int rank, cudaStream_t s) {
+    check(api().all_gather(static_cast<const char*>(buf) + size_t(rank) * chunk_bytes, buf, chunk_bytes, /*ncclUint8*/ 1, comm, s),
+          "ncclAllGather");
 }
 }  // namespace cslam

@@ -12,4 +12,6 @@ void comm_destroy(void* comm);
 void comm_allreduce_sum(void* comm, double* buf, size_t count, cudaStream_t s);
 void comm_allreduce_max(void* comm, double* buf, size_t count, cudaStream_t s);
 void comm_broadcast(void* comm, double* buf, size_t count, int root, cudaStream_t s);
+// in-place all-gather of raw bytes: rank r's chunk is buf[r * chunk_bytes .. (r + 1) * chunk_bytes)
+void comm_allgather_bytes(void* comm, void* buf, size_t chunk_bytes, int rank, cudaStream_t s);
 }  // namespace cslam

@@ -1109,21 +1109,45 @@ void Engine::upload() {
     const bool gpu_structure = n_st >= gpu_min && n_st > 0 && !lighting_in_solve();
     if (gpu_structure) {
         const int dev = opt.device;
-        d_raw_cam.alloc(n_st, stream);
-        d_raw_pt.alloc(n_st, stream);
-        d_raw_uvd.alloc(3 * n_st, stream);
-        d_raw_W.alloc(st_W_per_obs ? 9 * n_st : 9, stream);
-        d_raw_pts.alloc(3 * std::max<size_t>(n_points, 1), stream);
+        // Several ranks of one job share the host and its PCIe root: every rank uploading the whole problem
+        // multiplies the host-side traffic by the rank count (e2e at 8 GPUs was half of 1 GPU).  Instead rank r
+        // uploads the r-th slice of every array and the slices are exchanged over NVLink (in-place all-gather):
+        // chunk sizes are rounded up, so the device buffers carry a little padding.
+        const size_t R = size_t(std::max(1, n_ranks));
+        auto chunk_of = [&](size_t bytes) { return ((bytes + R - 1) / R + 255) & ~size_t(255); };
+        auto padded = [&](size_t bytes, size_t elem) { return R > 1 ? (chunk_of(bytes) * R + elem - 1) / elem : bytes / elem; };
+        auto h2d_slice = [&](void* dst, const void* src, size_t bytes) {
+            if (R == 1) {
+                parallel_h2d(dev, dst, src, bytes);
+                return;
+            }
+            const size_t ch = chunk_of(bytes), lo = std::min(bytes, size_t(rank) * ch), hi = std::min(bytes, lo + ch);
+            if (hi > lo) parallel_h2d(dev, static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+        };
+        auto gather = [&](void* buf, size_t bytes) {
+            if (R > 1) comm_allgather_bytes(nccl_comm, buf, chunk_of(bytes), rank, stream);
+        };
+        const size_t w_count = st_W_per_obs ? 9 * n_st : 9;
+        d_raw_cam.alloc(padded(n_st * sizeof(uint32_t), sizeof(uint32_t)), stream);
+        d_raw_pt.alloc(padded(n_st * sizeof(uint32_t), sizeof(uint32_t)), stream);
+        d_raw_uvd.alloc(padded(3 * n_st * sizeof(double), sizeof(double)), stream);
+        d_raw_W.alloc(st_W_per_obs ? padded(w_count * sizeof(double), sizeof(double)) : 9, stream);
+        d_raw_pts.alloc(padded(3 * std::max<size_t>(n_points, 1) * sizeof(double), sizeof(double)), stream);
         CSLAM_CUDA(cudaStreamSynchronize(stream));
-        parallel_h2d(dev, d_raw_cam.p, st_cam, n_st * sizeof(uint32_t));
-        parallel_h2d(dev, d_raw_pt.p, st_pt, n_st * sizeof(uint32_t));
+        h2d_slice(d_raw_cam.p, st_cam, n_st * sizeof(uint32_t));
+        h2d_slice(d_raw_pt.p, st_pt, n_st * sizeof(uint32_t));
+        gather(d_raw_cam.p, n_st * sizeof(uint32_t));
+        gather(d_raw_pt.p, n_st * sizeof(uint32_t));
         pt.lap("index H2D");
         std::exception_ptr rest_err;
         std::thread rest([&, dev]() {
             try {
-                parallel_h2d(dev, d_raw_uvd.p, st_uvd, 3 * n_st * sizeof(double));
-                parallel_h2d(dev, d_raw_W.p, st_W, (st_W_per_obs ? 9 * n_st : 9) * sizeof(double));
-                if (n_points) parallel_h2d(dev, d_raw_pts.p, h_points, 3 * size_t(n_points) * sizeof(double));
+                h2d_slice(d_raw_uvd.p, st_uvd, 3 * n_st * sizeof(double));
+                if (st_W_per_obs)
+                    h2d_slice(d_raw_W.p, st_W, w_count * sizeof(double));
+                else
+                    parallel_h2d(dev, d_raw_W.p, st_W, 9 * sizeof(double));
+                if (n_points) h2d_slice(d_raw_pts.p, h_points, 3 * size_t(n_points) * sizeof(double));
                 if (pt.on)
                     std::fprintf(stderr, "[cslam timing] %-28s %8.2f ms (second thread, from the start of upload)\n", "  raw H2D done",
                                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload).count());
@@ -1148,6 +1172,10 @@ void Engine::upload() {
         pt.lap(ok ? "build_structure_gpu" : "build_structure (host fallback)");
         rest.join();
         if (rest_err) std::rethrow_exception(rest_err);
+        // the other ranks' slices of the measurements and points (NCCL is driven from this thread only)
+        gather(d_raw_uvd.p, 3 * n_st * sizeof(double));
+        if (st_W_per_obs) gather(d_raw_W.p, w_count * sizeof(double));
+        if (n_points) gather(d_raw_pts.p, 3 * size_t(n_points) * sizeof(double));
         pt.lap("wait for raw H2D");
         if (ok && std::getenv("CSLAM_VERIFY_STRUCTURE")) {
             // debugging / tests: the host analysis must produce exactly the layout the device built
