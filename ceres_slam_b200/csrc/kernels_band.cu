@@ -668,8 +668,9 @@ __global__ void band_assemble_kernel(BandView B, double* T2, double* rhs2) {
 // walks it.  Only the d = 1 term depends on the value finished in the previous step, so the
 // d >= 2 terms of step k-1 are formed (lane groups 1..4) while step k is completed (lane group 0),
 // and the factor columns stream through a cp.async ring several steps ahead of their use.
+constexpr int BBS_T = 512;  // one warp walks the recurrence; the rest only helps with the two parallel passes around it
 template <int W, bool kSpike>
-__global__ void __launch_bounds__(128) band_backsub_kernel(BandView B, const double* ysep) {
+__global__ void __launch_bounds__(BBS_T) band_backsub_kernel(BandView B, const double* ysep) {
     constexpr int W1 = W + 1, GC = kSpike ? 1 + 6 * W : 1, b = 6 * W;
     constexpr int COLD = W1 * 36;           // doubles of one factor column
     constexpr int NST = 8, PD = 6;          // ring stages, prefetch distance
@@ -687,20 +688,45 @@ __global__ void __launch_bounds__(128) band_backsub_kernel(BandView B, const dou
     double* yl = z + 6 * (B.m + W);          // [b] separator before
     if (*B.fail) return;
     if (has_left)
-        for (int c = tid; c < b; c += 128) yl[c] = ysep[(long long)(p - 1) * b + c];
+        for (int c = tid; c < b; c += BBS_T) yl[c] = ysep[(long long)(p - 1) * b + c];
     if (has_right)
-        for (int c = tid; c < b; c += 128) {
+        for (int c = tid; c < b; c += BBS_T) {
             const double v = ysep[(long long)p * b + c];
             z[6 * ni + c] = v;
             B.y[6ll * ie + c] = v;
         }
     __syncthreads();
-    for (int idx = tid; idx < 6 * ni; idx += 128) {
-        const double* X = B.Xbuf + (long long)(6 * s + idx) * GC;
-        double v = X[0];
-        if (kSpike && has_left)
-            for (int c = 0; c < b; ++c) v -= X[1 + c] * yl[c];
-        z[idx] = v;
+    if (kSpike && has_left) {
+        // z = x_r - X_left y_left: a warp per row, the row's b spike entries read coalesced (a thread per row walked
+        // its 1 + b values one dependent global load at a time: 60 % of this kernel's time), four rows in flight
+        const int wp = tid >> 5, ln = tid & 31;
+        constexpr int NC = (b + 31) / 32;
+        double ylr[NC];
+#pragma unroll
+        for (int u = 0; u < NC; ++u) ylr[u] = ln + 32 * u < b ? yl[ln + 32 * u] : 0.0;
+        for (int row0 = 4 * wp; row0 < 6 * ni; row0 += 4 * (BBS_T / 32)) {
+            double v[4], x0[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int row = row0 + q;
+                v[q] = 0.0;
+                x0[q] = 0.0;
+                if (row < 6 * ni) {
+                    const double* X = B.Xbuf + (long long)(6 * s + row) * GC;
+                    x0[q] = X[0];
+#pragma unroll
+                    for (int u = 0; u < NC; ++u)
+                        if (ln + 32 * u < b) v[q] += X[1 + ln + 32 * u] * ylr[u];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double sum = warp_sum(v[q]);
+                if (ln == 0 && row0 + q < 6 * ni) z[row0 + q] = x0[q] - sum;
+            }
+        }
+    } else {
+        for (int idx = tid; idx < 6 * ni; idx += BBS_T) z[idx] = B.Xbuf[(long long)(6 * s + idx) * GC];
     }
     __syncthreads();
     if (tid < 32 && ni > 0) {
@@ -763,7 +789,7 @@ __global__ void __launch_bounds__(128) band_backsub_kernel(BandView B, const dou
         cp_async_wait<0>();
     }
     __syncthreads();
-    for (int idx = tid; idx < 6 * ni; idx += 128) B.y[6ll * s + idx] = z[idx];
+    for (int idx = tid; idx < 6 * ni; idx += BBS_T) B.y[6ll * s + idx] = z[idx];
 }
 
 __global__ void band_status_kernel(const int* fail, double* ps) {
@@ -805,7 +831,7 @@ void run_backsub(cudaStream_t s, const BandView& V, const double* ysep) {
         attr.mark(dev_);
     }
     const size_t smem = sizeof(double) * (8 * size_t(W + 1) * 36 + 6 * size_t(V.m + W) + 6 * size_t(W));
-    band_backsub_kernel<W, kSpike><<<V.P, 128, smem, s>>>(V, ysep);
+    band_backsub_kernel<W, kSpike><<<V.P, BBS_T, smem, s>>>(V, ysep);
     CSLAM_CUDA(cudaGetLastError());
 }
 
