@@ -439,12 +439,18 @@ cslam_status cslam_attach_comm(cslam_problem* p, int n_ranks, int rank, const ui
             e.nccl_comm = cslam::comm_create(n_ranks, rank, id);
             // NCCL connects its channels lazily at the first collective of each kind: do that here,
             // not inside the first solve
+            // (with messages of the size a solve sends: large collectives use more channels and other algorithms
+            // than small ones, and each of those is connected at its own first use — ~80 ms at 8 ranks)
+            const size_t nw = size_t(4) << 20;   // 32 MB of doubles
             double* tmp = nullptr;
-            CSLAM_CUDA(cudaMalloc(&tmp, 64 * sizeof(double)));
-            CSLAM_CUDA(cudaMemset(tmp, 0, 64 * sizeof(double)));
+            CSLAM_CUDA(cudaMalloc(&tmp, nw * sizeof(double)));
+            CSLAM_CUDA(cudaMemset(tmp, 0, nw * sizeof(double)));
             cslam::comm_allreduce_sum(e.nccl_comm, tmp, 64, nullptr);
+            cslam::comm_allreduce_sum(e.nccl_comm, tmp, nw, nullptr);
             cslam::comm_allreduce_max(e.nccl_comm, tmp, 1, nullptr);
             cslam::comm_broadcast(e.nccl_comm, tmp, 64, 0, nullptr);
+            cslam::comm_broadcast(e.nccl_comm, tmp, nw / 8, 0, nullptr);
+            cslam::comm_allgather_bytes(e.nccl_comm, tmp, (nw * sizeof(double) / size_t(n_ranks)) & ~size_t(255), rank, nullptr);
             CSLAM_CUDA(cudaDeviceSynchronize());
             cudaFree(tmp);
         }

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (parity PINNED: checked block by block against the reference's own unmodified
+// headers compiled in oracle/_ref, tests/test_ref_pin.py, 1e-14).
 //
 // Restatement of the reference's sensor / lighting models and Ceres cost functors as templates on
 // the scalar type.  Running them on oracle::Jet<N> reproduces what ceres::AutoDiffCostFunction

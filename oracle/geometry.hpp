@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (parity PINNED: checked against the reference's own unmodified headers compiled
+// in oracle/_ref, tests/test_ref_pin.py, 1e-14).
 //
 // CPU restatement, templated on the scalar (double or oracle::Jet<N>), of the reference's
 // header-only geometry: SO(3) as row-major 3x3, SE(3) as the 12-vector [t | R row-major],

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned: the reference ships no golden vectors).
+// ORACLE — TEST INFRASTRUCTURE ONLY (the functors evaluated with these dual numbers are PINNED against the reference's
+// own headers on oracle/_ref's stand-in for ceres::Jet, tests/test_ref_pin.py; the reference ships no golden vectors).
 //
 // Forward-mode dual number with N partials. This is the arithmetic that
 // `ceres::AutoDiffCostFunction` / `ceres::AutoDiffLocalParameterization` run the reference's

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (residual blocks PINNED via oracle/_ref; the solver rules below are Ceres' and
+// Ceres is absent: that part is parity UNPINNED).
 //
 // CPU restatement of the problem `solveWindow` of tests/dataset_ba_phong.cpp:26-255 hands to Ceres
 // when lighting is enabled (default / --dirlight, the joint solve of stage 3) and of what Ceres then

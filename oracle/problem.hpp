@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (residual blocks PINNED via oracle/_ref; the solver rules below are Ceres' and
+// Ceres is absent: that part is parity UNPINNED).
 //
 // CPU restatement of what the reference's `solveWindow` hands to Ceres and what Ceres then does
 // with it: problem assembly (tests/dataset_vo.cpp:22-85, tests/dataset_vo_sun.cpp:25-187),
