@@ -9,7 +9,11 @@
 // (the SPARSE_SCHUR-equivalent exact solve), back-substitution, step acceptance and trust-region
 // bookkeeping (Ceres rules; the same sequence Engine::lm_iterate drives from
 // the host).  A batch of windows is one launch; nothing returns to the host until every window
-// has terminated.
+// has terminated.  The kernel is instantiated twice: Levenberg-Marquardt, and DOGLEG (TRADITIONAL /
+// SUBSPACE, dataset_vo_sun.cpp:142-143 — the default of the workload scripts/ba_all_*.sh runs): the
+// Gauss-Newton solve goes through the same in-CTA Schur path with mu in place of 1/radius, the
+// eight inner products of dogleg_products_kernel are formed by the CTA, and thread 0 runs the
+// scalar strategy of dogleg_host.h (the functions the host-driven engine runs on the CPU).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -28,7 +32,7 @@ constexpr int WIN_THREADS = 128;
 constexpr int WIN_CAMV = 33;            // per camera: U upper triangle (21) | g (6) | rhs (6)
 
 struct WinOpts {
-    int max_iter, nonmono, max_nonmono, max_invalid, jacobi;
+    int max_iter, nonmono, max_nonmono, max_invalid, jacobi, dogleg_type;
     double r0, rmax, rmin, min_rel, dmin, dmax, ftol, gtol, ptol;
 };
 
@@ -51,6 +55,8 @@ struct WinBufs {
     const double *obs_u, *obs_v, *obs_d, *obs_W;
     double* sc_l;              // [sum n_lm][3] Jacobi scaling of the point columns
     double* gl;                // [sum n_lm][3] scaled point gradient of the last Schur pass
+    double* yl;                // [sum n_lm][3] DOGLEG: landmark part of the Gauss-Newton solve (scaled)
+    double* diag_l;            // [sum n_lm][3] DOGLEG: clamp(diag(J^T J)) of the point columns (scaled)
     const SunBlockData* suns;
     const PriorBlockData* priors;
     cslam_summary* summaries;
@@ -423,7 +429,8 @@ __device__ bool window_cholesky_solve(double* S, int n, const double* b, double*
 
 enum { CTL_STOP = 0, CTL_COPY_BEST, CTL_NEED_GRAD, CTL_ACCEPT, CTL_COUNT };
 
-__global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
+template <bool DOGLEG>
+__global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B, int win0) {
     __shared__ double sS[WIN_NMAX * WIN_NMAX];
     __shared__ double s_cam[WIN_PMAX * WIN_CAMV];
     __shared__ double s_bp[WIN_NMAX], s_y[WIN_NMAX], s_scp[WIN_NMAX], s_gp[WIN_NMAX];
@@ -434,9 +441,13 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
     __shared__ int s_flag;
     __shared__ double s_radius;
     __shared__ WinDesc D;
+    // DOGLEG: clamp(diag(J^T J)) of the pose columns, {c1, c2, model cost change} of the trial step, the model
+    __shared__ double s_dp[DOGLEG ? WIN_NMAX : 1], s_c[3];
+    __shared__ __align__(8) unsigned char s_model_raw[DOGLEG ? sizeof(DoglegModel) : 8];
 
     const int tid = threadIdx.x;
-    if (tid == 0) D = B.desc[blockIdx.x];
+    const int win = win0 + blockIdx.x;
+    if (tid == 0) D = B.desc[win];
     __syncthreads();
     const WinOpts& O = D.o;
     const int n = 6 * D.n_free;
@@ -464,6 +475,8 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
     double* pts_cur = B.pts + 3 * D.lm_off;
     double* pts_cand = B.pts_cand + 3 * D.lm_off;
     double* pts_best = B.pts_best + 3 * D.lm_off;
+    double* yl_g = B.yl + 3 * D.lm_off;
+    double* dl_g = B.diag_l + 3 * D.lm_off;
     double* logp = B.logs + D.log_off;
     int cur = 0, cand = 1;  // indices into s_pose; 2 = best
 
@@ -535,6 +548,12 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
     int termination_type = 1, termination_reason = 0, n_rows = 0;
     bool step_ok_prev = false, grad_fresh = true;
     const int max_nonmono = O.nonmono ? O.max_nonmono : 0;
+    // DOGLEG (DoglegStrategy): mu and `reuse` are uniform over the CTA (they change on decisions every thread sees);
+    // the model and the norm of the last step belong to thread 0
+    double mu = 1e-8, dl_step_norm = 0.0;
+    bool reuse = false;
+    DoglegModel& dmodel = *reinterpret_cast<DoglegModel*>(s_model_raw);
+    if (DOGLEG && tid == 0) dmodel = DoglegModel();
     auto push_row = [&](const double* row) {
         if (n_rows < D.log_cap) {
             for (int k = 0; k < CSLAM_LOG_COLS; ++k) logp[CSLAM_LOG_COLS * n_rows + k] = row[k];
@@ -590,22 +609,29 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
         }
         if (s_ctl[CTL_STOP]) break;
         const bool need_grad = s_ctl[CTL_NEED_GRAD] != 0;
-        const LmDiag dg{1.0 / s_radius, O.dmin, O.dmax};
-        // ---- Schur build at (x, radius) --------------------------------------------------------
-        double pass_cost, n_invalid;
-        window_schur_pass<false>(w, s_pose[cur], pts_cur, dg, sS, n, s_cam, nullptr, s_red, &pass_cost, &n_invalid);
-        unpack_cam();
-        // finalize: S_aa += U_aa + D^2 (finalize_kernel)
-        for (int i = tid; i < D.n_free * 36; i += WIN_THREADS) {
-            const int f = i / 36, a = (i % 36) / 6, b = i % 6;
-            const int lo = min(a, b), hi = max(a, b);
-            int t = 0;
-            for (int q = 0; q < lo; ++q) t += 6 - q;
-            double u = s_cam[f * WIN_CAMV + t + (hi - lo)];
-            if (a == b) u += fmin(fmax(u, dg.min_diag), dg.max_diag) * dg.inv_radius;
-            sS[(6 * f + a) * n + 6 * f + b] += u;
-        }
-        __syncthreads();
+        LmDiag dg{DOGLEG ? mu : 1.0 / s_radius, O.dmin, O.dmax};
+        // ---- Schur build at (x, radius); DOGLEG: at (x, mu), kept while rejected steps shrink the radius ----
+        double pass_cost, n_invalid = 0.0;
+        auto build_system = [&]() {
+            window_schur_pass<false>(w, s_pose[cur], pts_cur, dg, sS, n, s_cam, nullptr, s_red, &pass_cost, &n_invalid);
+            unpack_cam();
+            // finalize: S_aa += U_aa + D^2 (finalize_kernel)
+            for (int i = tid; i < D.n_free * 36; i += WIN_THREADS) {
+                const int f = i / 36, a = (i % 36) / 6, b = i % 6;
+                const int lo = min(a, b), hi = max(a, b);
+                int t = 0;
+                for (int q = 0; q < lo; ++q) t += 6 - q;
+                double u = s_cam[f * WIN_CAMV + t + (hi - lo)];
+                if (a == b) {
+                    const double dd = fmin(fmax(u, dg.min_diag), dg.max_diag);
+                    if (DOGLEG) s_dp[6 * f + a] = dd;
+                    u += dd * dg.inv_radius;
+                }
+                sS[(6 * f + a) * n + 6 * f + b] += u;
+            }
+            __syncthreads();
+        };
+        if (!DOGLEG || !reuse) build_system();
         if (need_grad) gradnorm(&gmax, &xnorm);
         if (tid == 0) {
             int stop = 0;
@@ -633,13 +659,242 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
         // ---- LevenbergMarquardtStrategy::ComputeStep: exact solve of the reduced system --------
         bool valid = n_invalid == 0.0;
         int lin_iters = 0;
-        if (valid && n > 0) {
+        double model = 0, ccost = 0, sn = 0, xn = 0, bad = 0;
+        if (DOGLEG) {
+            // ---- DoglegStrategy::ComputeStep (Engine::dogleg_step) ------------------------------------
+            valid = true;
+            if (!reuse) {
+                // Gauss-Newton solve (J^T J + mu D^2) y = J^T r, mu raised tenfold while the factorisation fails
+                bool solved = false, have = true;
+                while (mu < 1.0) {
+                    if (!have) {
+                        dg.inv_radius = mu;
+                        build_system();
+                        have = true;
+                    }
+                    bool ok = n_invalid == 0.0;
+                    if (ok && n > 0) ok = window_cholesky_solve(sS, n, s_bp, s_y, &s_flag);
+                    if (ok) {
+                        solved = true;
+                        break;
+                    }
+                    mu *= 10.0;
+                    have = false;
+                }
+                valid = solved;
+                if (solved) {
+                    lin_iters = 1;
+                    // landmark part of y (backsub_kernel), clamp(diag(J^T J)), and the eight sums of
+                    // dogleg_products_kernel / dogleg_products_cam_kernel
+                    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int j = tid; j < w.n_lm; j += WIN_THREADS) {
+                        const uint32_t e0 = w.lm_ptr[j], e1 = w.lm_ptr[j + 1];
+                        const double p[3] = {pts_cur[3 * j], pts_cur[3 * j + 1], pts_cur[3 * j + 2]};
+                        const double sl[3] = {w.sc_l[3 * j], w.sc_l[3 * j + 1], w.sc_l[3 * j + 2]};
+                        double V[6] = {0, 0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
+                        WObs o;
+                        for (uint32_t e = e0; e < e1; ++e) {
+                            w_eval(w, e, s_pose[cur], p, sl, o);
+                            double Jy[3] = {0, 0, 0};
+                            if (o.f >= 0) {
+                                const double* y = s_y + 6 * o.f;
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                                    for (int a = 0; a < 6; ++a) Jy[k] += o.Jc[6 * k + a] * y[a];
+                            }
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const double a = o.Jp[3 * k], b = o.Jp[3 * k + 1], c = o.Jp[3 * k + 2];
+                                V[0] += a * a; V[1] += a * b; V[2] += a * c; V[3] += b * b; V[4] += b * c; V[5] += c * c;
+                                const double wv = o.r[k] - Jy[k];
+                                t[0] += a * wv; t[1] += b * wv; t[2] += c * wv;
+                            }
+                        }
+                        double d2[3] = {V[0], V[3], V[5]};
+                        V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+                        V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+                        V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+                        double Vi[6], yl[3] = {0, 0, 0}, tg[3];
+                        if (invert_sym3(V, Vi)) {
+                            yl[0] = Vi[0] * t[0] + Vi[1] * t[1] + Vi[2] * t[2];
+                            yl[1] = Vi[1] * t[0] + Vi[3] * t[1] + Vi[4] * t[2];
+                            yl[2] = Vi[2] * t[0] + Vi[4] * t[1] + Vi[5] * t[2];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            d2[q] = fmin(fmax(d2[q], dg.min_diag), dg.max_diag);
+                            dl_g[3 * j + q] = d2[q];
+                            yl_g[3 * j + q] = yl[q];
+                            const double g = w.gl[3 * j + q];
+                            tg[q] = g / d2[q];
+                            acc[0] += g * g / d2[q];
+                            acc[1] -= g * yl[q];
+                            acc[2] += d2[q] * yl[q] * yl[q];
+                        }
+                        for (uint32_t e = e0; e < e1; ++e) {
+                            w_eval(w, e, s_pose[cur], p, sl, o);
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                double jg = o.Jp[3 * k] * tg[0] + o.Jp[3 * k + 1] * tg[1] + o.Jp[3 * k + 2] * tg[2];
+                                double jy = o.Jp[3 * k] * yl[0] + o.Jp[3 * k + 1] * yl[1] + o.Jp[3 * k + 2] * yl[2];
+                                if (o.f >= 0) {
+#pragma unroll
+                                    for (int a = 0; a < 6; ++a) {
+                                        jg += o.Jc[6 * k + a] * (s_gp[6 * o.f + a] / s_dp[6 * o.f + a]);
+                                        jy += o.Jc[6 * k + a] * s_y[6 * o.f + a];
+                                    }
+                                }
+                                acc[3] += jg * jg;
+                                acc[4] += jg * jy;
+                                acc[5] += jy * jy;
+                                acc[6] += jg * o.r[k];
+                                acc[7] += jy * o.r[k];
+                            }
+                        }
+                    }
+                    if (tid < n) {
+                        const double g = s_gp[tid], d2 = s_dp[tid], y = s_y[tid];
+                        acc[0] += g * g / d2;
+                        acc[1] -= g * y;
+                        acc[2] += d2 * y * y;
+                    }
+                    if (tid < w.n_sun + w.n_prior) {
+                        double r[6], J[36];
+                        int rows, cam;
+                        if (tid < w.n_sun) {
+                            const SunBlockData& sb = w.suns[tid];
+                            cam = int(sb.cam);
+                            rows = 2;
+                            sun_block(s_pose[cur] + 12 * cam, sb.obs_c, sb.ref_g, sb.W, sb.az_thresh, sb.zen_thresh, r, J);
+                            const double sq = r[0] * r[0] + r[1] * r[1];
+                            double rho0 = sq, sr = 1.0;
+                            if (sb.huber > 0.0) huber_rho(sb.huber, sq, &rho0, &sr);
+                            r[0] *= sr;
+                            r[1] *= sr;
+                            for (int k = 0; k < 12; ++k) J[k] *= sr;
+                        } else {
+                            const PriorBlockData& pr = w.priors[tid - w.n_sun];
+                            cam = int(pr.cam);
+                            rows = 6;
+                            prior_block(s_pose[cur] + 12 * cam, pr.Tref, pr.W, r, J);
+                        }
+                        const int f = s_free[cam];
+                        if (f >= 0)
+                            for (int k = 0; k < rows; ++k) {
+                                double jg = 0, jy = 0;
+                                for (int a = 0; a < 6; ++a) {
+                                    const double js = J[6 * k + a] * s_scp[6 * f + a];
+                                    jg += js * (s_gp[6 * f + a] / s_dp[6 * f + a]);
+                                    jy += js * s_y[6 * f + a];
+                                }
+                                acc[3] += jg * jg;
+                                acc[4] += jg * jy;
+                                acc[5] += jy * jy;
+                                acc[6] += jg * r[k];
+                                acc[7] += jy * r[k];
+                            }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = cta_sum(acc[k], s_red);
+                    if (tid == 0) {
+                        DoglegModel& m = dmodel;
+                        m.G11 = acc[0], m.G12 = acc[1], m.G22 = acc[2];
+                        m.JGG = acc[3], m.JGY = acc[4], m.JYY = acc[5], m.JGR = acc[6], m.JYR = acc[7];
+                        bool finite = true;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) finite = finite && isfinite(acc[k]);
+                        s_flag = (finite && m.prepare(O.dogleg_type == 1)) ? 1 : 0;
+                    }
+                    __syncthreads();
+                    valid = s_flag != 0;
+                    __syncthreads();
+                    if (valid) reuse = true;
+                }
+            }
+            if (valid) {
+                // ---- the step for this radius: two coefficients, Y = -c1 g / D^2 + c2 y (dogleg_combine_kernel) ----
+                if (tid == 0) {
+                    double c1, c2;
+                    if (O.dogleg_type == 1)
+                        dmodel.subspace(radius, &c1, &c2, &dl_step_norm);
+                    else
+                        dmodel.traditional(radius, &c1, &c2, &dl_step_norm);
+                    s_c[0] = c1;
+                    s_c[1] = c2;
+                    s_c[2] = dmodel.model_cost_change(c1, c2);
+                }
+                __syncthreads();
+                const double c1 = s_c[0], c2 = s_c[1];
+                if (tid < D.n_poses) {
+                    const int ff = s_free[tid];
+                    const double* x = s_pose[cur] + 12 * tid;
+                    double* yv = s_pose[cand] + 12 * tid;
+                    if (ff >= 0) {
+                        double eps[6], out[12];
+                        for (int k = 0; k < 6; ++k) {
+                            const double Y = -c1 * s_gp[6 * ff + k] / s_dp[6 * ff + k] + c2 * s_y[6 * ff + k];
+                            eps[k] = -Y * s_scp[6 * ff + k];
+                            if (isnan(eps[k]) || isinf(eps[k])) bad = 1;
+                        }
+                        se3_plus(x, eps, out);
+                        for (int k = 0; k < 12; ++k) {
+                            yv[k] = out[k];
+                            sn += (x[k] - out[k]) * (x[k] - out[k]);
+                            xn += out[k] * out[k];
+                        }
+                    } else {
+                        for (int k = 0; k < 12; ++k) yv[k] = x[k];
+                    }
+                }
+                __syncthreads();
+                // candidate landmarks and the cost there (points_apply_kernel)
+                for (int j = tid; j < w.n_lm; j += WIN_THREADS) {
+                    const uint32_t e0 = w.lm_ptr[j], e1 = w.lm_ptr[j + 1];
+                    double pn[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const double pq = pts_cur[3 * j + q];
+                        const double Y = -c1 * w.gl[3 * j + q] / dl_g[3 * j + q] + c2 * yl_g[3 * j + q];
+                        const double dl = -Y * w.sc_l[3 * j + q];
+                        if (isnan(dl) || isinf(dl)) bad = 1;
+                        pn[q] = pq + dl;
+                        pts_cand[3 * j + q] = pn[q];
+                        sn += (pq - pn[q]) * (pq - pn[q]);
+                        xn += pn[q] * pn[q];
+                    }
+                    for (uint32_t e = e0; e < e1; ++e) {
+                        double rc[3];
+                        const int c = w.obs_cam[e];
+                        const double* Wm = w.W_per_obs ? w.obs_W + 9ll * e : w.obs_W;
+                        stereo_block<false>(w.cam, s_pose[cand] + 12 * c, pn, w.obs_u[e], w.obs_v[e], w.obs_d[e], Wm, rc, nullptr,
+                                            nullptr);
+                        ccost += 0.5 * (rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2]);
+                    }
+                }
+                // camera-only blocks at the candidate (camonly_step_kernel)
+                if (tid < w.n_sun + w.n_prior) {
+                    double r[6];
+                    if (tid < w.n_sun) {
+                        const SunBlockData& sb = w.suns[tid];
+                        sun_block(s_pose[cand] + 12 * int(sb.cam), sb.obs_c, sb.ref_g, sb.W, sb.az_thresh, sb.zen_thresh, r, nullptr);
+                        const double sq = r[0] * r[0] + r[1] * r[1];
+                        double rho0 = sq, sr = 1.0;
+                        if (sb.huber > 0.0) huber_rho(sb.huber, sq, &rho0, &sr);
+                        ccost += 0.5 * rho0;
+                    } else {
+                        const PriorBlockData& pr = w.priors[tid - w.n_sun];
+                        prior_block(s_pose[cand] + 12 * int(pr.cam), pr.Tref, pr.W, r, nullptr);
+                        for (int k = 0; k < 6; ++k) ccost += 0.5 * r[k] * r[k];
+                    }
+                }
+            }
+        } else if (valid && n > 0) {
             valid = window_cholesky_solve(sS, n, s_bp, s_y, &s_flag);
             lin_iters = 1;
         }
         // ---- candidate: Plus, back-substitution, model cost change, candidate cost ---------------
-        double model = 0, ccost = 0, sn = 0, xn = 0, bad = 0;
-        if (valid) {
+        if (!DOGLEG && valid) {
             if (tid < D.n_poses) {
                 const int ff = s_free[tid];
                 const double* x = s_pose[cur] + 12 * tid;
@@ -770,6 +1025,7 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
         sn = cta_sum(sn, s_red);
         xn = cta_sum(xn, s_red);
         bad = cta_sum(bad, s_red);
+        if (DOGLEG && valid) model = s_c[2];
         if (valid && (bad != 0.0 || !(model > 0.0))) valid = false;
         // ---- step evaluation (thread 0) ---------------------------------------------------------
         if (tid == 0) {
@@ -788,8 +1044,10 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
                     termination_reason = 6;
                     stop = 1;
                 } else {
-                    radius = radius / decrease_factor;
-                    decrease_factor *= 2.0;
+                    if (!DOGLEG) {  // (DoglegStrategy::StepIsInvalid raises mu, below)
+                        radius = radius / decrease_factor;
+                        decrease_factor *= 2.0;
+                    }
                     row[6] = radius;
                     push_row(row);
                 }
@@ -827,9 +1085,18 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
                         step_ok_prev = true;
                         grad_fresh = false;
                         row[9] = 1;
-                        radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * row[5] - 1.0, 3.0));
-                        radius = fmin(O.rmax, radius);
-                        decrease_factor = 2.0;
+                        if (DOGLEG) {
+                            // DoglegStrategy::StepAccepted
+                            if (row[5] < 0.25) radius *= 0.5;
+                            if (row[5] > 0.75) {
+                                radius = fmax(radius, 3.0 * dl_step_norm);
+                                radius = fmin(radius, O.rmax);
+                            }
+                        } else {
+                            radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * row[5] - 1.0, 3.0));
+                            radius = fmin(O.rmax, radius);
+                            decrease_factor = 2.0;
+                        }
                         se_current = cand_cost;
                         se_acc_cand += model;
                         se_acc_ref += model;
@@ -849,6 +1116,8 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
                             se_reference = se_candidate;
                             se_acc_ref = se_acc_cand;
                         }
+                    } else if (DOGLEG) {
+                        radius *= 0.5;  // DoglegStrategy::StepRejected: the Gauss-Newton and gradient vectors stay valid
                     } else {
                         radius = radius / decrease_factor;
                         decrease_factor *= 2.0;
@@ -871,6 +1140,17 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
             pts_cur = pts_cand;
             pts_cand = tp;
         }
+        if (DOGLEG) {
+            if (!valid) {
+                mu *= 10.0;  // DoglegStrategy::StepIsInvalid
+                reuse = false;
+            } else if (s_ctl[CTL_ACCEPT]) {
+                mu = fmax(1e-8, 2.0 * mu / 10.0);
+                reuse = false;
+            } else {
+                reuse = true;
+            }
+        }
         const bool stop_now = s_ctl[CTL_STOP] != 0;
         __syncthreads();
         if (stop_now) break;
@@ -892,7 +1172,7 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
     __syncthreads();
     for (int i = tid; i < 12 * D.n_poses; i += WIN_THREADS) g_poses[i] = s_pose[2][i];
     if (tid == 0) {
-        cslam_summary& s = B.summaries[blockIdx.x];
+        cslam_summary& s = B.summaries[win];
         s.initial_cost = initial_cost;
         s.final_cost = minimum_cost;
         s.num_iterations = iteration;
@@ -903,7 +1183,7 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B) {
         s.final_radius = radius;
         s.total_linear_iterations = total_linear;
         s.device_ms = 0.0;
-        B.log_rows[blockIdx.x] = n_rows;
+        B.log_rows[win] = n_rows;
     }
 }
 
@@ -915,7 +1195,7 @@ void append(std::vector<T>& dst, const T* src, size_t n) {
 }  // namespace
 
 bool Engine::window_eligible() const {
-    if (opt.window_path == 1 || opt.trust_region_strategy != 0) return false;
+    if (opt.window_path == 1 || (opt.trust_region_strategy != 0 && opt.trust_region_strategy != 1)) return false;
     // the one-CTA window kernel has no lighting terms, no box projection and no held positions:
     // such problems take the generic engine (also inside cslam_solve_batch)
     if (lighting_in_solve() || bounded || hold_positions) return false;
@@ -993,6 +1273,12 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         }
     }
     if (take.empty()) return;
+    // Levenberg-Marquardt windows first, DOGLEG windows behind them: one launch per strategy present
+    std::stable_sort(take.begin(), take.end(), [&](int a, int b) {
+        return engines[a]->opt.trust_region_strategy < engines[b]->opt.trust_region_strategy;
+    });
+    int n_lm_windows = 0;
+    for (int i : take) n_lm_windows += engines[i]->opt.trust_region_strategy == 0 ? 1 : 0;
     Engine& first = *engines[take[0]];
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
@@ -1018,7 +1304,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         d.cam = e.cam;
         const cslam_options& o = e.opt;
         d.o = WinOpts{o.max_num_iterations, o.use_nonmonotonic_steps, o.max_consecutive_nonmonotonic_steps,
-                      o.max_num_consecutive_invalid_steps, o.jacobi_scaling, o.initial_trust_region_radius,
+                      o.max_num_consecutive_invalid_steps, o.jacobi_scaling, o.dogleg_type, o.initial_trust_region_radius,
                       o.max_trust_region_radius, o.min_trust_region_radius, o.min_relative_decrease, o.min_lm_diagonal,
                       o.max_lm_diagonal, o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance};
         // which blocks exist and which are free (dataset_vo.cpp:40-62)
@@ -1112,6 +1398,8 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
                  o_logs = place(size_t(log_total) * CSLAM_LOG_COLS * 8), o_rows = place(size_t(nw) * sizeof(int));
     const size_t down_end = cursor;
     const size_t o_cand = place(pts.size() * 8), o_scl = place(pts.size() * 8), o_gl = place(pts.size() * 8);
+    const bool any_dogleg = n_lm_windows < nw;
+    const size_t o_yl = place(any_dogleg ? pts.size() * 8 : 8), o_dl = place(any_dogleg ? pts.size() * 8 : 8);
     const size_t total = cursor;
 
     WindowArena* arena = window_arena_take(first.opt.device, down_end);
@@ -1160,14 +1448,22 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         B.obs_W = reinterpret_cast<double*>(dp + o_oW);
         B.sc_l = reinterpret_cast<double*>(dp + o_scl);
         B.gl = reinterpret_cast<double*>(dp + o_gl);
+        B.yl = reinterpret_cast<double*>(dp + o_yl);
+        B.diag_l = reinterpret_cast<double*>(dp + o_dl);
         B.suns = reinterpret_cast<SunBlockData*>(dp + o_suns);
         B.priors = reinterpret_cast<PriorBlockData*>(dp + o_priors);
         B.summaries = reinterpret_cast<cslam_summary*>(dp + o_sum);
         B.logs = reinterpret_cast<double*>(dp + o_logs);
         B.log_rows = reinterpret_cast<int*>(dp + o_rows);
         CSLAM_CUDA(cudaEventRecord(ev0, stream));
-        window_lm_kernel<<<nw, WIN_THREADS, 0, stream>>>(B);
-        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        if (n_lm_windows > 0) {
+            window_lm_kernel<false><<<n_lm_windows, WIN_THREADS, 0, stream>>>(B, 0);
+            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (any_dogleg) {
+            window_lm_kernel<true><<<nw - n_lm_windows, WIN_THREADS, 0, stream>>>(B, n_lm_windows);
+            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         CSLAM_CUDA(cudaGetLastError());
         CSLAM_CUDA(cudaEventRecord(ev1, stream));
         CSLAM_CUDA(cudaMemcpyAsync(hp + o_poses, dp + o_poses, down_end - o_poses, cudaMemcpyDeviceToHost, stream));

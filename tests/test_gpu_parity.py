@@ -165,6 +165,55 @@ def test_window_batch(product):
         check_lm((pg, sg, poses_g, points_g), (po, so, poses_o, points_o), tol=1e-5 if "initial_trust_region_radius" in extra else LM_TOL)
 
 
+@pytest.mark.parametrize("dogleg_type", [0, 1])
+def test_window_batch_dogleg(product, dogleg_type):
+    """The strategy dataset_vo_sun sets (dataset_vo_sun.cpp:142-143: DOGLEG, SUBSPACE_DOGLEG — the default of the
+    scripts/ba_all_*.sh workload) INSIDE the one-CTA-per-window kernel: the whole batch is one launch, and each window
+    matches the oracle's DoglegStrategy solving it alone.  Radii from 1e-2 to 1e4 so that Cauchy-limited,
+    interpolated / subspace-boundary and pure Gauss-Newton steps all occur, plus a poor start (rejected steps reuse
+    the Gauss-Newton and gradient vectors)."""
+    from ceres_slam_b200.problem import solve_batch
+    cases = _window_cases()
+    tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42))
+    for k1, size, radius in [(12, 2, 1e-1), (25, 3, 1.0), (47, 4, 10.0), (66, 8, 1.0)]:
+        cases.append((syn.window_of(tr, k1, k1 + size), dict(initial_trust_region_radius=radius)))
+    kw = dict(FIXED, max_num_iterations=6, trust_region_strategy=1, dogleg_type=dogleg_type)
+    gpu = [syn.build_problem(w, **dict(kw, **extra)) for w, extra in cases]
+    launches0 = product_launches(product)
+    sums = solve_batch([g[0] for g in gpu])
+    assert product_launches(product) - launches0 == 1, "the whole batch must be one kernel launch"
+    limited = 0
+    for (w, extra), (pg, poses_g, points_g), sg in zip(cases, gpu, sums):
+        po, poses_o, points_o = orc.build_problem(w, **dict(kw, **extra))
+        so = po.solve()
+        check_lm((pg, sg, poses_g, points_g), (po, so, poses_o, points_o), tol=1e-5 if "initial_trust_region_radius" in extra else LM_TOL)
+        lg, lo = pg.iteration_log(), po.iteration_log()
+        assert np.allclose(lg[:, 4], lo[:, 4], rtol=1e-5, atol=1e-12), "step norms"
+        assert np.array_equal(lg[:, 7], lo[:, 7]), "linear solves per iteration (0 when the vectors are reused)"
+        r0 = extra.get("initial_trust_region_radius", 1e4)
+        limited += int(r0 <= 10.0 and (lg[1, 6] != r0 or lg[1, 4] < 0.2 * lg[:, 4].max()))   # the region bound the first step
+    assert limited >= 3, "some windows must take region-limited steps"
+
+
+def test_window_mixed_strategies(product):
+    """LM and DOGLEG windows in one batch: one launch per strategy, each window equal to the same window solved by
+    the host-driven engine (window_path = 1)."""
+    from ceres_slam_b200.problem import solve_batch
+    tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42))
+    wins = [syn.window_of(tr, k1, k1 + size) for k1, size in [(5, 2), (17, 3), (40, 2), (52, 5), (60, 2)]]
+    strat = [0, 1, 1, 0, 1]
+    kw = dict(FIXED, max_num_iterations=5)
+    batch = [syn.build_problem(w, trust_region_strategy=s, initial_trust_region_radius=1.0 if s else 1e4, **kw) for w, s in zip(wins, strat)]
+    launches0 = product_launches(product)
+    sums = solve_batch([b[0] for b in batch])
+    assert product_launches(product) - launches0 == 2
+    for w, s, (pb, poses_b, points_b), sb in zip(wins, strat, batch, sums):
+        ph, poses_h, points_h = syn.build_problem(w, trust_region_strategy=s, initial_trust_region_radius=1.0 if s else 1e4,
+                                                  window_path=1, **kw)
+        sh = ph.solve()
+        check_lm((pb, sb, poses_b, points_b), (ph, sh, poses_h, points_h))
+
+
 def test_window_convergence(product):
     """With Ceres' default tolerances the in-kernel loop must stop where the oracle stops."""
     tr = syn.make_track(100, 15, 10, seed=42)
@@ -791,12 +840,15 @@ def test_dogleg_full_batch(product, dogleg_type, radius):
 
 def test_dogleg_window_with_prior(product):
     """A dataset_vo_sun window as the reference configures it: SUBSPACE_DOGLEG, no constant pose, pose
-    prior, sun blocks with Huber loss.  (DOGLEG problems go through the generic engine.)"""
+    prior, sun blocks with Huber loss — through the one-CTA window kernel (the default for <= 8 poses) and through
+    the host-driven engine."""
     tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42, per_obs_W=True))
     w = syn.window_of(tr, 20, 22)
     prior = (0, w["poses"][0].copy(), np.eye(6) * 1e6)
-    g, o = solve_pair(w, 6, sun=True, prior=prior, huber=1.0, hold_first=False, trust_region_strategy=1, dogleg_type=1)
-    check_lm(g, o)
+    for path in (2, 1):
+        g, o = solve_pair(w, 6, sun=True, prior=prior, huber=1.0, hold_first=False, trust_region_strategy=1, dogleg_type=1,
+                          window_path=path)
+        check_lm(g, o)
 
 
 def test_dogleg_rejected_steps_reuse(product):
