@@ -202,7 +202,7 @@ def workload_config(n_gpus):
             "l2": "inputs (640 MB of observations) larger than the 126 MB L2"}
 
 
-def bench_c4_windows(lib, n_windows=256, iters=6, reps=5, cpu_baseline=True):
+def bench_c4_windows(lib, n_windows=256, iters=6, reps=5, cpu_baseline=True, dogleg=False):
     """BASELINE.json config 4: 256 independent sliding windows (dataset_vo --window 2 shape: 2 poses,
     ~150 landmarks, ~300 observations each) packed into ONE launch; latency-bound, so the figures
     are windows/s and window-LM-iterations/s, not a roofline fraction."""
@@ -215,6 +215,8 @@ def bench_c4_windows(lib, n_windows=256, iters=6, reps=5, cpu_baseline=True):
             if len(wins) < n_windows:
                 wins.append(syn.window_of(tr, k1, k1 + 2))
     kw = dict(max_num_iterations=iters, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    if dogleg:  # the strategy dataset_vo_sun sets (dataset_vo_sun.cpp:142-143): DOGLEG, SUBSPACE_DOGLEG
+        kw.update(trust_region_strategy=1, dogleg_type=1)
     best_wall, dev_ms, n_it, n_obs = None, None, 0, sum(int(w["obs_cam"].size) for w in wins)
     for rep in range(reps + 1):
         probs = [syn.build_problem(w, **kw)[0] for w in wins]
@@ -246,7 +248,8 @@ def bench_c4_windows(lib, n_windows=256, iters=6, reps=5, cpu_baseline=True):
             "kernel_ms": dev_ms, "windows_per_s_kernel": n_windows / (dev_ms * 1e-3),
             "window_lm_iters_per_s_kernel": n_it / (dev_ms * 1e-3),
             "e2e_wall_ms": best_wall * 1e3, "windows_per_s_e2e": n_windows / best_wall,
-            "note": "one CTA per window, LM loop on the device, one launch per batch; e2e = host packing + "
+            "strategy": "SUBSPACE_DOGLEG" if dogleg else "LEVENBERG_MARQUARDT",
+            "note": "one CTA per window, trust-region loop on the device, one launch per batch; e2e = host packing + "
                     "H2D + kernel + D2H through cslam_solve_batch"}
 
 
@@ -416,7 +419,7 @@ def _driver_timing(stderr):
     for line in stderr.splitlines():
         if "cslam_b200 timing:" in line:      # (may follow an unterminated progress message on the same line)
             kv = dict(t.split("=") for t in line.split("cslam_b200 timing:", 1)[1].split())
-            out.append((int(kv["windows"]), float(kv["loop_s"]), kv.get("pass", "vo")))
+            out.append((int(kv["windows"]), float(kv["loop_s"]), kv.get("pass", "vo"), kv))
     return out
 
 
@@ -444,12 +447,13 @@ def bench_c1_c2_drivers(cpu=True):
                 r = subprocess.run([exe, csv, "--window", str(window), "--max-iters", "100"], capture_output=True, text=True, cwd=tmp)
                 if r.returncode != 0:
                     raise RuntimeError(r.stderr[-1000:])
-                nw, sec, _p = _driver_timing(r.stderr)[0]
-                best = sec if best is None else min(best, sec)
+                nw, sec, _p, kv = _driver_timing(r.stderr)[0]
+                if best is None or sec < best:
+                    best, phases = sec, {k: float(kv[k]) * 1e3 for k in ("initial_guess_s", "solve_s", "warmup_s") if k in kv}
             its = [int(l.split("Iterations:")[1].split(",")[0]) for l in r.stdout.splitlines() if "Iterations:" in l]
             key = "window2" if window == 2 else "full_batch"
             res[key] = {"windows": nw, "loop_ms": best * 1e3, "windows_per_s": nw / best, "lm_iterations": int(sum(its)),
-                        "lm_iters_per_s": sum(its) / best}
+                        "lm_iters_per_s": sum(its) / best, "phases_ms": phases}
             if cpu:
                 var = 1.0 / np.diag(np.asarray(tr["W"]).reshape(3, 3)) ** 2
                 its_o = []
@@ -461,7 +465,9 @@ def bench_c1_c2_drivers(cpu=True):
                                             "sample": "the same track and window loop on the oracle (RANSAC + solve per window)"}
         out["c1_dataset_vo"] = dict(res, track="100 poses, ~150 landmarks/frame, 14.6 k stereo observations",
                                     note="dataset_vo_b200: window 2 = 99 sequential windows (1 free pose, ~300 blocks each), "
-                                         "full batch = one RANSAC launch over 99 pairs + one bundle adjustment")
+                                         "full batch = one RANSAC launch over 99 pairs + one bundle adjustment; the driver "
+                                         "runs its first window once, untimed, before the loop (phases_ms.warmup_s: CUDA "
+                                         "context creation + kernel module loading, once per process)")
         # ---- config 2: 1 k poses, sun blocks, prior chain ------------------------------------------
         trs = _cut_states(syn.add_sun(syn.make_track(1018, 15, 10, seed=42, per_obs_W=True, pix_sigma=0.25), sigma_deg=1.0), 9, 1000)
         paths = [os.path.join(tmp, f) for f in ("c2.csv", "c2_ref.csv", "c2_obs.csv")]
@@ -685,6 +691,7 @@ def main():
                   "frac_of_hbm": 272 * n_obs / (rj_ms * 1e-3) / 1e9 / peak}
     p.close()
     c4 = bench_c4_windows(lib, cpu_baseline=not args.no_cpu and world == 1) if (rank == 0 and not args.no_c4) else None
+    c4_dl = bench_c4_windows(lib, cpu_baseline=not args.no_cpu and world == 1, dogleg=True) if (rank == 0 and not args.no_c4) else None
     phong = bench_phong_blocks(peak) if (rank == 0 and not args.no_phong) else None
     c3 = bench_c3_phong_solve(cpu=not args.no_cpu) if (rank == 0 and world == 1 and not args.no_phong) else None
     ransac = bench_ransac_front_end() if (rank == 0 and world == 1 and not args.no_c4) else None
@@ -747,7 +754,7 @@ def main():
             "obs_per_s": value * n_obs, "n_obs": n_obs, "n_landmarks": n_lm, "n_poses": n_cam,
             "e2e": e2e, "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
-            "resjac": resjac, "step_profile_ms": step_profile, "allreduce": allreduce, "c4_windows": c4, "phong_blocks": phong,
+            "resjac": resjac, "step_profile_ms": step_profile, "allreduce": allreduce, "c4_windows": c4, "c4_windows_dogleg": c4_dl, "phong_blocks": phong,
             "c3_phong_solve": c3, "ransac_front_end": ransac, "loop_closure_dense_solve": loop, "c5_ragged": ragged,
             "c1_dataset_vo": (drivers or {}).get("c1_dataset_vo"), "c2_dataset_vo_sun": (drivers or {}).get("c2_dataset_vo_sun"),
             "lm": {"cost_first": float(log[0, 1]), "cost_last": float(log[-1, 1]),

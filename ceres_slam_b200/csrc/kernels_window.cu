@@ -18,6 +18,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.cuh"
@@ -1285,6 +1288,14 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         throw CudaError("no CUDA device: the cslam_b200 back end has no CPU fallback");
     CSLAM_CUDA(cudaSetDevice(first.opt.device));
 
+    // CSLAM_WINDOW_TIMING=1: host phases of this call to stderr (packing / staging / device / unpacking)
+    static const bool timing = [] {
+        const char* e = std::getenv("CSLAM_WINDOW_TIMING");
+        return e && std::atoi(e) != 0;
+    }();
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    auto since = [&](clk::time_point t) { return std::chrono::duration<double, std::micro>(clk::now() - t).count(); };
     const int nw = int(take.size());
     std::vector<WinDesc> desc(nw);
     std::vector<double> poses, pts, ou, ov, od, oW;
@@ -1378,6 +1389,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
     // batch (a window is a few KB: a dozen separate copies and allocations cost more than the kernel).
     // Layout (256-byte aligned pieces):  [inputs ... | poses | best points | summaries | logs | log rows | scratch]
     // The copy up covers inputs + poses, the copy back poses .. log rows.
+    const double us_pack = since(t_begin);
     auto pad1 = [](auto& v) {
         if (v.empty()) v.resize(1);
     };
@@ -1423,6 +1435,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
     put(o_suns, suns.data(), suns.size() * sizeof(SunBlockData));
     put(o_priors, priors.data(), priors.size() * sizeof(PriorBlockData));
     put(o_poses, poses.data(), poses.size() * 8);
+    const double us_stage = since(t_begin);
     {
         DBuf<uint8_t> d_all;
         d_all.alloc(total, stream);
@@ -1468,6 +1481,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         CSLAM_CUDA(cudaEventRecord(ev1, stream));
         CSLAM_CUDA(cudaMemcpyAsync(hp + o_poses, dp + o_poses, down_end - o_poses, cudaMemcpyDeviceToHost, stream));
         CSLAM_CUDA(cudaStreamSynchronize(stream));
+        const double us_device = since(t_begin);
         float ms = 0;
         CSLAM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         const double* poses_out = reinterpret_cast<const double*>(hp + o_poses);
@@ -1496,6 +1510,10 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
             e.prof.launches[CSLAM_K_WINDOW] += wi == 0 ? 1 : 0;
             if (summaries) summaries[take[wi]] = sums[wi];
         }
+        if (timing)
+            std::fprintf(stderr, "[cslam window batch] %d windows: pack %.0f us, stage %.0f us, alloc+H2D+kernel(%.0f us)+D2H %.0f us, "
+                                 "unpack %.0f us\n", nw, us_pack, us_stage - us_pack, ms * 1e3, us_device - us_stage,
+                         since(t_begin) - us_device);
     }
 }
 

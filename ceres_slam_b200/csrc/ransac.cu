@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <random>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -269,6 +271,54 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(RansacArgs A) {
 
 }  // namespace
 
+// Per-call resources, pooled process-wide like the window batch's arena (kernels_window.cu): a stream, a pinned
+// staging block and a device block, all grow-only.  A sliding-window driver calls this once per window with a few
+// KB of points: creating a stream and eight stream-ordered buffers per call cost more than the kernel.
+struct RansacArena {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    char* pinned = nullptr;
+    char* dev = nullptr;
+    size_t cap = 0;
+};
+static std::mutex g_rs_mu;
+static std::vector<RansacArena*> g_rs_free;
+
+static RansacArena* ransac_arena_take(int device, size_t bytes) {
+    RansacArena* a = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_rs_mu);
+        for (size_t i = 0; i < g_rs_free.size(); ++i)
+            if (g_rs_free[i]->device == device) {
+                a = g_rs_free[i];
+                g_rs_free.erase(g_rs_free.begin() + long(i));
+                break;
+            }
+    }
+    if (!a) {
+        a = new RansacArena;
+        a->device = device;
+        CSLAM_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+    }
+    if (a->cap < bytes) {
+        if (a->pinned) cudaFreeHost(a->pinned);
+        if (a->dev) cudaFree(a->dev);
+        a->pinned = a->dev = nullptr;
+        a->cap = 0;
+        const size_t want = std::max(bytes + bytes / 2, size_t(1) << 20);
+        if (cudaMallocHost(reinterpret_cast<void**>(&a->pinned), want) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&a->dev), want) != cudaSuccess) {
+            if (a->pinned) cudaFreeHost(a->pinned);
+            a->pinned = nullptr;
+            std::lock_guard<std::mutex> g(g_rs_mu);
+            g_rs_free.push_back(a);
+            throw CudaError("RANSAC staging allocation failed");
+        }
+        a->cap = want;
+    }
+    return a;
+}
+
 void ransac_align_batch(int device, uint32_t n_pairs, const uint32_t* offsets, const double* pts0, const double* pts1,
                         const double* intr5, uint32_t num_iters, double thresh, int rng_variant, double* T12_out,
                         uint8_t* inlier_out, uint32_t* n_inliers_out) {
@@ -278,7 +328,9 @@ void ransac_align_batch(int device, uint32_t n_pairs, const uint32_t* offsets, c
         throw CudaError("no CUDA device: the cslam_b200 back end has no CPU fallback");
     CSLAM_CUDA(cudaSetDevice(device));
     const uint32_t total = offsets[n_pairs];
-    // one table of index triples per distinct cloud size
+    // one table of index triples per distinct cloud size (they depend on n only: cached across calls)
+    static std::mutex tri_mu;
+    static std::map<std::tuple<uint32_t, uint32_t, int>, std::vector<uint32_t>> tri_cache;
     std::map<uint32_t, uint32_t> table;
     std::vector<uint32_t> table_of(n_pairs), triples;
     uint32_t n_max = 0;
@@ -293,59 +345,79 @@ void ransac_align_batch(int device, uint32_t n_pairs, const uint32_t* offsets, c
         if (it == table.end()) {
             const uint32_t id = uint32_t(triples.size() / (3ull * num_iters));
             triples.resize(triples.size() + 3ull * num_iters);
-            ransac_triples(n, num_iters, rng_variant, triples.data() + 3ull * num_iters * id);
+            {
+                std::lock_guard<std::mutex> g(tri_mu);
+                const auto key = std::make_tuple(n, num_iters, rng_variant);
+                auto itc = tri_cache.find(key);
+                if (itc == tri_cache.end()) {
+                    if (tri_cache.size() > 4096) tri_cache.clear();  // bounded: a long track has a few hundred distinct sizes
+                    itc = tri_cache.emplace(key, std::vector<uint32_t>(3ull * num_iters)).first;
+                    ransac_triples(n, num_iters, rng_variant, itc->second.data());
+                }
+                std::memcpy(triples.data() + 3ull * num_iters * id, itc->second.data(), 12ull * num_iters);
+            }
             it = table.emplace(n, id).first;
         }
         table_of[p] = it->second;
     }
     if (triples.empty()) triples.assign(3ull * std::max<uint32_t>(num_iters, 1), 0);
-    cudaStream_t s = nullptr;
-    CSLAM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    DBuf<uint32_t> d_off, d_tri, d_tab, d_cnt;
-    DBuf<double> d_p0, d_p1, d_T;
-    DBuf<uint8_t> d_in;
-    try {
-        d_off.upload(offsets, size_t(n_pairs) + 1, s);
-        d_tri.upload(triples, s);
-        d_tab.upload(table_of, s);
-        d_p0.upload(pts0, 3ull * std::max<uint32_t>(total, 1), s);
-        d_p1.upload(pts1, 3ull * std::max<uint32_t>(total, 1), s);
-        d_T.alloc(12ull * n_pairs, s);
-        d_in.alloc(std::max<uint32_t>(total, 1), s);
-        d_cnt.alloc(n_pairs, s);
-        RansacArgs A;
-        A.cam = CameraIntrinsics{intr5[0], intr5[1], intr5[2], intr5[3], intr5[4]};
-        A.offsets = d_off.p;
-        A.pts0 = d_p0.p;
-        A.pts1 = d_p1.p;
-        A.triples = d_tri.p;
-        A.table_of = d_tab.p;
-        A.num_iters = num_iters;
-        A.thresh = thresh;
-        const int cap = 4096;  // points staged in shared memory: 48 B each
-        A.smem_points = int(std::min<uint32_t>(n_max, cap));
-        const size_t smem = size_t(A.smem_points) * 6 * sizeof(double);
-        if (smem > 48 * 1024)
-            CSLAM_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        A.T_out = d_T.p;
-        A.inlier_out = d_in.p;
-        A.count_out = d_cnt.p;
-        ransac_kernel<<<n_pairs, RS_THREADS, smem, s>>>(A);
-        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-        CSLAM_CUDA(cudaGetLastError());
-        CSLAM_CUDA(cudaMemcpyAsync(T12_out, d_T.p, 12ull * n_pairs * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (total && inlier_out) CSLAM_CUDA(cudaMemcpyAsync(inlier_out, d_in.p, total, cudaMemcpyDeviceToHost, s));
-        if (n_inliers_out)
-            CSLAM_CUDA(cudaMemcpyAsync(n_inliers_out, d_cnt.p, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CSLAM_CUDA(cudaStreamSynchronize(s));
-    } catch (...) {
-        cudaStreamSynchronize(s);
-        d_off.release(); d_tri.release(); d_tab.release(); d_cnt.release(); d_p0.release(); d_p1.release(); d_T.release(); d_in.release();
-        cudaStreamDestroy(s);
-        throw;
+
+    // layout (256-byte aligned pieces): [offsets | triples | table_of | pts0 | pts1 || T | counts | inliers]
+    size_t cursor = 0;
+    auto place = [&](size_t bytes) {
+        const size_t off = cursor;
+        cursor = (cursor + bytes + 255) & ~size_t(255);
+        return off;
+    };
+    const size_t npts = std::max<uint32_t>(total, 1);
+    const size_t o_off = place((size_t(n_pairs) + 1) * 4), o_tri = place(triples.size() * 4), o_tab = place(size_t(n_pairs) * 4),
+                 o_p0 = place(npts * 24), o_p1 = place(npts * 24);
+    const size_t up_bytes = cursor;
+    const size_t o_T = place(size_t(n_pairs) * 96), o_cnt = place(size_t(n_pairs) * 4), o_in = place(npts);
+    const size_t all_bytes = cursor;
+    RansacArena* arena = ransac_arena_take(device, all_bytes);
+    struct Give {
+        RansacArena* a;
+        ~Give() {
+            std::lock_guard<std::mutex> g(g_rs_mu);
+            g_rs_free.push_back(a);
+        }
+    } give{arena};
+    cudaStream_t s = arena->stream;
+    char *hp = arena->pinned, *dp = arena->dev;
+    std::memcpy(hp + o_off, offsets, (size_t(n_pairs) + 1) * 4);
+    std::memcpy(hp + o_tri, triples.data(), triples.size() * 4);
+    std::memcpy(hp + o_tab, table_of.data(), size_t(n_pairs) * 4);
+    if (total) {
+        std::memcpy(hp + o_p0, pts0, size_t(total) * 24);
+        std::memcpy(hp + o_p1, pts1, size_t(total) * 24);
     }
-    d_off.release(); d_tri.release(); d_tab.release(); d_cnt.release(); d_p0.release(); d_p1.release(); d_T.release(); d_in.release();
-    cudaStreamDestroy(s);
+    CSLAM_CUDA(cudaMemcpyAsync(dp, hp, up_bytes, cudaMemcpyHostToDevice, s));
+    RansacArgs A;
+    A.cam = CameraIntrinsics{intr5[0], intr5[1], intr5[2], intr5[3], intr5[4]};
+    A.offsets = reinterpret_cast<const uint32_t*>(dp + o_off);
+    A.pts0 = reinterpret_cast<const double*>(dp + o_p0);
+    A.pts1 = reinterpret_cast<const double*>(dp + o_p1);
+    A.triples = reinterpret_cast<const uint32_t*>(dp + o_tri);
+    A.table_of = reinterpret_cast<const uint32_t*>(dp + o_tab);
+    A.num_iters = num_iters;
+    A.thresh = thresh;
+    const int cap = 4096;  // points staged in shared memory: 48 B each
+    A.smem_points = int(std::min<uint32_t>(n_max, cap));
+    const size_t smem = size_t(A.smem_points) * 6 * sizeof(double);
+    if (smem > 48 * 1024)
+        CSLAM_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    A.T_out = reinterpret_cast<double*>(dp + o_T);
+    A.inlier_out = reinterpret_cast<uint8_t*>(dp + o_in);
+    A.count_out = reinterpret_cast<uint32_t*>(dp + o_cnt);
+    ransac_kernel<<<n_pairs, RS_THREADS, smem, s>>>(A);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    CSLAM_CUDA(cudaGetLastError());
+    CSLAM_CUDA(cudaMemcpyAsync(hp + o_T, dp + o_T, all_bytes - o_T, cudaMemcpyDeviceToHost, s));
+    CSLAM_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(T12_out, hp + o_T, size_t(n_pairs) * 96);
+    if (total && inlier_out) std::memcpy(inlier_out, hp + o_in, total);
+    if (n_inliers_out) std::memcpy(n_inliers_out, hp + o_cnt, size_t(n_pairs) * 4);
 }
 
 }  // namespace cslam

@@ -126,22 +126,43 @@ int main(int argc, char** argv) {
     Track t;
     if (!read_csv(filename, t)) return EXIT_FAILURE;
     if (window == 0 || window > t.num_states) window = t.num_states;  // 0 = full batch (dataset_vo.cpp:118-121)
+    // Warm-up, untimed and on a copy: the first window once, so that CUDA context creation and kernel module loading
+    // (0.3 - 2 s, once per process) are not billed to the window loop below
+    const auto t_warm = std::chrono::steady_clock::now();
+    if (t.num_states >= window) {
+        Track w = t;
+        if (ransac)
+            compute_initial_guess(w.obs, w.intr, w.num_states, 0, window, 4.0, false, w.poses, w.points, w.initialized,
+                                  [](unsigned, unsigned, const double*, unsigned) {});
+        else
+            constant_pose_guess(w, 0, window);
+        std::cout.setstate(std::ios_base::failbit);
+        solveWindow(w, 0, window, max_iters);
+        std::cout.clear();
+    }
+    const double warm_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_warm).count();
     std::cerr << "Computing VO" << std::endl;
     const auto t_loop = std::chrono::steady_clock::now();
     unsigned n_windows = 0;
+    double guess_s = 0.0, solve_s = 0.0;
     for (unsigned k1 = 0; k1 + window <= t.num_states; ++k1, ++n_windows) {
         const unsigned k2 = k1 + window;
+        const auto t_w0 = std::chrono::steady_clock::now();
         if (ransac)
             compute_initial_guess(t.obs, t.intr, t.num_states, k1, k2, 4.0, false, t.poses, t.points, t.initialized,
                                   [](unsigned, unsigned, const double*, unsigned) {});    // :127
         else
             constant_pose_guess(t, k1, k2);
+        const auto t_w1 = std::chrono::steady_clock::now();
         solveWindow(t, k1, k2, max_iters);                                                  // :128
+        guess_s += std::chrono::duration<double>(t_w1 - t_w0).count();
+        solve_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_w1).count();
         std::fill(t.initialized.begin(), t.initialized.end(), 0);                           // reset_points, :130
     }
     // front end + solve of every window, without the CSV input / output (bench.py's C1 line reads this)
     std::cerr << "cslam_b200 timing: windows=" << n_windows << " loop_s="
-              << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count() << std::endl;
+              << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count()
+              << " initial_guess_s=" << guess_s << " solve_s=" << solve_s << " warmup_s=" << warm_s << std::endl;
     write_poses_csv(file_stem(filename) + "_poses.csv", t.poses, t.num_states);
     return EXIT_SUCCESS;
 }

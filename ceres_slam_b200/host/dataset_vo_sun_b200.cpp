@@ -66,6 +66,21 @@ int main(int argc, char** argv) {
     SunDataset d;
     if (!read_csv(track, ref_sun, obs_sun, d)) return EXIT_FAILURE;
     if (window == 0 || window > d.num_states) window = d.num_states;
+    {
+        // Warm-up, untimed and on a copy: the first window once (CUDA context creation and kernel module loading happen
+        // once per process and are not part of the window loop the timing line reports)
+        const auto t_warm = std::chrono::steady_clock::now();
+        SunDataset w = d;
+        const InitialGuessStats st = compute_initial_guess(w.obs, w.intr, w.num_states, 0, window, 4.0, true, w.poses, w.points,
+                                                           w.initialized, [](unsigned, unsigned, const double*, unsigned) {});
+        if (st.ok) {
+            std::cout.setstate(std::ios_base::failbit);
+            solveWindow(w, 0, window, true, huber, az, zen, max_iters);
+            std::cout.clear();
+        }
+        std::cerr << "cslam_b200 warmup_s=" << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_warm).count()
+                  << std::endl;
+    }
     if (!sun_only) {
         std::cerr << "Computing VO without sun measurements" << std::endl;        // :271-296
         run_pass(d, window, false, 0., 1000., 1000., max_iters);
