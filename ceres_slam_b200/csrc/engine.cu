@@ -1727,10 +1727,8 @@ void Engine::check_phong_solve() {
     // the dense border system [n_g][n_g + 1] is factored inside one CTA's shared memory (227 KB)
     if (ph.n_g > 160) not_impl("lighting solve: at most 160 shared columns (3 per material + 1 per texture + 3)");
     ph.max_track = 0;
-    for (int j = 0; j < n_lm; ++j) {
-        if (lm_cnt_h[j] > 32) not_impl("lighting solve: at most 32 observations per vertex");
-        ph.max_track = std::max(ph.max_track, int(lm_cnt_h[j]));
-    }
+    // (vertices observed more than 32 times take the chunked kernels of kernels_phong_long.cu)
+    for (int j = 0; j < n_lm; ++j) ph.max_track = std::max(ph.max_track, int(lm_cnt_h[j]));
 }
 
 void Engine::setup_phong_solve() {
@@ -2847,6 +2845,13 @@ double Engine::time_phong(int reps) {
 void Engine::covariance_block(uint32_t cam, double* cov36) {
     if (cam >= n_poses) throw std::invalid_argument("covariance: pose index out of range");
     if (n_ranks > 1) throw std::invalid_argument("covariance: single-GPU problems only");
+    if (window_eligible(true)) {
+        // a sliding window (<= 8 poses): one launch of the one-CTA covariance kernel instead of upload + structure
+        // analysis + six host-driven solves (dataset_vo_sun asks for this block after every window)
+        Engine* self = this;
+        solve_window_batch(&self, 1, nullptr, int(cam), cov36);
+        return;
+    }
     // the reduced system at the caller's current values, undamped, exact solve
     const cslam_options keep = opt;
     opt.linear_solver = 0;
@@ -2861,6 +2866,7 @@ void Engine::covariance_block(uint32_t cam, double* cov36) {
     const int f = cam_free_h[cam];
     if (f < 0) throw std::invalid_argument("covariance: the pose block is constant");
     lm.radius = std::numeric_limits<double>::infinity();  // D = 0
+    dl.mu = 0.0;                                          // (a DOGLEG problem damps with mu, not 1 / radius)
     schur_pass();
     double sc1[SC_COUNT];
     read_scalars(d_scal, sc1, SC_COUNT);

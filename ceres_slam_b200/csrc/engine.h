@@ -261,7 +261,7 @@ class Engine {
     bool lighting_in_solve() const { return n_ph > 0; }
 
     // small-problem description used by the batched window kernel
-    bool window_eligible() const;
+    bool window_eligible(bool any_strategy = false) const;
     void set_window_summary(const cslam_summary& s);
 
    private:
@@ -454,6 +454,8 @@ class Engine {
 };
 
 // window batch (kernels_window.cu)
-void solve_window_batch(Engine** engines, int n, cslam_summary* summaries);
+// cov_cam >= 0 (n == 1): instead of solving, the marginal covariance block of that pose at the caller's current values
+// (cslam_covariance_block for a window-eligible problem: one launch of window_cov_kernel), 36 doubles to cov_out
+void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int cov_cam = -1, double* cov_out = nullptr);
 
 }  // namespace cslam

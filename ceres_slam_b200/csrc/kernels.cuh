@@ -108,6 +108,18 @@ void launch_phong_eval(cudaStream_t s, const PhongView& v, double* r_int, double
 // K2p for grouped vertices (kernels_phong_grouped.cu): items [0, n_items_small) have L <= 10, the rest L <= 16
 void launch_phong_build_grouped(cudaStream_t s, const DevView& v, const PhongSolveView& q, const GroupView& g, int n_items_small,
                                 LmDiag dg, const PhongSystem& o);
+// vertices observed more than 32 times (kernels_phong_long.cu): called by the launchers below when max_track_len > 32
+void launch_phong_build_long(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                             const PhongSystem& o, bool schur);
+void launch_phong_backsub_long(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                               const double* yp, const double* yg, const double* gv, double* yv, double* scal2);
+void launch_phong_dogleg_products_long(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
+                                       const double* gp, const double* diag_p, const double* yp, const double* gg,
+                                       const double* diag_g, const double* yg, const double* gv, const double* yv, double* diag_v,
+                                       double* sc_v, double* sums);
+void launch_phong_candidate_long(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, double alpha,
+                                 const double* yv, const double* poses_cand, const double* gx_cand, double* points_cand,
+                                 double* normals_cand, double* scal2);
 void launch_phong_build(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
                         const PhongSystem& o, bool schur, int max_track_len);
 void launch_phong_gfinalize(cudaStream_t s, const PhongSolveView& q, LmDiag dg, double* Sgg, double* bg, const double* hg,

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         const int j = vok ? jb + sub : lm_hi - 1;  // an idle half re-reads the last vertex and writes nothing
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
         const int L = vok ? int(v.lm_cnt[j]) : 0;
+        if (LW == 32 && L > 32) continue;  // (warp-uniform) a long vertex: kernels_phong_long.cu
         VertexCtx c;
         load_vertex(v, q, j, c);
         PhObs ob;
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         const int j = vok ? jb + sub : lm_hi - 1;
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
         const int L = vok ? int(v.lm_cnt[j]) : 0;
+        if (LW == 32 && L > 32) continue;  // (warp-uniform) a long vertex: kernels_phong_long.cu
         VertexCtx c;
         load_vertex(v, q, j, c);
         PhObs ob;
@@ -429,6 +431,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         const int j = vok ? jb + sub : lm_hi - 1;
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
         const int L = vok ? int(v.lm_cnt[j]) : 0;
+        if (LW == 32 && L > 32) continue;  // (warp-uniform) a long vertex: kernels_phong_long.cu
         VertexCtx c;
         load_vertex(v, q, j, c);
         PhObs ob;
@@ -550,6 +553,7 @@ __global__ void __launch_bounds__(PB_WARPS * 32)
         const int j = vok ? jb + sub : lm_hi - 1;
         const long long e0 = v.lm_base[j], es = v.lm_stride[j];
         const int L = vok ? int(v.lm_cnt[j]) : 0;
+        if (LW == 32 && L > 32) continue;  // (warp-uniform) a long vertex: kernels_phong_long.cu
         VertexCtx c;
         load_vertex(v, q, j, c);
         double pn[3], dn[3], nn[3];
@@ -831,6 +835,7 @@ void launch_phong_build(cudaStream_t s, const DevView& v, const PhongSolveView& 
     }
     count_launch();
     CSLAM_CUDA(cudaGetLastError());
+    if (max_track_len > 32) launch_phong_build_long(s, v, q, lm_lo, lm_hi, dg, o, schur);
 }
 
 void launch_phong_gfinalize(cudaStream_t s, const PhongSolveView& q, LmDiag dg, double* Sgg, double* bg, const double* hg,
@@ -873,6 +878,7 @@ void launch_phong_backsub(cudaStream_t s, const DevView& v, const PhongSolveView
         phong_backsub_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
     count_launch();
     CSLAM_CUDA(cudaGetLastError());
+    if (max_track_len > 32) launch_phong_backsub_long(s, v, q, lm_lo, lm_hi, dg, yp, yg, gv, yv, scal2);
 }
 
 void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongSolveView& q, int lm_lo, int lm_hi, LmDiag dg,
@@ -887,6 +893,8 @@ void launch_phong_dogleg_products(cudaStream_t s, const DevView& v, const PhongS
             phong_dogleg_products_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(
                 v, q, lm_lo, lm_hi, dg, gp, diag_p, yp, gg, diag_g, yg, gv, yv, diag_v, sc_v, sums);
         count_launch();
+        if (max_track_len > 32)
+            launch_phong_dogleg_products_long(s, v, q, lm_lo, lm_hi, dg, gp, diag_p, yp, gg, diag_g, yg, gv, yv, diag_v, sc_v, sums);
     }
     if (count_shared) {
         phong_dogleg_global_kernel<<<1, 128, 0, s>>>(q.n_g, q.g_used, gg, diag_g, yg, sums);
@@ -911,6 +919,8 @@ void launch_phong_candidate(cudaStream_t s, const DevView& v, const PhongSolveVi
             phong_candidate_kernel<32><<<vertex_grid(lm_hi - lm_lo), PB_WARPS * 32, 0, s>>>(
                 v, q, lm_lo, lm_hi, alpha, yv, poses_cand, gx_cand, points_cand, normals_cand, scal2);
         count_launch();
+        if (max_track_len > 32)
+            launch_phong_candidate_long(s, v, q, lm_lo, lm_hi, alpha, yv, poses_cand, gx_cand, points_cand, normals_cand, scal2);
     }
     CSLAM_CUDA(cudaGetLastError());
 }

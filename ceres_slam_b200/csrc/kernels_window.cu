@@ -380,11 +380,12 @@ __device__ void window_schur_pass(const Win& w, const double* poses, const doubl
 
 // In-place Cholesky of the dense SPD matrix S (lower triangle used) and solve S y = b.
 // Returns false (to every thread) when a pivot is not positive.
-__device__ bool window_cholesky_solve(double* S, int n, const double* b, double* y, int* s_flag) {
+// factor == false: S already holds the factor of an earlier call (further right-hand sides).
+__device__ bool window_cholesky_solve(double* S, int n, const double* b, double* y, int* s_flag, bool factor = true) {
     const int tid = threadIdx.x;
     if (tid == 0) *s_flag = 1;
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
+    for (int j = 0; j < n && factor; ++j) {
         if (tid == 0) {
             const double d = S[j * n + j];
             if (!(d > 0.0) || !(d < 1.7976931348623157e308))
@@ -1190,6 +1191,90 @@ __global__ void __launch_bounds__(WIN_THREADS) window_lm_kernel(WinBufs B, int w
     }
 }
 
+// cslam_covariance_block for a window: the block of pose `cam` of the inverse of the UNDAMPED reduced camera system
+// at the given values (what ceres::Covariance returns for a pose block after marginalising the landmarks;
+// dataset_vo_sun.cpp:159-183 feeds it to the next window's prior).  Same passes as the LM kernel — column norms for
+// the Jacobi scaling, Schur build with D = 0, in-CTA Cholesky — then six solves against the unit vectors of the block;
+// un-scaled on the way out: cov = diag(s) cov_s diag(s).  status: 0 ok, 1 a landmark block is rank deficient, 2 the
+// reduced system is not positive definite.
+__global__ void __launch_bounds__(WIN_THREADS) window_cov_kernel(WinBufs B, int cam, double* out) {
+    __shared__ double sS[WIN_NMAX * WIN_NMAX];
+    __shared__ double s_cam[WIN_PMAX * WIN_CAMV];
+    __shared__ double s_bp[WIN_NMAX], s_y[WIN_NMAX], s_scp[WIN_NMAX];
+    __shared__ double s_pose[WIN_PMAX * 12];
+    __shared__ int s_free[WIN_PMAX];
+    __shared__ double s_red[WIN_THREADS / 32];
+    __shared__ int s_flag;
+    __shared__ WinDesc D;
+    const int tid = threadIdx.x;
+    if (tid == 0) D = B.desc[0];
+    __syncthreads();
+    const WinOpts& O = D.o;
+    const int n = 6 * D.n_free;
+    Win w;
+    w.cam = D.cam;
+    w.n_poses = D.n_poses;
+    w.n_free = D.n_free;
+    w.n_lm = D.n_lm;
+    w.n_sun = D.n_sun;
+    w.n_prior = D.n_prior;
+    w.W_per_obs = D.W_per_obs;
+    w.free_idx = s_free;
+    w.scp = s_scp;
+    w.lm_ptr = B.lm_ptr + D.lmptr_off;
+    w.obs_cam = B.obs_cam + D.obs_off;
+    w.obs_u = B.obs_u + D.obs_off;
+    w.obs_v = B.obs_v + D.obs_off;
+    w.obs_d = B.obs_d + D.obs_off;
+    w.obs_W = B.obs_W + D.W_off;
+    w.sc_l = B.sc_l + 3 * D.lm_off;
+    w.gl = B.gl + 3 * D.lm_off;
+    w.suns = B.suns + D.sun_off;
+    w.priors = B.priors + D.prior_off;
+    const double* pts = B.pts + 3 * D.lm_off;
+    double* cn = B.pts_cand + 3 * D.lm_off;
+    for (int i = tid; i < 12 * D.n_poses; i += WIN_THREADS) s_pose[i] = B.poses[12 * D.pose_off + i];
+    for (int i = tid; i < D.n_poses; i += WIN_THREADS) s_free[i] = B.cam_free[D.pose_off + i];
+    for (int i = tid; i < WIN_NMAX; i += WIN_THREADS) s_scp[i] = 1.0;
+    for (int i = tid; i < 3 * D.n_lm; i += WIN_THREADS) w.sc_l[i] = 1.0;
+    __syncthreads();
+    double cost, n_invalid;
+    window_schur_pass<true>(w, s_pose, pts, LmDiag{0, 0, 0}, sS, n, s_cam, cn, s_red, &cost, &n_invalid);
+    if (O.jacobi) {
+        for (int i = tid; i < n; i += WIN_THREADS) {
+            const int f = i / 6, a = i % 6;
+            int t = 0;
+            for (int q = 0; q < a; ++q) t += 6 - q;
+            s_scp[i] = 1.0 / (1.0 + sqrt(s_cam[f * WIN_CAMV + t]));
+        }
+        for (int i = tid; i < 3 * D.n_lm; i += WIN_THREADS) w.sc_l[i] = 1.0 / (1.0 + sqrt(cn[i]));
+    }
+    __syncthreads();
+    const LmDiag dg{0.0, O.dmin, O.dmax};  // radius = infinity: D = 0
+    window_schur_pass<false>(w, s_pose, pts, dg, sS, n, s_cam, nullptr, s_red, &cost, &n_invalid);
+    for (int i = tid; i < D.n_free * 36; i += WIN_THREADS) {
+        const int f = i / 36, a = (i % 36) / 6, b = i % 6;
+        const int lo = min(a, b), hi = max(a, b);
+        int t = 0;
+        for (int q = 0; q < lo; ++q) t += 6 - q;
+        sS[(6 * f + a) * n + 6 * f + b] += s_cam[f * WIN_CAMV + t + (hi - lo)];
+    }
+    __syncthreads();
+    int status = n_invalid != 0.0 ? 1 : 0;
+    const int f = s_free[cam];
+    for (int c = 0; c < 6 && status == 0; ++c) {
+        for (int i = tid; i < n; i += WIN_THREADS) s_bp[i] = i == 6 * f + c ? 1.0 : 0.0;
+        __syncthreads();
+        if (!window_cholesky_solve(sS, n, s_bp, s_y, &s_flag, c == 0)) {
+            status = 2;
+            break;
+        }
+        if (tid < 6) out[6 * tid + c] = s_scp[6 * f + tid] * s_y[6 * f + tid] * s_scp[6 * f + c];
+        __syncthreads();
+    }
+    if (tid == 0) out[36] = double(status);
+}
+
 template <class T>
 void append(std::vector<T>& dst, const T* src, size_t n) {
     dst.insert(dst.end(), src, src + n);
@@ -1197,8 +1282,9 @@ void append(std::vector<T>& dst, const T* src, size_t n) {
 
 }  // namespace
 
-bool Engine::window_eligible() const {
-    if (opt.window_path == 1 || (opt.trust_region_strategy != 0 && opt.trust_region_strategy != 1)) return false;
+bool Engine::window_eligible(bool any_strategy) const {
+    if (opt.window_path == 1) return false;
+    if (!any_strategy && opt.trust_region_strategy != 0 && opt.trust_region_strategy != 1) return false;
     // the one-CTA window kernel has no lighting terms, no box projection and no held positions:
     // such problems take the generic engine (also inside cslam_solve_batch)
     if (lighting_in_solve() || bounded || hold_positions) return false;
@@ -1260,12 +1346,15 @@ static void window_arena_give(WindowArena* a) {
     g_arena_free.push_back(a);
 }
 
-void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
+void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int cov_cam, double* cov_out) {
     // windows the kernel does not take go through the generic engine
     std::vector<int> take;
+    const bool cov_mode = cov_cam >= 0;
+    if (cov_mode && (n != 1 || !cov_out || !engines[0]->window_eligible(true)))
+        throw std::invalid_argument("window covariance: one window-eligible problem expected");
     for (int i = 0; i < n; ++i) {
         Engine& e = *engines[i];
-        if (e.window_eligible()) {
+        if (cov_mode || e.window_eligible()) {
             take.push_back(i);
         } else {
             if (e.opt.window_path == 2) throw std::invalid_argument("window_path = 2 but the problem is not window-eligible");
@@ -1408,6 +1497,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
     const size_t up_bytes = cursor;
     const size_t o_best = place(pts.size() * 8), o_sum = place(size_t(nw) * sizeof(cslam_summary)),
                  o_logs = place(size_t(log_total) * CSLAM_LOG_COLS * 8), o_rows = place(size_t(nw) * sizeof(int));
+    const size_t o_cov = place(37 * sizeof(double));  // covariance mode: the block and a status word
     const size_t down_end = cursor;
     const size_t o_cand = place(pts.size() * 8), o_scl = place(pts.size() * 8), o_gl = place(pts.size() * 8);
     const bool any_dogleg = n_lm_windows < nw;
@@ -1468,6 +1558,21 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries) {
         B.summaries = reinterpret_cast<cslam_summary*>(dp + o_sum);
         B.logs = reinterpret_cast<double*>(dp + o_logs);
         B.log_rows = reinterpret_cast<int*>(dp + o_rows);
+        if (cov_mode) {
+            const Engine& e = *engines[take[0]];
+            if (uint32_t(cov_cam) >= e.n_poses) throw std::invalid_argument("covariance: pose index out of range");
+            if (cam_free[size_t(cov_cam)] < 0) throw std::invalid_argument("covariance: the pose block is constant");
+            window_cov_kernel<<<1, WIN_THREADS, 0, stream>>>(B, cov_cam, reinterpret_cast<double*>(dp + o_cov));
+            g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+            CSLAM_CUDA(cudaGetLastError());
+            CSLAM_CUDA(cudaMemcpyAsync(hp + o_cov, dp + o_cov, 37 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CSLAM_CUDA(cudaStreamSynchronize(stream));
+            const double* r = reinterpret_cast<const double*>(hp + o_cov);
+            if (r[36] == 1.0) throw std::domain_error("covariance: a landmark block is rank deficient");
+            if (r[36] != 0.0) throw std::domain_error("covariance: the reduced camera system is not positive definite");
+            std::memcpy(cov_out, r, 36 * sizeof(double));
+            return;
+        }
         CSLAM_CUDA(cudaEventRecord(ev0, stream));
         if (n_lm_windows > 0) {
             window_lm_kernel<false><<<n_lm_windows, WIN_THREADS, 0, stream>>>(B, 0);

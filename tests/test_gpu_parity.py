@@ -521,20 +521,37 @@ def _oracle_covariance(track, poses, points, cam, constant, **kw):
     return np.array([[X[pos[col_of[cam] + r], c] for c in range(6)] for r in range(6)])
 
 
-def test_covariance_block_window(product):
+@pytest.mark.parametrize("window_path", [0, 1])
+@pytest.mark.parametrize("strategy", [0, 1])
+def test_covariance_block_window(product, window_path, strategy):
     """the marginal covariance of the second pose of a dataset_vo_sun window
-    (sun blocks with Huber loss + pose prior), at the solution."""
+    (sun blocks with Huber loss + pose prior), at the solution — through the one-CTA covariance kernel
+    (window_path 0: one launch) and through the generic engine (window_path 1), after an LM and a DOGLEG solve."""
     tr = syn.add_sun(syn.make_track(100, 15, 10, seed=42, per_obs_W=True))
     w = syn.window_of(tr, 20, 22)
     prior = (0, w["poses"][0].copy(), np.eye(6) * 1e3)
     kw = dict(sun=True, prior=prior, huber=1.0)
-    pg, poses_g, points_g = syn.build_problem(w, hold_first=False, **kw)
+    pg, poses_g, points_g = syn.build_problem(w, hold_first=False, window_path=window_path, trust_region_strategy=strategy, **kw)
     pg.solve()
+    launches0 = product_launches(product)
     cov = pg.covariance_block(1)
+    if window_path == 0:
+        assert product_launches(product) - launches0 == 1, "one launch of the window covariance kernel"
     ref = _oracle_covariance(w, poses_g.copy(), points_g.copy(), 1, np.zeros(2, dtype=np.uint8), **kw)
     assert np.allclose(cov, cov.T, rtol=1e-9, atol=1e-18)
     assert rel_err(cov, ref) < 1e-7
     assert np.all(np.linalg.eigvalsh(cov) > 0)
+    # a longer window, a middle pose, first pose constant (no prior): 4 free poses, dense 24 x 24 reduced system
+    w5 = syn.window_of(tr, 40, 45)
+    p5, poses5, points5 = syn.build_problem(w5, window_path=window_path, trust_region_strategy=strategy, max_num_iterations=10)
+    p5.solve()
+    const5 = np.zeros(5, dtype=np.uint8)
+    const5[0] = 1
+    for cam in (2, 4):
+        assert rel_err(p5.covariance_block(cam), _oracle_covariance(w5, poses5.copy(), points5.copy(), cam, const5)) < 1e-7, cam
+    from ceres_slam_b200.problem import CslamError
+    with pytest.raises(CslamError):
+        p5.covariance_block(0)  # constant pose
 
 
 def test_covariance_block_full_batch(product):
@@ -638,6 +655,31 @@ def test_lm_phong_many_materials(product):
     assert lg.shape == lo.shape
     assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory"
     assert np.array_equal(lg[:, 9], lo[:, 9])
+    for k in ("poses", "points", "normals", "phong", "textures", "light"):
+        assert rel_err(stg[k], sto[k]) < LM_TOL, k
+
+
+@pytest.mark.parametrize("strategy,bounds", [(0, False), (0, True), (1, True)])
+def test_phong_long_tracks(product, strategy, bounds):
+    """Vertices observed more than 32 times (dataset_ba_phong.cpp:110-140 has no bound on a track): the chunked
+    warp-per-vertex kernels (kernels_phong_long.cu) next to the lane-per-observation ones, LM and SUBSPACE_DOGLEG,
+    against the oracle.  (400 poses on the loop: under 1 degree per frame, a landmark stays in view for up to 70.)"""
+    tr = syn.add_phong(syn.make_track(400, 2, 12, seed=9, ragged=dict(mean=30, max=70, drop=0.05)), shared_textures=True)
+    cnt = np.bincount(tr["obs_pt"], minlength=tr["n_points"])
+    assert (cnt > 32).sum() >= 30 and (cnt > 64).sum() >= 3 and ((cnt > 0) & (cnt <= 32)).sum() >= 30, np.sort(cnt)[-10:]
+    # (DOGLEG from radius 3: region-limited steps, which is what exercises the strategy's inner products.  With the
+    # default radius the first step is the pure Gauss-Newton point of a system damped by mu = 1e-8 only, whose ~1e-5
+    # conditioning noise — dense Cholesky here, band LDL^T in the oracle — is all such a comparison would see;
+    # scripts/debug_long.py prints both.)
+    (pg, sg, stg), (po, so, sto) = _phong_pair(tr, 5, bounds, trust_region_strategy=strategy, dogleg_type=1,
+                                               initial_trust_region_radius=3.0 if strategy else 1e4)
+    lg, lo = pg.iteration_log(), po.iteration_log()
+    assert lg.shape == lo.shape and sg.num_iterations == so.num_iterations
+    assert np.allclose(lg[:, 1], lo[:, 1], rtol=LM_TOL, atol=0), "cost trajectory"
+    assert np.array_equal(lg[:, 9], lo[:, 9]), "accept/reject pattern"
+    assert np.allclose(lg[:, 6], lo[:, 6], rtol=1e-5, atol=0), "radius trajectory"
+    assert abs(sg.final_cost - so.final_cost) <= LM_TOL * so.final_cost
+    assert sg.final_cost < (0.9 if strategy else 0.5) * sg.initial_cost
     for k in ("poses", "points", "normals", "phong", "textures", "light"):
         assert rel_err(stg[k], sto[k]) < LM_TOL, k
 
