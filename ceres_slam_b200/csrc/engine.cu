@@ -1724,8 +1724,9 @@ void Engine::check_phong_solve() {
     ph.n_mat = int(n_materials);
     ph.n_tex = int(n_tex_shared);
     ph.n_g = 3 * ph.n_mat + ph.n_tex + 3;
-    // the dense border system [n_g][n_g + 1] is factored inside one CTA's shared memory (227 KB)
-    if (ph.n_g > 160) not_impl("lighting solve: at most 160 shared columns (3 per material + 1 per texture + 3)");
+    // the dense border system [n_g][n_g + 1] is factored inside one CTA's shared memory up to 160 columns and in
+    // global memory beyond; the shared blocks' own kernels are one CTA with a thread per column
+    if (ph.n_g > 1024) not_impl("lighting solve: at most 1024 shared columns (3 per material + 1 per texture + 3)");
     ph.max_track = 0;
     // (vertices observed more than 32 times take the chunked kernels of kernels_phong_long.cu)
     for (int j = 0; j < n_lm; ++j) ph.max_track = std::max(ph.max_track, int(lm_cnt_h[j]));

@@ -756,12 +756,16 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Dense Cholesky solve of the n_g x n_g border system (one block); yg out, fail flag.
-__global__ void __launch_bounds__(128) phong_border_solve_kernel(int n_g, double* __restrict__ T, double* __restrict__ yg,
-                                                                 double* __restrict__ ps) {
-    extern __shared__ double sT[];  // [n_g][n_g + 1]
+// Dense Cholesky solve of the n_g x n_g border system (one block); yg out, fail flag.  The system lives in the
+// CTA's shared memory when it fits (n_g <= 160); a larger border (hundreds of materials / textures) is factored in
+// place in global memory — L2-resident, one CTA of 1024 threads — which is slower per column but has no size limit.
+__global__ void __launch_bounds__(1024) phong_border_solve_kernel(int n_g, double* __restrict__ T, double* __restrict__ yg,
+                                                                  double* __restrict__ ps, int in_shared) {
+    extern __shared__ double sT_sh[];  // [n_g][n_g + 1]
     const int ld = n_g + 1;
-    for (int i = threadIdx.x; i < n_g * ld; i += blockDim.x) sT[i] = T[i];
+    double* sT = in_shared ? sT_sh : T;
+    if (in_shared)
+        for (int i = threadIdx.x; i < n_g * ld; i += blockDim.x) sT[i] = T[i];
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
@@ -782,21 +786,23 @@ __global__ void __launch_bounds__(128) phong_border_solve_kernel(int n_g, double
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        // forward / backward substitution on the rhs column (index n_g)
-        for (int i = 0; i < n_g; ++i) {
-            double s = sT[i * ld + n_g];
-            for (int k = 0; k < i; ++k) s -= sT[i * ld + k] * sT[k * ld + n_g];
-            sT[i * ld + n_g] = s / sT[i * ld + i];
-        }
-        for (int i = n_g - 1; i >= 0; --i) {
-            double s = sT[i * ld + n_g];
-            for (int k = i + 1; k < n_g; ++k) s -= sT[k * ld + i] * sT[k * ld + n_g];
-            sT[i * ld + n_g] = s / sT[i * ld + i];
-        }
-        for (int i = 0; i < n_g; ++i) yg[i] = sT[i * ld + n_g];
-        if (!ok) ps[PS_FAIL] = 2.0;
+    // forward / backward substitution on the rhs column (index n_g), column oriented: one pivot, then every row
+    for (int j = 0; j < n_g; ++j) {
+        if (threadIdx.x == 0) sT[j * ld + n_g] /= sT[j * ld + j];
+        __syncthreads();
+        const double yj = sT[j * ld + n_g];
+        for (int i = j + 1 + threadIdx.x; i < n_g; i += blockDim.x) sT[i * ld + n_g] -= sT[i * ld + j] * yj;
+        __syncthreads();
     }
+    for (int j = n_g - 1; j >= 0; --j) {
+        if (threadIdx.x == 0) sT[j * ld + n_g] /= sT[j * ld + j];
+        __syncthreads();
+        const double yj = sT[j * ld + n_g];
+        for (int i = threadIdx.x; i < j; i += blockDim.x) sT[i * ld + n_g] -= sT[j * ld + i] * yj;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n_g; i += blockDim.x) yg[i] = sT[i * ld + n_g];
+    if (threadIdx.x == 0 && !ok) ps[PS_FAIL] = 2.0;
 }
 
 // y_c = x_b - X_g y_g
@@ -857,10 +863,11 @@ void launch_phong_border_solve(cudaStream_t s, int n_g, int nf6, const double* S
         CSLAM_CUDA(cudaMemcpy2DAsync(T + n_g, (n_g + 1) * sizeof(double), bg, sizeof(double), sizeof(double), n_g,
                                      cudaMemcpyDeviceToDevice, s));
     }
-    const size_t smem = size_t(n_g) * (n_g + 1) * sizeof(double);
+    const bool in_shared = n_g <= 160;
+    const size_t smem = in_shared ? size_t(n_g) * (n_g + 1) * sizeof(double) : 0;
     if (smem > 48 * 1024)   // per device: no process-wide cache
         CSLAM_CUDA(cudaFuncSetAttribute(phong_border_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    phong_border_solve_kernel<<<1, 128, smem, s>>>(n_g, T, yg, ps);
+    phong_border_solve_kernel<<<1, in_shared ? 128 : 1024, smem, s>>>(n_g, T, yg, ps, in_shared ? 1 : 0);
     count_launch();
     if (nf6 > 0) {
         phong_border_backsub_kernel<<<(nf6 + 255) / 256, 256, 0, s>>>(n_g, nf6, X, yg, yc);

@@ -1386,14 +1386,11 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
     const auto t_begin = clk::now();
     auto since = [&](clk::time_point t) { return std::chrono::duration<double, std::micro>(clk::now() - t).count(); };
     const int nw = int(take.size());
+    // ---- pass 1: sizes and offsets from the counts alone (a window's landmark arrays are sized by its point count,
+    // an upper bound of the landmarks it observes), so that pass 2 can write every window straight into the pinned
+    // staging block: no intermediate vectors, no second copy ----
     std::vector<WinDesc> desc(nw);
-    std::vector<double> poses, pts, ou, ov, od, oW;
-    std::vector<int> cam_free;
-    std::vector<uint32_t> lm_ptr;
-    std::vector<uint8_t> ocam;
-    std::vector<SunBlockData> suns;
-    std::vector<PriorBlockData> priors;
-    std::vector<std::vector<uint32_t>> lm_user(nw);
+    size_t n_pose_t = 0, n_pt_t = 0, n_lmptr_t = 0, n_obs_t = 0, n_W_t = 0, n_sun_t = 0, n_prior_t = 0;
     long long log_total = 0;
     for (int wi = 0; wi < nw; ++wi) {
         Engine& e = *engines[take[wi]];
@@ -1407,101 +1404,54 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
                       o.max_num_consecutive_invalid_steps, o.jacobi_scaling, o.dogleg_type, o.initial_trust_region_radius,
                       o.max_trust_region_radius, o.min_trust_region_radius, o.min_relative_decrease, o.min_lm_diagonal,
                       o.max_lm_diagonal, o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance};
-        // which blocks exist and which are free (dataset_vo.cpp:40-62)
-        std::vector<uint8_t> used(e.n_poses, 0);
-        std::vector<uint32_t> cnt(e.n_points, 0);
-        for (uint64_t i = 0; i < e.n_st; ++i) {
-            if (e.st_cam[i] >= e.n_poses || e.st_pt[i] >= e.n_points)
-                throw std::invalid_argument("stereo block index out of range");
-            used[e.st_cam[i]] = 1;
-            cnt[e.st_pt[i]]++;
-        }
-        for (auto& s : e.suns) used[s.cam] = 1;
-        for (auto& p : e.priors) used[p.cam] = 1;
         d.n_poses = int(e.n_poses);
-        d.pose_off = (long long)(poses.size() / 12);
-        int nf = 0;
-        for (uint32_t k = 0; k < e.n_poses; ++k) cam_free.push_back((used[k] && !e.pose_const[k]) ? nf++ : -1);
-        d.n_free = nf;
-        append(poses, e.h_poses, 12 * size_t(e.n_poses));
-        // landmark-major observation lists, landmarks in the caller's point order
-        std::vector<uint32_t> slot(e.n_points, 0xffffffffu), start;
-        d.lm_off = (long long)(pts.size() / 3);
-        d.lmptr_off = (long long)lm_ptr.size();
-        d.obs_off = (long long)ocam.size();
-        uint32_t acc = 0;
-        for (uint32_t j = 0; j < e.n_points; ++j)
-            if (cnt[j]) {
-                slot[j] = uint32_t(lm_user[wi].size());
-                lm_user[wi].push_back(j);
-                start.push_back(acc);
-                lm_ptr.push_back(acc);
-                acc += cnt[j];
-                append(pts, e.h_points + 3 * size_t(j), 3);
-            }
-        lm_ptr.push_back(acc);
-        d.n_lm = int(lm_user[wi].size());
-        const size_t base = ocam.size();
-        ocam.resize(base + e.n_st);
-        ou.resize(base + e.n_st);
-        ov.resize(base + e.n_st);
-        od.resize(base + e.n_st);
+        d.pose_off = (long long)n_pose_t;
+        d.lm_off = (long long)n_pt_t;
+        d.lmptr_off = (long long)n_lmptr_t;
+        d.obs_off = (long long)n_obs_t;
         d.W_per_obs = e.st_W_per_obs;
-        d.W_off = (long long)oW.size();
-        if (e.st_W_per_obs)
-            oW.resize(oW.size() + 9 * e.n_st);
-        else if (e.n_st)
-            append(oW, e.st_W, 9);
-        else
-            oW.resize(oW.size() + 9, 0.0);
-        for (uint64_t i = 0; i < e.n_st; ++i) {
-            const uint32_t s = slot[e.st_pt[i]];
-            const size_t pos = base + start[s]++;
-            ocam[pos] = uint8_t(e.st_cam[i]);
-            ou[pos] = e.st_uvd[3 * i];
-            ov[pos] = e.st_uvd[3 * i + 1];
-            od[pos] = e.st_uvd[3 * i + 2];
-            if (e.st_W_per_obs) std::memcpy(&oW[size_t(d.W_off) + 9 * (pos - base)], e.st_W + 9 * i, 72);
-        }
+        d.W_off = (long long)n_W_t;
         d.n_sun = int(e.suns.size());
         d.n_prior = int(e.priors.size());
-        d.sun_off = (long long)suns.size();
-        d.prior_off = (long long)priors.size();
-        suns.insert(suns.end(), e.suns.begin(), e.suns.end());
-        priors.insert(priors.end(), e.priors.begin(), e.priors.end());
+        d.sun_off = (long long)n_sun_t;
+        d.prior_off = (long long)n_prior_t;
         d.log_cap = std::min(std::max(o.max_num_iterations, 0), 254) + 2;
         d.log_off = log_total * CSLAM_LOG_COLS;
         log_total += d.log_cap;
+        n_pose_t += e.n_poses;
+        n_pt_t += e.n_points;
+        n_lmptr_t += size_t(e.n_points) + 1;
+        n_obs_t += e.n_st;
+        n_W_t += e.st_W_per_obs ? 9 * size_t(e.n_st) : 9;
+        n_sun_t += e.suns.size();
+        n_prior_t += e.priors.size();
     }
+    const double us_sizes = since(t_begin);
 
     // One pinned staging block, one device block, ONE host-to-device copy and ONE device-to-host copy per
     // batch (a window is a few KB: a dozen separate copies and allocations cost more than the kernel).
     // Layout (256-byte aligned pieces):  [inputs ... | poses | best points | summaries | logs | log rows | scratch]
     // The copy up covers inputs + poses, the copy back poses .. log rows.
-    const double us_pack = since(t_begin);
-    auto pad1 = [](auto& v) {
-        if (v.empty()) v.resize(1);
-    };
-    pad1(pts); pad1(ou); pad1(ov); pad1(od); pad1(oW); pad1(ocam); pad1(suns); pad1(priors);
     size_t cursor = 0;
     auto place = [&](size_t bytes) {
         const size_t off = cursor;
-        cursor = (cursor + bytes + 255) & ~size_t(255);
+        cursor = (cursor + std::max<size_t>(bytes, 8) + 255) & ~size_t(255);
         return off;
     };
-    const size_t o_desc = place(desc.size() * sizeof(WinDesc)), o_camfree = place(cam_free.size() * sizeof(int)),
-                 o_pts = place(pts.size() * 8), o_lmptr = place(lm_ptr.size() * sizeof(uint32_t)), o_ocam = place(ocam.size()),
-                 o_ou = place(ou.size() * 8), o_ov = place(ov.size() * 8), o_od = place(od.size() * 8), o_oW = place(oW.size() * 8),
-                 o_suns = place(suns.size() * sizeof(SunBlockData)), o_priors = place(priors.size() * sizeof(PriorBlockData));
-    const size_t o_poses = place(poses.size() * 8);
+    const size_t pts_bytes = std::max<size_t>(n_pt_t, 1) * 24;
+    const size_t o_desc = place(desc.size() * sizeof(WinDesc)), o_camfree = place(n_pose_t * sizeof(int)), o_pts = place(pts_bytes),
+                 o_lmptr = place(n_lmptr_t * sizeof(uint32_t)), o_ocam = place(n_obs_t), o_ou = place(n_obs_t * 8),
+                 o_ov = place(n_obs_t * 8), o_od = place(n_obs_t * 8), o_oW = place(n_W_t * 8),
+                 o_suns = place(n_sun_t * sizeof(SunBlockData)), o_priors = place(n_prior_t * sizeof(PriorBlockData));
+    const size_t o_poses = place(n_pose_t * 96);
     const size_t up_bytes = cursor;
-    const size_t o_best = place(pts.size() * 8), o_sum = place(size_t(nw) * sizeof(cslam_summary)),
+    const size_t o_best = place(pts_bytes), o_sum = place(size_t(nw) * sizeof(cslam_summary)),
                  o_logs = place(size_t(log_total) * CSLAM_LOG_COLS * 8), o_rows = place(size_t(nw) * sizeof(int));
     const size_t o_cov = place(37 * sizeof(double));  // covariance mode: the block and a status word
     const size_t down_end = cursor;
-    const size_t o_cand = place(pts.size() * 8), o_scl = place(pts.size() * 8), o_gl = place(pts.size() * 8);
+    const size_t o_cand = place(pts_bytes), o_scl = place(pts_bytes), o_gl = place(pts_bytes);
     const bool any_dogleg = n_lm_windows < nw;
-    const size_t o_yl = place(any_dogleg ? pts.size() * 8 : 8), o_dl = place(any_dogleg ? pts.size() * 8 : 8);
+    const size_t o_yl = place(any_dogleg ? pts_bytes : 8), o_dl = place(any_dogleg ? pts_bytes : 8);
     const size_t total = cursor;
 
     WindowArena* arena = window_arena_take(first.opt.device, down_end);
@@ -1512,19 +1462,83 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
     cudaStream_t stream = arena->stream;
     cudaEvent_t ev0 = arena->ev0, ev1 = arena->ev1;
     char* hp = arena->pinned;
-    auto put = [&](size_t off, const void* src, size_t bytes) { std::memcpy(hp + off, src, bytes); };
-    put(o_desc, desc.data(), desc.size() * sizeof(WinDesc));
-    put(o_camfree, cam_free.data(), cam_free.size() * sizeof(int));
-    put(o_pts, pts.data(), pts.size() * 8);
-    put(o_lmptr, lm_ptr.data(), lm_ptr.size() * sizeof(uint32_t));
-    put(o_ocam, ocam.data(), ocam.size());
-    put(o_ou, ou.data(), ou.size() * 8);
-    put(o_ov, ov.data(), ov.size() * 8);
-    put(o_od, od.data(), od.size() * 8);
-    put(o_oW, oW.data(), oW.size() * 8);
-    put(o_suns, suns.data(), suns.size() * sizeof(SunBlockData));
-    put(o_priors, priors.data(), priors.size() * sizeof(PriorBlockData));
-    put(o_poses, poses.data(), poses.size() * 8);
+
+    // ---- pass 2: every window written in place ----
+    int* cam_free = reinterpret_cast<int*>(hp + o_camfree);
+    double* h_pts = reinterpret_cast<double*>(hp + o_pts);
+    uint32_t* h_lmptr = reinterpret_cast<uint32_t*>(hp + o_lmptr);
+    uint8_t* h_ocam = reinterpret_cast<uint8_t*>(hp + o_ocam);
+    double* h_ou = reinterpret_cast<double*>(hp + o_ou);
+    double* h_ov = reinterpret_cast<double*>(hp + o_ov);
+    double* h_od = reinterpret_cast<double*>(hp + o_od);
+    double* h_oW = reinterpret_cast<double*>(hp + o_oW);
+    SunBlockData* h_suns = reinterpret_cast<SunBlockData*>(hp + o_suns);
+    PriorBlockData* h_priors = reinterpret_cast<PriorBlockData*>(hp + o_priors);
+    double* h_poses = reinterpret_cast<double*>(hp + o_poses);
+    std::vector<uint32_t> lm_user(std::max<size_t>(n_pt_t, 1));  // [lm_off + a] -> the caller's point index
+    std::vector<uint32_t> cnt, slot;                              // per-window scratch, reused
+    std::vector<uint8_t> used;
+    for (int wi = 0; wi < nw; ++wi) {
+        Engine& e = *engines[take[wi]];
+        WinDesc& d = desc[wi];
+        // which blocks exist and which are free (dataset_vo.cpp:40-62)
+        used.assign(e.n_poses, 0);
+        cnt.assign(e.n_points, 0);
+        for (uint64_t i = 0; i < e.n_st; ++i) {
+            if (e.st_cam[i] >= e.n_poses || e.st_pt[i] >= e.n_points)
+                throw std::invalid_argument("stereo block index out of range");
+            used[e.st_cam[i]] = 1;
+            cnt[e.st_pt[i]]++;
+        }
+        for (auto& sb : e.suns) used[sb.cam] = 1;
+        for (auto& pb : e.priors) used[pb.cam] = 1;
+        int nf = 0;
+        int* cf = cam_free + d.pose_off;
+        for (uint32_t k = 0; k < e.n_poses; ++k) cf[k] = (used[k] && !e.pose_const[k]) ? nf++ : -1;
+        d.n_free = nf;
+        std::memcpy(h_poses + 12 * size_t(d.pose_off), e.h_poses, 96 * size_t(e.n_poses));
+        // landmark-major observation lists, landmarks in the caller's point order; `slot[j]` becomes the write cursor
+        // of point j's list
+        slot.resize(e.n_points);
+        uint32_t* lp = h_lmptr + d.lmptr_off;
+        uint32_t* lu = lm_user.data() + d.lm_off;
+        double* wp = h_pts + 3 * size_t(d.lm_off);
+        uint32_t acc = 0, n_lm = 0;
+        for (uint32_t j = 0; j < e.n_points; ++j)
+            if (cnt[j]) {
+                lu[n_lm] = j;
+                lp[n_lm] = acc;
+                slot[j] = acc;
+                acc += cnt[j];
+                wp[3 * n_lm] = e.h_points[3 * size_t(j)];
+                wp[3 * n_lm + 1] = e.h_points[3 * size_t(j) + 1];
+                wp[3 * n_lm + 2] = e.h_points[3 * size_t(j) + 2];
+                ++n_lm;
+            }
+        lp[n_lm] = acc;
+        d.n_lm = int(n_lm);
+        const size_t base = size_t(d.obs_off);
+        double* Wdst = h_oW + d.W_off;
+        if (!e.st_W_per_obs) {
+            if (e.n_st)
+                std::memcpy(Wdst, e.st_W, 72);
+            else
+                std::memset(Wdst, 0, 72);
+        }
+        for (uint64_t i = 0; i < e.n_st; ++i) {
+            const size_t rel = slot[e.st_pt[i]]++;
+            const size_t pos = base + rel;
+            h_ocam[pos] = uint8_t(e.st_cam[i]);
+            h_ou[pos] = e.st_uvd[3 * i];
+            h_ov[pos] = e.st_uvd[3 * i + 1];
+            h_od[pos] = e.st_uvd[3 * i + 2];
+            if (e.st_W_per_obs) std::memcpy(Wdst + 9 * rel, e.st_W + 9 * i, 72);
+        }
+        if (!e.suns.empty()) std::memcpy(h_suns + d.sun_off, e.suns.data(), e.suns.size() * sizeof(SunBlockData));
+        if (!e.priors.empty()) std::memcpy(h_priors + d.prior_off, e.priors.data(), e.priors.size() * sizeof(PriorBlockData));
+    }
+    std::memcpy(hp + o_desc, desc.data(), desc.size() * sizeof(WinDesc));
+    const double us_pack = since(t_begin);
     const double us_stage = since(t_begin);
     {
         DBuf<uint8_t> d_all;
@@ -1602,7 +1616,7 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
                 if (cam_free[size_t(d.pose_off) + k] >= 0)
                     std::memcpy(e.h_poses + 12 * size_t(k), &poses_out[12 * (size_t(d.pose_off) + k)], 96);
             for (int a = 0; a < d.n_lm; ++a)
-                std::memcpy(e.h_points + 3 * size_t(lm_user[wi][a]), &pts_out[3 * (size_t(d.lm_off) + a)], 24);
+                std::memcpy(e.h_points + 3 * size_t(lm_user[size_t(d.lm_off) + a]), &pts_out[3 * (size_t(d.lm_off) + a)], 24);
             e.log.clear();
             for (int r = 0; r < log_rows[wi]; ++r) {
                 LmRow row;
@@ -1616,8 +1630,8 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
             if (summaries) summaries[take[wi]] = sums[wi];
         }
         if (timing)
-            std::fprintf(stderr, "[cslam window batch] %d windows: pack %.0f us, stage %.0f us, alloc+H2D+kernel(%.0f us)+D2H %.0f us, "
-                                 "unpack %.0f us\n", nw, us_pack, us_stage - us_pack, ms * 1e3, us_device - us_stage,
+            std::fprintf(stderr, "[cslam window batch] %d windows: sizes %.0f us, pack (in place) %.0f us, alloc+H2D+kernel(%.0f us)+D2H "
+                                 "%.0f us, unpack %.0f us\n", nw, us_sizes, us_pack - us_sizes, ms * 1e3, us_device - us_stage,
                          since(t_begin) - us_device);
     }
 }

@@ -64,7 +64,8 @@ typedef struct cslam_options {
     int band_leaves;        /* exact solve of a banded reduced system: number of leaves the band is cut
                                into (0 = auto) */
     int window_path;        /* small problems (<= 8 poses, exact solve): 0 = auto (one-CTA-per-window kernel
-                               with the LM loop on the device), 1 = never, 2 = require it */
+                               with the trust-region loop — LEVENBERG_MARQUARDT or DOGLEG — on the device; also
+                               cslam_covariance_block as one launch), 1 = never, 2 = require it */
     int band_separator_solver; /* exact solve of a banded reduced system, separator system between the
                                leaves: 0 = auto, 1 = banded Cholesky on one CTA, 2 = block cyclic reduction */
     int trust_region_strategy;  /* 0 = LEVENBERG_MARQUARDT (Ceres default, dataset_vo.cpp),
@@ -216,9 +217,9 @@ cslam_status cslam_time_phong(cslam_problem* p, int reps, double* ms_per_launch)
  * poses, vertex positions and normals, materials, textures and the light are optimised together and
  * all of those arrays are updated in place.  The lighting blocks must pair one-to-one with the stereo
  * blocks (the driver adds both while walking the same observations, :55-69 / :100-190), textures
- * must be shared blocks (cslam_set_textures), tracks hold at most 32 observations per vertex and
- * there are at most 160 shared columns (3 per material + 1 per texture + 3); anything else returns
- * CSLAM_ERR_NOT_IMPL.  Single GPU. */
+ * must be shared blocks (cslam_set_textures) and there are at most 1024 shared columns (3 per material
+ * + 1 per texture + 3); anything else returns CSLAM_ERR_NOT_IMPL.  A track may be of any length.
+ * With a communicator attached (cslam_attach_comm) the vertices are sharded over the ranks. */
 cslam_status cslam_solve(cslam_problem* p, cslam_summary* summary);
 
 /* The same, split so a caller can keep the problem resident in HBM:
@@ -235,7 +236,8 @@ cslam_status cslam_download(cslam_problem* p);
 cslam_status cslam_reset_state(cslam_problem* p);
 
 /* Config 4 (scripts/ba_all_*.sh: many independent tracks): solve n independent small problems
- * in one launch per GPU.  Each problem must already hold its data. */
+ * in one launch per GPU and trust-region strategy present (the scripts' default, SUBSPACE_DOGLEG of
+ * dataset_vo_sun.cpp:142-143, included).  Each problem must already hold its data. */
 cslam_status cslam_solve_batch(cslam_problem** problems, int n, cslam_summary* summaries);
 
 /* ceres::Covariance::Compute + GetCovarianceBlockInTangentSpace for one pose block
