@@ -21,7 +21,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <mutex>
+#include <thread>
 
 #include "kernels.cuh"
 
@@ -1476,9 +1478,10 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
     PriorBlockData* h_priors = reinterpret_cast<PriorBlockData*>(hp + o_priors);
     double* h_poses = reinterpret_cast<double*>(hp + o_poses);
     std::vector<uint32_t> lm_user(std::max<size_t>(n_pt_t, 1));  // [lm_off + a] -> the caller's point index
+    auto pack_range = [&](int w_lo, int w_hi) {
     std::vector<uint32_t> cnt, slot;                              // per-window scratch, reused
     std::vector<uint8_t> used;
-    for (int wi = 0; wi < nw; ++wi) {
+    for (int wi = w_lo; wi < w_hi; ++wi) {
         Engine& e = *engines[take[wi]];
         WinDesc& d = desc[wi];
         // which blocks exist and which are free (dataset_vo.cpp:40-62)
@@ -1536,6 +1539,34 @@ void solve_window_batch(Engine** engines, int n, cslam_summary* summaries, int c
         }
         if (!e.suns.empty()) std::memcpy(h_suns + d.sun_off, e.suns.data(), e.suns.size() * sizeof(SunBlockData));
         if (!e.priors.empty()) std::memcpy(h_priors + d.prior_off, e.priors.data(), e.priors.size() * sizeof(PriorBlockData));
+    }
+    };
+    // the windows are independent and write disjoint pieces: a large batch is packed by a few threads
+    const int n_pack = (nw >= 64 && n_obs_t >= 16384) ? int(std::min<unsigned>(4u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+    if (n_pack == 1) {
+        pack_range(0, nw);
+    } else {
+        std::vector<std::thread> th;
+        std::vector<std::exception_ptr> err(n_pack);
+        // contiguous ranges with about the same number of observations each
+        std::vector<int> cut(n_pack + 1, nw);
+        cut[0] = 0;
+        for (int t = 1, wi = 0; t < n_pack; ++t) {
+            const size_t target = n_obs_t * size_t(t) / size_t(n_pack);
+            while (wi < nw && size_t(desc[wi].obs_off) < target) ++wi;
+            cut[t] = wi;
+        }
+        for (int t = 0; t < n_pack; ++t)
+            th.emplace_back([&, t] {
+                try {
+                    pack_range(cut[t], cut[t + 1]);
+                } catch (...) {
+                    err[t] = std::current_exception();
+                }
+            });
+        for (auto& x : th) x.join();
+        for (auto& x : err)
+            if (x) std::rethrow_exception(x);
     }
     std::memcpy(hp + o_desc, desc.data(), desc.size() * sizeof(WinDesc));
     const double us_pack = since(t_begin);
