@@ -344,6 +344,19 @@ constexpr int G2_NT = 128;
 constexpr int G2_LMAX = 10;  // longest camera list this variant takes
 constexpr int G2_ZB = G2_NT * 18;  // doubles per Z buffer: one (landmark, slot) entry per thread
 constexpr int G2_ZPAD = 32;  // fragment rows of the last (partial) MMA row tile read past the batch
+// Z tile layout.  0: [landmark][slot][row 6][col 3] (a thread's 18 values contiguous; fragment loads have 2-way bank
+// conflicts).  1: [k = 3 landmark + col][row], row stride = the smallest value >= 8 T8 that is 4 mod 16 — the
+// fragment load of lane (g, t) reads word (4 ks + t) * stride + 8 tile + g: 4 t + g mod 16 is distinct over a
+// half-warp, conflict-free — with the producer threads slot-fastest (poses / scaling in padded shared arrays) so that
+// their 16-byte stores are conflict-free too; the buffers are dynamic shared memory (2 x G2_ZCAP doubles).
+#ifndef CSLAM_G2_KROW
+#define CSLAM_G2_KROW 1
+#endif
+constexpr bool G2_KROW = CSLAM_G2_KROW != 0;
+
+constexpr int G2_ZCAP = 3456;  // doubles per Z buffer, KROW layout (L >= 4: every thread produces)
+constexpr int G2_PSTR = 13, G2_SSTR = 7;  // KROW: row strides of the padded pose / scaling copies (odd: conflict-free)
+__device__ __forceinline__ int g2_zstride(int T8) { return ((8 * T8 + 11) / 16) * 16 + 4; }
 
 // D(8x8) += A(8x4) B(4x8): lane (g = lane/4, t = lane%4) holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -363,7 +376,10 @@ __global__ void __launch_bounds__(G2_NT, MINB)
     __shared__ __align__(128) double s_pose[G2_LMAX * 12];
     __shared__ double s_sp[G2_LMAX * 6];
     __shared__ double s_A[kItemMax * 9];
-    __shared__ __align__(16) double s_Z[2 * G2_ZB + G2_ZPAD];
+    __shared__ __align__(16) double s_Zst[G2_KROW ? 2 : 2 * G2_ZB + G2_ZPAD];
+    extern __shared__ __align__(16) double s_Zdyn[];  // KROW: 2 * G2_ZCAP doubles
+    double* const s_Z = G2_KROW ? s_Zdyn : s_Zst;
+    __shared__ double s_poseP[G2_KROW ? G2_LMAX * G2_PSTR : 1], s_spP[G2_KROW ? G2_LMAX * G2_SSTR : 1];
     __shared__ double s_redsum[32];
     __shared__ int s_free[G2_LMAX];
     __shared__ int s_blk[G2_LMAX * (G2_LMAX + 1) / 2];
@@ -417,13 +433,21 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         mbar_wait(&s_bar, phase);
         phase ^= 1;
         __syncthreads();
+        if (G2_KROW) {
+            // (visible to the producers after pass 1's barrier)
+            for (int k = tid; k < 12 * L; k += G2_NT) s_poseP[(k / 12) * G2_PSTR + k % 12] = s_pose[k];
+            for (int k = tid; k < 6 * L; k += G2_NT) s_spP[(k / 6) * G2_SSTR + k % 6] = s_sp[k];
+        }
 
         // ---- roles of the pipeline below; the first observation is requested before pass 1 ----
         // landmarks per batch (one observation per thread), a multiple of 4 so that a batch's
         // 3 TL columns are whole k-steps of 4
-        const int TL = (G2_NT / L) & ~3;
+        const int T8 = (6 * L + 7) >> 3;
+        const int ZS = g2_zstride(T8);
+        const int TL = G2_KROW ? min((G2_NT / L) & ~3, (G2_ZCAP / (3 * ZS)) & ~3) : (G2_NT / L) & ~3;
+        const int ZBUF = G2_KROW ? G2_ZCAP : G2_ZB;
         const int nbatch = (nj + TL - 1) / TL;
-        const int pq = tid % TL, pi = tid / TL;
+        const int pq = G2_KROW ? tid / L : tid % TL, pi = G2_KROW ? (tid < TL * L ? tid % L : L) : tid / TL;
         const bool p_active = pi < L;
         const int pf = p_active ? s_free[pi] : -1;
         const bool producing = p_active && pf >= 0;
@@ -568,7 +592,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         // warps (1 and 2) split the off-diagonal rectangle by rows.  nr <= 4 (2 for rectangles), nc <= 4.
         const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the role is warp-uniform
         const int lane = tid & 31, fg = lane >> 2, ft = lane & 3;
-        const int T8 = (6 * L + 7) >> 3, Th = (T8 + 1) >> 1, Th1 = (Th + 1) >> 1;
+        const int Th = (T8 + 1) >> 1, Th1 = (Th + 1) >> 1;
         const bool tri = warp == 0 || warp == 3;
         int r0, nr, c0, nc;
         if (warp == 0) {
@@ -589,14 +613,24 @@ __global__ void __launch_bounds__(G2_NT, MINB)
         for (int bt = 0; bt <= nbatch; ++bt) {
             if (bt < nbatch && producing) {
                 const int jl = bt * TL + pq;
+                // this thread's 6 rows x 3 columns of the tile
+                double* zt = G2_KROW ? s_Z + (bt & 1) * ZBUF + 3 * pq * ZS + 6 * pi : s_Z + (bt & 1) * ZBUF + (pq * L + pi) * 18;
+                auto zero_rows = [&]() {
+                    if (G2_KROW) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int a = 0; a < 6; a += 2) *reinterpret_cast<double2*>(zt + c * ZS + a) = make_double2(0.0, 0.0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(0.0, 0.0);
+                    }
+                };
                 if (RAG && jl < nj && nx_k == 0xff) {
                     // the landmark is not seen from this camera: zero rows
-                    double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
-#pragma unroll
-                    for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(0.0, 0.0);
+                    zero_rows();
                     prefetch(jl + TL);
                 } else if (jl < nj) {
-                    double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
                     const double p[3] = {nx[3], nx[4], nx[5]};
                     const double sl[3] = {nx[6], nx[7], nx[8]};
                     const double ou = nx[0], ov = nx[1], od = nx[2];
@@ -605,7 +639,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                     {
                         double pose[12], Wl[9];
 #pragma unroll
-                        for (int k = 0; k < 12; ++k) pose[k] = s_pose[12 * pi + k];
+                        for (int k = 0; k < 12; ++k) pose[k] = G2_KROW ? s_poseP[G2_PSTR * pi + k] : s_pose[12 * pi + k];
 #pragma unroll
                         for (int k = 0; k < 9; ++k) Wl[k] = WPO ? v.obs_W[9 * e + k] : s_W[k];
                         stereo_block<true>(v.cam, pose, p, ou, ov, od, Wl, r, Jc, Jp);
@@ -616,12 +650,13 @@ __global__ void __launch_bounds__(G2_NT, MINB)
 #pragma unroll
                         for (int q = 0; q < 3; ++q) Jp[3 * k + q] *= sl[q];
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= s_sp[6 * pi + q];
+                        for (int q = 0; q < 6; ++q) Jc[6 * k + q] *= G2_KROW ? s_spP[G2_SSTR * pi + q] : s_sp[6 * pi + q];
                     }
                     const double* A = s_A + 9 * jl;
                     const double a00 = A[0], a10 = A[1], a11 = A[2], a20 = A[3], a21 = A[4], a22 = A[5];
                     const double t0 = A[6], t1 = A[7], t2 = A[8];
                     int u = 0;
+                    double Zr[G2_KROW ? 18 : 1];  // KROW: [col][row], stored as 16-byte pairs below
 #pragma unroll
                     for (int a = 0; a < 6; ++a) {
                         const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3] + Jc[12 + a] * Jp[6];
@@ -630,9 +665,13 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                         const double z0 = w0 * a00;
                         const double z1 = w0 * a10 + w1 * a11;
                         const double z2 = w0 * a20 + w1 * a21 + w2 * a22;
-                        zt[3 * a] = z0;
-                        zt[3 * a + 1] = z1;
-                        zt[3 * a + 2] = z2;
+                        if (G2_KROW) {
+                            Zr[a] = z0, Zr[6 + a] = z1, Zr[12 + a] = z2;
+                        } else {
+                            zt[3 * a] = z0;
+                            zt[3 * a + 1] = z1;
+                            zt[3 * a + 2] = z2;
+                        }
                         const double ga = Jc[a] * r[0] + Jc[6 + a] * r[1] + Jc[12 + a] * r[2];
                         gpa[a] += ga;
                         bpa[a] = fma(-z0, t0, fma(-z1, t1, fma(-z2, t2, bpa[a] + ga)));
@@ -640,44 +679,64 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                         for (int b = a; b < 6; ++b, ++u)
                             U[u] = fma(Jc[a], Jc[b], fma(Jc[6 + a], Jc[6 + b], fma(Jc[12 + a], Jc[12 + b], U[u])));
                     }
+                    if (G2_KROW) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int a = 0; a < 6; a += 2)
+                                *reinterpret_cast<double2*>(zt + c * ZS + a) = make_double2(Zr[6 * c + a], Zr[6 * c + a + 1]);
+                    }
                 } else {
                     // a k-step of the last batch may reach one landmark past nj: zero columns
-                    double* zt = s_Z + (bt & 1) * G2_ZB + (pq * L + pi) * 18;
-#pragma unroll
-                    for (int k = 0; k < 18; k += 2) *reinterpret_cast<double2*>(zt + k) = make_double2(0.0, 0.0);
+                    zero_rows();
                 }
             }
             if (bt > 0) {
-                const double* zt = s_Z + ((bt - 1) & 1) * G2_ZB;
+                const double* zt = s_Z + ((bt - 1) & 1) * ZBUF;
                 const int nval = min(TL, nj - (bt - 1) * TL);
                 const int nk = (3 * nval + 3) >> 2;
+                // fragment word of (k, row): KROW k * ZS + row, else landmark * zlm + col + 3 row; rstep = one tile down
+                const int rstep = G2_KROW ? 8 : 24;
+                const int frow_r = G2_KROW ? 8 * r0 + fg : zrow_r, frow_c = G2_KROW ? 8 * c0 + fg : zrow_c;
+                // The fragments of k-step ks + 1 are requested right after the MMAs of k-step ks have been issued (they read
+                // their operands at issue), so the loads fly while the tensor pipe drains: 2.39 -> 2.33 ms on C5.  Loading
+                // them BEFORE the MMAs into a second register set and moving them over measured no better than the plain
+                // loop (2.39 ms: +4 registers, and the moves wait for the loads).
                 if (tri) {
-                    for (int ks = 0; ks < nk; ++ks) {
+                    auto ld = [&](int ks, double* f) {
                         const int kk = 4 * ks + ft, jj = kk / 3;
-                        const double* zb = zt + jj * zlm + (kk - 3 * jj) + zrow_r;
-                        double f[4];
+                        const double* zb = (G2_KROW ? zt + kk * ZS : zt + jj * zlm + (kk - 3 * jj)) + frow_r;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) f[i] = i < nr ? zb[24 * i] : 0.0;
+                        for (int i = 0; i < 4; ++i) f[i] = i < nr ? zb[rstep * i] : 0.0;
+                    };
+                    double f[4];
+                    ld(0, f);
+                    for (int ks = 0; ks < nk; ++ks) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = i; j < 4; ++j)
                                 if (j < nr) dmma884(M[2 * (4 * i - i * (i - 1) / 2 + j - i)], M[2 * (4 * i - i * (i - 1) / 2 + j - i) + 1], f[i], f[j]);
+                        if (ks + 1 < nk) ld(ks + 1, f);
                     }
                 } else {
-                    for (int ks = 0; ks < nk; ++ks) {
+                    auto ld = [&](int ks, double* fr, double* fc) {
                         const int kk = 4 * ks + ft, jj = kk / 3;
-                        const double* zb = zt + jj * zlm + (kk - 3 * jj);
-                        double fr[2], fc[4];
+                        const double* zb = G2_KROW ? zt + kk * ZS : zt + jj * zlm + (kk - 3 * jj);
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) fr[i] = i < nr ? zb[zrow_r + 24 * i] : 0.0;
+                        for (int i = 0; i < 2; ++i) fr[i] = i < nr ? zb[frow_r + rstep * i] : 0.0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) fc[j] = j < nc ? zb[zrow_c + 24 * j] : 0.0;
+                        for (int j = 0; j < 4; ++j) fc[j] = j < nc ? zb[frow_c + rstep * j] : 0.0;
+                    };
+                    double fr[2], fc[4];
+                    ld(0, fr, fc);
+                    for (int ks = 0; ks < nk; ++ks) {
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 if (i < nr && j < nc) dmma884(M[2 * (4 * i + j)], M[2 * (4 * i + j) + 1], fr[i], fc[j]);
+                        if (ks + 1 < nk) ld(ks + 1, fr, fc);
                     }
                 }
             }
@@ -735,7 +794,7 @@ __global__ void __launch_bounds__(G2_NT, MINB)
                 if (f < 0) continue;
                 double acc = 0.0;
                 const int nl = min(TL, nj);  // lanes beyond nj never produced
-                for (int q = 0; q < nl; ++q) acc += red[(i * TL + q) * 33 + k];
+                for (int q = 0; q < nl; ++q) acc += red[(G2_KROW ? q * L + i : i * TL + q) * 33 + k];
                 if (k < 21) {
                     int a = 0, rem = k;
                     while (rem >= 6 - a) {
@@ -758,6 +817,17 @@ __global__ void __launch_bounds__(G2_NT, MINB)
 
 }  // namespace
 
+namespace {
+constexpr int G2_DYN = G2_KROW ? 2 * G2_ZCAP * int(sizeof(double)) : 0;  // dynamic shared memory of schur_grouped2_kernel
+template <class K>
+void g2_launch(K kernel, int grid, cudaStream_t s, const DevView& v, const GroupView& g, int lo, int hi, LmDiag dg, double* S,
+               double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
+    // (the opt-in is per device and costs a microsecond: set at every launch rather than cached process-wide)
+    if (G2_DYN > 48 * 1024) CSLAM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN));
+    kernel<<<grid, G2_NT, G2_DYN, s>>>(v, g, lo, hi, dg, S, Bdiag, bp, gp, gl, scal);
+}
+}  // namespace
+
 void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, int n_items_small, int n_items_rag, LmDiag dg,
                           double* S, double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     // items: [0, n_items_small) exact groups with L <= 10, then exact groups with 10 < L <= 16, then the last
@@ -766,9 +836,9 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
         const int lo = g.n_items - n_items_rag;
         const int grid = n_items_rag < 2 * kSMs ? n_items_rag : 2 * kSMs;
         if (v.W_per_obs)
-            schur_grouped2_kernel<true, 2, true><<<grid, G2_NT, 0, s>>>(v, g, lo, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
+            g2_launch(schur_grouped2_kernel<true, 2, true>, grid, s, v, g, lo, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
         else
-            schur_grouped2_kernel<false, 2, true><<<grid, G2_NT, 0, s>>>(v, g, lo, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
+            g2_launch(schur_grouped2_kernel<false, 2, true>, grid, s, v, g, lo, g.n_items, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     // items [0, n_items_small) have L <= 10 (two consumer warps), the rest 10 < L <= 16 (five)
@@ -787,11 +857,11 @@ void launch_schur_grouped(cudaStream_t s, const DevView& v, const GroupView& g, 
         // (a single-evaluation variant — V_j reduced through shared memory inside the pipeline, no pass 1 —
         // was measured slower, 2.67 vs 2.50 ms on C5: its per-batch Cholesky chain is exposed latency)
         if (v.W_per_obs)
-            schur_grouped2_kernel<true, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+            g2_launch(schur_grouped2_kernel<true, 2>, grid, s, v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else if (occ == 3)
-            schur_grouped2_kernel<false, 3><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+            g2_launch(schur_grouped2_kernel<false, 3>, grid, s, v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         else
-            schur_grouped2_kernel<false, 2><<<grid, G2_NT, 0, s>>>(v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
+            g2_launch(schur_grouped2_kernel<false, 2>, grid, s, v, g, 0, n_items_small, dg, S, Bdiag, bp, gp, gl, scal);
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (g.n_items - n_items_rag > n_items_small) {
