@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libcslam_b200.so")
-SOURCES = ["kernels.cu", "kernels_grouped.cu", "kernels_pcg.cu", "kernels_window.cu", "kernels_band.cu", "kernels_dense.cu", "kernels_bandpcg.cu", "kernels_phong.cu", "kernels_phong_solve.cu", "kernels_phong_grouped.cu", "kernels_phong_long.cu", "ransac.cu", "structure.cu", "engine.cu", "capi.cu", "comm.cu"]
+SOURCES = ["kernels.cu", "kernels_grouped.cu", "kernels_pcg.cu", "kernels_window.cu", "kernels_band.cu", "kernels_dense.cu", "kernels_wband.cu", "kernels_bandpcg.cu", "kernels_phong.cu", "kernels_phong_solve.cu", "kernels_phong_grouped.cu", "kernels_phong_long.cu", "ransac.cu", "structure.cu", "engine.cu", "capi.cu", "comm.cu"]
 HEADERS = ["closed_form.h", "common.cuh", "engine.h", "dogleg_host.h", "kernels.cuh", "comm.h", "phong_common.cuh", "chol_chain.cuh",
            os.path.join("..", "..", "include", "cslam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

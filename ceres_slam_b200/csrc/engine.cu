@@ -1387,8 +1387,12 @@ void Engine::plan_band_solver() {
     for (int a = 0; a < n_free; ++a)
         if (s_rowptr_h[a + 1] > s_rowptr_h[a]) w = std::max(w, s_col_h[s_rowptr_h[a + 1] - 1] - a);
     bandpc_active = false;
+    wband_active = false;
     if (w > kBandWmax) {
-        // Not a narrow band.  Too large for the dense factorisation as well: conjugate gradients preconditioned
+        // Not a narrow band.  A wide band (tracks of 14 .. 65 frames) on a problem that is long compared with it: the
+        // chunked bordered-band factorisation (kernels_wband.cu) — exact, and far cheaper than the O(n^3) dense one.
+        if (opt.dense_solver <= 0 && opt.bandpc_solver != 1 && opt.bandpc_solver >= 0 && !ph.active && plan_wband_solver(w)) return;
+        // Too large for the dense factorisation as well: conjugate gradients preconditioned
         // with the banded solve of the short-track landmarks' part of the system (kernels_bandpcg.cu).
         if (6ll * n_free <= kDenseMaxN || opt.dense_solver > 0 || opt.bandpc_solver < 0 || n_free < 64 * kBandPcW || ph.active)
             return;
@@ -1464,6 +1468,127 @@ void Engine::plan_band_solver() {
     d_X2.alloc(6 * n2, stream);
     d_y2.alloc(6 * n2, stream);
     band_active = !bandpc_active;
+}
+
+// The exact solve of a wide block-banded reduced system (half-bandwidth w of 13 .. 64 blocks), kernels_wband.cu:
+// C chunks separated by separators of w poses.  Taken automatically (bandpc_solver = 0) when the trajectory is long
+// compared with the band; bandpc_solver = 2 takes it whenever the layout is possible (tests on small problems).
+bool Engine::plan_wband_solver(int w) {
+    if (w > kWbandMaxW) return false;
+    const int n = n_free;
+    const bool forced = opt.bandpc_solver == 2;
+    if (!forced && (n < 256 || n < 8 * (w + 1))) return false;
+    // chunk chains (~18 us per panel of 48 columns incl. the back-substitution) against the dense separator solve
+    // (~21 us per panel of the (C - 1) 6w separator unknowns)
+    int C = int(std::lround(std::sqrt(6.0 * n / (7.0 * w))));
+    C = std::min(C, 1 + kDenseMaxN / (6 * w));
+    C = std::min(C, (n + w) / (3 * w + 1));       // interiors of at least 2w + 1 poses
+    C = std::max(C, 1);
+    const int inter = n - (C - 1) * w;
+    if (inter < C * (w + 1)) return false;
+    const int base = inter / C, extra = inter % C;
+    std::vector<int> owner(n), local(n), p0(C), len(C);
+    int pos = 0;
+    for (int c = 0; c < C; ++c) {
+        len[c] = base + (c < extra ? 1 : 0);
+        p0[c] = pos;
+        for (int a = 0; a < len[c]; ++a) {
+            owner[pos] = c;
+            local[pos++] = a;
+        }
+        if (c + 1 < C)
+            for (int a = 0; a < w; ++a) {
+                owner[pos] = -(c + 1);
+                local[pos++] = a;
+            }
+    }
+    // every stored block must fit the layout (interior x interior of one chunk, interior x adjacent separator, or
+    // inside one separator): guaranteed by the band width, checked because a miss would be a silent wrong answer
+    for (int a = 0; a < n; ++a)
+        for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) {
+            const int oa = owner[a], ob = owner[s_col_h[e]];
+            const bool ok = (oa >= 0 && (ob == oa || ob == -(oa + 1))) || (oa < 0 && (ob == -oa || ob == oa));
+            if (!ok) return false;
+        }
+    const int nb = dense_panel_width();
+    const int m_pad = (6 * (base + (extra ? 1 : 0)) + nb - 1) / nb * nb;
+    const int sepw = C > 1 ? 6 * w : 0, nbr = 2 * sepw + 1, ldB = nbr + (nbr & 1);
+    const int bwr = (6 * w + 5 + 7) / 8 * 8, ld = bwr + nb;
+    const size_t a_stride = size_t(m_pad) * (ld + 1) + 2, b_stride = size_t(m_pad + ldB) * ldB;
+    const size_t ns = size_t(C - 1) * sepw, ns_pad = (ns + nb - 1) / nb * nb;
+    const size_t bytes = 8 * (C * (a_stride + b_stride) + (ns_pad + 8) * (ns_pad + 1));
+    if (bytes > (size_t(12) << 30)) return false;
+    wband_w = w;
+    wband_C = C;
+    wband_mpad = m_pad;
+    d_wb_owner.upload(owner, stream);
+    d_wb_local.upload(local, stream);
+    d_wb_p0.upload(p0, stream);
+    d_wb_len.upload(len, stream);
+    d_wb_A.alloc(a_stride * C, stream);
+    d_wb_Bd.alloc(b_stride * C, stream);
+    d_wb_Ld.alloc(size_t(C) * (m_pad / nb) * nb * nb, stream);
+    d_wb_inv.alloc(size_t(C) * m_pad, stream);
+    d_wb_xw.alloc(size_t(C) * m_pad, stream);
+    if (C > 1) {
+        d_wb_xsep.alloc(ns, stream);
+        d_wb_T.alloc((ns_pad + 8) * (ns_pad + 1), stream);
+        d_wb_TLd.alloc((ns_pad / nb) * nb * nb, stream);
+        d_wb_Tinv.alloc(ns_pad, stream);
+        d_wb_Txw.alloc(ns_pad, stream);
+    }
+    if (!d_band_fail.p) d_band_fail.alloc(1, stream);
+    wband_active = true;
+    if (std::getenv("CSLAM_DEBUG_SOLVER"))
+        std::fprintf(stderr, "[solver] wide-band Cholesky: %d free poses, half-bandwidth %d, %d chunks of <= %d unknowns, %zu separator unknowns\n",
+                     n, w, C, m_pad, ns);
+    return true;
+}
+
+WbandView Engine::wband_view(const double* rhs, double* y) {
+    const int nb = dense_panel_width();
+    WbandView V;
+    V.n_free = n_free;
+    V.w = wband_w;
+    V.C = wband_C;
+    V.m_pad = wband_mpad;
+    V.sepw = wband_C > 1 ? 6 * wband_w : 0;
+    V.nbr = 2 * V.sepw + 1;
+    V.bwr = (6 * wband_w + 5 + 7) / 8 * 8;
+    V.ld = V.bwr + nb;
+    V.ldB = V.nbr + (V.nbr & 1);
+    V.a_stride = (long long)V.m_pad * (V.ld + 1) + 2;
+    V.b_stride = (long long)(V.m_pad + V.ldB) * V.ldB;
+    V.rowptr = d_s_rowptr.p;
+    V.col = d_s_col.p;
+    V.S = d_S;
+    V.rhs = rhs;
+    V.owner = d_wb_owner.p;
+    V.local = d_wb_local.p;
+    V.chunk_p0 = d_wb_p0.p;
+    V.chunk_len = d_wb_len.p;
+    V.A = d_wb_A.p;
+    V.Bd = d_wb_Bd.p;
+    V.Ldiag = d_wb_Ld.p;
+    V.invd = d_wb_inv.p;
+    V.xw = d_wb_xw.p;
+    V.xsep = d_wb_xsep.p;
+    V.T.n = (wband_C - 1) * V.sepw;
+    V.T.n_pad = (V.T.n + nb - 1) / nb * nb;
+    V.T.ld = V.T.n_pad + 8;
+    V.T.rowptr = nullptr;
+    V.T.col = nullptr;
+    V.T.S = nullptr;
+    V.T.rhs = nullptr;
+    V.T.A = d_wb_T.p;
+    V.T.Ldiag = d_wb_TLd.p;
+    V.T.invd = d_wb_Tinv.p;
+    V.T.y = d_wb_xsep.p;
+    V.T.fail = d_band_fail.p;
+    V.Txw = d_wb_Txw.p;
+    V.y = y;
+    V.fail = d_band_fail.p;
+    return V;
 }
 
 // Conjugate gradients on S y = rhs preconditioned with the banded direct solve (kernels_bandpcg.cu).  Host-driven:
@@ -1542,7 +1667,7 @@ void Engine::bandpc_solve(const double* rhs, double* y) {
 // to 1e-15 needs hundreds of iterations there and is not exact) or dense enough to be a real contraction.
 void Engine::plan_dense_solver() {
     dense_active = false;
-    if (opt.linear_solver != 0 || n_free <= 0 || opt.dense_solver < 0 || ph.active) return;
+    if (opt.linear_solver != 0 || n_free <= 0 || opt.dense_solver < 0 || ph.active || wband_active) return;
     const long long n = 6ll * n_free;
     if (n > kDenseMaxN) return;
     // auto: whenever the band solver does not apply and the factor fits — measured on a closed 500-pose loop
@@ -2028,7 +2153,9 @@ void Engine::solve_reduced(const double* rhs, double* y) {
         max_it = opt.max_linear_solver_iterations;
         min_it = opt.min_linear_solver_iterations;
     }
-    if (bandpc_active) {
+    if (wband_active) {
+        launch_wband_solve(stream, wband_view(rhs, y), d_pscal.p);
+    } else if (bandpc_active) {
         bandpc_solve(rhs, y);
     } else if (dense_active) {
         DenseView V;

@@ -123,6 +123,41 @@ struct DenseView {
 };
 int dense_panel_width();
 
+// K3e — exact solve of a WIDE block-banded reduced system (half-bandwidth 13 .. 64 blocks: tracks longer than 13
+// frames on a problem too large, or too sparse, for the dense factorisation), kernels_wband.cu.  The poses are cut
+// into C chunks with separators of w poses; every chunk is a bordered band (border rows = [left separator | right
+// separator | rhs]) factored in band storage with the dense solver's panel / DMMA kernels, all chunks per launch;
+// the separator system (block tridiagonal, dense storage) goes through the dense solver.
+constexpr int kWbandMaxW = 64;
+struct WbandView {
+    int n_free, w, C;            // free poses, half-bandwidth (blocks), chunks
+    int m_pad;                   // padded interior size of a chunk (scalars, a multiple of 48; the same for every chunk)
+    int sepw;                    // 6 w (0 when C == 1)
+    int nbr;                     // border rows: 2 sepw + 1 (the last one is the right-hand side)
+    int bwr;                     // scalar half-bandwidth 6 w + 5 rounded up to a multiple of 8
+    int ld;                      // band storage: element (i, j), i >= j, of a chunk at A[j * ld + i], ld = bwr + 48
+    int ldB;                     // border storage: (border row b, column j) at Bd[j * ldB + b]; columns m_pad + b' hold the
+                                 //   border x border Schur complement
+    long long a_stride, b_stride;  // doubles per chunk in A / Bd
+    const int *rowptr, *col;     // upper block-CSR of S
+    const double* S;
+    const double* rhs;           // [6 n_free]
+    const int* owner;            // per free pose: chunk c >= 0 (interior) or -(s + 1) (separator s)
+    const int* local;            // its index inside the chunk interior / the separator
+    const int* chunk_p0;         // [C] first pose of the chunk interior
+    const int* chunk_len;        // [C] interior poses
+    double* A;                   // [C][a_stride]
+    double* Bd;                  // [C][b_stride]
+    double* Ldiag;               // [C][m_pad / 48][48][48]
+    double* invd;                // [C][m_pad]
+    double* xw;                  // [C][m_pad]
+    double* xsep;                // [(C - 1) sepw] separator unknowns
+    DenseView T;                 // separator system (n = (C - 1) sepw; y = xsep)
+    double* Txw;                 // [T.n_pad] work vector of the dense solve
+    double* y;                   // [6 n_free] solution
+    int* fail;
+};
+
 struct SunBlockData {
     uint32_t cam;
     double obs_c[3], ref_g[3], W[4], az_thresh, zen_thresh, huber;
@@ -339,6 +374,13 @@ class Engine {
     int dense_npad = 0, dense_ld = 0;
     DBuf<double> d_dense_A, d_dense_Ld, d_dense_inv, d_dense_xw;
     void plan_dense_solver();
+    // wide-band direct solver (linear_solver == 0, S block-banded with 12 < half-bandwidth <= 64)
+    bool wband_active = false;
+    int wband_w = 0, wband_C = 0, wband_mpad = 0;
+    DBuf<int> d_wb_owner, d_wb_local, d_wb_p0, d_wb_len;
+    DBuf<double> d_wb_A, d_wb_Bd, d_wb_Ld, d_wb_inv, d_wb_xw, d_wb_xsep, d_wb_T, d_wb_TLd, d_wb_Tinv, d_wb_Txw;
+    WbandView wband_view(const double* rhs, double* y);
+    bool plan_wband_solver(int w);
     // extra scratch sets + streams so that independent solves against the same banded S run
     // concurrently (the border columns of the lighting solve): each solve is a latency-bound chain
     // on a handful of CTAs, so n_g + 1 of them fit side by side on 148 SMs

@@ -66,6 +66,11 @@ void launch_bpc_xpby(cudaStream_t s, long long n, const double* z, double beta, 
 void launch_bpc_update(cudaStream_t s, long long n, double alpha, const double* p, const double* q, double* x, double* r);
 // K3d — dense Cholesky of a reduced system that is not a narrow band (kernels_dense.cu); xw: [n_pad] work vector
 void launch_dense_solve(cudaStream_t s, const DenseView& V, double* xw, double* ps);
+// the factorisation and both substitutions of a dense system the caller has already written into V.A (lower triangle,
+// identity padding, rhs as row n_pad); does not reset V.fail and writes no status
+void launch_dense_factor(cudaStream_t s, const DenseView& V, double* xw);
+// K3e — wide block-banded reduced system: chunks as bordered bands + dense separator system (kernels_wband.cu)
+void launch_wband_solve(cudaStream_t s, const WbandView& V, double* ps);
 
 // K4 — Plus on the poses, back-substitution, model cost change, candidate cost
 void launch_pose_plus(cudaStream_t s, const DevView& v, const double* yp, double* poses_cand, double* scal2,

@@ -248,11 +248,8 @@ __global__ void dense_status_kernel(const int* fail, double* ps) {
 
 int dense_panel_width() { return DNB; }
 
-void launch_dense_solve(cudaStream_t s, const DenseView& V, double* xw, double* ps) {
-    CSLAM_CUDA(cudaMemsetAsync(V.fail, 0, sizeof(int), s));
-    CSLAM_CUDA(cudaMemsetAsync(V.A, 0, sizeof(double) * size_t(V.ld) * size_t(V.n_pad + 1), s));
-    dense_fill_kernel<<<V.n / 6, 128, 0, s>>>(V);
-    int launched = 1;
+void launch_dense_factor(cudaStream_t s, const DenseView& V, double* xw) {
+    int launched = 0;
     constexpr size_t smem_syrk = sizeof(double) * 2 * DNB * DSL;
     CSLAM_CUDA(cudaFuncSetAttribute(dense_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_syrk)));
     for (int j0 = 0; j0 < V.n_pad; j0 += DNB) {
@@ -272,9 +269,18 @@ void launch_dense_solve(cudaStream_t s, const DenseView& V, double* xw, double* 
         dense_backsolve_kernel<<<std::max(1, (j0 + 255) / 256), 256, 0, s>>>(V, j0, xw, V.y);
         ++launched;
     }
+    CSLAM_CUDA(cudaGetLastError());
+    g_kernel_launches.fetch_add(launched, std::memory_order_relaxed);
+}
+
+void launch_dense_solve(cudaStream_t s, const DenseView& V, double* xw, double* ps) {
+    CSLAM_CUDA(cudaMemsetAsync(V.fail, 0, sizeof(int), s));
+    CSLAM_CUDA(cudaMemsetAsync(V.A, 0, sizeof(double) * size_t(V.ld) * size_t(V.n_pad + 1), s));
+    dense_fill_kernel<<<V.n / 6, 128, 0, s>>>(V);
+    launch_dense_factor(s, V, xw);
     dense_status_kernel<<<1, 1, 0, s>>>(V.fail, ps);
     CSLAM_CUDA(cudaGetLastError());
-    g_kernel_launches.fetch_add(launched + 1, std::memory_order_relaxed);
+    g_kernel_launches.fetch_add(2, std::memory_order_relaxed);
 }
 
 }  // namespace cslam

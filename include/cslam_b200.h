@@ -51,7 +51,8 @@ typedef struct cslam_options {
     int jacobi_scaling;                     /* 1 */
     int linear_solver;      /* 0 = exact Schur solve (SPARSE_SCHUR-equivalent): block-banded Cholesky cut
                                into leaves + separators when the reduced system is banded (half-bandwidth
-                               <= 12 blocks), in-kernel dense Cholesky for windows, else PCG run to 1e-15;
+                               <= 12 blocks), chunked bordered-band / dense Cholesky beyond (dense_solver,
+                               bandpc_solver), in-kernel dense Cholesky for windows, else PCG run to 1e-15;
                                1 = ITERATIVE_SCHUR (PCG, Ceres Q-rule, eta) */
     int preconditioner;     /* 0 = JACOBI (block diag of B), 1 = SCHUR_JACOBI (block diag of S) */
     double eta;                             /* 0.1 */
@@ -78,10 +79,15 @@ typedef struct cslam_options {
                                DMMA tensor cores when 6 x free poses <= 12288, i.e. a factor of at most 1.2 GB;
                                PCG run to 1e-15 beyond that), 1 = dense whenever it fits (also instead of the
                                banded solver), -1 = never */
-    int bandpc_solver;      /* exact solve of a reduced system that is neither a narrow band nor small enough for the dense
-                               factorisation (long tracks / loop closures on a large problem): 0 = auto (conjugate gradients
-                               preconditioned with the banded direct solve of the short-track landmarks' part of the
-                               system, run to a 1e-15 residual), -1 = never (block-Jacobi PCG run to 1e-15) */
+    int bandpc_solver;      /* exact solve of a reduced system that is not a narrow band (tracks longer than 13 frames):
+                               0 = auto: a WIDE band (half-bandwidth 13 .. 64 blocks) on a trajectory long compared with it
+                               is factored exactly as chunks of bordered bands + a dense separator system (this also
+                               replaces the dense factorisation there); otherwise, when too large for the dense
+                               factorisation, conjugate gradients preconditioned with the banded direct solve of the
+                               short-track landmarks' part of the system, run to a 1e-15 residual;
+                               1 = the preconditioned conjugate gradients, never the wide-band factorisation;
+                               2 = the wide-band factorisation whenever the layout allows it (also on small problems);
+                               -1 = neither (dense factorisation if it fits, else block-Jacobi PCG run to 1e-15) */
 } cslam_options;
 
 typedef struct cslam_summary {

@@ -293,13 +293,45 @@ def test_ragged_track_groups(product, per_obs_W):
     assert rel_err(g[2], poses1) < 1e-9 and rel_err(g[3], points1) < 1e-9
 
 
+@pytest.mark.parametrize("case", ["ragged_2300", "ragged_small_forced", "one_chunk_forced", "regular_len20"])
+def test_wide_band_cholesky(product, case, capfd, monkeypatch):
+    """Tracks longer than 13 frames make the reduced system a WIDE band (half-bandwidth 13 .. 64 blocks): the exact
+    solve is the chunked bordered-band Cholesky of kernels_wband.cu (chunks + dense separator system) — one direct
+    solve per LM iteration, the oracle's trajectory."""
+    monkeypatch.setenv("CSLAM_DEBUG_SOLVER", "1")
+    kw = {}
+    if case == "ragged_2300":       # auto: long compared with the band
+        tr = syn.make_track(2300, 6, 6, seed=37, ragged=dict(mean=6, max=20, drop=0.1))
+    elif case == "ragged_small_forced":
+        tr = syn.make_track(300, 8, 6, seed=38, ragged=dict(mean=7, max=20, drop=0.1))
+        kw = dict(bandpc_solver=2)
+    elif case == "one_chunk_forced":
+        tr = syn.make_track(90, 12, 6, seed=39, ragged=dict(mean=12, max=20, drop=0.05))   # half-bandwidth 19
+        kw = dict(bandpc_solver=2)
+    else:                           # every landmark seen by 20 consecutive frames
+        tr = syn.make_track(400, 10, 20, seed=40)
+    g, o = solve_pair(tr, 4, **kw)
+    err = capfd.readouterr().err
+    assert "[solver] wide-band Cholesky" in err, err
+    if case == "one_chunk_forced":
+        assert " 1 chunks" in err, err
+    check_lm(g, o)
+    assert np.all(g[0].iteration_log()[1:, 7] == 1), "one direct solve per LM iteration"
+    if case == "ragged_small_forced":
+        # the dense factorisation (what this size takes without the override) gives the same iterates
+        p1, poses1, points1 = syn.build_problem(tr, bandpc_solver=1, **dict(FIXED, max_num_iterations=4))
+        p1.solve()
+        assert "[solver]" not in capfd.readouterr().err
+        assert rel_err(g[2], poses1) < 1e-9 and rel_err(g[3], points1) < 1e-9
+
+
 def test_band_preconditioned_cg(product):
     """Ragged tracks as a stereo front end produces them (lengths 2 .. 20 with drop-outs) on a problem too large for
     the dense factorisation: the reduced system is a band plus weak far blocks, and the exact solve is conjugate
     gradients preconditioned with the banded direct solver (band-truncated, diagonally compensated system) run to a
     1e-15 residual — the oracle's exact trajectory in a handful of iterations per solve instead of thousands."""
     tr = syn.make_track(2300, 6, 6, seed=37, ragged=dict(mean=6, max=20, drop=0.1))
-    g, o = solve_pair(tr, 4)
+    g, o = solve_pair(tr, 4, bandpc_solver=1)
     check_lm(g, o)
     lin = g[0].iteration_log()[1:, 7]
     assert lin.min() >= 2 and lin.max() <= 400, lin   # (block-Jacobi PCG needs several thousand here)
