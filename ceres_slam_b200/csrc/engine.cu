@@ -1521,6 +1521,7 @@ bool Engine::plan_wband_solver(int w) {
     wband_w = w;
     wband_C = C;
     wband_mpad = m_pad;
+    wband_rstart = C > 1 ? 6 * (base - w) / nb * nb : 0;   // the right separator couples to a chunk's last w poses only
     d_wb_owner.upload(owner, stream);
     d_wb_local.upload(local, stream);
     d_wb_p0.upload(p0, stream);
@@ -1528,13 +1529,11 @@ bool Engine::plan_wband_solver(int w) {
     d_wb_A.alloc(a_stride * C, stream);
     d_wb_Bd.alloc(b_stride * C, stream);
     d_wb_Ld.alloc(size_t(C) * (m_pad / nb) * nb * nb, stream);
-    d_wb_inv.alloc(size_t(C) * m_pad, stream);
     d_wb_xw.alloc(size_t(C) * m_pad, stream);
     if (C > 1) {
         d_wb_xsep.alloc(ns, stream);
         d_wb_T.alloc((ns_pad + 8) * (ns_pad + 1), stream);
         d_wb_TLd.alloc((ns_pad / nb) * nb * nb, stream);
-        d_wb_Tinv.alloc(ns_pad, stream);
         d_wb_Txw.alloc(ns_pad, stream);
     }
     if (!d_band_fail.p) d_band_fail.alloc(1, stream);
@@ -1557,6 +1556,7 @@ WbandView Engine::wband_view(const double* rhs, double* y) {
     V.bwr = (6 * wband_w + 5 + 7) / 8 * 8;
     V.ld = V.bwr + nb;
     V.ldB = V.nbr + (V.nbr & 1);
+    V.r_start = wband_rstart;
     V.a_stride = (long long)V.m_pad * (V.ld + 1) + 2;
     V.b_stride = (long long)(V.m_pad + V.ldB) * V.ldB;
     V.rowptr = d_s_rowptr.p;
@@ -1570,7 +1570,6 @@ WbandView Engine::wband_view(const double* rhs, double* y) {
     V.A = d_wb_A.p;
     V.Bd = d_wb_Bd.p;
     V.Ldiag = d_wb_Ld.p;
-    V.invd = d_wb_inv.p;
     V.xw = d_wb_xw.p;
     V.xsep = d_wb_xsep.p;
     V.T.n = (wband_C - 1) * V.sepw;
@@ -1582,7 +1581,6 @@ WbandView Engine::wband_view(const double* rhs, double* y) {
     V.T.rhs = nullptr;
     V.T.A = d_wb_T.p;
     V.T.Ldiag = d_wb_TLd.p;
-    V.T.invd = d_wb_Tinv.p;
     V.T.y = d_wb_xsep.p;
     V.T.fail = d_band_fail.p;
     V.Txw = d_wb_Txw.p;
@@ -1678,7 +1676,6 @@ void Engine::plan_dense_solver() {
     dense_ld = dense_npad + 8;
     d_dense_A.alloc(size_t(dense_ld) * size_t(dense_npad + 1), stream);
     d_dense_Ld.alloc(size_t(dense_npad / nb) * nb * nb, stream);
-    d_dense_inv.alloc(size_t(dense_npad), stream);
     d_dense_xw.alloc(size_t(dense_npad), stream);
     if (!d_band_fail.p) d_band_fail.alloc(1, stream);
     dense_active = true;
@@ -2168,7 +2165,6 @@ void Engine::solve_reduced(const double* rhs, double* y) {
         V.rhs = rhs;
         V.A = d_dense_A.p;
         V.Ldiag = d_dense_Ld.p;
-        V.invd = d_dense_inv.p;
         V.y = y;
         V.fail = d_band_fail.p;
         launch_dense_solve(stream, V, d_dense_xw.p, d_pscal.p);

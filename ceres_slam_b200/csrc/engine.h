@@ -116,8 +116,7 @@ struct DenseView {
     const double* S;
     const double* rhs;           // [n]
     double* A;                   // [n_pad + 1][ld]
-    double* Ldiag;               // [n_pad / 48][48][48] factors of the diagonal blocks
-    double* invd;                // [n_pad] 1 / L[k][k]
+    double* Ldiag;               // [n_pad / 48][48][48]: L11^-T of every diagonal block, [c][i] = (L11^-T)[i][c]
     double* y;                   // [n] solution
     int* fail;
 };
@@ -133,7 +132,8 @@ struct WbandView {
     int n_free, w, C;            // free poses, half-bandwidth (blocks), chunks
     int m_pad;                   // padded interior size of a chunk (scalars, a multiple of 48; the same for every chunk)
     int sepw;                    // 6 w (0 when C == 1)
-    int nbr;                     // border rows: 2 sepw + 1 (the last one is the right-hand side)
+    int nbr;                     // border rows: 2 sepw + 1, [left separator | rhs | right separator]
+    int r_start;                 // first panel column from which the right separator's rows take part
     int bwr;                     // scalar half-bandwidth 6 w + 5 rounded up to a multiple of 8
     int ld;                      // band storage: element (i, j), i >= j, of a chunk at A[j * ld + i], ld = bwr + 48
     int ldB;                     // border storage: (border row b, column j) at Bd[j * ldB + b]; columns m_pad + b' hold the
@@ -148,8 +148,7 @@ struct WbandView {
     const int* chunk_len;        // [C] interior poses
     double* A;                   // [C][a_stride]
     double* Bd;                  // [C][b_stride]
-    double* Ldiag;               // [C][m_pad / 48][48][48]
-    double* invd;                // [C][m_pad]
+    double* Ldiag;               // [C][m_pad / 48][48][48]: L11^-T of every diagonal block, [c][i] = (L11^-T)[i][c]
     double* xw;                  // [C][m_pad]
     double* xsep;                // [(C - 1) sepw] separator unknowns
     DenseView T;                 // separator system (n = (C - 1) sepw; y = xsep)
@@ -372,13 +371,13 @@ class Engine {
     // dense direct solver (linear_solver == 0, S not banded, small or dense enough)
     bool dense_active = false;
     int dense_npad = 0, dense_ld = 0;
-    DBuf<double> d_dense_A, d_dense_Ld, d_dense_inv, d_dense_xw;
+    DBuf<double> d_dense_A, d_dense_Ld, d_dense_xw;
     void plan_dense_solver();
     // wide-band direct solver (linear_solver == 0, S block-banded with 12 < half-bandwidth <= 64)
     bool wband_active = false;
-    int wband_w = 0, wband_C = 0, wband_mpad = 0;
+    int wband_w = 0, wband_C = 0, wband_mpad = 0, wband_rstart = 0;
     DBuf<int> d_wb_owner, d_wb_local, d_wb_p0, d_wb_len;
-    DBuf<double> d_wb_A, d_wb_Bd, d_wb_Ld, d_wb_inv, d_wb_xw, d_wb_xsep, d_wb_T, d_wb_TLd, d_wb_Tinv, d_wb_Txw;
+    DBuf<double> d_wb_A, d_wb_Bd, d_wb_Ld, d_wb_xw, d_wb_xsep, d_wb_T, d_wb_TLd, d_wb_Txw;
     WbandView wband_view(const double* rhs, double* y);
     bool plan_wband_solver(int w);
     // extra scratch sets + streams so that independent solves against the same banded S run

@@ -20,9 +20,10 @@
 //                        slabs staged in shared memory; the 8 x 8 accumulator tile is computed
 //                        TRANSPOSED so that a lane's two values are consecutive rows of one column,
 //                        i.e. one 16-byte read-modify-write of the column-major matrix.
-//   dense_backsolve_kernel  L^T x = y from the last panel up: each CTA solves the 48 x 48 triangle
-//                        (again redundantly) and subtracts the panel's contribution from its 256
-//                        columns to the left.
+//   dense_backsolve_kernel  L^T x = y from the last panel up: each CTA forms L11^-T times the panel's entries
+//                        (the panel kernel solved 48 unit-vector rows along with the others, so the inverse
+//                        of the diagonal block is there: a product instead of a 48-step triangular solve) and
+//                        subtracts the panel's contribution from its 256 columns to the left.
 //
 // Work is n^3 / 3 flops (n = 6 x free poses), all of the O(n^3) part inside the DMMA kernel; it is
 // chosen over PCG only when the system is small or dense (engine.cu plan_dense_solver).
@@ -118,27 +119,21 @@ __global__ void __launch_bounds__(DPT, 1) dense_panel_kernel(DenseView V, int j0
         mbar_arrive(done1 + B - 1);
         if (__any_sync(0xffffffffu, bad) && lane == 0) *V.fail = 1;
     } else {
-        // one row of the panel below the diagonal block per thread (the last one is the right-hand side)
-        const int i = j0 + B + blockIdx.x * DPR + (warp - 2) * 32 + lane;
-        const bool valid = i <= V.n_pad;
+        // one row of the panel below the diagonal block per thread (the last one is the right-hand side); 48 more
+        // "rows" are the unit vectors: their solutions are the rows of L11^-T, which the back-substitution applies as
+        // a product instead of a 48-step triangular solve.  Ld[panel][c][i] = (L11^-T)[i][c]
+        const int rows = V.n_pad + 1 - (j0 + B);
+        const int rl = blockIdx.x * DPR + (warp - 2) * 32 + lane;
+        const bool valid = rl < rows + B;
+        double* rowp = rl < rows ? Ap + j0 + B + rl : V.Ldiag + (long long)(j0 / B) * B * B + (rl - rows);
+        const int stride = rl < rows ? int(ld) : B;
         double x[B];
 #pragma unroll
-        for (int c = 0; c < B; ++c) x[c] = valid ? Ap[c * ld + i] : 0.0;
-        double* outp = valid ? Ap + i : nullptr;
-        odd2_border_phase<B, B>(x, 0, 16, Lt2, sInv, done1, outp, int(ld));
-        odd2_border_phase<B, B - 16>(x, 16, 32, Lt2, sInv, done1, outp, int(ld));
-        odd2_border_phase<B, B - 32>(x, 32, B, Lt2, sInv, done1, outp, int(ld));
-    }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        // the factor of the diagonal block goes to its own buffer (the other CTAs of this launch may still be
-        // reading the block itself): Ld[panel][k][r] = L[r][k] = Lt2[(k + 1) * B + r - k - 1], 1 / L[k][k] = sInv[k]
-        double* Ld = V.Ldiag + (long long)(j0 / B) * B * B;
-        for (int idx = tid; idx < B * B; idx += DPT) {
-            const int k = idx / B, r = idx % B;
-            if (r > k) Ld[idx] = Lt2[(k + 1) * B + (r - k - 1)];
-        }
-        if (tid < B) V.invd[j0 + tid] = sInv[tid];
+        for (int c = 0; c < B; ++c) x[c] = !valid ? 0.0 : rl < rows ? rowp[(long long)c * stride] : (c == rl - rows ? 1.0 : 0.0);
+        double* outp = valid ? rowp : nullptr;
+        odd2_border_phase<B, B>(x, 0, 16, Lt2, sInv, done1, outp, stride);
+        odd2_border_phase<B, B - 16>(x, 16, 32, Lt2, sInv, done1, outp, stride);
+        odd2_border_phase<B, B - 32>(x, 32, B, Lt2, sInv, done1, outp, stride);
     }
 }
 
@@ -163,10 +158,24 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(DenseView V, int j0) {
     while ((long long)I * (I + 1) / 2 > blockIdx.x) --I;
     const int J = blockIdx.x - I * (I + 1) / 2;
     const double* Ap = V.A + j0 * ld + t0;
-    for (int idx = tid; idx < DNB * 64; idx += 256) {
-        const int k = idx >> 6, i = idx & 63;
-        Lr[k * DSL + i] = 64 * I + i < m ? Ap[k * ld + 64 * I + i] : 0.0;
-        Lc[k * DSL + i] = 64 * J + i < m ? Ap[k * ld + 64 * J + i] : 0.0;
+    {
+        // every thread stages 12 entries of each slab: row i = tid & 63, panel columns k = (tid >> 6) + 4 t.  All 24
+        // loads are issued before the first store (a loop with a store per load serialises on the load latency)
+        const int i = tid & 63, kq = tid >> 6;
+        const bool okr = 64 * I + i < m, okc = 64 * J + i < m;
+        const double* pr = Ap + kq * ld + 64 * I + i;
+        const double* pc = Ap + kq * ld + 64 * J + i;
+        double vr[12], vc[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+            vr[t] = okr ? pr[4 * t * ld] : 0.0;
+            vc[t] = okc ? pc[4 * t * ld] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+            Lr[(kq + 4 * t) * DSL + i] = vr[t];
+            Lc[(kq + 4 * t) * DSL + i] = vc[t];
+        }
     }
     __syncthreads();
     // warp = column tile jt of the 64 x 64 block; the transposed accumulator D[m][n] = C[i = 8 it + n][j = 8 jt + m]
@@ -186,56 +195,78 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(DenseView V, int j0) {
     const int j = 64 * J + 8 * jt + g;
     if (j < m) {
         double* Cc = V.A + (long long)(t0 + j) * ld + t0;
+        // read-modify-write of the lane's eight row pairs: all loads first, then all stores
+        double2 cv[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int i = 64 * I + 8 * it + 2 * q;  // two consecutive rows of column j
-            if (i + 1 < m) {
-                double2* p = reinterpret_cast<double2*>(Cc + i);
-                double2 c = *p;
-                c.x -= acc[it][0];
-                c.y -= acc[it][1];
-                *p = c;
-            } else if (i < m) {
-                Cc[i] -= acc[it][0];
-            }
+            cv[it] = make_double2(0.0, 0.0);
+            if (i + 1 < m)
+                cv[it] = *reinterpret_cast<const double2*>(Cc + i);
+            else if (i < m)
+                cv[it].x = Cc[i];
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = 64 * I + 8 * it + 2 * q;
+            cv[it].x -= acc[it][0];
+            cv[it].y -= acc[it][1];
+            if (i + 1 < m)
+                *reinterpret_cast<double2*>(Cc + i) = cv[it];
+            else if (i < m)
+                Cc[i] = cv[it].x;
         }
     }
 }
 
 // Panel j0 of L^T x = y.  xw: work vector (entries right of the panel are final, the panel's own have every
-// later panel's contribution subtracted already).  Every CTA solves the 48 x 48 triangle; CTA c then updates
-// columns [256 c, 256 c + 256) left of the panel.
+// later panel's contribution subtracted already).  Every CTA forms x_panel = L11^-T xw_panel (the inverse the panel
+// kernel left behind); CTA c then updates columns [256 c, 256 c + 256) left of the panel.
 __global__ void __launch_bounds__(256) dense_backsolve_kernel(DenseView V, int j0, double* xw, double* y) {
     constexpr int B = DNB;
-    __shared__ double Ls[B * (B + 1)];  // Ls[c][k] = L[j0 + c][j0 + k], c > k
-    __shared__ double xs[B], inv[B];
+    __shared__ double Ls[B * (B + 1)];   // Ls[c][i] = (L11^-T)[i][c] (zero for c < i), row stride B + 1
+    __shared__ double ts[B], xs[B];
     const int tid = threadIdx.x;
     const long long ld = V.ld;
     if (*V.fail) return;
-    const double* Ld = V.Ldiag + (long long)(j0 / B) * B * B;
-    for (int idx = tid; idx < B * B; idx += 256) {
-        const int k = idx / B, c = idx % B;
-        if (c > k) Ls[c * (B + 1) + k] = Ld[idx];
-    }
-    if (tid < B) inv[tid] = V.invd[j0 + tid];
-    double t = tid < B ? xw[j0 + tid] : 0.0;
-    __syncthreads();
-    if (tid < 64) {
-        for (int c = B - 1; c >= 0; --c) {
-            if (tid == c) xs[c] = t * inv[c];
-            asm volatile("bar.sync 1, 64;" ::: "memory");
-            if (tid < c) t -= Ls[c * (B + 1) + tid] * xs[c];
+    const double* Li = V.Ldiag + (long long)(j0 / B) * B * B;
+    {
+        double lv[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) lv[t] = Li[tid + 256 * t];   // 48 * 48 = 9 * 256
+        if (tid < B) ts[tid] = xw[j0 + tid];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int idx = tid + 256 * t;
+            Ls[(idx / B) * (B + 1) + idx % B] = lv[t];
         }
+    }
+    __syncthreads();
+    if (tid < 4 * B) {
+        // four lanes per row i: c = q, q + 4, ...
+        const int i = tid >> 2, q = tid & 3;
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < B; c += 4) a = fma(Ls[(c + q) * (B + 1) + i], ts[c + q], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (q == 0) xs[i] = a;
     }
     __syncthreads();
     if (blockIdx.x == 0 && tid < B && j0 + tid < V.n) y[j0 + tid] = xs[tid];
     const int j = blockIdx.x * 256 + tid;
     if (j < j0) {
-        const double* Lj = V.A + j * ld + j0;  // L[j0 .. j0 + 47][j]: contiguous
-        double d = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < B; ++k) d += Lj[k] * xs[k];
-        xw[j] -= d;
+        const double2* Lj = reinterpret_cast<const double2*>(V.A + j * ld + j0);  // L[j0 .. j0 + 47][j]: contiguous
+        double2 l[B / 2];
+#pragma unroll
+        for (int k = 0; k < B / 2; ++k) l[k] = Lj[k];
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < B / 2; ++k) {
+            d0 = fma(l[k].x, xs[2 * k], d0);
+            d1 = fma(l[k].y, xs[2 * k + 1], d1);
+        }
+        xw[j] -= d0 + d1;
     }
 }
 
@@ -254,7 +285,7 @@ void launch_dense_factor(cudaStream_t s, const DenseView& V, double* xw) {
     CSLAM_CUDA(cudaFuncSetAttribute(dense_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_syrk)));
     for (int j0 = 0; j0 < V.n_pad; j0 += DNB) {
         const int rows = V.n_pad + 1 - (j0 + DNB);  // rows below the diagonal block (>= 1: the right-hand side)
-        dense_panel_kernel<<<(rows + DPR - 1) / DPR, DPT, 0, s>>>(V, j0);
+        dense_panel_kernel<<<(rows + DNB + DPR - 1) / DPR, DPT, 0, s>>>(V, j0);   // + the 48 unit-vector rows
         ++launched;
         if (j0 + DNB < V.n_pad) {
             const long long T = (rows + 63) / 64;

@@ -10,17 +10,22 @@
 // is factored as a BORDERED band
 //
 //        [ B_c   Y^T ]      B_c: the chunk's interior (band, LAPACK-style band storage: element (i, j) at A[j ld + i])
-//        [ Y     D'  ]      border rows: [ left separator (6w) | right separator (6w) | right-hand side (1) ]
+//        [ Y     D'  ]      border rows: [ left separator (6w) | right-hand side (1) | right separator (6w) ]
 //
 // with the dense solver's machinery, 48 columns per panel, ALL chunks in every launch (blockIdx.y = chunk):
 //   wband_panel_kernel   the 48 x 48 diagonal block on the pivot-chain code of chol_chain.cuh, every other thread owns
 //                        one row below it — band rows and border rows alike — and solves l L11^T = a in registers;
+//                        48 more "rows" are the unit vectors: their solutions are L11^-T, which turns the
+//                        back-substitution's triangular solve into a product;
 //   wband_syrk_kernel    trailing update on the FP64 tensor cores (mma.sync m8n8k4 / DMMA.8x8x4) over the panel's
 //                        local index space [band rows within reach | border rows]: band x band, border x band, and
 //                        border x border, which accumulates the chunk's Schur complement D' on its separators.
 // The separator system T = S_sep,sep + sum of the chunks' D' is block tridiagonal with blocks of 6w; it is small
-// ((C - 1) 6w unknowns) and goes through the dense solver as it is.  Then L^T x = y - Y_sep^T x_sep per chunk, panel
-// by panel from the last one up.  C ~ sqrt(n / 7w) balances the chunk chains against the separator solve.
+// ((C - 1) 6w unknowns) and goes through the dense solver as it is.  Then L^T x = y - Y_sep^T x_sep per chunk: ONE
+// launch, a CTA per chunk walks its panels from the last one up (48 x 48 product with L11^-T, then the update of the
+// bwr columns to the left).  The right separator couples to the chunk's last w poses only, so its border rows are
+// structurally zero — and skipped — until panel r_start.  C ~ sqrt(n / 7w) balances the chunk chains against the
+// separator solve.
 // Deterministic: every entry has one owner per launch, the separator assembly is a gather.
 //
 // scripts/wband_model.py is the numpy model of exactly this layout and loop structure.
@@ -56,7 +61,7 @@ __global__ void wband_fill_kernel(WbandView V) {
             const int i = 6 * lb + c, j = 6 * la + r;
             if (i >= j) V.A[oa * V.a_stride + (long long)j * V.ld + i] = v;
         } else if (oa >= 0 && ob == -(oa + 1)) {      // the separator right of a's chunk
-            V.Bd[oa * V.b_stride + (long long)(6 * la + r) * V.ldB + V.sepw + 6 * lb + c] = v;
+            V.Bd[oa * V.b_stride + (long long)(6 * la + r) * V.ldB + V.sepw + 1 + 6 * lb + c] = v;
         } else if (oa < 0 && ob == -oa) {             // a in separator s = -oa - 1, b in chunk s + 1: its left separator
             V.Bd[ob * V.b_stride + (long long)(6 * lb + c) * V.ldB + 6 * la + r] = v;
         } else if (oa < 0 && ob == oa) {
@@ -70,7 +75,7 @@ __global__ void wband_fill_kernel(WbandView V) {
     if (threadIdx.x < 6) {
         const int r = threadIdx.x;
         if (oa >= 0)
-            V.Bd[oa * V.b_stride + (long long)(6 * la + r) * V.ldB + 2 * V.sepw] = V.rhs[6ll * a + r];
+            V.Bd[oa * V.b_stride + (long long)(6 * la + r) * V.ldB + V.sepw] = V.rhs[6ll * a + r];
         else
             V.T.A[((-oa - 1) * V.sepw + 6 * la + r) * ldT + V.T.n_pad] = V.rhs[6ll * a + r];
     }
@@ -89,7 +94,8 @@ __global__ void wband_pad_kernel(WbandView V) {
     }
 }
 
-// rows of the panel at j0: band rows [t0, t0 + mb) of the chunk, then the border rows
+// rows of the panel at j0: band rows [t0, t0 + mb) of the chunk, then the border rows [left separator | rhs | right
+// separator] — the right separator's only from panel r_start on (structurally zero before)
 struct PanelRows {
     int t0, mb, m;
 };
@@ -97,7 +103,7 @@ __device__ __forceinline__ PanelRows panel_rows(const WbandView& V, int j0) {
     PanelRows p;
     p.t0 = j0 + WNB;
     p.mb = min(V.bwr, V.m_pad - p.t0);
-    p.m = p.mb + V.nbr;
+    p.m = p.mb + (j0 >= V.r_start ? V.nbr : V.sepw + 1);
     return p;
 }
 
@@ -164,33 +170,27 @@ __global__ void __launch_bounds__(WPT, 1) wband_panel_kernel(WbandView V, int j0
         // one row below the diagonal block per thread: a band row, or a border row (separator / right-hand side)
         const PanelRows P = panel_rows(V, j0);
         const int rl = blockIdx.x * WPR + (warp - 2) * 32 + lane;
-        const bool valid = rl < P.m;
+        const bool valid = rl < P.m + B;
         double* rowp;
         int stride;
         if (rl < P.mb) {
             rowp = Ap + P.t0 + rl;
             stride = int(ld);
-        } else {
+        } else if (rl < P.m) {
             rowp = V.Bd + ch * V.b_stride + (long long)j0 * V.ldB + (rl - P.mb);
             stride = V.ldB;
+        } else {
+            // unit vector e_i, i = rl - m: its row of solutions is row i of L11^-T; Ld[chunk][panel][c][i]
+            rowp = V.Ldiag + ((long long)ch * (V.m_pad / B) + j0 / B) * B * B + (rl - P.m);
+            stride = B;
         }
         double x[B];
 #pragma unroll
-        for (int c = 0; c < B; ++c) x[c] = valid ? rowp[(long long)c * stride] : 0.0;
+        for (int c = 0; c < B; ++c) x[c] = !valid ? 0.0 : rl < P.m ? rowp[(long long)c * stride] : (c == rl - P.m ? 1.0 : 0.0);
         double* outp = valid ? rowp : nullptr;
         odd2_border_phase<B, B>(x, 0, 16, Lt2, sInv, done1, outp, stride);
         odd2_border_phase<B, B - 16>(x, 16, 32, Lt2, sInv, done1, outp, stride);
         odd2_border_phase<B, B - 32>(x, 32, B, Lt2, sInv, done1, outp, stride);
-    }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        // Ld[chunk][panel][k][r] = L[r][k] = Lt2[(k + 1) * B + r - k - 1], 1 / L[k][k] = sInv[k]
-        double* Ld = V.Ldiag + ((long long)ch * (V.m_pad / B) + j0 / B) * B * B;
-        for (int idx = tid; idx < B * B; idx += WPT) {
-            const int k = idx / B, r = idx % B;
-            if (r > k) Ld[idx] = Lt2[(k + 1) * B + (r - k - 1)];
-        }
-        if (tid < B) V.invd[(long long)ch * V.m_pad + j0 + tid] = sInv[tid];
     }
 }
 
@@ -221,11 +221,25 @@ __global__ void __launch_bounds__(256) wband_syrk_kernel(WbandView V, int j0) {
     double* Bb = V.Bd + ch * V.b_stride;
     const double* Apan = Ab + j0 * ld + t0;        // band rows of the panel: Apan[k * ld + l]
     const double* Bpan = Bb + j0 * ldB - mb;       // border rows of the panel: Bpan[k * ldB + l]
-    for (int idx = tid; idx < WNB * 64; idx += 256) {
-        const int k = idx >> 6, i = idx & 63;
+    {
+        // every thread stages 12 entries of each slab: row i = tid & 63, panel columns k = (tid >> 6) + 4 t.  All 24
+        // loads are issued before the first store (a loop with a store per load serialises on the load latency)
+        const int i = tid & 63, kq = tid >> 6;
         const int li = 64 * I + i, lj = 64 * J + i;
-        Lr[k * WSL + i] = li < m ? (li < mb ? Apan[k * ld + li] : Bpan[k * ldB + li]) : 0.0;
-        Lc[k * WSL + i] = lj < m ? (lj < mb ? Apan[k * ld + lj] : Bpan[k * ldB + lj]) : 0.0;
+        const double* pr = li < mb ? Apan + kq * ld + li : Bpan + kq * ldB + li;
+        const double* pc = lj < mb ? Apan + kq * ld + lj : Bpan + kq * ldB + lj;
+        const long long sr = 4 * (li < mb ? ld : ldB), sc = 4 * (lj < mb ? ld : ldB);
+        double vr[12], vc[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+            vr[t] = li < m ? pr[t * sr] : 0.0;
+            vc[t] = lj < m ? pc[t * sc] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+            Lr[(kq + 4 * t) * WSL + i] = vr[t];
+            Lc[(kq + 4 * t) * WSL + i] = vc[t];
+        }
     }
     __syncthreads();
     // warp = column tile jt of the 64 x 64 block; the transposed accumulator D[m][n] = C[i = 8 it + n][j = 8 jt + m]
@@ -247,22 +261,34 @@ __global__ void __launch_bounds__(256) wband_syrk_kernel(WbandView V, int j0) {
         // column j of the target: rows l < mb at colA[l], rows l >= mb at colB[l]
         double* colA = Ab + (long long)(t0 + j) * ld + t0;                                   // only when j < mb
         double* colB = Bb + (j < mb ? (long long)(t0 + j) : (long long)(V.m_pad + j - mb)) * ldB - mb;
+        // read-modify-write of the lane's eight row pairs: all loads first, then all stores
+        double2 cv[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int i = 64 * I + 8 * it + 2 * q;  // rows i, i + 1 of column j (mb is even: both band or both border)
+            cv[it] = make_double2(0.0, 0.0);
             if (i + 1 < j || i >= m) continue;      // above the diagonal / beyond the last row
+            const double* p = (i < mb ? colA : colB) + i;
+            if (i >= j && i + 1 < m)
+                cv[it] = *reinterpret_cast<const double2*>(p);
+            else if (i >= j)
+                cv[it].x = p[0];
+            else if (i + 1 < m)                     // i + 1 == j: the diagonal entry alone
+                cv[it].y = p[1];
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = 64 * I + 8 * it + 2 * q;
+            if (i + 1 < j || i >= m) continue;
             double* p = (i < mb ? colA : colB) + i;
-            if (i >= j && i + 1 < m) {
-                double2* p2 = reinterpret_cast<double2*>(p);
-                double2 c = *p2;
-                c.x -= acc[it][0];
-                c.y -= acc[it][1];
-                *p2 = c;
-            } else if (i >= j) {
-                p[0] -= acc[it][0];
-            } else if (i + 1 < m) {                 // i + 1 == j: the diagonal entry alone
-                p[1] -= acc[it][1];
-            }
+            cv[it].x -= acc[it][0];
+            cv[it].y -= acc[it][1];
+            if (i >= j && i + 1 < m)
+                *reinterpret_cast<double2*>(p) = cv[it];
+            else if (i >= j)
+                p[0] = cv[it].x;
+            else if (i + 1 < m)
+                p[1] = cv[it].y;
         }
     }
 }
@@ -278,15 +304,16 @@ __global__ void wband_sep_assemble_kernel(WbandView V) {
     const double* D1 = V.Bd + (sj + 1) * V.b_stride + (long long)V.m_pad * ldB;   // chunk sj + 1: its LEFT one
     double* Tc = V.T.A + gj * ldT;
     const int hi = min(ns, (sj + 2) * sepw);
+    const int R = sepw + 1;   // first right-separator border row
     for (int gi = gj + threadIdx.x; gi < hi; gi += blockDim.x) {
         const int si = gi / sepw, oi = gi % sepw;
         if (si == sj)
-            Tc[gi] += D0[(long long)(sepw + oj) * ldB + sepw + oi] + D1[(long long)oj * ldB + oi];
+            Tc[gi] += D0[(long long)(R + oj) * ldB + R + oi] + D1[(long long)oj * ldB + oi];
         else
-            Tc[gi] += D1[(long long)oj * ldB + sepw + oi];   // (separator sj + 1 is chunk sj + 1's right one)
+            Tc[gi] += D1[(long long)oj * ldB + R + oi];   // (separator sj + 1 is chunk sj + 1's right one)
     }
-    if (threadIdx.x == 0)
-        Tc[V.T.n_pad] += D0[(long long)(sepw + oj) * ldB + 2 * sepw] + D1[(long long)oj * ldB + 2 * sepw];
+    // right-hand side: border row sepw; against a right-separator row it is the COLUMN of the stored lower triangle
+    if (threadIdx.x == 0) Tc[V.T.n_pad] += D0[(long long)sepw * ldB + R + oj] + D1[(long long)oj * ldB + sepw];
 }
 
 // xw = y - Y_sep^T x_sep: one warp per column of a chunk
@@ -300,46 +327,85 @@ __global__ void __launch_bounds__(256) wband_backinit_kernel(WbandView V) {
     if (ch > 0)
         for (int b = lane; b < sepw; b += 32) d += col[b] * V.xsep[(ch - 1) * sepw + b];
     if (ch + 1 < V.C)
-        for (int b = lane; b < sepw; b += 32) d += col[sepw + b] * V.xsep[ch * sepw + b];
+        for (int b = lane; b < sepw; b += 32) d += col[sepw + 1 + b] * V.xsep[ch * sepw + b];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == 0) V.xw[(long long)ch * V.m_pad + j] = col[2 * sepw] - d;
+    if (lane == 0) V.xw[(long long)ch * V.m_pad + j] = col[sepw] - d;
 }
 
-// Panel j0 of L^T x = xw per chunk.  Every CTA solves the 48 x 48 triangle; CTA b then updates 256 of the bwr columns
-// left of the panel (further left the panel's rows are structurally zero).
-__global__ void __launch_bounds__(256) wband_backsolve_kernel(WbandView V, int j0) {
+// L^T x = xw, one CTA per chunk, panels from the last one up: x_panel = L11^-T xw_panel (a 48 x 48 product with the
+// inverse the panel kernel left behind, staged in shared memory one panel ahead), then the bwr columns left of the
+// panel lose the panel's contribution (further left the panel's rows are structurally zero).  One launch instead of
+// one per panel; a step costs two barriers and one round of global loads.
+constexpr int WBT = 512;   // threads of the back-substitution CTA
+__global__ void __launch_bounds__(WBT) wband_backsolve_kernel(WbandView V) {
     constexpr int B = WNB;
-    __shared__ double Ls[B * (B + 1)];  // Ls[c][k] = L[j0 + c][j0 + k], c > k
-    __shared__ double xs[B], inv[B];
-    const int tid = threadIdx.x, ch = blockIdx.y;
+    constexpr int NL = (B * B + WBT - 1) / WBT;   // entries of L11^-T per thread
+    __shared__ double Ls[B * (B + 1)];            // Ls[c][i] = (L11^-T)[i][c] (zero for c < i), row stride B + 1
+    __shared__ double ts[B], xs[B];
+    const int tid = threadIdx.x, ch = blockIdx.x;
     const long long ld = V.ld;
     if (*V.fail) return;
     double* xw = V.xw + (long long)ch * V.m_pad;
-    const double* Ld = V.Ldiag + ((long long)ch * (V.m_pad / B) + j0 / B) * B * B;
-    for (int idx = tid; idx < B * B; idx += 256) {
-        const int k = idx / B, c = idx % B;
-        if (c > k) Ls[c * (B + 1) + k] = Ld[idx];
-    }
-    if (tid < B) inv[tid] = V.invd[(long long)ch * V.m_pad + j0 + tid];
-    double t = tid < B ? xw[j0 + tid] : 0.0;
-    __syncthreads();
-    if (tid < 64) {
-        for (int c = B - 1; c >= 0; --c) {
-            if (tid == c) xs[c] = t * inv[c];
-            asm volatile("bar.sync 1, 64;" ::: "memory");
-            if (tid < c) t -= Ls[c * (B + 1) + tid] * xs[c];
+    const double* Ach = V.A + ch * V.a_stride;
+    const double* Lch = V.Ldiag + (long long)ch * (V.m_pad / B) * B * B;
+    const int n_own = 6 * V.chunk_len[ch];
+    double* yo = V.y + 6ll * V.chunk_p0[ch];
+    double lnext[NL];
+    auto load_L = [&](int j0) {
+        const double* Li = Lch + (long long)(j0 / B) * B * B;
+#pragma unroll
+        for (int t = 0; t < NL; ++t) lnext[t] = tid + t * WBT < B * B ? Li[tid + t * WBT] : 0.0;
+    };
+    auto store_L = [&]() {
+#pragma unroll
+        for (int t = 0; t < NL; ++t) {
+            const int idx = tid + t * WBT;
+            if (idx < B * B) Ls[(idx / B) * (B + 1) + idx % B] = lnext[t];
         }
-    }
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < B && j0 + tid < 6 * V.chunk_len[ch]) V.y[6ll * V.chunk_p0[ch] + j0 + tid] = xs[tid];
-    const int j = j0 - V.bwr + blockIdx.x * 256 + tid;
-    if (j >= 0 && j < j0) {
-        const double* Lj = V.A + ch * V.a_stride + j * ld + j0;  // L[j0 .. j0 + 47][j]: contiguous
-        double d = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < B; ++k) d += Lj[k] * xs[k];
-        xw[j] -= d;
+    };
+    load_L(V.m_pad - B);
+    for (int j0 = V.m_pad - B; j0 >= 0; j0 -= B) {
+        store_L();
+        if (tid < B) ts[tid] = xw[j0 + tid];
+        __syncthreads();
+        if (j0 >= B) load_L(j0 - B);   // the next panel's inverse flies during this panel's product and update
+        if (tid < 4 * B) {
+            // four lanes per row i: c = q, q + 4, ...
+            const int i = tid >> 2, q = tid & 3;
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < B; c += 4) a = fma(Ls[(c + q) * (B + 1) + i], ts[c + q], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (q == 0) {
+                xs[i] = a;
+                if (j0 + i < n_own) yo[j0 + i] = a;
+            }
+        }
+        __syncthreads();
+        // two lanes per column j left of the panel: rows j0 .. j0 + 23 and j0 + 24 .. j0 + 47 (contiguous in memory)
+        for (int base = 0; base < 2 * V.bwr; base += WBT) {   // (warp-uniform trip count: the pair sum is a shuffle)
+            const int it = base + tid;
+            const int j = it < 2 * V.bwr ? j0 - V.bwr + (it >> 1) : -1, h = it & 1;
+            double d0 = 0.0, d1 = 0.0;
+            if (j >= 0) {
+                const double2* Lj = reinterpret_cast<const double2*>(Ach + j * ld + j0 + 24 * h);
+                double2 l[B / 4];
+#pragma unroll
+                for (int k = 0; k < B / 4; ++k) l[k] = Lj[k];
+#pragma unroll
+                for (int k = 0; k < B / 4; ++k) {
+                    d0 = fma(l[k].x, xs[24 * h + 2 * k], d0);
+                    d1 = fma(l[k].y, xs[24 * h + 2 * k + 1], d1);
+                }
+            }
+            double d = d0 + d1;
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            if (h == 0 && j >= 0) xw[j] -= d;
+        }
+        // (the next iteration's first barrier orders these xw updates before its reads of ts and the stores to Ls / xs)
+        __syncthreads();
     }
 }
 
@@ -371,8 +437,8 @@ void launch_wband_solve(cudaStream_t s, const WbandView& V, double* ps) {
     constexpr size_t smem_syrk = sizeof(double) * 2 * WNB * WSL;
     CSLAM_CUDA(cudaFuncSetAttribute(wband_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_syrk)));
     for (int j0 = 0; j0 < V.m_pad; j0 += WNB) {
-        const int mb = std::min(V.bwr, V.m_pad - (j0 + WNB)), m = mb + V.nbr;
-        wband_panel_kernel<<<dim3((m + WPR - 1) / WPR, V.C), WPT, 0, s>>>(V, j0);
+        const int mb = std::min(V.bwr, V.m_pad - (j0 + WNB)), m = mb + (j0 >= V.r_start ? V.nbr : V.sepw + 1);
+        wband_panel_kernel<<<dim3((m + WNB + WPR - 1) / WPR, V.C), WPT, 0, s>>>(V, j0);   // + the 48 unit-vector rows
         const int T = (m + 63) / 64;
         wband_syrk_kernel<<<dim3(T * (T + 1) / 2, V.C), 256, smem_syrk, s>>>(V, j0);
         launched += 2;
@@ -384,10 +450,8 @@ void launch_wband_solve(cudaStream_t s, const WbandView& V, double* ps) {
     }
     wband_backinit_kernel<<<dim3((V.m_pad + 7) / 8, V.C), 256, 0, s>>>(V);
     ++launched;
-    for (int j0 = V.m_pad - WNB; j0 >= 0; j0 -= WNB) {
-        wband_backsolve_kernel<<<dim3(std::max(1, (V.bwr + 255) / 256), V.C), 256, 0, s>>>(V, j0);
-        ++launched;
-    }
+    wband_backsolve_kernel<<<V.C, WBT, 0, s>>>(V);
+    ++launched;
     if (V.C > 1) {
         wband_sep_scatter_kernel<<<(V.T.n + 255) / 256, 256, 0, s>>>(V);
         ++launched;

@@ -1,6 +1,6 @@
 """numpy model of K3e (kernels_wband.cu): the exact solve of a WIDE block-banded reduced system, cut into C chunks
-with separators of w poses, every chunk factored as a bordered band (border rows = [left separator | right
-separator | rhs]) in LAPACK-style band storage, panels of 48 columns.  Same storage formulas and the same loop
+with separators of w poses, every chunk factored as a bordered band (border rows = [left separator | rhs |
+right separator]) in LAPACK-style band storage, panels of 48 columns.  Same storage formulas and the same loop
 structure as the CUDA kernels (fill -> per panel: factor + trailing update -> separator assembly -> dense
 separator solve -> per chunk back-substitution), so an indexing mistake shows up here, on the CPU.
 
@@ -35,6 +35,9 @@ def solve(S_blocks, rhs, n_free, w, C):
     BWR = (bw + 7) // 8 * 8
     ld = BWR + NB                      # band storage: element (i, j), i >= j, at A[j * ld + i]
     ldB = NBRP
+    # border rows: [left separator | rhs | right separator]; the right separator's rows stay zero until the chunk's
+    # last w poses, so panels before r_start carry only the first sepw + 1 border rows
+    r_start = 6 * (min(lens) - w) // NB * NB if C > 1 else 0
     A = np.zeros((C, m_pad * (ld + 1)))
     Bd = np.zeros((C, (m_pad + NBRP) * ldB))
     ns = (C - 1) * sepw
@@ -66,7 +69,8 @@ def solve(S_blocks, rhs, n_free, w, C):
                         A[owner[a], j * ld + i] = v
                 elif kind[a] == 0 and kind[b] == 1:       # right separator of a's chunk
                     assert owner[b] == owner[a]
-                    Bd[owner[a], (6 * local[a] + r) * ldB + sepw + 6 * local[b] + cc] = v
+                    assert 6 * local[a] + r >= r_start
+                    Bd[owner[a], (6 * local[a] + r) * ldB + sepw + 1 + 6 * local[b] + cc] = v
                 elif kind[a] == 1 and kind[b] == 0:       # left separator of b's chunk
                     assert owner[b] == owner[a] + 1
                     Bd[owner[b], (6 * local[b] + cc) * ldB + 6 * local[a] + r] = v
@@ -78,7 +82,7 @@ def solve(S_blocks, rhs, n_free, w, C):
     for c in range(C):
         for j in range(m_pad):
             if j < 6 * lens[c]:
-                Bd[c, j * ldB + 2 * sepw] = rhs[6 * p0[c] + j]
+                Bd[c, j * ldB + sepw] = rhs[6 * p0[c] + j]
             else:
                 A[c, j * ld + j] = 1.0
     for j in range(ns_pad):
@@ -100,7 +104,7 @@ def solve(S_blocks, rhs, n_free, w, C):
     for j0 in range(0, m_pad, NB):
         t0 = j0 + NB
         mb = min(BWR, m_pad - t0)
-        m = mb + nbr
+        m = mb + (nbr if j0 >= r_start else sepw + 1)
         for c in range(C):
             # panel kernel: diagonal block + rows below
             D = np.zeros((NB, NB))
@@ -137,10 +141,11 @@ def solve(S_blocks, rhs, n_free, w, C):
         for gi in range(gj, ns):
             si, oi = divmod(gi, sepw)
             if si == sj:
-                T[gi, gj] += dp(si, sepw + oi, sepw + oj) + dp(si + 1, oi, oj)
+                T[gi, gj] += dp(si, sepw + 1 + oi, sepw + 1 + oj) + dp(si + 1, oi, oj)
             elif si == sj + 1:
-                T[gi, gj] += dp(si, sepw + oi, oj)
-        T[ns_pad, gj] += dp(sj, 2 * sepw, sepw + oj) + dp(sj + 1, 2 * sepw, oj)
+                T[gi, gj] += dp(si, sepw + 1 + oi, oj)
+        # (rhs, R_j) lies ABOVE the diagonal of D' in this order: D' is symmetric, the kernels keep (R_j, rhs)
+        T[ns_pad, gj] += dp(sj, sepw + 1 + oj, sepw) + dp(sj + 1, sepw, oj)
 
     # ---- dense separator solve (K3d) ----
     xsep = np.zeros(ns)
@@ -151,15 +156,15 @@ def solve(S_blocks, rhs, n_free, w, C):
     # ---- back-substitution per chunk ----
     y = np.zeros(6 * n_free)
     for c in range(C):
-        xs = np.zeros(2 * sepw)
+        xs = np.zeros(nbr)       # (the rhs slot stays zero)
         if C > 1:
             if c > 0:
                 xs[:sepw] = xsep[(c - 1) * sepw:c * sepw]
             if c < C - 1:
-                xs[sepw:] = xsep[c * sepw:(c + 1) * sepw]
+                xs[sepw + 1:] = xsep[c * sepw:(c + 1) * sepw]
         xw = np.zeros(m_pad)
         for j in range(m_pad):
-            xw[j] = Bd[c, j * ldB + 2 * sepw] - Bd[c, j * ldB:j * ldB + 2 * sepw] @ xs
+            xw[j] = Bd[c, j * ldB + sepw] - Bd[c, j * ldB:j * ldB + nbr] @ xs
         for j0 in range(m_pad - NB, -1, -NB):
             L11 = Ldiag[c, j0 // NB]
             xp = np.linalg.solve(L11.T, xw[j0:j0 + NB])
