@@ -634,6 +634,50 @@ void Engine::build_structure() {
                 for (uint32_t k = 0; k < len; ++k) obs_user_h[size_t(roff[r]) + k] = ob[k];
             }
         });
+        // ---- wide-window slices (kernels.cu schur_wide_kernel): the landmarks no group took are mostly the long
+        // tracks.  A run of them (they are in first-camera order) whose cameras all lie inside [c0, c0 + 32), c0 the
+        // run's first camera, is eliminated as one S_win -= Z Z^T on the tensor cores instead of one RED per entry of
+        // every camera pair.  Not eligible: a camera twice, more than 32 observations, a span beyond the window.
+        wide_lo_h.clear(); wide_hi_h.clear(); wide_c0_h.clear();
+        wide_flag_h.assign(rest.size(), 0);
+        wide_obs0 = obs_cursor;
+        n_wide_lm = 0;
+        static const bool no_wide = std::getenv("CSLAM_NO_WIDE") != nullptr;   // A/B knob
+        if (want_ragged && opt.schur_path != 1 && !lighting_in_solve() && !no_wide) {
+            constexpr uint32_t kWin = 32;
+            constexpr size_t kMinSlice = 8, kMaxSlice = 1 << 14;
+            const size_t R = rest.size();
+            std::vector<uint32_t> firstc(R), lastc(R);
+            std::vector<uint8_t> elig(R);
+            parallel_chunks(R, 1 << 12, [&](int, size_t r0, size_t r1) {
+                for (size_t r = r0; r < r1; ++r) {
+                    const uint32_t a = rest[r], len = lm_len(a);
+                    const uint32_t* ob = lm_obs(a);
+                    bool ok = len >= 1 && len <= kWin;
+                    for (uint32_t k = 1; k < len && ok; ++k) ok = st_cam[ob[k]] > st_cam[ob[k - 1]];
+                    firstc[r] = len ? st_cam[ob[0]] : 0;
+                    lastc[r] = len ? st_cam[ob[len - 1]] : 0;
+                    elig[r] = ok && lastc[r] - firstc[r] < kWin;
+                }
+            });
+            for (size_t i = 0; i < R;) {
+                if (!elig[i]) {
+                    ++i;
+                    continue;
+                }
+                const uint32_t c0 = firstc[i];
+                size_t j = i;
+                while (j < R && elig[j] && firstc[j] >= c0 && lastc[j] < c0 + kWin && j - i < kMaxSlice) ++j;
+                if (j - i >= kMinSlice) {
+                    wide_lo_h.push_back(n_lm_grouped + int(i));
+                    wide_hi_h.push_back(n_lm_grouped + int(j));
+                    wide_c0_h.push_back(int(c0));
+                    for (size_t r = i; r < j; ++r) wide_flag_h[r] = 1;
+                    n_wide_lm += (long long)(j - i);
+                }
+                i = j > i ? j : i + 1;
+            }
+        }
     }
     bt.lap("  remaining landmarks");
 }
@@ -1086,9 +1130,16 @@ void Engine::launch_schur(const DevView& v, const LmDiag& dg) {
     if (!item_group_h.empty())
         launch_schur_grouped(stream, v, group_view(), n_items_small, n_items_rag, dg, d_S, d_Bdiag, d_bp, d_gp, d_gl.p, d_scal);
     // (the landmarks no group takes are mostly the long tracks: beyond the banded preconditioner's window)
-    if (n_lm > n_lm_grouped)
-        launch_schur_generic(stream, v, n_lm_grouped, n_lm, dg, bandpc_active ? d_S2.p : d_S, bandpc_active ? d_Bdiag2.p : d_Bdiag,
-                             d_bp, d_gp, d_gl.p, d_scal);
+    if (n_lm > n_lm_grouped) {
+        double* St = bandpc_active ? d_S2.p : d_S;
+        double* Bt = bandpc_active ? d_Bdiag2.p : d_Bdiag;
+        const bool wide = !wide_lo_h.empty();
+        if (wide)
+            launch_schur_wide(stream, v, n_lm_grouped, n_lm, d_wide_flag.p, int(wide_lo_h.size()), d_wide_lo.p, d_wide_hi.p,
+                              d_wide_c0.p, wide_obs0, d_wide_Z.p, dg, St, Bt, d_bp, d_gp, d_gl.p, d_scal);
+        if (!wide || n_wide_lm < (long long)(n_lm - n_lm_grouped))
+            launch_schur_generic(stream, v, n_lm_grouped, n_lm, wide ? d_wide_flag.p : nullptr, dg, St, Bt, d_bp, d_gp, d_gl.p, d_scal);
+    }
 }
 
 void Engine::upload() {
@@ -1255,6 +1306,17 @@ void Engine::upload() {
     up_i(d_g_blk_off, g_blk_off_h);
     up_i(d_g_blk, g_blk_h);
     up_i(d_g_map_off, g_map_off_h);
+    if (structure_on_device) {   // (the device analysis forms no wide-window slices)
+        wide_lo_h.clear(); wide_hi_h.clear(); wide_c0_h.clear(); wide_flag_h.clear();
+        n_wide_lm = 0;
+    }
+    if (!wide_lo_h.empty()) {
+        up_i(d_wide_lo, wide_lo_h);
+        up_i(d_wide_hi, wide_hi_h);
+        up_i(d_wide_c0, wide_c0_h);
+        d_wide_flag.upload(wide_flag_h, stream);
+        d_wide_Z.alloc(18 * size_t(std::max<long long>(n_obs - wide_obs0, 1)), stream);
+    }
     d_g_map.upload(g_map_h.empty() ? std::vector<unsigned char>(1, 0xff) : g_map_h, stream);
     // internal order <- caller's order, on the device
     const size_t no = size_t(std::max<long long>(n_obs, 1));

@@ -345,6 +345,14 @@ class Engine {
     int max_group_L = 0, n_items_small = 0;
     GroupView group_view() const;
     void launch_schur(const DevView& v, const LmDiag& dg);
+    // wide-window slices (K2w): runs of ungrouped landmarks whose cameras fit [c0, c0 + 32); host analysis only
+    std::vector<int> wide_lo_h, wide_hi_h, wide_c0_h;
+    std::vector<uint8_t> wide_flag_h;      // per ungrouped landmark: 1 = in a slice
+    long long wide_obs0 = 0;               // first observation of the ungrouped landmarks
+    long long n_wide_lm = 0;
+    DBuf<int> d_wide_lo, d_wide_hi, d_wide_c0;
+    DBuf<uint8_t> d_wide_flag;
+    DBuf<double> d_wide_Z;                 // [observations of the ungrouped landmarks][18]
     DBuf<double> d_obs_u, d_obs_v, d_obs_d, d_obs_W;
     DBuf<double> d_sc_p, d_sc_l, d_cn_p, d_cn_l;
     DBuf<double> d_gl;                     // scaled point gradient from the last Schur pass

@@ -361,7 +361,7 @@ __device__ __forceinline__ void pair_to_S(const DevView& v, double* __restrict__
 }
 
 __global__ void __launch_bounds__(SG_WARPS * 32)
-    schur_generic_kernel(DevView v, int lm_lo, int lm_hi, LmDiag dg, double* __restrict__ S,
+    schur_generic_kernel(DevView v, int lm_lo, int lm_hi, const uint8_t* __restrict__ skip, LmDiag dg, double* __restrict__ S,
                          double* __restrict__ Bdiag, double* __restrict__ bp, double* __restrict__ gp,
                          double* __restrict__ gl, double* __restrict__ scal) {
     extern __shared__ __align__(128) unsigned char smem_sg[];
@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32)
     double cost = 0.0;
     const int warps_total = gridDim.x * SG_WARPS;
     for (int j = lm_lo + blockIdx.x * SG_WARPS + wib; j < lm_hi; j += warps_total) {
+        if (skip && skip[j - lm_lo]) continue;  // taken by the wide-window kernel
         const long long e0 = v.lm_base[j];
         const long long es = v.lm_stride[j];
         const int L = int(v.lm_cnt[j]);
@@ -489,6 +490,251 @@ __global__ void __launch_bounds__(SG_WARPS * 32)
         }
     }
     block_atomic_sum(cost, &scal[SC_COST], s_red);
+}
+
+// =============================================================================================
+// K2w — Schur build for LONG, ragged tracks: landmarks no group takes (more than 10 frames, or no companions) but
+// whose cameras fit a window of 32 consecutive poses.  The per-landmark kernel above issues one RED.ADD.F64 per
+// entry of every camera pair (7 560 for a track of 20 frames) and is bound by L2 atomics.  Here the elimination is
+// S_win -= Z Z^T per SLICE of such landmarks (consecutive in first-camera order, all inside [c0, c0 + 32)):
+//   schur_wide_produce_kernel  warp per landmark, lane per observation: pass 1 with warp sums, U_aa / gradient /
+//                              right-hand-side REDs as above, and Z_obs = W A (6 x 3, A A^T = V^-1) to global
+//                              memory, 18 doubles per observation;
+//   schur_wide_kernel          one CTA (10 warps) per slice: the whole 192 x 192 window tile stays in tensor-core
+//                              accumulators (300 upper MMA tiles: a 6 x 6 super-block per warp, 12 fragment loads
+//                              per 36 MMAs); batches of 20 landmarks: their Z
+//                              rows go to shared memory laid out [column][row] (6 rows per camera slot, rows of
+//                              cameras a landmark does not see are zero), DMMA m8n8k4 applies the batch's 60
+//                              columns; one flush per slice (entries that stayed zero are skipped).
+// Two kernels because the closed-form evaluation needs ~240 registers and the accumulators 76: together they spill.
+// =============================================================================================
+constexpr int WD_WIN = 32;                  // cameras in the window
+constexpr int WD_ROWS = 6 * WD_WIN;         // 192
+constexpr int WD_WARPS = 10;                // one per 6 x 6 super-block of the upper triangle of the 24 x 24 MMA tiles
+constexpr int WD_BATCH = 2 * WD_WARPS;      // landmarks per batch: two per warp
+constexpr int WD_ZS = WD_ROWS + 4;          // row stride of Z[column][row]: 4 mod 16 -> conflict-free fragment loads
+constexpr size_t WD_SMEM = sizeof(double) * 3 * WD_BATCH * WD_ZS;
+
+__global__ void __launch_bounds__(SG_WARPS * 32)
+    schur_wide_produce_kernel(DevView v, int lm_lo, int lm_hi, const uint8_t* __restrict__ wide, long long obs0, LmDiag dg,
+                              double* __restrict__ Zg, double* __restrict__ Bdiag, double* __restrict__ bp,
+                              double* __restrict__ gp, double* __restrict__ gl, double* __restrict__ scal) {
+    __shared__ double s_red[32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double cost = 0.0;
+    const int warps_total = gridDim.x * SG_WARPS;
+    for (int j = lm_lo + blockIdx.x * SG_WARPS + wib; j < lm_hi; j += warps_total) {
+        if (!wide[j - lm_lo]) continue;
+        const long long e0 = v.lm_base[j];
+        const long long es = v.lm_stride[j];
+        const int L = int(v.lm_cnt[j]);   // <= 32 (one observation per camera of the window)
+        const double p[3] = {v.points[3ll * j], v.points[3ll * j + 1], v.points[3ll * j + 2]};
+        const double sl[3] = {v.sc_l[3ll * j], v.sc_l[3ll * j + 1], v.sc_l[3ll * j + 2]};
+        double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
+        ObsEval o;
+        o.f = -1;
+        const long long e = e0 + lane * es;
+        if (lane < L) {
+            eval_obs_scaled(v, e, p, sl, o);
+            cost += 0.5 * (o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double a = o.Jp[3 * k], b = o.Jp[3 * k + 1], c = o.Jp[3 * k + 2];
+                V[0] += a * a;
+                V[1] += a * b;
+                V[2] += a * c;
+                V[3] += b * b;
+                V[4] += b * c;
+                V[5] += c * c;
+                gq[0] += a * o.r[k];
+                gq[1] += b * o.r[k];
+                gq[2] += c * o.r[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[k] = warp_sum(V[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gq[k] = warp_sum(gq[k]);
+        V[0] += fmin(fmax(V[0], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        V[3] += fmin(fmax(V[3], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        V[5] += fmin(fmax(V[5], dg.min_diag), dg.max_diag) * dg.inv_radius;
+        double Vi[6];
+        const bool pd = invert_sym3(V, Vi);
+        if (lane == 0) {
+            gl[3ll * j] = gq[0];
+            gl[3ll * j + 1] = gq[1];
+            gl[3ll * j + 2] = gq[2];
+            if (!pd) red_add(&scal[SC_INVALID], 1.0);
+        }
+        if (lane >= L) continue;
+        double Z[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) Z[k] = 0.0;
+        if (pd && o.f >= 0) {
+            double W[18], Y[18];
+            form_W(o, W);
+            form_Y(W, Vi, Y);
+            double* Bd = Bdiag + 36ll * o.f;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                for (int b = a; b < 6; ++b)
+                    red_add(&Bd[6 * a + b], o.Jc[a] * o.Jc[b] + o.Jc[6 + a] * o.Jc[6 + b] + o.Jc[12 + a] * o.Jc[12 + b]);
+                const double ga = o.Jc[a] * o.r[0] + o.Jc[6 + a] * o.r[1] + o.Jc[12 + a] * o.r[2];
+                const double yg = Y[3 * a] * gq[0] + Y[3 * a + 1] * gq[1] + Y[3 * a + 2] * gq[2];
+                red_add(&gp[6ll * o.f + a], ga);
+                red_add(&bp[6ll * o.f + a], ga - yg);
+            }
+            // A A^T = V^-1 (lower Cholesky factor of the inverse), Z = W A, stored [column][row]
+            const double a00 = sqrt(fmax(Vi[0], 0.0)), i00 = a00 > 0.0 ? 1.0 / a00 : 0.0;
+            const double a10 = Vi[1] * i00, a20 = Vi[2] * i00;
+            const double a11 = sqrt(fmax(Vi[3] - a10 * a10, 0.0)), i11 = a11 > 0.0 ? 1.0 / a11 : 0.0;
+            const double a21 = (Vi[4] - a20 * a10) * i11;
+            const double a22 = sqrt(fmax(Vi[5] - a20 * a20 - a21 * a21, 0.0));
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const double w0 = W[3 * r], w1 = W[3 * r + 1], w2 = W[3 * r + 2];
+                Z[r] = w0 * a00 + w1 * a10 + w2 * a20;
+                Z[6 + r] = w1 * a11 + w2 * a21;
+                Z[12 + r] = w2 * a22;
+            }
+        }
+        double2* out = reinterpret_cast<double2*>(Zg + 18 * (e - obs0));
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[k] = make_double2(Z[2 * k], Z[2 * k + 1]);
+    }
+    block_atomic_sum(cost, &scal[SC_COST], s_red);
+}
+
+__device__ __forceinline__ void wd_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// warp -> 6 x 6 super-block (wr, wc), wr <= wc, of the 4 x 4 grid of super-blocks over the 24 x 24 MMA tiles; ordered so
+// that the four schedulers (warp % 4) get 36 + 21 + 21, 36 + 21 + 21, 36 + 36, 36 + 36 tiles
+__device__ __forceinline__ void wd_super_block(int warp, int& wr, int& wc) {
+    constexpr unsigned WR = 0u | 0u << 2 | 0u << 4 | 1u << 6 | 0u << 8 | 2u << 10 | 1u << 12 | 2u << 14 | 1u << 16 | 3u << 18;
+    constexpr unsigned WC = 1u | 2u << 2 | 3u << 4 | 2u << 6 | 0u << 8 | 2u << 10 | 3u << 12 | 3u << 14 | 1u << 16 | 3u << 18;
+    wr = (WR >> (2 * warp)) & 3;
+    wc = (WC >> (2 * warp)) & 3;
+}
+
+__global__ void __launch_bounds__(WD_WARPS * 32, 1)
+    schur_wide_kernel(DevView v, int n_slices, const int* __restrict__ sl_lo, const int* __restrict__ sl_hi,
+                      const int* __restrict__ sl_c0, long long obs0, const double* __restrict__ Zg, double* __restrict__ S,
+                      double* __restrict__ scal) {
+    extern __shared__ __align__(16) double s_Z[];   // [3 * WD_BATCH][WD_ZS]
+    __shared__ int s_free[WD_WIN];
+    __shared__ int s_blk[WD_WIN * (WD_WIN + 1) / 2];   // pair (a <= b) -> block of S, -1: none
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    int wr, wc;
+    wd_super_block(warp, wr, wc);
+    const bool diag = wr == wc;
+    for (int sidx = blockIdx.x; sidx < n_slices; sidx += gridDim.x) {
+        const int lo = sl_lo[sidx], hi = sl_hi[sidx], c0 = sl_c0[sidx];
+        __syncthreads();   // (the previous slice's flush has read s_blk)
+        if (tid < WD_WIN) s_free[tid] = c0 + tid < v.n_cams ? v.cam_free[c0 + tid] : -1;
+        __syncthreads();
+        for (int pidx = tid; pidx < WD_WIN * (WD_WIN + 1) / 2; pidx += WD_WARPS * 32) {
+            // pair index -> (a, b), a <= b, row-major upper triangle of the 32 x 32 slot pairs
+            int a = 0, rem = pidx;
+            while (rem >= WD_WIN - a) {
+                rem -= WD_WIN - a;
+                ++a;
+            }
+            const int b = a + rem, fa = s_free[a], fb = s_free[b];
+            int e = -1;
+            if (fa >= 0 && fb >= 0) {
+                int l0 = v.s_rowptr[fa], h0 = v.s_rowptr[fa + 1];
+                while (l0 < h0) {
+                    const int mid = (l0 + h0) >> 1;
+                    if (v.s_col[mid] < fb)
+                        l0 = mid + 1;
+                    else
+                        h0 = mid;
+                }
+                if (l0 < v.s_rowptr[fa + 1] && v.s_col[l0] == fb) e = l0;
+            }
+            s_blk[pidx] = e;
+        }
+        // tile (i, jx) of the warp's super-block: MMA row tile 6 wr + i, column tile 6 wc + jx
+        double acc[6][6][2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) acc[i][jx][0] = acc[i][jx][1] = 0.0;
+
+        for (int b0 = lo; b0 < hi; b0 += WD_BATCH) {
+            const int nb = min(WD_BATCH, hi - b0);
+            __syncthreads();   // (the previous batch's MMAs have read Z)
+            for (int idx = tid; idx < 3 * WD_BATCH * WD_ZS; idx += WD_WARPS * 32) s_Z[idx] = 0.0;
+            __syncthreads();
+            // ---- stage: warp = landmark, lane = observation; its 18 doubles go to rows 6 slot .. + 5 of 3 columns ----
+            for (int l = warp; l < nb; l += WD_WARPS) {
+                const int j = b0 + l;
+                const int L = int(v.lm_cnt[j]);
+                if (lane < L) {
+                    const long long e = (long long)v.lm_base[j] + lane * (long long)v.lm_stride[j];
+                    const int slot = int(v.obs_cam[e]) - c0;
+                    const double2* in = reinterpret_cast<const double2*>(Zg + 18 * (e - obs0));
+                    if (slot >= 0 && slot < WD_WIN) {
+                        double* Zc = s_Z + (3 * l) * WD_ZS + 6 * slot;
+                        // entries 2k, 2k + 1 of [column][row 0..5]: column (2k) / 6, row (2k) % 6 (even: both in one column)
+                        double2 z[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) z[k] = in[k];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k)
+                            *reinterpret_cast<double2*>(Zc + ((2 * k) / 6) * WD_ZS + (2 * k) % 6) = z[k];
+                    } else {
+                        red_add(&scal[SC_INVALID], 1.0);   // (the slicing guarantees the window)
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- consume: the batch's 3 nb columns, four per k-step; 12 fragments feed the warp's 36 (21) MMAs ----
+            const int ksteps = (3 * nb + 3) / 4;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const double* Zk = s_Z + (4 * ks + q) * WD_ZS + g;
+                double fa[6], fb[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    fa[i] = Zk[8 * (6 * wr + i)];
+                    fb[i] = Zk[8 * (6 * wc + i)];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int jx = 0; jx < 6; ++jx) {
+                        if (jx < i && diag) continue;   // below the diagonal of a diagonal super-block
+                        wd_dmma(acc[i][jx][0], acc[i][jx][1], fa[i], fb[jx]);
+                    }
+            }
+        }
+        // ---- flush: lane (g, q) holds entries (row 8 I + g, columns 8 J + 2 q, + 1) of its tiles ----
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int r = 8 * (6 * wr + i) + g;
+            const int a = r / 6, pr = r - 6 * a;
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) {
+                if (jx < i && diag) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = 8 * (6 * wc + jx) + 2 * q + h;
+                    const double val = acc[i][jx][h];
+                    if (c < r || val == 0.0) continue;   // lower part of a diagonal MMA tile / a pair nobody observes
+                    const int b = c / 6, pc = c - 6 * b;
+                    // pair (a, b), a <= b: index in the row-major upper triangle
+                    const int e = s_blk[a * WD_WIN - a * (a - 1) / 2 + (b - a)];
+                    if (e >= 0) red_add(&S[36ll * e + 6 * pr + pc], -val);
+                }
+            }
+        }
+    }
 }
 
 // =============================================================================================
@@ -1166,8 +1412,22 @@ void launch_camonly_eval(cudaStream_t s, const DevView& v, const SunBlockData* s
     CSLAM_CUDA(cudaGetLastError());
 }
 
-void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, double* S, double* Bdiag,
-                          double* bp, double* gp, double* gl, double* scal) {
+void launch_schur_wide(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const uint8_t* wide, int n_slices, const int* sl_lo,
+                       const int* sl_hi, const int* sl_c0, long long obs0, double* Zg, LmDiag dg, double* S, double* Bdiag,
+                       double* bp, double* gp, double* gl, double* scal) {
+    if (n_slices <= 0 || lm_hi <= lm_lo) return;
+    schur_wide_produce_kernel<<<grid_for(lm_hi - lm_lo, SG_WARPS, 8 * kSMs), SG_WARPS * 32, 0, s>>>(v, lm_lo, lm_hi, wide, obs0, dg, Zg,
+                                                                                                Bdiag, bp, gp, gl, scal);
+    // (the opt-in is per device and costs a microsecond: set at every launch rather than cached process-wide)
+    CSLAM_CUDA(cudaFuncSetAttribute(schur_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WD_SMEM)));
+    const int grid = n_slices < kSMs ? n_slices : kSMs;
+    schur_wide_kernel<<<grid, WD_WARPS * 32, WD_SMEM, s>>>(v, n_slices, sl_lo, sl_hi, sl_c0, obs0, Zg, S, scal);
+    CSLAM_LAUNCHED(2);
+    CSLAM_CUDA(cudaGetLastError());
+}
+
+void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const uint8_t* skip, LmDiag dg, double* S,
+                          double* Bdiag, double* bp, double* gp, double* gl, double* scal) {
     if (lm_hi <= lm_lo) return;
     static PerDevice attr_done;
     const int dev_ = PerDevice::current();
@@ -1176,7 +1436,7 @@ void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi
         attr_done.mark(dev_);
     }
     const int grid = grid_for(lm_hi - lm_lo, SG_WARPS, 4 * kSMs);
-    schur_generic_kernel<<<grid, SG_WARPS * 32, SG_SMEM, s>>>(v, lm_lo, lm_hi, dg, S, Bdiag, bp, gp, gl, scal);
+    schur_generic_kernel<<<grid, SG_WARPS * 32, SG_SMEM, s>>>(v, lm_lo, lm_hi, skip, dg, S, Bdiag, bp, gp, gl, scal);
     CSLAM_LAUNCHED(1);
     CSLAM_CUDA(cudaGetLastError());
 }

@@ -24,8 +24,15 @@ void launch_camonly_eval(cudaStream_t s, const DevView& v, const SunBlockData* s
                          double* r_pr, double* J_pr, double* cost);
 
 // K2 — fused residual/Jacobian + Schur elimination, one warp per landmark (any track length)
-void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, LmDiag dg, double* S,
+// skip: optional flags [lm_hi - lm_lo], 1 = the landmark belongs to a slice of the wide-window kernel below
+void launch_schur_generic(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const uint8_t* skip, LmDiag dg, double* S,
                           double* Bdiag, double* bp, double* gp, double* gl, double* scal);
+// K2w — long ragged tracks: slices of ungrouped landmarks whose cameras fit a window of 32 consecutive poses
+// [c0, c0 + 32): Z = W chol(V^-1) per observation to Zg (18 doubles per observation, index e - obs0), then per slice the
+// 192 x 192 window tile of S in DMMA accumulators, one flush per slice.  wide: flags [lm_hi - lm_lo]
+void launch_schur_wide(cudaStream_t s, const DevView& v, int lm_lo, int lm_hi, const uint8_t* wide, int n_slices, const int* sl_lo,
+                       const int* sl_hi, const int* sl_c0, long long obs0, double* Zg, LmDiag dg, double* S, double* Bdiag,
+                       double* bp, double* gp, double* gl, double* scal);
 // K2 (fast path) — landmarks grouped by identical camera list: one CTA per slice of a group,
 // a producer warp forms Z = W chol(V)^-T per observation, consumer warps keep the 6x6 pair
 // blocks of the slice in registers and flush them once (SYRK-shaped, output stationary)

@@ -325,6 +325,24 @@ def test_wide_band_cholesky(product, case, capfd, monkeypatch):
         assert rel_err(g[2], poses1) < 1e-9 and rel_err(g[3], points1) < 1e-9
 
 
+@pytest.mark.parametrize("per_obs_W", [False, True])
+def test_long_ragged_tracks_wide_window(product, per_obs_W):
+    """Tracks of up to 30 frames with drop-outs: no group of the DMMA kernel (camera window 10) takes them; runs of
+    them whose cameras fit a window of 32 poses are eliminated by the wide-window kernel (S_win -= Z Z^T on the tensor
+    cores, kernels.cu schur_wide_kernel) instead of the per-landmark kernel's one RED per entry.  Same result as the
+    oracle, and as the per-landmark kernel alone (schur_path = 1)."""
+    tr = syn.make_track(260, 24, 6, seed=43, per_obs_W=per_obs_W, ragged=dict(mean=14, max=30, drop=0.1))
+    g, o = solve_pair(tr, 4)
+    check_lm(g, o)
+    p1, poses1, points1 = syn.build_problem(tr, schur_path=1, **dict(FIXED, max_num_iterations=4))
+    p1.solve()
+    assert rel_err(g[2], poses1) < 1e-9 and rel_err(g[3], points1) < 1e-9
+    # the first evaluation (cost, gradient) agrees to rounding
+    lg, l1 = g[0].iteration_log(), p1.iteration_log()
+    assert np.allclose(lg[:, 1], l1[:, 1], rtol=1e-12, atol=0)
+    assert np.allclose(lg[:, 3], l1[:, 3], rtol=1e-9, atol=0)
+
+
 def test_band_preconditioned_cg(product):
     """Ragged tracks as a stereo front end produces them (lengths 2 .. 20 with drop-outs) on a problem too large for
     the dense factorisation: the reduced system is a band plus weak far blocks, and the exact solve is conjugate
