@@ -416,7 +416,15 @@ void Engine::build_structure() {
         }
     });
     const uint32_t n_ok = sorted_off[n_poses];
+    // Exact groups below 24 landmarks are left to the ragged pass, where their first-camera bucket's landmarks share ONE
+    // group: every group is a work item with its own staging and pipeline fill, and real tracks produce thousands of
+    // groups of 4 .. 20 (ragged 5 k-pose track: Schur build 2.90 -> 2.27 ms; CSLAM_EXACT_MIN_GROUP: A/B knob)
+    static const int exact_min_env = [] {
+        const char* e = std::getenv("CSLAM_EXACT_MIN_GROUP");
+        return e ? std::atoi(e) : 24;
+    }();
     const size_t min_group = opt.schur_path == 2 ? 1 : 4;
+    const size_t min_exact = opt.schur_path == 2 ? 1 : (exact_min_env > 0 && want_ragged && !lighting_in_solve() ? size_t(exact_min_env) : min_group);
     g_L_h.clear(); g_G_h.clear(); g_lm0_h.clear(); g_obs0_h.clear(); g_off_h.clear(); g_cams_h.clear();
     g_blk_off_h.clear(); g_blk_h.clear(); item_group_h.clear(); item_j0_h.clear(); item_n_h.clear();
     std::vector<uint32_t> g_first;  // position of each group's first landmark in sorted_a
@@ -428,7 +436,7 @@ void Engine::build_structure() {
         uint32_t y = x + 1;
         while (y < n_ok && !run_start[y]) ++y;
         const uint32_t G = y - x;
-        if (G >= min_group) {
+        if (G >= min_exact) {
             const int L = int(lm_len(sorted_a[x]));
             const int gid = int(g_L_h.size());
             g_L_h.push_back(L);
