@@ -1543,19 +1543,12 @@ void Engine::plan_band_solver() {
 // The exact solve of a wide block-banded reduced system (half-bandwidth w of 13 .. 64 blocks), kernels_wband.cu:
 // C chunks separated by separators of w poses.  Taken automatically (bandpc_solver = 0) when the trajectory is long
 // compared with the band; bandpc_solver = 2 takes it whenever the layout is possible (tests on small problems).
-bool Engine::plan_wband_solver(int w) {
-    if (w > kWbandMaxW) return false;
-    const int n = n_free;
-    const bool forced = opt.bandpc_solver == 2;
-    if (!forced && (n < 256 || n < 8 * (w + 1))) return false;
-    // chunk chains (~18 us per panel of 48 columns incl. the back-substitution) against the dense separator solve
-    // (~21 us per panel of the (C - 1) 6w separator unknowns)
-    int C = int(std::lround(std::sqrt(6.0 * n / (7.0 * w))));
-    C = std::min(C, 1 + kDenseMaxN / (6 * w));
-    C = std::min(C, (n + w) / (3 * w + 1));       // interiors of at least 2w + 1 poses
-    C = std::max(C, 1);
+// One level of the layout: n_units blocks of `unit` scalars, half-bandwidth w units, C chunks.
+bool Engine::plan_wband_level(int lvl, int n_units, int unit, int w, int C) {
+    WbandLevel& L = wb[lvl];
+    const int n = n_units;
     const int inter = n - (C - 1) * w;
-    if (inter < C * (w + 1)) return false;
+    if (C < 1 || inter < C * (w + 1)) return false;
     const int base = inter / C, extra = inter % C;
     std::vector<int> owner(n), local(n), p0(C), len(C);
     int pos = 0;
@@ -1572,89 +1565,141 @@ bool Engine::plan_wband_solver(int w) {
                 local[pos++] = a;
             }
     }
-    // every stored block must fit the layout (interior x interior of one chunk, interior x adjacent separator, or
-    // inside one separator): guaranteed by the band width, checked because a miss would be a silent wrong answer
-    for (int a = 0; a < n; ++a)
-        for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) {
-            const int oa = owner[a], ob = owner[s_col_h[e]];
-            const bool ok = (oa >= 0 && (ob == oa || ob == -(oa + 1))) || (oa < 0 && (ob == -oa || ob == oa));
-            if (!ok) return false;
-        }
+    if (lvl == 0) {
+        // every stored block must fit the layout (interior x interior of one chunk, interior x adjacent separator, or
+        // inside one separator): guaranteed by the band width, checked because a miss would be a silent wrong answer
+        for (int a = 0; a < n; ++a)
+            for (int e = s_rowptr_h[a]; e < s_rowptr_h[a + 1]; ++e) {
+                const int oa = owner[a], ob = owner[s_col_h[e]];
+                const bool ok = (oa >= 0 && (ob == oa || ob == -(oa + 1))) || (oa < 0 && (ob == -oa || ob == oa));
+                if (!ok) return false;
+            }
+    }
     const int nb = dense_panel_width();
-    const int m_pad = (6 * (base + (extra ? 1 : 0)) + nb - 1) / nb * nb;
-    const int sepw = C > 1 ? 6 * w : 0, nbr = 2 * sepw + 1, ldB = nbr + (nbr & 1);
-    const int bwr = (6 * w + 5 + 7) / 8 * 8, ld = bwr + nb;
+    const int m_pad = (unit * (base + (extra ? 1 : 0)) + nb - 1) / nb * nb;
+    const int sepw = C > 1 ? unit * w : 0, nbr = 2 * sepw + 1, ldB = nbr + (nbr & 1);
+    const int bwr = (unit * (w + 1) - 1 + 7) / 8 * 8, ld = bwr + nb;
     const size_t a_stride = size_t(m_pad) * (ld + 1) + 2, b_stride = size_t(m_pad + ldB) * ldB;
     const size_t ns = size_t(C - 1) * sepw, ns_pad = (ns + nb - 1) / nb * nb;
     const size_t bytes = 8 * (C * (a_stride + b_stride) + (ns_pad + 8) * (ns_pad + 1));
     if (bytes > (size_t(12) << 30)) return false;
-    wband_w = w;
-    wband_C = C;
-    wband_mpad = m_pad;
-    wband_rstart = C > 1 ? 6 * (base - w) / nb * nb : 0;   // the right separator couples to a chunk's last w poses only
-    d_wb_owner.upload(owner, stream);
-    d_wb_local.upload(local, stream);
-    d_wb_p0.upload(p0, stream);
-    d_wb_len.upload(len, stream);
-    d_wb_A.alloc(a_stride * C, stream);
-    d_wb_Bd.alloc(b_stride * C, stream);
-    d_wb_Ld.alloc(size_t(C) * (m_pad / nb) * nb * nb, stream);
-    d_wb_xw.alloc(size_t(C) * m_pad, stream);
+    L.n_units = n;
+    L.unit = unit;
+    L.w = w;
+    L.C = C;
+    L.m_pad = m_pad;
+    L.r_start = C > 1 ? unit * (base - w) / nb * nb : 0;   // the right separator couples to a chunk's last w units only
+    L.owner.upload(owner, stream);
+    L.local.upload(local, stream);
+    L.p0.upload(p0, stream);
+    L.len.upload(len, stream);
+    L.A.alloc(a_stride * C, stream);
+    L.Bd.alloc(b_stride * C, stream);
+    L.Ld.alloc(size_t(C) * (m_pad / nb) * nb * nb, stream);
+    L.xw.alloc(size_t(C) * m_pad, stream);
     if (C > 1) {
-        d_wb_xsep.alloc(ns, stream);
-        d_wb_T.alloc((ns_pad + 8) * (ns_pad + 1), stream);
-        d_wb_TLd.alloc((ns_pad / nb) * nb * nb, stream);
-        d_wb_Txw.alloc(ns_pad, stream);
+        L.xsep.alloc(ns, stream);
+        L.T.alloc((ns_pad + 8) * (ns_pad + 1), stream);
+        L.TLd.alloc((ns_pad / nb) * nb * nb, stream);
+        L.Txw.alloc(ns_pad, stream);
     }
-    if (!d_band_fail.p) d_band_fail.alloc(1, stream);
-    wband_active = true;
     if (std::getenv("CSLAM_DEBUG_SOLVER"))
-        std::fprintf(stderr, "[solver] wide-band Cholesky: %d free poses, half-bandwidth %d, %d chunks of <= %d unknowns, %zu separator unknowns\n",
-                     n, w, C, m_pad, ns);
+        std::fprintf(stderr, "[solver] wide-band Cholesky%s: %d blocks of %d, half-bandwidth %d, %d chunks of <= %d unknowns, %zu separator unknowns\n",
+                     lvl ? " (separator level)" : "", n, unit, w, C, m_pad, ns);
     return true;
 }
 
-WbandView Engine::wband_view(const double* rhs, double* y) {
+bool Engine::plan_wband_solver(int w) {
+    if (w > kWbandMaxW) return false;
+    const int n = n_free;
+    const bool forced = opt.bandpc_solver == 2;
+    if (!forced && (n < 256 || n < 8 * (w + 1))) return false;
+    // Cost model (us, measured on the ragged 5 k-pose track): a chunk panel of 48 columns costs ~27 (factor + trailing update +
+    // its share of the one-launch back-substitution), a panel of a dense separator system ~26.  One level: C chunks +
+    // the dense solve of (C - 1) 6w separator unknowns.  Two levels: the separator system is block tridiagonal with
+    // blocks of 6w and is chunked again (separators of ONE block), its own separators go to the dense solver.
+    const double tp = 27.0, td = 26.0, sb = 6.0 * w / 48.0;   // sb: panels per separator block
+    auto panels = [](double scalars) { return std::ceil(scalars / 48.0); };
+    const int Cmax = std::max(1, std::min(1 + kDenseMaxN / (6 * w), (n + w) / (3 * w + 1)));
+    static const int force_levels = [] {
+        const char* e = std::getenv("CSLAM_WBAND_LEVELS");   // A/B knob: 1 = never chunk the separator system
+        return e ? std::atoi(e) : 0;
+    }();
+    double best = 1e300;
+    int bestC = 1, bestC2 = 0;
+    for (int C = 1; C <= Cmax; ++C) {
+        const double ns = (C - 1) * 6.0 * w;
+        const double chunk = panels(6.0 * (n - (C - 1) * w) / C) * tp + ns * ns * 8.0 / 6e6;   // (+ clearing the dense T)
+        const double one = chunk + panels(ns) * td;
+        if (one < best) {
+            best = one;
+            bestC = C;
+            bestC2 = 0;
+        }
+        const int B = C - 1;
+        if (force_levels == 1) continue;
+        for (int C2 = 2; B >= 8 && C2 <= (B + 1) / 3; ++C2) {
+            const double two = chunk + panels(6.0 * w * (B - (C2 - 1)) / C2) * tp + (C2 - 1) * sb * td + 40.0;
+            if (two < best) {
+                best = two;
+                bestC = C;
+                bestC2 = C2;
+            }
+        }
+    }
+    wb_levels = 0;
+    if (!plan_wband_level(0, n, 6, w, bestC)) return false;
+    wb_levels = 1;
+    if (bestC2 >= 2 && plan_wband_level(1, bestC - 1, 6 * w, 1, bestC2)) wb_levels = 2;
+    if (!d_band_fail.p) d_band_fail.alloc(1, stream);
+    wband_active = true;
+    return true;
+}
+
+WbandView Engine::wband_view(int lvl) {
     const int nb = dense_panel_width();
+    WbandLevel& L = wb[lvl];
     WbandView V;
-    V.n_free = n_free;
-    V.w = wband_w;
-    V.C = wband_C;
-    V.m_pad = wband_mpad;
-    V.sepw = wband_C > 1 ? 6 * wband_w : 0;
+    V.n_free = L.n_units;
+    V.unit = L.unit;
+    V.next = nullptr;
+    V.w = L.w;
+    V.C = L.C;
+    V.m_pad = L.m_pad;
+    V.sepw = L.C > 1 ? L.unit * L.w : 0;
     V.nbr = 2 * V.sepw + 1;
-    V.bwr = (6 * wband_w + 5 + 7) / 8 * 8;
+    V.bwr = (L.unit * (L.w + 1) - 1 + 7) / 8 * 8;
     V.ld = V.bwr + nb;
     V.ldB = V.nbr + (V.nbr & 1);
-    V.r_start = wband_rstart;
+    V.r_start = L.r_start;
     V.a_stride = (long long)V.m_pad * (V.ld + 1) + 2;
     V.b_stride = (long long)(V.m_pad + V.ldB) * V.ldB;
     V.rowptr = d_s_rowptr.p;
     V.col = d_s_col.p;
     V.S = d_S;
-    V.rhs = rhs;
-    V.owner = d_wb_owner.p;
-    V.local = d_wb_local.p;
-    V.chunk_p0 = d_wb_p0.p;
-    V.chunk_len = d_wb_len.p;
-    V.A = d_wb_A.p;
-    V.Bd = d_wb_Bd.p;
-    V.Ldiag = d_wb_Ld.p;
-    V.xw = d_wb_xw.p;
-    V.xsep = d_wb_xsep.p;
-    V.T.n = (wband_C - 1) * V.sepw;
+    V.rhs = nullptr;
+    V.owner = L.owner.p;
+    V.local = L.local.p;
+    V.chunk_p0 = L.p0.p;
+    V.chunk_len = L.len.p;
+    V.A = L.A.p;
+    V.Bd = L.Bd.p;
+    V.Ldiag = L.Ld.p;
+    V.xw = L.xw.p;
+    V.xsep = L.xsep.p;
+    V.T.n = (L.C - 1) * V.sepw;
     V.T.n_pad = (V.T.n + nb - 1) / nb * nb;
     V.T.ld = V.T.n_pad + 8;
     V.T.rowptr = nullptr;
     V.T.col = nullptr;
     V.T.S = nullptr;
     V.T.rhs = nullptr;
-    V.T.A = d_wb_T.p;
-    V.T.Ldiag = d_wb_TLd.p;
-    V.T.y = d_wb_xsep.p;
+    V.T.A = L.T.p;
+    V.T.Ldiag = L.TLd.p;
+    V.T.y = L.xsep.p;
     V.T.fail = d_band_fail.p;
-    V.Txw = d_wb_Txw.p;
-    V.y = y;
+    V.Txw = L.Txw.p;
+    V.y = nullptr;
     V.fail = d_band_fail.p;
     return V;
 }
@@ -2221,7 +2266,15 @@ void Engine::solve_reduced(const double* rhs, double* y) {
         min_it = opt.min_linear_solver_iterations;
     }
     if (wband_active) {
-        launch_wband_solve(stream, wband_view(rhs, y), d_pscal.p);
+        WbandView V0 = wband_view(0), V1;
+        V0.rhs = rhs;
+        V0.y = y;
+        if (wb_levels == 2) {
+            V1 = wband_view(1);
+            V1.y = V0.xsep;   // the separator level solves level 0's separator system in place of the dense solver
+            V0.next = &V1;
+        }
+        launch_wband_solve(stream, V0, d_pscal.p);
     } else if (bandpc_active) {
         bandpc_solve(rhs, y);
     } else if (dense_active) {

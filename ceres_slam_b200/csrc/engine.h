@@ -129,12 +129,14 @@ int dense_panel_width();
 // the separator system (block tridiagonal, dense storage) goes through the dense solver.
 constexpr int kWbandMaxW = 64;
 struct WbandView {
-    int n_free, w, C;            // free poses, half-bandwidth (blocks), chunks
+    int n_free, w, C;            // unknown blocks ("units": the free poses at level 0), half-bandwidth (units), chunks
+    int unit;                    // scalars per unit: 6 at level 0, 6w of level 0 at level 1 (its separator blocks)
+    const WbandView* next;       // host side only: the view that solves this level's separator system (nullptr: dense)
     int m_pad;                   // padded interior size of a chunk (scalars, a multiple of 48; the same for every chunk)
-    int sepw;                    // 6 w (0 when C == 1)
+    int sepw;                    // unit * w (0 when C == 1)
     int nbr;                     // border rows: 2 sepw + 1, [left separator | rhs | right separator]
     int r_start;                 // first panel column from which the right separator's rows take part
-    int bwr;                     // scalar half-bandwidth 6 w + 5 rounded up to a multiple of 8
+    int bwr;                     // scalar half-bandwidth unit (w + 1) - 1 rounded up to a multiple of 8
     int ld;                      // band storage: element (i, j), i >= j, of a chunk at A[j * ld + i], ld = bwr + 48
     int ldB;                     // border storage: (border row b, column j) at Bd[j * ldB + b]; columns m_pad + b' hold the
                                  //   border x border Schur complement
@@ -383,10 +385,17 @@ class Engine {
     void plan_dense_solver();
     // wide-band direct solver (linear_solver == 0, S block-banded with 12 < half-bandwidth <= 64)
     bool wband_active = false;
-    int wband_w = 0, wband_C = 0, wband_mpad = 0, wband_rstart = 0;
-    DBuf<int> d_wb_owner, d_wb_local, d_wb_p0, d_wb_len;
-    DBuf<double> d_wb_A, d_wb_Bd, d_wb_Ld, d_wb_xw, d_wb_xsep, d_wb_T, d_wb_TLd, d_wb_Txw;
-    WbandView wband_view(const double* rhs, double* y);
+    // level 0: the poses (unit 6, half-bandwidth w); level 1, when there are enough separators: the separator system of
+    // level 0, block tridiagonal with blocks of 6w — the same chunking again (unit 6w, half-bandwidth 1 block)
+    struct WbandLevel {
+        int n_units = 0, unit = 0, w = 0, C = 0, m_pad = 0, r_start = 0;
+        DBuf<int> owner, local, p0, len;
+        DBuf<double> A, Bd, Ld, xw, xsep, T, TLd, Txw;
+    };
+    WbandLevel wb[2];
+    int wb_levels = 0;
+    bool plan_wband_level(int lvl, int n_units, int unit, int w, int C);
+    WbandView wband_view(int lvl);
     bool plan_wband_solver(int w);
     // extra scratch sets + streams so that independent solves against the same banded S run
     // concurrently (the border columns of the lighting solve): each solve is a latency-bound chain

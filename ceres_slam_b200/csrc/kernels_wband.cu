@@ -87,10 +87,48 @@ __global__ void wband_pad_kernel(WbandView V) {
     const int per = V.m_pad;
     if (t < V.C * per) {
         const int c = t / per, j = t % per;
-        if (j >= 6 * V.chunk_len[c]) V.A[c * V.a_stride + (long long)j * V.ld + j] = 1.0;
+        if (j >= V.unit * V.chunk_len[c]) V.A[c * V.a_stride + (long long)j * V.ld + j] = 1.0;
     } else {
         const int j = t - V.C * per;
         if (V.C > 1 && j >= V.T.n && j < V.T.n_pad) V.T.A[(long long)j * V.T.ld + j] = 1.0;
+    }
+}
+
+// Separator level: the dense separator system T of view P (lower triangle, block tridiagonal with blocks of P.sepw =
+// V.unit scalars, rhs as row n_pad) is chunked again.  One CTA per column gj of T: its entries down to the end of the
+// next block go to V's band / border / separator storage, by the same rules as wband_fill_kernel with blocks of
+// V.unit scalars instead of 6.
+__global__ void wband_refill_kernel(WbandView P, WbandView V) {
+    const int gj = blockIdx.x;
+    const int u = V.unit, ns = P.T.n;
+    const int bj = gj / u, oj = gj % u;
+    const long long ldT = P.T.ld, ldT2 = V.T.ld;
+    const double* Tc = P.T.A + gj * ldT;
+    const int oa = V.owner[bj], la = V.local[bj];
+    const int hi = min(ns, (bj + 2) * u);
+    for (int gi = gj + threadIdx.x; gi < hi; gi += blockDim.x) {
+        const int bi = gi / u, oi = gi % u;
+        const int ob = V.owner[bi], lb = V.local[bi];
+        const double v = Tc[gi];
+        if (oa >= 0 && ob == oa) {
+            V.A[oa * V.a_stride + (long long)(u * la + oj) * V.ld + u * lb + oi] = v;
+        } else if (oa >= 0 && ob == -(oa + 1)) {      // bi is the separator right of bj's chunk
+            V.Bd[oa * V.b_stride + (long long)(u * la + oj) * V.ldB + V.sepw + 1 + u * lb + oi] = v;
+        } else if (oa < 0 && ob == -oa) {             // bj is separator s = -oa - 1, bi in chunk s + 1: its left separator
+            V.Bd[ob * V.b_stride + (long long)(u * lb + oi) * V.ldB + u * la + oj] = v;
+        } else if (oa < 0 && ob == oa) {
+            const int s = -oa - 1;
+            V.T.A[(s * V.sepw + u * la + oj) * ldT2 + s * V.sepw + u * lb + oi] = v;
+        } else {
+            *V.fail = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double r = Tc[P.T.n_pad];
+        if (oa >= 0)
+            V.Bd[oa * V.b_stride + (long long)(u * la + oj) * V.ldB + V.sepw] = r;
+        else
+            V.T.A[((-oa - 1) * V.sepw + u * la + oj) * ldT2 + V.T.n_pad] = r;
     }
 }
 
@@ -349,8 +387,8 @@ __global__ void __launch_bounds__(WBT) wband_backsolve_kernel(WbandView V) {
     double* xw = V.xw + (long long)ch * V.m_pad;
     const double* Ach = V.A + ch * V.a_stride;
     const double* Lch = V.Ldiag + (long long)ch * (V.m_pad / B) * B * B;
-    const int n_own = 6 * V.chunk_len[ch];
-    double* yo = V.y + 6ll * V.chunk_p0[ch];
+    const int n_own = V.unit * V.chunk_len[ch];
+    double* yo = V.y + (long long)V.unit * V.chunk_p0[ch];
     double lnext[NL];
     auto load_L = [&](int j0) {
         const double* Li = Lch + (long long)(j0 / B) * B * B;
@@ -413,7 +451,7 @@ __global__ void wband_sep_scatter_kernel(WbandView V) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= V.T.n) return;
     const int s = t / V.sepw, o = t % V.sepw;
-    V.y[6ll * (V.chunk_p0[s] + V.chunk_len[s]) + o] = V.xsep[t];
+    V.y[(long long)V.unit * (V.chunk_p0[s] + V.chunk_len[s]) + o] = V.xsep[t];
 }
 
 __global__ void wband_status_kernel(const int* fail, double* ps) {
@@ -423,17 +461,23 @@ __global__ void wband_status_kernel(const int* fail, double* ps) {
 
 }  // namespace
 
-void launch_wband_solve(cudaStream_t s, const WbandView& V, double* ps) {
-    CSLAM_CUDA(cudaMemsetAsync(V.fail, 0, sizeof(int), s));
+namespace {
+
+void wband_clear(cudaStream_t s, const WbandView& V) {
     CSLAM_CUDA(cudaMemsetAsync(V.A, 0, sizeof(double) * size_t(V.a_stride) * size_t(V.C), s));
     CSLAM_CUDA(cudaMemsetAsync(V.Bd, 0, sizeof(double) * size_t(V.b_stride) * size_t(V.C), s));
     if (V.C > 1) CSLAM_CUDA(cudaMemsetAsync(V.T.A, 0, sizeof(double) * size_t(V.T.ld) * size_t(V.T.n_pad + 1), s));
-    wband_fill_kernel<<<V.n_free, 128, 0, s>>>(V);
-    {
-        const int total = V.C * V.m_pad + (V.C > 1 ? V.T.n_pad : 0);
-        wband_pad_kernel<<<(total + 255) / 256, 256, 0, s>>>(V);
-    }
-    int launched = 2;
+}
+
+void wband_pad(cudaStream_t s, const WbandView& V) {
+    const int total = V.C * V.m_pad + (V.C > 1 ? V.T.n_pad : 0);
+    wband_pad_kernel<<<(total + 255) / 256, 256, 0, s>>>(V);
+}
+
+// Everything after the storage of V has been written: factorisation of the chunks, the separator system (dense, or
+// the next level), back-substitution into V.y.  Returns the number of kernels launched.
+int wband_factor_solve(cudaStream_t s, const WbandView& V) {
+    int launched = 0;
     constexpr size_t smem_syrk = sizeof(double) * 2 * WNB * WSL;
     CSLAM_CUDA(cudaFuncSetAttribute(wband_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_syrk)));
     for (int j0 = 0; j0 < V.m_pad; j0 += WNB) {
@@ -446,16 +490,34 @@ void launch_wband_solve(cudaStream_t s, const WbandView& V, double* ps) {
     if (V.C > 1) {
         wband_sep_assemble_kernel<<<V.T.n, 128, 0, s>>>(V);
         ++launched;
-        launch_dense_factor(s, V.T, V.Txw);
+        if (V.next) {
+            const WbandView& N = *V.next;   // (N.y == V.xsep: the next level solves T in place of the dense solver)
+            wband_clear(s, N);
+            wband_refill_kernel<<<V.T.n, 128, 0, s>>>(V, N);
+            wband_pad(s, N);
+            launched += 2 + wband_factor_solve(s, N);
+        } else {
+            launch_dense_factor(s, V.T, V.Txw);
+        }
     }
     wband_backinit_kernel<<<dim3((V.m_pad + 7) / 8, V.C), 256, 0, s>>>(V);
-    ++launched;
     wband_backsolve_kernel<<<V.C, WBT, 0, s>>>(V);
-    ++launched;
+    launched += 2;
     if (V.C > 1) {
         wband_sep_scatter_kernel<<<(V.T.n + 255) / 256, 256, 0, s>>>(V);
         ++launched;
     }
+    return launched;
+}
+
+}  // namespace
+
+void launch_wband_solve(cudaStream_t s, const WbandView& V, double* ps) {
+    CSLAM_CUDA(cudaMemsetAsync(V.fail, 0, sizeof(int), s));
+    wband_clear(s, V);
+    wband_fill_kernel<<<V.n_free, 128, 0, s>>>(V);
+    wband_pad(s, V);
+    const int launched = 2 + wband_factor_solve(s, V);
     wband_status_kernel<<<1, 1, 0, s>>>(V.fail, ps);
     CSLAM_CUDA(cudaGetLastError());
     g_kernel_launches.fetch_add(launched + 1, std::memory_order_relaxed);
