@@ -26,11 +26,14 @@ def main():
     lib = capi.load_product()
     tr_shared = syn.add_sun(syn.make_track(300, 40, 8, seed=77))
     tr_per_obs = syn.add_sun(syn.make_track(200, 30, 6, seed=78, per_obs_W=True))   # a weight per observation
+    # tracks of up to 24 frames with drop-outs: ragged groups and wide-window slices per shard, the wide-band solver
+    # (chunks of bordered bands) on every rank
+    tr_ragged = syn.add_sun(syn.make_track(400, 12, 6, seed=79, ragged=dict(mean=10, max=24, drop=0.1)))
     kw = dict(max_num_iterations=6, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0,
               device=local, sun=True)
     # (with CSLAM_GPU_STRUCTURE_MIN=0 the ranks analyse the structure on their GPUs; CSLAM_VERIFY_STRUCTURE=1
     # checks that layout against the host analysis)
-    for linear_solver, tr in ((0, tr_shared), (1, tr_shared), (0, tr_per_obs)):
+    for linear_solver, tr in ((0, tr_shared), (1, tr_shared), (0, tr_per_obs), (0, tr_ragged)):
         # reference: the whole problem on this rank's GPU
         p1, poses1, points1 = syn.build_problem(tr, linear_solver=linear_solver, **kw)
         s1 = p1.solve()
