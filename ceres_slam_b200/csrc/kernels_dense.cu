@@ -40,7 +40,8 @@ constexpr int DNB = 48;                     // panel width
 constexpr int DPW = 6;                      // row warps per panel CTA
 constexpr int DPT = 32 * (2 + DPW);         // threads of a panel CTA
 constexpr int DPR = 32 * DPW;               // panel rows per CTA
-constexpr int DSL = 72;                     // row stride of a staged panel slab ([k][64 rows], 72 = 8 mod 16: conflict-free)
+constexpr int DSL = 68;                     // row stride of a staged panel slab ([k][64 rows]); 4 mod 16: the fragment load of lane
+                                            // (g, q) reads word q * 68 + g (+ tile), distinct banks over a half-warp (72 was 2-way)
 
 // One CTA per block row of the upper block-CSR; block 0 also writes the right-hand-side row and the
 // identity padding.
@@ -144,7 +145,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 // Trailing update behind panel j0: rows / columns t0 = j0 + 48 .. n_pad (the last row is the right-hand side).
-__global__ void __launch_bounds__(256) dense_syrk_kernel(DenseView V, int j0) {
+// Four CTAs per SM (64 registers): more of a launch's latency-bound tiles are resident at once.
+__global__ void __launch_bounds__(256, 4) dense_syrk_kernel(DenseView V, int j0) {
     extern __shared__ __align__(16) double smem_syrk[];
     double* Lr = smem_syrk;           // Lr[k][i]: panel rows of the tile's row range
     double* Lc = Lr + DNB * DSL;      // panel rows of the tile's column range
@@ -195,26 +197,29 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(DenseView V, int j0) {
     const int j = 64 * J + 8 * jt + g;
     if (j < m) {
         double* Cc = V.A + (long long)(t0 + j) * ld + t0;
-        // read-modify-write of the lane's eight row pairs: all loads first, then all stores
-        double2 cv[8];
+        // read-modify-write of the lane's eight row pairs, four at a time: their loads first, then their stores
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int i = 64 * I + 8 * it + 2 * q;  // two consecutive rows of column j
-            cv[it] = make_double2(0.0, 0.0);
-            if (i + 1 < m)
-                cv[it] = *reinterpret_cast<const double2*>(Cc + i);
-            else if (i < m)
-                cv[it].x = Cc[i];
-        }
+        for (int h0 = 0; h0 < 8; h0 += 4) {
+            double2 cv[4];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int i = 64 * I + 8 * it + 2 * q;
-            cv[it].x -= acc[it][0];
-            cv[it].y -= acc[it][1];
-            if (i + 1 < m)
-                *reinterpret_cast<double2*>(Cc + i) = cv[it];
-            else if (i < m)
-                Cc[i] = cv[it].x;
+            for (int u = 0; u < 4; ++u) {
+                const int i = 64 * I + 8 * (h0 + u) + 2 * q;  // two consecutive rows of column j
+                cv[u] = make_double2(0.0, 0.0);
+                if (i + 1 < m)
+                    cv[u] = *reinterpret_cast<const double2*>(Cc + i);
+                else if (i < m)
+                    cv[u].x = Cc[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = 64 * I + 8 * (h0 + u) + 2 * q;
+                cv[u].x -= acc[h0 + u][0];
+                cv[u].y -= acc[h0 + u][1];
+                if (i + 1 < m)
+                    *reinterpret_cast<double2*>(Cc + i) = cv[u];
+                else if (i < m)
+                    Cc[i] = cv[u].x;
+            }
         }
     }
 }
@@ -283,6 +288,8 @@ void launch_dense_factor(cudaStream_t s, const DenseView& V, double* xw) {
     int launched = 0;
     constexpr size_t smem_syrk = sizeof(double) * 2 * DNB * DSL;
     CSLAM_CUDA(cudaFuncSetAttribute(dense_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_syrk)));
+    // (four 52 KB CTAs per SM need the large carve-out; the default left room for two)
+    CSLAM_CUDA(cudaFuncSetAttribute(dense_syrk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (int j0 = 0; j0 < V.n_pad; j0 += DNB) {
         const int rows = V.n_pad + 1 - (j0 + DNB);  // rows below the diagonal block (>= 1: the right-hand side)
         dense_panel_kernel<<<(rows + DNB + DPR - 1) / DPR, DPT, 0, s>>>(V, j0);   // + the 48 unit-vector rows

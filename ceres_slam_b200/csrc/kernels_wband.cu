@@ -42,7 +42,8 @@ constexpr int WNB = 48;                     // panel width (the dense solver's)
 constexpr int WPW = 6;                      // row warps per panel CTA
 constexpr int WPT = 32 * (2 + WPW);         // threads of a panel CTA
 constexpr int WPR = 32 * WPW;               // panel rows per CTA
-constexpr int WSL = 72;                     // row stride of a staged panel slab ([k][64 rows], 72 = 8 mod 16: conflict-free)
+constexpr int WSL = 68;                     // row stride of a staged panel slab ([k][64 rows]); 4 mod 16: the fragment load of lane
+                                            // (g, q) reads word q * 68 + g (+ tile), distinct banks over a half-warp (72 was 2-way)
 
 // One CTA per block row of the upper block-CSR.  Where a block goes depends on what its two poses are:
 // interior x interior -> the chunk's band, interior x separator -> the chunk's border rows, separator x separator ->
@@ -241,7 +242,8 @@ __device__ __forceinline__ void wb_dmma_m8n8k4(double& c0, double& c1, double a,
 // Trailing update behind panel j0 over the local index space [0, m): local row / column l < mb is the chunk's band
 // row / column t0 + l, l >= mb is border row l - mb (as a COLUMN: column m_pad + l - mb of the border array, the
 // border x border Schur complement).  Lower triangle only.
-__global__ void __launch_bounds__(256) wband_syrk_kernel(WbandView V, int j0) {
+// Four CTAs per SM (64 registers): the launch is one wave of latency-bound tiles — with 90 registers it was two.
+__global__ void __launch_bounds__(256, 4) wband_syrk_kernel(WbandView V, int j0) {
     extern __shared__ __align__(16) double smem_wsyrk[];
     double* Lr = smem_wsyrk;          // Lr[k][i]: panel rows of the tile's row range
     double* Lc = Lr + WNB * WSL;      // panel rows of the tile's column range
@@ -299,34 +301,37 @@ __global__ void __launch_bounds__(256) wband_syrk_kernel(WbandView V, int j0) {
         // column j of the target: rows l < mb at colA[l], rows l >= mb at colB[l]
         double* colA = Ab + (long long)(t0 + j) * ld + t0;                                   // only when j < mb
         double* colB = Bb + (j < mb ? (long long)(t0 + j) : (long long)(V.m_pad + j - mb)) * ldB - mb;
-        // read-modify-write of the lane's eight row pairs: all loads first, then all stores
-        double2 cv[8];
+        // read-modify-write of the lane's eight row pairs, four at a time: their loads first, then their stores
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int i = 64 * I + 8 * it + 2 * q;  // rows i, i + 1 of column j (mb is even: both band or both border)
-            cv[it] = make_double2(0.0, 0.0);
-            if (i + 1 < j || i >= m) continue;      // above the diagonal / beyond the last row
-            const double* p = (i < mb ? colA : colB) + i;
-            if (i >= j && i + 1 < m)
-                cv[it] = *reinterpret_cast<const double2*>(p);
-            else if (i >= j)
-                cv[it].x = p[0];
-            else if (i + 1 < m)                     // i + 1 == j: the diagonal entry alone
-                cv[it].y = p[1];
-        }
+        for (int h0 = 0; h0 < 8; h0 += 4) {
+            double2 cv[4];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int i = 64 * I + 8 * it + 2 * q;
-            if (i + 1 < j || i >= m) continue;
-            double* p = (i < mb ? colA : colB) + i;
-            cv[it].x -= acc[it][0];
-            cv[it].y -= acc[it][1];
-            if (i >= j && i + 1 < m)
-                *reinterpret_cast<double2*>(p) = cv[it];
-            else if (i >= j)
-                p[0] = cv[it].x;
-            else if (i + 1 < m)
-                p[1] = cv[it].y;
+            for (int u = 0; u < 4; ++u) {
+                const int i = 64 * I + 8 * (h0 + u) + 2 * q;  // rows i, i + 1 of column j (mb is even: both band or both border)
+                cv[u] = make_double2(0.0, 0.0);
+                if (i + 1 < j || i >= m) continue;            // above the diagonal / beyond the last row
+                const double* p = (i < mb ? colA : colB) + i;
+                if (i >= j && i + 1 < m)
+                    cv[u] = *reinterpret_cast<const double2*>(p);
+                else if (i >= j)
+                    cv[u].x = p[0];
+                else if (i + 1 < m)                           // i + 1 == j: the diagonal entry alone
+                    cv[u].y = p[1];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = 64 * I + 8 * (h0 + u) + 2 * q;
+                if (i + 1 < j || i >= m) continue;
+                double* p = (i < mb ? colA : colB) + i;
+                cv[u].x -= acc[h0 + u][0];
+                cv[u].y -= acc[h0 + u][1];
+                if (i >= j && i + 1 < m)
+                    *reinterpret_cast<double2*>(p) = cv[u];
+                else if (i >= j)
+                    p[0] = cv[u].x;
+                else if (i + 1 < m)
+                    p[1] = cv[u].y;
+            }
         }
     }
 }
@@ -480,6 +485,8 @@ int wband_factor_solve(cudaStream_t s, const WbandView& V) {
     int launched = 0;
     constexpr size_t smem_syrk = sizeof(double) * 2 * WNB * WSL;
     CSLAM_CUDA(cudaFuncSetAttribute(wband_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_syrk)));
+    // (four 52 KB CTAs per SM need the large carve-out; the default left room for two)
+    CSLAM_CUDA(cudaFuncSetAttribute(wband_syrk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (int j0 = 0; j0 < V.m_pad; j0 += WNB) {
         const int mb = std::min(V.bwr, V.m_pad - (j0 + WNB)), m = mb + (j0 >= V.r_start ? V.nbr : V.sepw + 1);
         wband_panel_kernel<<<dim3((m + WNB + WPR - 1) / WPR, V.C), WPT, 0, s>>>(V, j0);   // + the 48 unit-vector rows
