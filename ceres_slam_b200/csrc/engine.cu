@@ -1647,6 +1647,13 @@ bool Engine::plan_wband_solver(int w) {
             }
         }
     }
+    if (const char* e = std::getenv("CSLAM_WBAND_CHUNKS")) {   // A/B knob: "C0" or "C0,C1" chunk counts per level
+        int c0 = 0, c1 = 0;
+        if (std::sscanf(e, "%d,%d", &c0, &c1) >= 1 && c0 >= 1 && c0 <= Cmax) {
+            bestC = c0;
+            bestC2 = c1;
+        }
+    }
     wb_levels = 0;
     if (!plan_wband_level(0, n, 6, w, bestC)) return false;
     wb_levels = 1;

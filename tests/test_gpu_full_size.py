@@ -92,3 +92,27 @@ def test_c5_device_structure_analysis_equals_host(product, c5, monkeypatch):
         tr[k] = np.ascontiguousarray(c5[k][perm])
     p2, _, _ = syn.build_problem(tr, max_num_iterations=1, **FIXED)
     p2.upload()
+
+
+def test_ragged_5k_solvers_and_kernels_agree(product):
+    """The ragged benchmark track (5 k poses, 500 k landmarks, tracks of 2 .. 30 frames with drop-outs: bench.py
+    c5_ragged), too large for the oracle: the wide-band factorisation (K3e, two levels of chunked bordered bands) must
+    give the iterates of conjugate gradients preconditioned with the narrow-band solver run to 1e-15 (K3c), and the
+    grouped / wide-window Schur kernels (K2, K2w) those of the per-landmark kernel alone."""
+    tr = syn.make_track(5000, 100, 10, seed=42, ragged=dict(mean=8.0, max=30, drop=0.1))
+    kw = dict(FIXED, max_num_iterations=4)
+    res = {}
+    for name, opts in (("wband", {}), ("bandpc", dict(bandpc_solver=1)), ("per_landmark", dict(schur_path=1))):
+        p, poses, points = syn.build_problem(tr, **dict(kw, **opts))
+        s = p.solve()
+        res[name] = (s, p.iteration_log(), poses, points)
+    s0, log0, poses0, points0 = res["wband"]
+    assert np.all(log0[1:, 7] == 1), "one direct solve per LM iteration"
+    assert s0.final_cost < 0.05 * s0.initial_cost
+    for name in ("bandpc", "per_landmark"):
+        s, log, poses, points = res[name]
+        assert np.array_equal(log[:, 9], log0[:, 9]), name
+        assert np.allclose(log[:, 1], log0[:, 1], rtol=1e-9, atol=0), name
+        assert np.abs(poses - poses0).max() <= 1e-7 * np.abs(poses0).max(), name
+        assert np.abs(points - points0).max() <= 1e-7 * np.abs(points0).max(), name
+    assert res["bandpc"][1][1:, 7].min() >= 2   # (the preconditioned CG really iterated)
