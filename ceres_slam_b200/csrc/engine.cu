@@ -1614,11 +1614,13 @@ bool Engine::plan_wband_solver(int w) {
     const int n = n_free;
     const bool forced = opt.bandpc_solver == 2;
     if (!forced && (n < 256 || n < 8 * (w + 1))) return false;
-    // Cost model (us, measured on the ragged 5 k-pose track): a chunk panel of 48 columns costs ~27 (factor + trailing update +
-    // its share of the one-launch back-substitution), a panel of a dense separator system ~26.  One level: C chunks +
-    // the dense solve of (C - 1) 6w separator unknowns.  Two levels: the separator system is block tridiagonal with
-    // blocks of 6w and is chunked again (separators of ONE block), its own separators go to the dense solver.
-    const double tp = 27.0, td = 26.0, sb = 6.0 * w / 48.0;   // sb: panels per separator block
+    // Cost model (us, measured on the ragged 5 k-pose track): a chunk panel of 48 columns costs ~19 + 0.3 C (factor + trailing
+    // update — its tensor-core work grows with the number of chunks in the launch — + its share of the one-launch
+    // back-substitution), a panel of a dense separator system ~26.  One level: C chunks + the dense solve of (C - 1) 6w
+    // separator unknowns.  Two levels: the separator system is block tridiagonal with blocks of 6w and is chunked again
+    // (separators of ONE block; ~19 + 1.2 C2 per panel: three times the tiles per chunk), its own separators go to the
+    // dense solver.  The optimum is flat (20 .. 27 chunks + 4 .. 5 measured within 3 %).
+    const double td = 26.0, sb = 6.0 * w / 48.0;   // sb: panels per separator block
     auto panels = [](double scalars) { return std::ceil(scalars / 48.0); };
     const int Cmax = std::max(1, std::min(1 + kDenseMaxN / (6 * w), (n + w) / (3 * w + 1)));
     static const int force_levels = [] {
@@ -1629,7 +1631,7 @@ bool Engine::plan_wband_solver(int w) {
     int bestC = 1, bestC2 = 0;
     for (int C = 1; C <= Cmax; ++C) {
         const double ns = (C - 1) * 6.0 * w;
-        const double chunk = panels(6.0 * (n - (C - 1) * w) / C) * tp + ns * ns * 8.0 / 6e6;   // (+ clearing the dense T)
+        const double chunk = panels(6.0 * (n - (C - 1) * w) / C) * (19.0 + 0.3 * C) + ns * ns * 8.0 / 6e6;   // (+ clearing the dense T)
         const double one = chunk + panels(ns) * td;
         if (one < best) {
             best = one;
@@ -1639,7 +1641,8 @@ bool Engine::plan_wband_solver(int w) {
         const int B = C - 1;
         if (force_levels == 1) continue;
         for (int C2 = 2; B >= 8 && C2 <= (B + 1) / 3; ++C2) {
-            const double two = chunk + panels(6.0 * w * (B - (C2 - 1)) / C2) * tp + (C2 - 1) * sb * td + 40.0;
+            const double two = chunk + panels(6.0 * w * std::ceil(double(B - (C2 - 1)) / C2)) * (19.0 + 1.2 * C2) +
+                               std::ceil((C2 - 1) * sb) * td + 40.0;
             if (two < best) {
                 best = two;
                 bestC = C;
