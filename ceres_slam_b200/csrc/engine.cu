@@ -1747,6 +1747,7 @@ void Engine::bandpc_solve(const double* rhs, double* y) {
         return v;
     };
     const double normb2 = dot(rhs, rhs);
+    if (std::getenv("CSLAM_BPC_DEBUG")) std::fprintf(stderr, "[bandpc] |b|^2 %.6e (n %d, w %d, P %d)\n", normb2, n, band_w, band_P);
     const double tol2 = 1e-15 * 1e-15 * normb2;
     double rho_old = 0.0;
     int it = 0;
@@ -1762,6 +1763,9 @@ void Engine::bandpc_solve(const double* rhs, double* y) {
             read_scalars(d_pscal.p, ps, PS_COUNT);
             if (ps[PS_FAIL] == 2.0 || !std::isfinite(rho) || !(rho > 0.0)) {
                 fail = !(rho == 0.0);
+                if (std::getenv("CSLAM_BPC_DEBUG"))
+                    std::fprintf(stderr, "[bandpc] stopped at it %d: band factorisation %s, rho %.3e, |b|^2 %.3e\n", it,
+                                 ps[PS_FAIL] == 2.0 ? "FAILED" : "ok", rho, normb2);
                 break;
             }
             launch_bpc_xpby(stream, n6, z, it == 0 ? 0.0 : rho / rho_old, pv);
@@ -1769,6 +1773,8 @@ void Engine::bandpc_solve(const double* rhs, double* y) {
             const double pq = dot(pv, q);
             if (!std::isfinite(pq) || !(pq > 0.0)) {
                 fail = true;
+                if (std::getenv("CSLAM_BPC_DEBUG"))
+                    std::fprintf(stderr, "[bandpc] stopped at it %d: p.Sp = %.3e (rho %.3e): the system is not positive definite along p\n", it, pq, rho);
                 break;
             }
             launch_bpc_update(stream, n6, rho / pq, pv, q, y, r);

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) bpc_spmv_kernel(int n, const int* __restr
 
 __global__ void bpc_xpby_kernel(long long n, const double* __restrict__ z, double beta, double* __restrict__ p) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        p[i] = z[i] + beta * p[i];
+        p[i] = beta == 0.0 ? z[i] : z[i] + beta * p[i];   // (the first direction: p is uninitialised memory, 0 * NaN = NaN)
 }
 __global__ void bpc_update_kernel(long long n, double alpha, const double* __restrict__ p, const double* __restrict__ q,
                                   double* __restrict__ x, double* __restrict__ r) {
