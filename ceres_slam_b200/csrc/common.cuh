@@ -67,20 +67,32 @@ struct DBuf {
     }
     // With a stream the memory comes from the device's stream-ordered pool (cudaMallocAsync): no
     // implicit synchronisation with in-flight copies / kernels and reuse across solves.
-    void alloc(size_t count, cudaStream_t s = nullptr) {
-        if (count == n && p) return;
+    // Returns true when new memory was handed out (same size: the old block is kept as it is).
+    bool alloc_raw(size_t count, cudaStream_t s) {
+        if (count == n && p) return false;
         if (s) {
             release_async(s);
             n = count;
             if (count) CSLAM_CUDA(cudaMallocAsync(&p, count * sizeof(T), s));
-            return;
+            return count != 0;
         }
         release();
         n = count;
         if (count) CSLAM_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        return count != 0;
+    }
+    // New memory is handed out zeroed: what a kernel reads before anything wrote it (a first-iteration
+    // `0 * old` term, padding rows of a tile) must not depend on what the pool held before.  The fill runs at
+    // device bandwidth at upload / structure time, not inside an LM iteration.
+    void alloc(size_t count, cudaStream_t s = nullptr) {
+        if (!alloc_raw(count, s)) return;
+        CSLAM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+        // without a stream the fill ran on the legacy default stream, which the engines' non-blocking
+        // streams do not wait for: finish it before a kernel of theirs can write the block
+        if (!s) CSLAM_CUDA(cudaStreamSynchronize(nullptr));
     }
     void upload(const T* src, size_t count, cudaStream_t s) {
-        alloc(count, s);
+        alloc_raw(count, s);  // fully overwritten by the copy
         if (count) CSLAM_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
     void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
