@@ -2,8 +2,9 @@
 
 * `load_oracle()`  — oracle/_build/liboracle.so: the CPU restatement (prefix `cslam_oracle_`), same
   problem-building signatures as the product's C ABI, plus functor-level entry points;
-* `load_ref()`     — oracle/_ref/libcslam_ref.so: the reference's own unmodified headers compiled
-  against the Eigen / Jet stand-ins (oracle/ref_capi.cpp), functor level only;
+* `load_ref()`     — oracle/_ref/libcslam_ref.so: the reference's own unmodified headers and its
+  point_cloud_aligner.cpp compiled against the Eigen / Jet stand-ins (oracle/ref_capi.cpp): functor level and
+  the RANSAC front end;
 * `OracleProblem`, `build_problem`, `build_phong_problem`, `compute_initial_guess` — the host
   mirror of the product package driven by the oracle library instead, so a test builds the same
   problem twice and compares.
@@ -72,6 +73,10 @@ _REF = {
     "intensity_block": (C.c_int, [_dp] * 6 + [C.c_double, C.c_double, C.c_int] + [_dp] * 7),
     "normal_block": (C.c_int, [_dp] * 7),
     "point_light_shade": (C.c_double, [_dp, _dp, _dp, _dp, C.c_double, _dp]),
+    # the reference's own src/ceres_slam/point_cloud_aligner.cpp (same signature as cslam_ransac_align)
+    "ransac_align": capi._RANSAC_SIG,
+    "kabsch": (None, [C.c_uint32, _dp, _dp, _dp]),
+    "svd3": (None, [_dp, _dp, _dp, _dp]),
 }
 
 _cache = {}

@@ -14,14 +14,22 @@
 // the product.
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
 
+#include <ceres_slam/dataset_problem.hpp>
+#include <ceres_slam/dataset_problem_phong.hpp>
+#include <ceres_slam/dataset_problem_sun.hpp>
 #include <ceres_slam/geometry/geometry.hpp>
 #include <ceres_slam/intensity_error_directional_light.hpp>
 #include <ceres_slam/intensity_error_point_light.hpp>
 #include <ceres_slam/lighting/lighting.hpp>
 #include <ceres_slam/normal_error.hpp>
 #include <ceres_slam/perturbations.hpp>
+#include <ceres_slam/point_cloud_aligner.hpp>
 #include <ceres_slam/pose_error.hpp>
 #include <ceres_slam/stereo_camera.hpp>
 #include <ceres_slam/stereo_reprojection_error.hpp>
@@ -264,6 +272,232 @@ double cslam_ref_point_light_shade(const double* light_pos, const double* vpos, 
     double col = 1.0;
     cs::PointLight<double> light(lp, col);
     return light.shade(v, Vec(Eigen::Map<const Vec>(campos)));
+}
+// ---- front end: PointCloudAligner (src/ceres_slam/point_cloud_aligner.cpp, compiled unmodified from
+// where it lies as a second translation unit: oracle/Makefile) ---------------------------------------
+// compute_transformation_and_inliers (:64-136) per pose pair, as compute_initial_guess calls it
+// (dataset_problem.cpp:232-234); same argument order as cslam_oracle_ransac_align / cslam_ransac_align.
+// The draws are the real std::mt19937(42) + std::uniform_int_distribution<uint> of this compiler, the
+// SVD is the stand-in's (ref_standin/Eigen/Core); `rng_variant` is ignored.
+int cslam_ref_ransac_align(int, uint32_t n_pairs, const uint32_t* offsets, const double* pts0, const double* pts1,
+                           const double* intr5, uint32_t num_iters, double thresh, int, double* T12_out,
+                           uint8_t* inlier_out, uint32_t* n_inliers_out) {
+    Camera::ConstPtr cam = std::make_shared<const Camera>(intr5[0], intr5[1], intr5[2], intr5[3], intr5[4]);
+    cs::PointCloudAligner aligner;
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        const uint32_t o = offsets[p], n = offsets[p + 1] - o;
+        std::vector<Pt> a, b;
+        for (uint32_t i = 0; i < n; ++i) {
+            a.push_back(Pt(Eigen::Map<const Pt>(pts0 + 3 * size_t(o + i))));
+            b.push_back(Pt(Eigen::Map<const Pt>(pts1 + 3 * size_t(o + i))));
+        }
+        SE3 T;
+        std::vector<uint> in = aligner.compute_transformation_and_inliers(T, a, b, cam, num_iters, thresh);
+        std::memcpy(T12_out + 12 * size_t(p), T.data(), 24);
+        std::memcpy(T12_out + 12 * size_t(p) + 3, T.rotation().data(), 72);
+        if (inlier_out) {
+            for (uint32_t i = 0; i < n; ++i) inlier_out[o + i] = 0;
+            for (uint i : in) inlier_out[o + i] = 1;
+        }
+        if (n_inliers_out) n_inliers_out[p] = uint32_t(in.size());
+    }
+    return 0;
+}
+// compute_transformation (:12-62) on n >= 3 correspondences: T_1_0 as [t | R row-major]
+void cslam_ref_kabsch(uint32_t n, const double* pts0, const double* pts1, double* T12) {
+    cs::PointCloudAligner aligner;
+    std::vector<Pt> a, b;
+    for (uint32_t i = 0; i < n; ++i) {
+        a.push_back(Pt(Eigen::Map<const Pt>(pts0 + 3 * size_t(i))));
+        b.push_back(Pt(Eigen::Map<const Pt>(pts1 + 3 * size_t(i))));
+    }
+    SE3 T = aligner.compute_transformation(a, b);
+    std::memcpy(T12, T.data(), 24);
+    std::memcpy(T12 + 3, T.rotation().data(), 72);
+}
+// the stand-in SVD on its own: A (row-major 3x3) -> U, s, V (row-major), for the test of the stand-in
+void cslam_ref_svd3(const double* A9, double* U9, double* s3, double* V9) {
+    Eigen::Matrix3d A;
+    load(A, A9);
+    Eigen::JacobiSVD<Eigen::Matrix3d> svd(A, Eigen::ComputeThinU | Eigen::ComputeThinV);
+    for (int i = 0; i < 3; ++i) {
+        s3[i] = svd.singularValue(i);
+        for (int j = 0; j < 3; ++j) {
+            U9[3 * i + j] = svd.matrixU()(i, j);
+            V9[3 * i + j] = svd.matrixV()(i, j);
+        }
+    }
+}
+
+// ---- the three DatasetProblem classes (src/ceres_slam/dataset_problem{,_sun,_phong}.cpp, compiled unmodified
+// as further translation units): CSV readers, compute_initial_guess(k1, k2), CSV writers — everything the
+// drivers do around solveWindow (dataset_vo.cpp:107-136, dataset_vo_sun.cpp:232-290, dataset_ba_phong.cpp:300-340).
+// kind: 0 = DatasetProblem, 1 = DatasetProblemSun, 2 = DatasetProblemPhong.
+namespace {
+struct RefDataset {
+    int kind = 0;
+    cs::DatasetProblem vo;
+    cs::DatasetProblemSun sun;
+    cs::DatasetProblemPhong phong;
+    explicit RefDataset(int k, bool dir_light) : kind(k), phong(dir_light) {}
+};
+// the readers narrate on std::cerr / std::cout; keep the test output clean
+struct Quiet {
+    std::ostringstream sink;   // (declared first: the stream buffers below are taken from it)
+    std::streambuf *o, *e;
+    Quiet() : o(std::cout.rdbuf(sink.rdbuf())), e(std::cerr.rdbuf(sink.rdbuf())) {}
+    ~Quiet() {
+        std::cout.rdbuf(o);
+        std::cerr.rdbuf(e);
+    }
+};
+void put_pose(const SE3& T, double* P12) {
+    std::memcpy(P12, T.data(), 24);
+    std::memcpy(P12 + 3, T.rotation().data(), 72);
+}
+}  // namespace
+
+void* cslam_ref_dataset_open(int kind, const char* f1, const char* f2, const char* f3, int dir_light) {
+    Quiet q;
+    std::unique_ptr<RefDataset> d(new RefDataset(kind, dir_light != 0));
+    bool ok = false;
+    try {
+        if (kind == 0) ok = d->vo.read_csv(f1);
+        if (kind == 1) ok = d->sun.read_csv(f1, f2, f3);
+        if (kind == 2) ok = d->phong.read_csv(f1);
+    } catch (...) {
+        ok = false;
+    }
+    return ok ? d.release() : nullptr;
+}
+void cslam_ref_dataset_close(void* h) { delete static_cast<RefDataset*>(h); }
+void cslam_ref_dataset_dims(void* h, uint32_t* n_states, uint32_t* n_points, uint64_t* n_obs, uint32_t* n_materials) {
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    *n_materials = 0;
+    if (d.kind == 0) { *n_states = d.vo.num_states; *n_points = d.vo.num_points; *n_obs = d.vo.stereo_obs_list.size(); }
+    if (d.kind == 1) { *n_states = d.sun.num_states; *n_points = d.sun.num_points; *n_obs = d.sun.stereo_obs_list.size(); }
+    if (d.kind == 2) {
+        *n_states = d.phong.num_states; *n_points = d.phong.num_vertices; *n_obs = d.phong.stereo_obs_list.size();
+        *n_materials = d.phong.num_materials;
+    }
+}
+// what the readers stored: per observation the state index (the run of equal ids / timestamps it belongs to, as
+// obs_indices_at_state groups them), the point id and (u, v, d); intrinsics; the shared variance (kinds 0, 2)
+void cslam_ref_dataset_observations(void* h, uint32_t* state_of_obs, uint32_t* point_ids, double* uvd, double* intr5,
+                                    double* var3) {
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    auto fill = [&](auto& p, const std::vector<uint>& ids, uint n_states) {
+        for (size_t i = 0; i < p.stereo_obs_list.size(); ++i) {
+            point_ids[i] = ids[i];
+            for (int c = 0; c < 3; ++c) uvd[3 * i + c] = p.stereo_obs_list[i](c);
+        }
+        for (uint k = 0; k < n_states; ++k) {
+            std::vector<uint> idx;
+            try { idx = p.obs_indices_at_state(k); } catch (...) { break; }
+            for (uint i : idx) state_of_obs[i] = k;
+        }
+        intr5[0] = p.camera->fu(); intr5[1] = p.camera->fv(); intr5[2] = p.camera->cu(); intr5[3] = p.camera->cv();
+        intr5[4] = p.camera->b();
+    };
+    if (d.kind == 0) { fill(d.vo, d.vo.point_ids, d.vo.num_states); for (int c = 0; c < 3; ++c) var3[c] = d.vo.stereo_obs_var(c); }
+    if (d.kind == 1) fill(d.sun, d.sun.point_ids, d.sun.num_states);
+    if (d.kind == 2) { fill(d.phong, d.phong.vertex_ids, d.phong.num_states); for (int c = 0; c < 3; ++c) var3[c] = d.phong.stereo_obs_var(c); }
+}
+// kind 1: per-observation stereo covariances (9 each, row-major), per state: has-sun flag, observed sun direction
+// (camera frame), its 2x2 covariance, reference direction (global frame)
+void cslam_ref_dataset_sun_data(void* h, double* stereo_covars9, uint8_t* has_sun, double* sun_obs3, double* sun_covar4,
+                                double* sun_dir_g3) {
+    cs::DatasetProblemSun& p = static_cast<RefDataset*>(h)->sun;
+    for (size_t i = 0; i < p.stereo_obs_covars.size(); ++i)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) stereo_covars9[9 * i + 3 * r + c] = p.stereo_obs_covars[i](r, c);
+    for (uint k = 0; k < p.num_states; ++k) {
+        has_sun[k] = p.state_has_sun_obs[k] ? 1 : 0;
+        for (int c = 0; c < 3; ++c) {
+            sun_obs3[3 * k + c] = has_sun[k] ? p.sun_obs_list[k](c) : 0.0;
+            sun_dir_g3[3 * k + c] = has_sun[k] ? p.sun_dir_g[k](c) : 0.0;
+        }
+        for (int r = 0; r < 2; ++r)
+            for (int c = 0; c < 2; ++c) sun_covar4[4 * k + 2 * r + c] = has_sun[k] ? p.sun_obs_covars[k](r, c) : 0.0;
+    }
+}
+// kind 2: per observation material id, intensity, observed normal; the shared normal variance, intensity variance,
+// the light (position, or unit direction with dir_light)
+void cslam_ref_dataset_phong_data(void* h, uint32_t* material_ids, double* intensities, double* normal_obs3, double* normal_var3,
+                                  double* int_var, double* light3) {
+    cs::DatasetProblemPhong& p = static_cast<RefDataset*>(h)->phong;
+    for (size_t i = 0; i < p.int_list.size(); ++i) {
+        material_ids[i] = p.material_ids[i];
+        intensities[i] = p.int_list[i];
+        for (int c = 0; c < 3; ++c) normal_obs3[3 * i + c] = p.normal_obs_list[i](c);
+    }
+    for (int c = 0; c < 3; ++c) {
+        normal_var3[c] = p.normal_obs_var(c);
+        light3[c] = p.directional_light ? p.light_dir(c) : p.light_pos(c);
+    }
+    *int_var = p.int_var;
+}
+// compute_initial_guess(k1, k2); returns 0 when the sun variant gave up (fewer than 3 inliers), 1 otherwise
+int cslam_ref_dataset_initial_guess(void* h, uint32_t k1, uint32_t k2) {
+    Quiet q;
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    if (d.kind == 0) d.vo.compute_initial_guess(k1, k2);
+    if (d.kind == 1) return d.sun.compute_initial_guess(k1, k2) ? 1 : 0;
+    if (d.kind == 2) d.phong.compute_initial_guess(k1, k2);
+    return 1;
+}
+void cslam_ref_dataset_reset_points(void* h) {
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    if (d.kind == 0) d.vo.reset_points();
+    if (d.kind == 1) d.sun.reset_points();
+}
+// current state: poses [t | R] per state, point positions and initialised flags; kind 2 also the vertex normals,
+// Phong parameters (ka, ks, exponent — Material::phong_params order) and texture per INITIALISED vertex
+void cslam_ref_dataset_state(void* h, double* poses12, double* points3, uint8_t* initialized, double* normals3,
+                             double* phong3, double* texture1) {
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    auto put = [&](auto& p, auto& pts, const std::vector<bool>& init) {
+        for (size_t k = 0; k < p.poses.size(); ++k) put_pose(p.poses[k], poses12 + 12 * k);
+        for (size_t j = 0; j < init.size(); ++j) initialized[j] = init[j] ? 1 : 0;
+        (void)pts;
+    };
+    if (d.kind == 0) {
+        put(d.vo, d.vo.map_points, d.vo.initialized_point);
+        for (size_t j = 0; j < d.vo.map_points.size(); ++j)
+            for (int c = 0; c < 3; ++c) points3[3 * j + c] = d.vo.initialized_point[j] ? d.vo.map_points[j](c) : 0.0;
+    }
+    if (d.kind == 1) {
+        put(d.sun, d.sun.map_points, d.sun.initialized_point);
+        for (size_t j = 0; j < d.sun.map_points.size(); ++j)
+            for (int c = 0; c < 3; ++c) points3[3 * j + c] = d.sun.initialized_point[j] ? d.sun.map_points[j](c) : 0.0;
+    }
+    if (d.kind == 2) {
+        put(d.phong, d.phong.map_vertices, d.phong.initialized_vertex);
+        for (size_t j = 0; j < d.phong.map_vertices.size(); ++j) {
+            const bool in = d.phong.initialized_vertex[j];
+            for (int c = 0; c < 3; ++c) {
+                points3[3 * j + c] = in ? d.phong.map_vertices[j].position()(c) : 0.0;
+                if (normals3) normals3[3 * j + c] = in ? d.phong.map_vertices[j].normal()(c) : 0.0;
+                if (phong3) phong3[3 * j + c] = in ? d.phong.map_vertices[j].material()->phong_params()(c) : 0.0;
+            }
+            if (texture1) texture1[j] = in ? d.phong.map_vertices[j].texture()->col() : 0.0;
+        }
+    }
+}
+// overwrite the poses (what solveWindow leaves behind is outside this library; lets a test write a known state)
+void cslam_ref_dataset_set_pose(void* h, uint32_t k, const double* P12) {
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    SE3 T = SE3(Eigen::Map<const SE3>(P12));
+    if (d.kind == 0) d.vo.poses[k] = T;
+    if (d.kind == 1) d.sun.poses[k] = T;
+    if (d.kind == 2) d.phong.poses[k] = T;
+}
+int cslam_ref_dataset_write(void* h, const char* filename) {
+    Quiet q;
+    RefDataset& d = *static_cast<RefDataset*>(h);
+    if (d.kind == 0) return d.vo.write_csv(filename) ? 1 : 0;
+    if (d.kind == 1) return d.sun.write_csv(filename) ? 1 : 0;
+    return d.phong.write_csv(filename) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -240,3 +240,57 @@ def evaluate(kind, lib, cases):
         out.append(dict(R=R.tolist(), log_of_exp=back.tolist()))
     res["so3"] = out
     return res
+
+
+# ---- front end: pose pairs for PointCloudAligner (src/ceres_slam/point_cloud_aligner.cpp) --------------------
+REF_RANSAC = os.path.join(ROOT, "tests", "golden", "ref_ransac.json")
+RANSAC_SETTINGS = [(400, 4.0), (400, 25.0), (60, 9.0)]   # (num_iters, thresh); 400 / 25 are the header's defaults
+
+
+def build_ransac_pairs():
+    """Matched, triangulated point clouds of consecutive frames of a noisy synthetic track with 15 % gross
+    outliers (what compute_initial_guess hands to the aligner, dataset_problem.cpp:196-234), every pair with at
+    least 3 matches (below that the reference's draw loop does not terminate), plus one exactly rigid triple."""
+    from ceres_slam_b200 import initial_guess as ig, synthetic as syn
+    tr = syn.make_track(40, 15, 10, seed=5, pix_sigma=0.25)
+    rng = np.random.default_rng(6)
+    bad = rng.random(tr["uvd"].shape[0]) < 0.15
+    tr["uvd"][bad] += rng.normal(0, 25.0, (int(bad.sum()), 3))
+    tr["uvd"][:, 2] = np.maximum(tr["uvd"][:, 2], 1.0)
+    rg = ig.state_ranges(tr["obs_cam"], tr["n_poses"])
+    pt = tr["obs_pt"].astype(np.int64)
+    pairs0, pairs1 = [], []
+    for k in range(1, tr["n_poses"]):
+        kp, kc = ig.match_pair(pt[rg[k - 1]:rg[k]], pt[rg[k]:rg[k + 1]])
+        if min(kp.size, kc.size) < 3:
+            continue
+        pairs0.append(ig.triangulate(tr["cam"], tr["uvd"][rg[k - 1]:rg[k]][kp]))
+        pairs1.append(ig.triangulate(tr["cam"], tr["uvd"][rg[k]:rg[k + 1]][kc]))
+    R = _so3_exp(np.array([0.02, -0.05, 0.01]))
+    tri0 = np.array([[1.0, 0.5, 9.0], [-2.0, 0.3, 14.0], [0.5, -1.0, 20.0]])
+    pairs0.append(tri0)
+    pairs1.append(tri0 @ R.T + np.array([0.1, 0.0, -0.3]))
+    return tr["cam"], pairs0, pairs1
+
+
+def ransac_inputs_digest(cam, pairs0, pairs1):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.array([cam[k] for k in ("fu", "fv", "cu", "cv", "b")], dtype=np.float64).tobytes())
+    for a, b in zip(pairs0, pairs1):
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        h.update(np.ascontiguousarray(b, dtype=np.float64).tobytes())
+    return h.hexdigest()
+
+
+def evaluate_ransac(entry, cam, pairs0, pairs1, rng_variant=1):
+    """[{num_iters, thresh, T (n_pairs x 12), inliers (index lists), counts}] through any library's
+    ransac_align entry (the reference's source, the oracle, the CUDA kernel: one signature)."""
+    from ceres_slam_b200 import initial_guess as ig
+    out = []
+    for num_iters, thresh in RANSAC_SETTINGS:
+        T, inl, cnt = ig.ransac_align(pairs0, pairs1, cam, num_iters=num_iters, thresh=thresh, rng_variant=rng_variant,
+                                      entry=entry)
+        out.append({"num_iters": num_iters, "thresh": thresh, "T": [[float(x) for x in row] for row in T],
+                    "inliers": [[int(i) for i in np.flatnonzero(m)] for m in inl], "counts": [int(c) for c in cnt]})
+    return out

@@ -199,6 +199,88 @@ def test_closed_forms_match_reference_vectors(committed, cf):
     compare(got, {k: exp[k] for k in got}, cases, RJ_TOL)
 
 
+# ---- front end: the reference's own point_cloud_aligner.cpp ----------------------------------------
+RANSAC_T_TOL = 1e-9   # the best hypothesis is a 3-point fit: its rotation comes out of an SVD of a rank-2 matrix
+
+
+@pytest.fixture(scope="module")
+def committed_ransac():
+    with open(rc.REF_RANSAC) as f:
+        return json.load(f)
+
+
+def compare_ransac(got, exp):
+    worst = 0.0
+    assert len(got) == len(exp) == len(rc.RANSAC_SETTINGS)
+    for g, e in zip(got, exp):
+        assert (g["num_iters"], g["thresh"]) == (e["num_iters"], e["thresh"])
+        assert g["counts"] == e["counts"]
+        assert g["inliers"] == e["inliers"]
+        worst = max(worst, float(np.abs(A(g["T"]) - A(e["T"])).max()))
+    assert worst <= RANSAC_T_TOL, worst
+    return worst
+
+
+@needs_ref
+def test_standin_svd_against_lapack(ref):
+    """The one piece of the front end that is NOT the reference's code: Eigen::JacobiSVD's stand-in
+    (oracle/ref_standin/Eigen/Core).  Factors reproduce the matrix, are orthogonal, singular values are LAPACK's,
+    non-negative and decreasing (the contract compute_transformation relies on) — full rank, rank 2 (three
+    points), tiny scale."""
+    rng = np.random.default_rng(0)
+    for t in range(600):
+        M = rng.normal(0, 1, (3, 3))
+        if t % 3 == 0:
+            M = rng.normal(0, 1, (3, 2)) @ rng.normal(0, 1, (2, 3))
+        if t % 7 == 0:
+            M *= 1e-6
+        U, sv, V = np.zeros(9), np.zeros(3), np.zeros(9)
+        ref.svd3(d(np.ascontiguousarray(M)), d(U), d(sv), d(V))
+        U, V = U.reshape(3, 3), V.reshape(3, 3)
+        sc = np.abs(M).max()
+        assert sv[0] >= sv[1] >= sv[2] >= 0
+        assert np.abs(U @ np.diag(sv) @ V.T - M).max() <= 1e-14 * sc
+        assert np.abs(U.T @ U - np.eye(3)).max() <= 1e-14 and np.abs(V.T @ V - np.eye(3)).max() <= 1e-14
+        assert np.abs(sv - np.linalg.svd(M, compute_uv=False)).max() <= 1e-14 * sc
+
+
+@needs_ref
+def test_committed_ransac_vectors_are_the_reference_source_output(ref, committed_ransac):
+    cam, p0, p1 = rc.build_ransac_pairs()
+    assert rc.ransac_inputs_digest(cam, p0, p1) == committed_ransac["inputs_sha256"], \
+        "inputs changed: rerun tests/golden/make_ref_golden.py"
+    assert compare_ransac(rc.evaluate_ransac(ref.ransac_align, cam, p0, p1), committed_ransac["expected"]) == 0.0
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_oracle_ransac_matches_reference_source_vectors(oracle, committed_ransac, variant):
+    """The restated RANSAC (oracle/ransac.hpp: restated draws, one-sided long-double SVD) against the reference's
+    own source (real std::uniform_int_distribution, two-sided SVD stand-in): same best hypothesis — identical
+    inlier index lists and counts for every pair and setting — and the same transformation.  Variant 1 is this
+    image's libstdc++ draw for draw; variant 0 (older libstdc++) differs only near bucket edges, which these
+    pairs (at most ~110 matches) do not hit."""
+    cam, p0, p1 = rc.build_ransac_pairs()
+    assert rc.ransac_inputs_digest(cam, p0, p1) == committed_ransac["inputs_sha256"]
+    worst = compare_ransac(rc.evaluate_ransac(oracle.ransac_align, cam, p0, p1, rng_variant=variant),
+                           committed_ransac["expected"])
+    print("oracle RANSAC vs the reference's source: worst |dT|", worst)
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [3, 4, 50])
+def test_oracle_kabsch_matches_reference_source(ref, oracle, n):
+    """compute_transformation (point_cloud_aligner.cpp:12-62) on n correspondences, reference source vs oracle."""
+    rng = np.random.default_rng(100 + n)
+    for _ in range(20):
+        a = rng.normal(0, 5, (n, 3)) + np.array([0, 0, 15.0])
+        R = syn.so3_exp(rng.normal(0, 0.3, (1, 3)))[0]
+        b = a @ R.T + rng.normal(0, 0.5, 3) + rng.normal(0, 0.05, (n, 3))
+        Tr, To = np.zeros(12), np.zeros(12)
+        ref.kabsch(n, d(np.ascontiguousarray(a)), d(np.ascontiguousarray(b)), d(Tr))
+        oracle.kabsch(n, d(np.ascontiguousarray(a)), d(np.ascontiguousarray(b)), d(To))
+        assert np.abs(Tr - To).max() <= 1e-12
+
+
 # ---- GPU: the CUDA path through the C ABI -------------------------------------------------------
 def _one_pose(cases, pose, point=None):
     p = BAProblem()
@@ -269,3 +351,15 @@ def test_cuda_matches_reference_headers_on_whole_tracks(product):
             err = np.abs(eg[k] - er[k]).reshape(er[k].shape[0], -1).max(axis=1)
             scale = np.abs(er[k]).reshape(er[k].shape[0], -1).max(axis=1)
             assert (err <= RJ_TOL * np.maximum(scale, 1e-300)).all(), (k, float((err / np.maximum(scale, 1e-300)).max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cuda_ransac_matches_reference_source_vectors(product, committed_ransac, variant):
+    """`cslam_ransac_align` (one launch for all pairs) against what the reference's own
+    point_cloud_aligner.cpp produced: identical inlier sets and counts, transformations to 1e-9."""
+    cam, p0, p1 = rc.build_ransac_pairs()
+    assert rc.ransac_inputs_digest(cam, p0, p1) == committed_ransac["inputs_sha256"]
+    worst = compare_ransac(rc.evaluate_ransac(product.ransac_align, cam, p0, p1, rng_variant=variant),
+                           committed_ransac["expected"])
+    print("CUDA RANSAC vs the reference's source: worst |dT|", worst)
