@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned to the reference's own unmodified headers / sources compiled in
+// oracle/_ref: every residual / Jacobian / plus block and the RANSAC front end (tests/test_ref_pin.py,
+// tests/test_ref_frontend.py).  UNPINNED: the solver rules of problem.hpp / phong_problem.hpp (Ceres is absent).
 // C entry points over the CPU restatement, shaped like include/cslam_b200.h (prefix
 // `cslam_oracle_`) so the same Python harness can drive either library.  Only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load this.

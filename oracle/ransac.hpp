@@ -7,6 +7,8 @@
 // libstdc++ algorithms are restated (variant 0: scaling + rejection, GCC <= 10; variant 1: Lemire,
 // GCC >= 11) and tests/test_ransac.py pins variant 1 and the Mersenne twister against the
 // std:: classes of the compiler in this image.
+// PINNED: oracle/_ref compiles the reference's own point_cloud_aligner.cpp (unmodified) and tests/test_ref_pin.py
+// checks this restatement against it (identical inlier index lists, transformations to 2e-13).
 // Eigen::JacobiSVD is not available; the rotation U diag(1,1,det U det V) V^T is computed with a
 // one-sided Jacobi SVD in long double (the result is unique whenever the two largest singular
 // values are distinct and non-zero, so any accurate SVD gives the same rotation).
