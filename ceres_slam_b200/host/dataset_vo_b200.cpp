@@ -103,6 +103,21 @@ static void solveWindow(Track& t, unsigned k1, unsigned k2, int max_iters) {
     std::cout << summary.BriefReport() << std::endl << std::endl;
 }
 
+// DatasetProblem::write_csv (dataset_problem.cpp:125-166): <stem>_poses.csv and <stem>_map.csv, the latter one row per
+// point that is initialised at the time of the call (none after the last window's reset_points: a header-only file,
+// as the reference leaves it)
+static void write_outputs(const Track& t, const std::string& filename) {
+    const std::string stem = file_stem(filename);
+    write_poses_csv(stem + "_poses.csv", t.poses, t.num_states);
+    std::ofstream map_file(stem + "_map.csv");
+    map_file.precision(17);
+    map_file << "point_id, x, y, z\n";
+    for (unsigned j = 0; j < t.num_points; ++j)
+        if (t.initialized[j])
+            map_file << j << "," << t.points[3 * size_t(j)] << "," << t.points[3 * size_t(j) + 1] << ","
+                     << t.points[3 * size_t(j) + 2] << "\n";
+}
+
 int main(int argc, char** argv) {
     const std::string usage("usage: dataset_vo_b200 <input_file> [--window N=0] [--max-iters M=1000] [--init ransac|constant]");
     if (argc < 2) {
@@ -163,6 +178,6 @@ int main(int argc, char** argv) {
     std::cerr << "cslam_b200 timing: windows=" << n_windows << " loop_s="
               << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count()
               << " initial_guess_s=" << guess_s << " solve_s=" << solve_s << " warmup_s=" << warm_s << std::endl;
-    write_poses_csv(file_stem(filename) + "_poses.csv", t.poses, t.num_states);
+    write_outputs(t, filename);                                                             // :134
     return EXIT_SUCCESS;
 }

@@ -134,6 +134,15 @@ void fh_reset_points(void* h) {
     Data& d = *static_cast<Data*>(h);
     std::fill(d.initialized.begin(), d.initialized.end(), 0);
 }
+// the driver's output files for `filename` (<stem>_poses.csv, and what else the driver writes)
+void fh_write(void* h, const char* filename) {
+    Data& d = *static_cast<Data*>(h);
+#if KIND == 1
+    write_poses_csv(file_stem(filename) + "_poses.csv", d.poses, d.num_states);   // dataset_vo_sun_b200.cpp main
+#else
+    write_outputs(d, filename);
+#endif
+}
 void fh_state(void* h, double* poses12, double* points3, uint8_t* initialized, double* normals3, double* phong3, double* texture1) {
     Data& d = *static_cast<Data*>(h);
     std::memcpy(poses12, d.poses.data(), d.poses.size() * sizeof(double));

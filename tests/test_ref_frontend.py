@@ -289,3 +289,50 @@ def test_sun_front_end_gives_up_below_three_inliers(shims, tmp_path):
     assert ref.initial_guess(0, 12) == 1 and host.initial_guess(0, 12) == 1
     ref.close()
     host.close()
+
+
+def _read_table(path):
+    with open(path) as f:
+        lines = [ln.rstrip("\n") for ln in f if ln.strip()]
+    header = [h.strip() for h in lines[0].split(",")]
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[1:]]) if len(lines) > 1 else np.zeros((0, len(header)))
+    return header, rows
+
+
+@needs_ref
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("kind,directional", [(0, False), (1, False), (2, False), (2, True)])
+def test_host_writers_match_reference_writers(shims, tmp_path, kind, directional):
+    """write_csv (dataset_problem.cpp:125-166, dataset_problem_sun.cpp:181-204, dataset_problem_phong.cpp:175-232)
+    against the drivers' output: the same files (<stem>_poses.csv, _map.csv, _lights.csv), the same header lines, the
+    same rows.  The reference prints 4 significant digits (utils.hpp:34 CommaInitFmt), the product 17: values agree
+    to the reference's rounding."""
+    tr, files = _files(kind, tmp_path, directional)
+    lib = orc.load_ref()
+    shims[kind].fh_set_ransac_entry(_entry_address(lib, "ransac_align"))
+    shims[kind].fh_write.argtypes = [_vp, C.c_char_p]
+    shims[kind].fh_write.restype = None
+    lib.dll.cslam_ref_dataset_write.argtypes = [_vp, C.c_char_p]
+    lib.dll.cslam_ref_dataset_write.restype = C.c_int
+    ref = FrontEnd(lib.dll, "cslam_ref_dataset_", kind, files, directional)
+    host = FrontEnd(shims[kind], "fh_", kind, files, directional)
+    n = _usable_states(tr)
+    assert ref.initial_guess(0, n) == 1 and host.initial_guess(0, n) == 1      # a state worth writing
+    (tmp_path / "r").mkdir()
+    (tmp_path / "h").mkdir()
+    assert lib.dll.cslam_ref_dataset_write(ref.h, os.fsencode(str(tmp_path / "r" / "out.csv"))) == 1
+    shims[kind].fh_write(host.h, os.fsencode(str(tmp_path / "h" / "out.csv")))
+    names = sorted(os.listdir(tmp_path / "r"))
+    assert names == sorted(os.listdir(tmp_path / "h"))
+    assert names == {0: ["out_map.csv", "out_poses.csv"], 1: ["out_poses.csv"],
+                     2: ["out_lights.csv", "out_map.csv", "out_poses.csv"]}[kind]
+    for name in names:
+        hr, rr = _read_table(tmp_path / "r" / name)
+        hh, rh = _read_table(tmp_path / "h" / name)
+        assert hr == hh, name
+        if name == "out_poses.csv":      # states beyond the batch: default-constructed vs first pose (see above)
+            rr, rh = rr[:n], rh[:n]
+        assert rr.shape == rh.shape and rr.shape[0] > 0, name
+        assert np.all(np.abs(rr - rh) <= 5.01e-4 * np.abs(rh) + 1e-12), name
+    ref.close()
+    host.close()
