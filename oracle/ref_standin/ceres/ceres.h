@@ -16,6 +16,8 @@
 #include <cmath>
 #include <limits>
 #include <memory>
+#include <typeinfo>
+#include <utility>
 #include <vector>
 
 #include <Eigen/Core>
@@ -130,6 +132,9 @@ class CostFunction {
     virtual bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const = 0;
     const std::vector<int>& parameter_block_sizes() const { return sizes_; }
     int num_residuals() const { return num_residuals_; }
+    // stand-in only: the functor an AutoDiffCostFunction owns (for oracle/ref_driver's Problem facade)
+    virtual const void* functor_ptr() const { return nullptr; }
+    virtual const std::type_info& functor_type() const { return typeid(void); }
 
    protected:
     std::vector<int> sizes_;
@@ -185,6 +190,9 @@ class AutoDiffCostFunction : public CostFunction {
         }
         return true;
     }
+
+    const void* functor_ptr() const override { return functor_.get(); }
+    const std::type_info& functor_type() const override { return typeid(CostFunctor); }
 
    private:
     std::unique_ptr<CostFunctor> functor_;
