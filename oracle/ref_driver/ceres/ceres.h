@@ -11,15 +11,19 @@
 // whose Jet / AutoDiffCostFunction / AutoDiffLocalParameterization stand-ins it re-exports.  The cost functors keep
 // their data in private members; this header includes the functor headers with those members visible
 // (`#define private public` around the include, nothing else sees it).  A maintainer's binding would add accessors.
-// Covers the plain stereo driver (config 1).  Never part of the product.
+// Covers the plain stereo driver (config 1) and the sun-sensor driver (config 2: HuberLoss, pose prior, DOGLEG options,
+// ceres::Covariance).  Never part of the product.
 #ifndef CSLAM_REF_DRIVER_CERES_FACADE
 #define CSLAM_REF_DRIVER_CERES_FACADE
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -35,7 +39,9 @@
 #include <ceres_slam/stereo_camera.hpp>
 #include <ceres_slam/utils/utils.hpp>
 #define private public
+#include <ceres_slam/pose_error.hpp>
 #include <ceres_slam/stereo_reprojection_error.hpp>
+#include <ceres_slam/sun_sensor_error.hpp>
 #undef private
 
 #ifdef CSLAM_FACADE_ORACLE
@@ -66,8 +72,32 @@ namespace ceres {
 class LossFunction {
    public:
     virtual ~LossFunction() {}
+    virtual void Evaluate(double s, double rho[3]) const = 0;   // rho(s), rho'(s), rho''(s), s = |r|^2
+};
+// rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond (Ceres' documented HuberLoss)
+class HuberLoss : public LossFunction {
+   public:
+    explicit HuberLoss(double a) : a_(a), b_(a * a) {}
+    void Evaluate(double s, double rho[3]) const override {
+        if (s > b_) {
+            const double r = std::sqrt(s);
+            rho[0] = 2.0 * a_ * r - b_;
+            rho[1] = std::max(std::numeric_limits<double>::min(), a_ / r);
+            rho[2] = -rho[1] / (2.0 * s);
+        } else {
+            rho[0] = s;
+            rho[1] = 1.0;
+            rho[2] = 0.0;
+        }
+    }
+    double a_, b_;
 };
 typedef void* ResidualBlockId;
+
+enum TrustRegionStrategyType { LEVENBERG_MARQUARDT = 0, DOGLEG = 1 };
+enum DoglegType { TRADITIONAL_DOGLEG = 0, SUBSPACE_DOGLEG = 1 };
+enum SparseLinearAlgebraLibraryType { SUITE_SPARSE, CX_SPARSE, EIGEN_SPARSE, NO_SPARSE };
+enum CovarianceAlgorithmType { DENSE_SVD, SPARSE_QR };
 
 struct Solver {
     struct Options {
@@ -76,6 +106,8 @@ struct Solver {
         int num_linear_solver_threads = 1;
         int max_num_iterations = 50;        // Ceres' default; the drivers set 1000
         bool use_nonmonotonic_steps = false;
+        TrustRegionStrategyType trust_region_strategy_type = LEVENBERG_MARQUARDT;
+        DoglegType dogleg_type = TRADITIONAL_DOGLEG;
     };
     struct Summary {
         cslam_b200::Summary inner;
@@ -99,8 +131,46 @@ class Problem {
                 for (int c = 0; c < 3; ++c) W[3 * r + c] = f->stiffness_(r, c);
             }
             note_pose(x0);
+            blocks_.push_back({cost, nullptr, {x0, x1}});
             inner_.AddStereoBlock(x0, x1, obs, W);
             ++n_stereo_;
+            return cost;
+        }
+        throw std::runtime_error(std::string("facade: cost functor not on the path: ") + cost->functor_type().name());
+    }
+    // one-block residuals: SunSensorErrorAutomatic (+ HuberLoss) dataset_vo_sun.cpp:83-99, PoseErrorAutomatic :113-117
+    ResidualBlockId AddResidualBlock(CostFunction* cost, LossFunction* loss, double* x0) {
+        owned_.emplace_back(cost);
+        if (loss) loss_owned_.emplace_back(loss);
+        blocks_.push_back({cost, loss, {x0}});
+        note_pose(x0);
+        if (cost->functor_type() == typeid(ceres_slam::SunSensorErrorAutomatic)) {
+            const auto* f = static_cast<const ceres_slam::SunSensorErrorAutomatic*>(cost->functor_ptr());
+            double obs[3], ref[3], W2[4];
+            for (int r = 0; r < 3; ++r) obs[r] = f->observed_sun_dir_c_(r), ref[r] = f->expected_sun_dir_g_(r);
+            for (int r = 0; r < 2; ++r)
+                for (int c = 0; c < 2; ++c) W2[2 * r + c] = f->stiffness_(r, c);
+            double huber = 0.0;
+            if (loss) {
+                const HuberLoss* h = dynamic_cast<const HuberLoss*>(loss);
+                if (!h) throw std::runtime_error("facade: only HuberLoss is on the path");
+                huber = h->a_;
+            }
+            inner_.AddSunBlock(x0, obs, ref, W2, f->az_err_thresh_, f->zen_err_thresh_, huber);
+            return cost;
+        }
+        if (cost->functor_type() == typeid(ceres_slam::PoseErrorAutomatic)) {
+            if (loss) throw std::runtime_error("facade: a loss on the pose prior is not part of the path");
+            const auto* f = static_cast<const ceres_slam::PoseErrorAutomatic*>(cost->functor_ptr());
+            double Tref[12], W6[36];
+            for (int r = 0; r < 3; ++r) {
+                Tref[r] = f->T_k_0_ref_.translation()(r);
+                for (int c = 0; c < 3; ++c) Tref[3 + 3 * r + c] = f->T_k_0_ref_.rotation().matrix()(r, c);
+            }
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) W6[6 * r + c] = f->stiffness_(r, c);
+            inner_.AddPosePrior(x0, Tref, W6);
+            ++n_prior_;
             return cost;
         }
         throw std::runtime_error(std::string("facade: cost functor not on the path: ") + cost->functor_type().name());
@@ -113,12 +183,21 @@ class Problem {
     }
     void SetParameterBlockConstant(double* x) {
         note_pose(x);
+        constant_.push_back(x);
         inner_.SetParameterBlockConstant(x);
     }
 
+    struct Block {
+        CostFunction* cost;
+        LossFunction* loss;
+        std::vector<double*> x;
+    };
     cslam_b200::Problem inner_;
     std::vector<double*> poses_;   // pose blocks in order of first appearance
-    size_t n_stereo_ = 0;
+    std::vector<double*> constant_;
+    std::vector<Block> blocks_;
+    const LocalParameterization* lp() const { return lp_owned_.get(); }
+    size_t n_stereo_ = 0, n_prior_ = 0;
 
    private:
     void note_pose(double* x) {
@@ -127,6 +206,7 @@ class Problem {
         poses_.push_back(x);
     }
     std::vector<std::unique_ptr<CostFunction>> owned_;
+    std::vector<std::unique_ptr<LossFunction>> loss_owned_;
     std::unique_ptr<LocalParameterization> lp_owned_;
 };
 
@@ -148,7 +228,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
     o.max_num_iterations = options.max_num_iterations;   // dataset_vo.cpp:69
     o.use_nonmonotonic_steps = options.use_nonmonotonic_steps ? 1 : 0;  // :70
     o.num_threads = options.num_threads;                 // :67 (the GPU back end ignores it)
-    if (problem->n_stereo_ == 0) {
+    o.trust_region_strategy = int(options.trust_region_strategy_type);   // dataset_vo_sun.cpp:142
+    o.dogleg_type = int(options.dogleg_type);                            // :143
+    if (problem->n_stereo_ == 0 && problem->n_prior_ == 0) {
         // Ceres solves an empty problem trivially; the C ABI wants at least a camera
         cslam_summary s{};
         if (summary) summary->inner.s = s;
@@ -160,6 +242,143 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
     if (summary) summary->inner = inner;
     facade_trace(*problem, inner.s);
 }
+
+// ceres::Covariance as dataset_vo_sun.cpp:159-183 uses it: Compute({(pose, pose)}, &problem), then
+// GetCovarianceBlockInTangentSpace(pose, pose, out 6x6 row-major).
+//  * product build: cslam_covariance_block of the solved problem (the library's own kernel).
+//  * oracle build (the C ABI of the oracle has no covariance entry): (J^T J)^-1 formed HERE from the problem's own cost
+//    functions — the reference's functors differentiated by the AutoDiffCostFunction stand-in, chained with the
+//    SE3Perturbation plus-Jacobian, loss-corrected like Ceres' Corrector does for rho'' <= 0 (scale by sqrt(rho')) — with a
+//    dense Cholesky factorisation; what SPARSE_QR computes for a full-rank Jacobian.
+class Covariance {
+   public:
+    struct Options {
+        int num_threads = 1;
+        SparseLinearAlgebraLibraryType sparse_linear_algebra_library_type = SUITE_SPARSE;
+        CovarianceAlgorithmType algorithm_type = SPARSE_QR;
+    };
+    explicit Covariance(const Options&) {}
+    bool Compute(const std::vector<std::pair<const double*, const double*>>& blocks, Problem* problem) {
+        problem_ = problem;
+        cov_.clear();
+        for (const auto& b : blocks) {
+            if (b.first != b.second) throw std::runtime_error("facade: only diagonal covariance blocks are on the path");
+            std::vector<double> c(36);
+            if (!block(const_cast<double*>(b.first), c.data())) return false;
+            cov_[b.first] = c;
+        }
+        return true;
+    }
+    bool GetCovarianceBlockInTangentSpace(const double* x0, const double* x1, double* out) const {
+        auto it = cov_.find(x0);
+        if (x0 != x1 || it == cov_.end()) return false;
+        for (int i = 0; i < 36; ++i) out[i] = it->second[i];
+        if (const char* path = std::getenv("CSLAM_FACADE_TRACE")) {
+            std::ofstream f(path, std::ios::app);
+            f << std::setprecision(17) << "{\"covariance\": [";
+            for (int i = 0; i < 36; ++i) f << (i ? ", " : "") << out[i];
+            f << "]}\n";
+        }
+        return true;
+    }
+
+   private:
+    bool block(double* pose, double* out36) {
+#ifndef CSLAM_FACADE_ORACLE
+        return problem_->inner_.GetCovarianceBlockInTangentSpace(pose, out36);
+#else
+        Problem& p = *problem_;
+        // variable blocks: non-constant poses (6 tangent columns each), then points (3 each) in order of appearance
+        std::map<const double*, int> col;
+        int n = 0;
+        auto is_const = [&](const double* x) {
+            for (const double* c : p.constant_)
+                if (c == x) return true;
+            return false;
+        };
+        for (double* x : p.poses_)
+            if (!is_const(x)) col[x] = n, n += 6;
+        for (const auto& b : p.blocks_)
+            if (b.x.size() == 2 && !col.count(b.x[1])) col[b.x[1]] = n, n += 3;
+        if (!col.count(pose)) return false;
+        std::vector<double> H(size_t(n) * n, 0.0);
+        for (const auto& b : p.blocks_) {
+            const int m = b.cost->num_residuals();
+            std::vector<double> r(m), Ja(size_t(m) * 12), Jb(size_t(m) * 3), P(72);
+            double* jac[2] = {Ja.data(), Jb.data()};
+            const double* params[2] = {b.x[0], b.x.size() > 1 ? b.x[1] : nullptr};
+            if (!b.cost->Evaluate(params, r.data(), jac)) return false;
+            double scale = 1.0;
+            if (b.loss) {
+                double s = 0, rho[3];
+                for (double v : r) s += v * v;
+                b.loss->Evaluate(s, rho);
+                scale = std::sqrt(rho[1]);   // Corrector with rho'' <= 0 (Huber): alpha = 0
+            }
+            // tangent-space Jacobian of the block, m x w, and where its columns live
+            std::vector<std::pair<int, std::vector<double>>> parts;   // (first column, m x width row-major)
+            if (col.count(b.x[0])) {
+                p.lp()->ComputeJacobian(b.x[0], P.data());
+                std::vector<double> Jt(size_t(m) * 6, 0.0);
+                for (int i = 0; i < m; ++i)
+                    for (int c = 0; c < 6; ++c) {
+                        double a = 0;
+                        for (int k = 0; k < 12; ++k) a += Ja[size_t(i) * 12 + k] * P[k * 6 + c];
+                        Jt[size_t(i) * 6 + c] = scale * a;
+                    }
+                parts.push_back({col[b.x[0]], Jt});
+            }
+            if (b.x.size() > 1) {
+                std::vector<double> Jt(Jb);
+                for (double& v : Jt) v *= scale;
+                parts.push_back({col[b.x[1]], Jt});
+            }
+            for (const auto& A : parts)
+                for (const auto& B : parts) {
+                    const int wa = int(A.second.size()) / m, wb = int(B.second.size()) / m;
+                    for (int i = 0; i < wa; ++i)
+                        for (int j = 0; j < wb; ++j) {
+                            double a = 0;
+                            for (int q = 0; q < m; ++q) a += A.second[size_t(q) * wa + i] * B.second[size_t(q) * wb + j];
+                            H[size_t(A.first + i) * n + B.first + j] += a;
+                        }
+                }
+        }
+        // Cholesky H = L L^T, then the six columns of H^-1 that belong to the pose
+        for (int j = 0; j < n; ++j) {
+            double d = H[size_t(j) * n + j];
+            for (int k = 0; k < j; ++k) d -= H[size_t(j) * n + k] * H[size_t(j) * n + k];
+            if (!(d > 0.0)) return false;   // rank deficient: Ceres' Compute fails
+            d = std::sqrt(d);
+            H[size_t(j) * n + j] = d;
+            for (int i = j + 1; i < n; ++i) {
+                double a = H[size_t(i) * n + j];
+                for (int k = 0; k < j; ++k) a -= H[size_t(i) * n + k] * H[size_t(j) * n + k];
+                H[size_t(i) * n + j] = a / d;
+            }
+        }
+        const int c0 = col[pose];
+        for (int c = 0; c < 6; ++c) {
+            std::vector<double> y(n, 0.0);
+            y[c0 + c] = 1.0;
+            for (int i = 0; i < n; ++i) {
+                double a = y[i];
+                for (int k = 0; k < i; ++k) a -= H[size_t(i) * n + k] * y[k];
+                y[i] = a / H[size_t(i) * n + i];
+            }
+            for (int i = n - 1; i >= 0; --i) {
+                double a = y[i];
+                for (int k = i + 1; k < n; ++k) a -= H[size_t(k) * n + i] * y[k];
+                y[i] = a / H[size_t(i) * n + i];
+            }
+            for (int r = 0; r < 6; ++r) out36[6 * r + c] = y[c0 + r];
+        }
+        return true;
+#endif
+    }
+    Problem* problem_ = nullptr;
+    std::map<const double*, std::vector<double>> cov_;
+};
 
 }  // namespace ceres
 #endif  // CSLAM_REF_DRIVER_CERES_FACADE

@@ -1,4 +1,5 @@
-"""The reference's OWN driver, unmodified, on this repo's back end.
+"""The reference's OWN drivers, unmodified, on this repo's back end (the
+second half of the file is tests/dataset_vo_sun.cpp: Huber loss, pose prior, SUBSPACE_DOGLEG, ceres::Covariance).
 
 `oracle/_ref/libref_dataset_vo_{oracle,b200}.so` are /root/reference/tests/dataset_vo.cpp compiled as it is (its
 `main` renamed) together with the reference's dataset_problem.cpp / point_cloud_aligner.cpp, against
@@ -32,8 +33,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _lib(kind):
-    so = os.path.join(REF_DIR, f"libref_dataset_vo_{kind}.so")
+def _lib(kind, driver="dataset_vo"):
+    so = os.path.join(REF_DIR, f"libref_{driver}_{kind}.so")
     if not os.path.exists(so) and os.path.isdir(orc.REFERENCE_INCLUDE):
         orc.build_ref()
     if not os.path.exists(so):
@@ -44,19 +45,22 @@ def _lib(kind):
 _RUNNER = r"""
 import ctypes as C, sys
 lib = C.CDLL(sys.argv[1])
-lib.cslam_ref_dataset_vo_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
-args = [b"dataset_vo"] + [a.encode() for a in sys.argv[2:]]
-sys.exit(lib.cslam_ref_dataset_vo_main(len(args), (C.c_char_p * len(args))(*args)))
+main = getattr(lib, "cslam_ref_" + sys.argv[2] + "_main")
+main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+args = [sys.argv[2].encode()] + [a.encode() for a in sys.argv[3:]]
+sys.exit(main(len(args), (C.c_char_p * len(args))(*args)))
 """
 
 
-def _run_reference_driver(so, csv, window, trace):
-    """In a child process: the driver narrates on stdout / stderr, and a crash must not take the test session down."""
+def _run_reference_driver(so, csv, window, trace, driver="dataset_vo", extra=()):
+    """In a child process: the driver narrates on stdout / stderr, and a crash must not take the test session down.
+    `csv`: the input file, or the list of input files."""
     env = dict(os.environ, CSLAM_FACADE_TRACE=trace)
     if os.path.exists(trace):
         os.remove(trace)
-    r = subprocess.run([sys.executable, "-c", _RUNNER, so, csv, "--window", str(window)], env=env, capture_output=True,
-                       text=True, timeout=600)
+    files = [csv] if isinstance(csv, str) else list(csv)
+    r = subprocess.run([sys.executable, "-c", _RUNNER, so, driver] + files + ["--window", str(window)] + list(extra),
+                       env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     with open(trace) as f:
         return [json.loads(line) for line in f], r.stdout
@@ -116,3 +120,69 @@ def test_reference_driver_on_b200_matches_driver_mirror(product, tmp_path, windo
     syn.write_track_csv(tr, csv)
     rows, _ = _run_reference_driver(so, csv, window, str(tmp_path / "trace.jsonl"))
     _compare_with_mirror(tr, rows, window, 1e-6, max(1, len(rows) // 10))
+
+
+# ---- config 2: tests/dataset_vo_sun.cpp (both passes, Huber loss, pose prior, SUBSPACE_DOGLEG, covariance chain) ----
+def _sun_case(n, tmp_path):
+    tr = syn.add_sun(_steady_track(n, seed=23, per_obs_W=True), sigma_deg=1.0)
+    paths = [str(tmp_path / f) for f in ("track.csv", "sun_ref.csv", "sun_obs.csv")]
+    syn.write_sun_csvs(tr, *paths)
+    # the mirror reads what the driver reads: covariances are the CSV's (inverse squares of the stiffness)
+    W = np.asarray(tr["W"]).reshape(-1, 3, 3)
+    cov = np.stack([0.5 * (c + c.T) for c in (np.linalg.inv(w @ w) for w in W)]).reshape(-1, 9)
+    sW = tr["sun_W"].reshape(-1, 2, 2)
+    sun = dict(dir_g=tr["sun_ref_g"], obs=tr["sun_obs_c"], covars=np.stack([np.linalg.inv(w @ w) for w in sW]).reshape(-1, 4),
+               has=np.ones(n, dtype=bool))
+    return tr, paths, cov, sun
+
+
+def _compare_sun_with_mirror(tr, cov, sun, rows, tol, cov_tol, max_iteration_mismatches):
+    n = tr["n_poses"]
+    solves = [r for r in rows if "poses" in r]
+    covs = [r for r in rows if "covariance" in r]
+    assert len(solves) == len(covs) == 2 * (n - 1)           # pass 1 (VO) and pass 2 (with the sun blocks)
+    kw = dict(window=2, max_iters=1000, dogleg=True)         # dataset_vo_sun.cpp:140-143
+    its = []
+    p1, c1 = dm.dataset_vo_sun(tr, cov, sun, tr["poses_gt"][0], use_sun=False, on_window=lambda k1, s: its.append(s.num_iterations), **kw)
+    p2, c2 = dm.dataset_vo_sun(tr, cov, sun, tr["poses_gt"][0], use_sun=True, huber=1.0, poses=p1.copy(), pose_covars=c1.copy(),
+                               on_window=lambda k1, s: its.append(s.num_iterations), **kw)
+    bad = sum(r["iterations"] != i for r, i in zip(solves, its))
+    assert bad <= max_iteration_mismatches, ([r["iterations"] for r in solves], its)
+    worst = 0.0
+    for q, (pm, cm) in enumerate(((p1, c1), (p2, c2))):
+        P, Cv = np.zeros((n, 12)), np.zeros((n, 36))
+        for k1 in range(n - 1):
+            P[k1:k1 + 2] = np.array(solves[q * (n - 1) + k1]["poses"]).reshape(2, 12)
+            Cv[k1 + 1] = covs[q * (n - 1) + k1]["covariance"]
+        err = float(np.abs(P - pm).max())
+        assert err <= tol * np.abs(pm).max(), (q, err)
+        cerr = float(np.abs(Cv[1:] - cm[1:]).max() / np.abs(cm[1:]).max())
+        assert cerr <= cov_tol, (q, cerr)
+        worst = max(worst, err)
+    return worst
+
+
+def test_reference_sun_driver_on_oracle_equals_driver_mirror(tmp_path):
+    """tests/dataset_vo_sun.cpp, unmodified: per window the stereo blocks with per-observation stiffness (indexed by
+    point id, as the reference does), the sun block under a Huber loss, the prior from the previous window's
+    covariance, SUBSPACE_DOGLEG, then ceres::Covariance of the second pose.  In this build the covariance is formed
+    inside the facade from the REFERENCE'S functors (autodiff Jacobians, dense Cholesky), the mirror forms it from the
+    oracle's Jacobians through a sparse LU: poses to 1e-10, covariances to 1e-9 relative over both passes."""
+    so = _lib("oracle", "dataset_vo_sun")
+    tr, paths, cov, sun = _sun_case(16, tmp_path)
+    rows, _ = _run_reference_driver(so, paths, 2, str(tmp_path / "trace.jsonl"), "dataset_vo_sun", ["--huber-param", "1.0"])
+    assert os.path.exists(tmp_path / "track_poses.csv") and os.path.exists(tmp_path / "track_obs_poses.csv")   # :301, :322
+    err = _compare_sun_with_mirror(tr, cov, sun, rows, 1e-10, 1e-9, 0)
+    print(f"reference sun driver on the oracle vs mirror: worst pose difference {err:.3g}")
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: the CPU leg (same facade, "
+                   "oracle instead of the CUDA library) is verified, this leg has not run on a B200 yet")
+def test_reference_sun_driver_on_b200_matches_driver_mirror(product, tmp_path):
+    """The reference's tests/dataset_vo_sun.cpp, unmodified, with ceres::Solve and ceres::Covariance answered by the
+    CUDA library (window kernel with the DOGLEG loop on the device, cslam_covariance_block)."""
+    so = _lib("b200", "dataset_vo_sun")
+    tr, paths, cov, sun = _sun_case(25, tmp_path)
+    rows, _ = _run_reference_driver(so, paths, 2, str(tmp_path / "trace.jsonl"), "dataset_vo_sun", ["--huber-param", "1.0"])
+    _compare_sun_with_mirror(tr, cov, sun, rows, 1e-6, 1e-5, 5)
