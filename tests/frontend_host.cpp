@@ -5,10 +5,16 @@
 // tests/test_ref_frontend.py compares the result with the reference's own DatasetProblem* classes.
 //
 // Compiled three times (-DKIND=0 dataset_vo_b200, 1 dataset_vo_sun_b200, 2 dataset_ba_phong_b200): the driver
-// source is included as it is, its `main` renamed.  Nothing here is shipped.
+// source is included as it is, its `main` renamed.  With -DFH_ABI_TRACE also the C ABI calls of the driver's solves are
+// redirected (recorded, then answered by the CPU oracle): the whole driver runs here.  Nothing here is shipped.
 #include <cstdint>
 #include <cstring>
 
+#ifdef FH_ABI_TRACE
+// the whole driver on the CPU: its C ABI calls go through the recording layer oracle/ref_driver/abi_trace.cpp to the oracle
+#define CSLAM_REMAP_PREFIX cslam_trace_
+#include "../oracle/ref_driver/abi_remap.h"
+#endif
 #include "../include/cslam_b200.h"
 
 typedef cslam_status (*ransac_entry_t)(int, uint32_t, const uint32_t*, const double*, const double*, const double*, uint32_t,
@@ -36,6 +42,16 @@ typedef PhongDataset Data;
 #undef main
 
 extern "C" {
+
+// the driver's own main (argument parsing, window loop, output files)
+int fh_driver_main(int argc, char** argv) {
+    try {
+        return driver_main(argc, argv);
+    } catch (const std::exception& e) {
+        std::cerr << "driver failed: " << e.what() << std::endl;
+        return 70;
+    }
+}
 
 void fh_set_ransac_entry(void* fn) { g_entry = reinterpret_cast<ransac_entry_t>(fn); }
 

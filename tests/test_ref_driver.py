@@ -1,5 +1,6 @@
-"""The reference's OWN drivers, unmodified, on this repo's back end (the
-second half of the file is tests/dataset_vo_sun.cpp: Huber loss, pose prior, SUBSPACE_DOGLEG, ceres::Covariance).
+"""The reference's OWN drivers, unmodified, on this repo's back end (all three configs: the
+second part of the file is tests/dataset_vo_sun.cpp — Huber loss, pose prior, SUBSPACE_DOGLEG, ceres::Covariance — the
+third compares the C ABI call streams of tests/dataset_ba_phong.cpp / dataset_vo.cpp with the restated drivers').
 
 `oracle/_ref/libref_dataset_vo_{oracle,b200}.so` are /root/reference/tests/dataset_vo.cpp compiled as it is (its
 `main` renamed) together with the reference's dataset_problem.cpp / point_cloud_aligner.cpp, against
@@ -186,3 +187,114 @@ def test_reference_sun_driver_on_b200_matches_driver_mirror(product, tmp_path):
     tr, paths, cov, sun = _sun_case(25, tmp_path)
     rows, _ = _run_reference_driver(so, paths, 2, str(tmp_path / "trace.jsonl"), "dataset_vo_sun", ["--huber-param", "1.0"])
     _compare_sun_with_mirror(tr, cov, sun, rows, 1e-6, 1e-5, 5)
+
+
+# ---- the C ABI call streams of the reference's drivers and of this repo's restated drivers -------------------------------
+# Both end in the same boundary: include/cslam_b200.h.  With every call recorded on its way to the CPU oracle
+# (oracle/ref_driver/abi_trace.cpp) two drivers that assemble the same problems — blocks in the same order, stiffness,
+# constant flags, bounds, options, and (config 3) vertex / material / texture tables, across every window and stage —
+# leave the same stream.  Left: the reference's driver source over the Ceres-API facade.  Right: the product's driver
+# source (tests/frontend_host.cpp includes it as it is; its RANSAC calls answered by the reference's own aligner).
+_RUN_HOST = r"""
+import ctypes as C, sys
+ref = C.CDLL(sys.argv[2])
+lib = C.CDLL(sys.argv[1])
+lib.fh_set_ransac_entry.argtypes = [C.c_void_p]
+lib.fh_set_ransac_entry(C.cast(ref.cslam_ref_ransac_align, C.c_void_p))
+lib.fh_driver_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+args = [b"driver"] + [a.encode() for a in sys.argv[3:]]
+sys.exit(lib.fh_driver_main(len(args), (C.c_char_p * len(args))(*args)))
+"""
+
+
+def _host_trace_lib(kind):
+    from ceres_slam_b200 import capi
+    capi.load_product()
+    name = {0: "dataset_vo", 2: "dataset_ba_phong"}[kind]
+    so = os.path.join(ROOT, "tests", "_build", f"libdriver_{name}_trace.so")
+    host = os.path.join(ROOT, "ceres_slam_b200", "host")
+    srcs = [os.path.join(ROOT, "tests", "frontend_host.cpp"), os.path.join(ROOT, "oracle", "ref_driver", "abi_trace.cpp")]
+    deps = srcs + [os.path.join(ROOT, "oracle", "ref_driver", "abi_remap.h"), os.path.join(ROOT, "include", "cslam_b200.h")] + \
+        [os.path.join(host, f) for f in os.listdir(host) if f.endswith((".cpp", ".hpp"))]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        orc.build_oracle()
+        ob, cs = os.path.join(ROOT, "oracle", "_build"), os.path.join(ROOT, "ceres_slam_b200", "csrc")
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-fPIC", "-shared",
+                               f"-DKIND={kind}", "-DFH_ABI_TRACE", "-o", so] + srcs +
+                              ["-L" + ob, "-loracle", "-Wl,-rpath," + ob, "-L" + cs, "-lcslam_b200", "-Wl,-rpath," + cs])
+    return so
+
+
+def _abi_streams(driver, kind, write_input, flags, tmp_path):
+    ref_so, host_so = _lib("trace", driver), _host_trace_lib(kind)
+    aligner = os.path.join(REF_DIR, "libcslam_ref.so")
+    out = []
+    for side, cmd in (("ref", [sys.executable, "-c", _RUNNER, ref_so, driver]), ("host", [sys.executable, "-c", _RUN_HOST, host_so, aligner])):
+        d = tmp_path / side
+        d.mkdir()
+        files = write_input(d)
+        trace = str(d / "abi.jsonl")
+        r = subprocess.run(cmd + files + list(flags), env=dict(os.environ, CSLAM_ABI_TRACE=trace), capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, (side, r.stderr[-2000:])
+        with open(trace) as f:
+            out.append([json.loads(line) for line in f])
+    return out
+
+
+def _compare_streams(a_calls, b_calls):
+    assert [c["call"] for c in a_calls] == [c["call"] for c in b_calls]
+    worst, n_solves = 0.0, 0
+    for a, b in zip(a_calls, b_calls):
+        assert set(a) == set(b), a["call"]
+        n_solves += a["call"] == "solve"
+        for k in a:
+            if k == "call":
+                continue
+            # inert under LEVENBERG_MARQUARDT, and the one default cslam_options_init does not take from Ceres
+            # (it starts at SUBSPACE_DOGLEG, what the reference's drivers set whenever they choose DOGLEG)
+            if k == "dogleg_type" and a["trust_region_strategy"] == 0 and b["trust_region_strategy"] == 0:
+                continue
+            x, y = np.asarray(a[k], dtype=float), np.asarray(b[k], dtype=float)
+            assert x.shape == y.shape, (a["call"], k, x.shape, y.shape)
+            if x.size:
+                worst = max(worst, float(np.abs(x - y).max() / max(1.0, np.abs(x).max())))
+    return worst, n_solves
+
+
+@pytest.mark.parametrize("flags,n_solves", [((), 1), (("--nolight",), 1), (("--dirlight",), 1), (("--multistage",), 3),
+                                            (("--window", "4"), 7), (("--window", "3", "--multistage"), 24)])
+def test_phong_driver_abi_stream_equals_reference_driver(tmp_path, flags, n_solves):
+    """Config 3: tests/dataset_ba_phong.cpp (unmodified) against host/dataset_ba_phong_b200.cpp, call for call: the
+    initial guess, every window, every stage (stereo only / lighting only with poses and positions constant / joint),
+    point and directional light, bounds, SUBSPACE_DOGLEG options — and what each solve leaves in the parameter blocks.
+    The two streams are bit-identical today; the test allows 1e-12."""
+    def write_input(d):
+        tr = syn.add_phong(_steady_track(10, seed=29), directional="--dirlight" in flags, shared_textures=True)
+        path = str(d / "scene.csv")
+        syn.write_phong_csv(tr, path)
+        return [path]
+
+    a, b = _abi_streams("dataset_ba_phong", 2, write_input, flags, tmp_path)
+    worst, solves = _compare_streams(a, b)
+    assert solves == n_solves
+    assert worst <= 1e-12, worst
+    print(f"dataset_ba_phong {' '.join(flags) or '(joint)'}: {len(a)} C ABI calls, {solves} solves, worst difference {worst:.3g}")
+
+
+@pytest.mark.parametrize("window", [2, 0])
+def test_vo_driver_abi_stream_equals_reference_driver(tmp_path, window):
+    """Config 1 the same way.  The product driver first solves its first window once on a copy (an untimed warm-up for
+    CUDA context creation): that leading group of calls is dropped before comparing."""
+    def write_input(d):
+        path = str(d / "track.csv")
+        syn.write_track_csv(_steady_track(14, seed=17), path)
+        return [path]
+
+    a, b = _abi_streams("dataset_vo", 0, write_input, ("--window", str(window)), tmp_path)
+    first_solve = [c["call"] for c in b].index("solve")
+    b = b[first_solve + 1:]
+    worst, solves = _compare_streams(a, b)
+    assert solves == (13 if window == 2 else 1)
+    assert worst <= 1e-12, worst
