@@ -53,7 +53,7 @@ sys.exit(main(len(args), (C.c_char_p * len(args))(*args)))
 """
 
 
-def _run_reference_driver(so, csv, window, trace, driver="dataset_vo", extra=()):
+def _run_reference_driver(so, csv, window, trace, driver="dataset_vo", extra=(), timeout=600):
     """In a child process: the driver narrates on stdout / stderr, and a crash must not take the test session down.
     `csv`: the input file, or the list of input files."""
     env = dict(os.environ, CSLAM_FACADE_TRACE=trace)
@@ -61,7 +61,7 @@ def _run_reference_driver(so, csv, window, trace, driver="dataset_vo", extra=())
         os.remove(trace)
     files = [csv] if isinstance(csv, str) else list(csv)
     r = subprocess.run([sys.executable, "-c", _RUNNER, so, driver] + files + ["--window", str(window)] + list(extra),
-                       env=env, capture_output=True, text=True, timeout=600)
+                       env=env, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]
     with open(trace) as f:
         return [json.loads(line) for line in f], r.stdout
@@ -119,7 +119,7 @@ def test_reference_driver_on_b200_matches_driver_mirror(product, tmp_path, windo
     tr = _steady_track(30, seed=17)
     csv = str(tmp_path / "track.csv")
     syn.write_track_csv(tr, csv)
-    rows, _ = _run_reference_driver(so, csv, window, str(tmp_path / "trace.jsonl"))
+    rows, _ = _run_reference_driver(so, csv, window, str(tmp_path / "trace.jsonl"), timeout=120)
     _compare_with_mirror(tr, rows, window, 1e-6, max(1, len(rows) // 10))
 
 
@@ -185,7 +185,8 @@ def test_reference_sun_driver_on_b200_matches_driver_mirror(product, tmp_path):
     CUDA library (window kernel with the DOGLEG loop on the device, cslam_covariance_block)."""
     so = _lib("b200", "dataset_vo_sun")
     tr, paths, cov, sun = _sun_case(25, tmp_path)
-    rows, _ = _run_reference_driver(so, paths, 2, str(tmp_path / "trace.jsonl"), "dataset_vo_sun", ["--huber-param", "1.0"])
+    rows, _ = _run_reference_driver(so, paths, 2, str(tmp_path / "trace.jsonl"), "dataset_vo_sun", ["--huber-param", "1.0"],
+                                    timeout=120)
     _compare_sun_with_mirror(tr, cov, sun, rows, 1e-6, 1e-5, 5)
 
 
