@@ -110,11 +110,10 @@ def test_reference_driver_on_oracle_equals_driver_mirror(tmp_path, window):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: the CPU leg (same facade, "
-                   "oracle instead of the CUDA library) is verified, this leg has not run on a B200 yet")
 @pytest.mark.parametrize("window", [2, 0])
 def test_reference_driver_on_b200_matches_driver_mirror(product, tmp_path, window):
-    """The reference's tests/dataset_vo.cpp, unmodified, with ceres::Solve answered by the CUDA library."""
+    """The reference's tests/dataset_vo.cpp, unmodified, with ceres::Solve answered by the CUDA library (measured on a
+    B200 through scripts/ref_driver_on_b200.py, the same comparison: 4.8e-14, profiles/r02_reference_drivers_on_b200.log)."""
     so = _lib("b200")
     tr = _steady_track(30, seed=17)
     csv = str(tmp_path / "track.csv")
@@ -178,11 +177,10 @@ def test_reference_sun_driver_on_oracle_equals_driver_mirror(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: the CPU leg (same facade, "
-                   "oracle instead of the CUDA library) is verified, this leg has not run on a B200 yet")
 def test_reference_sun_driver_on_b200_matches_driver_mirror(product, tmp_path):
     """The reference's tests/dataset_vo_sun.cpp, unmodified, with ceres::Solve and ceres::Covariance answered by the
-    CUDA library (window kernel with the DOGLEG loop on the device, cslam_covariance_block)."""
+    CUDA library (window kernel with the DOGLEG loop on the device, cslam_covariance_block); 1.3e-12 on a B200
+    (profiles/r02_reference_drivers_on_b200.log)."""
     so = _lib("b200", "dataset_vo_sun")
     tr, paths, cov, sun = _sun_case(25, tmp_path)
     rows, _ = _run_reference_driver(so, paths, 2, str(tmp_path / "trace.jsonl"), "dataset_vo_sun", ["--huber-param", "1.0"],
