@@ -4,6 +4,8 @@
 // C entry points over the CPU restatement, shaped like include/cslam_b200.h (prefix
 // `cslam_oracle_`) so the same Python harness can drive either library.  Only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load this.
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -188,6 +190,88 @@ int cslam_oracle_evaluate(cslam_oracle_problem* p, int apply_loss, double* cost,
     cp(J_sun, ev.J_sun);
     cp(r_prior, ev.r_pr);
     cp(J_prior, ev.J_pr);
+    return CSLAM_OK;
+}
+// ceres::Covariance::Compute + GetCovarianceBlockInTangentSpace for one pose block (dataset_vo_sun.cpp:159-183), same
+// contract as cslam_covariance_block: the (cam, cam) 6x6 block of (J^T J)^-1 in tangent coordinates at the current
+// parameter values, loss-corrected Jacobians, no damping.  Dense normal equations over the free poses and the points,
+// Cholesky, six solves (a window has a few hundred unknowns).
+int cslam_oracle_covariance_block(cslam_oracle_problem* p, uint32_t cam, double* cov36) {
+    Problem& q = p->prob;
+    if (cam >= q.pose_const.size() || q.pose_const[cam]) {
+        p->err = "covariance of a constant or unknown pose";
+        return CSLAM_ERR_INVALID;
+    }
+    Problem::Eval ev;
+    if (!q.evaluate(q.poses, q.points, true, true, ev, p->opt.num_threads)) {
+        p->err = "evaluation failed";
+        return CSLAM_ERR_NUMERIC;
+    }
+    const size_t nc = q.pose_const.size();
+    std::vector<long> pcol(nc, -1);
+    long n = 0;
+    for (size_t k = 0; k < nc; ++k)
+        if (!q.pose_const[k]) pcol[k] = n, n += 6;
+    uint32_t n_pts = 0;
+    for (uint32_t j : q.st_pt) n_pts = std::max(n_pts, j + 1);
+    const long x0 = n;
+    n += 3 * long(n_pts);
+    std::vector<double> H(size_t(n) * size_t(n), 0.0);
+    // H += A^T B for an m-row block pair with column offsets ca, cb and widths wa, wb (row-major inputs)
+    auto acc = [&](const double* A, long ca, int wa, const double* B, long cb, int wb, int m) {
+        for (int i = 0; i < wa; ++i)
+            for (int j = 0; j < wb; ++j) {
+                double a = 0;
+                for (int r = 0; r < m; ++r) a += A[r * wa + i] * B[r * wb + j];
+                H[size_t(ca + i) * n + size_t(cb + j)] += a;
+            }
+    };
+    for (size_t i = 0; i < q.n_stereo(); ++i) {
+        const double *Jc = &ev.Jc_st[18 * i], *Jp = &ev.Jp_st[9 * i];
+        const long cc = pcol[q.st_cam[i]], cp = x0 + 3 * long(q.st_pt[i]);
+        if (cc >= 0) {
+            acc(Jc, cc, 6, Jc, cc, 6, 3);
+            acc(Jc, cc, 6, Jp, cp, 3, 3);
+            acc(Jp, cp, 3, Jc, cc, 6, 3);
+        }
+        acc(Jp, cp, 3, Jp, cp, 3, 3);
+    }
+    for (size_t i = 0; i < q.suns.size(); ++i)
+        if (pcol[q.suns[i].cam] >= 0) acc(&ev.J_sun[12 * i], pcol[q.suns[i].cam], 6, &ev.J_sun[12 * i], pcol[q.suns[i].cam], 6, 2);
+    for (size_t i = 0; i < q.priors.size(); ++i)
+        if (pcol[q.priors[i].cam] >= 0) acc(&ev.J_pr[36 * i], pcol[q.priors[i].cam], 6, &ev.J_pr[36 * i], pcol[q.priors[i].cam], 6, 6);
+    for (long j = 0; j < n; ++j) {
+        double d = H[size_t(j) * n + j];
+        for (long k = 0; k < j; ++k) d -= H[size_t(j) * n + k] * H[size_t(j) * n + k];
+        if (!(d > 0.0)) {
+            p->err = "covariance: the Jacobian is rank deficient";
+            return CSLAM_ERR_NUMERIC;
+        }
+        d = std::sqrt(d);
+        H[size_t(j) * n + j] = d;
+        for (long i = j + 1; i < n; ++i) {
+            double a = H[size_t(i) * n + j];
+            for (long k = 0; k < j; ++k) a -= H[size_t(i) * n + k] * H[size_t(j) * n + k];
+            H[size_t(i) * n + j] = a / d;
+        }
+    }
+    const long c0 = pcol[cam];
+    std::vector<double> y(n);
+    for (int c = 0; c < 6; ++c) {
+        std::fill(y.begin(), y.end(), 0.0);
+        y[c0 + c] = 1.0;
+        for (long i = 0; i < n; ++i) {
+            double a = y[i];
+            for (long k = 0; k < i; ++k) a -= H[size_t(i) * n + k] * y[k];
+            y[i] = a / H[size_t(i) * n + i];
+        }
+        for (long i = n - 1; i >= 0; --i) {
+            double a = y[i];
+            for (long k = i + 1; k < n; ++k) a -= H[size_t(k) * n + i] * y[k];
+            y[i] = a / H[size_t(i) * n + i];
+        }
+        for (int r = 0; r < 6; ++r) cov36[6 * r + c] = y[c0 + r];
+    }
     return CSLAM_OK;
 }
 // ---- lighting blocks (dataset_ba_phong.cpp:100-205) ------------------------------------------------

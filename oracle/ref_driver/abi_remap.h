@@ -26,4 +26,5 @@
 #define cslam_set_materials CSLAM_REMAP(set_materials)
 #define cslam_set_textures CSLAM_REMAP(set_textures)
 #define cslam_set_vertices CSLAM_REMAP(set_vertices)
+#define cslam_covariance_block CSLAM_REMAP(covariance_block)
 #endif

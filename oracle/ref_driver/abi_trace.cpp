@@ -128,6 +128,11 @@ cslam_status cslam_trace_set_vertices(cslam_problem* p, uint32_t n, double* norm
     g_arrays[p].normals = normals3;
     return cslam_oracle_set_vertices(p, n, normals3, textures, material_id);
 }
+cslam_status cslam_trace_covariance_block(cslam_problem* p, uint32_t cam, double* cov6x6) {
+    const cslam_status st = cslam_oracle_covariance_block(p, cam, cov6x6);
+    Line("covariance_block").num("cam", cam).num("status", int(st)).arr("covariance", cov6x6, st == CSLAM_OK ? 36 : 0);
+    return st;
+}
 cslam_status cslam_trace_solve(cslam_problem* p, cslam_summary* s) {
     const cslam_status st = cslam_oracle_solve(p, s);
     const Arrays& a = g_arrays[p];

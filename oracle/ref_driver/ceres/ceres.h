@@ -351,8 +351,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
 
 // ceres::Covariance as dataset_vo_sun.cpp:159-183 uses it: Compute({(pose, pose)}, &problem), then
 // GetCovarianceBlockInTangentSpace(pose, pose, out 6x6 row-major).
-//  * product build: cslam_covariance_block of the solved problem (the library's own kernel).
-//  * oracle build (the C ABI of the oracle has no covariance entry): (J^T J)^-1 formed HERE from the problem's own cost
+//  * product build (and the ABI-trace build, where the oracle's covariance entry answers): cslam_covariance_block of the
+//    solved problem.
+//  * oracle build — deliberately NOT through the oracle's covariance entry, as an independent route: (J^T J)^-1 formed HERE from the problem's own cost
 //    functions — the reference's functors differentiated by the AutoDiffCostFunction stand-in, chained with the
 //    SE3Perturbation plus-Jacobian, loss-corrected like Ceres' Corrector does for rho'' <= 0 (scale by sqrt(rho')) — with a
 //    dense Cholesky factorisation; what SPARSE_QR computes for a full-rank Jacobian.
@@ -390,7 +391,7 @@ class Covariance {
 
    private:
     bool block(double* pose, double* out36) {
-#ifndef CSLAM_FACADE_ORACLE
+#if !defined(CSLAM_FACADE_ORACLE) || defined(CSLAM_FACADE_ABI_TRACE)
         return problem_->solved_ && problem_->solved_->GetCovarianceBlockInTangentSpace(pose, out36);
 #else
         Problem& p = *problem_;

@@ -209,7 +209,7 @@ sys.exit(lib.fh_driver_main(len(args), (C.c_char_p * len(args))(*args)))
 def _host_trace_lib(kind):
     from ceres_slam_b200 import capi
     capi.load_product()
-    name = {0: "dataset_vo", 2: "dataset_ba_phong"}[kind]
+    name = {0: "dataset_vo", 1: "dataset_vo_sun", 2: "dataset_ba_phong"}[kind]
     so = os.path.join(ROOT, "tests", "_build", f"libdriver_{name}_trace.so")
     host = os.path.join(ROOT, "ceres_slam_b200", "host")
     srcs = [os.path.join(ROOT, "tests", "frontend_host.cpp"), os.path.join(ROOT, "oracle", "ref_driver", "abi_trace.cpp")]
@@ -297,3 +297,33 @@ def test_vo_driver_abi_stream_equals_reference_driver(tmp_path, window):
     worst, solves = _compare_streams(a, b)
     assert solves == (13 if window == 2 else 1)
     assert worst <= 1e-12, worst
+
+
+def test_sun_driver_abi_stream_equals_reference_driver(tmp_path):
+    """Config 2 the same way, both passes: stereo blocks with per-observation stiffness, sun blocks with their Huber
+    parameter and thresholds, the prior (reference pose and stiffness from the previous window's covariance), DOGLEG
+    options, each solve's result and each covariance block.  The covariance is the oracle's C entry here on both sides
+    (cslam_oracle_covariance_block); the facade's own route — the reference's functors, dense — is checked against it
+    at the end.  The product driver's untimed warm-up (first window on a copy) is dropped."""
+    paths_of = {}
+
+    def write_input(d):
+        tr, paths, _, _ = _sun_case(14, d)
+        paths_of[d.name] = paths
+        return paths
+
+    flags = ("--window", "2", "--huber-param", "1.0")
+    a, b = _abi_streams("dataset_vo_sun", 1, write_input, flags, tmp_path)
+    b = b[[c["call"] for c in b].index("covariance_block") + 1:]
+    worst, solves = _compare_streams(a, b)
+    assert solves == 2 * 13 and sum(c["call"] == "covariance_block" for c in a) == 2 * 13
+    assert worst <= 1e-12, worst
+    # the same driver with the facade's independent covariance (reference functors + autodiff stand-in, dense Cholesky)
+    rows, _ = _run_reference_driver(_lib("oracle", "dataset_vo_sun"), paths_of["ref"], 2, str(tmp_path / "trace.jsonl"),
+                                    "dataset_vo_sun", ["--huber-param", "1.0"])
+    own = [np.array(r["covariance"]) for r in rows if "covariance" in r]
+    abi = [np.array(c["covariance"]) for c in a if c["call"] == "covariance_block"]
+    assert len(own) == len(abi) == 26
+    rel = max(float(np.abs(x - y).max() / np.abs(y).max()) for x, y in zip(own, abi))
+    assert rel <= 1e-9, rel
+    print(f"dataset_vo_sun: {len(a)} C ABI calls, worst stream difference {worst:.3g}; covariance routes agree to {rel:.3g}")
