@@ -427,6 +427,43 @@ def _driver_timing(stderr):
     return out
 
 
+_REF_DRIVER_RUNNER = r"""
+import ctypes as C, sys, time
+lib = C.CDLL(sys.argv[1])
+main = getattr(lib, "cslam_ref_" + sys.argv[2] + "_main")
+main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+args = [sys.argv[2].encode()] + [a.encode() for a in sys.argv[3:]]
+t0 = time.perf_counter()
+rc = main(len(args), (C.c_char_p * len(args))(*args))
+sys.stderr.write("\nreference_driver_wall_s=%.6f\n" % (time.perf_counter() - t0))
+sys.exit(rc)
+"""
+
+
+def reference_driver_baseline(driver, files, flags, cwd):
+    """CPU figure for configs 1 / 2 from the REFERENCE'S OWN driver source (tests/dataset_vo.cpp, tests/dataset_vo_sun.cpp,
+    unmodified) compiled over the Ceres-API facade with the CPU oracle answering ceres::Solve / ceres::Covariance
+    (oracle/_ref/libref_<driver>_oracle.so, prebuilt by `make -C oracle ref`): no Python in the window loop.
+    Wall time of the driver's whole `main` (its CSV reader and writer included; one solve per Report line).  Never
+    raises: a missing library or a failed run is reported as {"unavailable": why}."""
+    try:
+        so = os.path.join(ROOT, "oracle", "_ref", f"libref_{driver}_oracle.so")
+        if not os.path.exists(so):
+            return {"unavailable": f"{os.path.relpath(so, ROOT)} not built (make -C oracle ref needs /root/reference)"}
+        r = subprocess.run([sys.executable, "-c", _REF_DRIVER_RUNNER, so, driver] + list(files) + list(flags), capture_output=True,
+                           text=True, cwd=cwd, timeout=900)
+        if r.returncode != 0:
+            return {"unavailable": "reference driver exited with %d: %s" % (r.returncode, r.stderr[-300:])}
+        wall = float(r.stderr.rsplit("reference_driver_wall_s=", 1)[1].split()[0])
+        its = [int(l.split("Iterations:")[1].split(",")[0]) for l in r.stdout.splitlines() if "Iterations:" in l]
+        return {"value": len(its) / wall, "unit": "windows/s", "cores": 1, "kind": "reference driver + port solver",
+                "windows": len(its), "wall_s": wall, "lm_iters_per_s": sum(its) / wall,
+                "sample": f"the reference's own tests/{driver}.cpp, unmodified, over the Ceres-API facade on the CPU oracle: the whole "
+                          "run of its main on the same files (CSV reader / writer included)"}
+    except Exception as e:  # noqa: BLE001 - a baseline must not take the bench line down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def bench_c1_c2_drivers(cpu=True):
     """BASELINE.json configs 1 and 2 through the restated C++ drivers (host/dataset_vo_b200,
     host/dataset_vo_sun_b200): sequential sliding windows, each = RANSAC initial guess + window solve
@@ -467,6 +504,7 @@ def bench_c1_c2_drivers(cpu=True):
                 res[key]["cpu_baseline"] = {"value": len(its_o) / dt, "unit": "windows/s", "cores": 1, "kind": "port",
                                             "lm_iters_per_s": sum(its_o) / dt,
                                             "sample": "the same track and window loop on the oracle (RANSAC + solve per window)"}
+                res[key]["cpu_reference_driver"] = reference_driver_baseline("dataset_vo", [csv], ["--window", str(window)], tmp)
         out["c1_dataset_vo"] = dict(res, track="100 poses, ~150 landmarks/frame, 14.6 k stereo observations",
                                     note="dataset_vo_b200: window 2 = 99 sequential windows (1 free pose, ~300 blocks each), "
                                          "full batch = one RANSAC launch over 99 pairs + one bundle adjustment; the driver "
@@ -506,6 +544,7 @@ def bench_c1_c2_drivers(cpu=True):
                                    "lm_iters_per_s": sum(its_o) / dt,
                                    "sample": "the sun pass over the first 100 windows of the same track on the oracle (RANSAC + "
                                              "SUBSPACE_DOGLEG solve + sparse-LU covariance per window)"}
+            res["cpu_reference_driver"] = reference_driver_baseline("dataset_vo_sun", paths, ["--window", "2", "--huber-param", "1.0"], tmp)
         out["c2_dataset_vo_sun"] = dict(res, track="1000 poses, ~150 landmarks/frame, per-observation covariances, sun + prior blocks",
                                         note="dataset_vo_sun_b200 --window 2, both passes (VO, then with sun blocks): 2 x 999 sequential "
                                              "windows, each RANSAC + solve + covariance block; dogleg = the reference's SUBSPACE_DOGLEG")
