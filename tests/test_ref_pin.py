@@ -363,3 +363,83 @@ def test_cuda_ransac_matches_reference_source_vectors(product, committed_ransac,
     worst = compare_ransac(rc.evaluate_ransac(product.ransac_align, cam, p0, p1, rng_variant=variant),
                            committed_ransac["expected"])
     print("CUDA RANSAC vs the reference's source: worst |dT|", worst)
+
+
+# ---- minimiser level: the oracle's solve against an independent Gauss-Newton on the reference's own functors ---------
+def _reference_minimiser(ref, tr, poses, points, iters=60):
+    """Damped Gauss-Newton written here in numpy — nothing of oracle/problem.hpp — on residuals and tangent-space
+    Jacobians that come from the REFERENCE'S OWN functors (oracle/_ref, autodiff through the stand-in), with the
+    reference's own SE3 plus as the retraction; first pose constant (dataset_vo.cpp:62).  Runs until the step is at
+    rounding level: the local minimum of the reference's cost function, whatever trust-region rules lead there."""
+    poses, points = poses.copy(), points.copy()
+    n_p, n_l = poses.shape[0], points.shape[0]
+    cam, pt = tr["obs_cam"].astype(np.int64), tr["obs_pt"].astype(np.int64)
+    n_obs = cam.size
+
+    def linearise(P, X):
+        ev = ref_track_blocks(ref, tr, P, X)
+        r = np.concatenate([ev["r_stereo"].reshape(-1), ev["r_sun"].reshape(-1)])
+        J = np.zeros((r.size, 6 * n_p + 3 * n_l))
+        rows = 3 * np.arange(n_obs)
+        for k in range(3):
+            for c in range(6):
+                J[rows + k, 6 * cam + c] = ev["Jpose_stereo"][:, k, c]
+            for c in range(3):
+                J[rows + k, 6 * n_p + 3 * pt + c] = ev["Jpoint_stereo"][:, k, c]
+        for i, kc in enumerate(tr["sun_cam"].astype(np.int64)):
+            J[3 * n_obs + 2 * i:3 * n_obs + 2 * i + 2, 6 * kc:6 * kc + 6] = ev["J_sun"][i]
+        return r, J[:, 6:]                      # the first pose has no columns
+
+    def retract(P, X, dx):
+        Pn, Xn = P.copy(), X + dx[6 * (n_p - 1):].reshape(n_l, 3)
+        for k in range(1, n_p):
+            out = np.zeros(12)
+            ref.se3_plus(d(np.ascontiguousarray(P[k])), d(np.ascontiguousarray(dx[6 * (k - 1):6 * k])), d(out))
+            Pn[k] = out
+        return Pn, Xn
+
+    lam = 1e-4
+    r, J = linearise(poses, points)
+    cost = 0.5 * float(r @ r)
+    for _ in range(iters):
+        H, g = J.T @ J, J.T @ r
+        act = np.diag(H) > 0                    # blocks nothing observes have no columns in Ceres either
+        dx = np.zeros_like(g)
+        Ha = H[np.ix_(act, act)]
+        dx[act] = -np.linalg.solve(Ha + lam * np.diag(np.diag(Ha)), g[act])
+        Pn, Xn = retract(poses, points, dx)
+        rn, Jn = linearise(Pn, Xn)
+        cn = 0.5 * float(rn @ rn)
+        if cn <= cost:
+            poses, points, r, J, cost, lam = Pn, Xn, rn, Jn, cn, max(lam * 0.1, 1e-12)
+            if np.abs(dx).max() < 1e-13:
+                break
+        else:
+            lam *= 10.0
+    return poses, points, cost, float(np.abs(J.T @ r).max())
+
+
+@needs_ref
+def test_oracle_solve_reaches_the_minimum_of_the_reference_cost(ref):
+    """What the restated Ceres rules cannot be pinned against (Ceres is absent) is pinned at the level of the ANSWER:
+    the oracle's Levenberg-Marquardt and DOGLEG solves, run to tight tolerances, end at the minimiser an independent
+    Gauss-Newton finds on the reference's own residuals and autodiff Jacobians — same cost to 1e-10, same poses and
+    points to 1e-7.  (The GPU solves are compared with the oracle's trajectory elsewhere.)"""
+    from test_gpu_parity import _steady_track     # every state observes points, so the constant first pose fixes the gauge
+    tr = syn.add_sun(_steady_track(12, seed=77), sigma_deg=1.0)
+    tight = dict(max_num_iterations=200, function_tolerance=1e-15, parameter_tolerance=1e-15, gradient_tolerance=1e-15)
+    p0, poses0, points0 = orc.build_problem(tr, sun=True, **tight)
+    start_poses, start_points = poses0.copy(), points0.copy()
+    s = p0.solve()
+    Pm, Xm, cost_m, grad_m = _reference_minimiser(ref, tr, start_poses, start_points)
+    assert grad_m < 1e-6 * max(1.0, cost_m)
+    assert abs(s.final_cost - cost_m) <= 1e-10 * cost_m, (s.final_cost, cost_m)
+    assert np.abs(poses0 - Pm).max() <= 1e-7 and np.abs(points0 - Xm).max() <= 1e-7
+    p0.close()
+    for dogleg_type in (0, 1):
+        p1, poses1, points1 = orc.build_problem(tr, sun=True, trust_region_strategy=1, dogleg_type=dogleg_type, **tight)
+        s1 = p1.solve()
+        assert abs(s1.final_cost - cost_m) <= 1e-10 * cost_m, (dogleg_type, s1.final_cost, cost_m)
+        assert np.abs(poses1 - Pm).max() <= 1e-7 and np.abs(points1 - Xm).max() <= 1e-7
+        p1.close()
+    print(f"minimum of the reference's cost {cost_m:.9g} (gradient {grad_m:.2g}); oracle LM {s.final_cost:.9g} in {s.num_iterations} iterations")
