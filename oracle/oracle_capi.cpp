@@ -207,15 +207,25 @@ int cslam_oracle_covariance_block(cslam_oracle_problem* p, uint32_t cam, double*
         p->err = "evaluation failed";
         return CSLAM_ERR_NUMERIC;
     }
+    // columns only for parameter blocks some residual block touches (others are not part of a ceres::Problem)
     const size_t nc = q.pose_const.size();
+    std::vector<char> pose_used(nc, 0);
+    for (uint32_t c : q.st_cam) pose_used[c] = 1;
+    for (const auto& sb : q.suns) pose_used[sb.cam] = 1;
+    for (const auto& pb : q.priors) pose_used[pb.cam] = 1;
     std::vector<long> pcol(nc, -1);
     long n = 0;
     for (size_t k = 0; k < nc; ++k)
-        if (!q.pose_const[k]) pcol[k] = n, n += 6;
+        if (!q.pose_const[k] && pose_used[k]) pcol[k] = n, n += 6;
+    if (pcol[cam] < 0) {
+        p->err = "covariance of a pose no residual block touches";
+        return CSLAM_ERR_INVALID;
+    }
     uint32_t n_pts = 0;
     for (uint32_t j : q.st_pt) n_pts = std::max(n_pts, j + 1);
-    const long x0 = n;
-    n += 3 * long(n_pts);
+    std::vector<long> xcol(n_pts, -1);
+    for (uint32_t j : q.st_pt)
+        if (xcol[j] < 0) xcol[j] = n, n += 3;
     std::vector<double> H(size_t(n) * size_t(n), 0.0);
     // H += A^T B for an m-row block pair with column offsets ca, cb and widths wa, wb (row-major inputs)
     auto acc = [&](const double* A, long ca, int wa, const double* B, long cb, int wb, int m) {
@@ -228,7 +238,7 @@ int cslam_oracle_covariance_block(cslam_oracle_problem* p, uint32_t cam, double*
     };
     for (size_t i = 0; i < q.n_stereo(); ++i) {
         const double *Jc = &ev.Jc_st[18 * i], *Jp = &ev.Jp_st[9 * i];
-        const long cc = pcol[q.st_cam[i]], cp = x0 + 3 * long(q.st_pt[i]);
+        const long cc = pcol[q.st_cam[i]], cp = xcol[q.st_pt[i]];
         if (cc >= 0) {
             acc(Jc, cc, 6, Jc, cc, 6, 3);
             acc(Jc, cc, 6, Jp, cp, 3, 3);

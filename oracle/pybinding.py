@@ -27,6 +27,7 @@ _ORACLE_ONLY = {
     "poly_root_real_parts": (C.c_int, [_dp, C.c_int, _dp]),
     "dogleg_boundary_minimum": (C.c_int, [_dp, _dp, C.c_double, _dp]),
     "ransac_draws": (None, [C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p]),
+    "covariance_block": (C.c_int, [capi._h, C.c_uint32, _dp]),   # same contract as cslam_covariance_block
     "kabsch": (None, [C.c_uint32, _dp, _dp, _dp]),
     "so3_exp": (None, [_dp, _dp]),
     "so3_log": (None, [_dp, _dp]),

@@ -416,7 +416,11 @@ def _reference_minimiser(ref, tr, poses, points, iters=60):
                 break
         else:
             lam *= 10.0
-    return poses, points, cost, float(np.abs(J.T @ r).max())
+    H = J.T @ J
+    act = np.diag(H) > 0
+    cov = np.zeros_like(H)
+    cov[np.ix_(act, act)] = np.linalg.inv(H[np.ix_(act, act)])
+    return poses, points, cost, float(np.abs(J.T @ r).max()), cov      # cov: (J^T J)^-1 over [poses 1.. | points]
 
 
 @needs_ref
@@ -431,10 +435,15 @@ def test_oracle_solve_reaches_the_minimum_of_the_reference_cost(ref):
     p0, poses0, points0 = orc.build_problem(tr, sun=True, **tight)
     start_poses, start_points = poses0.copy(), points0.copy()
     s = p0.solve()
-    Pm, Xm, cost_m, grad_m = _reference_minimiser(ref, tr, start_poses, start_points)
+    Pm, Xm, cost_m, grad_m, cov_m = _reference_minimiser(ref, tr, start_poses, start_points)
     assert grad_m < 1e-6 * max(1.0, cost_m)
     assert abs(s.final_cost - cost_m) <= 1e-10 * cost_m, (s.final_cost, cost_m)
     assert np.abs(poses0 - Pm).max() <= 1e-7 and np.abs(points0 - Xm).max() <= 1e-7
+    # ceres::Covariance at the solution (dataset_vo_sun.cpp:159-183): the oracle's entry against (J^T J)^-1 of the
+    # reference functors' Jacobians, pose by pose
+    for k in (1, 5, tr["n_poses"] - 1):
+        ck = cov_m[6 * (k - 1):6 * k, 6 * (k - 1):6 * k]
+        assert np.abs(p0.covariance_block(k) - ck).max() <= 1e-6 * np.abs(ck).max(), k
     p0.close()
     for dogleg_type in (0, 1):
         p1, poses1, points1 = orc.build_problem(tr, sun=True, trust_region_strategy=1, dogleg_type=dogleg_type, **tight)
